@@ -1,0 +1,104 @@
+"""ctypes binding of libunopose_b200.so (the C ABI declared in include/unopose_b200.h).
+
+There is NO fallback: if the shared library is missing or a symbol cannot be
+resolved, importing/calling raises.  The product path never routes through the
+CPU oracle or through plain torch ops.
+"""
+import ctypes
+import os
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "lib", "libunopose_b200.so")
+
+_lib = None
+
+c_f = ctypes.c_void_p  # device pointers are passed as raw addresses
+c_i = ctypes.c_int
+c_fl = ctypes.c_float
+c_st = ctypes.c_void_p
+
+# name -> argtypes (restype is always int unless noted)
+_SIGNATURES = {
+    "upk_abi_version": [],
+    "upk_built_sm": [],
+    "upk_furthest_point_sampling": [c_f, c_i, c_i, c_i, c_f, c_st],
+    "upk_gather_points": [c_f, c_f, c_i, c_i, c_i, c_i, c_f, c_st],
+    "upk_gather_points_grad": [c_f, c_f, c_i, c_i, c_i, c_i, c_f, c_st],
+    "upk_ball_query": [c_f, c_f, c_i, c_i, c_i, c_fl, c_i, c_f, c_st],
+    "upk_group_points": [c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_f, c_st],
+    "upk_group_points_grad": [c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_f, c_st],
+    "upk_three_nn": [c_f, c_f, c_i, c_i, c_i, c_f, c_f, c_st],
+    "upk_three_interpolate": [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_f, c_st],
+    "upk_three_interpolate_grad": [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_f, c_st],
+}
+
+
+class UnoposeNativeError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise UnoposeNativeError(
+            "libunopose_b200.so not found at %s — build it with `python -m unopose_b200.build` "
+            "(there is no CPU/torch fallback)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.argtypes = argtypes
+        fn.restype = ctypes.c_int
+    lib.upk_launch_count.argtypes = []
+    lib.upk_launch_count.restype = ctypes.c_ulonglong
+    _lib = lib
+    return lib
+
+
+def exported_symbols():
+    return sorted(list(_SIGNATURES) + ["upk_launch_count"])
+
+
+def launch_count():
+    return int(load().upk_launch_count())
+
+
+def check(rc, what):
+    if rc == 0:
+        return
+    if rc < 0:
+        raise UnoposeNativeError("%s: invalid/unsupported arguments (code %d)" % (what, rc))
+    raise UnoposeNativeError("%s: CUDA error %d" % (what, rc))
+
+
+def stream_ptr(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def ptr(t):
+    return t.data_ptr() if t is not None else None
+
+
+# --- argument checks with the reference's error text (_ext_src/include/utils.h:10-30) ---
+def check_cuda(x, name):
+    if not x.is_cuda:
+        raise RuntimeError("CPU not supported")  # sampling.cpp:39,65,87
+
+
+def check_contiguous(x, name):
+    if not x.is_contiguous():
+        raise RuntimeError("%s must be a contiguous tensor" % name)
+
+
+def check_float(x, name):
+    if x.dtype != torch.float32:
+        raise RuntimeError("%s must be a float tensor" % name)
+
+
+def check_int(x, name):
+    if x.dtype != torch.int32:
+        raise RuntimeError("%s must be an int tensor" % name)

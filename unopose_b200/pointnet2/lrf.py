@@ -1,0 +1,44 @@
+"""Per-centre local reference frames (host-side torch code; "next" row f1 of SURVEY.md §8).
+
+``LRF_batch`` follows the maths of the reference class of the same name
+(core/unopose/model/pointnet2/pointnet2_utils.py:429-481): z axis = covariance
+eigenvector of the smallest eigenvalue with majority-vote sign, x axis =
+distance/height-weighted projection, y = x × z; neighbours are expressed in
+that frame, scaled by 1/r.
+"""
+import torch
+import torch.nn as nn
+
+
+class LRF_batch(nn.Module):
+    def __init__(self, eps=1e-10, r_lrf=0.1):
+        super().__init__()
+        self.eps = eps
+        self.r_lrf = r_lrf
+
+    def forward(self, xyz, xyz_group):
+        """xyz (B,N,3) centres, xyz_group (B,N,3,M) neighbours -> (B,N,3,M)."""
+        B, N, _, M = xyz_group.shape
+        centre = xyz.unsqueeze(3)
+        to_centre = centre - xyz_group  # p - p_i, (B,N,3,M)
+        cov = torch.einsum("bnim,bnjm->bnij", to_centre, to_centre) / M
+        _, _, v = torch.svd(cov)
+        z_raw = v[..., -1]  # (B,N,3) direction of least variance
+        with torch.no_grad():
+            h = torch.einsum("bni,bnim->bnm", z_raw, to_centre)
+            vote = (h > 1e-3).sum(-1) - (h < -1e-3).sum(-1)
+            sign = 1.0 - 2.0 * (vote < 0).to(xyz_group.dtype)
+        zp = sign.unsqueeze(-1) * z_raw  # (B,N,3)
+
+        rel = -to_centre  # p_i - p
+        height = torch.einsum("bni,bnim->bnm", zp, rel)  # (B,N,M)
+        in_plane = rel - height.unsqueeze(2) * zp.unsqueeze(3)
+        dist = torch.sqrt((rel ** 2).sum(dim=2))  # (B,N,M)
+        alpha = (self.r_lrf - dist) ** 2
+        beta = height * height
+        x_dir = ((alpha * beta).unsqueeze(2) * in_plane).sum(3)  # (B,N,3)
+        xp = x_dir / (torch.sqrt((x_dir ** 2).sum(2, keepdim=True)) + self.eps)
+        yp = torch.cross(xp, zp, dim=2)
+        frame = torch.stack((xp, yp, zp), dim=3)  # columns x,y,z  (B,N,3,3)
+        local = (xyz_group - centre) / self.r_lrf
+        return torch.einsum("bnij,bnim->bnjm", frame, local)
