@@ -15,16 +15,17 @@
  * against the fixtures under tests/golden/ that were produced by it.
  *
  * Arithmetic: the reference is compiled with nvcc's default -fmad=true, which
- * contracts  a*a + b*b + c*c  into  fma(c,c, fma(b,b, a*a))  (SASS-verified,
- * SURVEY.md Appendix A.1).  Build this file with -ffp-contract=off; the fused
- * operations are spelled out with fmaf().
+ * contracts  a*a + b*b + c*c  into  fma(c,c, fma(a,a, b*b))  (read off the SASS of
+ * the reference extension compiled for sm_100a: FMUL on the y term, FFMA x,
+ * FFMA z; SURVEY.md Appendix A.1 has x and y swapped).  Build this file with
+ * -ffp-contract=off; the fused operations are spelled out with fmaf().
  */
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
 static inline float sqdist(float dx, float dy, float dz) {
-  return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+  return fmaf(dz, dz, fmaf(dx, dx, dy * dy));
 }
 
 /* cuda_utils.h:20-24  opt_n_threads */
@@ -201,7 +202,7 @@ void oracle_three_interpolate(const float* points, const int* idx, const float* 
         const float* w = weight + ((size_t)bi * n + j) * 3;
         const float* p = points + ((size_t)bi * c + l) * m;
         out[((size_t)bi * c + l) * n + j] =
-            fmaf(p[ix[2]], w[2], fmaf(p[ix[1]], w[1], p[ix[0]] * w[0]));
+            fmaf(p[ix[2]], w[2], fmaf(p[ix[0]], w[0], p[ix[1]] * w[1]));
       }
 }
 

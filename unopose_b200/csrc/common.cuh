@@ -31,9 +31,13 @@ __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; 
 
 // Squared distance with the exact rounding sequence the reference's nvcc build
 // produces (default -fmad=true contraction of dx*dx + dy*dy + dz*dz):
-//   fma(dz, dz, fma(dy, dy, dx*dx))          
+//   fma(dz, dz, fma(dx, dx, dy*dy))
+// read off the SASS of the reference extension compiled unmodified for sm_100a
+// (FMUL on the y difference, then FFMA x, then FFMA z — identical in
+// sampling_gpu.cu, ball_query_gpu.cu and interpolate_gpu.cu).  SURVEY.md
+// Appendix A.1 states the x/y roles the other way round; the SASS wins.
 __device__ __forceinline__ float sqdist_ref(float dx, float dy, float dz) {
-  return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+  return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -400,9 +400,9 @@ three_interpolate_kernel(const float* __restrict__ points, const int* __restrict
   const float* p = points + ((size_t)b * c + l) * m;
   const int* ix = idx + ((size_t)b * n + j) * 3;
   const float* w = weight + ((size_t)b * n + j) * 3;
-  // interpolate_gpu.cu:103-104 under -fmad=true: fma(p3,w3, fma(p2,w2, p1*w1))
+  // interpolate_gpu.cu:103-104 under -fmad=true (reference SASS): fma(p3,w3, fma(p1,w1, p2*w2))
   float v = __fmaf_rn(__ldg(p + ix[2]), w[2],
-                      __fmaf_rn(__ldg(p + ix[1]), w[1], __fmul_rn(__ldg(p + ix[0]), w[0])));
+                      __fmaf_rn(__ldg(p + ix[0]), w[0], __fmul_rn(__ldg(p + ix[1]), w[1])));
   out[((size_t)b * c + l) * n + j] = v;
 }
 
@@ -438,9 +438,10 @@ int upk_furthest_point_sampling(const float* xyz, int b, int n, int m, int* idx_
   int bs_log2 = 0;
   while ((2 << bs_log2) <= n && bs_log2 < 9) ++bs_log2;
   if (((long long)n >> bs_log2) >= (1 << 20)) return UPK_ERR_UNSUPPORTED;
+  // THREADS must be a multiple of the reference block size BS = 2^bs_log2 (see fps_kernel)
   if (n <= 128) return launch_fps<128, 1>(xyz, b, n, m, bs_log2, idx_out, st);
-  if (n <= 256) return launch_fps<128, 2>(xyz, b, n, m, bs_log2, idx_out, st);
-  if (n <= 512) return launch_fps<256, 2>(xyz, b, n, m, bs_log2, idx_out, st);
+  if (n < 256) return launch_fps<128, 2>(xyz, b, n, m, bs_log2, idx_out, st);
+  if (n < 512) return launch_fps<256, 2>(xyz, b, n, m, bs_log2, idx_out, st);
   if (n <= 1024) return launch_fps<512, 2>(xyz, b, n, m, bs_log2, idx_out, st);
   if (n <= 2048) return launch_fps<512, 4>(xyz, b, n, m, bs_log2, idx_out, st);
   if (n <= 3072) return launch_fps<1024, 3>(xyz, b, n, m, bs_log2, idx_out, st);
