@@ -23,6 +23,8 @@
 #ifndef UNOPOSE_B200_H
 #define UNOPOSE_B200_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -97,6 +99,113 @@ int upk_three_interpolate(const float* points, const int* idx, const float* weig
 int upk_three_interpolate_grad(const float* grad_out, const int* idx,
                                const float* weight, int b, int c, int n, int m,
                                float* grad_points, upk_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
+ * (1) feature similarity — compute_feature_similarity, model_utils.py:260-282
+ * ------------------------------------------------------------------------- */
+
+/* feat1[b,n,c], feat2[b,m,c] -> atten[b,n,m].
+ * normalize != 0: rows L2-normalised first (F.normalize, eps 1e-12) — needs the
+ * workspace (two normalised copies).  sim_type 0 = "cosine": f1.f2^T / temp;
+ * 1 = "L2": sqrt(clamp(2 - 2 f1.f2^T, 0)) / temp. */
+size_t upk_feature_similarity_workspace_bytes(int b, int n, int m, int c, int normalize);
+int upk_feature_similarity(const float* feat1, const float* feat2, int b, int n, int m,
+                           int c, float temp, int normalize, int sim_type,
+                           void* workspace, size_t workspace_bytes, float* atten_out,
+                           upk_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
+ * (2)(3)(4) coarse pose — compute_coarse_Rt[_overlap], model_utils.py:336-490
+ * ------------------------------------------------------------------------- */
+
+/* Optional device buffers receiving the intermediates (any member may be NULL;
+ * pass dbg == NULL for none).  Used by the stage-wise parity tests. */
+typedef struct upk_coarse_debug {
+  float* w1;     /* [b,n1]   foreground mask of the query points (label1 > 0)   */
+  float* w2;     /* [b,n2]                                                       */
+  float* cdf;    /* [b,n1*n2] normalised sampling CDF                            */
+  int* idx1;     /* [b,n_hyp,3] sampled query indices  (both or neither)         */
+  int* idx2;     /* [b,n_hyp,3] sampled reference indices                        */
+  float* Rs;     /* [b,n_hyp,9] */
+  float* ts;     /* [b,n_hyp,3] */
+  float* resid;  /* [b,n_hyp]   mean triplet residual                            */
+  int* top;      /* [b,n_keep]  pool indices of the n_keep smallest residuals, ascending index */
+  float* scores; /* [b,n_keep]  */
+} upk_coarse_debug;
+
+/* atten[b,n1+1,n2+1] (background token at row/col 0); score1[b,n1] / score2[b,n2]
+ * with row strides score*_ld (both NULL => compute_coarse_Rt, no overlap scores);
+ * pts1[b,n1,3] query, pts2[b,n2,3] reference, model_pts[b,n_model,3] or NULL (= pts2);
+ * u[b,3*n_hyp] uniform draws in [0,1) (the reference's torch.rand, :462 — drawn by
+ * the HOST so the Philox stream position is unchanged).
+ * Outputs R[b,9] row-major, t[b,3], score[b], pool_idx[b] (index in [0,n_hyp) of the
+ * selected hypothesis; may be NULL).  Pose convention: p_ref ~= (p_query - t) @ R. */
+size_t upk_coarse_pose_workspace_bytes(int b, int n1, int n2, int n_hyp, int n_keep);
+int upk_coarse_pose(const float* atten, const float* score1, int score1_ld,
+                    const float* score2, int score2_ld, const float* pts1,
+                    const float* pts2, const float* model_pts, int n_model,
+                    const float* u, int b, int n1, int n2, int n_hyp, int n_keep,
+                    void* workspace, size_t workspace_bytes, float* R_out, float* t_out,
+                    float* score_out, int* pool_idx_out, const upk_coarse_debug* dbg,
+                    upk_stream_t stream);
+
+/* Stage-wise entry points (same kernels; used for identical-input parity tests
+ * and for hypothesis sharding across GPUs). */
+
+/* searchsorted(cdf,u) -> triplets -> Kabsch -> residual for hypotheses
+ * [h_begin,h_end) of every instance (model_utils.py:462-475). Rs/ts/resid are
+ * indexed by the global hypothesis index ([b,n_hyp,...]). */
+int upk_sample_hypotheses(const float* cdf, const float* u, const float* pts1,
+                          const float* pts2, int b, int n1, int n2, int n_hyp,
+                          int h_begin, int h_end, int* idx1_out, int* idx2_out,
+                          float* Rs, float* ts, float* resid, upk_stream_t stream);
+/* Kabsch on n explicit triplets: p1[n,3,3] (query), p2[n,3,3] (reference)
+ * == WeightedProcrustes()(p2, p1, None), model_utils.py:469. resid may be NULL. */
+int upk_kabsch_triplets(const float* p1, const float* p2, int n, float* Rs, float* ts,
+                        float* resid, upk_stream_t stream);
+/* indices of the k smallest of vals[b,n], ascending index order (torch.topk largest=False, :476) */
+int upk_topk_smallest(const float* vals, int b, int n, int k, int* idx_out,
+                      upk_stream_t stream);
+/* scores[b,n_keep] for kept hypotheses [k_begin,k_end) (model_utils.py:481-485);
+ * top == NULL means hypothesis k is pool index k. */
+int upk_score_hypotheses(const float* pts1, const float* model_pts, const float* w1,
+                         const float* Rs, const float* ts, const int* top, int b, int n1,
+                         int n_model, int n_hyp, int n_keep, int k_begin, int k_end,
+                         float* scores, upk_stream_t stream);
+/* first arg-max over scores[b,n_keep] and gather (model_utils.py:486-488) */
+int upk_select_best(const float* scores, const int* top, const float* Rs, const float* ts,
+                    int b, int n_hyp, int n_keep, float* R_out, float* t_out,
+                    float* score_out, int* pool_idx_out, upk_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
+ * fine pose — compute_fine_Rt[_overlap], model_utils.py:493-566
+ * ------------------------------------------------------------------------- */
+typedef struct upk_fine_debug {
+  float* w1;   /* [b,n1] */
+  float* w2;   /* [b,n2] */
+  float* soft; /* [b,n1,3] soft correspondences (assignment-weighted reference points) */
+  float* asum; /* [b,n1]   row sums of the masked assignment (Procrustes weights)       */
+  float* nn;   /* [b,n1]   nearest-neighbour distance of each transformed query point   */
+} upk_fine_debug;
+
+/* weight_thresh: 0.001 for the _overlap variant (:528), 0.0 for compute_fine_Rt (:502). */
+size_t upk_fine_pose_workspace_bytes(int b, int n1, int n2);
+int upk_fine_pose(const float* atten, const float* score1, int score1_ld,
+                  const float* score2, int score2_ld, const float* pts1, const float* pts2,
+                  const float* model_pts, int n_model, int b, int n1, int n2,
+                  float dis_thres, float weight_thresh, void* workspace,
+                  size_t workspace_bytes, float* R_out, float* t_out, float* score_out,
+                  const upk_fine_debug* dbg, upk_stream_t stream);
+
+/* weighted_procrustes(src[b,n,3], ref[b,n,3], weights[b,n] or NULL, thresh, eps)
+ * -> R[b,9], t[b,3] with ref ~= R src + t  (model_utils.py:667-743). */
+int upk_weighted_procrustes(const float* src, const float* ref, const float* weights, int b,
+                            int n, float weight_thresh, float eps, float* R_out,
+                            float* t_out, upk_stream_t stream);
+
+/* HOST function (no GPU): the 3x3 Procrustes rotation solver of kernel family (3),
+ * compiled from the same source as the device code.  H[n,9] row-major -> R[n,9]. */
+int upk_host_procrustes_rotation(const double* H, int n, double* R_out);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,270 @@
+"""GPU parity tests of the pose kernels (families (1)-(4)), through the C ABI, against the oracle
+(oracle/pose_oracle.py run on the same device = the reference's GPU torch path) and the golden
+vectors generated from the reference itself.
+
+Bars (BASELINE.json north_star): masks / sampled indices / top-K set / selected index bit-exact
+GIVEN IDENTICAL STAGE INPUTS; R <= 1e-3 deg geodesic; t <= 1e-5 relative.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pose_oracle as PO
+from util_clouds import matching_batch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+ROT_TOL_DEG = 1e-3
+T_TOL_REL = 1e-5
+
+
+def MU():
+    from unopose_b200 import model_utils
+
+    return model_utils
+
+
+def batch(seed, b, n, c, dev):
+    d = matching_batch(seed, b, n, c)
+    return {k: torch.from_numpy(v).to(dev) for k, v in d.items() if k in ("pts1", "pts2", "f1", "f2", "score", "R", "t")}
+
+
+# ------------------------------------------------------------------ (1) similarity
+@pytest.mark.parametrize("n,m,c", [(197, 197, 256), (2049, 2049, 256), (50, 77, 33), (130, 129, 256)])
+def test_similarity_matches_oracle(cuda, n, m, c):
+    g = torch.Generator(device="cpu").manual_seed(n + m)
+    f1 = torch.randn(2, n, c, generator=g).to(cuda)
+    f2 = torch.randn(2, m, c, generator=g).to(cuda)
+    for kind in ("cosine", "L2"):
+        mine = MU().compute_feature_similarity(f1, f2, kind, 0.1, True)
+        ref = PO.feature_similarity(f1, f2, kind, 0.1, True)
+        # logits are O(10); fp32 accumulation-order noise only.  L2 takes a sqrt near 0 -> looser
+        assert torch.allclose(mine, ref, atol=2e-5 if kind == "cosine" else 2e-3, rtol=1e-5)
+    mine = MU().compute_feature_similarity(f1, f2, "cosine", 1.0, False)
+    assert torch.allclose(mine, f1 @ f2.transpose(1, 2), atol=1e-3, rtol=1e-5)
+
+
+# ------------------------------------------------------------------ coarse, stage-wise
+@pytest.mark.parametrize("seed,n,H,K", [(0, 196, 5000, 300), (1, 196, 6000, 300), (2, 64, 500, 50), (3, 100, 1000, 1000)])
+def test_coarse_stagewise(cuda, seed, n, H, K):
+    B = 3
+    d = batch(seed, B, n, 128, cuda)
+    atten = PO.feature_similarity(d["f1"], d["f2"], "cosine", 0.1, True)
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    u = torch.rand(B, 3 * H, generator=g).to(cuda)
+    R, t, s, m = MU()._coarse(atten, d["score"], d["pts1"], d["pts2"], None, H, K, u=u, return_debug=True)
+    Ro, to, so, o = PO.coarse_pose(atten, d["score"], d["pts1"], d["pts2"], None, H, K, u=u, debug=True)
+    # a2: masks bit-exact
+    assert torch.equal(m["w1"], o["w1"]) and torch.equal(m["w2"], o["w2"])
+    # a3: CDF close (fp64 scan vs torch's fp32 tree scan), monotone, ends at ~1
+    assert torch.allclose(m["cdf"], o["cdf"], rtol=2e-5, atol=1e-7)
+    assert (m["cdf"][:, 1:] >= m["cdf"][:, :-1]).all()
+    # a3: searchsorted + split + clamp — bit-exact given the SAME cdf and u
+    i1, i2 = PO.sample_correspondences(m["cdf"], u, n, n)
+    assert torch.equal(m["idx1"].reshape(B, -1).long(), i1) and torch.equal(m["idx2"].reshape(B, -1).long(), i2)
+    # a4: Kabsch on the SAME triplets vs torch.svd path
+    p1 = torch.gather(d["pts1"], 1, i1.unsqueeze(2).repeat(1, 1, 3)).reshape(B * H, 3, 3)
+    p2 = torch.gather(d["pts2"], 1, i2.unsqueeze(2).repeat(1, 1, 3)).reshape(B * H, 3, 3)
+    Rr, tr = PO.weighted_procrustes(p2, p1, None, weight_thresh=0.5)
+    # conditioning of each triplet: second singular value of the centred reference triangle
+    sv = torch.linalg.svdvals((p2 - p2.mean(1, keepdim=True)).double())
+    good = sv[:, 1] > 5e-2 * sv[:, 0].clamp_min(1e-12)
+    ang = PO.rotation_geodesic_deg(m["Rs"].reshape(-1, 3, 3), Rr)
+    assert good.float().mean() > 0.5
+    assert ang[good].max() <= ROT_TOL_DEG
+    terr = (m["ts"].reshape(-1, 3) - tr).norm(dim=1)
+    assert terr[good].max() <= 2e-5          # absolute, points are O(1); cuSOLVER fp32 noise dominates
+    assert torch.isfinite(m["Rs"]).all() and torch.isfinite(m["ts"]).all() and torch.isfinite(m["resid"]).all()
+    det = torch.det(m["Rs"].reshape(-1, 3, 3).double())
+    assert (det - 1).abs().max() < 1e-5
+    # a5: residual formula on MY R,t ; top-K set bit-exact given MY residuals
+    p1b, p2b = p1.reshape(B, H, 3, 3), p2.reshape(B, H, 3, 3)
+    resid = torch.norm((p1b - m["ts"].unsqueeze(2)) @ m["Rs"] - p2b, dim=3).mean(2)
+    assert torch.allclose(m["resid"], resid, rtol=1e-4, atol=2e-6)
+    top_ref = torch.topk(m["resid"], K, dim=1, largest=False)[1]
+    kth = torch.gather(m["resid"], 1, top_ref).max(1)[0]
+    for b in range(B):
+        mine_set = set(m["top"][b].tolist())
+        assert len(mine_set) == K
+        strictly = set(torch.nonzero(m["resid"][b] < kth[b]).flatten().tolist())
+        assert strictly <= mine_set                                    # everything below the K-th value
+        assert (m["resid"][b, m["top"][b].long()] <= kth[b]).all()     # nothing above it
+        assert (m["top"][b, 1:] > m["top"][b, :-1]).all()              # ascending pool index
+    # a6: scores given MY kept hypotheses
+    top = m["top"].long()
+    Rk = torch.gather(m["Rs"], 1, top.reshape(B, K, 1, 1).repeat(1, 1, 3, 3))
+    tk = torch.gather(m["ts"], 1, top.reshape(B, K, 1).repeat(1, 1, 3)).unsqueeze(2)
+    X = ((d["pts1"].unsqueeze(1) - tk) @ Rk).reshape(B * K, -1, 3)
+    M = d["pts2"].unsqueeze(1).repeat(1, K, 1, 1).reshape(B * K, -1, 3)
+    nn = torch.sqrt(PO.pairwise_sqdist(X, M)).min(2)[0].reshape(B, K, -1)
+    sc = m["w1"].unsqueeze(1).sum(2) / ((nn * m["w1"].unsqueeze(1)).sum(2) + 1e-8)
+    assert torch.allclose(m["scores"], sc, rtol=2e-4)
+    # a6: selection bit-exact given MY scores
+    best = m["scores"].max(1)[1]
+    assert torch.equal(m["pool"].long(), torch.gather(top, 1, best.unsqueeze(1)).squeeze(1))
+    assert torch.equal(R, torch.gather(Rk, 1, best.reshape(B, 1, 1, 1).repeat(1, 1, 3, 3)).squeeze(1))
+    assert torch.equal(s, m["scores"].max(1)[0])
+
+
+def test_coarse_end_to_end_vs_oracle(cuda):
+    """Whole solver vs the oracle on the same device with the same draws: the selected pool index
+    must agree (bit-exact) in the overwhelming majority of instances, and R/t must then meet the
+    tolerance.  A disagreement is only tolerated when the two winners score within 1e-4 relative
+    (float noise deciding between near-identical hypotheses)."""
+    n, H, K, B = 196, 5000, 300, 4
+    agree = total = 0
+    for seed in range(5):
+        d = batch(100 + seed, B, n, 256, cuda)
+        atten = PO.feature_similarity(d["f1"], d["f2"], "cosine", 0.1, True)
+        u = torch.rand(B, 3 * H, generator=torch.Generator().manual_seed(seed)).to(cuda)
+        R, t, s, m = MU()._coarse(atten, d["score"], d["pts1"], d["pts2"], None, H, K, u=u, return_debug=True)
+        Ro, to, so, o = PO.coarse_pose(atten, d["score"], d["pts1"], d["pts2"], None, H, K, u=u, debug=True)
+        for b in range(B):
+            total += 1
+            if int(m["pool"][b]) == int(o["pool"][b]):
+                agree += 1
+                assert PO.rotation_geodesic_deg(R[b], Ro[b]) <= ROT_TOL_DEG
+                assert PO.relative_translation_error(t[b], to[b]) <= T_TOL_REL
+                assert abs(float(s[b]) - float(so[b])) <= 2e-4 * abs(float(so[b]))
+            else:
+                assert abs(float(s[b]) - float(so[b])) <= 1e-4 * abs(float(so[b]))
+    assert agree >= 0.9 * total, (agree, total)
+
+
+def test_coarse_api_rng_and_variants(cuda):
+    n, H, K, B = 196, 2000, 100, 2
+    d = batch(7, B, n, 64, cuda)
+    atten = MU().compute_feature_similarity(d["f1"], d["f2"], "cosine", 0.1, True)
+    torch.manual_seed(123)
+    R, t, s = MU().compute_coarse_Rt_overlap(atten, d["score"], d["pts1"], d["pts2"], None, H, K)
+    after = torch.rand(1, device=cuda)
+    torch.manual_seed(123)
+    Ro, to, so = PO.coarse_pose(atten, d["score"], d["pts1"], d["pts2"], None, H, K)
+    after_o = torch.rand(1, device=cuda)
+    assert torch.equal(after, after_o)           # same Philox consumption as the reference path
+    assert PO.rotation_geodesic_deg(R, Ro).max() <= ROT_TOL_DEG or torch.allclose(s, so, rtol=1e-4)
+    torch.manual_seed(5)
+    R0, t0, s0 = MU().compute_coarse_Rt(atten, d["pts1"], d["pts2"], None, H, K)
+    torch.manual_seed(5)
+    R0o, t0o, s0o = PO.coarse_pose(atten, None, d["pts1"], d["pts2"], None, H, K)
+    assert torch.allclose(s0, s0o, rtol=1e-4)
+    # planted transform recovered: p_query = R p_ref + t
+    assert PO.rotation_geodesic_deg(R, d["R"]).max() < 5.0
+    # determinism: same draws -> bitwise identical outputs
+    torch.manual_seed(123)
+    R2, t2, s2 = MU().compute_coarse_Rt_overlap(atten, d["score"], d["pts1"], d["pts2"], None, H, K)
+    assert torch.equal(R, R2) and torch.equal(t, t2) and torch.equal(s, s2)
+
+
+def test_coarse_degenerate_all_background(cuda):
+    """Background token dominates every row: all masks zero, CDF all zero, every draw overflows
+    and is clamped to (N1-1, 0) exactly like the reference (:463-465)."""
+    n, H, K, B = 64, 200, 20, 2
+    d = batch(9, B, n, 32, cuda)
+    atten = torch.randn(B, n + 1, n + 1, device=cuda)
+    atten[:, :, 0] += 30.0
+    u = torch.rand(B, 3 * H, device=cuda)
+    R, t, s, m = MU()._coarse(atten, d["score"], d["pts1"], d["pts2"], None, H, K, u=u, return_debug=True)
+    Ro, to, so, o = PO.coarse_pose(atten, d["score"], d["pts1"], d["pts2"], None, H, K, u=u, debug=True)
+    assert torch.equal(m["w1"], o["w1"]) and m["w1"].sum() == 0
+    assert torch.equal(m["idx1"].reshape(B, -1).long(), o["idx1"]) and torch.equal(m["idx2"].reshape(B, -1).long(), o["idx2"])
+    assert torch.isfinite(R).all() and torch.isfinite(t).all()
+
+
+# ------------------------------------------------------------------ fine
+@pytest.mark.parametrize("seed,n,c", [(0, 2048, 256), (1, 500, 64), (2, 130, 32)])
+def test_fine_stagewise_and_end_to_end(cuda, seed, n, c):
+    B = 2
+    d = batch(200 + seed, B, n, c, cuda)
+    atten = PO.feature_similarity(d["f1"], d["f2"], "cosine", 0.1, True)
+    for score in (d["score"], None):
+        R, t, s, m = MU()._fine(atten, score, d["pts1"], d["pts2"], None, 0.15, 0.001 if score is not None else 0.0,
+                                return_debug=True)
+        Ro, to, so, o = PO.fine_pose(atten, score, d["pts1"], d["pts2"], None, 0.15, debug=True)
+        assert torch.equal(m["w1"], o["w1"])
+        assert torch.allclose(m["asum"], o["rowsum"], rtol=1e-4, atol=1e-9)
+        assert torch.allclose(m["soft"], o["soft"], rtol=1e-4, atol=1e-5)
+        assert PO.rotation_geodesic_deg(R, Ro).max() <= ROT_TOL_DEG
+        assert PO.relative_translation_error(t, to).max() <= T_TOL_REL
+        # inlier ratio: a borderline point (|d - 0.15| ~ 1e-7) may flip -> at most a couple of counts
+        assert (s - so).abs().max() <= 2.5 / n
+        assert PO.rotation_geodesic_deg(R, d["R"]).max() < 1.0
+        # weighted Kabsch given the SAME soft correspondences and weights
+        Rw, tw = MU().weighted_procrustes(m["soft"], d["pts1"], m["asum"], weight_thresh=0.001)
+        Rwo, two = PO.weighted_procrustes(m["soft"], d["pts1"], m["asum"], weight_thresh=0.001)
+        assert PO.rotation_geodesic_deg(Rw, Rwo).max() <= ROT_TOL_DEG
+        assert PO.relative_translation_error(tw, two).max() <= T_TOL_REL
+
+
+def test_fine_api_and_determinism(cuda):
+    d = batch(300, 2, 2048, 256, cuda)
+    atten = MU().compute_feature_similarity(d["f1"], d["f2"], "cosine", 0.1, True)
+    a = MU().compute_fine_Rt_overlap(atten, d["score"], d["pts1"], d["pts2"])
+    b = MU().compute_fine_Rt_overlap(atten, d["score"], d["pts1"], d["pts2"])
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    R = a[0]
+    assert (torch.det(R.double()) - 1).abs().max() < 1e-5
+    assert (R @ R.transpose(1, 2) - torch.eye(3, device=cuda)).abs().max() < 1e-5
+    c = MU().compute_fine_Rt(atten, d["pts1"], d["pts2"])
+    co = PO.fine_pose(atten, None, d["pts1"], d["pts2"])
+    assert PO.rotation_geodesic_deg(c[0], co[0]).max() <= ROT_TOL_DEG
+
+
+# ------------------------------------------------------------------ golden vectors (reference, CPU run)
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "pose_coarse_*.npz"))))
+def test_coarse_against_reference_golden(cuda, path):
+    g = np.load(path)
+    T = lambda k: torch.from_numpy(g[k]).to(cuda)
+    H, K = int(g["H"]), int(g["K"])
+    R, t, s, m = MU()._coarse(T("atten"), T("score"), T("pts1"), T("pts2"), None, H, K, u=T("u"), return_debug=True)
+    for b in range(R.shape[0]):
+        ang = float(PO.rotation_geodesic_deg(R[b], T("R")[b]))
+        if ang <= ROT_TOL_DEG:
+            assert float(PO.relative_translation_error(t[b], T("t")[b])) <= T_TOL_REL
+            assert abs(float(s[b]) - float(g["s"][b])) <= 2e-4 * float(g["s"][b])
+        else:  # a different (near-tied) hypothesis won: scores must be equal to float noise
+            assert abs(float(s[b]) - float(g["s"][b])) <= 1e-4 * float(g["s"][b]), (ang, float(s[b]), float(g["s"][b]))
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "pose_fine_*.npz"))))
+def test_fine_against_reference_golden(cuda, path):
+    g = np.load(path)
+    T = lambda k: torch.from_numpy(g[k]).to(cuda)
+    R, t, s = MU().compute_fine_Rt_overlap(T("atten"), T("score"), T("pts1"), T("pts2"))
+    assert PO.rotation_geodesic_deg(R, T("R")).max() <= ROT_TOL_DEG
+    assert PO.relative_translation_error(t, T("t")).max() <= T_TOL_REL
+    assert (s - T("s")).abs().max() <= 2.5 / g["pts1"].shape[1]
+    R0, t0, s0 = MU().compute_fine_Rt(T("atten"), T("pts1"), T("pts2"))
+    assert PO.rotation_geodesic_deg(R0, T("R_plain")).max() <= ROT_TOL_DEG
+
+
+def test_procrustes_against_reference_golden(cuda):
+    g = np.load(os.path.join(GOLD, "pose_procrustes.npz"))
+    T = lambda k: torch.from_numpy(g[k]).to(cuda)
+    R1, t1 = MU().weighted_procrustes(T("src"), T("ref"), T("w"), weight_thresh=0.3)
+    assert PO.rotation_geodesic_deg(R1, T("R1")).max() <= ROT_TOL_DEG
+    assert PO.relative_translation_error(t1, T("t1")).max() <= T_TOL_REL
+    R2, t2 = MU().WeightedProcrustes()(T("src")[:, :3].contiguous(), T("ref")[:, :3].contiguous(), None)
+    assert PO.rotation_geodesic_deg(R2, T("R2")).max() <= ROT_TOL_DEG
+    assert PO.relative_translation_error(t2, T("t2")).max() <= 5e-5   # 3-point fits: cuSOLVER/LAPACK noise
+    r, tt = MU().weighted_procrustes(T("src")[0], T("ref")[0])
+    assert r.shape == (3, 3) and tt.shape == (3,)
+    Tm = MU().weighted_procrustes(T("src"), T("ref"), return_transform=True)
+    assert Tm.shape == (5, 4, 4)
+
+
+def test_sample_pts_feats_api(cuda):
+    from util_clouds import batch_clouds
+
+    pts = torch.from_numpy(batch_clouds(1, 2, 5000, "surface")).to(cuda)
+    feats = torch.randn(2, 5000, 256, device=cuda)
+    p, f, idx = MU().sample_pts_feats(pts, feats, 2048, return_index=True)
+    assert p.shape == (2, 2048, 3) and f.shape == (2, 2048, 256) and idx.dtype == torch.int32
+    assert torch.equal(p, torch.gather(pts, 1, idx.long().unsqueeze(2).repeat(1, 1, 3)))
+    assert torch.equal(f, torch.gather(feats, 1, idx.long().unsqueeze(2).repeat(1, 1, 256)))
+    p2, l2, f2 = MU().sample_pts_feats_wlrf(p, p * 2, f, 196)
+    assert p2.shape == (2, 196, 3) and torch.equal(l2, p2 * 2)

@@ -18,6 +18,7 @@ c_f = ctypes.c_void_p  # device pointers are passed as raw addresses
 c_i = ctypes.c_int
 c_fl = ctypes.c_float
 c_st = ctypes.c_void_p
+c_sz = ctypes.c_size_t
 
 # name -> argtypes (restype is always int unless noted)
 _SIGNATURES = {
@@ -32,7 +33,37 @@ _SIGNATURES = {
     "upk_three_nn": [c_f, c_f, c_i, c_i, c_i, c_f, c_f, c_st],
     "upk_three_interpolate": [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_f, c_st],
     "upk_three_interpolate_grad": [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_f, c_st],
+    "upk_feature_similarity": [c_f, c_f, c_i, c_i, c_i, c_i, c_fl, c_i, c_i, c_f, c_sz, c_f, c_st],
+    "upk_coarse_pose": [c_f, c_f, c_i, c_f, c_i, c_f, c_f, c_f, c_i, c_f, c_i, c_i, c_i, c_i, c_i,
+                        c_f, c_sz, c_f, c_f, c_f, c_f, c_f, c_st],
+    "upk_sample_hypotheses": [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_f, c_st],
+    "upk_kabsch_triplets": [c_f, c_f, c_i, c_f, c_f, c_f, c_st],
+    "upk_topk_smallest": [c_f, c_i, c_i, c_i, c_f, c_st],
+    "upk_score_hypotheses": [c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_st],
+    "upk_select_best": [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_st],
+    "upk_fine_pose": [c_f, c_f, c_i, c_f, c_i, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_fl, c_fl,
+                      c_f, c_sz, c_f, c_f, c_f, c_f, c_st],
+    "upk_weighted_procrustes": [c_f, c_f, c_f, c_i, c_i, c_fl, c_fl, c_f, c_f, c_st],
+    "upk_host_procrustes_rotation": [c_f, c_i, c_f],
 }
+
+# size_t-returning workspace queries
+_SIZE_FUNCS = {
+    "upk_feature_similarity_workspace_bytes": [c_i, c_i, c_i, c_i, c_i],
+    "upk_coarse_pose_workspace_bytes": [c_i, c_i, c_i, c_i, c_i],
+    "upk_fine_pose_workspace_bytes": [c_i, c_i, c_i],
+}
+
+
+class CoarseDebug(ctypes.Structure):
+    """struct upk_coarse_debug (include/unopose_b200.h)"""
+    _fields_ = [(n, ctypes.c_void_p) for n in
+                ("w1", "w2", "cdf", "idx1", "idx2", "Rs", "ts", "resid", "top", "scores")]
+
+
+class FineDebug(ctypes.Structure):
+    """struct upk_fine_debug (include/unopose_b200.h)"""
+    _fields_ = [(n, ctypes.c_void_p) for n in ("w1", "w2", "soft", "asum", "nn")]
 
 
 class UnoposeNativeError(RuntimeError):
@@ -53,6 +84,10 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
         fn.argtypes = argtypes
         fn.restype = ctypes.c_int
+    for name, argtypes in _SIZE_FUNCS.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = ctypes.c_size_t
     lib.upk_launch_count.argtypes = []
     lib.upk_launch_count.restype = ctypes.c_ulonglong
     _lib = lib
@@ -60,7 +95,7 @@ def load():
 
 
 def exported_symbols():
-    return sorted(list(_SIGNATURES) + ["upk_launch_count"])
+    return sorted(list(_SIGNATURES) + list(_SIZE_FUNCS) + ["upk_launch_count"])
 
 
 def launch_count():

@@ -1,0 +1,493 @@
+// Coarse pose solve: kernel families (2) correspondence sampling + triplet hypotheses,
+// (3) batched Kabsch on 3-point sets, (4) fused hypothesis scoring + arg-max.
+// Reference: compute_coarse_Rt[_overlap], core/unopose/utils/model_utils.py:336-490
+// (~60 ATen/cuBLAS/cuSOLVER launches, a (B*K,196,196) distance tensor of 46 MB per
+// instance).  Here: 4 kernels after the assignment passes, nothing larger than the
+// (B,H) hypothesis pool is ever materialised.
+#include <math.h>
+
+#include "common.cuh"
+#include "launch_count.h"
+#include "pose_internal.h"
+#include "solver3.cuh"
+#include "../../include/unopose_b200.h"
+
+namespace upk {
+
+// ---------------------------------------------------------------- (2)+(3)
+// torch.searchsorted(cdf, u)  (right=False): first index with cdf[idx] >= u
+__device__ __forceinline__ int lower_bound_f(const float* __restrict__ a, int n, float u) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (__ldg(a + mid) < u) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// Kabsch on one 3-point hypothesis, float arithmetic laid out like the reference's
+// weighted_procrustes (model_utils.py:704-730) with weights == ones: every weight is
+// 1/(3 + eps) (eps = 1e-5 quirk), src = reference triplet p2,
+// ref = query triplet p1 (call site :469).  The 3x3 solve runs in fp64 registers.
+__device__ __forceinline__ void kabsch_triplet(const float (&p1)[3][3], const float (&p2)[3][3], float* R,
+                                               float* t, float& resid) {
+  const float wn = 1.0f / (3.0f + 1e-5f);
+  float cs[3], cr[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    cs[a] = (p2[0][a] * wn + p2[1][a] * wn) + p2[2][a] * wn;
+    cr[a] = (p1[0][a] * wn + p1[1][a] * wn) + p1[2][a] * wn;
+  }
+  double H[9];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float h = 0.f;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) h = fmaf(p2[k][a] - cs[a], wn * (p1[k][c] - cr[c]), h);
+      H[a * 3 + c] = (double)h;
+    }
+  double Rd[9];
+  procrustes_rotation(H, Rd);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) R[i] = (float)Rd[i];
+  // t = c_ref - R c_src   (:729)
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+    t[a] = cr[a] - fmaf(R[a * 3 + 2], cs[2], fmaf(R[a * 3 + 1], cs[1], R[a * 3 + 0] * cs[0]));
+  // residual: mean_k || (p1_k - t) @ R - p2_k ||   (:475)
+  float acc = 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float d0 = p1[k][0] - t[0], d1 = p1[k][1] - t[1], d2 = p1[k][2] - t[2];
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float x = fmaf(d2, R[6 + c], fmaf(d1, R[3 + c], d0 * R[c])) - p2[k][c];
+      s = fmaf(x, x, s);
+    }
+    acc += sqrtf(s);
+  }
+  resid = acc / 3.0f;
+}
+
+constexpr int HY_THREADS = 128;
+
+// one thread = one hypothesis: 3 searchsorted draws -> triplet gather -> Kabsch -> residual
+__global__ void __launch_bounds__(HY_THREADS)
+k_hypotheses(const float* __restrict__ cdf, const float* __restrict__ u, const float* __restrict__ pts1,
+             const float* __restrict__ pts2, int n1, int n2, int H, int h0, int h1,
+             int* __restrict__ idx1_out, int* __restrict__ idx2_out, float* __restrict__ Rs,
+             float* __restrict__ ts, float* __restrict__ resid) {
+  const int b = blockIdx.y;
+  const int h = h0 + blockIdx.x * HY_THREADS + threadIdx.x;
+  if (h >= h1) return;
+  const float* cdf_b = cdf + (size_t)b * n1 * n2;
+  const float* p1b = pts1 + (size_t)b * n1 * 3;
+  const float* p2b = pts2 + (size_t)b * n2 * 3;
+  float p1[3][3], p2[3][3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float uu = u[((size_t)b * H + h) * 3 + k];
+    int idx = lower_bound_f(cdf_b, n1 * n2, uu);
+    int i1 = min(idx / n2, n1 - 1);  // :463-465 (clamp of the overflow index n1*n2)
+    int i2 = min(idx % n2, n2 - 1);
+    if (idx1_out) {
+      idx1_out[((size_t)b * H + h) * 3 + k] = i1;
+      idx2_out[((size_t)b * H + h) * 3 + k] = i2;
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      p1[k][a] = __ldg(p1b + i1 * 3 + a);
+      p2[k][a] = __ldg(p2b + i2 * 3 + a);
+    }
+  }
+  float R[9], t[3], r;
+  kabsch_triplet(p1, p2, R, t, r);
+  float* Ro = Rs + ((size_t)b * H + h) * 9;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) Ro[i] = R[i];
+  float* to = ts + ((size_t)b * H + h) * 3;
+  to[0] = t[0]; to[1] = t[1]; to[2] = t[2];
+  resid[(size_t)b * H + h] = r;
+}
+
+// Kabsch only (stage-wise entry: caller supplies the triplets)
+__global__ void __launch_bounds__(HY_THREADS)
+k_kabsch_triplets(const float* __restrict__ p1s, const float* __restrict__ p2s, int n,
+                  float* __restrict__ Rs, float* __restrict__ ts, float* __restrict__ resid) {
+  const int h = blockIdx.x * HY_THREADS + threadIdx.x;
+  if (h >= n) return;
+  float p1[3][3], p2[3][3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      p1[k][a] = p1s[(size_t)h * 9 + k * 3 + a];
+      p2[k][a] = p2s[(size_t)h * 9 + k * 3 + a];
+    }
+  float R[9], t[3], r;
+  kabsch_triplet(p1, p2, R, t, r);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) Rs[(size_t)h * 9 + i] = R[i];
+  ts[(size_t)h * 3 + 0] = t[0]; ts[(size_t)h * 3 + 1] = t[1]; ts[(size_t)h * 3 + 2] = t[2];
+  if (resid) resid[h] = r;
+}
+
+// ---------------------------------------------------------------- top-K smallest residuals
+// torch.topk(dis, K, largest=False) (:476).  One CTA per instance: 4-pass 8-bit radix select on
+// the float bit patterns (residuals are >= 0, NaN sorts last like torch), then an ORDERED
+// compaction: the selected set is emitted in ascending pool index; ties at the K-th value are
+// resolved towards the lower pool index (torch leaves that order unspecified).
+constexpr int TK_THREADS = 1024;
+
+__device__ __forceinline__ unsigned block_excl_scan_u32(unsigned v, unsigned* s_warp, unsigned& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned t = __shfl_up_sync(kFull, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned w = lane < (int)(blockDim.x >> 5) ? s_warp[lane] : 0u;
+    unsigned winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned t = __shfl_up_sync(kFull, winc, o);
+      if (lane >= o) winc += t;
+    }
+    s_warp[lane] = winc - w;  // exclusive per-warp offsets
+    if (lane == 31) s_warp[32] = winc;
+  }
+  __syncthreads();
+  unsigned res = s_warp[warp] + inc - v;
+  total = s_warp[32];
+  __syncthreads();
+  return res;
+}
+
+__global__ void __launch_bounds__(TK_THREADS)
+k_topk_smallest(const float* __restrict__ vals, int H, int K, int* __restrict__ top) {
+  __shared__ unsigned hist[256];
+  __shared__ unsigned s_warp[33];
+  __shared__ unsigned s_prefix, s_kth_rank;
+  const int b = blockIdx.x;
+  const unsigned* v = reinterpret_cast<const unsigned*>(vals) + (size_t)b * H;
+  top += (size_t)b * K;
+  unsigned prefix = 0, mask = 0;
+  unsigned want = (unsigned)K;  // rank (1-based) of the K-th smallest within the current bucket
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int i = threadIdx.x; i < 256; i += TK_THREADS) hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < H; i += TK_THREADS) {
+      unsigned x = v[i];
+      if ((x & mask) == prefix) atomicAdd(&hist[(x >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned acc = 0;
+      int d = 0;
+      for (; d < 256; ++d) {
+        if (acc + hist[d] >= want) break;
+        acc += hist[d];
+      }
+      s_prefix = prefix | ((unsigned)d << shift);
+      s_kth_rank = want - acc;
+    }
+    __syncthreads();
+    prefix = s_prefix;
+    want = s_kth_rank;
+    mask |= 255u << shift;
+    __syncthreads();
+  }
+  const unsigned kth = prefix;    // bit pattern of the K-th smallest value
+  const unsigned n_equal = want;  // how many elements == kth belong to the selection
+  // ordered compaction: each thread owns a contiguous chunk
+  const int per = (H + TK_THREADS - 1) / TK_THREADS;
+  const int beg = min(H, (int)threadIdx.x * per), end = min(H, beg + per);
+  unsigned nl = 0, ne = 0;
+  for (int i = beg; i < end; ++i) {
+    unsigned x = v[i];
+    nl += x < kth;
+    ne += x == kth;
+  }
+  unsigned tot;
+  unsigned l0 = block_excl_scan_u32(nl, s_warp, tot);
+  unsigned e0 = block_excl_scan_u32(ne, s_warp, tot);
+  for (int i = beg; i < end; ++i) {
+    unsigned x = v[i];
+    if (x < kth) {
+      top[l0 + min(e0, n_equal)] = i;
+      ++l0;
+    } else if (x == kth) {
+      if (e0 < n_equal) top[l0 + e0] = i;
+      ++e0;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- (4) scoring
+// For hypothesis (R,t):  X = (pts1 - t) @ R ; d_i = sqrt(clamp(min_j (|X_i|^2 - 2 X_i.Y_j + |Y_j|^2), 0))
+// score = sum_i w1_i / (sum_i d_i w1_i + 1e-8)        (model_utils.py:481-485, pairwise_distance :246-256)
+// One CTA per (instance, kept hypothesis); model points staged in smem as (x,y,z,|y|^2);
+// 6 issue slots per point pair; the (B*K,N1,N2) distance tensor never exists.
+constexpr int SC_THREADS = 128;
+
+__global__ void __launch_bounds__(SC_THREADS)
+k_score(const float* __restrict__ pts1, const float* __restrict__ model, const float* __restrict__ w1,
+        const float* __restrict__ Rs, const float* __restrict__ ts, const int* __restrict__ top,
+        int n1, int nm, int H, int K, int k0, float* __restrict__ scores) {
+  extern __shared__ float4 sm_model[];  // nm
+  __shared__ double s_red[2][SC_THREADS / 32];
+  const int b = blockIdx.y;
+  const int k = k0 + blockIdx.x;
+  const float* mb = model + (size_t)b * nm * 3;
+  for (int j = threadIdx.x; j < nm; j += SC_THREADS) {
+    float x = mb[j * 3 + 0], y = mb[j * 3 + 1], z = mb[j * 3 + 2];
+    // y2 = sum(y**2, -1): products rounded separately, then summed
+    float y2 = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+    sm_model[j] = make_float4(x, y, z, y2);
+  }
+  const int h = top ? top[(size_t)b * K + k] : k;
+  const float* R = Rs + ((size_t)b * H + h) * 9;
+  const float* t = ts + ((size_t)b * H + h) * 3;
+  const float r00 = R[0], r01 = R[1], r02 = R[2], r10 = R[3], r11 = R[4], r12 = R[5], r20 = R[6],
+              r21 = R[7], r22 = R[8];
+  const float t0 = t[0], t1 = t[1], t2 = t[2];
+  __syncthreads();
+  double num = 0.0, den = 0.0;
+  for (int i = threadIdx.x; i < n1; i += SC_THREADS) {
+    const float* p = pts1 + ((size_t)b * n1 + i) * 3;
+    float d0 = p[0] - t0, d1 = p[1] - t1, d2 = p[2] - t2;
+    float x0 = fmaf(d2, r20, fmaf(d1, r10, d0 * r00));
+    float x1 = fmaf(d2, r21, fmaf(d1, r11, d0 * r01));
+    float x2 = fmaf(d2, r22, fmaf(d1, r12, d0 * r02));
+    float xx = __fadd_rn(__fadd_rn(__fmul_rn(x0, x0), __fmul_rn(x1, x1)), __fmul_rn(x2, x2));
+    float best = INFINITY;
+#pragma unroll 4
+    for (int j = 0; j < nm; ++j) {
+      float4 q = sm_model[j];
+      float xy = fmaf(x2, q.z, fmaf(x1, q.y, x0 * q.x));
+      float d = __fadd_rn(fmaf(-2.0f, xy, xx), q.w);  // (x2 - 2xy) + y2
+      best = fminf(best, d);
+    }
+    float dist = sqrtf(fmaxf(best, 0.f));
+    float w = w1[(size_t)b * n1 + i];
+    num += (double)w;
+    den += (double)(dist * w);
+  }
+  num = warp_sum(num);
+  den = warp_sum(den);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { s_red[0][warp] = num; s_red[1][warp] = den; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double n = 0.0, d = 0.0;
+    for (int w = 0; w < SC_THREADS / 32; ++w) { n += s_red[0][w]; d += s_red[1][w]; }
+    scores[(size_t)b * K + k] = (float)n / ((float)d + 1e-8f);
+  }
+}
+
+// arg-max over the K kept hypotheses (first maximum), gather R, t, score, pool index (:486-488)
+__global__ void __launch_bounds__(256)
+k_select(const float* __restrict__ scores, const int* __restrict__ top, const float* __restrict__ Rs,
+         const float* __restrict__ ts, int H, int K, float* __restrict__ R_out, float* __restrict__ t_out,
+         float* __restrict__ score_out, int* __restrict__ pool_out) {
+  __shared__ float s_v[8];
+  __shared__ int s_i[8];
+  const int b = blockIdx.x;
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  bool seen_nan = false;
+  for (int k = threadIdx.x; k < K; k += 256) {
+    float v = scores[(size_t)b * K + k];
+    if (v != v) { if (!seen_nan) { seen_nan = true; bv = v; bi = k; } continue; }
+    if (!seen_nan && (v > bv || (v == bv && k < bi))) { bv = v; bi = k; }
+  }
+  // warp reduce (NaN wins, then larger value, then smaller index) — torch.max propagates NaN
+  for (int o = 16; o > 0; o >>= 1) {
+    float ov = __shfl_xor_sync(kFull, bv, o);
+    int oi = __shfl_xor_sync(kFull, bi, o);
+    bool a_nan = bv != bv, b_nan = ov != ov;
+    bool take = b_nan ? (!a_nan || oi < bi) : (!a_nan && (ov > bv || (ov == bv && oi < bi)));
+    if (take) { bv = ov; bi = oi; }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { s_v[warp] = bv; s_i[warp] = bi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) {
+      float ov = s_v[w];
+      int oi = s_i[w];
+      bool a_nan = bv != bv, b_nan = ov != ov;
+      bool take = b_nan ? (!a_nan || oi < bi) : (!a_nan && (ov > bv || (ov == bv && oi < bi)));
+      if (take) { bv = ov; bi = oi; }
+    }
+    if (bi == 0x7fffffff) bi = 0;
+    int h = top ? top[(size_t)b * K + bi] : bi;
+    for (int i = 0; i < 9; ++i) R_out[(size_t)b * 9 + i] = Rs[((size_t)b * H + h) * 9 + i];
+    for (int i = 0; i < 3; ++i) t_out[(size_t)b * 3 + i] = ts[((size_t)b * H + h) * 3 + i];
+    score_out[b] = bv;
+    if (pool_out) pool_out[b] = h;
+  }
+}
+
+struct CoarseWs {
+  AssignWs a;
+  float* w1; float* w2;
+  float* pmat; double* prow; float* cdf;
+  float* Rs; float* ts; float* resid;
+  int* top; float* scores;
+};
+
+static void carve_coarse(Carver& cv, int b, int n1, int n2, int H, int K, const AssignGeom& g, CoarseWs& w) {
+  carve_assign(cv, b, g, w.a);
+  w.w1 = cv.take<float>((size_t)b * n1);
+  w.w2 = cv.take<float>((size_t)b * n2);
+  w.pmat = cv.take<float>((size_t)b * n1 * n2);
+  w.prow = cv.take<double>((size_t)b * n1 * g.ntc);
+  w.cdf = cv.take<float>((size_t)b * n1 * n2);
+  w.Rs = cv.take<float>((size_t)b * H * 9);
+  w.ts = cv.take<float>((size_t)b * H * 3);
+  w.resid = cv.take<float>((size_t)b * H);
+  w.top = cv.take<int>((size_t)b * K);
+  w.scores = cv.take<float>((size_t)b * K);
+}
+
+static int launch_score(const float* pts1, const float* model, const float* w1, const float* Rs,
+                        const float* ts, const int* top, int b, int n1, int nm, int H, int K, int k0, int k1,
+                        float* scores, cudaStream_t st) {
+  if (k1 <= k0) return UPK_OK;
+  size_t smem = (size_t)nm * sizeof(float4);
+  if (smem > 200 * 1024) return UPK_ERR_UNSUPPORTED;
+  if (smem > 48 * 1024)
+    UPK_CUDA_TRY(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(k1 - k0, b);
+  k_score<<<grid, SC_THREADS, smem, st>>>(pts1, model, w1, Rs, ts, top, n1, nm, H, K, k0, scores);
+  count_launch();
+  UPK_RETURN_LAST_ERROR();
+}
+
+}  // namespace upk
+
+using namespace upk;
+
+extern "C" {
+
+size_t upk_coarse_pose_workspace_bytes(int b, int n1, int n2, int n_hyp, int n_keep) {
+  if (b <= 0 || n1 <= 0 || n2 <= 0 || n_hyp <= 0 || n_keep <= 0) return 0;
+  Carver cv(nullptr);
+  CoarseWs w;
+  carve_coarse(cv, b, n1, n2, n_hyp, n_keep, assign_geom(n1 + 1, n2 + 1), w);
+  return cv.bytes();
+}
+
+int upk_coarse_pose(const float* atten, const float* score1, int score1_ld, const float* score2,
+                    int score2_ld, const float* pts1, const float* pts2, const float* model_pts,
+                    int n_model, const float* u, int b, int n1, int n2, int n_hyp, int n_keep,
+                    void* workspace, size_t workspace_bytes, float* R_out, float* t_out, float* score_out,
+                    int* pool_idx_out, const upk_coarse_debug* dbg, upk_stream_t stream) {
+  if (b < 0 || n1 <= 0 || n2 <= 0 || n_hyp <= 0 || n_keep <= 0 || n_keep > n_hyp) return UPK_ERR_INVALID_ARG;
+  if (b == 0) return UPK_OK;
+  if (!atten || !pts1 || !pts2 || !u || !workspace || !R_out || !t_out || !score_out) return UPK_ERR_INVALID_ARG;
+  if ((score1 == nullptr) != (score2 == nullptr)) return UPK_ERR_INVALID_ARG;
+  if ((long long)n1 * n2 >= (1LL << 31)) return UPK_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  AssignGeom g = assign_geom(n1 + 1, n2 + 1);
+  Carver cv(workspace);
+  CoarseWs w;
+  carve_coarse(cv, b, n1, n2, n_hyp, n_keep, g, w);
+  if (cv.bytes() > workspace_bytes) return UPK_ERR_INVALID_ARG;
+  if (!model_pts) { model_pts = pts2; n_model = n2; }
+  int rc;
+  if ((rc = run_assignment_labels(atten, score1, score1_ld, score2, score2_ld, b, g, w.a, w.w1, w.w2, st))) return rc;
+  if ((rc = run_coarse_P(atten, score1, score1_ld, score2, score2_ld, b, g, w.a, w.w1, w.w2, w.pmat, w.prow, st))) return rc;
+  if ((rc = run_cdf(w.pmat, w.prow, b, n1, n2, g.ntc, w.cdf, st))) return rc;
+  {
+    dim3 grid(ceil_div(n_hyp, HY_THREADS), b);
+    k_hypotheses<<<grid, HY_THREADS, 0, st>>>(w.cdf, u, pts1, pts2, n1, n2, n_hyp, 0, n_hyp,
+                                              dbg ? dbg->idx1 : nullptr, dbg ? dbg->idx2 : nullptr, w.Rs,
+                                              w.ts, w.resid);
+    count_launch();
+  }
+  k_topk_smallest<<<b, TK_THREADS, 0, st>>>(w.resid, n_hyp, n_keep, w.top);
+  count_launch();
+  if ((rc = launch_score(pts1, model_pts, w.w1, w.Rs, w.ts, w.top, b, n1, n_model, n_hyp, n_keep, 0, n_keep,
+                         w.scores, st)))
+    return rc;
+  k_select<<<b, 256, 0, st>>>(w.scores, w.top, w.Rs, w.ts, n_hyp, n_keep, R_out, t_out, score_out, pool_idx_out);
+  count_launch();
+  if (dbg) {
+    // optional copies of the intermediates for stage-wise parity tests
+    if (dbg->w1) UPK_CUDA_TRY(cudaMemcpyAsync(dbg->w1, w.w1, sizeof(float) * (size_t)b * n1, cudaMemcpyDeviceToDevice, st));
+    if (dbg->w2) UPK_CUDA_TRY(cudaMemcpyAsync(dbg->w2, w.w2, sizeof(float) * (size_t)b * n2, cudaMemcpyDeviceToDevice, st));
+    if (dbg->cdf) UPK_CUDA_TRY(cudaMemcpyAsync(dbg->cdf, w.cdf, sizeof(float) * (size_t)b * n1 * n2, cudaMemcpyDeviceToDevice, st));
+    if (dbg->Rs) UPK_CUDA_TRY(cudaMemcpyAsync(dbg->Rs, w.Rs, sizeof(float) * (size_t)b * n_hyp * 9, cudaMemcpyDeviceToDevice, st));
+    if (dbg->ts) UPK_CUDA_TRY(cudaMemcpyAsync(dbg->ts, w.ts, sizeof(float) * (size_t)b * n_hyp * 3, cudaMemcpyDeviceToDevice, st));
+    if (dbg->resid) UPK_CUDA_TRY(cudaMemcpyAsync(dbg->resid, w.resid, sizeof(float) * (size_t)b * n_hyp, cudaMemcpyDeviceToDevice, st));
+    if (dbg->top) UPK_CUDA_TRY(cudaMemcpyAsync(dbg->top, w.top, sizeof(int) * (size_t)b * n_keep, cudaMemcpyDeviceToDevice, st));
+    if (dbg->scores) UPK_CUDA_TRY(cudaMemcpyAsync(dbg->scores, w.scores, sizeof(float) * (size_t)b * n_keep, cudaMemcpyDeviceToDevice, st));
+  }
+  UPK_RETURN_LAST_ERROR();
+}
+
+// ---- stage-wise entry points (identical-input parity tests, hypothesis sharding) ----
+
+int upk_sample_hypotheses(const float* cdf, const float* u, const float* pts1, const float* pts2, int b,
+                          int n1, int n2, int n_hyp, int h_begin, int h_end, int* idx1_out, int* idx2_out,
+                          float* Rs, float* ts, float* resid, upk_stream_t stream) {
+  if (b < 0 || n1 <= 0 || n2 <= 0 || n_hyp <= 0 || h_begin < 0 || h_end > n_hyp || h_begin > h_end)
+    return UPK_ERR_INVALID_ARG;
+  if (b == 0 || h_begin == h_end) return UPK_OK;
+  if ((idx1_out == nullptr) != (idx2_out == nullptr)) return UPK_ERR_INVALID_ARG;
+  dim3 grid(ceil_div(h_end - h_begin, HY_THREADS), b);
+  k_hypotheses<<<grid, HY_THREADS, 0, (cudaStream_t)stream>>>(cdf, u, pts1, pts2, n1, n2, n_hyp, h_begin, h_end,
+                                                              idx1_out, idx2_out, Rs, ts, resid);
+  count_launch();
+  UPK_RETURN_LAST_ERROR();
+}
+
+int upk_kabsch_triplets(const float* p1, const float* p2, int n, float* Rs, float* ts, float* resid,
+                        upk_stream_t stream) {
+  if (n < 0) return UPK_ERR_INVALID_ARG;
+  if (n == 0) return UPK_OK;
+  k_kabsch_triplets<<<ceil_div(n, HY_THREADS), HY_THREADS, 0, (cudaStream_t)stream>>>(p1, p2, n, Rs, ts, resid);
+  count_launch();
+  UPK_RETURN_LAST_ERROR();
+}
+
+int upk_topk_smallest(const float* vals, int b, int n, int k, int* idx_out, upk_stream_t stream) {
+  if (b < 0 || n <= 0 || k <= 0 || k > n) return UPK_ERR_INVALID_ARG;
+  if (b == 0) return UPK_OK;
+  k_topk_smallest<<<b, TK_THREADS, 0, (cudaStream_t)stream>>>(vals, n, k, idx_out);
+  count_launch();
+  UPK_RETURN_LAST_ERROR();
+}
+
+int upk_score_hypotheses(const float* pts1, const float* model_pts, const float* w1, const float* Rs,
+                         const float* ts, const int* top, int b, int n1, int n_model, int n_hyp, int n_keep,
+                         int k_begin, int k_end, float* scores, upk_stream_t stream) {
+  if (b < 0 || n1 <= 0 || n_model <= 0 || n_hyp <= 0 || n_keep <= 0 || k_begin < 0 || k_end > n_keep ||
+      k_begin > k_end)
+    return UPK_ERR_INVALID_ARG;
+  if (b == 0) return UPK_OK;
+  return launch_score(pts1, model_pts, w1, Rs, ts, top, b, n1, n_model, n_hyp, n_keep, k_begin, k_end, scores,
+                      (cudaStream_t)stream);
+}
+
+int upk_select_best(const float* scores, const int* top, const float* Rs, const float* ts, int b, int n_hyp,
+                    int n_keep, float* R_out, float* t_out, float* score_out, int* pool_idx_out,
+                    upk_stream_t stream) {
+  if (b < 0 || n_hyp <= 0 || n_keep <= 0) return UPK_ERR_INVALID_ARG;
+  if (b == 0) return UPK_OK;
+  k_select<<<b, 256, 0, (cudaStream_t)stream>>>(scores, top, Rs, ts, n_hyp, n_keep, R_out, t_out, score_out,
+                                                pool_idx_out);
+  count_launch();
+  UPK_RETURN_LAST_ERROR();
+}
+
+}  // extern "C"

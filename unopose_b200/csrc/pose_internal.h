@@ -1,0 +1,66 @@
+// Internal (non-ABI) declarations shared by the pose translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace upk {
+
+// Bump allocator over a caller-provided workspace; with base == nullptr it only
+// measures (used by the *_workspace_bytes entry points).
+struct Carver {
+  char* base;
+  size_t off;
+  explicit Carver(void* p) : base((char*)p), off(0) {}
+  template <class T>
+  T* take(size_t n) {
+    off = (off + 255) & ~(size_t)255;
+    T* r = base ? (T*)(base + off) : (T*)nullptr;
+    off += n * sizeof(T);
+    return r;
+  }
+  size_t bytes() const { return (off + 255) & ~(size_t)255; }
+};
+
+// Tile geometry of the assignment passes (assign.cu)
+struct AssignGeom {
+  int R, C;      // rows / cols of atten (incl. background row/col 0)
+  int TR, TC;    // tile shape
+  int ntr, ntc;  // tile counts
+};
+AssignGeom assign_geom(int R, int C);
+
+// Workspace of the dual-softmax assignment passes.
+struct AssignWs {
+  float2* rowpart;  // [b][R][ntc]  (max, sumexp) partials
+  float2* colpart;  // [b][C][ntr]
+  float* rmax;      // [b][R]
+  float* rsum;
+  float* cmax;      // [b][C]
+  float* csum;
+  float* rowpm;     // [b][R][ntc]  partial row max of A over cols >= 1
+  float* colpm;     // [b][C][ntr]  partial col max of A over rows >= 1
+  float* ai0;       // [b][R]  A[i][0]
+  float* a0j;       // [b][C]  A[0][j]
+};
+void carve_assign(Carver& cv, int b, const AssignGeom& g, AssignWs& ws);
+
+// stats + labels: fills ws.{rmax,rsum,cmax,csum} and w1 [b][R-1], w2 [b][C-1]
+int run_assignment_labels(const float* atten, const float* score1, int ld1, const float* score2, int ld2,
+                          int b, const AssignGeom& g, const AssignWs& ws, float* w1, float* w2,
+                          cudaStream_t st);
+
+// coarse: P = (A w1 w2)^1.5 over the foreground block -> pmat [b][N1*N2], row-sum partials (double)
+int run_coarse_P(const float* atten, const float* score1, int ld1, const float* score2, int ld2, int b,
+                 const AssignGeom& g, const AssignWs& ws, const float* w1, const float* w2, float* pmat,
+                 double* prow /*[b][N1][ntc]*/, cudaStream_t st);
+// cdf[k] = float(prefix_k) / (float(total) + 1e-8)
+int run_cdf(const float* pmat, const double* prow, int b, int n1, int n2, int ntc, float* cdf, cudaStream_t st);
+
+// fine: per-row  sum_j A_ij w2_j {x,y,z,1}_j  (times w1_i)  -> soft [b][N1][3], asum [b][N1]
+int run_fine_rowsums(const float* atten, const float* score1, int ld1, const float* score2, int ld2, int b,
+                     const AssignGeom& g, const AssignWs& ws, const float* w1, const float* w2,
+                     const float* pts2, float4* rowpart4 /*[b][N1][ntc]*/, float* soft, float* asum,
+                     cudaStream_t st);
+
+}  // namespace upk

@@ -1,0 +1,284 @@
+"""Drop-in for the hot-path functions of ``core.unopose.utils.model_utils`` (reference file).
+
+Same names, argument meaning, return values and RNG consumption as the reference;
+the work runs in the sm_100a kernels of libunopose_b200.so through the C ABI
+(include/unopose_b200.h).  CUDA tensors only — there is no CPU or plain-torch
+fallback for the kernel families (1)-(5).
+
+Pose convention (reference): ``p_ref ~= (p_query - t) @ R``  <=>  ``p_query = R p_ref + t``.
+"""
+import ctypes
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from .pointnet2.pointnet2_utils import furthest_point_sample, gather_operation
+
+
+def _f32c(x):
+    return x.float().contiguous()
+
+
+def _need_cuda(x, what):
+    if not x.is_cuda:
+        raise RuntimeError("%s: CPU not supported (CUDA tensors only; no fallback path)" % what)
+
+
+def _workspace(nbytes, device):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+# --------------------------------------------------------------------------- a1
+def compute_feature_similarity(feat1, feat2, type="cosine", temp=1.0, normalize_feat=True):
+    """(B,N,C),(B,M,C) -> (B,N,M).  Reference: model_utils.py:260-282."""
+    if type not in ("cosine", "L2"):
+        raise AssertionError(type)
+    _need_cuda(feat1, "compute_feature_similarity")
+    f1, f2 = _f32c(feat1), _f32c(feat2)
+    b, n, c = f1.shape
+    m = f2.shape[1]
+    lib = L.load()
+    out = torch.empty((b, n, m), dtype=torch.float32, device=f1.device)
+    nbytes = lib.upk_feature_similarity_workspace_bytes(b, n, m, c, int(bool(normalize_feat)))
+    ws = _workspace(nbytes, f1.device)
+    with torch.cuda.device(f1.device):
+        L.check(lib.upk_feature_similarity(L.ptr(f1), L.ptr(f2), b, n, m, c, float(temp), int(bool(normalize_feat)),
+                                           0 if type == "cosine" else 1, L.ptr(ws), ws.numel(), L.ptr(out),
+                                           L.stream_ptr(f1)), "feature_similarity")
+    return out
+
+
+def pairwise_distance(x, y, normalized=False, channel_first=False):
+    """Squared pairwise distances, expansion form, clamped at 0.  Reference: model_utils.py:230-257.
+
+    Host-side torch glue: inside the pose solvers this arithmetic is fused into the
+    scoring kernels (families (4)); as a standalone function it only serves the
+    geometric embedding (a "next" row), so it stays a plain torch expression."""
+    if channel_first:
+        xy = torch.matmul(x.transpose(-1, -2), y)
+        cdim = -2
+    else:
+        xy = torch.matmul(x, y.transpose(-1, -2))
+        cdim = -1
+    if normalized:
+        d = 2.0 - 2.0 * xy
+    else:
+        d = torch.sum(x ** 2, dim=cdim).unsqueeze(-1) - 2 * xy + torch.sum(y ** 2, dim=cdim).unsqueeze(-2)
+    return d.clamp(min=0.0)
+
+
+# --------------------------------------------------------------------------- a7
+def _coarse(atten, score, pts1, pts2, model_pts, n_proposal1, n_proposal2, u=None, return_debug=False):
+    _need_cuda(pts1, "compute_coarse_Rt")
+    B, N1, _ = pts1.shape
+    N2 = pts2.shape[1]
+    dev = pts1.device
+    atten, pts1, pts2 = _f32c(atten), _f32c(pts1), _f32c(pts2)
+    n_model = N2
+    if model_pts is not None:
+        model_pts = _f32c(model_pts)
+        n_model = model_pts.shape[1]
+    H, K = int(n_proposal1), int(n_proposal2)
+    s1 = s2 = None
+    ld = 0
+    if score is not None:
+        score = _f32c(score)
+        ld = score.shape[1]
+        s1 = score  # score[:, :N1]
+        # reference quirk (model_utils.py:440): score2 = score[:, N2:]  — only N2 long when N1 == N2
+        if score.shape[1] - N2 != N2:
+            raise RuntimeError("compute_coarse_Rt_overlap: score[:, N2:] must have N2 columns "
+                               "(the reference slices score[:, N2:], which requires N1 == N2)")
+        s2 = score[:, N2:]
+    # RNG: exactly one torch.rand(B, 3H) from the default generator, at the reference's position (:462)
+    if u is None:
+        u = torch.rand(B, H * 3, device=dev)
+    u = _f32c(u)
+    lib = L.load()
+    ws = _workspace(lib.upk_coarse_pose_workspace_bytes(B, N1, N2, H, K), dev)
+    R = torch.empty((B, 3, 3), dtype=torch.float32, device=dev)
+    t = torch.empty((B, 3), dtype=torch.float32, device=dev)
+    sc = torch.empty((B,), dtype=torch.float32, device=dev)
+    pool = torch.empty((B,), dtype=torch.int32, device=dev)
+    dbg = None
+    dbg_t = None
+    if return_debug:
+        dbg_t = dict(
+            w1=torch.empty((B, N1), device=dev), w2=torch.empty((B, N2), device=dev),
+            cdf=torch.empty((B, N1 * N2), device=dev),
+            idx1=torch.empty((B, H, 3), dtype=torch.int32, device=dev),
+            idx2=torch.empty((B, H, 3), dtype=torch.int32, device=dev),
+            Rs=torch.empty((B, H, 3, 3), device=dev), ts=torch.empty((B, H, 3), device=dev),
+            resid=torch.empty((B, H), device=dev), top=torch.empty((B, K), dtype=torch.int32, device=dev),
+            scores=torch.empty((B, K), device=dev))
+        dbg = L.CoarseDebug(**{k: v.data_ptr() for k, v in dbg_t.items()})
+    with torch.cuda.device(dev):
+        L.check(lib.upk_coarse_pose(
+            L.ptr(atten), L.ptr(s1), ld, (s2.data_ptr() if s2 is not None else None), ld,
+            L.ptr(pts1), L.ptr(pts2), L.ptr(model_pts), n_model, L.ptr(u), B, N1, N2, H, K,
+            L.ptr(ws), ws.numel(), L.ptr(R), L.ptr(t), L.ptr(sc), L.ptr(pool),
+            ctypes.addressof(dbg) if dbg is not None else None, L.stream_ptr(pts1)), "coarse_pose")
+    if return_debug:
+        dbg_t["pool"] = pool
+        dbg_t["u"] = u
+        return R, t, sc, dbg_t
+    return R, t, sc
+
+
+def compute_coarse_Rt(atten, pts1, pts2, model_pts=None, n_proposal1=6000, n_proposal2=300):
+    """Reference: model_utils.py:336-408.  -> (R (B,3,3), t (B,3), pose_score (B,))."""
+    return _coarse(atten, None, pts1, pts2, model_pts, n_proposal1, n_proposal2)
+
+
+def compute_coarse_Rt_overlap(atten, score, pts1, pts2, model_pts=None, n_proposal1=6000, n_proposal2=300):
+    """Reference: model_utils.py:411-490 (the variant the model calls, coarse module :99)."""
+    return _coarse(atten, score, pts1, pts2, model_pts, n_proposal1, n_proposal2)
+
+
+# --------------------------------------------------------------------------- a8
+def _fine(atten, score, pts1, pts2, model_pts, dis_thres, weight_thresh, return_debug=False):
+    _need_cuda(pts1, "compute_fine_Rt")
+    B, N1 = pts1.shape[:2]
+    N2 = pts2.shape[1]
+    dev = pts1.device
+    atten, pts1, pts2 = _f32c(atten), _f32c(pts1), _f32c(pts2)
+    n_model = N2
+    if model_pts is not None:
+        model_pts = _f32c(model_pts)
+        n_model = model_pts.shape[1]
+    s1 = s2 = None
+    ld = 0
+    if score is not None:
+        score = _f32c(score)
+        ld = score.shape[1]
+        s1 = score
+        s2 = score[:, N1:]  # model_utils.py:538
+        if s2.shape[1] != N2:
+            raise RuntimeError("compute_fine_Rt_overlap: score must be (B, N1 + N2)")
+    lib = L.load()
+    ws = _workspace(lib.upk_fine_pose_workspace_bytes(B, N1, N2), dev)
+    R = torch.empty((B, 3, 3), dtype=torch.float32, device=dev)
+    t = torch.empty((B, 3), dtype=torch.float32, device=dev)
+    sc = torch.empty((B,), dtype=torch.float32, device=dev)
+    dbg = None
+    dbg_t = None
+    if return_debug:
+        dbg_t = dict(w1=torch.empty((B, N1), device=dev), w2=torch.empty((B, N2), device=dev),
+                     soft=torch.empty((B, N1, 3), device=dev), asum=torch.empty((B, N1), device=dev),
+                     nn=torch.empty((B, N1), device=dev))
+        dbg = L.FineDebug(**{k: v.data_ptr() for k, v in dbg_t.items()})
+    with torch.cuda.device(dev):
+        L.check(lib.upk_fine_pose(
+            L.ptr(atten), L.ptr(s1), ld, (s2.data_ptr() if s2 is not None else None), ld,
+            L.ptr(pts1), L.ptr(pts2), L.ptr(model_pts), n_model, B, N1, N2, float(dis_thres),
+            float(weight_thresh), L.ptr(ws), ws.numel(), L.ptr(R), L.ptr(t), L.ptr(sc),
+            ctypes.addressof(dbg) if dbg is not None else None, L.stream_ptr(pts1)), "fine_pose")
+    if return_debug:
+        return R, t, sc, dbg_t
+    return R, t, sc
+
+
+def compute_fine_Rt(atten, pts1, pts2, model_pts=None, dis_thres=0.15):
+    """Reference: model_utils.py:493-524 (weight_thresh 0.0)."""
+    return _fine(atten, None, pts1, pts2, model_pts, dis_thres, 0.0)
+
+
+def compute_fine_Rt_overlap(atten, score, pts1, pts2, model_pts=None, dis_thres=0.15):
+    """Reference: model_utils.py:527-566 (weight_thresh 0.001; the variant the model calls, fine module :120)."""
+    return _fine(atten, score, pts1, pts2, model_pts, dis_thres, 0.001)
+
+
+# --------------------------------------------------------------------------- a4
+def weighted_procrustes(src_points, ref_points, weights=None, weight_thresh=0.0, eps=1e-5,
+                        return_transform=False, src_centroid=None, ref_centroid=None):
+    """Reference: model_utils.py:667-743.  (N,3)/(B,N,3) inputs; returns (R, t) or a 4x4 transform.
+    ``ref ~= R src + t``.  The reference's optional precomputed centroids are never passed by
+    any caller in the repository and are not supported by the kernel."""
+    if src_centroid is not None or ref_centroid is not None:
+        raise NotImplementedError("weighted_procrustes: precomputed centroids are not supported")
+    _need_cuda(src_points, "weighted_procrustes")
+    squeeze = src_points.ndim == 2
+    if squeeze:
+        src_points = src_points.unsqueeze(0)
+        ref_points = ref_points.unsqueeze(0)
+        if weights is not None:
+            weights = weights.unsqueeze(0)
+    src, ref = _f32c(src_points), _f32c(ref_points)
+    w = _f32c(weights) if weights is not None else None
+    B, N, _ = src.shape
+    dev = src.device
+    R = torch.empty((B, 3, 3), dtype=torch.float32, device=dev)
+    t = torch.empty((B, 3), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        if N == 3 and w is None and weight_thresh <= 1.0 and eps == 1e-5:
+            # triplet fast path == WeightedProcrustes()(src, ref, None): ref plays "p1", src plays "p2"
+            L.check(L.load().upk_kabsch_triplets(L.ptr(ref), L.ptr(src), B, L.ptr(R), L.ptr(t), None,
+                                                 L.stream_ptr(src)), "kabsch_triplets")
+        else:
+            L.check(L.load().upk_weighted_procrustes(L.ptr(src), L.ptr(ref), L.ptr(w), B, N, float(weight_thresh),
+                                                     float(eps), L.ptr(R), L.ptr(t), L.stream_ptr(src)),
+                    "weighted_procrustes")
+    if return_transform:
+        T = torch.eye(4, device=dev).unsqueeze(0).repeat(B, 1, 1)
+        T[:, :3, :3] = R
+        T[:, :3, 3] = t
+        return T.squeeze(0) if squeeze else T
+    if squeeze:
+        return R.squeeze(0), t.squeeze(0)
+    return R, t
+
+
+class WeightedProcrustes(nn.Module):
+    """Reference: model_utils.py:746-763."""
+
+    def __init__(self, weight_thresh=0.5, eps=1e-5, return_transform=False):
+        super().__init__()
+        self.weight_thresh = weight_thresh
+        self.eps = eps
+        self.return_transform = return_transform
+
+    def forward(self, src_points, tgt_points, weights=None, src_centroid=None, ref_centroid=None):
+        return weighted_procrustes(src_points, tgt_points, weights=weights, weight_thresh=self.weight_thresh,
+                                   eps=self.eps, return_transform=self.return_transform,
+                                   src_centroid=src_centroid, ref_centroid=ref_centroid)
+
+
+# --------------------------------------------------------------------------- a15
+def _gather_rows(x, idx):
+    """x (B,N,C) gathered along N by idx (B,m) int32 -> (B,m,C), via the channel-first gather kernel."""
+    return gather_operation(x.transpose(1, 2).contiguous(), idx).transpose(1, 2).contiguous()
+
+
+def sample_pts_feats(pts, feats, npoint=2048, return_index=False):
+    """FPS + gather of points and features.  Reference: model_utils.py:137-153."""
+    with torch.autocast(device_type="cuda", enabled=False):
+        pts = pts.to(dtype=torch.float32)
+        feats = feats.to(dtype=torch.float32)
+        idx = furthest_point_sample(pts.contiguous(), npoint)
+        pts, feats = _gather_rows(pts, idx), _gather_rows(feats, idx)
+    return (pts, feats, idx) if return_index else (pts, feats)
+
+
+def sample_pts_feats_wlrf(pts, pts_lrf, feats, npoint=2048, return_index=False):
+    """Reference: model_utils.py:156-177."""
+    with torch.autocast(device_type="cuda", enabled=False):
+        pts = pts.to(dtype=torch.float32)
+        pts_lrf = pts_lrf.to(dtype=torch.float32)
+        feats = feats.to(dtype=torch.float32)
+        idx = furthest_point_sample(pts.contiguous(), npoint)
+        pts, pts_lrf, feats = _gather_rows(pts, idx), _gather_rows(pts_lrf, idx), _gather_rows(feats, idx)
+    return (pts, pts_lrf, feats, idx) if return_index else (pts, pts_lrf, feats)
+
+
+def gather_pts_feats(sample_idx, pts, feats):
+    """Reference: model_utils.py:180-193."""
+    with torch.autocast(device_type="cuda", enabled=False):
+        return _gather_rows(pts.float(), sample_idx), _gather_rows(feats.float(), sample_idx)
+
+
+def gather_pts_feats_wlrf(sample_idx, pts, pts_lrf, feats):
+    """Reference: model_utils.py:196-212."""
+    with torch.autocast(device_type="cuda", enabled=False):
+        return (_gather_rows(pts.float(), sample_idx), _gather_rows(pts_lrf.float(), sample_idx),
+                _gather_rows(feats.float(), sample_idx))
