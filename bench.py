@@ -1,0 +1,426 @@
+#!/usr/bin/env python
+"""bench.py — instances posed / s (and hypotheses scored / s) of the correspondence-and-pose hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
+
+A "step" = one pass of the hot path (unopose_b200.pipeline.run_hot_path) over one batch of B synthetic
+instances per GPU (BASELINE.json configs[1] fine matching + configs[0] coarse solve, with the FPS /
+ball-query / grouping stages of §8(a)).  Instances are independent, so ranks shard them with no
+data-path collective ("scaling": "weak"); the only collective is the final gather of results.
+
+Timing: W warm-up steps, then exactly K steps between (barrier + cuda synchronize), CUDA events on the
+launching stream, MAX over ranks.  Inputs rotate over several resident sets whose total size exceeds
+L2, so no step re-reads its inputs from L2.
+
+`--impl reference`: the reference's CPU implementation of the same step (oracle port on the host
+cores, all threads) on a bounded sample of the workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=16, help="instances per GPU per step (reference instance_batch_size=16)")
+    ap.add_argument("--sets", type=int, default=4, help="resident input sets to rotate over (defeats L2 reuse)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=8, help="instances in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-torch-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tensor_burst=d["bf16_tflops"], tensor_sustained=d["bf16_tflops_sustained"],
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tensor_burst=1590.0, tensor_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [s for s in sm if s > 0.5 * max(sm)]
+        return {"sm_mhz": statistics.median(busy or sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- reference (CPU) arm
+def cpu_leg(cfg, sample_b, steps, warmup):
+    """The reference's CPU path (oracle port) on `sample_b` instances per step; returns (inst/s, hyp/s, info)."""
+    from oracle import hotpath_cpu
+    from oracle import pose_oracle as PO
+    from unopose_b200.pipeline import synthetic_inputs
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    inp = synthetic_inputs(1234, sample_b, cfg, device=None)
+    for _ in range(warmup):
+        hotpath_cpu.run_hot_path_cpu(inp, cfg, threads)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        hotpath_cpu.run_hot_path_cpu(inp, cfg, threads)
+    dt = (time.perf_counter() - t0) / steps
+    # coarse solve alone (hypotheses scored / s)
+    c_atten = PO.feature_similarity(inp["c_f1"], inp["c_f2"], "cosine", cfg.temp, True)
+    t0 = time.perf_counter()
+    for _ in range(max(steps, 2)):
+        PO.coarse_pose(c_atten, inp["c_score"], inp["c_pts1"], inp["c_pts2"], None, cfg.n_proposal1, cfg.n_proposal2)
+    dtc = (time.perf_counter() - t0) / max(steps, 2)
+    return sample_b / dt, sample_b * cfg.n_proposal1 / dtc, dict(threads=threads, ms_per_step=dt * 1e3)
+
+
+def run_reference(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    v, hyp, info = cpu_leg(cfg, args.cpu_sample, steps, warm)
+    sample = "%d instances/step, %d timed steps, full hot path on host cores (torch CPU ops + C oracle)" % (
+        args.cpu_sample, steps)
+    line = {
+        "impl": "reference", "metric": "instances_posed_per_s", "value": v, "unit": "instances/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": info["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(cfg, args.cpu_sample),
+        "hypotheses_scored_per_s": hyp,
+        "cpu_baseline": {"value": v, "unit": "instances/s", "cores": info["threads"], "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "instances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(cfg, batch):
+    return {"workload": "coarse(196x196,C=256,H=%d,K=%d)+fine(2048x2048,C=256)+FPS(5000->2048,2048->196 x2)+"
+                        "ball_query/group(r=.1/64,r=.2/256 x2 clouds)" % (cfg.n_proposal1, cfg.n_proposal2),
+            "instances_per_gpu_per_step": batch, "l2": "inputs rotate over resident sets larger than L2",
+            "parallelism": "instances sharded across ranks (no data-path collective)"}
+
+
+# ----------------------------------------------------------------------------- our arm
+def main():
+    args = parse()
+    from unopose_b200.pipeline import HotPathConfig
+
+    cfg = HotPathConfig()
+    if args.impl == "reference":
+        return run_reference(args, cfg)
+
+    from unopose_b200 import _lib
+    from unopose_b200 import model_utils as MU
+    from unopose_b200.pipeline import input_bytes, run_hot_path, synthetic_inputs, to_device
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=ours) needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+    B = args.batch
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # resident input sets (each rank owns different instances: weak scaling)
+    sets = [synthetic_inputs(1000 * rank + 17 * s, B, cfg, device=dev) for s in range(args.sets)]
+    set_bytes = input_bytes(sets[0])
+    results = []
+
+    def step(i):
+        out = run_hot_path(sets[i % len(sets)], cfg)
+        return out
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.1)
+    launches0 = _lib.launch_count()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        out = step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    launches = _lib.launch_count() - launches0
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    if dist is not None:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        # the path's one collective: gather of per-instance results (R 9, t 3, score 1) on all ranks
+        res = torch.cat([out["pred_R"].reshape(B, 9), out["pred_t"], out["pred_pose_score"].unsqueeze(1)], 1)
+        gathered = [torch.empty_like(res) for _ in range(world)]
+        dist.all_gather(gathered, res)
+    ms_per_step = ms / args.steps
+    value = B * world / (ms_per_step * 1e-3)
+
+    # ---- coarse solve alone: hypotheses scored / s (a2..a6 on resident atten)
+    c_att = [MU.compute_feature_similarity(s["c_f1"], s["c_f2"], "cosine", cfg.temp, True) for s in sets]
+    torch.cuda.synchronize()
+
+    def coarse_only(i):
+        s = sets[i % len(sets)]
+        MU.compute_coarse_Rt_overlap(c_att[i % len(sets)], s["c_score"], s["c_pts1"], s["c_pts2"], None,
+                                     cfg.n_proposal1, cfg.n_proposal2)
+
+    for i in range(3):
+        coarse_only(i)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        coarse_only(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_c = e0.elapsed_time(e1) / args.steps
+    if dist is not None:
+        t = torch.tensor([ms_c], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_c = float(t.item())
+    hyp_per_s = B * world * cfg.n_proposal1 / (ms_c * 1e-3)
+
+    # ---- per-stage device times (events between stages, same stream), rank 0 only reporting
+    stage_ms = {}
+    plan_n = 5
+    for rep in range(plan_n + 1):
+        plan = []
+        run_hot_path(sets[rep % len(sets)], cfg, stages=plan)
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(plan) + 1)]
+        evs[0].record()
+        for k, (name, fn) in enumerate(plan):
+            fn()
+            evs[k + 1].record()
+        torch.cuda.synchronize()
+        if rep == 0:
+            continue
+        for k, (name, _) in enumerate(plan):
+            stage_ms.setdefault(name, []).append(evs[k].elapsed_time(evs[k + 1]))
+    stage_ms = {k: statistics.median(v) for k, v in stage_ms.items()}
+
+    # ---- end to end through the public API with HOST (pinned) buffers: H2D of every step input,
+    #      D2H of the step result, both inside the timed region
+    host_sets = [synthetic_inputs(5000 + 1000 * rank + 17 * s, B, cfg, pin=True) for s in range(2)]
+    res_host = torch.empty((B, 13), dtype=torch.float32).pin_memory()
+
+    def e2e_step(i):
+        d = to_device(host_sets[i % len(host_sets)], dev)
+        o = run_hot_path(d, cfg)
+        r = torch.cat([o["pred_R"].reshape(B, 9), o["pred_t"], o["pred_pose_score"].unsqueeze(1)], 1)
+        res_host.copy_(r, non_blocking=True)
+        torch.cuda.current_stream().synchronize()   # the caller reads the result every step
+        return res_host
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        e2e_step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    ms_e = e0.elapsed_time(e1) / args.steps
+    if dist is not None:
+        t = torch.tensor([ms_e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e = float(t.item())
+    e2e = {"value": B * world / (ms_e * 1e-3), "unit": "instances/s", "h2d_bytes_per_step": input_bytes(host_sets[0]),
+           "d2h_bytes_per_step": res_host.numel() * 4, "ms_per_step": ms_e}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant stage's kernel
+    pk = peaks()
+    total_stage = sum(stage_ms.values())
+    dom = max(stage_ms, key=stage_ms.get)
+    n1 = cfg.n_fine + 1
+    roof_models = {
+        # stage -> (kernel, bound, algorithmic work per launch, unit scale)
+        "fine_similarity": ("k_sgemm_nt<0> (2049x2049x256 per instance)", "tensor", 2.0 * n1 * n1 * cfg.feat_dim * B),
+        "fine_pose": ("assign tile passes (3 reads of the 2049^2 fp32 matrix)", "hbm", 3.0 * n1 * n1 * 4 * B),
+        "fps_template+gather": ("fps_kernel<1024,5> (5000->2048, serial chain)", "hbm",
+                                (12.0 * cfg.n_template + 4.0 * cfg.n_fine) * B),
+        "ball_query+group": ("ball_query_kernel + group_kernel", "hbm",
+                             sum(2 * (12.0 * 2 * cfg.n_fine + 4.0 * cfg.n_fine * ns + 16.0 * cfg.n_fine * ns)
+                                 for _, ns in cfg.pe) * B),
+        "coarse_pose": ("k_score (K x 196 x 196 pairs, 6 lane-ops each)", "fp32",
+                        6.0 * cfg.n_proposal2 * cfg.n_coarse * cfg.n_coarse * B),
+    }
+    kname, bound, work = roof_models.get(dom, (dom, "hbm", float(set_bytes)))
+    dur_s = stage_ms[dom] * 1e-3
+    if bound == "tensor":
+        achieved, peak, unit = work / dur_s / 1e12, pk["tensor_sustained"], "TFLOP/s"
+    elif bound == "fp32":
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        achieved, peak, unit = work / dur_s / 1e12, sms * 128 * 1.965e9 / 1e12, "Tlane-op/s"
+    else:
+        achieved, peak, unit = work / dur_s / 1e9, pk["hbm"], "GB/s"
+    roofline = {"kernel": kname, "stage": dom, "stage_share_of_step": stage_ms[dom] / total_stage,
+                "bound": "tensor" if bound == "tensor" else "hbm" if bound == "hbm" else "fp32-issue",
+                "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak, "traffic": None,
+                "peak_source": pk["source"], "duration_ms": stage_ms[dom]}
+
+    line = {
+        "metric": "instances_posed_per_s", "value": value, "unit": "instances/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(cfg, B),
+        "hypotheses_scored_per_s": hyp_per_s, "coarse_solve_ms": ms_c,
+        "stage_ms": stage_ms,
+        "roofline": roofline,
+        "e2e": e2e,
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "resident_input_bytes": set_bytes * len(sets),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        v, hyp, info = cpu_leg(cfg, args.cpu_sample, 3, 1)
+        line["cpu_baseline"] = {"value": v, "unit": "instances/s", "cores": info["threads"], "kind": "port",
+                                "sample": "%d instances/step x 3 steps of the same workload (oracle port: torch CPU "
+                                          "ops + C restatement of the pointnet2 kernels)" % args.cpu_sample,
+                                "hypotheses_scored_per_s": hyp}
+    if world == 1 and not args.no_gpu_torch_baseline:
+        try:
+            line["gpu_torch_baseline"] = gpu_torch_leg(cfg, sets, B, dev)
+        except Exception as ex:  # reported, never fatal
+            line["gpu_torch_baseline"] = {"unavailable": repr(ex)[:200]}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def gpu_torch_leg(cfg, sets, B, dev):
+    """The reference's GPU path on the same box and inputs: its torch ops (oracle port on CUDA tensors)
+    plus its own pointnet2 extension compiled unmodified (oracle/_ref) — the ">= 10x" denominator of
+    BASELINE.json.  Reported baseline only."""
+    from oracle import pose_oracle as PO
+    from oracle import ref_ext
+
+    ext = ref_ext.load()
+    if ext is None:
+        return {"unavailable": "oracle/_ref/ref_pointnet2_ext.so not present"}
+
+    def sample(pts, feats, m):
+        idx = ext.furthest_point_sampling(pts.contiguous(), m)
+        p = ext.gather_points(pts.transpose(1, 2).contiguous(), idx).transpose(1, 2).contiguous()
+        f = ext.gather_points(feats.transpose(1, 2).contiguous(), idx).transpose(1, 2).contiguous()
+        return p, f
+
+    def ref_step(s):
+        tem_sub, tem_f = sample(s["tem_pts"], s["tem_feats"], cfg.n_fine)
+        sample(s["pts"], s["pts_feats"], cfg.n_coarse)
+        sample(tem_sub, tem_f, cfg.n_coarse)
+        ca = PO.feature_similarity(s["c_f1"], s["c_f2"], "cosine", cfg.temp, True)
+        PO.coarse_pose(ca, s["c_score"], s["c_pts1"], s["c_pts2"], None, cfg.n_proposal1, cfg.n_proposal2)
+        for cloud in (s["pts"], tem_sub):
+            cf = cloud.transpose(1, 2).contiguous()
+            for r, ns in cfg.pe:
+                ext.group_points(cf, ext.ball_query(cloud, cloud, r, ns))
+        fa = PO.feature_similarity(s["f_f1"], s["f_f2"], "cosine", cfg.temp, True)
+        return PO.fine_pose(fa, s["f_score"], s["f_pts1"], s["f_pts2"], None, cfg.dis_thres)
+
+    for i in range(2):
+        ref_step(sets[i % len(sets)])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 5
+    e0.record()
+    for i in range(n):
+        ref_step(sets[i % len(sets)])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    # coarse solve alone
+    ca = PO.feature_similarity(sets[0]["c_f1"], sets[0]["c_f2"], "cosine", cfg.temp, True)
+    s = sets[0]
+    e0.record()
+    for i in range(n):
+        PO.coarse_pose(ca, s["c_score"], s["c_pts1"], s["c_pts2"], None, cfg.n_proposal1, cfg.n_proposal2)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_c = e0.elapsed_time(e1) / n
+    return {"value": B / (ms * 1e-3), "unit": "instances/s", "ms_per_step": ms, "kind": "port+reference_ext",
+            "hypotheses_scored_per_s": B * cfg.n_proposal1 / (ms_c * 1e-3),
+            "what": "reference torch-op sequence on CUDA tensors + reference pointnet2 _ext (unmodified, sm_100a)"}
+
+
+if __name__ == "__main__":
+    sys.exit(main())

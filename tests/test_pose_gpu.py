@@ -101,7 +101,9 @@ def test_coarse_stagewise(cuda, seed, n, H, K):
     M = d["pts2"].unsqueeze(1).repeat(1, K, 1, 1).reshape(B * K, -1, 3)
     nn = torch.sqrt(PO.pairwise_sqdist(X, M)).min(2)[0].reshape(B, K, -1)
     sc = m["w1"].unsqueeze(1).sum(2) / ((nn * m["w1"].unsqueeze(1)).sum(2) + 1e-8)
-    assert torch.allclose(m["scores"], sc, rtol=2e-4)
+    # expansion-form distances cancel: |x|^2 - 2x.y + |y|^2 carries ~1e-7 absolute error on a d^2 of
+    # ~1e-4, i.e. up to ~1e-3 relative on a score, whatever the summation order (cuBLAS vs fused FMA)
+    assert torch.allclose(m["scores"], sc, rtol=1e-3)
     # a6: selection bit-exact given MY scores
     best = m["scores"].max(1)[1]
     assert torch.equal(m["pool"].long(), torch.gather(top, 1, best.unsqueeze(1)).squeeze(1))

@@ -397,7 +397,7 @@ static int stats_labels_t(const float* atten, const float* score1, int ld1, cons
   const size_t smem = (size_t)TR * TC * sizeof(float);
   auto k1 = k_stats_tile<TR, TC>;
   auto k2 = k_labels_tile<TR, TC>;
-  if (smem + sizeof(TileConsts<TR, TC>) > 48 * 1024) {
+  if (smem + sizeof(TileConsts<TR, TC>) > 40 * 1024) {
     UPK_CUDA_TRY(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     UPK_CUDA_TRY(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
@@ -426,7 +426,7 @@ static int coarse_P_t(const float* atten, const float* score1, int ld1, const fl
                       float* pmat, double* prow, cudaStream_t st) {
   const size_t smem = (size_t)TR * TC * sizeof(float);
   auto k = k_coarse_P_tile<TR, TC>;
-  if (smem + sizeof(TileConsts<TR, TC>) > 48 * 1024)
+  if (smem + sizeof(TileConsts<TR, TC>) > 40 * 1024)
     UPK_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(g.ntc, g.ntr, b);
   k<<<grid, AT, smem, st>>>(atten, g.R, g.C, g.ntc, ws.rmax, ws.rsum, ws.cmax, ws.csum, score1, ld1,
@@ -445,7 +445,7 @@ int run_coarse_P(const float* atten, const float* score1, int ld1, const float* 
 int run_cdf(const float* pmat, const double* prow, int b, int n1, int n2, int ntc, float* cdf,
             cudaStream_t st) {
   size_t smem = (size_t)n1 * sizeof(double);
-  if (smem > 48 * 1024)
+  if (smem > 40 * 1024)
     UPK_CUDA_TRY(cudaFuncSetAttribute(k_cdf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(ceil_div(n1, CDF_ROWS), b);
   k_cdf<<<grid, CDF_ROWS * 32, smem, st>>>(pmat, prow, n1, n2, ntc, cdf);
@@ -459,7 +459,7 @@ static int fine_rows_t(const float* atten, const float* score1, int ld1, const f
                        const float* pts2, float4* rowpart4, float* soft, float* asum, cudaStream_t st) {
   const size_t smem = (size_t)TR * TC * sizeof(float);
   auto k = k_fine_rows_tile<TR, TC>;
-  if (smem + sizeof(TileConsts<TR, TC>) + TC * 16 > 48 * 1024)
+  if (smem + sizeof(TileConsts<TR, TC>) + TC * 16 > 40 * 1024)
     UPK_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(g.ntc, g.ntr, b);
   k<<<grid, AT, smem, st>>>(atten, g.R, g.C, g.ntc, ws.rmax, ws.rsum, ws.cmax, ws.csum, score1, ld1,

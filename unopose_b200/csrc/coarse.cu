@@ -364,7 +364,7 @@ static int launch_score(const float* pts1, const float* model, const float* w1, 
   if (k1 <= k0) return UPK_OK;
   size_t smem = (size_t)nm * sizeof(float4);
   if (smem > 200 * 1024) return UPK_ERR_UNSUPPORTED;
-  if (smem > 48 * 1024)
+  if (smem > 40 * 1024)
     UPK_CUDA_TRY(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(k1 - k0, b);
   k_score<<<grid, SC_THREADS, smem, st>>>(pts1, model, w1, Rs, ts, top, n1, nm, H, K, k0, scores);

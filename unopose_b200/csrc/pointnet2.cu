@@ -168,7 +168,7 @@ static int launch_fps(const float* xyz, int b, int n, int m, int bs_log2, int* o
                       cudaStream_t st) {
   size_t smem = (size_t)n * 3 * sizeof(float);
   auto kern = fps_kernel<THREADS, PPT>;
-  if (smem > 48 * 1024) {
+  if (smem > 40 * 1024) {  // dynamic + the 512 B of static smem must stay within the default 48 KB
     UPK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   kern<<<b, THREADS, smem, st>>>(xyz, n, m, bs_log2, out);
@@ -448,7 +448,7 @@ int upk_furthest_point_sampling(const float* xyz, int b, int n, int m, int* idx_
   if (n <= 4096) return launch_fps<1024, 4>(xyz, b, n, m, bs_log2, idx_out, st);
   if (n <= 5120) return launch_fps<1024, 5>(xyz, b, n, m, bs_log2, idx_out, st);
   if (n <= 8192) return launch_fps<512, 16>(xyz, b, n, m, bs_log2, idx_out, st);
-  if (n <= 12288) return launch_fps<256, 48>(xyz, b, n, m, bs_log2, idx_out, st);
+  if (n <= 12288) return launch_fps<512, 24>(xyz, b, n, m, bs_log2, idx_out, st);
   size_t smem = (size_t)n * sizeof(float);
   if (smem > 200 * 1024) return UPK_ERR_UNSUPPORTED;
   auto kern = fps_kernel_large<1024>;

@@ -1,0 +1,123 @@
+"""One pass of the correspondence-and-pose hot path over a batch of instances.
+
+This is the call a user of the package makes when the ViT / transformer layers around the
+path are somebody else's (they are out of scope here): given, per instance,
+
+    tem_pts   (B,5000,3)   template cloud              tem_feats (B,5000,C)  its per-point features
+    pts       (B,2048,3)   observed (query) cloud      pts_feats (B,2048,C)
+    c_pts1/2  (B,196,3)    sparse query / reference    c_f1/2    (B,197,C)   coarse matching features
+    f_pts1/2  (B,2048,3)   dense query / reference     f_f1/2    (B,2049,C)  fine matching features
+    c_score   (B,392)      f_score (B,4096)            overlap scores
+
+it runs, in the reference's order (UNOPose.forward):
+  a15  sample_pts_feats(tem_pts, tem_feats, 2048)            FPS 5000->2048 + gathers
+  a15  sample_pts_feats(pts / template subset, 196) x2       FPS 2048->196 + gathers
+  a1   compute_feature_similarity(c_f1, c_f2)                197 x 197
+  a7   compute_coarse_Rt_overlap(...)                        H hypotheses, K kept
+  a12/a13  ball_query + grouping (r=.1,ns=64),(r=.2,ns=256) on both dense clouds  (PositionalEncoding geometry)
+  a1   compute_feature_similarity(f_f1, f_f2)                2049 x 2049
+  a8   compute_fine_Rt_overlap(...)
+and returns pred_R (B,3,3), pred_t (B,3), pred_pose_score (B,), init_R, init_t, init_pose_score.
+
+Every stage is one of the package's drop-in functions, i.e. sm_100a kernels behind the C ABI.
+"""
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import model_utils as MU
+from .pointnet2 import pointnet2_utils as P
+from .synthetic import batch_clouds, matching_batch
+
+
+@dataclass
+class HotPathConfig:
+    n_template: int = 5000       # n_sample_template_point  (configs/main_cfg.py:215)
+    n_fine: int = 2048           # fine_npoint              (:131)
+    n_coarse: int = 196          # coarse_npoint            (:130)
+    feat_dim: int = 256
+    temp: float = 0.1
+    n_proposal1: int = 5000      # BASELINE.json config 1 (the reference cfg uses 6000, main_cfg.py:160)
+    n_proposal2: int = 300
+    pe: tuple = ((0.1, 64), (0.2, 256))   # (radius, nsample) of the two PositionalEncoding scales (:167-178)
+    dis_thres: float = 0.15
+
+
+def synthetic_inputs(seed, batch, cfg=HotPathConfig(), device=None, pin=False):
+    """Seeded synthetic instance batch of the reference's shapes (numpy -> torch)."""
+    fine = matching_batch(seed, batch, cfg.n_fine, cfg.feat_dim)
+    coarse = matching_batch(seed + 1, batch, cfg.n_coarse, cfg.feat_dim, kind="ball")
+    rng = np.random.default_rng(seed + 2)
+    d = dict(
+        tem_pts=batch_clouds(seed + 3, batch, cfg.n_template, "surface"),
+        tem_feats=rng.standard_normal((batch, cfg.n_template, cfg.feat_dim), dtype=np.float32),
+        pts=fine["pts1"], pts_feats=rng.standard_normal((batch, cfg.n_fine, cfg.feat_dim), dtype=np.float32),
+        c_pts1=coarse["pts1"], c_pts2=coarse["pts2"], c_f1=coarse["f1"], c_f2=coarse["f2"], c_score=coarse["score"],
+        f_pts1=fine["pts1"], f_pts2=fine["pts2"], f_f1=fine["f1"], f_f2=fine["f2"], f_score=fine["score"],
+    )
+    out = {}
+    for k, v in d.items():
+        t = torch.from_numpy(np.ascontiguousarray(v))
+        if pin:
+            t = t.pin_memory()
+        elif device is not None:
+            t = t.to(device)
+        out[k] = t
+    out["_gt_R"] = torch.from_numpy(fine["R"])
+    out["_gt_t"] = torch.from_numpy(fine["t"])
+    return out
+
+
+def input_bytes(inp):
+    return int(sum(v.numel() * v.element_size() for k, v in inp.items() if not k.startswith("_")))
+
+
+def to_device(inp, device, non_blocking=True):
+    return {k: (v.to(device, non_blocking=non_blocking) if not k.startswith("_") else v) for k, v in inp.items()}
+
+
+def run_hot_path(inp, cfg=HotPathConfig(), stages=None):
+    """One step.  `inp` holds CUDA tensors (see module docstring).  `stages` optionally receives
+    a list of (name, callable) instead of executing, for per-stage timing."""
+    out = {}
+
+    def s_template():
+        out["tem_sub"], out["tem_sub_feats"], out["tem_idx"] = MU.sample_pts_feats(
+            inp["tem_pts"], inp["tem_feats"], cfg.n_fine, return_index=True)
+
+    def s_sparse():
+        out["sp1"], out["sf1"], out["fps_idx1"] = MU.sample_pts_feats(inp["pts"], inp["pts_feats"], cfg.n_coarse, True)
+        out["sp2"], out["sf2"], out["fps_idx2"] = MU.sample_pts_feats(out["tem_sub"], out["tem_sub_feats"],
+                                                                      cfg.n_coarse, True)
+
+    def s_coarse_sim():
+        out["c_atten"] = MU.compute_feature_similarity(inp["c_f1"], inp["c_f2"], "cosine", cfg.temp, True)
+
+    def s_coarse_pose():
+        out["init_R"], out["init_t"], out["init_pose_score"] = MU.compute_coarse_Rt_overlap(
+            out["c_atten"], inp["c_score"], inp["c_pts1"], inp["c_pts2"], None, cfg.n_proposal1, cfg.n_proposal2)
+
+    def s_pe_geometry():
+        for name, cloud in (("q", inp["pts"]), ("r", out["tem_sub"])):
+            cf = cloud.transpose(1, 2).contiguous()
+            for i, (r, ns) in enumerate(cfg.pe):
+                idx = P.ball_query(r, ns, cloud, cloud)
+                out["pe_%s%d" % (name, i)] = P.grouping_operation(cf, idx)
+
+    def s_fine_sim():
+        out["f_atten"] = MU.compute_feature_similarity(inp["f_f1"], inp["f_f2"], "cosine", cfg.temp, True)
+
+    def s_fine_pose():
+        out["pred_R"], out["pred_t"], out["pred_pose_score"] = MU.compute_fine_Rt_overlap(
+            out["f_atten"], inp["f_score"], inp["f_pts1"], inp["f_pts2"], None, cfg.dis_thres)
+
+    plan = [("fps_template+gather", s_template), ("fps_sparse+gather", s_sparse), ("coarse_similarity", s_coarse_sim),
+            ("coarse_pose", s_coarse_pose), ("ball_query+group", s_pe_geometry), ("fine_similarity", s_fine_sim),
+            ("fine_pose", s_fine_pose)]
+    if stages is not None:
+        stages.extend(plan)
+        return out
+    for _, fn in plan:
+        fn()
+    return out
