@@ -315,11 +315,11 @@ def main():
         # stage -> (kernel, bound, algorithmic work per launch, unit scale)
         "fine_similarity": ("k_sgemm_nt<0> (2049x2049x256 per instance)", "tensor", 2.0 * n1 * n1 * cfg.feat_dim * B),
         "fine_pose": ("assign tile passes (3 reads of the 2049^2 fp32 matrix)", "hbm", 3.0 * n1 * n1 * 4 * B),
-        "fps_template+gather": ("fps_kernel<1024,5> (5000->2048, serial chain)", "hbm",
+        "fps_template+gather": ("fps_kernel<512,10> (5000->2048, serial chain)", "hbm",
                                 (12.0 * cfg.n_template + 4.0 * cfg.n_fine) * B),
-        "ball_query+group": ("ball_query_kernel + group_kernel", "hbm",
-                             sum(2 * (12.0 * 2 * cfg.n_fine + 4.0 * cfg.n_fine * ns + 16.0 * cfg.n_fine * ns)
-                                 for _, ns in cfg.pe) * B),
+        "ball_query+group_query": ("ball_query_kernel + group_kernel", "hbm",
+                                   sum((12.0 * 2 * cfg.n_fine + 4.0 * cfg.n_fine * ns + 16.0 * cfg.n_fine * ns)
+                                       for _, ns in cfg.pe) * B),
         "coarse_pose": ("k_score (K x 196 x 196 pairs, 6 lane-ops each)", "fp32",
                         6.0 * cfg.n_proposal2 * cfg.n_coarse * cfg.n_coarse * B),
     }

@@ -82,6 +82,14 @@ int upk_group_points_grad(const float* grad_out, const int* idx, int b, int c,
                           int n, int npoints, int nsample, float* grad_points,
                           upk_stream_t stream);
 
+/* Row gather, channel-last: x[b,n,c], idx[b,m] -> out[b,m,c] (and its scatter-add gradient).
+ * Replaces the transpose -> _ext.gather_points -> transpose sequences of
+ * sample_pts_feats / sample_pts_feats_wlrf / gather_pts_feats* (model_utils.py:137-212). */
+int upk_gather_rows(const float* x, const int* idx, int b, int n, int m, int c, float* out,
+                    upk_stream_t stream);
+int upk_gather_rows_grad(const float* grad_out, const int* idx, int b, int n, int m, int c,
+                         float* grad_x, upk_stream_t stream);
+
 /* three_nn(unknown[b,n,3], known[b,m,3]) -> dist2[b,n,3], idx[b,n,3]
  * replaces _ext.three_nn (interpolate.cpp:19-45, interpolate_gpu.cu:14-73).
  * dist2 is the SQUARED distance (the Python wrapper takes the sqrt). */

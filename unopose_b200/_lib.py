@@ -30,6 +30,8 @@ _SIGNATURES = {
     "upk_ball_query": [c_f, c_f, c_i, c_i, c_i, c_fl, c_i, c_f, c_st],
     "upk_group_points": [c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_f, c_st],
     "upk_group_points_grad": [c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_f, c_st],
+    "upk_gather_rows": [c_f, c_f, c_i, c_i, c_i, c_i, c_f, c_st],
+    "upk_gather_rows_grad": [c_f, c_f, c_i, c_i, c_i, c_i, c_f, c_st],
     "upk_three_nn": [c_f, c_f, c_i, c_i, c_i, c_f, c_f, c_st],
     "upk_three_interpolate": [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_f, c_st],
     "upk_three_interpolate_grad": [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_f, c_st],

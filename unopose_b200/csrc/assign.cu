@@ -21,6 +21,18 @@ namespace upk {
 
 constexpr int AT = 256;  // threads per CTA in every tile kernel
 
+// Arithmetic mode per tile shape.  The small tiles (coarse, 197x197: the sampling CDF is built
+// from these values and index parity is judged on it) use expf() and IEEE division exactly as
+// torch.softmax does.  The large tiles (fine, 2049x2049: HBM-bound, only the R/t tolerance
+// applies) use ex2.approx-based __expf and multiply by one reciprocal per row / column: the
+// relative error of __expf grows as |x|*2^-24 with x = v - max <= 0, i.e. it is largest on the
+// entries whose weight exp(x) is smallest.
+template <int TR>
+struct TileMath {
+  static constexpr bool kFast = TR >= 64;
+  static __device__ __forceinline__ float ex(float x) { return kFast ? __expf(x) : expf(x); }
+};
+
 AssignGeom assign_geom(int R, int C) {
   AssignGeom g;
   g.R = R;
@@ -76,7 +88,7 @@ k_stats_tile(const float* __restrict__ atten, int R, int C, int ntr, int ntc,
     for (int c = lane; c < nc; c += 32) m = fmaxf(m, row[c]);
     m = warp_max(m);
     float s = 0.f;
-    for (int c = lane; c < nc; c += 32) s += expf(row[c] - m);
+    for (int c = lane; c < nc; c += 32) s += TileMath<TR>::ex(row[c] - m);
     s = warp_sum(s);
     if (lane == 0) rowpart[((size_t)b * R + r0 + r) * ntc + tc] = make_float2(m, s);
   }
@@ -84,7 +96,7 @@ k_stats_tile(const float* __restrict__ atten, int R, int C, int ntr, int ntc,
     float m = -INFINITY;
     for (int r = 0; r < nr; ++r) m = fmaxf(m, tile[r * TC + c]);
     float s = 0.f;
-    for (int r = 0; r < nr; ++r) s += expf(tile[r * TC + c] - m);
+    for (int r = 0; r < nr; ++r) s += TileMath<TR>::ex(tile[r * TC + c] - m);
     colpart[((size_t)b * C + c0 + c) * ntr + tr] = make_float2(m, s);
   }
 }
@@ -130,7 +142,8 @@ __device__ __forceinline__ void load_consts(TileConsts<TR, TC>& k, int b, int R,
     int gi = r0 + r;
     bool ok = r < nr;
     k.rm[r] = ok ? rmax[(size_t)b * R + gi] : 0.f;
-    k.rs[r] = ok ? rsum[(size_t)b * R + gi] : 1.f;
+    float rs = ok ? rsum[(size_t)b * R + gi] : 1.f;
+    k.rs[r] = TileMath<TR>::kFast ? 1.f / rs : rs;  // fast mode keeps the reciprocal
     // background row/col carry score 1.0 (model_utils.py:443-445)
     k.s1[r] = (ok && gi > 0 && score1) ? score1[(size_t)b * ld1 + gi - 1] : 1.f;
   }
@@ -138,7 +151,8 @@ __device__ __forceinline__ void load_consts(TileConsts<TR, TC>& k, int b, int R,
     int gj = c0 + c;
     bool ok = c < nc;
     k.cm[c] = ok ? cmax[(size_t)b * C + gj] : 0.f;
-    k.cs[c] = ok ? csum[(size_t)b * C + gj] : 1.f;
+    float cs = ok ? csum[(size_t)b * C + gj] : 1.f;
+    k.cs[c] = TileMath<TR>::kFast ? 1.f / cs : cs;
     k.s2[c] = (ok && gj > 0 && score2) ? score2[(size_t)b * ld2 + gj - 1] : 1.f;
   }
 }
@@ -151,8 +165,14 @@ __device__ __forceinline__ void compute_A_inplace(float* tile, const TileConsts<
     float a = 0.f;
     if (c < nc) {
       float v = tile[i];
-      float er = expf(v - k.rm[r]) / k.rs[r];
-      float ec = expf(v - k.cm[c]) / k.cs[c];
+      float er, ec;
+      if (TileMath<TR>::kFast) {
+        er = __expf(v - k.rm[r]) * k.rs[r];
+        ec = __expf(v - k.cm[c]) * k.cs[c];
+      } else {
+        er = expf(v - k.rm[r]) / k.rs[r];
+        ec = expf(v - k.cm[c]) / k.cs[c];
+      }
       a = ((er * ec) * k.s1[r]) * k.s2[c];
     }
     tile[i] = a;
@@ -389,6 +409,252 @@ k_fine_rows_merge(const float4* __restrict__ rowpart4, const float* __restrict__
   asum[(size_t)b * n1 + i] = sw;
 }
 
+// ====================================================================================
+// Register-streaming variants for the LARGE geometry (fine stage, 2049 x 2049 per instance).
+// The tile kernels above stage a tile in shared memory and spend ~60 issue slots per element
+// (ncu: issue-bound at 12-15 % of HBM bandwidth).  Here a CTA of 8 warps owns a 64-row x
+// 256-column tile; a warp streams whole 256-column row segments straight from global memory
+// into registers (lane l owns columns l, l+32, ..., l+224: every load instruction is one
+// coalesced 128-byte line), two rows (16 independent loads per thread) in flight.  Per-column
+// constants live in registers for the whole tile, per-row constants are two broadcast loads.
+// Row results need one warp reduction per row, column results one shared-memory combine per
+// tile.  ~10-15 issue slots per element, so the passes become HBM-bound.
+// Same partial-buffer layout as the tile kernels (TR = 64, TC = 256), same merge kernels.
+// ====================================================================================
+constexpr int ST_TR = 64, ST_TC = 256, ST_CPT = 8, ST_WARPS = 8;
+constexpr float kLog2e = 1.4426950408889634f;
+
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// pass 1: (max, sum exp) partials per row (exact two-step per row) and per column (online)
+__global__ void __launch_bounds__(ST_WARPS * 32)
+k_stats_stream(const float* __restrict__ atten, int R, int C, int ntr, int ntc,
+               float2* __restrict__ rowpart, float2* __restrict__ colpart) {
+  __shared__ float2 s_col[ST_WARPS][ST_TC];
+  const int b = blockIdx.z, tr = blockIdx.y, tc = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r0 = tr * ST_TR, c0 = tc * ST_TC;
+  const float* A = atten + (size_t)b * R * C;
+  float cm[ST_CPT], cs[ST_CPT];
+  bool cok[ST_CPT];
+#pragma unroll
+  for (int k = 0; k < ST_CPT; ++k) {
+    cm[k] = -INFINITY;
+    cs[k] = 0.f;
+    cok[k] = c0 + lane + 32 * k < C;
+  }
+  for (int rr = warp; rr < ST_TR; rr += 2 * ST_WARPS) {
+    const int ga = r0 + rr, gb = ga + ST_WARPS;
+    if (ga >= R) break;
+    const bool hasb = gb < R;
+    float va[ST_CPT], vb[ST_CPT];
+#pragma unroll
+    for (int k = 0; k < ST_CPT; ++k) {
+      va[k] = cok[k] ? __ldg(A + (size_t)ga * C + c0 + lane + 32 * k) : -INFINITY;
+      vb[k] = (cok[k] && hasb) ? __ldg(A + (size_t)gb * C + c0 + lane + 32 * k) : -INFINITY;
+    }
+    float ma = va[0], mb = vb[0];
+#pragma unroll
+    for (int k = 1; k < ST_CPT; ++k) { ma = fmaxf(ma, va[k]); mb = fmaxf(mb, vb[k]); }
+    ma = warp_max(ma);
+    mb = warp_max(mb);
+    const float mal = ma * kLog2e, mbl = mb * kLog2e;
+    float sa = 0.f, sb = 0.f;
+#pragma unroll
+    for (int k = 0; k < ST_CPT; ++k) {
+      sa += ex2_fast(fmaf(va[k], kLog2e, -mal));
+      sb += ex2_fast(fmaf(vb[k], kLog2e, -mbl));
+      // online column update with both rows
+      float mn = fmaxf(cm[k], fmaxf(va[k], vb[k]));
+      float mnl = mn * kLog2e;
+      cs[k] = cs[k] * ex2_fast(fmaf(cm[k], kLog2e, -mnl)) + ex2_fast(fmaf(va[k], kLog2e, -mnl)) +
+              ex2_fast(fmaf(vb[k], kLog2e, -mnl));
+      cm[k] = mn;
+    }
+    sa = warp_sum(sa);
+    sb = warp_sum(sb);
+    if (lane == 0) {
+      rowpart[((size_t)b * R + ga) * ntc + tc] = make_float2(ma, sa);
+      if (hasb) rowpart[((size_t)b * R + gb) * ntc + tc] = make_float2(mb, sb);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < ST_CPT; ++k) s_col[warp][lane + 32 * k] = make_float2(cm[k], cs[k]);
+  __syncthreads();
+  const int c = threadIdx.x;
+  if (c0 + c < C) {
+    float m = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < ST_WARPS; ++w) m = fmaxf(m, s_col[w][c].x);
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < ST_WARPS; ++w) {
+      float2 p = s_col[w][c];
+      sum += p.x == -INFINITY ? 0.f : p.y * ex2_fast((p.x - m) * kLog2e);
+    }
+    colpart[((size_t)b * C + c0 + c) * ntr + tr] = make_float2(m, sum);
+  }
+}
+
+// Per-thread column constants of the streaming label / row-sum passes:
+//   A_ij = exp(v - rm_i)/rs_i * exp(v - cm_j)/cs_j * s1_i * s2_j
+//        = ex2( v*2log2e - (rm_i + cm_j) log2e ) * (s1_i / rs_i) * (s2_j / cs_j)
+struct ColConst {
+  float cml[ST_CPT];   // cm_j * log2e   (+inf for out-of-range columns -> A = 0)
+  float cmul[ST_CPT];  // s2_j / cs_j
+};
+
+__device__ __forceinline__ void load_col_consts(ColConst& k, int b, int C, int c0, int lane,
+                                                const float* __restrict__ cmax, const float* __restrict__ csum,
+                                                const float* __restrict__ score2, int ld2) {
+#pragma unroll
+  for (int q = 0; q < ST_CPT; ++q) {
+    int gj = c0 + lane + 32 * q;
+    bool ok = gj < C;
+    float cm = ok ? cmax[(size_t)b * C + gj] : INFINITY;
+    float cs = ok ? csum[(size_t)b * C + gj] : 1.f;
+    float s2 = (ok && gj > 0 && score2) ? score2[(size_t)b * ld2 + gj - 1] : 1.f;
+    k.cml[q] = cm * kLog2e;
+    k.cmul[q] = ok ? s2 / cs : 0.f;
+  }
+}
+
+// pass 2: background-vs-foreground arg-max tests (see k_labels_tile)
+__global__ void __launch_bounds__(ST_WARPS * 32)
+k_labels_stream(const float* __restrict__ atten, int R, int C, int ntr, int ntc,
+                const float* __restrict__ rmax, const float* __restrict__ rsum,
+                const float* __restrict__ cmax, const float* __restrict__ csum,
+                const float* __restrict__ score1, int ld1, const float* __restrict__ score2, int ld2,
+                float* __restrict__ rowpm, float* __restrict__ colpm, float* __restrict__ ai0,
+                float* __restrict__ a0j) {
+  __shared__ float s_col[ST_WARPS][ST_TC];
+  const int b = blockIdx.z, tr = blockIdx.y, tc = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r0 = tr * ST_TR, c0 = tc * ST_TC;
+  const float* A = atten + (size_t)b * R * C;
+  ColConst kc;
+  load_col_consts(kc, b, C, c0, lane, cmax, csum, score2, ld2);
+  float cmx[ST_CPT];
+#pragma unroll
+  for (int k = 0; k < ST_CPT; ++k) cmx[k] = -INFINITY;
+  const bool first_col_mine = (c0 == 0 && lane == 0);  // global column 0 == my k = 0
+  for (int rr = warp; rr < ST_TR; rr += 2 * ST_WARPS) {
+    const int ga = r0 + rr, gb = ga + ST_WARPS;
+    if (ga >= R) break;
+    const bool hasb = gb < R;
+    float va[ST_CPT], vb[ST_CPT];
+#pragma unroll
+    for (int k = 0; k < ST_CPT; ++k) {
+      bool ok = c0 + lane + 32 * k < C;
+      va[k] = ok ? __ldg(A + (size_t)ga * C + c0 + lane + 32 * k) : 0.f;
+      vb[k] = (ok && hasb) ? __ldg(A + (size_t)gb * C + c0 + lane + 32 * k) : 0.f;
+    }
+    const int gbb = hasb ? gb : ga;
+    const float rmla = rmax[(size_t)b * R + ga] * kLog2e, rmlb = rmax[(size_t)b * R + gbb] * kLog2e;
+    const float s1a = (ga > 0 && score1) ? score1[(size_t)b * ld1 + ga - 1] : 1.f;
+    const float s1b = (gbb > 0 && score1) ? score1[(size_t)b * ld1 + gbb - 1] : 1.f;
+    const float rmula = s1a / rsum[(size_t)b * R + ga], rmulb = s1b / rsum[(size_t)b * R + gbb];
+    float ra = -INFINITY, rb = -INFINITY, a0 = 0.f, b0 = 0.f;
+#pragma unroll
+    for (int k = 0; k < ST_CPT; ++k) {
+      float aa = (ex2_fast(fmaf(va[k], 2.f * kLog2e, -(rmla + kc.cml[k]))) * rmula) * kc.cmul[k];
+      float ab = (ex2_fast(fmaf(vb[k], 2.f * kLog2e, -(rmlb + kc.cml[k]))) * rmulb) * kc.cmul[k];
+      if (k == 0 && first_col_mine) {
+        a0 = aa; b0 = ab;            // background column: excluded from the row max
+      } else {
+        ra = fmaxf(ra, aa);
+        rb = fmaxf(rb, ab);
+      }
+      // column max over rows >= 1 ; row 0 is the background row
+      if (ga > 0) cmx[k] = fmaxf(cmx[k], aa); else if (c0 + lane + 32 * k < C) a0j[(size_t)b * C + c0 + lane + 32 * k] = aa;
+      if (hasb) cmx[k] = fmaxf(cmx[k], ab);
+    }
+    ra = warp_max(ra);
+    rb = warp_max(rb);
+    if (lane == 0) {
+      rowpm[((size_t)b * R + ga) * ntc + tc] = ra;
+      if (hasb) rowpm[((size_t)b * R + gb) * ntc + tc] = rb;
+      if (c0 == 0) {
+        ai0[(size_t)b * R + ga] = a0;
+        if (hasb) ai0[(size_t)b * R + gb] = b0;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < ST_CPT; ++k) s_col[warp][lane + 32 * k] = cmx[k];
+  __syncthreads();
+  const int c = threadIdx.x;
+  if (c0 + c < C) {
+    float m = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < ST_WARPS; ++w) m = fmaxf(m, s_col[w][c]);
+    colpm[((size_t)b * C + c0 + c) * ntr + tr] = m;
+  }
+}
+
+// pass 3 (fine): per row  sum_{j>=1} A_ij w2_j {x_j, y_j, z_j, 1}
+__global__ void __launch_bounds__(ST_WARPS * 32)
+k_fine_rows_stream(const float* __restrict__ atten, int R, int C, int ntc,
+                   const float* __restrict__ rmax, const float* __restrict__ rsum,
+                   const float* __restrict__ cmax, const float* __restrict__ csum,
+                   const float* __restrict__ score1, int ld1, const float* __restrict__ score2, int ld2,
+                   const float* __restrict__ w2, const float* __restrict__ pts2,
+                   float4* __restrict__ rowpart4) {
+  const int b = blockIdx.z, tr = blockIdx.y, tc = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r0 = tr * ST_TR, c0 = tc * ST_TC;
+  const int N1 = R - 1, N2 = C - 1;
+  const float* A = atten + (size_t)b * R * C;
+  ColConst kc;
+  load_col_consts(kc, b, C, c0, lane, cmax, csum, score2, ld2);
+  float px[ST_CPT], py[ST_CPT], pz[ST_CPT];
+#pragma unroll
+  for (int k = 0; k < ST_CPT; ++k) {
+    int gj = c0 + lane + 32 * k;
+    bool ok = gj < C && gj > 0;
+    const float* p = pts2 + ((size_t)b * N2 + (ok ? gj - 1 : 0)) * 3;
+    px[k] = p[0]; py[k] = p[1]; pz[k] = p[2];
+    kc.cmul[k] = ok ? kc.cmul[k] * w2[(size_t)b * N2 + gj - 1] : 0.f;  // fold the column mask, drop the bg column
+  }
+  for (int rr = warp; rr < ST_TR; rr += 2 * ST_WARPS) {
+    int ga = r0 + rr, gb = ga + ST_WARPS;
+    if (ga >= R) break;
+    const bool hasb = gb < R;
+    float va[ST_CPT], vb[ST_CPT];
+#pragma unroll
+    for (int k = 0; k < ST_CPT; ++k) {
+      bool ok = c0 + lane + 32 * k < C;
+      va[k] = ok ? __ldg(A + (size_t)ga * C + c0 + lane + 32 * k) : 0.f;
+      vb[k] = (ok && hasb) ? __ldg(A + (size_t)gb * C + c0 + lane + 32 * k) : 0.f;
+    }
+    const int gbb = hasb ? gb : ga;
+    const float rmla = rmax[(size_t)b * R + ga] * kLog2e, rmlb = rmax[(size_t)b * R + gbb] * kLog2e;
+    const float s1a = (ga > 0 && score1) ? score1[(size_t)b * ld1 + ga - 1] : 1.f;
+    const float s1b = (gbb > 0 && score1) ? score1[(size_t)b * ld1 + gbb - 1] : 1.f;
+    const float rmula = s1a / rsum[(size_t)b * R + ga], rmulb = s1b / rsum[(size_t)b * R + gbb];
+    float ax = 0.f, ay = 0.f, az = 0.f, aw = 0.f, bx = 0.f, by = 0.f, bz = 0.f, bw = 0.f;
+#pragma unroll
+    for (int k = 0; k < ST_CPT; ++k) {
+      float aa = ex2_fast(fmaf(va[k], 2.f * kLog2e, -(rmla + kc.cml[k]))) * kc.cmul[k];
+      float ab = ex2_fast(fmaf(vb[k], 2.f * kLog2e, -(rmlb + kc.cml[k]))) * kc.cmul[k];
+      ax = fmaf(aa, px[k], ax); ay = fmaf(aa, py[k], ay); az = fmaf(aa, pz[k], az); aw += aa;
+      bx = fmaf(ab, px[k], bx); by = fmaf(ab, py[k], by); bz = fmaf(ab, pz[k], bz); bw += ab;
+    }
+    ax = warp_sum(ax); ay = warp_sum(ay); az = warp_sum(az); aw = warp_sum(aw);
+    bx = warp_sum(bx); by = warp_sum(by); bz = warp_sum(bz); bw = warp_sum(bw);
+    if (lane == 0) {
+      if (ga > 0)
+        rowpart4[((size_t)b * N1 + ga - 1) * ntc + tc] = make_float4(ax * rmula, ay * rmula, az * rmula, aw * rmula);
+      if (hasb)
+        rowpart4[((size_t)b * N1 + gb - 1) * ntc + tc] = make_float4(bx * rmulb, by * rmulb, bz * rmulb, bw * rmulb);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ host launchers
 template <int TR, int TC>
 static int stats_labels_t(const float* atten, const float* score1, int ld1, const float* score2, int ld2,
@@ -417,7 +683,18 @@ int run_assignment_labels(const float* atten, const float* score1, int ld1, cons
                           int b, const AssignGeom& g, const AssignWs& ws, float* w1, float* w2,
                           cudaStream_t st) {
   if (g.TR == 32) return stats_labels_t<32, 128>(atten, score1, ld1, score2, ld2, b, g, ws, w1, w2, st);
-  return stats_labels_t<64, 256>(atten, score1, ld1, score2, ld2, b, g, ws, w1, w2, st);
+  // large geometry: register-streaming passes (same partial layout, same merges)
+  dim3 grid(g.ntc, g.ntr, b);
+  dim3 mg(ceil_div(g.R + g.C, 256), b);
+  k_stats_stream<<<grid, ST_WARPS * 32, 0, st>>>(atten, g.R, g.C, g.ntr, g.ntc, ws.rowpart, ws.colpart);
+  k_stats_merge<<<mg, 256, 0, st>>>(ws.rowpart, ws.colpart, g.R, g.C, g.ntr, g.ntc, ws.rmax, ws.rsum,
+                                    ws.cmax, ws.csum);
+  k_labels_stream<<<grid, ST_WARPS * 32, 0, st>>>(atten, g.R, g.C, g.ntr, g.ntc, ws.rmax, ws.rsum, ws.cmax,
+                                                  ws.csum, score1, ld1, score2, ld2, ws.rowpm, ws.colpm,
+                                                  ws.ai0, ws.a0j);
+  k_labels_merge<<<mg, 256, 0, st>>>(ws.rowpm, ws.colpm, ws.ai0, ws.a0j, g.R, g.C, g.ntr, g.ntc, w1, w2);
+  count_launch(4);
+  UPK_RETURN_LAST_ERROR();
 }
 
 template <int TR, int TC>
@@ -476,7 +753,14 @@ int run_fine_rowsums(const float* atten, const float* score1, int ld1, const flo
                      const float* pts2, float4* rowpart4, float* soft, float* asum, cudaStream_t st) {
   if (g.TR == 32)
     return fine_rows_t<32, 128>(atten, score1, ld1, score2, ld2, b, g, ws, w1, w2, pts2, rowpart4, soft, asum, st);
-  return fine_rows_t<64, 256>(atten, score1, ld1, score2, ld2, b, g, ws, w1, w2, pts2, rowpart4, soft, asum, st);
+  dim3 grid(g.ntc, g.ntr, b);
+  k_fine_rows_stream<<<grid, ST_WARPS * 32, 0, st>>>(atten, g.R, g.C, g.ntc, ws.rmax, ws.rsum, ws.cmax, ws.csum,
+                                                     score1, ld1, score2, ld2, w2, pts2, rowpart4);
+  int n1 = g.R - 1;
+  dim3 mg(ceil_div(n1, 256), b);
+  k_fine_rows_merge<<<mg, 256, 0, st>>>(rowpart4, w1, n1, g.ntc, soft, asum);
+  count_launch(2);
+  UPK_RETURN_LAST_ERROR();
 }
 
 }  // namespace upk

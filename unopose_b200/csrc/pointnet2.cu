@@ -6,6 +6,8 @@
 // with bit-exact indices (see DESIGN.md §kernels and SURVEY.md Appendix A.1-A.4).
 // The launch shapes are NOT the reference's (one CTA per instance): they are
 // sized for 148 SMs, coalesced 128-bit accesses and register/smem residency.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "launch_count.h"
 #include "../../include/unopose_b200.h"
@@ -43,16 +45,15 @@ template <int THREADS, int PPT>
 __global__ void __launch_bounds__(THREADS, 1)
 fps_kernel(const float* __restrict__ xyz, int n, int m, int bs_log2,
            int* __restrict__ idx_out) {
-  constexpr int NW = THREADS / 32;
   extern __shared__ float smem_f[];
   float* sx = smem_f;
   float* sy = sx + n;
   float* sz = sy + n;
-  __shared__ uint2 sred[2][32];
+  constexpr int NW = THREADS / 32;
+  __shared__ int2 sred[2][32];  // per-warp (hi, lo) candidates, double-buffered -> one barrier / iteration
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
-  const int warp = tid >> 5;
   xyz += (size_t)blockIdx.x * n * 3;
   idx_out += (size_t)blockIdx.x * m;
 
@@ -64,8 +65,9 @@ fps_kernel(const float* __restrict__ xyz, int n, int m, int bs_log2,
   }
   __syncthreads();
 
+  // Points past the end of the cloud carry a running distance of -1: min(d, -1) = -1 never beats
+  // `best` (initialised to -1, strict >), so the scan below needs no bounds checks.
   float px[PPT], py[PPT], pz[PPT], td[PPT];
-  int cnt = 0;
 #pragma unroll
   for (int p = 0; p < PPT; ++p) {
     int k = tid + p * THREADS;
@@ -73,39 +75,39 @@ fps_kernel(const float* __restrict__ xyz, int n, int m, int bs_log2,
     px[p] = ok ? sx[k] : 0.f;
     py[p] = ok ? sy[k] : 0.f;
     pz[p] = ok ? sz[k] : 0.f;
-    td[p] = 1e10f;  // sampling.cpp:78-80
-    cnt += ok ? 1 : 0;
+    td[p] = ok ? 1e10f : -1.f;  // sampling.cpp:78-80
   }
   const unsigned bs_mask = (1u << bs_log2) - 1u;
   const unsigned my_rev = bitrev_n((unsigned)tid & bs_mask, bs_log2) << 20;
 
   if (tid == 0) idx_out[0] = 0;
   float x1 = sx[0], y1 = sy[0], z1 = sz[0];
+  const int warp = tid >> 5;
   int buf = 0;
   for (int j = 1; j < m; ++j) {
     float best = -1.f;
     int bestp = 0;
 #pragma unroll
     for (int p = 0; p < PPT; ++p) {
-      if (p < cnt) {
-        float d = sqdist_ref(px[p] - x1, py[p] - y1, pz[p] - z1);
-        float d2 = fminf(d, td[p]);
-        td[p] = d2;
-        bool g = d2 > best;
-        bestp = g ? p : bestp;
-        best = g ? d2 : best;
-      }
+      float d = sqdist_ref(px[p] - x1, py[p] - y1, pz[p] - z1);
+      float d2 = fminf(d, td[p]);
+      td[p] = d2;
+      bool g = d2 > best;
+      bestp = g ? p : bestp;
+      best = g ? d2 : best;
     }
-    unsigned hi = cnt > 0 ? __float_as_uint(best) : 0u;
-    unsigned lo = cnt > 0 ? (my_rev | ((unsigned)(tid + bestp * THREADS) >> bs_log2)) : 0xffffffffu;
-    unsigned whi = __reduce_max_sync(kFull, hi);
-    unsigned wlo = __reduce_min_sync(kFull, hi == whi ? lo : 0xffffffffu);
-    if (lane == 0) sred[buf][warp] = make_uint2(whi, wlo);
+    // d2 >= 0 for real points, so signed-int order of the bit patterns == float order and the
+    // sentinel -1.0f (negative as int) loses against everything
+    const int hi = __float_as_int(best);
+    const unsigned lo = my_rev | ((unsigned)(tid + bestp * THREADS) >> bs_log2);
+    const int whi = __reduce_max_sync(kFull, hi);
+    const unsigned wlo = __reduce_min_sync(kFull, hi == whi ? lo : 0xffffffffu);
+    if (lane == 0) sred[buf][warp] = make_int2(whi, (int)wlo);
     __syncthreads();
-    uint2 e = lane < NW ? sred[buf][lane] : make_uint2(0u, 0xffffffffu);
-    unsigned bhi = __reduce_max_sync(kFull, e.x);
-    unsigned blo = __reduce_min_sync(kFull, e.x == bhi ? e.y : 0xffffffffu);
-    int old = (int)(((blo & 0xfffffu) << bs_log2) | bitrev_n(blo >> 20, bs_log2));
+    const int2 e = lane < NW ? sred[buf][lane] : make_int2(-1, -1);
+    const int bhi = __reduce_max_sync(kFull, e.x);
+    const unsigned blo = __reduce_min_sync(kFull, e.x == bhi ? (unsigned)e.y : 0xffffffffu);
+    const int old = (int)(((blo & 0xfffffu) << bs_log2) | bitrev_n(blo >> 20, bs_log2));
     x1 = sx[old];
     y1 = sy[old];
     z1 = sz[old];
@@ -163,6 +165,16 @@ fps_kernel_large(const float* __restrict__ xyz, int n, int m, int bs_log2,
   }
 }
 
+// UPK_FPS_CFG (dev knob): 1 = 1024-thread variants, 2 = 512-thread variants; default = tuned choice
+static int fps_cfg() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("UPK_FPS_CFG");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
 template <int THREADS, int PPT>
 static int launch_fps(const float* xyz, int b, int n, int m, int bs_log2, int* out,
                       cudaStream_t st) {
@@ -187,73 +199,89 @@ static int launch_fps(const float* xyz, int b, int n, int m, int bs_log2, int* o
 constexpr int BQ_WARPS = 8;
 constexpr int BQ_QPW = 4;                    // queries per warp
 constexpr int BQ_QPB = BQ_WARPS * BQ_QPW;    // queries per block
-constexpr int BQ_TILE = 4096;                // points per smem tile (48 KB)
+constexpr int BQ_TILE = 3968;                // points per smem tile (46.5 KB), multiple of 128
+
+// One ballot step over 32 points: returns the hit mask (warp-uniform).
+__device__ __forceinline__ unsigned bq_hits(const float* sx, const float* sy, const float* sz, int k,
+                                            float qx, float qy, float qz, float r2) {
+  // (new_x - x)^2 + ... with the reference's FMA contraction
+  float d2 = sqdist_ref(qx - sx[k], qy - sy[k], qz - sz[k]);
+  return __ballot_sync(kFull, d2 < r2);
+}
+
+// Append the hits of one 32-point step in ascending k (popc prefix keeps the slot order).
+__device__ __forceinline__ void bq_append(unsigned mask, int kbase, int lane, int nsample, int& cnt,
+                                          int& first, int* __restrict__ row) {
+  if (mask) {
+    if (cnt == 0) first = kbase + __ffs(mask) - 1;
+    int slot = cnt + __popc(mask & ((1u << lane) - 1u));
+    if (((mask >> lane) & 1u) && slot < nsample) row[slot] = kbase + lane;
+    cnt += __popc(mask);
+  }
+}
 
 __global__ void __launch_bounds__(BQ_WARPS * 32)
 ball_query_kernel(const float* __restrict__ new_xyz, const float* __restrict__ xyz,
                   int n, int m, float radius2, int nsample, int* __restrict__ idx) {
   __shared__ float sx[BQ_TILE], sy[BQ_TILE], sz[BQ_TILE];
+  __shared__ int s_cnt[BQ_QPB], s_first[BQ_QPB];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.y;
   xyz += (size_t)b * n * 3;
   new_xyz += (size_t)b * m * 3;
   idx += (size_t)b * m * nsample;
-
   const int q0 = blockIdx.x * BQ_QPB + warp * BQ_QPW;
-  float qx[BQ_QPW], qy[BQ_QPW], qz[BQ_QPW];
-  int cnt[BQ_QPW], first[BQ_QPW];
-#pragma unroll
-  for (int q = 0; q < BQ_QPW; ++q) {
-    int j = q0 + q;
-    bool ok = j < m;
-    qx[q] = ok ? new_xyz[j * 3 + 0] : 0.f;
-    qy[q] = ok ? new_xyz[j * 3 + 1] : 0.f;
-    qz[q] = ok ? new_xyz[j * 3 + 2] : 0.f;
-    cnt[q] = ok ? 0 : nsample;  // out-of-range queries are "done"
-    first[q] = 0;
+  if (lane < BQ_QPW) {
+    s_cnt[warp * BQ_QPW + lane] = (q0 + lane < m) ? 0 : nsample;  // out-of-range queries are "done"
+    s_first[warp * BQ_QPW + lane] = 0;
   }
-
   for (int t0 = 0; t0 < n; t0 += BQ_TILE) {
     const int tn = min(BQ_TILE, n - t0);
+    const int tn_pad = (tn + 127) & ~127;  // sentinel padding: far-away points never hit
     __syncthreads();
     for (int i = tid; i < tn * 3; i += BQ_WARPS * 32) {
       float v = xyz[(size_t)t0 * 3 + i];
       int k = i / 3, c = i - k * 3;
       (c == 0 ? sx : (c == 1 ? sy : sz))[k] = v;
     }
+    for (int k = tn + tid; k < tn_pad; k += BQ_WARPS * 32) sx[k] = sy[k] = sz[k] = 1e30f;
     __syncthreads();
-#pragma unroll
     for (int q = 0; q < BQ_QPW; ++q) {
-      if (cnt[q] >= nsample) continue;
-      int* row = idx + (size_t)(q0 + q) * nsample;
-      for (int base = 0; base < tn; base += 32) {
-        int k = base + lane;
-        bool hit = false;
-        if (k < tn) {
-          // (new_x - x)^2 + ... with the reference's FMA contraction
-          float d2 = sqdist_ref(qx[q] - sx[k], qy[q] - sy[k], qz[q] - sz[k]);
-          hit = d2 < radius2;
-        }
-        unsigned mask = __ballot_sync(kFull, hit);
-        if (mask) {
-          if (cnt[q] == 0) first[q] = t0 + base + __ffs(mask) - 1;
-          int slot = cnt[q] + __popc(mask & ((1u << lane) - 1u));
-          if (hit && slot < nsample) row[slot] = t0 + k;
-          cnt[q] += __popc(mask);
-          if (cnt[q] >= nsample) break;
+      int cnt = s_cnt[warp * BQ_QPW + q];
+      if (cnt >= nsample) continue;
+      int first = s_first[warp * BQ_QPW + q];
+      const int j = q0 + q;
+      const float qx = new_xyz[j * 3 + 0], qy = new_xyz[j * 3 + 1], qz = new_xyz[j * 3 + 2];
+      int* row = idx + (size_t)j * nsample;
+      for (int base = 0; base < tn_pad; base += 128) {
+        const int k = base + lane;
+        unsigned m0 = bq_hits(sx, sy, sz, k, qx, qy, qz, radius2);
+        unsigned m1 = bq_hits(sx, sy, sz, k + 32, qx, qy, qz, radius2);
+        unsigned m2 = bq_hits(sx, sy, sz, k + 64, qx, qy, qz, radius2);
+        unsigned m3 = bq_hits(sx, sy, sz, k + 96, qx, qy, qz, radius2);
+        if (m0 | m1 | m2 | m3) {
+          bq_append(m0, t0 + base, lane, nsample, cnt, first, row);
+          bq_append(m1, t0 + base + 32, lane, nsample, cnt, first, row);
+          bq_append(m2, t0 + base + 64, lane, nsample, cnt, first, row);
+          bq_append(m3, t0 + base + 96, lane, nsample, cnt, first, row);
+          if (cnt >= nsample) break;
         }
       }
+      if (lane == 0) {
+        s_cnt[warp * BQ_QPW + q] = cnt;
+        s_first[warp * BQ_QPW + q] = first;
+      }
+      __syncwarp();
     }
   }
   // complete the rows: slots [cnt, nsample) <- first hit (or 0 when no hit)
-#pragma unroll
   for (int q = 0; q < BQ_QPW; ++q) {
-    int j = q0 + q;
+    const int j = q0 + q;
     if (j >= m) continue;
     int* row = idx + (size_t)j * nsample;
-    int c = min(cnt[q], nsample);
-    int fillv = cnt[q] > 0 ? first[q] : 0;
-    for (int s = c + lane; s < nsample; s += 32) row[s] = fillv;
+    const int cnt = s_cnt[warp * BQ_QPW + q];
+    const int fillv = cnt > 0 ? s_first[warp * BQ_QPW + q] : 0;
+    for (int s = min(cnt, nsample) + lane; s < nsample; s += 32) row[s] = fillv;
   }
 }
 
@@ -332,6 +360,47 @@ static int launch_group_grad(const float* grad_out, const int* idx, int b, int c
   group_grad_kernel<<<grid, GP_THREADS, 0, st>>>(grad_out, idx, c, n, L, grad_points);
   count_launch();
   UPK_RETURN_LAST_ERROR();
+}
+
+// ---------------------------------------------------------------------------
+// Row gather (channel-last):  out[b,j,:] = x[b,idx[b,j],:]   x:(b,n,c)  idx:(b,m)
+// What sample_pts_feats / gather_pts_feats need (model_utils.py:137-212).  The reference reaches
+// it through transpose -> channel-first gather_points -> transpose, i.e. two full copies of the
+// (B,N,C) tensor per call; here each output row is one coalesced 128-bit-vectorised row copy.
+// ---------------------------------------------------------------------------
+constexpr int GR_THREADS = 256;
+
+template <bool VEC>
+__global__ void __launch_bounds__(GR_THREADS)
+gather_rows_kernel(const float* __restrict__ x, const int* __restrict__ idx, int n, int m, int c,
+                   float* __restrict__ out) {
+  const int b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x * (GR_THREADS / 32) + warp;
+  if (j >= m) return;
+  const int src = __ldg(idx + (size_t)b * m + j);
+  const float* p = x + ((size_t)b * n + src) * c;
+  float* o = out + ((size_t)b * m + j) * c;
+  if (VEC) {
+    const float4* p4 = reinterpret_cast<const float4*>(p);
+    float4* o4 = reinterpret_cast<float4*>(o);
+    for (int k = lane; k < c / 4; k += 32) o4[k] = __ldg(p4 + k);
+  } else {
+    for (int k = lane; k < c; k += 32) o[k] = __ldg(p + k);
+  }
+}
+
+__global__ void __launch_bounds__(GR_THREADS)
+gather_rows_grad_kernel(const float* __restrict__ grad_out, const int* __restrict__ idx, int n, int m, int c,
+                        float* __restrict__ grad_x) {
+  const int b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x * (GR_THREADS / 32) + warp;
+  if (j >= m) return;
+  const int src = __ldg(idx + (size_t)b * m + j);
+  const float* g = grad_out + ((size_t)b * m + j) * c;
+  float* o = grad_x + ((size_t)b * n + src) * c;
+  for (int k = lane; k < c; k += 32) atomicAdd(o + k, g[k]);
 }
 
 // ---------------------------------------------------------------------------
@@ -443,10 +512,19 @@ int upk_furthest_point_sampling(const float* xyz, int b, int n, int m, int* idx_
   if (n < 256) return launch_fps<128, 2>(xyz, b, n, m, bs_log2, idx_out, st);
   if (n < 512) return launch_fps<256, 2>(xyz, b, n, m, bs_log2, idx_out, st);
   if (n <= 1024) return launch_fps<512, 2>(xyz, b, n, m, bs_log2, idx_out, st);
-  if (n <= 2048) return launch_fps<512, 4>(xyz, b, n, m, bs_log2, idx_out, st);
+  const int cfg = fps_cfg();
+  if (n <= 2048) {
+    if (cfg == 1) return launch_fps<1024, 2>(xyz, b, n, m, bs_log2, idx_out, st);
+    if (cfg == 2) return launch_fps<512, 4>(xyz, b, n, m, bs_log2, idx_out, st);
+    return launch_fps<512, 4>(xyz, b, n, m, bs_log2, idx_out, st);
+  }
   if (n <= 3072) return launch_fps<1024, 3>(xyz, b, n, m, bs_log2, idx_out, st);
   if (n <= 4096) return launch_fps<1024, 4>(xyz, b, n, m, bs_log2, idx_out, st);
-  if (n <= 5120) return launch_fps<1024, 5>(xyz, b, n, m, bs_log2, idx_out, st);
+  if (n <= 5120) {
+    if (cfg == 1) return launch_fps<1024, 5>(xyz, b, n, m, bs_log2, idx_out, st);
+    if (cfg == 2) return launch_fps<512, 10>(xyz, b, n, m, bs_log2, idx_out, st);
+    return launch_fps<512, 10>(xyz, b, n, m, bs_log2, idx_out, st);
+  }
   if (n <= 8192) return launch_fps<512, 16>(xyz, b, n, m, bs_log2, idx_out, st);
   if (n <= 12288) return launch_fps<512, 24>(xyz, b, n, m, bs_log2, idx_out, st);
   size_t smem = (size_t)n * sizeof(float);
@@ -496,6 +574,31 @@ int upk_group_points_grad(const float* grad_out, const int* idx, int b, int c, i
   long long L = (long long)npoints * nsample;
   if (L > 0x7fffffffLL) return UPK_ERR_UNSUPPORTED;
   return launch_group_grad(grad_out, idx, b, c, n, (int)L, grad_points, (cudaStream_t)stream);
+}
+
+int upk_gather_rows(const float* x, const int* idx, int b, int n, int m, int c, float* out,
+                    upk_stream_t stream) {
+  if (b < 0 || n < 0 || m < 0 || c < 0) return UPK_ERR_INVALID_ARG;
+  if (b == 0 || m == 0 || c == 0) return UPK_OK;
+  dim3 grid(ceil_div(m, GR_THREADS / 32), b);
+  bool vec = (c % 4 == 0) && (((uintptr_t)x | (uintptr_t)out) % 16 == 0);
+  if (vec) gather_rows_kernel<true><<<grid, GR_THREADS, 0, (cudaStream_t)stream>>>(x, idx, n, m, c, out);
+  else gather_rows_kernel<false><<<grid, GR_THREADS, 0, (cudaStream_t)stream>>>(x, idx, n, m, c, out);
+  count_launch();
+  UPK_RETURN_LAST_ERROR();
+}
+
+int upk_gather_rows_grad(const float* grad_out, const int* idx, int b, int n, int m, int c,
+                         float* grad_x, upk_stream_t stream) {
+  if (b < 0 || n < 0 || m < 0 || c < 0) return UPK_ERR_INVALID_ARG;
+  if (b == 0 || n == 0 || c == 0) return UPK_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  UPK_CUDA_TRY(cudaMemsetAsync(grad_x, 0, (size_t)b * n * c * sizeof(float), st));
+  if (m == 0) return UPK_OK;
+  dim3 grid(ceil_div(m, GR_THREADS / 32), b);
+  gather_rows_grad_kernel<<<grid, GR_THREADS, 0, st>>>(grad_out, idx, n, m, c, grad_x);
+  count_launch();
+  UPK_RETURN_LAST_ERROR();
 }
 
 int upk_three_nn(const float* unknown, const float* known, int b, int n, int m,

@@ -245,9 +245,41 @@ class WeightedProcrustes(nn.Module):
 
 
 # --------------------------------------------------------------------------- a15
+class _GatherRows(torch.autograd.Function):
+    """x (B,N,C), idx (B,m) int32 -> (B,m,C): one coalesced row copy per sample.  Same values as the
+    reference's transpose -> gather_operation -> transpose (model_utils.py:146-149), without the two
+    full-tensor transposes."""
+
+    @staticmethod
+    def forward(ctx, x, idx):
+        L.check_cuda(x, "x")
+        L.check_int(idx, "idx")
+        x = x.contiguous()
+        idx = idx.contiguous()
+        b, n, c = x.shape
+        m = idx.shape[1]
+        ctx.save_for_backward(idx)
+        ctx.n_src = n
+        out = torch.empty((b, m, c), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            L.check(L.load().upk_gather_rows(L.ptr(x), L.ptr(idx), b, n, m, c, L.ptr(out), L.stream_ptr(x)),
+                    "gather_rows")
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (idx,) = ctx.saved_tensors
+        g = grad_out.contiguous()
+        b, m, c = g.shape
+        gx = torch.empty((b, ctx.n_src, c), dtype=torch.float32, device=g.device)
+        with torch.cuda.device(g.device):
+            L.check(L.load().upk_gather_rows_grad(L.ptr(g), L.ptr(idx), b, ctx.n_src, m, c, L.ptr(gx),
+                                                  L.stream_ptr(g)), "gather_rows_grad")
+        return gx, None
+
+
 def _gather_rows(x, idx):
-    """x (B,N,C) gathered along N by idx (B,m) int32 -> (B,m,C), via the channel-first gather kernel."""
-    return gather_operation(x.transpose(1, 2).contiguous(), idx).transpose(1, 2).contiguous()
+    return _GatherRows.apply(x, idx)
 
 
 def sample_pts_feats(pts, feats, npoint=2048, return_index=False):

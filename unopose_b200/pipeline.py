@@ -77,17 +77,34 @@ def to_device(inp, device, non_blocking=True):
     return {k: (v.to(device, non_blocking=non_blocking) if not k.startswith("_") else v) for k, v in inp.items()}
 
 
-def run_hot_path(inp, cfg=HotPathConfig(), stages=None):
-    """One step.  `inp` holds CUDA tensors (see module docstring).  `stages` optionally receives
-    a list of (name, callable) instead of executing, for per-stage timing."""
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    key = torch.device(device).index
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
+def run_hot_path(inp, cfg=HotPathConfig(), stages=None, overlap=True):
+    """One step.  `inp` holds CUDA tensors (see module docstring).
+
+    overlap=True runs the reference-cloud chain (template FPS -> sparse FPS -> ball query/grouping of
+    the reference cloud: a serial, latency-bound chain that occupies one SM per instance) on a side
+    CUDA stream, concurrently with the query-cloud chain and both pose solves on the current stream;
+    the two are joined by events before returning.  `stages` optionally receives the list of
+    (name, callable) in serial order instead of executing, for per-stage timing."""
     out = {}
 
     def s_template():
         out["tem_sub"], out["tem_sub_feats"], out["tem_idx"] = MU.sample_pts_feats(
             inp["tem_pts"], inp["tem_feats"], cfg.n_fine, return_index=True)
 
-    def s_sparse():
+    def s_sparse_q():
         out["sp1"], out["sf1"], out["fps_idx1"] = MU.sample_pts_feats(inp["pts"], inp["pts_feats"], cfg.n_coarse, True)
+
+    def s_sparse_r():
         out["sp2"], out["sf2"], out["fps_idx2"] = MU.sample_pts_feats(out["tem_sub"], out["tem_sub_feats"],
                                                                       cfg.n_coarse, True)
 
@@ -98,12 +115,17 @@ def run_hot_path(inp, cfg=HotPathConfig(), stages=None):
         out["init_R"], out["init_t"], out["init_pose_score"] = MU.compute_coarse_Rt_overlap(
             out["c_atten"], inp["c_score"], inp["c_pts1"], inp["c_pts2"], None, cfg.n_proposal1, cfg.n_proposal2)
 
-    def s_pe_geometry():
-        for name, cloud in (("q", inp["pts"]), ("r", out["tem_sub"])):
-            cf = cloud.transpose(1, 2).contiguous()
-            for i, (r, ns) in enumerate(cfg.pe):
-                idx = P.ball_query(r, ns, cloud, cloud)
-                out["pe_%s%d" % (name, i)] = P.grouping_operation(cf, idx)
+    def pe_geometry(name, cloud):
+        cf = cloud.transpose(1, 2).contiguous()
+        for i, (r, ns) in enumerate(cfg.pe):
+            idx = P.ball_query(r, ns, cloud, cloud)
+            out["pe_%s%d" % (name, i)] = P.grouping_operation(cf, idx)
+
+    def s_pe_q():
+        pe_geometry("q", inp["pts"])
+
+    def s_pe_r():
+        pe_geometry("r", out["tem_sub"])
 
     def s_fine_sim():
         out["f_atten"] = MU.compute_feature_similarity(inp["f_f1"], inp["f_f2"], "cosine", cfg.temp, True)
@@ -112,12 +134,29 @@ def run_hot_path(inp, cfg=HotPathConfig(), stages=None):
         out["pred_R"], out["pred_t"], out["pred_pose_score"] = MU.compute_fine_Rt_overlap(
             out["f_atten"], inp["f_score"], inp["f_pts1"], inp["f_pts2"], None, cfg.dis_thres)
 
-    plan = [("fps_template+gather", s_template), ("fps_sparse+gather", s_sparse), ("coarse_similarity", s_coarse_sim),
-            ("coarse_pose", s_coarse_pose), ("ball_query+group", s_pe_geometry), ("fine_similarity", s_fine_sim),
-            ("fine_pose", s_fine_pose)]
+    ref_chain = [("fps_template+gather", s_template), ("fps_sparse_ref+gather", s_sparse_r),
+                 ("ball_query+group_ref", s_pe_r)]
+    main_chain = [("fps_sparse_query+gather", s_sparse_q), ("coarse_similarity", s_coarse_sim),
+                  ("coarse_pose", s_coarse_pose), ("ball_query+group_query", s_pe_q),
+                  ("fine_similarity", s_fine_sim), ("fine_pose", s_fine_pose)]
     if stages is not None:
-        stages.extend(plan)
+        stages.extend(ref_chain + main_chain)
         return out
-    for _, fn in plan:
+    if not overlap:
+        for _, fn in ref_chain + main_chain:
+            fn()
+        return out
+    dev = inp["pts"].device
+    main = torch.cuda.current_stream(dev)
+    side = _side_stream(dev)
+    side.wait_stream(main)          # inputs produced on the current stream are visible to the side chain
+    with torch.cuda.stream(side):
+        for _, fn in ref_chain:
+            fn()
+    for _, fn in main_chain:
         fn()
+    main.wait_stream(side)          # join
+    for k in ("tem_sub", "tem_sub_feats", "tem_idx", "sp2", "sf2", "fps_idx2", "pe_r0", "pe_r1"):
+        if k in out:
+            out[k].record_stream(main)   # allocated on the side stream, consumed on the current one
     return out
