@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--sets", type=int, default=4, help="resident input sets to rotate over (defeats L2 reuse)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=8, help="instances in the bounded CPU-baseline sample")
+    ap.add_argument("--no-overlap", action="store_true", help="run the two chains of a step serially on one stream")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-torch-baseline", action="store_true")
     return ap.parse_args()
@@ -196,7 +197,7 @@ def main():
     results = []
 
     def step(i):
-        out = run_hot_path(sets[i % len(sets)], cfg)
+        out = run_hot_path(sets[i % len(sets)], cfg, overlap=not args.no_overlap)
         return out
 
     for i in range(max(args.warmup, 3)):
@@ -278,7 +279,7 @@ def main():
 
     def e2e_step(i):
         d = to_device(host_sets[i % len(host_sets)], dev)
-        o = run_hot_path(d, cfg)
+        o = run_hot_path(d, cfg, overlap=not args.no_overlap)
         r = torch.cat([o["pred_R"].reshape(B, 9), o["pred_t"], o["pred_pose_score"].unsqueeze(1)], 1)
         res_host.copy_(r, non_blocking=True)
         torch.cuda.current_stream().synchronize()   # the caller reads the result every step

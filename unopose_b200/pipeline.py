@@ -156,7 +156,7 @@ def run_hot_path(inp, cfg=HotPathConfig(), stages=None, overlap=True):
     for _, fn in main_chain:
         fn()
     main.wait_stream(side)          # join
-    for k in ("tem_sub", "tem_sub_feats", "tem_idx", "sp2", "sf2", "fps_idx2", "pe_r0", "pe_r1"):
-        if k in out:
-            out[k].record_stream(main)   # allocated on the side stream, consumed on the current one
+    # Tensors allocated on the side stream are consumed on the current stream only after this join,
+    # and the next step's side chain starts with side.wait_stream(main): the caching allocator can
+    # recycle them on the side stream without record_stream() (which would defer every reuse).
     return out
