@@ -35,6 +35,7 @@ _SIGNATURES = {
     "upk_three_nn": [c_f, c_f, c_i, c_i, c_i, c_f, c_f, c_st],
     "upk_three_interpolate": [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_f, c_st],
     "upk_three_interpolate_grad": [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_f, c_st],
+    "upk_set_similarity_mode": [c_i],
     "upk_feature_similarity": [c_f, c_f, c_i, c_i, c_i, c_i, c_fl, c_i, c_i, c_f, c_sz, c_f, c_st],
     "upk_coarse_pose": [c_f, c_f, c_i, c_f, c_i, c_f, c_f, c_f, c_i, c_f, c_i, c_i, c_i, c_i, c_i,
                         c_f, c_sz, c_f, c_f, c_f, c_f, c_f, c_st],

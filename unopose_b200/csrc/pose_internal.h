@@ -63,4 +63,11 @@ int run_fine_rowsums(const float* atten, const float* score1, int ld1, const flo
                      const float* pts2, float4* rowpart4 /*[b][N1][ntc]*/, float* soft, float* asum,
                      cudaStream_t st);
 
+// tensor-core similarity path (similarity_tc.cu)
+int similarity_mode();  // 3 = 3xTF32 tcgen05 (default), 1 = 1xTF32 tcgen05, 0 = fp32 SIMT
+bool similarity_tc_eligible(int n, int m, int c);
+size_t similarity_tc_workspace_bytes(int b, int n, int m, int c);
+int run_similarity_tc(const float* f1, const float* f2, int b, int n, int m, int c, float temp, int normalize,
+                      int sim_type, void* workspace, size_t workspace_bytes, float* out, cudaStream_t st);
+
 }  // namespace upk

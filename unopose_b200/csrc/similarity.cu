@@ -10,6 +10,7 @@
 
 #include "common.cuh"
 #include "launch_count.h"
+#include "pose_internal.h"
 #include "../../include/unopose_b200.h"
 
 namespace upk {
@@ -123,6 +124,7 @@ using namespace upk;
 extern "C" {
 
 size_t upk_feature_similarity_workspace_bytes(int b, int n, int m, int c, int normalize) {
+  if (b > 0 && similarity_tc_eligible(n, m, c)) return similarity_tc_workspace_bytes(b, n, m, c);
   if (!normalize || b <= 0) return 0;
   size_t a = (((size_t)b * n * c * sizeof(float)) + 255) & ~(size_t)255;
   size_t bb = (((size_t)b * m * c * sizeof(float)) + 255) & ~(size_t)255;
@@ -136,6 +138,9 @@ int upk_feature_similarity(const float* feat1, const float* feat2, int b, int n,
   if (sim_type != 0 && sim_type != 1) return UPK_ERR_INVALID_ARG;
   if (b == 0) return UPK_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  if (similarity_tc_eligible(n, m, c))  // large problems: tcgen05 tensor-core path (3xTF32)
+    return run_similarity_tc(feat1, feat2, b, n, m, c, temp, normalize, sim_type, workspace, workspace_bytes,
+                             atten_out, st);
   const float* a = feat1;
   const float* bm = feat2;
   if (normalize) {

@@ -1,0 +1,380 @@
+// (1a) Feature-similarity GEMM on the 5th-gen tensor cores: tcgen05.mma (kind::tf32) with TMEM
+// accumulators, operands staged by TMA (cp.async.bulk.tensor, SWIZZLE_128B) — the fine-stage
+// 2049 x 2049 x 256 NT GEMM of compute_feature_similarity (model_utils.py:260-282).
+//
+// Precision: the reference runs this GEMM in true fp32 (cuBLAS SGEMM, TF32 off,
+// main_unopose.py:139-141) and the logits are divided by temp = 0.1, so a plain TF32 product
+// (2^-11 per operand) is not enough for the R/t tolerance.  We use the 3xTF32 split
+//     a = a_hi + a_lo,  a_hi = rna_tf32(a),  a_lo = a - a_hi   (exact in fp32)
+//     a.b ~= a_hi.b_hi + a_hi.b_lo + a_lo.b_hi                 (dropped terms ~2^-22)
+// accumulated in the fp32 TMEM accumulator: ~fp32 accuracy at 3 MMAs per product.
+// The split (and the F.normalize) is done once per operand by k_normalize_split.
+//
+// Kernel anatomy (persistent, one CTA per SM, 192 threads):
+//   warp 0      TMA producer : 4 boxes / K-chunk (A_hi, A_lo: 128x32 fp32; B_hi, B_lo: 256x32 fp32)
+//   warp 1      MMA issuer   : 12 x tcgen05.mma M128 N256 K8 per K-chunk, tcgen05.commit -> mbarriers
+//   warps 2..5  epilogue     : tcgen05.ld 32x32b.x32 -> /temp -> smem transpose -> coalesced stores
+// Pipelines: 2 smem stages (96 KB each) between TMA and MMA; 2 TMEM accumulators (2 x 256 columns)
+// between MMA and epilogue, so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <cuda.h>
+#include <math.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "launch_count.h"
+#include "../../include/unopose_b200.h"
+
+namespace upk {
+
+constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 32, TC_STAGES = 2;
+constexpr int TC_THREADS = 192;
+constexpr uint32_t TC_STAGE_BYTES = (2 * TC_BM * TC_BK + 2 * TC_BN * TC_BK) * 4;  // 98304
+
+struct __align__(1024) TcSmem {
+  float a_hi[TC_STAGES][TC_BM * TC_BK];
+  float a_lo[TC_STAGES][TC_BM * TC_BK];
+  float b_hi[TC_STAGES][TC_BN * TC_BK];
+  float b_lo[TC_STAGES][TC_BN * TC_BK];
+  float epi[4][32][33];
+  unsigned long long full[TC_STAGES], empty[TC_STAGES], tfull[2], tempty[2];
+  uint32_t tmem_base;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(void* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(void* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(void* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, void* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((unsigned long long)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(void* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+// start>>4 | LBO(=1)<<16 | SBO(=1024B>>4)<<32 | version(=1)<<46 | layout SWIZZLE_128B(=2)<<61
+__device__ __forceinline__ uint64_t make_desc_sw128(const void* smem) {
+  uint64_t d = (uint64_t)((smem_u32(smem) & 0x3ffff) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor: D=F32, A=B=TF32, both K-major, N=256, M=128 (cute::UMMA::InstrDescriptor)
+constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
+                                ((uint32_t)(TC_BM >> 4) << 24);
+
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---------------------------------------------------------------- operand preparation
+// out_hi = rna_tf32(x / max(||x||, 1e-12)) ; out_lo = x_n - out_hi.   One warp per row.
+__global__ void __launch_bounds__(256)
+k_normalize_split(const float* __restrict__ x, long long rows, int c, int normalize,
+                  float* __restrict__ hi, float* __restrict__ lo) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* p = x + row * c;
+  float nrm = 1.f;
+  if (normalize) {
+    float s = 0.f;
+    for (int k = lane; k < c; k += 32) {
+      float v = p[k];
+      s = fmaf(v, v, s);
+    }
+    s = warp_sum(s);
+    nrm = fmaxf(sqrtf(s), 1e-12f);
+  }
+  for (int k = lane; k < c; k += 32) {
+    float v = normalize ? p[k] / nrm : p[k];
+    uint32_t h;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+    float vh = __uint_as_float(h);
+    hi[row * c + k] = vh;
+    lo[row * c + k] = v - vh;
+  }
+}
+
+// ---------------------------------------------------------------- the GEMM
+template <int MODE, int NTERMS>  // MODE 0: dot/temp, 1: sqrt(clamp(2-2dot,0))/temp ; NTERMS 3 = 3xTF32, 1 = TF32
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_similarity_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                int batch, int M, int N, int K, float temp, float* __restrict__ C) {
+  extern __shared__ unsigned char smem_raw[];
+  TcSmem& sm = *reinterpret_cast<TcSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mt = (M + TC_BM - 1) / TC_BM, nt = (N + TC_BN - 1) / TC_BN;
+  const int total = batch * mt * nt;
+  const int kchunks = K / TC_BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&sm.tfull[a], 1); mbar_init(&sm.tempty[a], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sm.tmem_base;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    int s = 0;
+    uint32_t ph = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+      const int b = t / (mt * nt), rem = t - b * mt * nt;
+      const int mi = rem / nt, ni = rem - mi * nt;
+      for (int kc = 0; kc < kchunks; ++kc) {
+        mbar_wait(&sm.empty[s], ph ^ 1);
+        if (lane == 0) {
+          mbar_expect_tx(&sm.full[s], NTERMS == 3 ? TC_STAGE_BYTES : TC_STAGE_BYTES / 2);
+          tma_load_3d(&map_a_hi, &sm.full[s], sm.a_hi[s], kc * TC_BK, mi * TC_BM, b);
+          tma_load_3d(&map_b_hi, &sm.full[s], sm.b_hi[s], kc * TC_BK, ni * TC_BN, b);
+          if (NTERMS == 3) {
+            tma_load_3d(&map_a_lo, &sm.full[s], sm.a_lo[s], kc * TC_BK, mi * TC_BM, b);
+            tma_load_3d(&map_b_lo, &sm.full[s], sm.b_lo[s], kc * TC_BK, ni * TC_BN, b);
+          }
+        }
+        __syncwarp();
+        if (++s == TC_STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    int s = 0;
+    uint32_t ph = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_ph = (it >> 1) & 1;
+      mbar_wait(&sm.tempty[acc], acc_ph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * TC_BN;
+      for (int kc = 0; kc < kchunks; ++kc) {
+        mbar_wait(&sm.full[s], ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint64_t ahi = make_desc_sw128(sm.a_hi[s]), alo = make_desc_sw128(sm.a_lo[s]);
+          const uint64_t bhi = make_desc_sw128(sm.b_hi[s]), blo = make_desc_sw128(sm.b_lo[s]);
+#pragma unroll
+          for (int kk = 0; kk < TC_BK / 8; ++kk) {
+            const uint64_t adv = (uint64_t)(kk * 8 * 4 >> 4);  // 32 B along K inside the 128 B swizzle row
+            if (NTERMS == 3) {
+              tc_mma_tf32(d_tmem, alo + adv, bhi + adv, kIdescTf32, (kc | kk) ? 1u : 0u);
+              tc_mma_tf32(d_tmem, ahi + adv, blo + adv, kIdescTf32, 1u);
+              tc_mma_tf32(d_tmem, ahi + adv, bhi + adv, kIdescTf32, 1u);
+            } else {
+              tc_mma_tf32(d_tmem, ahi + adv, bhi + adv, kIdescTf32, (kc | kk) ? 1u : 0u);
+            }
+          }
+          tc_commit(&sm.empty[s]);                       // smem stage reusable once these MMAs retire
+          if (kc == kchunks - 1) tc_commit(&sm.tfull[acc]);  // accumulator complete
+        }
+        __syncwarp();
+        if (++s == TC_STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else {
+    // ===== epilogue warps (TMEM lane quarter = warp % 4) =====
+    const int q = warp & 3;
+    float (*tr)[33] = sm.epi[warp - 2];
+    int it = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+      const int b = t / (mt * nt), rem = t - b * mt * nt;
+      const int mi = rem / nt, ni = rem - mi * nt;
+      const int acc = it & 1;
+      const uint32_t acc_ph = (it >> 1) & 1;
+      mbar_wait(&sm.tfull[acc], acc_ph);
+      tc_fence_after();
+      float* Cb = C + (size_t)b * M * N;
+      const int row0 = mi * TC_BM + q * 32;
+#pragma unroll 1
+      for (int cb = 0; cb < TC_BN / 32; ++cb) {
+        const int col0 = ni * TC_BN + cb * 32;
+        if (col0 >= N) break;
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + acc * TC_BN + cb * 32 + ((uint32_t)(q * 32) << 16), r);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float v = __uint_as_float(r[j]);
+          if (MODE == 1) v = sqrtf(fmaxf(2.0f - 2.0f * v, 0.f));
+          tr[lane][j] = v / temp;
+        }
+        __syncwarp();
+        const int col = col0 + lane;
+        if (col < N) {
+#pragma unroll 8
+          for (int rr = 0; rr < 32; ++rr) {
+            const int row = row0 + rr;
+            if (row < M) Cb[(size_t)row * N + col] = tr[rr][lane];
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      if (lane == 0) mbar_arrive(&sm.tempty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+static int make_map(CUtensorMap* map, const float* base, int batch, int rows, int K, int box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return UPK_ERR_UNSUPPORTED;
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)batch};
+  cuuint64_t strides[2] = {(cuuint64_t)K * 4, (cuuint64_t)rows * K * 4};
+  cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? UPK_OK : UPK_ERR_INVALID_ARG;
+}
+
+static int g_sim_mode = -1;  // 3 = 3xTF32 tensor cores (default), 1 = 1xTF32, 0 = fp32 SIMT
+
+int similarity_mode() {
+  if (g_sim_mode < 0) {
+    const char* e = getenv("UPK_SIMILARITY_MODE");
+    g_sim_mode = e ? atoi(e) : 3;
+    if (g_sim_mode != 0 && g_sim_mode != 1 && g_sim_mode != 3) g_sim_mode = 3;
+  }
+  return g_sim_mode;
+}
+
+size_t similarity_tc_workspace_bytes(int b, int n, int m, int c) {
+  size_t a = (((size_t)b * n * c * sizeof(float)) + 1023) & ~(size_t)1023;
+  size_t bb = (((size_t)b * m * c * sizeof(float)) + 1023) & ~(size_t)1023;
+  return 2 * a + 2 * bb + 1024;
+}
+
+bool similarity_tc_eligible(int n, int m, int c) {
+  return similarity_mode() != 0 && c % TC_BK == 0 && c >= TC_BK && (long long)n * m >= 512LL * 512LL &&
+         get_encode() != nullptr;
+}
+
+int run_similarity_tc(const float* f1, const float* f2, int b, int n, int m, int c, float temp, int normalize,
+                      int sim_type, void* workspace, size_t workspace_bytes, float* out, cudaStream_t st) {
+  if (workspace_bytes < similarity_tc_workspace_bytes(b, n, m, c)) return UPK_ERR_INVALID_ARG;
+  char* w = (char*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
+  size_t a = (((size_t)b * n * c * sizeof(float)) + 1023) & ~(size_t)1023;
+  size_t bb = (((size_t)b * m * c * sizeof(float)) + 1023) & ~(size_t)1023;
+  float* a_hi = (float*)w;
+  float* a_lo = (float*)(w + a);
+  float* b_hi = (float*)(w + 2 * a);
+  float* b_lo = (float*)(w + 2 * a + bb);
+  long long r1 = (long long)b * n, r2 = (long long)b * m;
+  k_normalize_split<<<(unsigned)((r1 + 7) / 8), 256, 0, st>>>(f1, r1, c, normalize, a_hi, a_lo);
+  k_normalize_split<<<(unsigned)((r2 + 7) / 8), 256, 0, st>>>(f2, r2, c, normalize, b_hi, b_lo);
+  count_launch(2);
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  int rc;
+  if ((rc = make_map(&ma_hi, a_hi, b, n, c, TC_BM))) return rc;
+  if ((rc = make_map(&ma_lo, a_lo, b, n, c, TC_BM))) return rc;
+  if ((rc = make_map(&mb_hi, b_hi, b, m, c, TC_BN))) return rc;
+  if ((rc = make_map(&mb_lo, b_lo, b, m, c, TC_BN))) return rc;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int tiles = b * ((n + TC_BM - 1) / TC_BM) * ((m + TC_BN - 1) / TC_BN);
+  const int grid = tiles < sms ? tiles : sms;
+  const size_t smem = sizeof(TcSmem) + 1024;
+  const int terms = similarity_mode() == 1 ? 1 : 3;
+#define UPK_LAUNCH_TC(MODE, NT)                                                                              \
+  do {                                                                                                       \
+    auto kern = k_similarity_tc<MODE, NT>;                                                                   \
+    UPK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+    kern<<<grid, TC_THREADS, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, b, n, m, c, temp, out);                 \
+  } while (0)
+  if (sim_type == 0) {
+    if (terms == 3) UPK_LAUNCH_TC(0, 3); else UPK_LAUNCH_TC(0, 1);
+  } else {
+    if (terms == 3) UPK_LAUNCH_TC(1, 3); else UPK_LAUNCH_TC(1, 1);
+  }
+#undef UPK_LAUNCH_TC
+  count_launch();
+  UPK_RETURN_LAST_ERROR();
+}
+
+}  // namespace upk
+
+extern "C" int upk_set_similarity_mode(int mode) {
+  int prev = upk::similarity_mode();
+  if (mode == 0 || mode == 1 || mode == 3) upk::g_sim_mode = mode;
+  return prev;
+}
