@@ -1,5 +1,5 @@
 // (1a) Feature-similarity GEMM on the 5th-gen tensor cores: tcgen05.mma (kind::tf32) with TMEM
-// accumulators, operands staged by TMA (cp.async.bulk.tensor, SWIZZLE_128B) — the fine-stage
+// accumulators, operands staged by TMA (cp.async.bulk.tensor, SWIZZLE_64B) — the fine-stage
 // 2049 x 2049 x 256 NT GEMM of compute_feature_similarity (model_utils.py:260-282).
 //
 // Precision: the reference runs this GEMM in true fp32 (cuBLAS SGEMM, TF32 off,
@@ -11,10 +11,10 @@
 // The split (and the F.normalize) is done once per operand by k_normalize_split.
 //
 // Kernel anatomy (persistent, one CTA per SM, 192 threads):
-//   warp 0      TMA producer : 4 boxes / K-chunk (A_hi, A_lo: 128x32 fp32; B_hi, B_lo: 256x32 fp32)
-//   warp 1      MMA issuer   : 12 x tcgen05.mma M128 N256 K8 per K-chunk, tcgen05.commit -> mbarriers
-//   warps 2..5  epilogue     : tcgen05.ld 32x32b.x32 -> /temp -> smem transpose -> coalesced stores
-// Pipelines: 2 smem stages (96 KB each) between TMA and MMA; 2 TMEM accumulators (2 x 256 columns)
+//   warp 0      TMA producer : 4 boxes / K-chunk (A_hi, A_lo: 128x16 fp32; B_hi, B_lo: 256x16 fp32)
+//   warp 1      MMA issuer   : 6 x tcgen05.mma M128 N256 K8 per K-chunk, tcgen05.commit -> mbarriers
+//   warps 2..9  epilogue     : tcgen05.ld 32x32b.x32 -> * 1/temp -> smem transpose -> coalesced stores
+// Pipelines: 3 smem stages (48 KB each) between TMA and MMA; 2 TMEM accumulators (2 x 256 columns)
 // between MMA and epilogue, so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <cuda.h>
 #include <math.h>
@@ -26,16 +26,17 @@
 
 namespace upk {
 
-constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 32, TC_STAGES = 2;
-constexpr int TC_THREADS = 192;
-constexpr uint32_t TC_STAGE_BYTES = (2 * TC_BM * TC_BK + 2 * TC_BN * TC_BK) * 4;  // 98304
+constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 16, TC_STAGES = 3;  // 64-byte K rows (SWIZZLE_64B), 48 KB / stage
+constexpr int TC_EPI_WARPS = 8;  // two warps per TMEM lane quarter, each takes half of the 256 columns
+constexpr int TC_THREADS = 64 + TC_EPI_WARPS * 32;
+constexpr uint32_t TC_STAGE_BYTES = (2 * TC_BM * TC_BK + 2 * TC_BN * TC_BK) * 4;  // 49152
 
 struct __align__(1024) TcSmem {
   float a_hi[TC_STAGES][TC_BM * TC_BK];
   float a_lo[TC_STAGES][TC_BM * TC_BK];
   float b_hi[TC_STAGES][TC_BN * TC_BK];
   float b_lo[TC_STAGES][TC_BN * TC_BK];
-  float epi[4][32][33];
+  float epi[TC_EPI_WARPS][32][33];
   unsigned long long full[TC_STAGES], empty[TC_STAGES], tfull[2], tempty[2];
   uint32_t tmem_base;
 };
@@ -86,14 +87,16 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uin
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
-// start>>4 | LBO(=1)<<16 | SBO(=1024B>>4)<<32 | version(=1)<<46 | layout SWIZZLE_128B(=2)<<61
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout) for rows of
+// TC_BK fp32 = 64 bytes, SWIZZLE_64B: 8-row groups of 512 B.
+// start>>4 | LBO(=1)<<16 | SBO(=512B>>4)<<32 | version(=1)<<46 | layout SWIZZLE_64B(=4)<<61
+static_assert(TC_BK * 4 == 64, "descriptor below assumes 64-byte K rows");
 __device__ __forceinline__ uint64_t make_desc_sw128(const void* smem) {
   uint64_t d = (uint64_t)((smem_u32(smem) & 0x3ffff) >> 4);
   d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)(512 >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)4 << 61;
   return d;
 }
 // instruction descriptor: D=F32, A=B=TF32, both K-major, N=256, M=128 (cute::UMMA::InstrDescriptor)
@@ -157,7 +160,7 @@ k_similarity_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&sm.tfull[a], 1); mbar_init(&sm.tempty[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&sm.tfull[a], 1); mbar_init(&sm.tempty[a], TC_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -210,7 +213,7 @@ k_similarity_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
           const uint64_t bhi = make_desc_sw128(sm.b_hi[s]), blo = make_desc_sw128(sm.b_lo[s]);
 #pragma unroll
           for (int kk = 0; kk < TC_BK / 8; ++kk) {
-            const uint64_t adv = (uint64_t)(kk * 8 * 4 >> 4);  // 32 B along K inside the 128 B swizzle row
+            const uint64_t adv = (uint64_t)(kk * 8 * 4 >> 4);  // 32 B along K inside the swizzled row
             if (NTERMS == 3) {
               tc_mma_tf32(d_tmem, alo + adv, bhi + adv, kIdescTf32, (kc | kk) ? 1u : 0u);
               tc_mma_tf32(d_tmem, ahi + adv, blo + adv, kIdescTf32, 1u);
@@ -227,9 +230,15 @@ k_similarity_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
       }
     }
   } else {
-    // ===== epilogue warps (TMEM lane quarter = warp % 4) =====
+    // ===== epilogue warps (TMEM lane quarter = warp % 4; warps 2..5 take columns [0,128),
+    //       warps 6..9 columns [128,256)).  A single warp issues roughly one dependent instruction
+    //       every ~6 cycles, so the epilogue is kept short: multiply by 1/temp, pointer-increment
+    //       addressing, LDS/STS through a padded 32x33 transpose so every store is a 128-byte row
+    //       segment. =====
     const int q = warp & 3;
-    float (*tr)[33] = sm.epi[warp - 2];
+    const int half = (warp - 2) >> 2;
+    float* tr = &sm.epi[warp - 2][0][0];
+    const float inv_temp = 1.0f / temp;
     int it = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
       const int b = t / (mt * nt), rem = t - b * mt * nt;
@@ -238,10 +247,11 @@ k_similarity_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
       const uint32_t acc_ph = (it >> 1) & 1;
       mbar_wait(&sm.tfull[acc], acc_ph);
       tc_fence_after();
-      float* Cb = C + (size_t)b * M * N;
       const int row0 = mi * TC_BM + q * 32;
+      const int nrows = min(32, M - row0);
+      float* Cb = C + ((size_t)b * M + row0) * N;
 #pragma unroll 1
-      for (int cb = 0; cb < TC_BN / 32; ++cb) {
+      for (int cb = half * 4; cb < half * 4 + 4; ++cb) {
         const int col0 = ni * TC_BN + cb * 32;
         if (col0 >= N) break;
         uint32_t r[32];
@@ -250,15 +260,17 @@ k_similarity_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         for (int j = 0; j < 32; ++j) {
           float v = __uint_as_float(r[j]);
           if (MODE == 1) v = sqrtf(fmaxf(2.0f - 2.0f * v, 0.f));
-          tr[lane][j] = v / temp;
+          tr[lane * 33 + j] = v * inv_temp;
         }
         __syncwarp();
-        const int col = col0 + lane;
-        if (col < N) {
-#pragma unroll 8
-          for (int rr = 0; rr < 32; ++rr) {
-            const int row = row0 + rr;
-            if (row < M) Cb[(size_t)row * N + col] = tr[rr][lane];
+        if (col0 + lane < N && nrows > 0) {
+          float* dst = Cb + col0 + lane;
+          const float* src = tr + lane;
+          if (nrows == 32) {
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr) dst[(size_t)rr * N] = src[rr * 33];
+          } else {
+            for (int rr = 0; rr < nrows; ++rr) dst[(size_t)rr * N] = src[rr * 33];
           }
         }
         __syncwarp();
@@ -301,7 +313,7 @@ static int make_map(CUtensorMap* map, const float* base, int batch, int rows, in
   cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? UPK_OK : UPK_ERR_INVALID_ARG;
 }
