@@ -169,7 +169,7 @@ def main():
 
     from unopose_b200 import _lib
     from unopose_b200 import model_utils as MU
-    from unopose_b200.pipeline import input_bytes, run_hot_path, synthetic_inputs, to_device
+    from unopose_b200.pipeline import HostFedHotPath, input_bytes, run_hot_path, synthetic_inputs
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -275,21 +275,20 @@ def main():
     # ---- end to end through the public API with HOST (pinned) buffers: H2D of every step input,
     #      D2H of the step result, both inside the timed region
     host_sets = [synthetic_inputs(5000 + 1000 * rank + 17 * s, B, cfg, pin=True) for s in range(2)]
-    res_host = torch.empty((B, 13), dtype=torch.float32).pin_memory()
+    fed = HostFedHotPath(cfg, B, dev, overlap=not args.no_overlap)
 
     def e2e_step(i):
-        d = to_device(host_sets[i % len(host_sets)], dev)
-        o = run_hot_path(d, cfg, overlap=not args.no_overlap)
-        r = torch.cat([o["pred_R"].reshape(B, 9), o["pred_t"], o["pred_pose_score"].unsqueeze(1)], 1)
-        res_host.copy_(r, non_blocking=True)
-        torch.cuda.current_stream().synchronize()   # the caller reads the result every step
-        return res_host
+        # prefetch the NEXT step's inputs (copy stream) while this step computes; every timed step
+        # therefore contains one full H2D of a step's inputs, one compute and one D2H of the result
+        fed.stage((i + 1) % 2, host_sets[(i + 1) % len(host_sets)])
+        return fed.run(i % 2)
 
+    fed.stage(0, host_sets[0])
     for i in range(3):
         e2e_step(i)
     barrier()
     e0.record()
-    for i in range(args.steps):
+    for i in range(3, 3 + args.steps):
         e2e_step(i)
     e1.record()
     torch.cuda.synchronize()
@@ -299,6 +298,7 @@ def main():
         t = torch.tensor([ms_e], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_e = float(t.item())
+    res_host = fed.result
     e2e = {"value": B * world / (ms_e * 1e-3), "unit": "instances/s", "h2d_bytes_per_step": input_bytes(host_sets[0]),
            "d2h_bytes_per_step": res_host.numel() * 4, "ms_per_step": ms_e}
 
@@ -307,36 +307,49 @@ def main():
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the dominant stage's kernel
+    # ---- rooflines: one model per stage (algorithmic work per launch is defined in DESIGN.md §5);
+    #      `roofline` is the model of the stage with the largest share of the (serial) step time
     pk = peaks()
     total_stage = sum(stage_ms.values())
-    dom = max(stage_ms, key=stage_ms.get)
     n1 = cfg.n_fine + 1
-    roof_models = {
-        # stage -> (kernel, bound, algorithmic work per launch, unit scale)
-        "fine_similarity": ("k_sgemm_nt<0> (2049x2049x256 per instance)", "tensor", 2.0 * n1 * n1 * cfg.feat_dim * B),
-        "fine_pose": ("assign tile passes (3 reads of the 2049^2 fp32 matrix)", "hbm", 3.0 * n1 * n1 * 4 * B),
-        "fps_template+gather": ("fps_kernel<512,10> (5000->2048, serial chain)", "hbm",
-                                (12.0 * cfg.n_template + 4.0 * cfg.n_fine) * B),
-        "ball_query+group_query": ("ball_query_kernel + group_kernel", "hbm",
-                                   sum((12.0 * 2 * cfg.n_fine + 4.0 * cfg.n_fine * ns + 16.0 * cfg.n_fine * ns)
-                                       for _, ns in cfg.pe) * B),
-        "coarse_pose": ("k_score (K x 196 x 196 pairs, 6 lane-ops each)", "fp32",
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    fp32_peak = sms * 128 * 1.965e9 / 1e12          # T lane-op/s, whole chip at max clock
+    pe_bytes = sum((12.0 * 2 * cfg.n_fine + 4.0 * cfg.n_fine * ns + 16.0 * cfg.n_fine * ns) for _, ns in cfg.pe) * B
+    fps_ops = lambda n, m: 10.0 * (m - 1) * n * B   # 10 lane-ops per distance update
+    models = {
+        "fine_similarity": ("k_similarity_tc<0,3> (tcgen05 3xTF32, 2049x2049x256/instance) + k_normalize_split x2",
+                            "tensor", 2.0 * n1 * n1 * cfg.feat_dim * B),
+        "fine_pose": ("k_stats_stream + k_labels_stream + k_fine_rows_stream (3 reads of the 2049^2 fp32 matrix)",
+                      "hbm", 3.0 * n1 * n1 * 4 * B),
+        "fps_template+gather": ("fps_kernel<512,10> (5000->2048; serial chain, one SM per instance)", "fp32",
+                                fps_ops(cfg.n_template, cfg.n_fine)),
+        "fps_sparse_ref+gather": ("fps_kernel<512,4> (2048->196)", "fp32", fps_ops(cfg.n_fine, cfg.n_coarse)),
+        "fps_sparse_query+gather": ("fps_kernel<512,4> (2048->196)", "fp32", fps_ops(cfg.n_fine, cfg.n_coarse)),
+        "ball_query+group_query": ("ball_query_kernel + group_kernel", "hbm", pe_bytes),
+        "ball_query+group_ref": ("ball_query_kernel + group_kernel", "hbm", pe_bytes),
+        "coarse_pose": ("k_score (K x 196 x 196 point pairs, 6 lane-ops each) + assignment/sampling/top-K", "fp32",
                         6.0 * cfg.n_proposal2 * cfg.n_coarse * cfg.n_coarse * B),
+        "coarse_similarity": ("k_sgemm_nt<0> (fp32 SIMT, 197x197x256/instance)", "fp32",
+                              2.0 * (cfg.n_coarse + 1) ** 2 * cfg.feat_dim * B / 2),
     }
-    kname, bound, work = roof_models.get(dom, (dom, "hbm", float(set_bytes)))
-    dur_s = stage_ms[dom] * 1e-3
-    if bound == "tensor":
-        achieved, peak, unit = work / dur_s / 1e12, pk["tensor_sustained"], "TFLOP/s"
-    elif bound == "fp32":
-        sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        achieved, peak, unit = work / dur_s / 1e12, sms * 128 * 1.965e9 / 1e12, "Tlane-op/s"
-    else:
-        achieved, peak, unit = work / dur_s / 1e9, pk["hbm"], "GB/s"
-    roofline = {"kernel": kname, "stage": dom, "stage_share_of_step": stage_ms[dom] / total_stage,
-                "bound": "tensor" if bound == "tensor" else "hbm" if bound == "hbm" else "fp32-issue",
-                "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak, "traffic": None,
-                "peak_source": pk["source"], "duration_ms": stage_ms[dom]}
+
+    def roof(stage):
+        kname, bound, work = models[stage]
+        dur_s = stage_ms[stage] * 1e-3
+        if bound == "tensor":
+            achieved, peak, unit, bname = work / dur_s / 1e12, pk["tensor_sustained"], "TFLOP/s", "tensor"
+        elif bound == "fp32":
+            achieved, peak, unit, bname = work / dur_s / 1e12, fp32_peak, "Tlane-op/s", "fp32-issue"
+        else:
+            achieved, peak, unit, bname = work / dur_s / 1e9, pk["hbm"], "GB/s", "hbm"
+        return {"kernel": kname, "stage": stage, "stage_share_of_step": stage_ms[stage] / total_stage,
+                "bound": bname, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
+                "traffic": None, "peak_source": pk["source"] if bound != "fp32" else "#SM*128*1.965 GHz",
+                "duration_ms": stage_ms[stage]}
+
+    stage_rooflines = {k: roof(k) for k in stage_ms if k in models}
+    dom = max(stage_ms, key=stage_ms.get)
+    roofline = stage_rooflines[dom]
 
     line = {
         "metric": "instances_posed_per_s", "value": value, "unit": "instances/s", "n_gpus": world,
@@ -346,6 +359,7 @@ def main():
         "hypotheses_scored_per_s": hyp_per_s, "coarse_solve_ms": ms_c,
         "stage_ms": stage_ms,
         "roofline": roofline,
+        "stage_rooflines": stage_rooflines,
         "e2e": e2e,
         "gpu_launches": int(launches),
         "clocks": clocks,

@@ -164,6 +164,14 @@ int upk_coarse_pose(const float* atten, const float* score1, int score1_ld,
 /* Stage-wise entry points (same kernels; used for identical-input parity tests
  * and for hypothesis sharding across GPUs). */
 
+/* a2 + first half of a3 alone: masks w1[b,n1], w2[b,n2] and the normalised sampling CDF
+ * cdf[b,n1*n2] (model_utils.py:443-461). */
+size_t upk_coarse_assignment_workspace_bytes(int b, int n1, int n2);
+int upk_coarse_assignment(const float* atten, const float* score1, int score1_ld,
+                          const float* score2, int score2_ld, int b, int n1, int n2,
+                          void* workspace, size_t workspace_bytes, float* w1_out,
+                          float* w2_out, float* cdf_out, upk_stream_t stream);
+
 /* searchsorted(cdf,u) -> triplets -> Kabsch -> residual for hypotheses
  * [h_begin,h_end) of every instance (model_utils.py:462-475). Rs/ts/resid are
  * indexed by the global hypothesis index ([b,n_hyp,...]). */

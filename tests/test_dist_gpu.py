@@ -1,0 +1,36 @@
+"""GPU: hypothesis-sharded coarse solver (unopose_b200/dist.py) is bit-identical to the single-GPU solver.
+world=1 always; world=2 under torchrun/NCCL when the box has >= 2 GPUs."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from oracle import pose_oracle as PO
+from util_clouds import matching_batch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_sharded_equals_fused_world1(cuda):
+    from unopose_b200 import model_utils as MU
+    from unopose_b200.dist import coarse_pose_hypothesis_sharded
+
+    B, n, H, K = 3, 196, 5000, 300
+    d = {k: torch.from_numpy(v).to(cuda) for k, v in matching_batch(5, B, n, 128).items() if k in ("pts1", "pts2", "f1", "f2", "score")}
+    atten = PO.feature_similarity(d["f1"], d["f2"], "cosine", 0.1, True)
+    u = torch.rand(B, 3 * H, device=cuda)
+    R, t, s, m = MU._coarse(atten, d["score"], d["pts1"], d["pts2"], None, H, K, u=u, return_debug=True)
+    R2, t2, s2, pool2 = coarse_pose_hypothesis_sharded(atten, d["score"], d["pts1"], d["pts2"], H, K, u)
+    assert torch.equal(R, R2) and torch.equal(t, t2) and torch.equal(s, s2) and torch.equal(m["pool"], pool2)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_sharded_world2_nccl():
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(ROOT, "tests", "mp_hyp_shard.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "SHARD_OK" in r.stdout

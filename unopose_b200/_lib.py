@@ -39,6 +39,7 @@ _SIGNATURES = {
     "upk_feature_similarity": [c_f, c_f, c_i, c_i, c_i, c_i, c_fl, c_i, c_i, c_f, c_sz, c_f, c_st],
     "upk_coarse_pose": [c_f, c_f, c_i, c_f, c_i, c_f, c_f, c_f, c_i, c_f, c_i, c_i, c_i, c_i, c_i,
                         c_f, c_sz, c_f, c_f, c_f, c_f, c_f, c_st],
+    "upk_coarse_assignment": [c_f, c_f, c_i, c_f, c_i, c_i, c_i, c_i, c_f, c_sz, c_f, c_f, c_f, c_st],
     "upk_sample_hypotheses": [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_f, c_st],
     "upk_kabsch_triplets": [c_f, c_f, c_i, c_f, c_f, c_f, c_st],
     "upk_topk_smallest": [c_f, c_i, c_i, c_i, c_f, c_st],
@@ -54,6 +55,7 @@ _SIGNATURES = {
 _SIZE_FUNCS = {
     "upk_feature_similarity_workspace_bytes": [c_i, c_i, c_i, c_i, c_i],
     "upk_coarse_pose_workspace_bytes": [c_i, c_i, c_i, c_i, c_i],
+    "upk_coarse_assignment_workspace_bytes": [c_i, c_i, c_i],
     "upk_fine_pose_workspace_bytes": [c_i, c_i, c_i],
 }
 

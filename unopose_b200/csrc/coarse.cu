@@ -437,6 +437,38 @@ int upk_coarse_pose(const float* atten, const float* score1, int score1_ld, cons
 
 // ---- stage-wise entry points (identical-input parity tests, hypothesis sharding) ----
 
+size_t upk_coarse_assignment_workspace_bytes(int b, int n1, int n2) {
+  if (b <= 0 || n1 <= 0 || n2 <= 0) return 0;
+  Carver cv(nullptr);
+  AssignGeom g = assign_geom(n1 + 1, n2 + 1);
+  AssignWs a;
+  carve_assign(cv, b, g, a);
+  cv.take<float>((size_t)b * n1 * n2);
+  cv.take<double>((size_t)b * n1 * g.ntc);
+  return cv.bytes();
+}
+
+int upk_coarse_assignment(const float* atten, const float* score1, int score1_ld, const float* score2,
+                          int score2_ld, int b, int n1, int n2, void* workspace, size_t workspace_bytes,
+                          float* w1_out, float* w2_out, float* cdf_out, upk_stream_t stream) {
+  if (b < 0 || n1 <= 0 || n2 <= 0) return UPK_ERR_INVALID_ARG;
+  if (b == 0) return UPK_OK;
+  if (!atten || !workspace || !w1_out || !w2_out || !cdf_out) return UPK_ERR_INVALID_ARG;
+  if ((score1 == nullptr) != (score2 == nullptr)) return UPK_ERR_INVALID_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  AssignGeom g = assign_geom(n1 + 1, n2 + 1);
+  Carver cv(workspace);
+  AssignWs a;
+  carve_assign(cv, b, g, a);
+  float* pmat = cv.take<float>((size_t)b * n1 * n2);
+  double* prow = cv.take<double>((size_t)b * n1 * g.ntc);
+  if (cv.bytes() > workspace_bytes) return UPK_ERR_INVALID_ARG;
+  int rc;
+  if ((rc = run_assignment_labels(atten, score1, score1_ld, score2, score2_ld, b, g, a, w1_out, w2_out, st))) return rc;
+  if ((rc = run_coarse_P(atten, score1, score1_ld, score2, score2_ld, b, g, a, w1_out, w2_out, pmat, prow, st))) return rc;
+  return run_cdf(pmat, prow, b, n1, n2, g.ntc, cdf_out, st);
+}
+
 int upk_sample_hypotheses(const float* cdf, const float* u, const float* pts1, const float* pts2, int b,
                           int n1, int n2, int n_hyp, int h_begin, int h_end, int* idx1_out, int* idx2_out,
                           float* Rs, float* ts, float* resid, upk_stream_t stream) {

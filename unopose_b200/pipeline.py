@@ -160,3 +160,45 @@ def run_hot_path(inp, cfg=HotPathConfig(), stages=None, overlap=True):
     # and the next step's side chain starts with side.wait_stream(main): the caching allocator can
     # recycle them on the side stream without record_stream() (which would defer every reuse).
     return out
+
+
+class HostFedHotPath:
+    """Host-buffer front end of the hot path: pinned host inputs in, pinned host results out.
+
+    Two device input sets are kept; the host->device copy of step i+1 runs on a copy stream while
+    step i computes (events order buffer reuse), and the (B,13) result row [R(9) | t(3) | score]
+    is copied back to pinned memory every step."""
+
+    def __init__(self, cfg, batch, device, overlap=True):
+        self.cfg, self.batch, self.device, self.overlap = cfg, batch, torch.device(device), overlap
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.bufs = [None, None]
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.free = [torch.cuda.Event(), torch.cuda.Event()]
+        self.result = torch.empty((batch, 13), dtype=torch.float32).pin_memory()
+        self._staged = [False, False]
+
+    def stage(self, slot, host_inp):
+        """Enqueue the H2D copy of `host_inp` (pinned tensors) into device slot `slot`."""
+        if self.bufs[slot] is None:
+            self.bufs[slot] = {k: torch.empty(v.shape, dtype=v.dtype, device=self.device)
+                               for k, v in host_inp.items() if not k.startswith("_")}
+        with torch.cuda.stream(self.copy_stream):
+            if self._staged[slot]:
+                self.copy_stream.wait_event(self.free[slot])   # the step that used this slot has finished
+            for k, d in self.bufs[slot].items():
+                d.copy_(host_inp[k], non_blocking=True)
+            self.ready[slot].record(self.copy_stream)
+        self._staged[slot] = True
+
+    def run(self, slot):
+        """Run one step on device slot `slot` (its copy must have been staged); returns the pinned result."""
+        main = torch.cuda.current_stream(self.device)
+        main.wait_event(self.ready[slot])
+        o = run_hot_path(self.bufs[slot], self.cfg, overlap=self.overlap)
+        self.free[slot].record(main)
+        B = self.batch
+        r = torch.cat([o["pred_R"].reshape(B, 9), o["pred_t"], o["pred_pose_score"].unsqueeze(1)], 1)
+        self.result.copy_(r, non_blocking=True)
+        main.synchronize()    # the caller reads the result every step
+        return self.result
