@@ -41,10 +41,37 @@ __device__ __forceinline__ unsigned bitrev_n(unsigned v, int nbits) {
   return nbits == 0 ? 0u : (__brev(v) >> (32 - nbits));
 }
 
-template <int THREADS, int PPT>
+// Blackwell packed fp32 pairs (FADD2/FMUL2/FFMA2): two IEEE-rn operations per issue slot, bit-identical
+// to the scalar instructions lane by lane.
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
+template <int THREADS, int PPT, bool X2 = false>
 __global__ void __launch_bounds__(THREADS, 1)
 fps_kernel(const float* __restrict__ xyz, int n, int m, int bs_log2,
            int* __restrict__ idx_out) {
+  static_assert(!X2 || PPT % 2 == 0, "packed variant needs an even number of points per thread");
   extern __shared__ float smem_f[];
   float* sx = smem_f;
   float* sy = sx + n;
@@ -87,14 +114,37 @@ fps_kernel(const float* __restrict__ xyz, int n, int m, int bs_log2,
   for (int j = 1; j < m; ++j) {
     float best = -1.f;
     int bestp = 0;
+    if (X2) {
+      // (x2 - x1) == x2 + (-x1) exactly; d = fma(dz,dz, fma(dx,dx, dy*dy)) on two points per instruction
+      const unsigned long long nx = pack2(-x1, -x1), ny = pack2(-y1, -y1), nz = pack2(-z1, -z1);
 #pragma unroll
-    for (int p = 0; p < PPT; ++p) {
-      float d = sqdist_ref(px[p] - x1, py[p] - y1, pz[p] - z1);
-      float d2 = fminf(d, td[p]);
-      td[p] = d2;
-      bool g = d2 > best;
-      bestp = g ? p : bestp;
-      best = g ? d2 : best;
+      for (int p = 0; p < PPT; p += 2) {
+        unsigned long long dx = add2(pack2(px[p], px[p + 1]), nx);
+        unsigned long long dy = add2(pack2(py[p], py[p + 1]), ny);
+        unsigned long long dz = add2(pack2(pz[p], pz[p + 1]), nz);
+        unsigned long long dd = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
+        float da, db;
+        unpack2(dd, da, db);
+        float d2a = fminf(da, td[p]), d2b = fminf(db, td[p + 1]);
+        td[p] = d2a;
+        td[p + 1] = d2b;
+        bool ga = d2a > best;
+        bestp = ga ? p : bestp;
+        best = ga ? d2a : best;
+        bool gb = d2b > best;
+        bestp = gb ? p + 1 : bestp;
+        best = gb ? d2b : best;
+      }
+    } else {
+#pragma unroll
+      for (int p = 0; p < PPT; ++p) {
+        float d = sqdist_ref(px[p] - x1, py[p] - y1, pz[p] - z1);
+        float d2 = fminf(d, td[p]);
+        td[p] = d2;
+        bool g = d2 > best;
+        bestp = g ? p : bestp;
+        best = g ? d2 : best;
+      }
     }
     // d2 >= 0 for real points, so signed-int order of the bit patterns == float order and the
     // sentinel -1.0f (negative as int) loses against everything
@@ -165,7 +215,8 @@ fps_kernel_large(const float* __restrict__ xyz, int n, int m, int bs_log2,
   }
 }
 
-// UPK_FPS_CFG (dev knob): 1 = 1024-thread variants, 2 = 512-thread variants; default = tuned choice
+// UPK_FPS_CFG (dev knob): 1 = 1024-thread variants, 2 = 512-thread scalar, 4 = 512-thread packed f32x2;
+// default = tuned choice
 static int fps_cfg() {
   static int v = -1;
   if (v < 0) {
@@ -175,11 +226,24 @@ static int fps_cfg() {
   return v;
 }
 
-template <int THREADS, int PPT>
+static int fps_exclusive() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("UPK_FPS_EXCLUSIVE");
+    v = e ? atoi(e) : 0;  // measured: no gain on the step median, kept as an opt-in knob
+  }
+  return v;
+}
+
+template <int THREADS, int PPT, bool X2 = false>
 static int launch_fps(const float* xyz, int b, int n, int m, int bs_log2, int* out,
                       cudaStream_t st) {
   size_t smem = (size_t)n * 3 * sizeof(float);
-  auto kern = fps_kernel<THREADS, PPT>;
+  // A long FPS is a serial latency chain: when it overlaps other kernels on a second stream, CTAs that
+  // co-reside on its SM steal issue slots and stretch every one of its m-1 iterations.  Claiming most of
+  // the SM's shared memory keeps the SM exclusive (opt-in: UPK_FPS_EXCLUSIVE=1).
+  if (fps_exclusive() && (long long)n * m >= 4096LL * 1024LL && smem < 200 * 1024) smem = 200 * 1024;
+  auto kern = fps_kernel<THREADS, PPT, X2>;
   if (smem > 40 * 1024) {  // dynamic + the 512 B of static smem must stay within the default 48 KB
     UPK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
@@ -516,14 +580,16 @@ int upk_furthest_point_sampling(const float* xyz, int b, int n, int m, int* idx_
   if (n <= 2048) {
     if (cfg == 1) return launch_fps<1024, 2>(xyz, b, n, m, bs_log2, idx_out, st);
     if (cfg == 2) return launch_fps<512, 4>(xyz, b, n, m, bs_log2, idx_out, st);
-    return launch_fps<512, 4>(xyz, b, n, m, bs_log2, idx_out, st);
+    if (cfg == 4) return launch_fps<512, 4, true>(xyz, b, n, m, bs_log2, idx_out, st);
+    return launch_fps<512, 4, true>(xyz, b, n, m, bs_log2, idx_out, st);
   }
   if (n <= 3072) return launch_fps<1024, 3>(xyz, b, n, m, bs_log2, idx_out, st);
   if (n <= 4096) return launch_fps<1024, 4>(xyz, b, n, m, bs_log2, idx_out, st);
   if (n <= 5120) {
     if (cfg == 1) return launch_fps<1024, 5>(xyz, b, n, m, bs_log2, idx_out, st);
     if (cfg == 2) return launch_fps<512, 10>(xyz, b, n, m, bs_log2, idx_out, st);
-    return launch_fps<512, 10>(xyz, b, n, m, bs_log2, idx_out, st);
+    if (cfg == 4) return launch_fps<512, 10, true>(xyz, b, n, m, bs_log2, idx_out, st);
+    return launch_fps<512, 10, true>(xyz, b, n, m, bs_log2, idx_out, st);
   }
   if (n <= 8192) return launch_fps<512, 16>(xyz, b, n, m, bs_log2, idx_out, st);
   if (n <= 12288) return launch_fps<512, 24>(xyz, b, n, m, bs_log2, idx_out, st);

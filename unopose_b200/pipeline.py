@@ -162,6 +162,34 @@ def run_hot_path(inp, cfg=HotPathConfig(), stages=None, overlap=True):
     return out
 
 
+class GraphedHotPath:
+    """One hot-path step captured into a CUDA graph (both streams of `run_hot_path`, every kernel of the
+    C-ABI library, the torch.rand draw and the workspace allocations) and replayed: a step is ~45 short
+    launches, and issuing them from Python costs more than several of them take to run.
+
+    The graph is bound to the tensors of `inp` (static addresses): refill them in place (copy_) and call
+    replay().  Outputs are the same tensor objects on every replay."""
+
+    def __init__(self, inp, cfg=HotPathConfig(), overlap=True, warmup=2):
+        self.inp, self.cfg = inp, cfg
+        dev = inp["pts"].device
+        cur = torch.cuda.current_stream(dev)
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(cur)
+        with torch.cuda.stream(s):          # eager warm-up on a side stream (sets kernel attributes, fills pools)
+            for _ in range(warmup):
+                run_hot_path(inp, cfg, overlap=overlap)
+        cur.wait_stream(s)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = run_hot_path(inp, cfg, overlap=overlap)
+
+    def replay(self):
+        self.graph.replay()
+        return self.out
+
+
 class HostFedHotPath:
     """Host-buffer front end of the hot path: pinned host inputs in, pinned host results out.
 
@@ -169,8 +197,10 @@ class HostFedHotPath:
     step i computes (events order buffer reuse), and the (B,13) result row [R(9) | t(3) | score]
     is copied back to pinned memory every step."""
 
-    def __init__(self, cfg, batch, device, overlap=True):
+    def __init__(self, cfg, batch, device, overlap=True, use_graph=True):
         self.cfg, self.batch, self.device, self.overlap = cfg, batch, torch.device(device), overlap
+        self.use_graph = use_graph
+        self.graphs = [None, None]
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self.bufs = [None, None]
         self.ready = [torch.cuda.Event(), torch.cuda.Event()]
@@ -195,7 +225,12 @@ class HostFedHotPath:
         """Run one step on device slot `slot` (its copy must have been staged); returns the pinned result."""
         main = torch.cuda.current_stream(self.device)
         main.wait_event(self.ready[slot])
-        o = run_hot_path(self.bufs[slot], self.cfg, overlap=self.overlap)
+        if self.use_graph:
+            if self.graphs[slot] is None:
+                self.graphs[slot] = GraphedHotPath(self.bufs[slot], self.cfg, overlap=self.overlap)
+            o = self.graphs[slot].replay()
+        else:
+            o = run_hot_path(self.bufs[slot], self.cfg, overlap=self.overlap)
         self.free[slot].record(main)
         B = self.batch
         r = torch.cat([o["pred_R"].reshape(B, 9), o["pred_t"], o["pred_pose_score"].unsqueeze(1)], 1)
