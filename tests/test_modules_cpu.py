@@ -1,0 +1,78 @@
+"""CPU: the host-side (torch) parts of the module wrappers against golden vectors produced by the
+REFERENCE modules (tests/golden/make_module_golden.py), and state-dict compatibility at the real config."""
+import json
+import os
+
+import torch
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+class Cfg(dict):
+    __getattr__ = dict.__getitem__
+
+
+def _g():
+    return torch.load(os.path.join(GOLD, "modules_small.pt"), weights_only=False)
+
+
+def test_state_dict_names_and_shapes_match_reference():
+    from unopose_b200.modules import CoarsePointMatchingOneRef, FinePointMatchingOneRef, GeometricStructureEmbedding
+
+    keys = json.load(open(os.path.join(GOLD, "modules_state_keys.json")))
+    real_c = Cfg(nblock=3, input_dim=256, hidden_dim=256, out_dim=256, temp=0.1, sim_type="cosine", normalize_feat=True,
+                 nproposal1=6000, nproposal2=300)
+    real_f = Cfg(nblock=3, input_dim=256, hidden_dim=256, out_dim=256, pe_radius1=0.1, pe_radius2=0.2, focusing_factor=3,
+                 temp=0.1, sim_type="cosine", normalize_feat=True, use_lrf=True, use_xyz=True, nsample1=64, nsample2=256)
+    real_g = Cfg(sigma_d=0.2, sigma_a=15, angle_k=3, reduction_a="max", hidden_dim=256)
+    for name, mod in (("coarse", CoarsePointMatchingOneRef(real_c)), ("fine", FinePointMatchingOneRef(real_f)),
+                      ("geo", GeometricStructureEmbedding(real_g))):
+        mine = {k: list(v.shape) for k, v in mod.state_dict().items()}
+        assert mine == keys[name], (name, set(mine) ^ set(keys[name]))
+
+
+def test_geometric_embedding_matches_reference():
+    from unopose_b200.modules import GeometricStructureEmbedding
+
+    g = _g()
+    m = GeometricStructureEmbedding(Cfg(g["cfg_geo"])).eval()
+    m.load_state_dict(g["sd_geo"])
+    with torch.no_grad():
+        out = m(torch.cat([torch.ones(2, 1, 3), g["sp1"]], 1))
+    assert torch.allclose(out, g["geo1"], atol=2e-5, rtol=1e-5)
+
+
+def test_coarse_module_features_match_reference():
+    from unopose_b200.modules import CoarsePointMatchingOneRef
+
+    g = _g()
+    m = CoarsePointMatchingOneRef(Cfg(g["cfg_coarse"])).eval()
+    m.load_state_dict(g["sd_coarse"])           # strict: every reference parameter has a home
+    with torch.no_grad():
+        g1, g2, score = m.matching_features(g["sf1"], g["geo1"], g["sf2"], g["geo2"])
+    assert torch.allclose(g1, g["coarse_g1"], atol=1e-5, rtol=1e-4)
+    assert torch.allclose(g2, g["coarse_g2"], atol=1e-5, rtol=1e-4)
+    assert score.shape == (2, 2 * g["sp1"].shape[1]) and (score >= 0).all() and (score <= 1).all()
+
+
+def test_lrf_batch_and_global_lrf_match_reference():
+    from unopose_b200.model_utils import LRF
+    from unopose_b200.pointnet2.lrf import LRF_batch
+
+    g = _g()
+    out = LRF_batch(r_lrf=0.4)(g["p1"], g["lrf_grouped"].transpose(1, 2))
+    assert torch.allclose(out, g["lrf_batch"], atol=1e-4, rtol=1e-4)
+    p1 = g["p1"]
+    out = LRF(r_lrf=g["lrf_r"])(p1.mean(1, keepdim=True).transpose(1, 2), p1.transpose(1, 2).contiguous())
+    assert torch.allclose(out, g["lrf_global"], atol=1e-4, rtol=1e-4)
+
+
+def test_training_branch_is_explicitly_unsupported():
+    import pytest
+
+    from unopose_b200.modules import CoarsePointMatchingOneRef
+
+    g = _g()
+    m = CoarsePointMatchingOneRef(Cfg(g["cfg_coarse"])).train()
+    with pytest.raises(NotImplementedError):
+        m(g["sp1"], g["sf1"], g["geo1"], g["sp2"], g["sf2"], g["geo2"], g["radius"], {})

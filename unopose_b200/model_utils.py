@@ -13,7 +13,8 @@ import torch
 import torch.nn as nn
 
 from . import _lib as L
-from .pointnet2.pointnet2_utils import furthest_point_sample, gather_operation
+from .pointnet2.lrf import LRF  # noqa: F401  (reference model_utils.py:766-823)
+from .pointnet2.pointnet2_utils import furthest_point_sample, gather_operation  # noqa: F401
 
 
 def _f32c(x):

@@ -42,3 +42,39 @@ class LRF_batch(nn.Module):
         frame = torch.stack((xp, yp, zp), dim=3)  # columns x,y,z  (B,N,3,3)
         local = (xyz_group - centre) / self.r_lrf
         return torch.einsum("bnij,bnim->bnjm", frame, local)
+
+
+class LRF(nn.Module):
+    """Global (per-cloud) reference frame, anchored at a given centre — the reference class of the same
+    name (core/unopose/utils/model_utils.py:766-823).  Host-side torch code.
+
+    forward(xyz (B,3,1) centre, xyz_group (B,3,N) cloud) -> (B,3,N) coordinates in the frame, scaled by 1/r_lrf
+    with r_lrf a (B,) tensor."""
+
+    def __init__(self, r_lrf, eps=1e-10):
+        super().__init__()
+        self.eps = eps
+        self.r_lrf = r_lrf
+
+    def forward(self, xyz, xyz_group):
+        B, _, N = xyz_group.shape
+        r = self.r_lrf[:, None, None]
+        to_centre = xyz - xyz_group                                   # p - p_i  (B,3,N)
+        cov = torch.bmm(to_centre, to_centre.transpose(1, 2)) / N
+        _, _, v = torch.svd(cov)
+        z_raw = v[..., -1]                                            # (B,3)
+        with torch.no_grad():
+            h = torch.einsum("bi,bin->bn", z_raw, to_centre)
+            vote = (h > 1e-3).sum(-1) - (h < -1e-3).sum(-1)
+            sign = 1.0 - 2.0 * (vote < 0).to(xyz_group.dtype)
+        zp = sign.unsqueeze(-1) * z_raw                               # (B,3)
+        rel = -to_centre
+        height = torch.einsum("bi,bin->bn", zp, rel)                  # (B,N)
+        in_plane = rel - zp.unsqueeze(2) * height.unsqueeze(1)
+        dist = torch.sqrt((rel ** 2).sum(dim=1))                      # (B,N)
+        alpha = (self.r_lrf[:, None] - dist) ** 2
+        x_dir = ((alpha * height * height).unsqueeze(1) * in_plane).sum(2)
+        xp = x_dir / (torch.sqrt((x_dir ** 2).sum(1, keepdim=True)) + self.eps)
+        yp = torch.cross(xp, zp, dim=1)
+        frame = torch.stack((xp, yp, zp), dim=2)                      # columns x,y,z
+        return torch.einsum("bij,bin->bjn", frame, (xyz_group - xyz) / r)
