@@ -365,6 +365,13 @@ def main():
                 "duration_ms": stage_ms[stage]}
 
     stage_rooflines = {k: roof(k) for k in stage_ms if k in models}
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tpath):       # measured DRAM traffic per launch from the committed ncu --set full capture
+        tj = json.load(open(tpath))
+        for k, r in stage_rooflines.items():
+            if k in tj["stage_traffic_bytes"]:
+                r["traffic"] = tj["stage_traffic_bytes"][k] * B / tj["batch"]
+                r["traffic_source"] = "profiles/r1_traffic.json (ncu --set full, scaled by batch)"
     dom = max(stage_ms, key=stage_ms.get)
     roofline = stage_rooflines[dom]
 

@@ -430,7 +430,79 @@ __device__ __forceinline__ float ex2_fast(float x) {
   return y;
 }
 
+// Butterfly reduction of N (power of two) per-lane values across the warp in log2(N) "halving" steps
+// (each step exchanges half of the values) + the remaining xor steps on one value: N=8 needs
+// 4+2+1+1+1 = 9 shuffles instead of 40.  On return v[0] of lane l holds the total of value index
+// l >> (5 - log2 N), identical in all lanes of that group.
+template <int N, class Op>
+__device__ __forceinline__ void warp_reduce_multi(float (&v)[N], Op op) {
+  const int lane = threadIdx.x & 31;
+  int offset = 16;
+#pragma unroll
+  for (int n = N; n > 1; n >>= 1, offset >>= 1) {
+    const bool upper = (lane & offset) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      float send = upper ? v[i] : v[i + n / 2];
+      float keep = upper ? v[i + n / 2] : v[i];
+      v[i] = op(keep, __shfl_xor_sync(kFull, send, offset));
+    }
+  }
+#pragma unroll
+  for (; offset > 0; offset >>= 1) v[0] = op(v[0], __shfl_xor_sync(kFull, v[0], offset));
+}
+struct OpAdd { __device__ __forceinline__ float operator()(float a, float b) const { return a + b; } };
+struct OpMax { __device__ __forceinline__ float operator()(float a, float b) const { return fmaxf(a, b); } };
+
+// 8 coalesced loads of one 256-column row segment (lane owns columns lane + 32k).  CHECK = edge tile.
+template <bool CHECK>
+__device__ __forceinline__ void load_row8(const float* __restrict__ rowptr, int ncols_left, bool row_ok, float fill,
+                                          float (&v)[ST_CPT]) {
+#pragma unroll
+  for (int k = 0; k < ST_CPT; ++k) {
+    if (CHECK) v[k] = (row_ok && 32 * k < ncols_left) ? __ldg(rowptr + 32 * k) : fill;
+    else v[k] = __ldg(rowptr + 32 * k);
+  }
+}
+
 // pass 1: (max, sum exp) partials per row (exact two-step per row) and per column (online)
+template <bool CHECK>
+__device__ __forceinline__ void stats_stream_body(const float* __restrict__ A, int R, int C, int ntc, int b, int tc,
+                                                  int r0, int c0, int warp, int lane, float (&cm)[ST_CPT],
+                                                  float (&cs)[ST_CPT], float2* __restrict__ rowpart) {
+  const int ncols_left = C - c0 - lane;
+  for (int rr = warp; rr < ST_TR; rr += 2 * ST_WARPS) {
+    const int ga = r0 + rr, gb = ga + ST_WARPS;
+    if (CHECK && ga >= R) break;
+    const bool hasb = !CHECK || gb < R;
+    float va[ST_CPT], vb[ST_CPT];
+    const float* pa = A + (size_t)ga * C + c0 + lane;
+    load_row8<CHECK>(pa, ncols_left, true, -INFINITY, va);
+    load_row8<CHECK>(pa + (size_t)ST_WARPS * C, ncols_left, hasb, -INFINITY, vb);
+    float mx[2] = {va[0], vb[0]};
+#pragma unroll
+    for (int k = 1; k < ST_CPT; ++k) { mx[0] = fmaxf(mx[0], va[k]); mx[1] = fmaxf(mx[1], vb[k]); }
+    warp_reduce_multi<2>(mx, OpMax());                       // lanes 0-15: row a, lanes 16-31: row b
+    const float ma = __shfl_sync(kFull, mx[0], 0), mb = __shfl_sync(kFull, mx[0], 16);
+    const float mal = ma * kLog2e, mbl = mb * kLog2e;
+    float sm[2] = {0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < ST_CPT; ++k) {
+      sm[0] += ex2_fast(fmaf(va[k], kLog2e, -mal));
+      sm[1] += ex2_fast(fmaf(vb[k], kLog2e, -mbl));
+      // online column update with both rows
+      float mn = fmaxf(cm[k], fmaxf(va[k], vb[k]));
+      float mnl = mn * kLog2e;
+      cs[k] = cs[k] * ex2_fast(fmaf(cm[k], kLog2e, -mnl)) + ex2_fast(fmaf(va[k], kLog2e, -mnl)) +
+              ex2_fast(fmaf(vb[k], kLog2e, -mnl));
+      cm[k] = mn;
+    }
+    warp_reduce_multi<2>(sm, OpAdd());
+    if (lane == 0) rowpart[((size_t)b * R + ga) * ntc + tc] = make_float2(ma, sm[0]);
+    if (lane == 16 && hasb) rowpart[((size_t)b * R + gb) * ntc + tc] = make_float2(mb, sm[0]);
+  }
+}
+
 __global__ void __launch_bounds__(ST_WARPS * 32)
 k_stats_stream(const float* __restrict__ atten, int R, int C, int ntr, int ntc,
                float2* __restrict__ rowpart, float2* __restrict__ colpart) {
@@ -440,48 +512,10 @@ k_stats_stream(const float* __restrict__ atten, int R, int C, int ntr, int ntc,
   const int r0 = tr * ST_TR, c0 = tc * ST_TC;
   const float* A = atten + (size_t)b * R * C;
   float cm[ST_CPT], cs[ST_CPT];
-  bool cok[ST_CPT];
 #pragma unroll
-  for (int k = 0; k < ST_CPT; ++k) {
-    cm[k] = -INFINITY;
-    cs[k] = 0.f;
-    cok[k] = c0 + lane + 32 * k < C;
-  }
-  for (int rr = warp; rr < ST_TR; rr += 2 * ST_WARPS) {
-    const int ga = r0 + rr, gb = ga + ST_WARPS;
-    if (ga >= R) break;
-    const bool hasb = gb < R;
-    float va[ST_CPT], vb[ST_CPT];
-#pragma unroll
-    for (int k = 0; k < ST_CPT; ++k) {
-      va[k] = cok[k] ? __ldg(A + (size_t)ga * C + c0 + lane + 32 * k) : -INFINITY;
-      vb[k] = (cok[k] && hasb) ? __ldg(A + (size_t)gb * C + c0 + lane + 32 * k) : -INFINITY;
-    }
-    float ma = va[0], mb = vb[0];
-#pragma unroll
-    for (int k = 1; k < ST_CPT; ++k) { ma = fmaxf(ma, va[k]); mb = fmaxf(mb, vb[k]); }
-    ma = warp_max(ma);
-    mb = warp_max(mb);
-    const float mal = ma * kLog2e, mbl = mb * kLog2e;
-    float sa = 0.f, sb = 0.f;
-#pragma unroll
-    for (int k = 0; k < ST_CPT; ++k) {
-      sa += ex2_fast(fmaf(va[k], kLog2e, -mal));
-      sb += ex2_fast(fmaf(vb[k], kLog2e, -mbl));
-      // online column update with both rows
-      float mn = fmaxf(cm[k], fmaxf(va[k], vb[k]));
-      float mnl = mn * kLog2e;
-      cs[k] = cs[k] * ex2_fast(fmaf(cm[k], kLog2e, -mnl)) + ex2_fast(fmaf(va[k], kLog2e, -mnl)) +
-              ex2_fast(fmaf(vb[k], kLog2e, -mnl));
-      cm[k] = mn;
-    }
-    sa = warp_sum(sa);
-    sb = warp_sum(sb);
-    if (lane == 0) {
-      rowpart[((size_t)b * R + ga) * ntc + tc] = make_float2(ma, sa);
-      if (hasb) rowpart[((size_t)b * R + gb) * ntc + tc] = make_float2(mb, sb);
-    }
-  }
+  for (int k = 0; k < ST_CPT; ++k) { cm[k] = -INFINITY; cs[k] = 0.f; }
+  if (r0 + ST_TR <= R && c0 + ST_TC <= C) stats_stream_body<false>(A, R, C, ntc, b, tc, r0, c0, warp, lane, cm, cs, rowpart);
+  else stats_stream_body<true>(A, R, C, ntc, b, tc, r0, c0, warp, lane, cm, cs, rowpart);
 #pragma unroll
   for (int k = 0; k < ST_CPT; ++k) s_col[warp][lane + 32 * k] = make_float2(cm[k], cs[k]);
   __syncthreads();
@@ -523,7 +557,63 @@ __device__ __forceinline__ void load_col_consts(ColConst& k, int b, int C, int c
   }
 }
 
+// per-row constants (broadcast loads): rm_i*log2e and s1_i/rs_i
+__device__ __forceinline__ void load_row_consts(int b, int R, int g, const float* __restrict__ rmax,
+                                                const float* __restrict__ rsum, const float* __restrict__ score1,
+                                                int ld1, float& rml, float& rmul) {
+  rml = rmax[(size_t)b * R + g] * kLog2e;
+  const float s1 = (g > 0 && score1) ? score1[(size_t)b * ld1 + g - 1] : 1.f;
+  rmul = s1 / rsum[(size_t)b * R + g];
+}
+
 // pass 2: background-vs-foreground arg-max tests (see k_labels_tile)
+template <bool CHECK>
+__device__ __forceinline__ void labels_stream_body(const float* __restrict__ A, int R, int C, int ntc, int b, int tc,
+                                                   int r0, int c0, int warp, int lane, const ColConst& kc,
+                                                   float (&cmx)[ST_CPT], const float* __restrict__ rmax,
+                                                   const float* __restrict__ rsum, const float* __restrict__ score1,
+                                                   int ld1, float* __restrict__ rowpm, float* __restrict__ ai0,
+                                                   float* __restrict__ a0j) {
+  const int ncols_left = C - c0 - lane;
+  const bool first_col_mine = (c0 == 0 && lane == 0);  // global column 0 == my k = 0
+  for (int rr = warp; rr < ST_TR; rr += 2 * ST_WARPS) {
+    const int ga = r0 + rr, gb = ga + ST_WARPS;
+    if (CHECK && ga >= R) break;
+    const bool hasb = !CHECK || gb < R;
+    float va[ST_CPT], vb[ST_CPT];
+    const float* pa = A + (size_t)ga * C + c0 + lane;
+    load_row8<CHECK>(pa, ncols_left, true, 0.f, va);
+    load_row8<CHECK>(pa + (size_t)ST_WARPS * C, ncols_left, hasb, 0.f, vb);
+    float rmla, rmula, rmlb, rmulb;
+    load_row_consts(b, R, ga, rmax, rsum, score1, ld1, rmla, rmula);
+    load_row_consts(b, R, hasb ? gb : ga, rmax, rsum, score1, ld1, rmlb, rmulb);
+    float rm[2] = {-INFINITY, -INFINITY};
+    float a0 = 0.f, b0 = 0.f;
+#pragma unroll
+    for (int k = 0; k < ST_CPT; ++k) {
+      float aa = (ex2_fast(fmaf(va[k], 2.f * kLog2e, -(rmla + kc.cml[k]))) * rmula) * kc.cmul[k];
+      float ab = (ex2_fast(fmaf(vb[k], 2.f * kLog2e, -(rmlb + kc.cml[k]))) * rmulb) * kc.cmul[k];
+      if (k == 0 && first_col_mine) {
+        a0 = aa; b0 = ab;            // background column: excluded from the row max
+      } else {
+        rm[0] = fmaxf(rm[0], aa);
+        rm[1] = fmaxf(rm[1], ab);
+      }
+      // column max over rows >= 1 ; row 0 is the background row (only in the tile row tr == 0, warp 0)
+      if (ga > 0) cmx[k] = fmaxf(cmx[k], aa);
+      else if (32 * k < ncols_left) a0j[(size_t)b * C + c0 + lane + 32 * k] = aa;
+      if (hasb) cmx[k] = fmaxf(cmx[k], ab);
+    }
+    warp_reduce_multi<2>(rm, OpMax());
+    if (lane == 0) rowpm[((size_t)b * R + ga) * ntc + tc] = rm[0];
+    if (lane == 16 && hasb) rowpm[((size_t)b * R + gb) * ntc + tc] = rm[0];
+    if (first_col_mine) {
+      ai0[(size_t)b * R + ga] = a0;
+      if (hasb) ai0[(size_t)b * R + gb] = b0;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(ST_WARPS * 32)
 k_labels_stream(const float* __restrict__ atten, int R, int C, int ntr, int ntc,
                 const float* __restrict__ rmax, const float* __restrict__ rsum,
@@ -541,49 +631,10 @@ k_labels_stream(const float* __restrict__ atten, int R, int C, int ntr, int ntc,
   float cmx[ST_CPT];
 #pragma unroll
   for (int k = 0; k < ST_CPT; ++k) cmx[k] = -INFINITY;
-  const bool first_col_mine = (c0 == 0 && lane == 0);  // global column 0 == my k = 0
-  for (int rr = warp; rr < ST_TR; rr += 2 * ST_WARPS) {
-    const int ga = r0 + rr, gb = ga + ST_WARPS;
-    if (ga >= R) break;
-    const bool hasb = gb < R;
-    float va[ST_CPT], vb[ST_CPT];
-#pragma unroll
-    for (int k = 0; k < ST_CPT; ++k) {
-      bool ok = c0 + lane + 32 * k < C;
-      va[k] = ok ? __ldg(A + (size_t)ga * C + c0 + lane + 32 * k) : 0.f;
-      vb[k] = (ok && hasb) ? __ldg(A + (size_t)gb * C + c0 + lane + 32 * k) : 0.f;
-    }
-    const int gbb = hasb ? gb : ga;
-    const float rmla = rmax[(size_t)b * R + ga] * kLog2e, rmlb = rmax[(size_t)b * R + gbb] * kLog2e;
-    const float s1a = (ga > 0 && score1) ? score1[(size_t)b * ld1 + ga - 1] : 1.f;
-    const float s1b = (gbb > 0 && score1) ? score1[(size_t)b * ld1 + gbb - 1] : 1.f;
-    const float rmula = s1a / rsum[(size_t)b * R + ga], rmulb = s1b / rsum[(size_t)b * R + gbb];
-    float ra = -INFINITY, rb = -INFINITY, a0 = 0.f, b0 = 0.f;
-#pragma unroll
-    for (int k = 0; k < ST_CPT; ++k) {
-      float aa = (ex2_fast(fmaf(va[k], 2.f * kLog2e, -(rmla + kc.cml[k]))) * rmula) * kc.cmul[k];
-      float ab = (ex2_fast(fmaf(vb[k], 2.f * kLog2e, -(rmlb + kc.cml[k]))) * rmulb) * kc.cmul[k];
-      if (k == 0 && first_col_mine) {
-        a0 = aa; b0 = ab;            // background column: excluded from the row max
-      } else {
-        ra = fmaxf(ra, aa);
-        rb = fmaxf(rb, ab);
-      }
-      // column max over rows >= 1 ; row 0 is the background row
-      if (ga > 0) cmx[k] = fmaxf(cmx[k], aa); else if (c0 + lane + 32 * k < C) a0j[(size_t)b * C + c0 + lane + 32 * k] = aa;
-      if (hasb) cmx[k] = fmaxf(cmx[k], ab);
-    }
-    ra = warp_max(ra);
-    rb = warp_max(rb);
-    if (lane == 0) {
-      rowpm[((size_t)b * R + ga) * ntc + tc] = ra;
-      if (hasb) rowpm[((size_t)b * R + gb) * ntc + tc] = rb;
-      if (c0 == 0) {
-        ai0[(size_t)b * R + ga] = a0;
-        if (hasb) ai0[(size_t)b * R + gb] = b0;
-      }
-    }
-  }
+  if (r0 + ST_TR <= R && c0 + ST_TC <= C && r0 > 0)
+    labels_stream_body<false>(A, R, C, ntc, b, tc, r0, c0, warp, lane, kc, cmx, rmax, rsum, score1, ld1, rowpm, ai0, a0j);
+  else
+    labels_stream_body<true>(A, R, C, ntc, b, tc, r0, c0, warp, lane, kc, cmx, rmax, rsum, score1, ld1, rowpm, ai0, a0j);
 #pragma unroll
   for (int k = 0; k < ST_CPT; ++k) s_col[warp][lane + 32 * k] = cmx[k];
   __syncthreads();
@@ -597,6 +648,47 @@ k_labels_stream(const float* __restrict__ atten, int R, int C, int ntr, int ntc,
 }
 
 // pass 3 (fine): per row  sum_{j>=1} A_ij w2_j {x_j, y_j, z_j, 1}
+template <bool CHECK>
+__device__ __forceinline__ void rows_stream_body(const float* __restrict__ A, int R, int C, int ntc, int b, int tc,
+                                                 int r0, int c0, int warp, int lane, const ColConst& kc,
+                                                 const float (&px)[ST_CPT], const float (&py)[ST_CPT],
+                                                 const float (&pz)[ST_CPT], const float* __restrict__ rmax,
+                                                 const float* __restrict__ rsum, const float* __restrict__ score1,
+                                                 int ld1, float4* __restrict__ rowpart4) {
+  const int ncols_left = C - c0 - lane;
+  const int N1 = R - 1;
+  for (int rr = warp; rr < ST_TR; rr += 2 * ST_WARPS) {
+    const int ga = r0 + rr, gb = ga + ST_WARPS;
+    if (CHECK && ga >= R) break;
+    const bool hasb = !CHECK || gb < R;
+    float va[ST_CPT], vb[ST_CPT];
+    const float* pa = A + (size_t)ga * C + c0 + lane;
+    load_row8<CHECK>(pa, ncols_left, true, 0.f, va);
+    load_row8<CHECK>(pa + (size_t)ST_WARPS * C, ncols_left, hasb, 0.f, vb);
+    float rmla, rmula, rmlb, rmulb;
+    load_row_consts(b, R, ga, rmax, rsum, score1, ld1, rmla, rmula);
+    load_row_consts(b, R, hasb ? gb : ga, rmax, rsum, score1, ld1, rmlb, rmulb);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // a: x y z w | b: x y z w
+#pragma unroll
+    for (int k = 0; k < ST_CPT; ++k) {
+      float aa = ex2_fast(fmaf(va[k], 2.f * kLog2e, -(rmla + kc.cml[k]))) * kc.cmul[k];
+      float ab = ex2_fast(fmaf(vb[k], 2.f * kLog2e, -(rmlb + kc.cml[k]))) * kc.cmul[k];
+      acc[0] = fmaf(aa, px[k], acc[0]); acc[1] = fmaf(aa, py[k], acc[1]); acc[2] = fmaf(aa, pz[k], acc[2]); acc[3] += aa;
+      acc[4] = fmaf(ab, px[k], acc[4]); acc[5] = fmaf(ab, py[k], acc[5]); acc[6] = fmaf(ab, pz[k], acc[6]); acc[7] += ab;
+    }
+    warp_reduce_multi<8>(acc, OpAdd());          // lane group (lane >> 2) holds component (lane >> 2)
+    if ((lane & 3) == 0) {
+      const int comp = lane >> 2;                // 0..3 row a, 4..7 row b
+      const bool isb = comp >= 4;
+      const int g = isb ? gb : ga;
+      if (g > 0 && (!isb || hasb)) {
+        float* dst = reinterpret_cast<float*>(rowpart4 + ((size_t)b * N1 + g - 1) * ntc + tc) + (comp & 3);
+        *dst = acc[0] * (isb ? rmulb : rmula);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(ST_WARPS * 32)
 k_fine_rows_stream(const float* __restrict__ atten, int R, int C, int ntc,
                    const float* __restrict__ rmax, const float* __restrict__ rsum,
@@ -607,7 +699,7 @@ k_fine_rows_stream(const float* __restrict__ atten, int R, int C, int ntc,
   const int b = blockIdx.z, tr = blockIdx.y, tc = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r0 = tr * ST_TR, c0 = tc * ST_TC;
-  const int N1 = R - 1, N2 = C - 1;
+  const int N2 = C - 1;
   const float* A = atten + (size_t)b * R * C;
   ColConst kc;
   load_col_consts(kc, b, C, c0, lane, cmax, csum, score2, ld2);
@@ -620,39 +712,10 @@ k_fine_rows_stream(const float* __restrict__ atten, int R, int C, int ntc,
     px[k] = p[0]; py[k] = p[1]; pz[k] = p[2];
     kc.cmul[k] = ok ? kc.cmul[k] * w2[(size_t)b * N2 + gj - 1] : 0.f;  // fold the column mask, drop the bg column
   }
-  for (int rr = warp; rr < ST_TR; rr += 2 * ST_WARPS) {
-    int ga = r0 + rr, gb = ga + ST_WARPS;
-    if (ga >= R) break;
-    const bool hasb = gb < R;
-    float va[ST_CPT], vb[ST_CPT];
-#pragma unroll
-    for (int k = 0; k < ST_CPT; ++k) {
-      bool ok = c0 + lane + 32 * k < C;
-      va[k] = ok ? __ldg(A + (size_t)ga * C + c0 + lane + 32 * k) : 0.f;
-      vb[k] = (ok && hasb) ? __ldg(A + (size_t)gb * C + c0 + lane + 32 * k) : 0.f;
-    }
-    const int gbb = hasb ? gb : ga;
-    const float rmla = rmax[(size_t)b * R + ga] * kLog2e, rmlb = rmax[(size_t)b * R + gbb] * kLog2e;
-    const float s1a = (ga > 0 && score1) ? score1[(size_t)b * ld1 + ga - 1] : 1.f;
-    const float s1b = (gbb > 0 && score1) ? score1[(size_t)b * ld1 + gbb - 1] : 1.f;
-    const float rmula = s1a / rsum[(size_t)b * R + ga], rmulb = s1b / rsum[(size_t)b * R + gbb];
-    float ax = 0.f, ay = 0.f, az = 0.f, aw = 0.f, bx = 0.f, by = 0.f, bz = 0.f, bw = 0.f;
-#pragma unroll
-    for (int k = 0; k < ST_CPT; ++k) {
-      float aa = ex2_fast(fmaf(va[k], 2.f * kLog2e, -(rmla + kc.cml[k]))) * kc.cmul[k];
-      float ab = ex2_fast(fmaf(vb[k], 2.f * kLog2e, -(rmlb + kc.cml[k]))) * kc.cmul[k];
-      ax = fmaf(aa, px[k], ax); ay = fmaf(aa, py[k], ay); az = fmaf(aa, pz[k], az); aw += aa;
-      bx = fmaf(ab, px[k], bx); by = fmaf(ab, py[k], by); bz = fmaf(ab, pz[k], bz); bw += ab;
-    }
-    ax = warp_sum(ax); ay = warp_sum(ay); az = warp_sum(az); aw = warp_sum(aw);
-    bx = warp_sum(bx); by = warp_sum(by); bz = warp_sum(bz); bw = warp_sum(bw);
-    if (lane == 0) {
-      if (ga > 0)
-        rowpart4[((size_t)b * N1 + ga - 1) * ntc + tc] = make_float4(ax * rmula, ay * rmula, az * rmula, aw * rmula);
-      if (hasb)
-        rowpart4[((size_t)b * N1 + gb - 1) * ntc + tc] = make_float4(bx * rmulb, by * rmulb, bz * rmulb, bw * rmulb);
-    }
-  }
+  if (r0 + ST_TR <= R && c0 + ST_TC <= C)
+    rows_stream_body<false>(A, R, C, ntc, b, tc, r0, c0, warp, lane, kc, px, py, pz, rmax, rsum, score1, ld1, rowpart4);
+  else
+    rows_stream_body<true>(A, R, C, ntc, b, tc, r0, c0, warp, lane, kc, px, py, pz, rmax, rsum, score1, ld1, rowpart4);
 }
 
 // ------------------------------------------------------------------ host launchers
