@@ -233,25 +233,21 @@ k_topk_smallest(const float* __restrict__ vals, int H, int K, int* __restrict__ 
 // ---------------------------------------------------------------- (4) scoring
 // For hypothesis (R,t):  X = (pts1 - t) @ R ; d_i = sqrt(clamp(min_j (|X_i|^2 - 2 X_i.Y_j + |Y_j|^2), 0))
 // score = sum_i w1_i / (sum_i d_i w1_i + 1e-8)        (model_utils.py:481-485, pairwise_distance :246-256)
-// One CTA per (instance, kept hypothesis); model points staged in smem as (x,y,z,|y|^2);
-// 6 issue slots per point pair; the (B*K,N1,N2) distance tensor never exists.
+// One CTA per (instance, kept hypothesis); model points staged in smem (SoA x|y|z||y|^2), four model
+// points per step with packed f32x2 arithmetic (4.5 issue slots per point pair); the (B*K,N1,N2) distance tensor never exists.
 constexpr int SC_THREADS = 128;
 
 __global__ void __launch_bounds__(SC_THREADS)
 k_score(const float* __restrict__ pts1, const float* __restrict__ model, const float* __restrict__ w1,
         const float* __restrict__ Rs, const float* __restrict__ ts, const int* __restrict__ top,
         int n1, int nm, int H, int K, int k0, float* __restrict__ scores) {
-  extern __shared__ float4 sm_model[];  // nm
+  extern __shared__ __align__(16) float sm_model[];  // 4 x nm_pad (SoA x | y | z | |y|^2)
   __shared__ double s_red[2][SC_THREADS / 32];
   const int b = blockIdx.y;
   const int k = k0 + blockIdx.x;
-  const float* mb = model + (size_t)b * nm * 3;
-  for (int j = threadIdx.x; j < nm; j += SC_THREADS) {
-    float x = mb[j * 3 + 0], y = mb[j * 3 + 1], z = mb[j * 3 + 2];
-    // y2 = sum(y**2, -1): products rounded separately, then summed
-    float y2 = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
-    sm_model[j] = make_float4(x, y, z, y2);
-  }
+  const int nm_pad = (nm + 3) & ~3;
+  float* mx = sm_model; float* my = mx + nm_pad; float* mz = my + nm_pad; float* mn = mz + nm_pad;
+  stage_model_soa(model + (size_t)b * nm * 3, nm, nm_pad, mx, my, mz, mn);
   const int h = top ? top[(size_t)b * K + k] : k;
   const float* R = Rs + ((size_t)b * H + h) * 9;
   const float* t = ts + ((size_t)b * H + h) * 3;
@@ -267,14 +263,7 @@ k_score(const float* __restrict__ pts1, const float* __restrict__ model, const f
     float x1 = fmaf(d2, r21, fmaf(d1, r11, d0 * r01));
     float x2 = fmaf(d2, r22, fmaf(d1, r12, d0 * r02));
     float xx = __fadd_rn(__fadd_rn(__fmul_rn(x0, x0), __fmul_rn(x1, x1)), __fmul_rn(x2, x2));
-    float best = INFINITY;
-#pragma unroll 4
-    for (int j = 0; j < nm; ++j) {
-      float4 q = sm_model[j];
-      float xy = fmaf(x2, q.z, fmaf(x1, q.y, x0 * q.x));
-      float d = __fadd_rn(fmaf(-2.0f, xy, xx), q.w);  // (x2 - 2xy) + y2
-      best = fminf(best, d);
-    }
+    float best = nn_min_expansion(mx, my, mz, mn, nm_pad, x0, x1, x2, xx);
     float dist = sqrtf(fmaxf(best, 0.f));
     float w = w1[(size_t)b * n1 + i];
     num += (double)w;
@@ -362,7 +351,7 @@ static int launch_score(const float* pts1, const float* model, const float* w1, 
                         const float* ts, const int* top, int b, int n1, int nm, int H, int K, int k0, int k1,
                         float* scores, cudaStream_t st) {
   if (k1 <= k0) return UPK_OK;
-  size_t smem = (size_t)nm * sizeof(float4);
+  size_t smem = (size_t)((nm + 3) & ~3) * 4 * sizeof(float);
   if (smem > 200 * 1024) return UPK_ERR_UNSUPPORTED;
   if (smem > 40 * 1024)
     UPK_CUDA_TRY(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -404,9 +393,13 @@ int upk_coarse_pose(const float* atten, const float* score1, int score1_ld, cons
   if (cv.bytes() > workspace_bytes) return UPK_ERR_INVALID_ARG;
   if (!model_pts) { model_pts = pts2; n_model = n2; }
   int rc;
-  if ((rc = run_assignment_labels(atten, score1, score1_ld, score2, score2_ld, b, g, w.a, w.w1, w.w2, st))) return rc;
-  if ((rc = run_coarse_P(atten, score1, score1_ld, score2, score2_ld, b, g, w.a, w.w1, w.w2, w.pmat, w.prow, st))) return rc;
-  if ((rc = run_cdf(w.pmat, w.prow, b, n1, n2, g.ntc, w.cdf, st))) return rc;
+  if (coarse_assign_fused_ok(n1, n2)) {
+    if ((rc = run_coarse_assign_fused(atten, score1, score1_ld, score2, score2_ld, b, n1, n2, w.w1, w.w2, w.cdf, st))) return rc;
+  } else {
+    if ((rc = run_assignment_labels(atten, score1, score1_ld, score2, score2_ld, b, g, w.a, w.w1, w.w2, st))) return rc;
+    if ((rc = run_coarse_P(atten, score1, score1_ld, score2, score2_ld, b, g, w.a, w.w1, w.w2, w.pmat, w.prow, st))) return rc;
+    if ((rc = run_cdf(w.pmat, w.prow, b, n1, n2, g.ntc, w.cdf, st))) return rc;
+  }
   {
     dim3 grid(ceil_div(n_hyp, HY_THREADS), b);
     k_hypotheses<<<grid, HY_THREADS, 0, st>>>(w.cdf, u, pts1, pts2, n1, n2, n_hyp, 0, n_hyp,
@@ -464,6 +457,8 @@ int upk_coarse_assignment(const float* atten, const float* score1, int score1_ld
   double* prow = cv.take<double>((size_t)b * n1 * g.ntc);
   if (cv.bytes() > workspace_bytes) return UPK_ERR_INVALID_ARG;
   int rc;
+  if (coarse_assign_fused_ok(n1, n2))
+    return run_coarse_assign_fused(atten, score1, score1_ld, score2, score2_ld, b, n1, n2, w1_out, w2_out, cdf_out, st);
   if ((rc = run_assignment_labels(atten, score1, score1_ld, score2, score2_ld, b, g, a, w1_out, w2_out, st))) return rc;
   if ((rc = run_coarse_P(atten, score1, score1_ld, score2, score2_ld, b, g, a, w1_out, w2_out, pmat, prow, st))) return rc;
   return run_cdf(pmat, prow, b, n1, n2, g.ntc, cdf_out, st);

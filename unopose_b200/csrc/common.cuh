@@ -61,6 +61,72 @@ __device__ __forceinline__ float warp_min(float v) {
   return v;
 }
 
+// Blackwell packed fp32 pairs (FADD2 / FMUL2 / FFMA2): two IEEE round-to-nearest operations per issue
+// slot, bit-identical to the scalar instructions lane by lane.
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
+// Nearest-model-point search in the reference's expansion form (pairwise_distance, model_utils.py:246-256):
+//   d_j = (|x|^2 - 2 x.y_j) + |y_j|^2 ,  x.y = fma(x2,yz, fma(x1,yy, x0*yx))
+// over a model staged in shared memory as SoA arrays padded to a multiple of 4 (sentinel points far
+// away).  Four model points per step: 4 LDS.128 + 10 packed ops + 4 FMNMX.  Returns min_j d_j.
+__device__ __forceinline__ float nn_min_expansion(const float* __restrict__ mx, const float* __restrict__ my,
+                                                  const float* __restrict__ mz, const float* __restrict__ mn,
+                                                  int nm_pad, float x0, float x1, float x2, float xx) {
+  const unsigned long long X0 = pack2(x0, x0), X1 = pack2(x1, x1), X2 = pack2(x2, x2);
+  const unsigned long long XX = pack2(xx, xx), M2 = pack2(-2.0f, -2.0f);
+  float best = INFINITY;
+#pragma unroll 2
+  for (int j = 0; j < nm_pad; j += 4) {
+    const ulonglong2 qx = *reinterpret_cast<const ulonglong2*>(mx + j);
+    const ulonglong2 qy = *reinterpret_cast<const ulonglong2*>(my + j);
+    const ulonglong2 qz = *reinterpret_cast<const ulonglong2*>(mz + j);
+    const ulonglong2 qn = *reinterpret_cast<const ulonglong2*>(mn + j);
+    unsigned long long ta = fma2(X2, qz.x, fma2(X1, qy.x, mul2(X0, qx.x)));
+    unsigned long long tb = fma2(X2, qz.y, fma2(X1, qy.y, mul2(X0, qx.y)));
+    ta = add2(fma2(M2, ta, XX), qn.x);
+    tb = add2(fma2(M2, tb, XX), qn.y);
+    float d0, d1, d2, d3;
+    unpack2(ta, d0, d1);
+    unpack2(tb, d2, d3);
+    best = fminf(fminf(best, d0), fminf(d1, fminf(d2, d3)));
+  }
+  return best;
+}
+
+// stage a model cloud (AoS global) into the SoA layout nn_min_expansion expects; call with all threads
+__device__ __forceinline__ void stage_model_soa(const float* __restrict__ model, int nm, int nm_pad, float* mx,
+                                                float* my, float* mz, float* mn) {
+  for (int j = threadIdx.x; j < nm_pad; j += blockDim.x) {
+    float x = 1e15f, y = 1e15f, z = 1e15f;
+    if (j < nm) { x = model[j * 3 + 0]; y = model[j * 3 + 1]; z = model[j * 3 + 2]; }
+    mx[j] = x; my[j] = y; mz[j] = z;
+    // y2 = sum(y**2, -1): products rounded separately, then summed
+    mn[j] = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+  }
+}
+
 // Streaming (read-once) 128-bit global load that does not pollute L1.
 __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
   float4 r;

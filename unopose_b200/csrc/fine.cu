@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(FS_THREADS)
 k_fine_inliers(const float* __restrict__ pts1, const float* __restrict__ model,
                const float* __restrict__ w1, const float* __restrict__ Rm, const float* __restrict__ tv,
                int n1, int nm, float thr, int* __restrict__ counters, float* __restrict__ nn_out) {
-  __shared__ float4 sm_model[FS_TILE];
+  __shared__ __align__(16) float sm_model[4 * FS_TILE];
   __shared__ int s_cnt[2];
   const int b = blockIdx.y;
   const int i = blockIdx.x * FS_THREADS + threadIdx.x;
@@ -128,20 +128,12 @@ k_fine_inliers(const float* __restrict__ pts1, const float* __restrict__ model,
   const float* mb = model + (size_t)b * nm * 3;
   for (int j0 = 0; j0 < nm; j0 += FS_TILE) {
     const int tn = min(FS_TILE, nm - j0);
+    const int tn_pad = (tn + 3) & ~3;
+    float* mx = sm_model; float* my = mx + FS_TILE; float* mz = my + FS_TILE; float* mn = mz + FS_TILE;
     __syncthreads();
-    for (int j = threadIdx.x; j < tn; j += FS_THREADS) {
-      float x = mb[(size_t)(j0 + j) * 3 + 0], y = mb[(size_t)(j0 + j) * 3 + 1], z = mb[(size_t)(j0 + j) * 3 + 2];
-      sm_model[j] = make_float4(x, y, z, __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
-    }
+    stage_model_soa(mb + (size_t)j0 * 3, tn, tn_pad, mx, my, mz, mn);
     __syncthreads();
-    if (ok) {
-#pragma unroll 4
-      for (int j = 0; j < tn; ++j) {
-        float4 q = sm_model[j];
-        float xy = fmaf(x2, q.z, fmaf(x1, q.y, x0 * q.x));
-        best = fminf(best, __fadd_rn(fmaf(-2.0f, xy, xx), q.w));
-      }
-    }
+    if (ok) best = fminf(best, nn_min_expansion(mx, my, mz, mn, tn_pad, x0, x1, x2, xx));
   }
   int inl = 0, fg = 0;
   if (ok) {

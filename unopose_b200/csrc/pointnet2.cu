@@ -41,32 +41,6 @@ __device__ __forceinline__ unsigned bitrev_n(unsigned v, int nbits) {
   return nbits == 0 ? 0u : (__brev(v) >> (32 - nbits));
 }
 
-// Blackwell packed fp32 pairs (FADD2/FMUL2/FFMA2): two IEEE-rn operations per issue slot, bit-identical
-// to the scalar instructions lane by lane.
-__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
-  unsigned long long r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
-  unsigned long long d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
-  unsigned long long d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
-  unsigned long long d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-
 template <int THREADS, int PPT, bool X2 = false>
 __global__ void __launch_bounds__(THREADS, 1)
 fps_kernel(const float* __restrict__ xyz, int n, int m, int bs_log2,
@@ -265,29 +239,48 @@ constexpr int BQ_QPW = 4;                    // queries per warp
 constexpr int BQ_QPB = BQ_WARPS * BQ_QPW;    // queries per block
 constexpr int BQ_TILE = 3968;                // points per smem tile (46.5 KB), multiple of 128
 
-// One ballot step over 32 points: returns the hit mask (warp-uniform).
-__device__ __forceinline__ unsigned bq_hits(const float* sx, const float* sy, const float* sz, int k,
-                                            float qx, float qy, float qz, float r2) {
-  // (new_x - x)^2 + ... with the reference's FMA contraction
-  float d2 = sqdist_ref(qx - sx[k], qy - sy[k], qz - sz[k]);
-  return __ballot_sync(kFull, d2 < r2);
+// One ballot step over 64 points (two per lane, packed f32x2 arithmetic): lane l tests points
+// k0 + 2l and k0 + 2l + 1.  Returns the two hit masks (bit l of `even`/`odd` = lane l's first/second point).
+__device__ __forceinline__ void bq_hits2(const float* sx, const float* sy, const float* sz, int k,
+                                         unsigned long long nqx, unsigned long long nqy, unsigned long long nqz,
+                                         float r2, unsigned& even, unsigned& odd) {
+  // (new_x - x)^2 == (x - new_x)^2 exactly; d2 = fma(dz,dz, fma(dx,dx, dy*dy)) as the reference's SASS
+  const float2 x = *reinterpret_cast<const float2*>(sx + k);
+  const float2 y = *reinterpret_cast<const float2*>(sy + k);
+  const float2 z = *reinterpret_cast<const float2*>(sz + k);
+  unsigned long long dx = add2(pack2(x.x, x.y), nqx);
+  unsigned long long dy = add2(pack2(y.x, y.y), nqy);
+  unsigned long long dz = add2(pack2(z.x, z.y), nqz);
+  unsigned long long dd = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
+  float d0, d1;
+  unpack2(dd, d0, d1);
+  even = __ballot_sync(kFull, d0 < r2);
+  odd = __ballot_sync(kFull, d1 < r2);
 }
 
-// Append the hits of one 32-point step in ascending k (popc prefix keeps the slot order).
-__device__ __forceinline__ void bq_append(unsigned mask, int kbase, int lane, int nsample, int& cnt,
-                                          int& first, int* __restrict__ row) {
-  if (mask) {
-    if (cnt == 0) first = kbase + __ffs(mask) - 1;
-    int slot = cnt + __popc(mask & ((1u << lane) - 1u));
-    if (((mask >> lane) & 1u) && slot < nsample) row[slot] = kbase + lane;
-    cnt += __popc(mask);
+// Append the hits of one 64-point step in ascending k: point order is lane0.even, lane0.odd, lane1.even, ...
+__device__ __forceinline__ void bq_append2(unsigned even, unsigned odd, int kbase, int lane, int nsample, int& cnt,
+                                           int& first, int* __restrict__ row) {
+  if (even | odd) {
+    if (cnt == 0) {
+      const int fe = even ? __ffs(even) - 1 : 64, fo = odd ? __ffs(odd) - 1 : 64;
+      first = kbase + (fe <= fo ? 2 * fe : 2 * fo + 1);
+    }
+    const unsigned lt = (1u << lane) - 1u;
+    const int before = __popc(even & lt) + __popc(odd & lt);
+    const int he = (even >> lane) & 1u, ho = (odd >> lane) & 1u;
+    int slot = cnt + before;
+    if (he && slot < nsample) row[slot] = kbase + 2 * lane;
+    slot += he;
+    if (ho && slot < nsample) row[slot] = kbase + 2 * lane + 1;
+    cnt += __popc(even) + __popc(odd);
   }
 }
 
 __global__ void __launch_bounds__(BQ_WARPS * 32)
 ball_query_kernel(const float* __restrict__ new_xyz, const float* __restrict__ xyz,
                   int n, int m, float radius2, int nsample, int* __restrict__ idx) {
-  __shared__ float sx[BQ_TILE], sy[BQ_TILE], sz[BQ_TILE];
+  __shared__ __align__(8) float sx[BQ_TILE], sy[BQ_TILE], sz[BQ_TILE];
   __shared__ int s_cnt[BQ_QPB], s_first[BQ_QPB];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.y;
@@ -317,17 +310,15 @@ ball_query_kernel(const float* __restrict__ new_xyz, const float* __restrict__ x
       const int j = q0 + q;
       const float qx = new_xyz[j * 3 + 0], qy = new_xyz[j * 3 + 1], qz = new_xyz[j * 3 + 2];
       int* row = idx + (size_t)j * nsample;
+      const unsigned long long nqx = pack2(-qx, -qx), nqy = pack2(-qy, -qy), nqz = pack2(-qz, -qz);
       for (int base = 0; base < tn_pad; base += 128) {
-        const int k = base + lane;
-        unsigned m0 = bq_hits(sx, sy, sz, k, qx, qy, qz, radius2);
-        unsigned m1 = bq_hits(sx, sy, sz, k + 32, qx, qy, qz, radius2);
-        unsigned m2 = bq_hits(sx, sy, sz, k + 64, qx, qy, qz, radius2);
-        unsigned m3 = bq_hits(sx, sy, sz, k + 96, qx, qy, qz, radius2);
-        if (m0 | m1 | m2 | m3) {
-          bq_append(m0, t0 + base, lane, nsample, cnt, first, row);
-          bq_append(m1, t0 + base + 32, lane, nsample, cnt, first, row);
-          bq_append(m2, t0 + base + 64, lane, nsample, cnt, first, row);
-          bq_append(m3, t0 + base + 96, lane, nsample, cnt, first, row);
+        const int k = base + 2 * lane;
+        unsigned e0, o0, e1, o1;
+        bq_hits2(sx, sy, sz, k, nqx, nqy, nqz, radius2, e0, o0);
+        bq_hits2(sx, sy, sz, k + 64, nqx, nqy, nqz, radius2, e1, o1);
+        if (e0 | o0 | e1 | o1) {
+          bq_append2(e0, o0, t0 + base, lane, nsample, cnt, first, row);
+          bq_append2(e1, o1, t0 + base + 64, lane, nsample, cnt, first, row);
           if (cnt >= nsample) break;
         }
       }

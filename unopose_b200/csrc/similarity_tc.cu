@@ -336,7 +336,7 @@ size_t similarity_tc_workspace_bytes(int b, int n, int m, int c) {
 }
 
 bool similarity_tc_eligible(int n, int m, int c) {
-  return similarity_mode() != 0 && c % TC_BK == 0 && c >= TC_BK && (long long)n * m >= 512LL * 512LL &&
+  return similarity_mode() != 0 && c % TC_BK == 0 && c >= TC_BK && (long long)n * m >= 128LL * 128LL &&
          get_encode() != nullptr;
 }
 
