@@ -718,146 +718,6 @@ k_fine_rows_stream(const float* __restrict__ atten, int R, int C, int ntc,
     rows_stream_body<true>(A, R, C, ntc, b, tc, r0, c0, warp, lane, kc, px, py, pz, rmax, rsum, score1, ld1, rowpart4);
 }
 
-// ====================================================================================
-// Fused small-geometry assignment (coarse stage, 197 x 197): ONE CTA per instance keeps the whole
-// matrix in shared memory (155 KB) and runs stats -> labels -> P -> CDF back to back, replacing six
-// launches of the tile pipeline (the coarse solve is launch-latency dominated).  Arithmetic: expf and
-// IEEE division exactly as torch.softmax, fp64 row sums and CDF as in k_cdf.
-// ====================================================================================
-constexpr int FA_THREADS = 1024;
-
-__global__ void __launch_bounds__(FA_THREADS, 1)
-k_coarse_assign_fused(const float* __restrict__ atten, const float* __restrict__ score1, int ld1,
-                      const float* __restrict__ score2, int ld2, int R, int C, float* __restrict__ w1_out,
-                      float* __restrict__ w2_out, float* __restrict__ cdf) {
-  extern __shared__ unsigned char fa_smem[];
-  double* s_rowtot = reinterpret_cast<double*>(fa_smem);           // R  (row totals, then row offsets)
-  float* s_rm = reinterpret_cast<float*>(s_rowtot + R);             // R
-  float* s_rs = s_rm + R;                                           // R
-  float* s_cm = s_rs + R;                                           // C
-  float* s_cs = s_cm + C;                                           // C
-  float* s_w1 = s_cs + C;                                           // R  (index 0 unused)
-  float* s_w2 = s_w1 + R;                                           // C
-  float* S = s_w2 + C;                                              // R*C
-  __shared__ double s_total;
-  const int b = blockIdx.x;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = FA_THREADS / 32;
-  const int N1 = R - 1, N2 = C - 1;
-  const float* A = atten + (size_t)b * R * C;
-  for (int i = threadIdx.x; i < R * C; i += FA_THREADS) S[i] = __ldg(A + i);
-  __syncthreads();
-  // row / column softmax statistics
-  for (int r = warp; r < R; r += nw) {
-    float m = -INFINITY;
-    for (int c = lane; c < C; c += 32) m = fmaxf(m, S[r * C + c]);
-    m = warp_max(m);
-    float sum = 0.f;
-    for (int c = lane; c < C; c += 32) sum += expf(S[r * C + c] - m);
-    sum = warp_sum(sum);
-    if (lane == 0) { s_rm[r] = m; s_rs[r] = sum; }
-  }
-  for (int c = warp; c < C; c += nw) {
-    float m = -INFINITY;
-    for (int r = lane; r < R; r += 32) m = fmaxf(m, S[r * C + c]);
-    m = warp_max(m);
-    float sum = 0.f;
-    for (int r = lane; r < R; r += 32) sum += expf(S[r * C + c] - m);
-    sum = warp_sum(sum);
-    if (lane == 0) { s_cm[c] = m; s_cs[c] = sum; }
-  }
-  __syncthreads();
-  // A = softmax_row * softmax_col * s1 * s2 (in place)
-  for (int i = threadIdx.x; i < R * C; i += FA_THREADS) {
-    const int r = i / C, c = i - r * C;
-    const float v = S[i];
-    const float er = expf(v - s_rm[r]) / s_rs[r];
-    const float ec = expf(v - s_cm[c]) / s_cs[c];
-    const float s1 = (r > 0 && score1) ? __ldg(score1 + (size_t)b * ld1 + r - 1) : 1.f;
-    const float s2 = (c > 0 && score2) ? __ldg(score2 + (size_t)b * ld2 + c - 1) : 1.f;
-    S[i] = ((er * ec) * s1) * s2;
-  }
-  __syncthreads();
-  // labels: is the background entry the (first) arg-max of its row / column?
-  for (int r = 1 + warp; r < R; r += nw) {
-    float m = -INFINITY;
-    for (int c = 1 + lane; c < C; c += 32) m = fmaxf(m, S[r * C + c]);
-    m = warp_max(m);
-    if (lane == 0) {
-      float w = m > S[r * C] ? 1.f : 0.f;
-      s_w1[r] = w;
-      w1_out[(size_t)b * N1 + r - 1] = w;
-    }
-  }
-  for (int c = 1 + warp; c < C; c += nw) {
-    float m = -INFINITY;
-    for (int r = 1 + lane; r < R; r += 32) m = fmaxf(m, S[r * C + c]);
-    m = warp_max(m);
-    if (lane == 0) {
-      float w = m > S[c] ? 1.f : 0.f;
-      s_w2[c] = w;
-      w2_out[(size_t)b * N2 + c - 1] = w;
-    }
-  }
-  __syncthreads();
-  // P = (A w1 w2)^1.5 in place + fp64 row totals
-  for (int r = 1 + warp; r < R; r += nw) {
-    const float wr = s_w1[r];
-    double acc = 0.0;
-    for (int c = 1 + lane; c < C; c += 32) {
-      float a = (S[r * C + c] * wr) * s_w2[c];
-      float p = a * sqrtf(a);
-      S[r * C + c] = p;
-      acc += (double)p;
-    }
-    acc = warp_sum(acc);
-    if (lane == 0) s_rowtot[r] = acc;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {        // sequential (canonical) exclusive prefix of the row totals
-    double acc = 0.0;
-    for (int r = 1; r < R; ++r) {
-      double t = s_rowtot[r];
-      s_rowtot[r] = acc;
-      acc += t;
-    }
-    s_total = acc;
-  }
-  __syncthreads();
-  const float denom = (float)s_total + 1e-8f;
-  for (int r = 1 + warp; r < R; r += nw) {
-    double carry = s_rowtot[r];
-    float* out = cdf + ((size_t)b * N1 + r - 1) * N2;
-    for (int c0 = 0; c0 < N2; c0 += 32) {
-      const int c = c0 + lane;
-      double v = c < N2 ? (double)S[r * C + 1 + c] : 0.0;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        double t = __shfl_up_sync(kFull, v, o);
-        if (lane >= o) v += t;
-      }
-      if (c < N2) out[c] = __fdiv_rn((float)(carry + v), denom);
-      carry += __shfl_sync(kFull, v, 31);
-    }
-  }
-}
-
-static size_t fused_assign_smem(int R, int C) {
-  return (size_t)R * sizeof(double) + ((size_t)3 * R + 3 * C + (size_t)R * C) * sizeof(float);
-}
-
-bool coarse_assign_fused_ok(int n1, int n2) { return fused_assign_smem(n1 + 1, n2 + 1) <= 200 * 1024; }
-
-int run_coarse_assign_fused(const float* atten, const float* score1, int ld1, const float* score2, int ld2, int b,
-                            int n1, int n2, float* w1, float* w2, float* cdf, cudaStream_t st) {
-  const int R = n1 + 1, C = n2 + 1;
-  const size_t smem = fused_assign_smem(R, C);
-  if (smem > 40 * 1024)
-    UPK_CUDA_TRY(cudaFuncSetAttribute(k_coarse_assign_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_coarse_assign_fused<<<b, FA_THREADS, smem, st>>>(atten, score1, ld1, score2, ld2, R, C, w1, w2, cdf);
-  count_launch();
-  UPK_RETURN_LAST_ERROR();
-}
-
 // ------------------------------------------------------------------ host launchers
 template <int TR, int TC>
 static int stats_labels_t(const float* atten, const float* score1, int ld1, const float* score2, int ld2,

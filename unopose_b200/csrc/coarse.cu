@@ -235,7 +235,7 @@ k_topk_smallest(const float* __restrict__ vals, int H, int K, int* __restrict__ 
 // score = sum_i w1_i / (sum_i d_i w1_i + 1e-8)        (model_utils.py:481-485, pairwise_distance :246-256)
 // One CTA per (instance, kept hypothesis); model points staged in smem (SoA x|y|z||y|^2), four model
 // points per step with packed f32x2 arithmetic (4.5 issue slots per point pair); the (B*K,N1,N2) distance tensor never exists.
-constexpr int SC_THREADS = 128;
+constexpr int SC_THREADS = 224;  // 7 warps: one query point per thread at n1 = 196
 
 __global__ void __launch_bounds__(SC_THREADS)
 k_score(const float* __restrict__ pts1, const float* __restrict__ model, const float* __restrict__ w1,
@@ -393,13 +393,11 @@ int upk_coarse_pose(const float* atten, const float* score1, int score1_ld, cons
   if (cv.bytes() > workspace_bytes) return UPK_ERR_INVALID_ARG;
   if (!model_pts) { model_pts = pts2; n_model = n2; }
   int rc;
-  if (coarse_assign_fused_ok(n1, n2)) {
-    if ((rc = run_coarse_assign_fused(atten, score1, score1_ld, score2, score2_ld, b, n1, n2, w.w1, w.w2, w.cdf, st))) return rc;
-  } else {
-    if ((rc = run_assignment_labels(atten, score1, score1_ld, score2, score2_ld, b, g, w.a, w.w1, w.w2, st))) return rc;
-    if ((rc = run_coarse_P(atten, score1, score1_ld, score2, score2_ld, b, g, w.a, w.w1, w.w2, w.pmat, w.prow, st))) return rc;
-    if ((rc = run_cdf(w.pmat, w.prow, b, n1, n2, g.ntc, w.cdf, st))) return rc;
-  }
+  // (a single-CTA-per-instance fused variant of these three steps, matrix resident in smem, was
+  //  measured at 70 us against ~50 us for the tile pipeline at B = 16: too little parallelism)
+  if ((rc = run_assignment_labels(atten, score1, score1_ld, score2, score2_ld, b, g, w.a, w.w1, w.w2, st))) return rc;
+  if ((rc = run_coarse_P(atten, score1, score1_ld, score2, score2_ld, b, g, w.a, w.w1, w.w2, w.pmat, w.prow, st))) return rc;
+  if ((rc = run_cdf(w.pmat, w.prow, b, n1, n2, g.ntc, w.cdf, st))) return rc;
   {
     dim3 grid(ceil_div(n_hyp, HY_THREADS), b);
     k_hypotheses<<<grid, HY_THREADS, 0, st>>>(w.cdf, u, pts1, pts2, n1, n2, n_hyp, 0, n_hyp,
@@ -457,8 +455,6 @@ int upk_coarse_assignment(const float* atten, const float* score1, int score1_ld
   double* prow = cv.take<double>((size_t)b * n1 * g.ntc);
   if (cv.bytes() > workspace_bytes) return UPK_ERR_INVALID_ARG;
   int rc;
-  if (coarse_assign_fused_ok(n1, n2))
-    return run_coarse_assign_fused(atten, score1, score1_ld, score2, score2_ld, b, n1, n2, w1_out, w2_out, cdf_out, st);
   if ((rc = run_assignment_labels(atten, score1, score1_ld, score2, score2_ld, b, g, a, w1_out, w2_out, st))) return rc;
   if ((rc = run_coarse_P(atten, score1, score1_ld, score2, score2_ld, b, g, a, w1_out, w2_out, pmat, prow, st))) return rc;
   return run_cdf(pmat, prow, b, n1, n2, g.ntc, cdf_out, st);

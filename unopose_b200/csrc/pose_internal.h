@@ -63,11 +63,6 @@ int run_fine_rowsums(const float* atten, const float* score1, int ld1, const flo
                      const float* pts2, float4* rowpart4 /*[b][N1][ntc]*/, float* soft, float* asum,
                      cudaStream_t st);
 
-// coarse (small) geometry: whole assignment + CDF in one CTA per instance, matrix resident in smem
-bool coarse_assign_fused_ok(int n1, int n2);
-int run_coarse_assign_fused(const float* atten, const float* score1, int ld1, const float* score2, int ld2, int b,
-                            int n1, int n2, float* w1, float* w2, float* cdf, cudaStream_t st);
-
 // tensor-core similarity path (similarity_tc.cu)
 int similarity_mode();  // 3 = 3xTF32 tcgen05 (default), 1 = 1xTF32 tcgen05, 0 = fp32 SIMT
 bool similarity_tc_eligible(int n, int m, int c);
