@@ -431,6 +431,7 @@ def gpu_torch_leg(cfg, sets, B, dev):
         ca = PO.feature_similarity(s["c_f1"], s["c_f2"], "cosine", cfg.temp, True)
         PO.coarse_pose(ca, s["c_score"], s["c_pts1"], s["c_pts2"], None, cfg.n_proposal1, cfg.n_proposal2)
         for cloud in (s["pts"], tem_sub):
+            cloud = cloud.contiguous()
             cf = cloud.transpose(1, 2).contiguous()
             for r, ns in cfg.pe:
                 ext.group_points(cf, ext.ball_query(cloud, cloud, r, ns))

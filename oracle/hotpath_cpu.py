@@ -54,7 +54,8 @@ def run_hot_path_cpu(inp, cfg, threads=None):
     out["init_R"], out["init_t"], out["init_pose_score"] = PO.coarse_pose(
         c_atten, inp["c_score"], inp["c_pts1"], inp["c_pts2"], None, cfg.n_proposal1, cfg.n_proposal2)
     b = npf["pts"].shape[0]
-    for name, cloud in (("q", npf["pts"]), ("r", tem_sub)):
+    p1_ = ((inp["pts"] - out["init_t"].unsqueeze(1)) @ out["init_R"]).contiguous().numpy()   # fine module :65-72
+    for name, cloud in (("q", p1_), ("r", tem_sub)):
         for k, (r, ns) in enumerate(cfg.pe):
             def one(i, cloud=cloud, r=r, ns=ns):
                 idx = O.ball_query(cloud[i:i + 1], cloud[i:i + 1], r, ns)

@@ -80,8 +80,8 @@ def to_device(inp, device, non_blocking=True):
 _SIDE_STREAMS = {}
 
 
-def _side_stream(device):
-    key = torch.device(device).index
+def _side_stream(device, which=0):
+    key = (torch.device(device).index, which)
     if key not in _SIDE_STREAMS:
         _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
     return _SIDE_STREAMS[key]
@@ -92,8 +92,9 @@ def run_hot_path(inp, cfg=HotPathConfig(), stages=None, overlap=True):
 
     overlap=True runs the reference-cloud chain (template FPS -> sparse FPS -> ball query/grouping of
     the reference cloud: a serial, latency-bound chain that occupies one SM per instance) on a side
-    CUDA stream, concurrently with the query-cloud chain and both pose solves on the current stream;
-    the two are joined by events before returning.  `stages` optionally receives the list of
+    CUDA stream and the sparse FPS of the query cloud on another, concurrently with the pose-solve chain
+    (coarse -> query-cloud geometry at the coarse pose -> fine) on the current stream; all are joined by
+    events before returning.  `stages` optionally receives the list of
     (name, callable) in serial order instead of executing, for per-stage timing."""
     out = {}
 
@@ -122,7 +123,9 @@ def run_hot_path(inp, cfg=HotPathConfig(), stages=None, overlap=True):
             out["pe_%s%d" % (name, i)] = P.grouping_operation(cf, idx)
 
     def s_pe_q():
-        pe_geometry("q", inp["pts"])
+        # the fine module encodes the query cloud AFTER moving it by the coarse pose (fine module :65-72)
+        p1_ = (inp["pts"] - out["init_t"].unsqueeze(1)) @ out["init_R"]
+        pe_geometry("q", p1_.contiguous())
 
     def s_pe_r():
         pe_geometry("r", out["tem_sub"])
@@ -136,26 +139,31 @@ def run_hot_path(inp, cfg=HotPathConfig(), stages=None, overlap=True):
 
     ref_chain = [("fps_template+gather", s_template), ("fps_sparse_ref+gather", s_sparse_r),
                  ("ball_query+group_ref", s_pe_r)]
-    main_chain = [("fps_sparse_query+gather", s_sparse_q), ("coarse_similarity", s_coarse_sim),
-                  ("coarse_pose", s_coarse_pose), ("ball_query+group_query", s_pe_q),
-                  ("fine_similarity", s_fine_sim), ("fine_pose", s_fine_pose)]
+    aux_chain = [("fps_sparse_query+gather", s_sparse_q)]      # independent of both other chains
+    main_chain = [("coarse_similarity", s_coarse_sim), ("coarse_pose", s_coarse_pose),
+                  ("ball_query+group_query", s_pe_q), ("fine_similarity", s_fine_sim), ("fine_pose", s_fine_pose)]
     if stages is not None:
-        stages.extend(ref_chain + main_chain)
+        stages.extend(ref_chain + aux_chain + main_chain)
         return out
     if not overlap:
-        for _, fn in ref_chain + main_chain:
+        for _, fn in ref_chain + aux_chain + main_chain:
             fn()
         return out
     dev = inp["pts"].device
     main = torch.cuda.current_stream(dev)
-    side = _side_stream(dev)
-    side.wait_stream(main)          # inputs produced on the current stream are visible to the side chain
+    side, aux = _side_stream(dev, 0), _side_stream(dev, 1)
+    side.wait_stream(main)          # inputs produced on the current stream are visible to the other chains
+    aux.wait_stream(main)
     with torch.cuda.stream(side):
         for _, fn in ref_chain:
+            fn()
+    with torch.cuda.stream(aux):
+        for _, fn in aux_chain:
             fn()
     for _, fn in main_chain:
         fn()
     main.wait_stream(side)          # join
+    main.wait_stream(aux)
     # Tensors allocated on the side stream are consumed on the current stream only after this join,
     # and the next step's side chain starts with side.wait_stream(main): the caching allocator can
     # recycle them on the side stream without record_stream() (which would defer every reuse).
