@@ -342,8 +342,8 @@ def main():
                                 fps_ops(cfg.n_template, cfg.n_fine)),
         "fps_sparse_ref+gather": ("fps_kernel<512,4> (2048->196)", "fp32", fps_ops(cfg.n_fine, cfg.n_coarse)),
         "fps_sparse_query+gather": ("fps_kernel<512,4> (2048->196)", "fp32", fps_ops(cfg.n_fine, cfg.n_coarse)),
-        "ball_query+group_query": ("ball_query_kernel + group_kernel", "hbm", pe_bytes),
-        "ball_query+group_ref": ("ball_query_kernel + group_kernel", "hbm", pe_bytes),
+        "ball_query+group_query": ("ball_group_kernel<2 scales> (fused ball query + grouping)", "hbm", pe_bytes),
+        "ball_query+group_ref": ("ball_group_kernel<2 scales> (fused ball query + grouping)", "hbm", pe_bytes),
         "coarse_pose": ("k_score (K x 196 x 196 point pairs, 6 lane-ops each) + assignment/sampling/top-K", "fp32",
                         6.0 * cfg.n_proposal2 * cfg.n_coarse * cfg.n_coarse * B),
         "coarse_similarity": ("k_sgemm_nt<0> (fp32 SIMT, 197x197x256/instance)", "fp32",

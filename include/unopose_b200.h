@@ -71,6 +71,18 @@ int upk_gather_points_grad(const float* grad_out, const int* idx, int b, int c,
 int upk_ball_query(const float* new_xyz, const float* xyz, int b, int n, int m,
                    float radius, int nsample, int* idx_out, upk_stream_t stream);
 
+/* Fused ball_query + group_points of the xyz channels, for ONE or TWO (radius, nsample) scales in one
+ * scan of the cloud: what QueryAndGroup / QueryAndLRFGroup (pointnet2_utils.py:292-378, :484-584) and the
+ * two-scale PositionalEncoding (oneref_predator_fine_point_matching.py:159-178) compute with
+ * ball_query -> transpose -> grouping_operation per scale.
+ *   idxK[b,m,nsampleK] int32     == upk_ball_query(new_xyz, xyz, radiusK, nsampleK)          (bit-exact)
+ *   groupedK[b,3,m,nsampleK]     == upk_group_points(xyz^T[b,3,n], idxK)   (may be NULL: indices only)
+ * A scale with nsampleK == 0 is skipped (single-scale call). */
+int upk_ball_query_group(const float* new_xyz, const float* xyz, int b, int n, int m,
+                         float radius0, int nsample0, int* idx0, float* grouped0,
+                         float radius1, int nsample1, int* idx1, float* grouped1,
+                         upk_stream_t stream);
+
 /* group_points(points[b,c,n], idx[b,npoints,nsample]) -> out[b,c,npoints,nsample]
  * replaces _ext.group_points (group_points.cpp:17-40, group_points_gpu.cu:13-44). */
 int upk_group_points(const float* points, const int* idx, int b, int c, int n,

@@ -68,6 +68,48 @@ def test_ball_query_no_hit_rows_zero(cuda):
     assert (got == 0).all()
 
 
+@pytest.mark.parametrize("n,m,scales", [
+    (2048, 2048, [(0.1, 64), (0.2, 256)]),      # the PositionalEncoding configuration
+    (2048, 2048, [(0.2, 256), (0.1, 64)]),      # larger radius first
+    (2048, 2048, [(0.2, 16), (0.1, 64)]),       # outer row saturates before the inner one
+    (2048, 2048, [(0.15, 32)]),
+    (300, 77, [(0.25, 16), (0.25, 3)]),         # equal radii
+    (5000, 196, [(0.15, 32), (0.3, 100)]),      # three smem tiles
+    (9000, 40, [(0.3, 500), (0.05, 7)]),
+    (50, 50, [(10.0, 64), (0.01, 5)]),
+    (33, 65, [(0.01, 5)]),
+    (4097, 31, [(0.5, 1), (0.6, 2)]),
+])
+def test_ball_query_group_fused_matches_oracle(cuda, n, m, scales):
+    xyz = batch_clouds(n + m + 1, 2, n, "surface")
+    q = xyz[:, :m] if m <= n else batch_clouds(5, 2, m)
+    q = np.ascontiguousarray(q)
+    xyz_cf = np.ascontiguousarray(xyz.transpose(0, 2, 1))
+    for group in (True, False):
+        outs = _ext().ball_query_group(T(q, cuda), T(xyz, cuda), scales, group=group)
+        assert len(outs) == len(scales)
+        for (r, ns), (idx, g) in zip(scales, outs):
+            exp = O.ball_query(q, xyz, r, ns)
+            assert np.array_equal(idx.cpu().numpy(), exp), (r, ns)
+            if group:
+                assert np.array_equal(g.cpu().numpy(), O.group_points(xyz_cf, exp)), (r, ns)
+            else:
+                assert g is None
+
+
+def test_ball_query_group_fused_no_hit_and_duplicates(cuda):
+    xyz = batch_clouds(3, 1, 100)
+    q = np.ascontiguousarray(xyz[:, :10] + 50.0)
+    (i0, g0), (i1, g1) = _ext().ball_query_group(T(q, cuda), T(xyz, cuda), [(0.1, 8), (0.3, 4)])
+    assert (i0 == 0).all() and (i1 == 0).all()
+    p0 = torch.from_numpy(xyz[:, 0]).to(cuda)          # zero rows group point 0
+    assert torch.equal(g0, p0[:, :, None, None].expand_as(g0)) and torch.equal(g1, p0[:, :, None, None].expand_as(g1))
+    # duplicated points: every copy is a hit, ascending index order
+    d = np.ascontiguousarray(np.repeat(batch_clouds(4, 2, 40), 3, axis=1))
+    (idx, g), = _ext().ball_query_group(T(d, cuda), T(d, cuda), [(1e-3, 5)])
+    assert np.array_equal(idx.cpu().numpy(), O.ball_query(d, d, 1e-3, 5))
+
+
 @pytest.mark.parametrize("c,n,npoints,ns", [(3, 2048, 2048, 64), (3, 2048, 2048, 256), (5, 100, 7, 3), (256, 500, 64, 1),
                                             (1, 10, 1, 1)])
 def test_group_and_grad_match_oracle(cuda, c, n, npoints, ns):

@@ -28,6 +28,7 @@ _SIGNATURES = {
     "upk_gather_points": [c_f, c_f, c_i, c_i, c_i, c_i, c_f, c_st],
     "upk_gather_points_grad": [c_f, c_f, c_i, c_i, c_i, c_i, c_f, c_st],
     "upk_ball_query": [c_f, c_f, c_i, c_i, c_i, c_fl, c_i, c_f, c_st],
+    "upk_ball_query_group": [c_f, c_f, c_i, c_i, c_i, c_fl, c_i, c_f, c_f, c_fl, c_i, c_f, c_f, c_st],
     "upk_group_points": [c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_f, c_st],
     "upk_group_points_grad": [c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_f, c_st],
     "upk_gather_rows": [c_f, c_f, c_i, c_i, c_i, c_i, c_f, c_st],

@@ -9,7 +9,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ..model_utils import compute_coarse_Rt_overlap, compute_feature_similarity, compute_fine_Rt_overlap
-from ..pointnet2.pointnet2_utils import QueryAndGroup, QueryAndLRFGroup
+from ..pointnet2.pointnet2_utils import QueryAndGroup, QueryAndLRFGroup, ball_query_and_group
 from .layers import Conv1d, SharedMLP
 from .transformer import GeometricTransformer, SparseToDenseTransformer
 
@@ -98,8 +98,14 @@ class PositionalEncoding(nn.Module):
         pts2 = pts2.to(dtype=torch.float32).contiguous()
         with torch.autocast(device_type="cuda", enabled=False):
             feats = pts1.transpose(1, 2).contiguous()
-            f1 = self.mlp1(self.group1(pts1, pts2, feats)).max(dim=3)[0]
-            f2 = self.mlp2(self.group2(pts1, pts2, feats)).max(dim=3)[0]
+            pre1 = pre2 = None
+            g1, g2 = self.group1, self.group2
+            if pts1.is_cuda and not (g1.sample_uniformly or g2.sample_uniformly) and \
+                    not (torch.is_grad_enabled() and pts1.requires_grad):
+                # both scales from ONE scan of the cloud (fused ball query + grouping kernel)
+                pre1, pre2 = ball_query_and_group(pts1, pts2, [(g1.radius, g1.nsample), (g2.radius, g2.nsample)])
+            f1 = self.mlp1(g1(pts1, pts2, feats, pre=pre1)).max(dim=3)[0]
+            f2 = self.mlp2(g2(pts1, pts2, feats, pre=pre2)).max(dim=3)[0]
             return self.mlp3(torch.cat([f1, f2], dim=1)).transpose(1, 2)
 
 

@@ -117,10 +117,12 @@ def run_hot_path(inp, cfg=HotPathConfig(), stages=None, overlap=True):
             out["c_atten"], inp["c_score"], inp["c_pts1"], inp["c_pts2"], None, cfg.n_proposal1, cfg.n_proposal2)
 
     def pe_geometry(name, cloud):
-        cf = cloud.transpose(1, 2).contiguous()
-        for i, (r, ns) in enumerate(cfg.pe):
-            idx = P.ball_query(r, ns, cloud, cloud)
-            out["pe_%s%d" % (name, i)] = P.grouping_operation(cf, idx)
+        # both PositionalEncoding scales from one fused scan (ball query + grouping of the xyz channels)
+        pe = list(cfg.pe)
+        for i0 in range(0, len(pe), 2):
+            for i, (idx, grouped) in enumerate(P.ball_query_and_group(cloud, cloud, pe[i0:i0 + 2]), i0):
+                out["pe_idx_%s%d" % (name, i)] = idx
+                out["pe_%s%d" % (name, i)] = grouped
 
     def s_pe_q():
         # the fine module encodes the query cloud AFTER moving it by the coarse pose (fine module :65-72)

@@ -83,6 +83,38 @@ def ball_query(new_xyz, xyz, radius, nsample):
     return out
 
 
+def ball_query_group(new_xyz, xyz, scales, group=True):
+    """Fused ball_query (+ grouping of the xyz channels) for one or two (radius, nsample) scales in one
+    scan of the cloud (upk_ball_query_group).  new_xyz (B,M,3), xyz (B,N,3), scales = [(r, ns)] or
+    [(r0, ns0), (r1, ns1)] -> [(idx (B,M,ns) int32, grouped_xyz (B,3,M,ns) | None), ...] with
+    idx == ball_query(new_xyz, xyz, r, ns) and grouped_xyz == group_points(xyz^T, idx), bit-exact.
+    Not part of the reference's _ext; it replaces the ball_query -> transpose -> grouping_operation
+    sequences of QueryAndGroup / QueryAndLRFGroup (pointnet2_utils.py:292-378, :484-584)."""
+    L.check_contiguous(new_xyz, "new_xyz")
+    L.check_contiguous(xyz, "xyz")
+    L.check_float(new_xyz, "new_xyz")
+    L.check_float(xyz, "xyz")
+    L.check_cuda(new_xyz, "new_xyz")
+    if not xyz.is_cuda:
+        raise RuntimeError("xyz must be a CUDA tensor")
+    if not 1 <= len(scales) <= 2:
+        raise ValueError("ball_query_group takes one or two (radius, nsample) scales")
+    b, m, _ = new_xyz.shape
+    n = xyz.shape[1]
+    outs, args = [], []
+    for r, ns in scales:
+        idx = torch.empty((b, m, int(ns)), dtype=torch.int32, device=new_xyz.device)
+        g = torch.empty((b, 3, m, int(ns)), dtype=torch.float32, device=new_xyz.device) if group else None
+        outs.append((idx, g))
+        args += [float(r), int(ns), L.ptr(idx), L.ptr(g) if g is not None else None]
+    if len(scales) == 1:
+        args += [0.0, 0, None, None]
+    with _dev(new_xyz):
+        L.check(L.load().upk_ball_query_group(L.ptr(new_xyz), L.ptr(xyz), b, n, m, *args,
+                                              L.stream_ptr(new_xyz)), "ball_query_group")
+    return outs
+
+
 def group_points(points, idx):
     """points (B,C,N), idx (B,npoints,nsample) -> (B,C,npoints,nsample).  Ref: group_points.cpp:17-40."""
     L.check_contiguous(points, "points")

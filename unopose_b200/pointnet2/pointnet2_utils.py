@@ -121,6 +121,20 @@ class BallQuery(Function):
 ball_query = BallQuery.apply
 
 
+def _fusable(xyz, sample_uniformly):
+    # the fused kernel has no autograd edge to xyz; the unfused sequence keeps the reference's
+    # GroupingOperation.backward for callers that differentiate through the grouped coordinates
+    return xyz.is_cuda and not sample_uniformly and not (torch.is_grad_enabled() and xyz.requires_grad)
+
+
+def ball_query_and_group(xyz, new_xyz, scales):
+    """[(radius, nsample)] x1 or x2 -> [(idx (B,npoint,nsample) int32, grouped_xyz (B,3,npoint,nsample))]:
+    ball_query + grouping_operation(xyz^T, idx) per scale in one fused scan (_ext.ball_query_group).
+    Non-differentiable (evaluation path)."""
+    with torch.no_grad():
+        return _ext.ball_query_group(new_xyz.contiguous(), xyz.contiguous(), list(scales), group=True)
+
+
 def _uniform_resample_(idx, nsample):
     """sample_uniformly branch of the reference groupers (pointnet2_utils.py:342-351,
     :542-551): per ball, unique indices padded with random re-draws.  Host loop,
@@ -152,10 +166,17 @@ class QueryAndGroup(nn.Module):
         if self.ret_unique_cnt:
             assert self.sample_uniformly
 
-    def forward(self, xyz, new_xyz, features=None):
-        idx = ball_query(self.radius, self.nsample, xyz, new_xyz)
-        unique_cnt = _uniform_resample_(idx, self.nsample) if self.sample_uniformly else None
-        grouped_xyz = grouping_operation(xyz.transpose(1, 2).contiguous(), idx)
+    def forward(self, xyz, new_xyz, features=None, pre=None):
+        """`pre` = (idx, grouped_xyz) from ball_query_and_group (a caller that shares one scan between scales)."""
+        unique_cnt = None
+        if pre is None and _fusable(xyz, self.sample_uniformly):
+            pre = ball_query_and_group(xyz, new_xyz, [(self.radius, self.nsample)])[0]
+        if pre is not None:
+            idx, grouped_xyz = pre
+        else:
+            idx = ball_query(self.radius, self.nsample, xyz, new_xyz)
+            unique_cnt = _uniform_resample_(idx, self.nsample) if self.sample_uniformly else None
+            grouped_xyz = grouping_operation(xyz.transpose(1, 2).contiguous(), idx)
         grouped_xyz = grouped_xyz - new_xyz.transpose(1, 2).unsqueeze(-1)
         if self.normalize_xyz:
             grouped_xyz = grouped_xyz / self.radius
@@ -212,10 +233,17 @@ class QueryAndLRFGroup(nn.Module):
         if self.ret_unique_cnt:
             assert self.sample_uniformly
 
-    def forward(self, xyz, new_xyz, features=None):
-        idx = ball_query(self.radius, self.nsample, xyz, new_xyz)
-        unique_cnt = _uniform_resample_(idx, self.nsample) if self.sample_uniformly else None
-        grouped_xyz = grouping_operation(xyz.transpose(1, 2).contiguous(), idx)  # (B,3,npoint,nsample)
+    def forward(self, xyz, new_xyz, features=None, pre=None):
+        """`pre` = (idx, grouped_xyz) from ball_query_and_group (a caller that shares one scan between scales)."""
+        unique_cnt = None
+        if pre is None and _fusable(xyz, self.sample_uniformly):
+            pre = ball_query_and_group(xyz, new_xyz, [(self.radius, self.nsample)])[0]
+        if pre is not None:
+            idx, grouped_xyz = pre
+        else:
+            idx = ball_query(self.radius, self.nsample, xyz, new_xyz)
+            unique_cnt = _uniform_resample_(idx, self.nsample) if self.sample_uniformly else None
+            grouped_xyz = grouping_operation(xyz.transpose(1, 2).contiguous(), idx)  # (B,3,npoint,nsample)
         lrf_features = self.lrf(xyz, grouped_xyz.transpose(1, 2))  # (B,npoint,3,nsample)
         lrf_features = lrf_features.transpose(1, 2).contiguous()
         grouped_xyz = grouped_xyz - new_xyz.transpose(1, 2).unsqueeze(-1)
