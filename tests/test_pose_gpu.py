@@ -202,6 +202,46 @@ def test_fine_stagewise_and_end_to_end(cuda, seed, n, c):
         assert PO.relative_translation_error(tw, two).max() <= T_TOL_REL
 
 
+def _ragged_fine_inputs(seed, B, n1, n2, dev, scale):
+    """Planted correspondences between clouds of different sizes + logits of a chosen dynamic range."""
+    g = torch.Generator().manual_seed(seed)
+    p2 = torch.randn(B, n2, 3, generator=g)
+    p2 = p2 / p2.norm(dim=2, keepdim=True).clamp_min(1e-6) * torch.rand(B, n2, 1, generator=g) ** (1 / 3)
+    perm = torch.stack([torch.randperm(n2, generator=g)[:n1] if n1 <= n2 else torch.randint(0, n2, (n1,), generator=g)
+                        for _ in range(B)])
+    Rg = torch.linalg.qr(torch.randn(B, 3, 3, generator=g))[0]
+    Rg = Rg * torch.sign(torch.det(Rg)).view(B, 1, 1)
+    tg = 0.3 * torch.randn(B, 3, generator=g)
+    src = torch.gather(p2, 1, perm.unsqueeze(2).expand(B, n1, 3))
+    p1 = src @ Rg.transpose(1, 2) + tg.unsqueeze(1) + 0.005 * torch.randn(B, n1, 3, generator=g)
+    att = torch.randn(B, n1 + 1, n2 + 1, generator=g)
+    att[:, 1:, 1:].scatter_add_(2, (perm).unsqueeze(2), torch.full((B, n1, 1), 6.0))
+    score = 0.5 + 0.5 * torch.rand(B, n1 + n2, generator=g)
+    return (att * scale).to(dev), score.to(dev), p1.to(dev), p2.to(dev)
+
+
+@pytest.mark.parametrize("n1,n2,scale", [
+    (700, 900, 1.0),      # ragged large geometry: partial last strip and row tile
+    (1023, 513, 1.5),
+    (2048, 2048, 1.0),
+    (2048, 2048, 30.0),   # logit range ~ 500: the single-reference sums are flagged, exact path redoes them
+    (600, 1100, 12.0),
+])
+def test_fine_large_geometry_ragged_and_wide_range(cuda, n1, n2, scale):
+    att, score, p1, p2 = _ragged_fine_inputs(n1 + n2, 2, n1, n2, cuda, scale)
+    for sc in (score, None):
+        R, t, s, m = MU()._fine(att, sc, p1, p2, None, 0.15, 0.001 if sc is not None else 0.0, return_debug=True)
+        Ro, to, so, o = PO.fine_pose(att, sc, p1, p2, None, 0.15, debug=True)
+        assert torch.isfinite(R).all() and torch.isfinite(t).all()
+        # masks: bit-exact except where the two candidates of an arg-max are equal to float noise
+        assert (m["w1"] != o["w1"]).float().mean() <= 2e-3
+        same = (m["w1"] == o["w1"])
+        assert torch.allclose(m["asum"][same], o["rowsum"][same], rtol=2e-4, atol=1e-9)
+        if torch.equal(m["w1"], o["w1"]):
+            assert PO.rotation_geodesic_deg(R, Ro).max() <= ROT_TOL_DEG
+            assert PO.relative_translation_error(t, to).max() <= T_TOL_REL
+
+
 def test_fine_api_and_determinism(cuda):
     d = batch(300, 2, 2048, 256, cuda)
     atten = MU().compute_feature_similarity(d["f1"], d["f2"], "cosine", 0.1, True)

@@ -56,6 +56,7 @@ void carve_assign(Carver& cv, int b, const AssignGeom& g, AssignWs& ws) {
   ws.colpm = cv.take<float>((size_t)b * g.C * g.ntr);
   ws.ai0 = cv.take<float>((size_t)b * g.R);
   ws.a0j = cv.take<float>((size_t)b * g.C);
+  ws.flags = cv.take<int>((size_t)b);
 }
 
 template <int TR, int TC>
@@ -104,8 +105,9 @@ k_stats_tile(const float* __restrict__ atten, int R, int C, int ntr, int ntc,
 __global__ void __launch_bounds__(256)
 k_stats_merge(const float2* __restrict__ rowpart, const float2* __restrict__ colpart, int R, int C,
               int ntr, int ntc, float* __restrict__ rmax, float* __restrict__ rsum,
-              float* __restrict__ cmax, float* __restrict__ csum) {
+              float* __restrict__ cmax, float* __restrict__ csum, const int* __restrict__ only_flagged) {
   const int b = blockIdx.y;
+  if (only_flagged && !only_flagged[b]) return;
   const int i = blockIdx.x * 256 + threadIdx.x;
   const float2* p;
   int n;
@@ -505,9 +507,10 @@ __device__ __forceinline__ void stats_stream_body(const float* __restrict__ A, i
 
 __global__ void __launch_bounds__(ST_WARPS * 32)
 k_stats_stream(const float* __restrict__ atten, int R, int C, int ntr, int ntc,
-               float2* __restrict__ rowpart, float2* __restrict__ colpart) {
+               float2* __restrict__ rowpart, float2* __restrict__ colpart, const int* __restrict__ only_flagged) {
   __shared__ float2 s_col[ST_WARPS][ST_TC];
   const int b = blockIdx.z, tr = blockIdx.y, tc = blockIdx.x;
+  if (only_flagged && !only_flagged[b]) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r0 = tr * ST_TR, c0 = tc * ST_TC;
   const float* A = atten + (size_t)b * R * C;
@@ -534,190 +537,6 @@ k_stats_stream(const float* __restrict__ atten, int R, int C, int ntr, int ntc,
   }
 }
 
-// Per-thread column constants of the streaming label / row-sum passes:
-//   A_ij = exp(v - rm_i)/rs_i * exp(v - cm_j)/cs_j * s1_i * s2_j
-//        = ex2( v*2log2e - (rm_i + cm_j) log2e ) * (s1_i / rs_i) * (s2_j / cs_j)
-struct ColConst {
-  float cml[ST_CPT];   // cm_j * log2e   (+inf for out-of-range columns -> A = 0)
-  float cmul[ST_CPT];  // s2_j / cs_j
-};
-
-__device__ __forceinline__ void load_col_consts(ColConst& k, int b, int C, int c0, int lane,
-                                                const float* __restrict__ cmax, const float* __restrict__ csum,
-                                                const float* __restrict__ score2, int ld2) {
-#pragma unroll
-  for (int q = 0; q < ST_CPT; ++q) {
-    int gj = c0 + lane + 32 * q;
-    bool ok = gj < C;
-    float cm = ok ? cmax[(size_t)b * C + gj] : INFINITY;
-    float cs = ok ? csum[(size_t)b * C + gj] : 1.f;
-    float s2 = (ok && gj > 0 && score2) ? score2[(size_t)b * ld2 + gj - 1] : 1.f;
-    k.cml[q] = cm * kLog2e;
-    k.cmul[q] = ok ? s2 / cs : 0.f;
-  }
-}
-
-// per-row constants (broadcast loads): rm_i*log2e and s1_i/rs_i
-__device__ __forceinline__ void load_row_consts(int b, int R, int g, const float* __restrict__ rmax,
-                                                const float* __restrict__ rsum, const float* __restrict__ score1,
-                                                int ld1, float& rml, float& rmul) {
-  rml = rmax[(size_t)b * R + g] * kLog2e;
-  const float s1 = (g > 0 && score1) ? score1[(size_t)b * ld1 + g - 1] : 1.f;
-  rmul = s1 / rsum[(size_t)b * R + g];
-}
-
-// pass 2: background-vs-foreground arg-max tests (see k_labels_tile)
-template <bool CHECK>
-__device__ __forceinline__ void labels_stream_body(const float* __restrict__ A, int R, int C, int ntc, int b, int tc,
-                                                   int r0, int c0, int warp, int lane, const ColConst& kc,
-                                                   float (&cmx)[ST_CPT], const float* __restrict__ rmax,
-                                                   const float* __restrict__ rsum, const float* __restrict__ score1,
-                                                   int ld1, float* __restrict__ rowpm, float* __restrict__ ai0,
-                                                   float* __restrict__ a0j) {
-  const int ncols_left = C - c0 - lane;
-  const bool first_col_mine = (c0 == 0 && lane == 0);  // global column 0 == my k = 0
-  for (int rr = warp; rr < ST_TR; rr += 2 * ST_WARPS) {
-    const int ga = r0 + rr, gb = ga + ST_WARPS;
-    if (CHECK && ga >= R) break;
-    const bool hasb = !CHECK || gb < R;
-    float va[ST_CPT], vb[ST_CPT];
-    const float* pa = A + (size_t)ga * C + c0 + lane;
-    load_row8<CHECK>(pa, ncols_left, true, 0.f, va);
-    load_row8<CHECK>(pa + (size_t)ST_WARPS * C, ncols_left, hasb, 0.f, vb);
-    float rmla, rmula, rmlb, rmulb;
-    load_row_consts(b, R, ga, rmax, rsum, score1, ld1, rmla, rmula);
-    load_row_consts(b, R, hasb ? gb : ga, rmax, rsum, score1, ld1, rmlb, rmulb);
-    float rm[2] = {-INFINITY, -INFINITY};
-    float a0 = 0.f, b0 = 0.f;
-#pragma unroll
-    for (int k = 0; k < ST_CPT; ++k) {
-      float aa = (ex2_fast(fmaf(va[k], 2.f * kLog2e, -(rmla + kc.cml[k]))) * rmula) * kc.cmul[k];
-      float ab = (ex2_fast(fmaf(vb[k], 2.f * kLog2e, -(rmlb + kc.cml[k]))) * rmulb) * kc.cmul[k];
-      if (k == 0 && first_col_mine) {
-        a0 = aa; b0 = ab;            // background column: excluded from the row max
-      } else {
-        rm[0] = fmaxf(rm[0], aa);
-        rm[1] = fmaxf(rm[1], ab);
-      }
-      // column max over rows >= 1 ; row 0 is the background row (only in the tile row tr == 0, warp 0)
-      if (ga > 0) cmx[k] = fmaxf(cmx[k], aa);
-      else if (32 * k < ncols_left) a0j[(size_t)b * C + c0 + lane + 32 * k] = aa;
-      if (hasb) cmx[k] = fmaxf(cmx[k], ab);
-    }
-    warp_reduce_multi<2>(rm, OpMax());
-    if (lane == 0) rowpm[((size_t)b * R + ga) * ntc + tc] = rm[0];
-    if (lane == 16 && hasb) rowpm[((size_t)b * R + gb) * ntc + tc] = rm[0];
-    if (first_col_mine) {
-      ai0[(size_t)b * R + ga] = a0;
-      if (hasb) ai0[(size_t)b * R + gb] = b0;
-    }
-  }
-}
-
-__global__ void __launch_bounds__(ST_WARPS * 32)
-k_labels_stream(const float* __restrict__ atten, int R, int C, int ntr, int ntc,
-                const float* __restrict__ rmax, const float* __restrict__ rsum,
-                const float* __restrict__ cmax, const float* __restrict__ csum,
-                const float* __restrict__ score1, int ld1, const float* __restrict__ score2, int ld2,
-                float* __restrict__ rowpm, float* __restrict__ colpm, float* __restrict__ ai0,
-                float* __restrict__ a0j) {
-  __shared__ float s_col[ST_WARPS][ST_TC];
-  const int b = blockIdx.z, tr = blockIdx.y, tc = blockIdx.x;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int r0 = tr * ST_TR, c0 = tc * ST_TC;
-  const float* A = atten + (size_t)b * R * C;
-  ColConst kc;
-  load_col_consts(kc, b, C, c0, lane, cmax, csum, score2, ld2);
-  float cmx[ST_CPT];
-#pragma unroll
-  for (int k = 0; k < ST_CPT; ++k) cmx[k] = -INFINITY;
-  if (r0 + ST_TR <= R && c0 + ST_TC <= C && r0 > 0)
-    labels_stream_body<false>(A, R, C, ntc, b, tc, r0, c0, warp, lane, kc, cmx, rmax, rsum, score1, ld1, rowpm, ai0, a0j);
-  else
-    labels_stream_body<true>(A, R, C, ntc, b, tc, r0, c0, warp, lane, kc, cmx, rmax, rsum, score1, ld1, rowpm, ai0, a0j);
-#pragma unroll
-  for (int k = 0; k < ST_CPT; ++k) s_col[warp][lane + 32 * k] = cmx[k];
-  __syncthreads();
-  const int c = threadIdx.x;
-  if (c0 + c < C) {
-    float m = -INFINITY;
-#pragma unroll
-    for (int w = 0; w < ST_WARPS; ++w) m = fmaxf(m, s_col[w][c]);
-    colpm[((size_t)b * C + c0 + c) * ntr + tr] = m;
-  }
-}
-
-// pass 3 (fine): per row  sum_{j>=1} A_ij w2_j {x_j, y_j, z_j, 1}
-template <bool CHECK>
-__device__ __forceinline__ void rows_stream_body(const float* __restrict__ A, int R, int C, int ntc, int b, int tc,
-                                                 int r0, int c0, int warp, int lane, const ColConst& kc,
-                                                 const float (&px)[ST_CPT], const float (&py)[ST_CPT],
-                                                 const float (&pz)[ST_CPT], const float* __restrict__ rmax,
-                                                 const float* __restrict__ rsum, const float* __restrict__ score1,
-                                                 int ld1, float4* __restrict__ rowpart4) {
-  const int ncols_left = C - c0 - lane;
-  const int N1 = R - 1;
-  for (int rr = warp; rr < ST_TR; rr += 2 * ST_WARPS) {
-    const int ga = r0 + rr, gb = ga + ST_WARPS;
-    if (CHECK && ga >= R) break;
-    const bool hasb = !CHECK || gb < R;
-    float va[ST_CPT], vb[ST_CPT];
-    const float* pa = A + (size_t)ga * C + c0 + lane;
-    load_row8<CHECK>(pa, ncols_left, true, 0.f, va);
-    load_row8<CHECK>(pa + (size_t)ST_WARPS * C, ncols_left, hasb, 0.f, vb);
-    float rmla, rmula, rmlb, rmulb;
-    load_row_consts(b, R, ga, rmax, rsum, score1, ld1, rmla, rmula);
-    load_row_consts(b, R, hasb ? gb : ga, rmax, rsum, score1, ld1, rmlb, rmulb);
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // a: x y z w | b: x y z w
-#pragma unroll
-    for (int k = 0; k < ST_CPT; ++k) {
-      float aa = ex2_fast(fmaf(va[k], 2.f * kLog2e, -(rmla + kc.cml[k]))) * kc.cmul[k];
-      float ab = ex2_fast(fmaf(vb[k], 2.f * kLog2e, -(rmlb + kc.cml[k]))) * kc.cmul[k];
-      acc[0] = fmaf(aa, px[k], acc[0]); acc[1] = fmaf(aa, py[k], acc[1]); acc[2] = fmaf(aa, pz[k], acc[2]); acc[3] += aa;
-      acc[4] = fmaf(ab, px[k], acc[4]); acc[5] = fmaf(ab, py[k], acc[5]); acc[6] = fmaf(ab, pz[k], acc[6]); acc[7] += ab;
-    }
-    warp_reduce_multi<8>(acc, OpAdd());          // lane group (lane >> 2) holds component (lane >> 2)
-    if ((lane & 3) == 0) {
-      const int comp = lane >> 2;                // 0..3 row a, 4..7 row b
-      const bool isb = comp >= 4;
-      const int g = isb ? gb : ga;
-      if (g > 0 && (!isb || hasb)) {
-        float* dst = reinterpret_cast<float*>(rowpart4 + ((size_t)b * N1 + g - 1) * ntc + tc) + (comp & 3);
-        *dst = acc[0] * (isb ? rmulb : rmula);
-      }
-    }
-  }
-}
-
-__global__ void __launch_bounds__(ST_WARPS * 32)
-k_fine_rows_stream(const float* __restrict__ atten, int R, int C, int ntc,
-                   const float* __restrict__ rmax, const float* __restrict__ rsum,
-                   const float* __restrict__ cmax, const float* __restrict__ csum,
-                   const float* __restrict__ score1, int ld1, const float* __restrict__ score2, int ld2,
-                   const float* __restrict__ w2, const float* __restrict__ pts2,
-                   float4* __restrict__ rowpart4) {
-  const int b = blockIdx.z, tr = blockIdx.y, tc = blockIdx.x;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int r0 = tr * ST_TR, c0 = tc * ST_TC;
-  const int N2 = C - 1;
-  const float* A = atten + (size_t)b * R * C;
-  ColConst kc;
-  load_col_consts(kc, b, C, c0, lane, cmax, csum, score2, ld2);
-  float px[ST_CPT], py[ST_CPT], pz[ST_CPT];
-#pragma unroll
-  for (int k = 0; k < ST_CPT; ++k) {
-    int gj = c0 + lane + 32 * k;
-    bool ok = gj < C && gj > 0;
-    const float* p = pts2 + ((size_t)b * N2 + (ok ? gj - 1 : 0)) * 3;
-    px[k] = p[0]; py[k] = p[1]; pz[k] = p[2];
-    kc.cmul[k] = ok ? kc.cmul[k] * w2[(size_t)b * N2 + gj - 1] : 0.f;  // fold the column mask, drop the bg column
-  }
-  if (r0 + ST_TR <= R && c0 + ST_TC <= C)
-    rows_stream_body<false>(A, R, C, ntc, b, tc, r0, c0, warp, lane, kc, px, py, pz, rmax, rsum, score1, ld1, rowpart4);
-  else
-    rows_stream_body<true>(A, R, C, ntc, b, tc, r0, c0, warp, lane, kc, px, py, pz, rmax, rsum, score1, ld1, rowpart4);
-}
-
 // ------------------------------------------------------------------ host launchers
 template <int TR, int TC>
 static int stats_labels_t(const float* atten, const float* score1, int ld1, const float* score2, int ld2,
@@ -734,7 +553,7 @@ static int stats_labels_t(const float* atten, const float* score1, int ld1, cons
   k1<<<grid, AT, smem, st>>>(atten, g.R, g.C, g.ntr, g.ntc, ws.rowpart, ws.colpart);
   dim3 mg(ceil_div(g.R + g.C, 256), b);
   k_stats_merge<<<mg, 256, 0, st>>>(ws.rowpart, ws.colpart, g.R, g.C, g.ntr, g.ntc, ws.rmax, ws.rsum,
-                                    ws.cmax, ws.csum);
+                                    ws.cmax, ws.csum, nullptr);
   k2<<<grid, AT, smem, st>>>(atten, g.R, g.C, g.ntr, g.ntc, ws.rmax, ws.rsum, ws.cmax, ws.csum, score1,
                              ld1, score2, ld2, ws.rowpm, ws.colpm, ws.ai0, ws.a0j);
   k_labels_merge<<<mg, 256, 0, st>>>(ws.rowpm, ws.colpm, ws.ai0, ws.a0j, g.R, g.C, g.ntr, g.ntc, w1, w2);
@@ -746,17 +565,35 @@ int run_assignment_labels(const float* atten, const float* score1, int ld1, cons
                           int b, const AssignGeom& g, const AssignWs& ws, float* w1, float* w2,
                           cudaStream_t st) {
   if (g.TR == 32) return stats_labels_t<32, 128>(atten, score1, ld1, score2, ld2, b, g, ws, w1, w2, st);
-  // large geometry: register-streaming passes (same partial layout, same merges)
+  // large geometry: the streaming passes of assign_fine.cu
+  return run_fine_labels2(atten, score1, ld1, score2, ld2, b, g, ws, w1, w2, st);
+}
+
+// Exact (max-subtracting) statistics for the instances flagged by the single-reference pass of assign_fine.cu;
+// natural-log maxima and sums land in ws.{rmax,rsum,cmax,csum}.  Unflagged instances exit immediately.
+int run_exact_stats_flagged(const float* atten, int b, const AssignGeom& g, const AssignWs& ws, cudaStream_t st) {
   dim3 grid(g.ntc, g.ntr, b);
   dim3 mg(ceil_div(g.R + g.C, 256), b);
-  k_stats_stream<<<grid, ST_WARPS * 32, 0, st>>>(atten, g.R, g.C, g.ntr, g.ntc, ws.rowpart, ws.colpart);
-  k_stats_merge<<<mg, 256, 0, st>>>(ws.rowpart, ws.colpart, g.R, g.C, g.ntr, g.ntc, ws.rmax, ws.rsum,
-                                    ws.cmax, ws.csum);
-  k_labels_stream<<<grid, ST_WARPS * 32, 0, st>>>(atten, g.R, g.C, g.ntr, g.ntc, ws.rmax, ws.rsum, ws.cmax,
-                                                  ws.csum, score1, ld1, score2, ld2, ws.rowpm, ws.colpm,
-                                                  ws.ai0, ws.a0j);
-  k_labels_merge<<<mg, 256, 0, st>>>(ws.rowpm, ws.colpm, ws.ai0, ws.a0j, g.R, g.C, g.ntr, g.ntc, w1, w2);
-  count_launch(4);
+  k_stats_stream<<<grid, ST_WARPS * 32, 0, st>>>(atten, g.R, g.C, g.ntr, g.ntc, ws.rowpart, ws.colpart, ws.flags);
+  k_stats_merge<<<mg, 256, 0, st>>>(ws.rowpart, ws.colpart, g.R, g.C, g.ntr, g.ntc, ws.rmax, ws.rsum, ws.cmax,
+                                    ws.csum, ws.flags);
+  count_launch(2);
+  UPK_RETURN_LAST_ERROR();
+}
+
+int launch_labels_merge(const float* rowpm, const float* colpm, const float* ai0, const float* a0j, int b, int R,
+                        int C, int ntr, int ntc, float* w1, float* w2, cudaStream_t st) {
+  dim3 mg(ceil_div(R + C, 256), b);
+  k_labels_merge<<<mg, 256, 0, st>>>(rowpm, colpm, ai0, a0j, R, C, ntr, ntc, w1, w2);
+  count_launch();
+  UPK_RETURN_LAST_ERROR();
+}
+
+int launch_fine_rows_merge(const float4* rowpart4, const float* w1, int b, int n1, int ntc, float* soft,
+                           float* asum, cudaStream_t st) {
+  dim3 mg(ceil_div(n1, 256), b);
+  k_fine_rows_merge<<<mg, 256, 0, st>>>(rowpart4, w1, n1, ntc, soft, asum);
+  count_launch();
   UPK_RETURN_LAST_ERROR();
 }
 
@@ -816,14 +653,7 @@ int run_fine_rowsums(const float* atten, const float* score1, int ld1, const flo
                      const float* pts2, float4* rowpart4, float* soft, float* asum, cudaStream_t st) {
   if (g.TR == 32)
     return fine_rows_t<32, 128>(atten, score1, ld1, score2, ld2, b, g, ws, w1, w2, pts2, rowpart4, soft, asum, st);
-  dim3 grid(g.ntc, g.ntr, b);
-  k_fine_rows_stream<<<grid, ST_WARPS * 32, 0, st>>>(atten, g.R, g.C, g.ntc, ws.rmax, ws.rsum, ws.cmax, ws.csum,
-                                                     score1, ld1, score2, ld2, w2, pts2, rowpart4);
-  int n1 = g.R - 1;
-  dim3 mg(ceil_div(n1, 256), b);
-  k_fine_rows_merge<<<mg, 256, 0, st>>>(rowpart4, w1, n1, g.ntc, soft, asum);
-  count_launch(2);
-  UPK_RETURN_LAST_ERROR();
+  return run_fine_rows2(atten, b, g, ws, w1, w2, pts2, rowpart4, soft, asum, st);
 }
 
 }  // namespace upk

@@ -1,0 +1,623 @@
+// (1b) Dual-softmax assignment, LARGE geometry (fine stage: 2049 x 2049 logits per instance).
+// Reference: compute_fine_Rt[_overlap], model_utils.py:493-566 (softmax over rows x softmax over columns
+// x scores, background-vs-foreground arg-max tests, masked soft correspondences).
+//
+// Three streaming passes over `atten`, each reading every logit exactly once from HBM:
+//   pass 1  k_fine_stats   sum of exponentials per row and per column
+//   pass 2  k_fine_labels  max_j S_ij / max_i S_ij against the background entries  -> w1, w2
+//   pass 3  k_fine_rows    sum_j S_ij w2_j {x_j, y_j, z_j, 1}                       -> soft correspondences
+// with S_ij = softmax_row * softmax_col * s1_i * s2_j = 2^(2 v log2e - rml_i - cml_j) * rmul_i * cmul_j.
+//
+// Layout.  The background row 0 and column 0 are peeled off, so the main block (rows 1.., columns 1..)
+// of the standard shape is exactly 2048 x 2048: no edge tiles.  A CTA of 8 warps owns 128 rows x one
+// 256-column strip; a warp streams whole 256-column row segments from global memory into registers, two
+// rows per step (lane l owns columns l, l+32, ..: every load instruction is one coalesced 128-byte line;
+// `atten` rows are only 4-byte aligned, pitch 2049 floats, so neither 128-bit loads nor TMA apply), the
+// next two rows are prefetched while the current two are processed.  Column constants stay in registers
+// for the CTA's 128 rows, row constants are precomputed by the merge kernels (no division in the loops).
+// Arithmetic is packed f32x2 where two independent values share an instruction.
+//
+// Pass 1 uses ONE reference exponent per warp instead of per-row / per-column maxima: any reference
+// gives the same softmax as long as nothing overflows or underflows, so e = 2^(v log2e - g) serves the
+// row sum AND the column sum (one MUFU per logit).  g starts 8 octaves above the first row pair's
+// maximum and is raised (column sums rescaled) if a later partial sum exceeds 2^20.  Partial sums that
+// come out below 2^-80 or non-finite (logit range > ~50: never for cosine/temperature logits) raise a
+// per-instance flag and the exact max-subtracting kernels of assign.cu redo that instance.
+#include <math.h>
+
+#include "common.cuh"
+#include "launch_count.h"
+#include "pose_internal.h"
+
+namespace upk {
+
+constexpr int F2_RT = 128;                   // rows per CTA
+constexpr int F2_TC = 256;                   // columns per strip
+constexpr int F2_CPT = F2_TC / 32;           // 8 columns per lane
+constexpr int F2_WARPS = 8;
+constexpr int F2_THREADS = F2_WARPS * 32;
+constexpr int F2_PAIRS = F2_RT / (2 * F2_WARPS);  // 8 row pairs per warp
+constexpr float kL2E = 1.4426950408889634f;
+constexpr float kRefMargin = 8.f;            // octaves between a fresh reference and the observed maximum
+constexpr float kSumHigh = 1048576.f;        // 2^20: raise the reference
+constexpr float kSumLow = 8.271806e-25f;     // 2^-80: partial sums below this are not trusted
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ld_stream_f1(const float* p) {
+  float r;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ bool sum_untrusted(float s) { return !(s >= kSumLow && s < INFINITY); }
+
+// Sum / max of two per-lane values across the warp: lanes 0-15 return row a's total, lanes 16-31 row b's.
+template <class Op>
+__device__ __forceinline__ float reduce_pair(float a, float b, int lane, Op op) {
+  const bool upper = (lane & 16) != 0;
+  float v = op(upper ? b : a, __shfl_xor_sync(kFull, upper ? a : b, 16));
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(kFull, v, o));
+  return v;
+}
+struct F2Add { __device__ __forceinline__ float operator()(float a, float b) const { return a + b; } };
+struct F2Max { __device__ __forceinline__ float operator()(float a, float b) const { return fmaxf(a, b); } };
+
+// Two row segments (rows ra and ra + 8) of the strip: 16 independent coalesced loads.
+struct RowPair {
+  float a[F2_CPT], b[F2_CPT];
+};
+template <bool CHECK>
+__device__ __forceinline__ void load_pair(const float* __restrict__ pa, size_t pitch8, int ncl, bool oka, bool okb,
+                                          RowPair& v) {
+#pragma unroll
+  for (int k = 0; k < F2_CPT; ++k) {
+    if (CHECK) {
+      const bool c = 32 * k < ncl;
+      v.a[k] = (oka && c) ? ld_stream_f1(pa + 32 * k) : -INFINITY;
+      v.b[k] = (okb && c) ? ld_stream_f1(pa + pitch8 + 32 * k) : -INFINITY;
+    } else {
+      v.a[k] = ld_stream_f1(pa + 32 * k);
+      v.b[k] = ld_stream_f1(pa + pitch8 + 32 * k);
+    }
+  }
+}
+
+// CTA coordinates shared by the three passes
+struct F2Tile {
+  int b, cs, rt, warp, lane;
+  int i0;    // first row of this warp (rows i0 + 16 p and i0 + 16 p + 8, p < F2_PAIRS)
+  int j0;    // first column of this lane (columns j0 + 32 k)
+  int ncl;   // C - j0: column k is valid iff 32 k < ncl
+  bool full; // no row / column of the CTA's tile is out of range
+};
+__device__ __forceinline__ F2Tile f2_tile(int R, int C) {
+  F2Tile t;
+  t.b = blockIdx.z; t.rt = blockIdx.y; t.cs = blockIdx.x;
+  t.warp = threadIdx.x >> 5; t.lane = threadIdx.x & 31;
+  t.i0 = 1 + t.rt * F2_RT + t.warp;
+  t.j0 = 1 + t.cs * F2_TC + t.lane;
+  t.ncl = C - t.j0;
+  t.full = (1 + (t.rt + 1) * F2_RT <= R) && (1 + (t.cs + 1) * F2_TC <= C);
+  return t;
+}
+
+// ------------------------------------------------------------------ pass 1: sums of exponentials
+struct StatsState {
+  float g;            // warp reference exponent (log2 units); -inf until the first row pair
+  float cs[F2_CPT];   // column sums of 2^(v log2e - g) over this warp's rows
+  float c0;           // same for the background column (strip 0, lane 0)
+  bool bad;
+};
+
+// One row pair.  SINGLE: only row `ra` exists (the background row 0, or a ragged last pair).
+template <bool CHECK, bool STRIP0>
+__device__ __forceinline__ void stats_pair(const RowPair& v, float v0a, float v0b, int lane, StatsState& st,
+                                           float2& out_a, float2& out_b) {
+  if (st.g == -INFINITY) {  // first pair of this warp: reference = maximum + margin (warp-uniform branch)
+    float m = fmaxf(v0a, v0b);
+#pragma unroll
+    for (int k = 0; k < F2_CPT; ++k) m = fmaxf(m, fmaxf(v.a[k], v.b[k]));
+    m = warp_max(m);
+    st.g = fmaf(m, kL2E, kRefMargin);
+  }
+  const float g = st.g;
+  const unsigned long long L2 = pack2(kL2E, kL2E), NG = pack2(-g, -g);
+  unsigned long long sa2 = pack2(0.f, 0.f), sb2 = sa2;
+#pragma unroll
+  for (int kk = 0; kk < F2_CPT / 2; ++kk) {
+    float xa0, xa1, xb0, xb1;
+    unpack2(fma2(pack2(v.a[2 * kk], v.a[2 * kk + 1]), L2, NG), xa0, xa1);
+    unpack2(fma2(pack2(v.b[2 * kk], v.b[2 * kk + 1]), L2, NG), xb0, xb1);
+    const unsigned long long ea = pack2(ex2_approx(xa0), ex2_approx(xa1));
+    const unsigned long long eb = pack2(ex2_approx(xb0), ex2_approx(xb1));
+    sa2 = add2(sa2, ea);
+    sb2 = add2(sb2, eb);
+    float c0, c1;
+    unpack2(add2(add2(ea, eb), pack2(st.cs[2 * kk], st.cs[2 * kk + 1])), c0, c1);
+    st.cs[2 * kk] = c0;
+    st.cs[2 * kk + 1] = c1;
+  }
+  float sa, sb, t0, t1;
+  unpack2(sa2, t0, t1); sa = t0 + t1;
+  unpack2(sb2, t0, t1); sb = t0 + t1;
+  if (STRIP0) {  // background column: lane 0 carries v0a / v0b, the other lanes -inf (-> 0)
+    const float e0a = ex2_approx(fmaf(v0a, kL2E, -g)), e0b = ex2_approx(fmaf(v0b, kL2E, -g));
+    sa += e0a; sb += e0b;
+    st.c0 += e0a + e0b;
+  }
+  const float tot = reduce_pair(sa, sb, lane, F2Add());
+  out_a = out_b = make_float2(g, tot);
+  if (__any_sync(kFull, fmaxf(sa, sb) > kSumHigh)) {
+    // some logit sits far above the reference: raise it for the rows to come (this pair's sums stay
+    // attached to the old reference) and rescale the running column sums
+    const float mx = warp_max(fmaxf(sa, sb));
+    const float gn = g + lg2_approx(mx) + kRefMargin;
+    const float sc = ex2_approx(g - gn);
+#pragma unroll
+    for (int k = 0; k < F2_CPT; ++k) st.cs[k] *= sc;
+    st.c0 *= sc;
+    st.g = gn;
+  }
+}
+
+template <bool CHECK, bool STRIP0>
+__device__ __forceinline__ void stats_body(const float* __restrict__ A, int R, int C, int nstrip, const F2Tile& t,
+                                           float2* __restrict__ rowpart, StatsState& st) {
+  const size_t pitch8 = (size_t)8 * C;
+  const float* col0 = A;  // column 0 of row i: A[i * C]
+  auto emit = [&](int ra, bool okb, const float2& oa, const float2& ob) {
+    if (t.lane == 0) {
+      rowpart[((size_t)t.b * R + ra) * nstrip + t.cs] = oa;
+      st.bad |= sum_untrusted(oa.y);
+    }
+    if (t.lane == 16 && okb) {
+      rowpart[((size_t)t.b * R + ra + 8) * nstrip + t.cs] = ob;
+      st.bad |= sum_untrusted(ob.y);
+    }
+  };
+  if (t.rt == 0 && t.warp == 0) {  // the background row 0 rides with the first row tile
+    RowPair v;
+    load_pair<true>(A + t.j0, pitch8, t.ncl, true, false, v);
+    float v0a = -INFINITY;
+    if (STRIP0 && t.lane == 0) v0a = col0[0];
+    float2 oa, ob;
+    stats_pair<true, STRIP0>(v, v0a, -INFINITY, t.lane, st, oa, ob);
+    if (t.lane == 0) {
+      rowpart[((size_t)t.b * R) * nstrip + t.cs] = oa;
+      st.bad |= sum_untrusted(oa.y);
+    }
+  }
+  // two row pairs in flight: the loads of pair p + 1 are issued before pair p is processed
+  auto ld = [&](RowPair& v, float& z0a, float& z0b, int p) {
+    const int ra = t.i0 + 16 * p;
+    const bool oka = !CHECK || ra < R, okb = !CHECK || ra + 8 < R;
+    load_pair<CHECK>(A + (size_t)ra * C + t.j0, pitch8, t.ncl, oka, okb, v);
+    if (STRIP0) {
+      z0a = z0b = -INFINITY;
+      if (t.lane == 0) {
+        if (oka) z0a = col0[(size_t)ra * C];
+        if (okb) z0b = col0[(size_t)(ra + 8) * C];
+      }
+    }
+  };
+  auto comp = [&](const RowPair& v, float z0a, float z0b, int p) {
+    const int ra = t.i0 + 16 * p;
+    if (CHECK && ra >= R) return;
+    float2 oa, ob;
+    stats_pair<CHECK, STRIP0>(v, z0a, z0b, t.lane, st, oa, ob);
+    emit(ra, !CHECK || ra + 8 < R, oa, ob);
+  };
+  RowPair va, vb;
+  float a0a = -INFINITY, a0b = -INFINITY, b0a = -INFINITY, b0b = -INFINITY;
+  ld(va, a0a, a0b, 0);
+#pragma unroll 1
+  for (int p = 0; p < F2_PAIRS; p += 2) {
+    ld(vb, b0a, b0b, p + 1);
+    comp(va, a0a, a0b, p);
+    if (p + 2 < F2_PAIRS) ld(va, a0a, a0b, p + 2);
+    comp(vb, b0a, b0b, p + 1);
+  }
+}
+
+__global__ void __launch_bounds__(F2_THREADS, 2)
+k_fine_stats(const float* __restrict__ atten, int R, int C, int nstrip, int nrt, float2* __restrict__ rowpart,
+             float2* __restrict__ colpart, int* __restrict__ flags) {
+  __shared__ float s_cs[F2_WARPS][F2_TC + 1];
+  __shared__ float s_g[F2_WARPS];
+  const F2Tile t = f2_tile(R, C);
+  const float* A = atten + (size_t)t.b * R * C;
+  StatsState st;
+  st.g = -INFINITY; st.c0 = 0.f; st.bad = false;
+#pragma unroll
+  for (int k = 0; k < F2_CPT; ++k) st.cs[k] = 0.f;
+  if (t.cs == 0) {
+    if (t.full) stats_body<false, true>(A, R, C, nstrip, t, rowpart, st);
+    else stats_body<true, true>(A, R, C, nstrip, t, rowpart, st);
+  } else {
+    if (t.full) stats_body<false, false>(A, R, C, nstrip, t, rowpart, st);
+    else stats_body<true, false>(A, R, C, nstrip, t, rowpart, st);
+  }
+  // combine the 8 warps' column sums (each attached to its own reference)
+#pragma unroll
+  for (int k = 0; k < F2_CPT; ++k) s_cs[t.warp][t.lane + 32 * k] = st.cs[k];
+  if (t.lane == 0) {
+    s_cs[t.warp][F2_TC] = st.c0;
+    s_g[t.warp] = st.g;
+  }
+  __syncthreads();
+  float G = -INFINITY;
+#pragma unroll
+  for (int w = 0; w < F2_WARPS; ++w) G = fmaxf(G, s_g[w]);
+  bool bad = st.bad;
+  for (int c = threadIdx.x; c < F2_TC + (t.cs == 0 ? 1 : 0); c += F2_THREADS) {
+    const int gj = c == F2_TC ? 0 : 1 + t.cs * F2_TC + c;
+    if (gj >= C) continue;
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < F2_WARPS; ++w) {
+      const float gw = s_g[w];
+      if (gw != -INFINITY) s += s_cs[w][c] * ex2_approx(gw - G);
+    }
+    colpart[((size_t)t.b * C + gj) * nrt + t.rt] = make_float2(G, s);
+    bad |= sum_untrusted(s);
+  }
+  if (bad) atomicOr(flags + t.b, 1);
+}
+
+// rows and columns: total = sum_p s_p 2^(g_p - G);  outputs rml = G (log2 units), rmul = score / total.
+// Instances flagged by pass 1 are skipped here (the exact path fills them in).
+__global__ void __launch_bounds__(256)
+k_fine_stats_merge(const float2* __restrict__ rowpart, const float2* __restrict__ colpart, int R, int C, int nstrip,
+                   int nrt, const float* __restrict__ score1, int ld1, const float* __restrict__ score2, int ld2,
+                   const int* __restrict__ flags, float* __restrict__ rml, float* __restrict__ rmul,
+                   float* __restrict__ cml, float* __restrict__ cmul) {
+  const int b = blockIdx.y;
+  if (flags[b]) return;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const float2* p;
+  int n;
+  float *ol, *om, sc = 1.f;
+  if (i < R) {
+    p = rowpart + ((size_t)b * R + i) * nstrip; n = nstrip;
+    ol = rml + (size_t)b * R + i; om = rmul + (size_t)b * R + i;
+    if (i > 0 && score1) sc = score1[(size_t)b * ld1 + i - 1];
+  } else if (i < R + C) {
+    const int c = i - R;
+    p = colpart + ((size_t)b * C + c) * nrt; n = nrt;
+    ol = cml + (size_t)b * C + c; om = cmul + (size_t)b * C + c;
+    if (c > 0 && score2) sc = score2[(size_t)b * ld2 + c - 1];
+  } else {
+    return;
+  }
+  float G = -INFINITY;
+  for (int k = 0; k < n; ++k) G = fmaxf(G, p[k].x);
+  float s = 0.f;
+  for (int k = 0; k < n; ++k) s += p[k].y * exp2f(p[k].x - G);
+  *ol = G;
+  *om = sc / s;
+}
+
+// exact-path results (natural-log maxima and sums from assign.cu's k_stats_stream / k_stats_merge, written
+// into the same buffers) -> the (rml, rmul, cml, cmul) form, flagged instances only
+__global__ void __launch_bounds__(256)
+k_fine_stats_convert(int R, int C, const float* __restrict__ score1, int ld1, const float* __restrict__ score2,
+                     int ld2, const int* __restrict__ flags, float* __restrict__ rml, float* __restrict__ rmul,
+                     float* __restrict__ cml, float* __restrict__ cmul) {
+  const int b = blockIdx.y;
+  if (!flags[b]) return;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i < R) {
+    const float sc = (i > 0 && score1) ? score1[(size_t)b * ld1 + i - 1] : 1.f;
+    const size_t o = (size_t)b * R + i;
+    rml[o] = rml[o] * kL2E;
+    rmul[o] = sc / rmul[o];
+  } else if (i < R + C) {
+    const int c = i - R;
+    const float sc = (c > 0 && score2) ? score2[(size_t)b * ld2 + c - 1] : 1.f;
+    const size_t o = (size_t)b * C + c;
+    cml[o] = cml[o] * kL2E;
+    cmul[o] = sc / cmul[o];
+  }
+}
+
+// ------------------------------------------------------------------ passes 2 and 3: shared pieces
+struct ColConst2 {
+  unsigned long long ncml[F2_CPT / 2];  // packed -cml_j
+  unsigned long long cmul[F2_CPT / 2];  // packed  s2_j / cs_j   (pass 3: times w2_j)
+};
+__device__ __forceinline__ void load_col_consts2(ColConst2& kc, const F2Tile& t, int C, const float* __restrict__ cml,
+                                                 const float* __restrict__ cmul, const float* __restrict__ w2) {
+#pragma unroll
+  for (int kk = 0; kk < F2_CPT / 2; ++kk) {
+    float l[2], m[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int k = 2 * kk + h;
+      const bool ok = 32 * k < t.ncl;
+      const size_t o = (size_t)t.b * C + t.j0 + 32 * k;
+      l[h] = ok ? -cml[o] : 0.f;
+      m[h] = ok ? cmul[o] : 0.f;
+      if (w2 && ok) m[h] *= w2[(size_t)t.b * (C - 1) + t.j0 + 32 * k - 1];
+    }
+    kc.ncml[kk] = pack2(l[0], l[1]);
+    kc.cmul[kk] = pack2(m[0], m[1]);
+  }
+}
+
+// e_k = 2^(2 v_k log2e - rml - cml_k) for the 8 columns of one row, as 4 packed pairs
+__device__ __forceinline__ void row_exps(const float (&v)[F2_CPT], float nrml, const ColConst2& kc,
+                                         unsigned long long (&e)[F2_CPT / 2]) {
+  const unsigned long long L2 = pack2(2.f * kL2E, 2.f * kL2E), NR = pack2(nrml, nrml);
+#pragma unroll
+  for (int kk = 0; kk < F2_CPT / 2; ++kk) {
+    float x0, x1;
+    unpack2(fma2(pack2(v[2 * kk], v[2 * kk + 1]), L2, add2(NR, kc.ncml[kk])), x0, x1);
+    e[kk] = pack2(ex2_approx(x0), ex2_approx(x1));
+  }
+}
+
+// ------------------------------------------------------------------ pass 2: background-vs-foreground tests
+//   w1[i-1] = (argmax_j S[i][:] > 0)  <=>  max_{j>=1} S[i][j] > S[i][0]   (torch.max keeps the first maximum)
+template <bool CHECK, bool STRIP0>
+__device__ __forceinline__ void labels_body(const float* __restrict__ A, int R, int C, int nstrip, const F2Tile& t,
+                                            const ColConst2& kc, float cml0, float cmul0,
+                                            const float* __restrict__ rml, const float* __restrict__ rmul,
+                                            float* __restrict__ rowpm, float* __restrict__ ai0,
+                                            float (&cmx)[F2_CPT]) {
+  const size_t pitch8 = (size_t)8 * C;
+  auto ld = [&](RowPair& v, float& z0a, float& z0b, int p) {
+    const int ra = t.i0 + 16 * p;
+    const bool oka = !CHECK || ra < R, okb = !CHECK || ra + 8 < R;
+    load_pair<CHECK>(A + (size_t)ra * C + t.j0, pitch8, t.ncl, oka, okb, v);
+    if (STRIP0 && t.lane == 0) {
+      z0a = oka ? A[(size_t)ra * C] : 0.f;
+      z0b = okb ? A[(size_t)(ra + 8) * C] : 0.f;
+    }
+  };
+  auto comp = [&](const RowPair& cur, float c0a, float c0b, int p) {
+    const int ra = t.i0 + 16 * p, rb = ra + 8;
+    if (CHECK && ra >= R) return;
+    const bool okb = !CHECK || rb < R;
+    const size_t oa = (size_t)t.b * R + ra, ob = (size_t)t.b * R + (okb ? rb : ra);
+    const float rmla = rml[oa], rmula = rmul[oa], rmlb = rml[ob], rmulb = rmul[ob];
+    unsigned long long ea[F2_CPT / 2], eb[F2_CPT / 2];
+    row_exps(cur.a, -rmla, kc, ea);
+    row_exps(cur.b, -rmlb, kc, eb);
+    const unsigned long long MA = pack2(rmula, rmula), MB = pack2(rmulb, rmulb);
+    float ma = -INFINITY, mb = -INFINITY;
+#pragma unroll
+    for (int kk = 0; kk < F2_CPT / 2; ++kk) {
+      float a0, a1, b0, b1;
+      unpack2(mul2(mul2(ea[kk], MA), kc.cmul[kk]), a0, a1);
+      unpack2(mul2(mul2(eb[kk], MB), kc.cmul[kk]), b0, b1);
+      if (CHECK) {  // out-of-range entries must not take part in any maximum
+        const bool v0 = 32 * (2 * kk) < t.ncl, v1 = 32 * (2 * kk + 1) < t.ncl;
+        a0 = v0 ? a0 : -INFINITY; a1 = v1 ? a1 : -INFINITY;
+        b0 = (v0 && okb) ? b0 : -INFINITY; b1 = (v1 && okb) ? b1 : -INFINITY;
+      }
+      ma = fmaxf(ma, fmaxf(a0, a1));
+      mb = fmaxf(mb, fmaxf(b0, b1));
+      cmx[2 * kk] = fmaxf(cmx[2 * kk], fmaxf(a0, b0));
+      cmx[2 * kk + 1] = fmaxf(cmx[2 * kk + 1], fmaxf(a1, b1));
+    }
+    const float m = reduce_pair(ma, mb, t.lane, F2Max());
+    if (t.lane == 0) rowpm[oa * nstrip + t.cs] = m;
+    if (t.lane == 16 && okb) rowpm[((size_t)t.b * R + rb) * nstrip + t.cs] = m;
+    if (STRIP0 && t.lane == 0) {
+      ai0[oa] = (ex2_approx(fmaf(c0a, 2.f * kL2E, -(rmla + cml0))) * rmula) * cmul0;
+      if (okb) ai0[(size_t)t.b * R + rb] = (ex2_approx(fmaf(c0b, 2.f * kL2E, -(rmlb + cml0))) * rmulb) * cmul0;
+    }
+  };
+  RowPair va, vb;
+  float a0a = 0.f, a0b = 0.f, b0a = 0.f, b0b = 0.f;
+  ld(va, a0a, a0b, 0);
+#pragma unroll 1
+  for (int p = 0; p < F2_PAIRS; p += 2) {
+    ld(vb, b0a, b0b, p + 1);
+    comp(va, a0a, a0b, p);
+    if (p + 2 < F2_PAIRS) ld(va, a0a, a0b, p + 2);
+    comp(vb, b0a, b0b, p + 1);
+  }
+}
+
+__global__ void __launch_bounds__(F2_THREADS, 2)
+k_fine_labels(const float* __restrict__ atten, int R, int C, int nstrip, int nrt, const float* __restrict__ rml,
+              const float* __restrict__ rmul, const float* __restrict__ cml, const float* __restrict__ cmul,
+              float* __restrict__ rowpm, float* __restrict__ colpm, float* __restrict__ ai0,
+              float* __restrict__ a0j) {
+  __shared__ float s_cm[F2_WARPS][F2_TC];
+  const F2Tile t = f2_tile(R, C);
+  const float* A = atten + (size_t)t.b * R * C;
+  ColConst2 kc;
+  load_col_consts2(kc, t, C, cml, cmul, nullptr);
+  float cmx[F2_CPT];
+#pragma unroll
+  for (int k = 0; k < F2_CPT; ++k) cmx[k] = -INFINITY;
+  if (t.rt == 0 && t.warp == 0) {  // S[0][j] for this strip's columns (the background row is in no maximum)
+    RowPair v;
+    load_pair<true>(A + t.j0, 0, t.ncl, true, false, v);
+    const float rml0 = rml[(size_t)t.b * R], rmul0 = rmul[(size_t)t.b * R];
+    unsigned long long e[F2_CPT / 2];
+    row_exps(v.a, -rml0, kc, e);
+    const unsigned long long M0 = pack2(rmul0, rmul0);
+#pragma unroll
+    for (int kk = 0; kk < F2_CPT / 2; ++kk) {
+      float a0, a1;
+      unpack2(mul2(mul2(e[kk], M0), kc.cmul[kk]), a0, a1);
+      if (32 * (2 * kk) < t.ncl) a0j[(size_t)t.b * C + t.j0 + 32 * (2 * kk)] = a0;
+      if (32 * (2 * kk + 1) < t.ncl) a0j[(size_t)t.b * C + t.j0 + 32 * (2 * kk + 1)] = a1;
+    }
+  }
+  const float cml0 = cml[(size_t)t.b * C], cmul0 = cmul[(size_t)t.b * C];
+  if (t.cs == 0) {
+    if (t.full) labels_body<false, true>(A, R, C, nstrip, t, kc, cml0, cmul0, rml, rmul, rowpm, ai0, cmx);
+    else labels_body<true, true>(A, R, C, nstrip, t, kc, cml0, cmul0, rml, rmul, rowpm, ai0, cmx);
+  } else {
+    if (t.full) labels_body<false, false>(A, R, C, nstrip, t, kc, cml0, cmul0, rml, rmul, rowpm, ai0, cmx);
+    else labels_body<true, false>(A, R, C, nstrip, t, kc, cml0, cmul0, rml, rmul, rowpm, ai0, cmx);
+  }
+#pragma unroll
+  for (int k = 0; k < F2_CPT; ++k) s_cm[t.warp][t.lane + 32 * k] = cmx[k];
+  __syncthreads();
+  const int c = threadIdx.x;
+  const int gj = 1 + t.cs * F2_TC + c;
+  if (gj < C) {
+    float m = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < F2_WARPS; ++w) m = fmaxf(m, s_cm[w][c]);
+    colpm[((size_t)t.b * C + gj) * nrt + t.rt] = m;
+  }
+}
+
+// ------------------------------------------------------------------ pass 3: masked soft correspondences
+//   per row i >= 1:  rmul_i * sum_{j>=1} e_ij (cmul_j w2_j) {x_j, y_j, z_j, 1}      (model_utils.py:549-555)
+template <bool CHECK>
+__device__ __forceinline__ void rows_body(const float* __restrict__ A, int R, int C, int nstrip, const F2Tile& t,
+                                          const ColConst2& kc, const unsigned long long (&px)[F2_CPT / 2],
+                                          const unsigned long long (&py)[F2_CPT / 2],
+                                          const unsigned long long (&pz)[F2_CPT / 2], const float* __restrict__ rml,
+                                          const float* __restrict__ rmul, float4* __restrict__ rowpart4) {
+  const size_t pitch8 = (size_t)8 * C;
+  const int N1 = R - 1;
+  auto ld = [&](RowPair& v, int p) {
+    const int ra = t.i0 + 16 * p;
+    load_pair<CHECK>(A + (size_t)ra * C + t.j0, pitch8, t.ncl, !CHECK || ra < R, !CHECK || ra + 8 < R, v);
+  };
+  auto comp = [&](const RowPair& cur, int p) {
+    const int ra = t.i0 + 16 * p, rb = ra + 8;
+    if (CHECK && ra >= R) return;
+    const bool okb = !CHECK || rb < R;
+    const size_t oa = (size_t)t.b * R + ra, ob = (size_t)t.b * R + (okb ? rb : ra);
+    const float rmla = rml[oa], rmula = rmul[oa], rmlb = rml[ob], rmulb = rmul[ob];
+    unsigned long long ea[F2_CPT / 2], eb[F2_CPT / 2];
+    row_exps(cur.a, -rmla, kc, ea);
+    row_exps(cur.b, -rmlb, kc, eb);
+    const unsigned long long Z = pack2(0.f, 0.f);
+    unsigned long long ax = Z, ay = Z, az = Z, aw = Z, bx = Z, by = Z, bz = Z, bw = Z;
+#pragma unroll
+    for (int kk = 0; kk < F2_CPT / 2; ++kk) {
+      const unsigned long long ta = mul2(ea[kk], kc.cmul[kk]), tb = mul2(eb[kk], kc.cmul[kk]);
+      ax = fma2(ta, px[kk], ax); ay = fma2(ta, py[kk], ay); az = fma2(ta, pz[kk], az); aw = add2(aw, ta);
+      bx = fma2(tb, px[kk], bx); by = fma2(tb, py[kk], by); bz = fma2(tb, pz[kk], bz); bw = add2(bw, tb);
+    }
+    float acc[8], u0, u1;
+    unpack2(ax, u0, u1); acc[0] = u0 + u1;
+    unpack2(ay, u0, u1); acc[1] = u0 + u1;
+    unpack2(az, u0, u1); acc[2] = u0 + u1;
+    unpack2(aw, u0, u1); acc[3] = u0 + u1;
+    unpack2(bx, u0, u1); acc[4] = u0 + u1;
+    unpack2(by, u0, u1); acc[5] = u0 + u1;
+    unpack2(bz, u0, u1); acc[6] = u0 + u1;
+    unpack2(bw, u0, u1); acc[7] = u0 + u1;
+    // 8 values across 32 lanes: halving exchanges (4 + 2 + 1 shuffles) then two xor steps;
+    // afterwards lane group (lane >> 2) holds component (lane >> 2): 0..3 = row a {x,y,z,w}, 4..7 = row b
+    {
+      int off = 16;
+#pragma unroll
+      for (int n = 8; n > 1; n >>= 1, off >>= 1) {
+        const bool upper = (t.lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) {
+          const float send = upper ? acc[i] : acc[i + n / 2];
+          const float keep = upper ? acc[i + n / 2] : acc[i];
+          acc[i] = keep + __shfl_xor_sync(kFull, send, off);
+        }
+      }
+      acc[0] += __shfl_xor_sync(kFull, acc[0], 2);
+      acc[0] += __shfl_xor_sync(kFull, acc[0], 1);
+    }
+    if ((t.lane & 3) == 0) {
+      const int cmp = t.lane >> 2;
+      const bool isb = cmp >= 4;
+      if (!isb || okb) {
+        float* dst = reinterpret_cast<float*>(rowpart4 + ((size_t)t.b * N1 + (isb ? rb : ra) - 1) * nstrip + t.cs) +
+                     (cmp & 3);
+        *dst = acc[0] * (isb ? rmulb : rmula);
+      }
+    }
+  };
+  RowPair va, vb;
+  ld(va, 0);
+#pragma unroll 1
+  for (int p = 0; p < F2_PAIRS; p += 2) {
+    ld(vb, p + 1);
+    comp(va, p);
+    if (p + 2 < F2_PAIRS) ld(va, p + 2);
+    comp(vb, p + 1);
+  }
+}
+
+__global__ void __launch_bounds__(F2_THREADS, 2)
+k_fine_rows(const float* __restrict__ atten, int R, int C, int nstrip, const float* __restrict__ rml,
+            const float* __restrict__ rmul, const float* __restrict__ cml, const float* __restrict__ cmul,
+            const float* __restrict__ w2, const float* __restrict__ pts2, float4* __restrict__ rowpart4) {
+  const F2Tile t = f2_tile(R, C);
+  const float* A = atten + (size_t)t.b * R * C;
+  ColConst2 kc;
+  load_col_consts2(kc, t, C, cml, cmul, w2);
+  unsigned long long px[F2_CPT / 2], py[F2_CPT / 2], pz[F2_CPT / 2];
+#pragma unroll
+  for (int kk = 0; kk < F2_CPT / 2; ++kk) {
+    float x[2], y[2], z[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int k = 2 * kk + h;
+      const bool ok = 32 * k < t.ncl;
+      const float* p = pts2 + ((size_t)t.b * (C - 1) + (ok ? t.j0 + 32 * k - 1 : 0)) * 3;
+      x[h] = p[0]; y[h] = p[1]; z[h] = p[2];
+    }
+    px[kk] = pack2(x[0], x[1]); py[kk] = pack2(y[0], y[1]); pz[kk] = pack2(z[0], z[1]);
+  }
+  if (t.full) rows_body<false>(A, R, C, nstrip, t, kc, px, py, pz, rml, rmul, rowpart4);
+  else rows_body<true>(A, R, C, nstrip, t, kc, px, py, pz, rml, rmul, rowpart4);
+}
+
+// ------------------------------------------------------------------ host side
+FineGeom2 fine_geom2(int R, int C) {
+  FineGeom2 g;
+  g.nstrip = ceil_div(C - 1, F2_TC);
+  g.nrt = ceil_div(R - 1, F2_RT);
+  return g;
+}
+
+int run_fine_labels2(const float* atten, const float* score1, int ld1, const float* score2, int ld2, int b,
+                     const AssignGeom& g, const AssignWs& ws, float* w1, float* w2, cudaStream_t st) {
+  const FineGeom2 f = fine_geom2(g.R, g.C);
+  const dim3 grid(f.nstrip, f.nrt, b);
+  const dim3 mg(ceil_div(g.R + g.C, 256), b);
+  UPK_CUDA_TRY(cudaMemsetAsync(ws.flags, 0, sizeof(int) * (size_t)b, st));
+  k_fine_stats<<<grid, F2_THREADS, 0, st>>>(atten, g.R, g.C, f.nstrip, f.nrt, ws.rowpart, ws.colpart, ws.flags);
+  k_fine_stats_merge<<<mg, 256, 0, st>>>(ws.rowpart, ws.colpart, g.R, g.C, f.nstrip, f.nrt, score1, ld1, score2,
+                                         ld2, ws.flags, ws.rmax, ws.rsum, ws.cmax, ws.csum);
+  count_launch(2);
+  // exact redo of flagged instances (early exit otherwise), then into the (rml, rmul, cml, cmul) form
+  int rc = run_exact_stats_flagged(atten, b, g, ws, st);
+  if (rc) return rc;
+  k_fine_stats_convert<<<mg, 256, 0, st>>>(g.R, g.C, score1, ld1, score2, ld2, ws.flags, ws.rmax, ws.rsum, ws.cmax,
+                                           ws.csum);
+  k_fine_labels<<<grid, F2_THREADS, 0, st>>>(atten, g.R, g.C, f.nstrip, f.nrt, ws.rmax, ws.rsum, ws.cmax, ws.csum,
+                                             ws.rowpm, ws.colpm, ws.ai0, ws.a0j);
+  count_launch(2);
+  return launch_labels_merge(ws.rowpm, ws.colpm, ws.ai0, ws.a0j, b, g.R, g.C, f.nrt, f.nstrip, w1, w2, st);
+}
+
+int run_fine_rows2(const float* atten, int b, const AssignGeom& g, const AssignWs& ws, const float* w1,
+                   const float* w2, const float* pts2, float4* rowpart4, float* soft, float* asum, cudaStream_t st) {
+  const FineGeom2 f = fine_geom2(g.R, g.C);
+  const dim3 grid(f.nstrip, f.nrt, b);
+  k_fine_rows<<<grid, F2_THREADS, 0, st>>>(atten, g.R, g.C, f.nstrip, ws.rmax, ws.rsum, ws.cmax, ws.csum, w2, pts2,
+                                           rowpart4);
+  count_launch();
+  return launch_fine_rows_merge(rowpart4, w1, b, g.R - 1, f.nstrip, soft, asum, st);
+}
+
+}  // namespace upk

@@ -42,6 +42,7 @@ struct AssignWs {
   float* colpm;     // [b][C][ntr]  partial col max of A over rows >= 1
   float* ai0;       // [b][R]  A[i][0]
   float* a0j;       // [b][C]  A[0][j]
+  int* flags;       // [b]  large geometry: pass 1's single-reference sums were not trustworthy -> exact redo
 };
 void carve_assign(Carver& cv, int b, const AssignGeom& g, AssignWs& ws);
 
@@ -62,6 +63,23 @@ int run_fine_rowsums(const float* atten, const float* score1, int ld1, const flo
                      const AssignGeom& g, const AssignWs& ws, const float* w1, const float* w2,
                      const float* pts2, float4* rowpart4 /*[b][N1][ntc]*/, float* soft, float* asum,
                      cudaStream_t st);
+
+// Large-geometry (fine) streaming passes, assign_fine.cu.  They reuse the AssignWs buffers: rmax/rsum/cmax/csum
+// hold rml (row reference, log2 units) / rmul (score1 / row sum) / cml / cmul there.
+struct FineGeom2 {
+  int nstrip, nrt;  // 256-column strips / 128-row tiles of the main block (background row and column peeled off)
+};
+FineGeom2 fine_geom2(int R, int C);
+int run_fine_labels2(const float* atten, const float* score1, int ld1, const float* score2, int ld2, int b,
+                     const AssignGeom& g, const AssignWs& ws, float* w1, float* w2, cudaStream_t st);
+int run_fine_rows2(const float* atten, int b, const AssignGeom& g, const AssignWs& ws, const float* w1,
+                   const float* w2, const float* pts2, float4* rowpart4, float* soft, float* asum, cudaStream_t st);
+// helpers living in assign.cu
+int run_exact_stats_flagged(const float* atten, int b, const AssignGeom& g, const AssignWs& ws, cudaStream_t st);
+int launch_labels_merge(const float* rowpm, const float* colpm, const float* ai0, const float* a0j, int b, int R,
+                        int C, int ntr, int ntc, float* w1, float* w2, cudaStream_t st);
+int launch_fine_rows_merge(const float4* rowpart4, const float* w1, int b, int n1, int ntc, float* soft,
+                           float* asum, cudaStream_t st);
 
 // tensor-core similarity path (similarity_tc.cu)
 int similarity_mode();  // 3 = 3xTF32 tcgen05 (default), 1 = 1xTF32 tcgen05, 0 = fp32 SIMT
