@@ -30,7 +30,10 @@ def T(a, dev):
 
 @pytest.mark.parametrize("n,m", [(1, 1), (2, 2), (3, 3), (31, 7), (196, 64), (255, 200), (256, 33), (500, 100),
                                  (777, 64), (1024, 128), (2048, 196), (2500, 300), (4096, 50), (5000, 2048),
-                                 (7000, 40), (10000, 30), (14000, 20)])
+                                 (7000, 40), (10000, 30), (14000, 20),
+                                 # long runs -> the box-pruned kernel (m >= 512, 2048 <= n <= 8192)
+                                 (2048, 2048), (2049, 512), (3000, 600), (4096, 1000), (5120, 700), (8000, 513),
+                                 (8192, 600), (8193, 600)])
 def test_fps_matches_oracle(cuda, n, m):
     xyz = batch_clouds(n * 7 + m, 3, n)
     got = _ext().furthest_point_sampling(T(xyz, cuda), m).cpu().numpy()
@@ -43,9 +46,9 @@ def test_fps_ties_match_oracle(cuda, n):
     """Quantised coordinates + duplicated points + more samples than distinct points."""
     xyz = np.round(batch_clouds(n, 2, n) * 4) / 4
     xyz[:, n // 2:] = xyz[:, : n - n // 2]
-    m = min(n, 400)
-    got = _ext().furthest_point_sampling(T(xyz, cuda), m).cpu().numpy()
-    assert np.array_equal(got, O.furthest_point_sampling(xyz, m))
+    for m in (min(n, 400), min(n, 1500)):   # 1500 >= 512: the box-pruned kernel for n >= 2048
+        got = _ext().furthest_point_sampling(T(xyz, cuda), m).cpu().numpy()
+        assert np.array_equal(got, O.furthest_point_sampling(xyz, m))
     z = np.zeros((1, n, 3), np.float32)
     assert (_ext().furthest_point_sampling(T(z, cuda), 9).cpu().numpy() == 0).all()
 
