@@ -7,12 +7,14 @@
 //
 // Here: thread-per-query scan with the query in registers and the cloud broadcast from shared memory
 // (SoA, LDS.128 = 4 points per load, packed f32x2 distance arithmetic, bit-identical to the reference's
-// fma(dz,dz, fma(dx,dx, dy*dy))).  Hits are recorded as BIT MASKS (one 32-point word per register), so
-// the ascending-index order of the reference falls out of the bit order.  Only the OUTER radius is
-// tested in the scan; the inner radius is re-tested on the few outer hits during emission (the same
-// expression on the same operands gives the same bits).  Emission is warp-per-query: popc + warp prefix
-// scan give every hit its slot; rows are completed (first-hit padding / zero rows) and the grouped xyz
-// rows (b,3,m,nsample) are written with coalesced warp stores from the smem copy of the cloud.
+// fma(dz,dz, fma(dx,dx, dy*dy))).  Hits are recorded as BIT MASKS: the sign bit of (d2 - r2) is shifted
+// into a 32-point word (one packed subtract per two points + one funnel shift per point), so the
+// ascending-index order of the reference falls out of the bit order.  Only the OUTER radius is tested in
+// the scan; the inner radius is re-tested on the few outer hits during emission (the same expression on the
+// same operands gives the same bits).  Emission is warp-per-query: popc + one warp prefix scan give every
+// hit its slot.  When the whole cloud fits one tile (n <= 2048: the UNOPose shapes) the row is staged in
+// shared memory, completed (first-hit padding / zero rows) and written together with the grouped xyz rows
+// (b,3,m,nsample) by 128-bit coalesced stores; longer clouds accumulate their rows in global memory.
 #include "common.cuh"
 #include "launch_count.h"
 #include "../../include/unopose_b200.h"
@@ -26,7 +28,8 @@ constexpr int BG_PARTS = BG_WARPS / 2;     // the tile's points are split over 4
 constexpr int BG_TILE = 2048;              // points per smem tile
 constexpr int BG_WORDS = BG_TILE / 32;     // 64 mask words per query per tile
 constexpr int BG_WPP = BG_WORDS / BG_PARTS;  // 16 words per thread per tile
-constexpr int BG_MPITCH = BG_WORDS + 1;    // +1: a warp stores one word index for 32 queries -> no bank conflicts
+constexpr int BG_MPITCH = BG_WORDS + 2;    // even (64-bit reads of word pairs), 2-way conflicts on the 16 stores only
+constexpr int BG_ROWCAP = 512;             // staged path: nsample0 + nsample1 <= 512 ints per warp
 
 struct BgScale {
   float r2;      // radius*radius (fp32 product, ball_query_gpu.cu:27)
@@ -39,10 +42,12 @@ __device__ __forceinline__ float bg_d2(float px, float py, float pz, float nqx, 
   return sqdist_ref(px + nqx, py + nqy, pz + nqz);
 }
 
-// 32 points -> hit mask against r2 (packed arithmetic, two points per instruction)
+// 32 points -> hit mask against r2.  d2 < r2  <=>  sign(d2 - r2) for every finite or infinite d2 (round to
+// nearest never turns a non-zero difference into zero, x - x = +0, NaN results are the canonical positive NaN).
 __device__ __forceinline__ unsigned bg_scan_word(const float* __restrict__ sx, const float* __restrict__ sy,
                                                  const float* __restrict__ sz, int k0, unsigned long long nqx,
-                                                 unsigned long long nqy, unsigned long long nqz, float r2) {
+                                                 unsigned long long nqy, unsigned long long nqz,
+                                                 unsigned long long nr2) {
   unsigned mask = 0u;
 #pragma unroll
   for (int g = 0; g < 8; ++g) {
@@ -50,18 +55,15 @@ __device__ __forceinline__ unsigned bg_scan_word(const float* __restrict__ sx, c
     const ulonglong2 Y = *reinterpret_cast<const ulonglong2*>(sy + k0 + 4 * g);
     const ulonglong2 Z = *reinterpret_cast<const ulonglong2*>(sz + k0 + 4 * g);
     unsigned long long dx = add2(X.x, nqx), dy = add2(Y.x, nqy), dz = add2(Z.x, nqz);
-    unsigned long long da = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
+    const unsigned long long sa = add2(fma2(dz, dz, fma2(dx, dx, mul2(dy, dy))), nr2);
     dx = add2(X.y, nqx); dy = add2(Y.y, nqy); dz = add2(Z.y, nqz);
-    unsigned long long db = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
-    float d0, d1, d2, d3;
-    unpack2(da, d0, d1);
-    unpack2(db, d2, d3);
-    if (d0 < r2) mask |= 1u << (4 * g);
-    if (d1 < r2) mask |= 1u << (4 * g + 1);
-    if (d2 < r2) mask |= 1u << (4 * g + 2);
-    if (d3 < r2) mask |= 1u << (4 * g + 3);
+    const unsigned long long sb = add2(fma2(dz, dz, fma2(dx, dx, mul2(dy, dy))), nr2);
+    mask = __funnelshift_l((unsigned)sa, mask, 1);
+    mask = __funnelshift_l((unsigned)(sa >> 32), mask, 1);
+    mask = __funnelshift_l((unsigned)sb, mask, 1);
+    mask = __funnelshift_l((unsigned)(sb >> 32), mask, 1);
   }
-  return mask;
+  return __brev(mask);  // point k0 + i -> bit i
 }
 
 // inclusive warp scan of a packed pair of 16-bit counters
@@ -74,15 +76,47 @@ __device__ __forceinline__ unsigned bg_incl_scan(unsigned v, int lane) {
   return v;
 }
 
-template <bool TWO>
+// Stage one tile of the cloud (AoS global -> SoA shared), sentinel-pad the rest of the tile.
+__device__ __forceinline__ void bg_load_tile(const float* __restrict__ xyz, int t0, int tn, float* sx, float* sy,
+                                             float* sz) {
+  const int tid = threadIdx.x;
+  const float* src = xyz + (size_t)t0 * 3;
+  int done = 0;
+  if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    const int nv = (tn * 3) >> 2;
+    for (int q = tid; q < nv; q += BG_THREADS) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(src) + q);
+      const float vv[4] = {v.x, v.y, v.z, v.w};
+      const int e0 = 4 * q, k = e0 / 3, c = e0 - 3 * k;  // element e0 + i: point k + (c + i) / 3, component (c + i) % 3
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int ci = c + i;
+        const int wrap = (ci >= 3 ? 1 : 0) + (ci >= 6 ? 1 : 0);
+        const int cc = ci - 3 * wrap;
+        (cc == 0 ? sx : (cc == 1 ? sy : sz))[k + wrap] = vv[i];
+      }
+    }
+    done = 4 * nv;
+  }
+  for (int e = done + tid; e < tn * 3; e += BG_THREADS) {
+    const int k = e / 3, c = e - 3 * k;
+    (c == 0 ? sx : (c == 1 ? sy : sz))[k] = src[e];
+  }
+  for (int k = tn + tid; k < BG_TILE; k += BG_THREADS) sx[k] = sy[k] = sz[k] = 1e30f;  // never hit
+}
+
+// STAGED: the cloud is a single tile; rows live in shared memory until they are complete.
+template <bool TWO, bool STAGED>
 __global__ void __launch_bounds__(BG_THREADS)
 ball_group_kernel(const float* __restrict__ new_xyz, const float* __restrict__ xyz, int n, int m,
                   BgScale in, BgScale out) {
   // `out` = the scan radius (the larger one when TWO); `in` = the inner radius, a subset of `out`'s hits
-  __shared__ __align__(16) float sx[BG_TILE];
-  __shared__ __align__(16) float sy[BG_TILE];
-  __shared__ __align__(16) float sz[BG_TILE];
-  __shared__ unsigned s_mask[BG_QPB * BG_MPITCH];
+  extern __shared__ __align__(16) unsigned char bg_smem[];
+  float* sx = reinterpret_cast<float*>(bg_smem);
+  float* sy = sx + BG_TILE;
+  float* sz = sy + BG_TILE;
+  unsigned* s_mask = reinterpret_cast<unsigned*>(sz + BG_TILE);          // BG_QPB * BG_MPITCH
+  int* s_rows = reinterpret_cast<int*>(s_mask + BG_QPB * BG_MPITCH);     // STAGED: BG_WARPS * BG_ROWCAP
   __shared__ int s_cnt[2][BG_QPB], s_first[2][BG_QPB];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.y;
@@ -92,7 +126,7 @@ ball_group_kernel(const float* __restrict__ new_xyz, const float* __restrict__ x
   int* const idx_o = out.idx + (size_t)b * m * out.ns;
   int* const idx_i = TWO ? in.idx + (size_t)b * m * in.ns : nullptr;
 
-  if (tid < BG_QPB) {
+  if (!STAGED && tid < BG_QPB) {
     s_cnt[0][tid] = s_cnt[1][tid] = 0;
     s_first[0][tid] = s_first[1][tid] = 0;
   }
@@ -102,16 +136,12 @@ ball_group_kernel(const float* __restrict__ new_xyz, const float* __restrict__ x
   const unsigned long long nqx = pack2(-new_xyz[sj * 3 + 0], -new_xyz[sj * 3 + 0]);
   const unsigned long long nqy = pack2(-new_xyz[sj * 3 + 1], -new_xyz[sj * 3 + 1]);
   const unsigned long long nqz = pack2(-new_xyz[sj * 3 + 2], -new_xyz[sj * 3 + 2]);
+  const unsigned long long nr2 = pack2(-out.r2, -out.r2);
 
   for (int t0 = 0; t0 < n; t0 += BG_TILE) {
     const int tn = min(BG_TILE, n - t0);
     __syncthreads();  // previous tile fully consumed (and the counters initialised)
-    for (int i = tid; i < tn * 3; i += BG_THREADS) {
-      const float v = xyz[(size_t)t0 * 3 + i];
-      const int k = i / 3, c = i - k * 3;
-      (c == 0 ? sx : (c == 1 ? sy : sz))[k] = v;
-    }
-    for (int k = tn + tid; k < BG_TILE; k += BG_THREADS) sx[k] = sy[k] = sz[k] = 1e30f;  // never hit
+    bg_load_tile(xyz, t0, tn, sx, sy, sz);
     __syncthreads();
     // ---- scan: 16 words of 32 points per thread
     const int nwords = (tn + 31) >> 5;
@@ -119,76 +149,126 @@ ball_group_kernel(const float* __restrict__ new_xyz, const float* __restrict__ x
     for (int w = 0; w < BG_WPP; ++w) {
       const int word = part * BG_WPP + w;
       unsigned mask = 0u;
-      if (word < nwords) mask = bg_scan_word(sx, sy, sz, word * 32, nqx, nqy, nqz, out.r2);
+      if (word < nwords) mask = bg_scan_word(sx, sy, sz, word * 32, nqx, nqy, nqz, nr2);
       s_mask[sq * BG_MPITCH + word] = mask;
     }
     __syncthreads();
-    // ---- emission: warp per query
+    // ---- emission: warp per query; lane l owns points [64 l, 64 l + 64) of the tile
     for (int qi = warp; qi < BG_QPB; qi += BG_WARPS) {
       const int j = q0 + qi;
       if (j >= m) break;
-      int cnt_o = s_cnt[0][qi], cnt_i = s_cnt[1][qi];
-      if (cnt_o >= out.ns && (!TWO || cnt_i >= in.ns)) continue;
-      const float qx = -new_xyz[j * 3 + 0], qy = -new_xyz[j * 3 + 1], qz = -new_xyz[j * 3 + 2];
-      int* const row_o = idx_o + (size_t)j * out.ns;
-      int* const row_i = TWO ? idx_i + (size_t)j * in.ns : nullptr;
-#pragma unroll 1
-      for (int half = 0; half < BG_WORDS / 32; ++half) {
-        const unsigned w = s_mask[qi * BG_MPITCH + half * 32 + lane];
-        const unsigned any = __ballot_sync(kFull, w != 0u);
-        if (any == 0u) continue;
-        const int kb = half * 1024 + lane * 32;  // tile-local index of bit 0 of my word
-        unsigned win = 0u;
-        if (TWO) {
-          unsigned u = w;
-          while (u) {
-            const int bit = __ffs(u) - 1;
-            u &= u - 1;
-            const int k = kb + bit;
-            if (bg_d2(sx[k], sy[k], sz[k], qx, qy, qz) < in.r2) win |= 1u << bit;
-          }
-        }
-        const unsigned v = (unsigned)__popc(w) | ((unsigned)__popc(win) << 16);
-        const unsigned incl = bg_incl_scan(v, lane);
-        const unsigned tot = __shfl_sync(kFull, incl, 31);
-        const unsigned excl = incl - v;
-        if (cnt_o == 0) {  // first hit overall = lowest bit of the lowest lane that has one
-          const int src = __ffs(any) - 1;
-          const int f = __shfl_sync(kFull, t0 + kb + __ffs(w) - 1, src);
-          if (lane == 0) s_first[0][qi] = f;
-        }
-        if (TWO && cnt_i == 0) {
-          const unsigned anyi = __ballot_sync(kFull, win != 0u);
-          if (anyi) {
-            const int src = __ffs(anyi) - 1;
-            const int f = __shfl_sync(kFull, t0 + kb + __ffs(win) - 1, src);
-            if (lane == 0) s_first[1][qi] = f;
-          }
-        }
-        int so = cnt_o + (int)(excl & 0xffffu), si = cnt_i + (int)(excl >> 16);
-        unsigned u = w;
+      int cnt_o = 0, cnt_i = 0;
+      if (!STAGED) {
+        cnt_o = s_cnt[0][qi];
+        cnt_i = s_cnt[1][qi];
+        if (cnt_o >= out.ns && (!TWO || cnt_i >= in.ns)) continue;
+      }
+      int* const row_o = STAGED ? s_rows + warp * BG_ROWCAP : idx_o + (size_t)j * out.ns;
+      int* const row_i = STAGED ? row_o + ((out.ns + 3) & ~3) : (TWO ? idx_i + (size_t)j * in.ns : nullptr);
+      const uint2 w2 = *reinterpret_cast<const uint2*>(s_mask + qi * BG_MPITCH + 2 * lane);
+      const int kb = 64 * lane;  // tile-local index of bit 0 of my first word
+      uint2 win = make_uint2(0u, 0u);
+      if (TWO) {
+        const float qx = -new_xyz[j * 3 + 0], qy = -new_xyz[j * 3 + 1], qz = -new_xyz[j * 3 + 2];
+        unsigned u = w2.x;
         while (u) {
           const int bit = __ffs(u) - 1;
           u &= u - 1;
-          if (so < out.ns) row_o[so] = t0 + kb + bit;
+          if (bg_d2(sx[kb + bit], sy[kb + bit], sz[kb + bit], qx, qy, qz) < in.r2) win.x |= 1u << bit;
+        }
+        u = w2.y;
+        while (u) {
+          const int bit = __ffs(u) - 1;
+          u &= u - 1;
+          if (bg_d2(sx[kb + 32 + bit], sy[kb + 32 + bit], sz[kb + 32 + bit], qx, qy, qz) < in.r2) win.y |= 1u << bit;
+        }
+      }
+      const unsigned v = (unsigned)(__popc(w2.x) + __popc(w2.y)) | ((unsigned)(__popc(win.x) + __popc(win.y)) << 16);
+      const unsigned incl = bg_incl_scan(v, lane);
+      const unsigned tot = __shfl_sync(kFull, incl, 31);
+      const unsigned excl = incl - v;
+      int first_o = 0, first_i = 0;
+      if (cnt_o == 0 && (tot & 0xffffu)) {  // first hit overall = lowest bit of the lowest lane that has one
+        const unsigned any = __ballot_sync(kFull, (w2.x | w2.y) != 0u);
+        const int mine = t0 + kb + (w2.x ? __ffs(w2.x) - 1 : 32 + __ffs(w2.y) - 1);
+        first_o = __shfl_sync(kFull, mine, __ffs(any) - 1);
+        if (!STAGED && lane == 0) s_first[0][qi] = first_o;
+      }
+      if (TWO && cnt_i == 0 && (tot >> 16)) {
+        const unsigned any = __ballot_sync(kFull, (win.x | win.y) != 0u);
+        const int mine = t0 + kb + (win.x ? __ffs(win.x) - 1 : 32 + __ffs(win.y) - 1);
+        first_i = __shfl_sync(kFull, mine, __ffs(any) - 1);
+        if (!STAGED && lane == 0) s_first[1][qi] = first_i;
+      }
+      int so = cnt_o + (int)(excl & 0xffffu), si = cnt_i + (int)(excl >> 16);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        unsigned u = h ? w2.y : w2.x;
+        const unsigned ui = h ? win.y : win.x;
+        while (u) {
+          const int bit = __ffs(u) - 1;
+          u &= u - 1;
+          const int k = t0 + kb + 32 * h + bit;
+          if (so < out.ns) row_o[so] = k;
           ++so;
-          if (TWO && ((win >> bit) & 1u)) {
-            if (si < in.ns) row_i[si] = t0 + kb + bit;
+          if (TWO && ((ui >> bit) & 1u)) {
+            if (si < in.ns) row_i[si] = k;
             ++si;
           }
         }
-        cnt_o += (int)(tot & 0xffffu);
-        cnt_i += (int)(tot >> 16);
       }
-      if (lane == 0) {
-        s_cnt[0][qi] = cnt_o;
-        s_cnt[1][qi] = cnt_i;
+      cnt_o += (int)(tot & 0xffffu);
+      cnt_i += (int)(tot >> 16);
+      if (!STAGED) {
+        if (lane == 0) {
+          s_cnt[0][qi] = cnt_o;
+          s_cnt[1][qi] = cnt_i;
+        }
+        continue;
       }
+      // ---- STAGED completion of this query: pad, write idx and the grouped rows with 128-bit stores
+      __syncwarp();
+#pragma unroll 1
+      for (int sc = 0; sc < (TWO ? 2 : 1); ++sc) {
+        const BgScale S = sc == 0 ? out : in;
+        const int* row = sc == 0 ? row_o : row_i;
+        const int cnt = min(sc == 0 ? cnt_o : cnt_i, S.ns);
+        const int fillv = cnt > 0 ? (sc == 0 ? first_o : first_i) : 0;
+        int* const grow = S.idx + ((size_t)b * m + j) * S.ns;
+        float* const g = S.grp ? S.grp + (size_t)b * 3 * m * S.ns + (size_t)j * S.ns : nullptr;
+        const size_t cstride = (size_t)m * S.ns;
+        if ((S.ns & 3) == 0) {  // rows are 16-byte aligned whenever the base pointers are (checked by the launcher)
+          for (int s4 = 4 * lane; s4 < S.ns; s4 += 128) {
+            int4 k4 = *reinterpret_cast<const int4*>(row + s4);
+            if (s4 + 0 >= cnt) k4.x = fillv;
+            if (s4 + 1 >= cnt) k4.y = fillv;
+            if (s4 + 2 >= cnt) k4.z = fillv;
+            if (s4 + 3 >= cnt) k4.w = fillv;
+            __stcs(reinterpret_cast<int4*>(grow + s4), k4);
+            if (g) {
+              __stcs(reinterpret_cast<float4*>(g + s4), make_float4(sx[k4.x], sx[k4.y], sx[k4.z], sx[k4.w]));
+              __stcs(reinterpret_cast<float4*>(g + cstride + s4), make_float4(sy[k4.x], sy[k4.y], sy[k4.z], sy[k4.w]));
+              __stcs(reinterpret_cast<float4*>(g + 2 * cstride + s4), make_float4(sz[k4.x], sz[k4.y], sz[k4.z], sz[k4.w]));
+            }
+          }
+        } else {
+          for (int s = lane; s < S.ns; s += 32) {
+            const int k = s < cnt ? row[s] : fillv;
+            grow[s] = k;
+            if (g) {
+              g[s] = sx[k];
+              g[cstride + s] = sy[k];
+              g[2 * cstride + s] = sz[k];
+            }
+          }
+        }
+      }
+      __syncwarp();  // the row buffer is reused by this warp's next query
     }
   }
+  if (STAGED) return;
   __syncthreads();  // every row's hits are in global memory (same-CTA visibility), counters final
   // ---- completion: pad the rows with the first hit (zero rows when no hit) + grouped xyz
-  const bool tile_resident = n <= BG_TILE;  // the smem tile still holds the whole cloud
 #pragma unroll 1
   for (int sc = 0; sc < (TWO ? 2 : 1); ++sc) {
     const BgScale S = sc == 0 ? out : in;
@@ -206,17 +286,30 @@ ball_group_kernel(const float* __restrict__ new_xyz, const float* __restrict__ x
         if (s < cnt) k = row[s];
         else row[s] = fillv;
         if (g) {
-          float x, y, z;
-          if (tile_resident) { x = sx[k]; y = sy[k]; z = sz[k]; }
-          else { x = __ldg(xyz + k * 3 + 0); y = __ldg(xyz + k * 3 + 1); z = __ldg(xyz + k * 3 + 2); }
           float* o = g + (size_t)j * S.ns + s;
-          __stcs(o, x);
-          __stcs(o + cstride, y);
-          __stcs(o + 2 * cstride, z);
+          __stcs(o, __ldg(xyz + k * 3 + 0));
+          __stcs(o + cstride, __ldg(xyz + k * 3 + 1));
+          __stcs(o + 2 * cstride, __ldg(xyz + k * 3 + 2));
         }
       }
     }
   }
+}
+
+constexpr size_t BG_SMEM_BASE = (size_t)3 * BG_TILE * sizeof(float) + (size_t)BG_QPB * BG_MPITCH * sizeof(unsigned);
+constexpr size_t BG_SMEM_STAGED = BG_SMEM_BASE + (size_t)BG_WARPS * BG_ROWCAP * sizeof(int);
+
+template <bool TWO, bool STAGED>
+static int launch_ball_group(const float* new_xyz, const float* xyz, int b, int n, int m, const BgScale& in,
+                             const BgScale& out, cudaStream_t st) {
+  auto kern = ball_group_kernel<TWO, STAGED>;
+  const size_t smem = STAGED ? BG_SMEM_STAGED : BG_SMEM_BASE;
+  if (smem > 47 * 1024)
+    UPK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(ceil_div(m, BG_QPB), b);
+  kern<<<grid, BG_THREADS, smem, st>>>(new_xyz, xyz, n, m, in, out);
+  count_launch();
+  UPK_RETURN_LAST_ERROR();
 }
 
 }  // namespace upk
@@ -237,17 +330,23 @@ int upk_ball_query_group(const float* new_xyz, const float* xyz, int b, int n, i
   cudaStream_t st = (cudaStream_t)stream;
   BgScale s0{radius0 * radius0, nsample0, idx0, grouped0};
   BgScale s1{radius1 * radius1, nsample1, idx1, grouped1};
-  dim3 grid(ceil_div(m, BG_QPB), b);
-  if (nsample0 > 0 && nsample1 > 0) {
+  const bool two = nsample0 > 0 && nsample1 > 0;
+  // shared-memory row staging: one tile, rows fit, and every 128-bit store is aligned
+  auto aligned = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const bool staged = n <= BG_TILE && nsample0 + nsample1 + 3 <= BG_ROWCAP &&
+                      (nsample0 == 0 || (aligned(idx0) && aligned(grouped0))) &&
+                      (nsample1 == 0 || (aligned(idx1) && aligned(grouped1)));
+  if (two) {
     // the scan runs on the larger radius; the other one is a subset of its hits
     const bool swap = s0.r2 > s1.r2;
-    ball_group_kernel<true><<<grid, BG_THREADS, 0, st>>>(new_xyz, xyz, n, m, swap ? s1 : s0, swap ? s0 : s1);
-  } else {
-    const BgScale s = nsample0 > 0 ? s0 : s1;
-    ball_group_kernel<false><<<grid, BG_THREADS, 0, st>>>(new_xyz, xyz, n, m, s, s);
+    const BgScale& in = swap ? s1 : s0;
+    const BgScale& out = swap ? s0 : s1;
+    return staged ? launch_ball_group<true, true>(new_xyz, xyz, b, n, m, in, out, st)
+                  : launch_ball_group<true, false>(new_xyz, xyz, b, n, m, in, out, st);
   }
-  count_launch();
-  UPK_RETURN_LAST_ERROR();
+  const BgScale& s = nsample0 > 0 ? s0 : s1;
+  return staged ? launch_ball_group<false, true>(new_xyz, xyz, b, n, m, s, s, st)
+                : launch_ball_group<false, false>(new_xyz, xyz, b, n, m, s, s, st);
 }
 
 }  // extern "C"
