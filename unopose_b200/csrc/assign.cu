@@ -105,9 +105,8 @@ k_stats_tile(const float* __restrict__ atten, int R, int C, int ntr, int ntc,
 __global__ void __launch_bounds__(256)
 k_stats_merge(const float2* __restrict__ rowpart, const float2* __restrict__ colpart, int R, int C,
               int ntr, int ntc, float* __restrict__ rmax, float* __restrict__ rsum,
-              float* __restrict__ cmax, float* __restrict__ csum, const int* __restrict__ only_flagged) {
+              float* __restrict__ cmax, float* __restrict__ csum) {
   const int b = blockIdx.y;
-  if (only_flagged && !only_flagged[b]) return;
   const int i = blockIdx.x * 256 + threadIdx.x;
   const float2* p;
   int n;
@@ -411,132 +410,6 @@ k_fine_rows_merge(const float4* __restrict__ rowpart4, const float* __restrict__
   asum[(size_t)b * n1 + i] = sw;
 }
 
-// ====================================================================================
-// Register-streaming variants for the LARGE geometry (fine stage, 2049 x 2049 per instance).
-// The tile kernels above stage a tile in shared memory and spend ~60 issue slots per element
-// (ncu: issue-bound at 12-15 % of HBM bandwidth).  Here a CTA of 8 warps owns a 64-row x
-// 256-column tile; a warp streams whole 256-column row segments straight from global memory
-// into registers (lane l owns columns l, l+32, ..., l+224: every load instruction is one
-// coalesced 128-byte line), two rows (16 independent loads per thread) in flight.  Per-column
-// constants live in registers for the whole tile, per-row constants are two broadcast loads.
-// Row results need one warp reduction per row, column results one shared-memory combine per
-// tile.  ~10-15 issue slots per element, so the passes become HBM-bound.
-// Same partial-buffer layout as the tile kernels (TR = 64, TC = 256), same merge kernels.
-// ====================================================================================
-constexpr int ST_TR = 64, ST_TC = 256, ST_CPT = 8, ST_WARPS = 8;
-constexpr float kLog2e = 1.4426950408889634f;
-
-__device__ __forceinline__ float ex2_fast(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-// Butterfly reduction of N (power of two) per-lane values across the warp in log2(N) "halving" steps
-// (each step exchanges half of the values) + the remaining xor steps on one value: N=8 needs
-// 4+2+1+1+1 = 9 shuffles instead of 40.  On return v[0] of lane l holds the total of value index
-// l >> (5 - log2 N), identical in all lanes of that group.
-template <int N, class Op>
-__device__ __forceinline__ void warp_reduce_multi(float (&v)[N], Op op) {
-  const int lane = threadIdx.x & 31;
-  int offset = 16;
-#pragma unroll
-  for (int n = N; n > 1; n >>= 1, offset >>= 1) {
-    const bool upper = (lane & offset) != 0;
-#pragma unroll
-    for (int i = 0; i < n / 2; ++i) {
-      float send = upper ? v[i] : v[i + n / 2];
-      float keep = upper ? v[i + n / 2] : v[i];
-      v[i] = op(keep, __shfl_xor_sync(kFull, send, offset));
-    }
-  }
-#pragma unroll
-  for (; offset > 0; offset >>= 1) v[0] = op(v[0], __shfl_xor_sync(kFull, v[0], offset));
-}
-struct OpAdd { __device__ __forceinline__ float operator()(float a, float b) const { return a + b; } };
-struct OpMax { __device__ __forceinline__ float operator()(float a, float b) const { return fmaxf(a, b); } };
-
-// 8 coalesced loads of one 256-column row segment (lane owns columns lane + 32k).  CHECK = edge tile.
-template <bool CHECK>
-__device__ __forceinline__ void load_row8(const float* __restrict__ rowptr, int ncols_left, bool row_ok, float fill,
-                                          float (&v)[ST_CPT]) {
-#pragma unroll
-  for (int k = 0; k < ST_CPT; ++k) {
-    if (CHECK) v[k] = (row_ok && 32 * k < ncols_left) ? __ldg(rowptr + 32 * k) : fill;
-    else v[k] = __ldg(rowptr + 32 * k);
-  }
-}
-
-// pass 1: (max, sum exp) partials per row (exact two-step per row) and per column (online)
-template <bool CHECK>
-__device__ __forceinline__ void stats_stream_body(const float* __restrict__ A, int R, int C, int ntc, int b, int tc,
-                                                  int r0, int c0, int warp, int lane, float (&cm)[ST_CPT],
-                                                  float (&cs)[ST_CPT], float2* __restrict__ rowpart) {
-  const int ncols_left = C - c0 - lane;
-  for (int rr = warp; rr < ST_TR; rr += 2 * ST_WARPS) {
-    const int ga = r0 + rr, gb = ga + ST_WARPS;
-    if (CHECK && ga >= R) break;
-    const bool hasb = !CHECK || gb < R;
-    float va[ST_CPT], vb[ST_CPT];
-    const float* pa = A + (size_t)ga * C + c0 + lane;
-    load_row8<CHECK>(pa, ncols_left, true, -INFINITY, va);
-    load_row8<CHECK>(pa + (size_t)ST_WARPS * C, ncols_left, hasb, -INFINITY, vb);
-    float mx[2] = {va[0], vb[0]};
-#pragma unroll
-    for (int k = 1; k < ST_CPT; ++k) { mx[0] = fmaxf(mx[0], va[k]); mx[1] = fmaxf(mx[1], vb[k]); }
-    warp_reduce_multi<2>(mx, OpMax());                       // lanes 0-15: row a, lanes 16-31: row b
-    const float ma = __shfl_sync(kFull, mx[0], 0), mb = __shfl_sync(kFull, mx[0], 16);
-    const float mal = ma * kLog2e, mbl = mb * kLog2e;
-    float sm[2] = {0.f, 0.f};
-#pragma unroll
-    for (int k = 0; k < ST_CPT; ++k) {
-      sm[0] += ex2_fast(fmaf(va[k], kLog2e, -mal));
-      sm[1] += ex2_fast(fmaf(vb[k], kLog2e, -mbl));
-      // online column update with both rows
-      float mn = fmaxf(cm[k], fmaxf(va[k], vb[k]));
-      float mnl = mn * kLog2e;
-      cs[k] = cs[k] * ex2_fast(fmaf(cm[k], kLog2e, -mnl)) + ex2_fast(fmaf(va[k], kLog2e, -mnl)) +
-              ex2_fast(fmaf(vb[k], kLog2e, -mnl));
-      cm[k] = mn;
-    }
-    warp_reduce_multi<2>(sm, OpAdd());
-    if (lane == 0) rowpart[((size_t)b * R + ga) * ntc + tc] = make_float2(ma, sm[0]);
-    if (lane == 16 && hasb) rowpart[((size_t)b * R + gb) * ntc + tc] = make_float2(mb, sm[0]);
-  }
-}
-
-__global__ void __launch_bounds__(ST_WARPS * 32)
-k_stats_stream(const float* __restrict__ atten, int R, int C, int ntr, int ntc,
-               float2* __restrict__ rowpart, float2* __restrict__ colpart, const int* __restrict__ only_flagged) {
-  __shared__ float2 s_col[ST_WARPS][ST_TC];
-  const int b = blockIdx.z, tr = blockIdx.y, tc = blockIdx.x;
-  if (only_flagged && !only_flagged[b]) return;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int r0 = tr * ST_TR, c0 = tc * ST_TC;
-  const float* A = atten + (size_t)b * R * C;
-  float cm[ST_CPT], cs[ST_CPT];
-#pragma unroll
-  for (int k = 0; k < ST_CPT; ++k) { cm[k] = -INFINITY; cs[k] = 0.f; }
-  if (r0 + ST_TR <= R && c0 + ST_TC <= C) stats_stream_body<false>(A, R, C, ntc, b, tc, r0, c0, warp, lane, cm, cs, rowpart);
-  else stats_stream_body<true>(A, R, C, ntc, b, tc, r0, c0, warp, lane, cm, cs, rowpart);
-#pragma unroll
-  for (int k = 0; k < ST_CPT; ++k) s_col[warp][lane + 32 * k] = make_float2(cm[k], cs[k]);
-  __syncthreads();
-  const int c = threadIdx.x;
-  if (c0 + c < C) {
-    float m = -INFINITY;
-#pragma unroll
-    for (int w = 0; w < ST_WARPS; ++w) m = fmaxf(m, s_col[w][c].x);
-    float sum = 0.f;
-#pragma unroll
-    for (int w = 0; w < ST_WARPS; ++w) {
-      float2 p = s_col[w][c];
-      sum += p.x == -INFINITY ? 0.f : p.y * ex2_fast((p.x - m) * kLog2e);
-    }
-    colpart[((size_t)b * C + c0 + c) * ntr + tr] = make_float2(m, sum);
-  }
-}
-
 // ------------------------------------------------------------------ host launchers
 template <int TR, int TC>
 static int stats_labels_t(const float* atten, const float* score1, int ld1, const float* score2, int ld2,
@@ -553,7 +426,7 @@ static int stats_labels_t(const float* atten, const float* score1, int ld1, cons
   k1<<<grid, AT, smem, st>>>(atten, g.R, g.C, g.ntr, g.ntc, ws.rowpart, ws.colpart);
   dim3 mg(ceil_div(g.R + g.C, 256), b);
   k_stats_merge<<<mg, 256, 0, st>>>(ws.rowpart, ws.colpart, g.R, g.C, g.ntr, g.ntc, ws.rmax, ws.rsum,
-                                    ws.cmax, ws.csum, nullptr);
+                                    ws.cmax, ws.csum);
   k2<<<grid, AT, smem, st>>>(atten, g.R, g.C, g.ntr, g.ntc, ws.rmax, ws.rsum, ws.cmax, ws.csum, score1,
                              ld1, score2, ld2, ws.rowpm, ws.colpm, ws.ai0, ws.a0j);
   k_labels_merge<<<mg, 256, 0, st>>>(ws.rowpm, ws.colpm, ws.ai0, ws.a0j, g.R, g.C, g.ntr, g.ntc, w1, w2);
@@ -567,18 +440,6 @@ int run_assignment_labels(const float* atten, const float* score1, int ld1, cons
   if (g.TR == 32) return stats_labels_t<32, 128>(atten, score1, ld1, score2, ld2, b, g, ws, w1, w2, st);
   // large geometry: the streaming passes of assign_fine.cu
   return run_fine_labels2(atten, score1, ld1, score2, ld2, b, g, ws, w1, w2, st);
-}
-
-// Exact (max-subtracting) statistics for the instances flagged by the single-reference pass of assign_fine.cu;
-// natural-log maxima and sums land in ws.{rmax,rsum,cmax,csum}.  Unflagged instances exit immediately.
-int run_exact_stats_flagged(const float* atten, int b, const AssignGeom& g, const AssignWs& ws, cudaStream_t st) {
-  dim3 grid(g.ntc, g.ntr, b);
-  dim3 mg(ceil_div(g.R + g.C, 256), b);
-  k_stats_stream<<<grid, ST_WARPS * 32, 0, st>>>(atten, g.R, g.C, g.ntr, g.ntc, ws.rowpart, ws.colpart, ws.flags);
-  k_stats_merge<<<mg, 256, 0, st>>>(ws.rowpart, ws.colpart, g.R, g.C, g.ntr, g.ntc, ws.rmax, ws.rsum, ws.cmax,
-                                    ws.csum, ws.flags);
-  count_launch(2);
-  UPK_RETURN_LAST_ERROR();
 }
 
 int launch_labels_merge(const float* rowpm, const float* colpm, const float* ai0, const float* a0j, int b, int R,

@@ -22,7 +22,7 @@
 // row sum AND the column sum (one MUFU per logit).  g starts 8 octaves above the first row pair's
 // maximum and is raised (column sums rescaled) if a later partial sum exceeds 2^20.  Partial sums that
 // come out below 2^-80 or non-finite (logit range > ~50: never for cosine/temperature logits) raise a
-// per-instance flag and the exact max-subtracting kernels of assign.cu redo that instance.
+// per-instance flag; the merge kernel then recomputes that instance's statistics exactly (max-subtracting).
 #include <math.h>
 
 #include "common.cuh"
@@ -274,59 +274,45 @@ k_fine_stats(const float* __restrict__ atten, int R, int C, int nstrip, int nrt,
 }
 
 // rows and columns: total = sum_p s_p 2^(g_p - G);  outputs rml = G (log2 units), rmul = score / total.
-// Instances flagged by pass 1 are skipped here (the exact path fills them in).
+// Instances flagged by pass 1 (logit range beyond what one reference per warp can carry) are recomputed here
+// exactly, max-subtracting like torch.softmax, one thread per row / column: slow, but only ever taken for
+// pathological logits, and it keeps the common path at one launch.
 __global__ void __launch_bounds__(256)
-k_fine_stats_merge(const float2* __restrict__ rowpart, const float2* __restrict__ colpart, int R, int C, int nstrip,
-                   int nrt, const float* __restrict__ score1, int ld1, const float* __restrict__ score2, int ld2,
+k_fine_stats_merge(const float* __restrict__ atten, const float2* __restrict__ rowpart,
+                   const float2* __restrict__ colpart, int R, int C, int nstrip, int nrt,
+                   const float* __restrict__ score1, int ld1, const float* __restrict__ score2, int ld2,
                    const int* __restrict__ flags, float* __restrict__ rml, float* __restrict__ rmul,
                    float* __restrict__ cml, float* __restrict__ cmul) {
   const int b = blockIdx.y;
-  if (flags[b]) return;
   const int i = blockIdx.x * 256 + threadIdx.x;
-  const float2* p;
-  int n;
-  float *ol, *om, sc = 1.f;
-  if (i < R) {
-    p = rowpart + ((size_t)b * R + i) * nstrip; n = nstrip;
-    ol = rml + (size_t)b * R + i; om = rmul + (size_t)b * R + i;
-    if (i > 0 && score1) sc = score1[(size_t)b * ld1 + i - 1];
-  } else if (i < R + C) {
-    const int c = i - R;
-    p = colpart + ((size_t)b * C + c) * nrt; n = nrt;
-    ol = cml + (size_t)b * C + c; om = cmul + (size_t)b * C + c;
-    if (c > 0 && score2) sc = score2[(size_t)b * ld2 + c - 1];
-  } else {
+  if (i >= R + C) return;
+  const bool is_row = i < R;
+  const int c = i - R;
+  float sc = 1.f;
+  if (is_row) { if (i > 0 && score1) sc = score1[(size_t)b * ld1 + i - 1]; }
+  else if (c > 0 && score2) sc = score2[(size_t)b * ld2 + c - 1];
+  float* const ol = is_row ? rml + (size_t)b * R + i : cml + (size_t)b * C + c;
+  float* const om = is_row ? rmul + (size_t)b * R + i : cmul + (size_t)b * C + c;
+  if (flags[b]) {
+    const float* A = atten + (size_t)b * R * C + (is_row ? (size_t)i * C : (size_t)c);
+    const size_t step = is_row ? 1 : (size_t)C;
+    const int len = is_row ? C : R;
+    float mx = -INFINITY;
+    for (int k = 0; k < len; ++k) mx = fmaxf(mx, A[k * step]);
+    float sum = 0.f;
+    for (int k = 0; k < len; ++k) sum += expf(A[k * step] - mx);
+    *ol = mx * kL2E;
+    *om = sc / sum;
     return;
   }
+  const float2* p = is_row ? rowpart + ((size_t)b * R + i) * nstrip : colpart + ((size_t)b * C + c) * nrt;
+  const int n = is_row ? nstrip : nrt;
   float G = -INFINITY;
   for (int k = 0; k < n; ++k) G = fmaxf(G, p[k].x);
   float s = 0.f;
   for (int k = 0; k < n; ++k) s += p[k].y * exp2f(p[k].x - G);
   *ol = G;
   *om = sc / s;
-}
-
-// exact-path results (natural-log maxima and sums from assign.cu's k_stats_stream / k_stats_merge, written
-// into the same buffers) -> the (rml, rmul, cml, cmul) form, flagged instances only
-__global__ void __launch_bounds__(256)
-k_fine_stats_convert(int R, int C, const float* __restrict__ score1, int ld1, const float* __restrict__ score2,
-                     int ld2, const int* __restrict__ flags, float* __restrict__ rml, float* __restrict__ rmul,
-                     float* __restrict__ cml, float* __restrict__ cmul) {
-  const int b = blockIdx.y;
-  if (!flags[b]) return;
-  const int i = blockIdx.x * 256 + threadIdx.x;
-  if (i < R) {
-    const float sc = (i > 0 && score1) ? score1[(size_t)b * ld1 + i - 1] : 1.f;
-    const size_t o = (size_t)b * R + i;
-    rml[o] = rml[o] * kL2E;
-    rmul[o] = sc / rmul[o];
-  } else if (i < R + C) {
-    const int c = i - R;
-    const float sc = (c > 0 && score2) ? score2[(size_t)b * ld2 + c - 1] : 1.f;
-    const size_t o = (size_t)b * C + c;
-    cml[o] = cml[o] * kL2E;
-    cmul[o] = sc / cmul[o];
-  }
 }
 
 // ------------------------------------------------------------------ passes 2 and 3: shared pieces
@@ -596,17 +582,11 @@ int run_fine_labels2(const float* atten, const float* score1, int ld1, const flo
   const dim3 mg(ceil_div(g.R + g.C, 256), b);
   UPK_CUDA_TRY(cudaMemsetAsync(ws.flags, 0, sizeof(int) * (size_t)b, st));
   k_fine_stats<<<grid, F2_THREADS, 0, st>>>(atten, g.R, g.C, f.nstrip, f.nrt, ws.rowpart, ws.colpart, ws.flags);
-  k_fine_stats_merge<<<mg, 256, 0, st>>>(ws.rowpart, ws.colpart, g.R, g.C, f.nstrip, f.nrt, score1, ld1, score2,
-                                         ld2, ws.flags, ws.rmax, ws.rsum, ws.cmax, ws.csum);
-  count_launch(2);
-  // exact redo of flagged instances (early exit otherwise), then into the (rml, rmul, cml, cmul) form
-  int rc = run_exact_stats_flagged(atten, b, g, ws, st);
-  if (rc) return rc;
-  k_fine_stats_convert<<<mg, 256, 0, st>>>(g.R, g.C, score1, ld1, score2, ld2, ws.flags, ws.rmax, ws.rsum, ws.cmax,
-                                           ws.csum);
+  k_fine_stats_merge<<<mg, 256, 0, st>>>(atten, ws.rowpart, ws.colpart, g.R, g.C, f.nstrip, f.nrt, score1, ld1,
+                                         score2, ld2, ws.flags, ws.rmax, ws.rsum, ws.cmax, ws.csum);
   k_fine_labels<<<grid, F2_THREADS, 0, st>>>(atten, g.R, g.C, f.nstrip, f.nrt, ws.rmax, ws.rsum, ws.cmax, ws.csum,
                                              ws.rowpm, ws.colpm, ws.ai0, ws.a0j);
-  count_launch(2);
+  count_launch(3);
   return launch_labels_merge(ws.rowpm, ws.colpm, ws.ai0, ws.a0j, b, g.R, g.C, f.nrt, f.nstrip, w1, w2, st);
 }
 

@@ -93,12 +93,13 @@ __device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigne
 // away).  Four model points per step: 4 LDS.128 + 10 packed ops + 4 FMNMX.  Returns min_j d_j.
 __device__ __forceinline__ float nn_min_expansion(const float* __restrict__ mx, const float* __restrict__ my,
                                                   const float* __restrict__ mz, const float* __restrict__ mn,
-                                                  int nm_pad, float x0, float x1, float x2, float xx) {
+                                                  int nm_pad, float x0, float x1, float x2, float xx,
+                                                  int first = 0, const int step = 4) {
   const unsigned long long X0 = pack2(x0, x0), X1 = pack2(x1, x1), X2 = pack2(x2, x2);
   const unsigned long long XX = pack2(xx, xx), M2 = pack2(-2.0f, -2.0f);
   float best = INFINITY;
 #pragma unroll 2
-  for (int j = 0; j < nm_pad; j += 4) {
+  for (int j = first; j < nm_pad; j += step) {  // (first, step) = (4 p, 4 P): P threads interleave one cloud
     const ulonglong2 qx = *reinterpret_cast<const ulonglong2*>(mx + j);
     const ulonglong2 qy = *reinterpret_cast<const ulonglong2*>(my + j);
     const ulonglong2 qz = *reinterpret_cast<const ulonglong2*>(mz + j);

@@ -100,17 +100,23 @@ k_weighted_kabsch(const float* __restrict__ src, const float* __restrict__ ref,
 
 // Inlier score (model_utils.py:558-564): X = (pts1 - t) @ R; d_i = NN distance to the model cloud
 // (expansion form, clamp, sqrt); score = sum_fg[d<thr] / (n_fg + 1e-8) * n_fg / N1.
+// FS_PARTS threads share a query point, each scanning interleaved groups of the staged model tile (min via
+// shuffles); the last CTA of an instance (ticket counter) turns the integer counts into the score.
 constexpr int FS_THREADS = 128;
+constexpr int FS_PARTS = 2;
+constexpr int FS_QPB = FS_THREADS / FS_PARTS;   // 64 query points per CTA
 constexpr int FS_TILE = 2048;
 
 __global__ void __launch_bounds__(FS_THREADS)
 k_fine_inliers(const float* __restrict__ pts1, const float* __restrict__ model,
                const float* __restrict__ w1, const float* __restrict__ Rm, const float* __restrict__ tv,
-               int n1, int nm, float thr, int* __restrict__ counters, float* __restrict__ nn_out) {
+               int n1, int nm, float thr, int* __restrict__ counters /* [b][3]: inliers, fg, ticket */,
+               float* __restrict__ nn_out, float* __restrict__ score) {
   __shared__ __align__(16) float sm_model[4 * FS_TILE];
   __shared__ int s_cnt[2];
   const int b = blockIdx.y;
-  const int i = blockIdx.x * FS_THREADS + threadIdx.x;
+  const int part = threadIdx.x & (FS_PARTS - 1);
+  const int i = blockIdx.x * FS_QPB + threadIdx.x / FS_PARTS;
   const float* R = Rm + (size_t)b * 9;
   const float* t = tv + (size_t)b * 3;
   if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
@@ -128,15 +134,18 @@ k_fine_inliers(const float* __restrict__ pts1, const float* __restrict__ model,
   const float* mb = model + (size_t)b * nm * 3;
   for (int j0 = 0; j0 < nm; j0 += FS_TILE) {
     const int tn = min(FS_TILE, nm - j0);
-    const int tn_pad = (tn + 3) & ~3;
+    const int tn_pad = (tn + 4 * FS_PARTS - 1) & ~(4 * FS_PARTS - 1);   // every part scans a multiple of 4 points
     float* mx = sm_model; float* my = mx + FS_TILE; float* mz = my + FS_TILE; float* mn = mz + FS_TILE;
     __syncthreads();
     stage_model_soa(mb + (size_t)j0 * 3, tn, tn_pad, mx, my, mz, mn);
     __syncthreads();
-    if (ok) best = fminf(best, nn_min_expansion(mx, my, mz, mn, tn_pad, x0, x1, x2, xx));
+    // the four threads of a query take interleaved groups of 4 points: their LDS.128 hit distinct banks
+    best = fminf(best, nn_min_expansion(mx, my, mz, mn, tn_pad, x0, x1, x2, xx, 4 * part, 4 * FS_PARTS));
   }
+#pragma unroll
+  for (int o = 1; o < FS_PARTS; o <<= 1) best = fminf(best, __shfl_xor_sync(kFull, best, o));
   int inl = 0, fg = 0;
-  if (ok) {
+  if (ok && part == 0) {
     float dist = sqrtf(fmaxf(best, 0.f));
     if (nn_out) nn_out[(size_t)b * n1 + i] = dist;
     fg = w1[(size_t)b * n1 + i] > 0.f ? 1 : 0;
@@ -149,14 +158,16 @@ k_fine_inliers(const float* __restrict__ pts1, const float* __restrict__ model,
     atomicAdd(&s_cnt[1], fg);
   }
   __syncthreads();
-  if (threadIdx.x < 2) atomicAdd(&counters[b * 2 + threadIdx.x], s_cnt[threadIdx.x]);
-}
-
-__global__ void k_fine_finish(const int* __restrict__ counters, int b, int n1, float* __restrict__ score) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= b) return;
-  float inl = (float)counters[i * 2 + 0], fg = (float)counters[i * 2 + 1];
-  score[i] = (inl / (fg + 1e-8f)) * (fg / (float)n1);
+  if (threadIdx.x == 0) {
+    int* c = counters + b * 3;
+    atomicAdd(c + 0, s_cnt[0]);
+    atomicAdd(c + 1, s_cnt[1]);
+    __threadfence();
+    if (atomicAdd(c + 2, 1) == (int)gridDim.x - 1) {   // every CTA of this instance has contributed
+      const float fi = (float)atomicAdd(c + 0, 0), ff = (float)atomicAdd(c + 1, 0);
+      score[b] = (fi / (ff + 1e-8f)) * (ff / (float)n1);
+    }
+  }
 }
 
 struct FineWs {
@@ -174,7 +185,7 @@ static void carve_fine(Carver& cv, int b, int n1, int n2, const AssignGeom& g, F
   w.rowpart4 = cv.take<float4>((size_t)b * n1 * g.ntc);
   w.soft = cv.take<float>((size_t)b * n1 * 3);
   w.asum = cv.take<float>((size_t)b * n1);
-  w.counters = cv.take<int>((size_t)b * 2);
+  w.counters = cv.take<int>((size_t)b * 3);
 }
 
 }  // namespace upk
@@ -221,12 +232,11 @@ int upk_fine_pose(const float* atten, const float* score1, int score1_ld, const 
                              w.rowpart4, w.soft, w.asum, st)))
     return rc;
   k_weighted_kabsch<<<b, FK_THREADS, 0, st>>>(w.soft, pts1, w.asum, n1, weight_thresh, 1e-5f, R_out, t_out);
-  UPK_CUDA_TRY(cudaMemsetAsync(w.counters, 0, sizeof(int) * 2 * (size_t)b, st));
-  dim3 grid(ceil_div(n1, FS_THREADS), b);
+  UPK_CUDA_TRY(cudaMemsetAsync(w.counters, 0, sizeof(int) * 3 * (size_t)b, st));
+  dim3 grid(ceil_div(n1, FS_QPB), b);
   k_fine_inliers<<<grid, FS_THREADS, 0, st>>>(pts1, model_pts, w.w1, R_out, t_out, n1, n_model, dis_thres,
-                                              w.counters, dbg ? dbg->nn : nullptr);
-  k_fine_finish<<<ceil_div(b, 128), 128, 0, st>>>(w.counters, b, n1, score_out);
-  count_launch(3);
+                                              w.counters, dbg ? dbg->nn : nullptr, score_out);
+  count_launch(2);
   if (dbg) {
     if (dbg->w1) UPK_CUDA_TRY(cudaMemcpyAsync(dbg->w1, w.w1, sizeof(float) * (size_t)b * n1, cudaMemcpyDeviceToDevice, st));
     if (dbg->w2) UPK_CUDA_TRY(cudaMemcpyAsync(dbg->w2, w.w2, sizeof(float) * (size_t)b * n2, cudaMemcpyDeviceToDevice, st));

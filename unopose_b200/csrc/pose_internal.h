@@ -75,7 +75,6 @@ int run_fine_labels2(const float* atten, const float* score1, int ld1, const flo
 int run_fine_rows2(const float* atten, int b, const AssignGeom& g, const AssignWs& ws, const float* w1,
                    const float* w2, const float* pts2, float4* rowpart4, float* soft, float* asum, cudaStream_t st);
 // helpers living in assign.cu
-int run_exact_stats_flagged(const float* atten, int b, const AssignGeom& g, const AssignWs& ws, cudaStream_t st);
 int launch_labels_merge(const float* rowpm, const float* colpm, const float* ai0, const float* a0j, int b, int R,
                         int C, int ntr, int ntc, float* w1, float* w2, cudaStream_t st);
 int launch_fine_rows_merge(const float4* rowpart4, const float* w1, int b, int n1, int ntc, float* soft,

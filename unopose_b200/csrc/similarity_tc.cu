@@ -118,12 +118,37 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
 
 // ---------------------------------------------------------------- operand preparation
 // out_hi = rna_tf32(x / max(||x||, 1e-12)) ; out_lo = x_n - out_hi.   One warp per row.
+// BORDER (the GEMM tiles start at (1,1)): the same warp also produces this row's entry of the peeled
+// background row / column of the output, i.e. its dot product with row 0 of the OTHER operand
+// (`other`, normalised on the fly with the same operations, so the values equal the split ones):
+//   first operand  (is_a = 1): C[b][row][0]      second operand (is_a = 0): C[b][0][row]
+template <int MODE>
 __global__ void __launch_bounds__(256)
-k_normalize_split(const float* __restrict__ x, long long rows, int c, int normalize,
-                  float* __restrict__ hi, float* __restrict__ lo) {
-  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+k_normalize_split(const float* __restrict__ x, int rows_per_batch, int c, int normalize,
+                  float* __restrict__ hi, float* __restrict__ lo,
+                  const float* __restrict__ other, int other_rows_per_batch, int is_a,
+                  float temp, float* __restrict__ C, int M, int N) {
+  extern __shared__ float s_q[];   // BORDER: the normalised row 0 of the other operand (c floats)
+  const int bidx = blockIdx.y;
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
+  if (other) {
+    const float* q = other + (size_t)bidx * other_rows_per_batch * c;
+    float qn = 1.f;
+    if (normalize) {   // every warp computes the same norm (c loads from L1/L2), no extra barrier needed
+      float s = 0.f;
+      for (int k = lane; k < c; k += 32) {
+        float v = q[k];
+        s = fmaf(v, v, s);
+      }
+      s = warp_sum(s);
+      qn = fmaxf(sqrtf(s), 1e-12f);
+    }
+    for (int k = threadIdx.x; k < c; k += 256) s_q[k] = normalize ? q[k] / qn : q[k];
+    __syncthreads();
+  }
+  if (r >= rows_per_batch) return;
+  const size_t row = (size_t)bidx * rows_per_batch + r;
   const float* p = x + row * c;
   float nrm = 1.f;
   if (normalize) {
@@ -135,6 +160,7 @@ k_normalize_split(const float* __restrict__ x, long long rows, int c, int normal
     s = warp_sum(s);
     nrm = fmaxf(sqrtf(s), 1e-12f);
   }
+  float dot = 0.f;
   for (int k = lane; k < c; k += 32) {
     float v = normalize ? p[k] / nrm : p[k];
     uint32_t h;
@@ -142,6 +168,15 @@ k_normalize_split(const float* __restrict__ x, long long rows, int c, int normal
     float vh = __uint_as_float(h);
     hi[row * c + k] = vh;
     lo[row * c + k] = v - vh;
+    if (other) dot = fmaf(v, s_q[k], dot);
+  }
+  if (other) {
+    dot = warp_sum(dot);
+    if (MODE == 1) dot = sqrtf(fmaxf(2.0f - 2.0f * dot, 0.f));
+    if (lane == 0) {
+      float* o = is_a ? C + ((size_t)bidx * M + r) * N : C + (size_t)bidx * M * N + r;
+      if (is_a || r > 0) *o = dot * (1.0f / temp);   // C[0][0] is written once, by the first operand's row 0
+    }
   }
 }
 
@@ -150,11 +185,13 @@ template <int MODE, int NTERMS>  // MODE 0: dot/temp, 1: sqrt(clamp(2-2dot,0))/t
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_similarity_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-                int batch, int M, int N, int K, float temp, float* __restrict__ C) {
+                int batch, int M, int N, int K, float temp, int off, float* __restrict__ C) {
+  // `off` (0 or 1): the tiles cover rows/columns [off, M) x [off, N); with off = 1 the background row 0 and
+  // column 0 are produced by k_similarity_border, so the 2049 x 2049 fine shape is exactly 16 x 8 tiles
   extern __shared__ unsigned char smem_raw[];
   TcSmem& sm = *reinterpret_cast<TcSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int mt = (M + TC_BM - 1) / TC_BM, nt = (N + TC_BN - 1) / TC_BN;
+  const int mt = (M - off + TC_BM - 1) / TC_BM, nt = (N - off + TC_BN - 1) / TC_BN;
   const int total = batch * mt * nt;
   const int kchunks = K / TC_BK;
 
@@ -183,11 +220,11 @@ k_similarity_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         mbar_wait(&sm.empty[s], ph ^ 1);
         if (lane == 0) {
           mbar_expect_tx(&sm.full[s], NTERMS == 3 ? TC_STAGE_BYTES : TC_STAGE_BYTES / 2);
-          tma_load_3d(&map_a_hi, &sm.full[s], sm.a_hi[s], kc * TC_BK, mi * TC_BM, b);
-          tma_load_3d(&map_b_hi, &sm.full[s], sm.b_hi[s], kc * TC_BK, ni * TC_BN, b);
+          tma_load_3d(&map_a_hi, &sm.full[s], sm.a_hi[s], kc * TC_BK, off + mi * TC_BM, b);
+          tma_load_3d(&map_b_hi, &sm.full[s], sm.b_hi[s], kc * TC_BK, off + ni * TC_BN, b);
           if (NTERMS == 3) {
-            tma_load_3d(&map_a_lo, &sm.full[s], sm.a_lo[s], kc * TC_BK, mi * TC_BM, b);
-            tma_load_3d(&map_b_lo, &sm.full[s], sm.b_lo[s], kc * TC_BK, ni * TC_BN, b);
+            tma_load_3d(&map_a_lo, &sm.full[s], sm.a_lo[s], kc * TC_BK, off + mi * TC_BM, b);
+            tma_load_3d(&map_b_lo, &sm.full[s], sm.b_lo[s], kc * TC_BK, off + ni * TC_BN, b);
           }
         }
         __syncwarp();
@@ -247,12 +284,12 @@ k_similarity_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
       const uint32_t acc_ph = (it >> 1) & 1;
       mbar_wait(&sm.tfull[acc], acc_ph);
       tc_fence_after();
-      const int row0 = mi * TC_BM + q * 32;
+      const int row0 = off + mi * TC_BM + q * 32;
       const int nrows = min(32, M - row0);
       float* Cb = C + ((size_t)b * M + row0) * N;
 #pragma unroll 1
       for (int cb = half * 4; cb < half * 4 + 4; ++cb) {
-        const int col0 = ni * TC_BN + cb * 32;
+        const int col0 = off + ni * TC_BN + cb * 32;
         if (col0 >= N) break;
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + acc * TC_BN + cb * 32 + ((uint32_t)(q * 32) << 16), r);
@@ -350,9 +387,20 @@ int run_similarity_tc(const float* f1, const float* f2, int b, int n, int m, int
   float* a_lo = (float*)(w + a);
   float* b_hi = (float*)(w + 2 * a);
   float* b_lo = (float*)(w + 2 * a + bb);
-  long long r1 = (long long)b * n, r2 = (long long)b * m;
-  k_normalize_split<<<(unsigned)((r1 + 7) / 8), 256, 0, st>>>(f1, r1, c, normalize, a_hi, a_lo);
-  k_normalize_split<<<(unsigned)((r2 + 7) / 8), 256, 0, st>>>(f2, r2, c, normalize, b_hi, b_lo);
+  // peel the first row and column off when that saves tiles (2049 = 2048 + the background token); the
+  // peeled entries are produced by the operand-preparation kernels
+  const int tiles0 = ((n + TC_BM - 1) / TC_BM) * ((m + TC_BN - 1) / TC_BN);
+  const int tiles1 = ((n - 1 + TC_BM - 1) / TC_BM) * ((m - 1 + TC_BN - 1) / TC_BN);
+  const int off = (n > 1 && m > 1 && tiles1 < tiles0) ? 1 : 0;
+  const dim3 g1((n + 7) / 8, b), g2((m + 7) / 8, b);
+  const size_t qs = off ? (size_t)c * sizeof(float) : 0;
+  if (sim_type == 0) {
+    k_normalize_split<0><<<g1, 256, qs, st>>>(f1, n, c, normalize, a_hi, a_lo, off ? f2 : nullptr, m, 1, temp, out, n, m);
+    k_normalize_split<0><<<g2, 256, qs, st>>>(f2, m, c, normalize, b_hi, b_lo, off ? f1 : nullptr, n, 0, temp, out, n, m);
+  } else {
+    k_normalize_split<1><<<g1, 256, qs, st>>>(f1, n, c, normalize, a_hi, a_lo, off ? f2 : nullptr, m, 1, temp, out, n, m);
+    k_normalize_split<1><<<g2, 256, qs, st>>>(f2, m, c, normalize, b_hi, b_lo, off ? f1 : nullptr, n, 0, temp, out, n, m);
+  }
   count_launch(2);
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int rc;
@@ -363,7 +411,7 @@ int run_similarity_tc(const float* f1, const float* f2, int b, int n, int m, int
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int tiles = b * ((n + TC_BM - 1) / TC_BM) * ((m + TC_BN - 1) / TC_BN);
+  const int tiles = b * (off ? tiles1 : tiles0);
   const int grid = tiles < sms ? tiles : sms;
   const size_t smem = sizeof(TcSmem) + 1024;
   const int terms = similarity_mode() == 1 ? 1 : 3;
@@ -371,7 +419,7 @@ int run_similarity_tc(const float* f1, const float* f2, int b, int n, int m, int
   do {                                                                                                       \
     auto kern = k_similarity_tc<MODE, NT>;                                                                   \
     UPK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
-    kern<<<grid, TC_THREADS, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, b, n, m, c, temp, out);                 \
+    kern<<<grid, TC_THREADS, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, b, n, m, c, temp, off, out);            \
   } while (0)
   if (sim_type == 0) {
     if (terms == 3) UPK_LAUNCH_TC(0, 3); else UPK_LAUNCH_TC(0, 1);
