@@ -376,7 +376,7 @@ def main():
     pe_bytes = sum((12.0 * 2 * cfg.n_fine + 4.0 * cfg.n_fine * ns + 16.0 * cfg.n_fine * ns) for _, ns in cfg.pe) * B
     fps_ops = lambda n, m: 10.0 * (m - 1) * n * B   # 10 lane-ops per distance update
     models = {
-        "fine_similarity": ("k_similarity_tc<0,3> (tcgen05 3xTF32, 2049x2049x256/instance) + k_normalize_split x2",
+        "fine_similarity": ("k_similarity_tc<0,3> (tcgen05 3xTF32, 2048x2048x256 tiles per instance, background row/column peeled) + k_normalize_split x2",
                             "tensor", 2.0 * n1 * n1 * cfg.feat_dim * B),
         "fine_pose": ("k_fine_stats + k_fine_labels + k_fine_rows (3 reads of the 2049^2 fp32 matrix) + Kabsch + inliers",
                       "hbm", 3.0 * n1 * n1 * 4 * B),
@@ -388,8 +388,8 @@ def main():
         "ball_query+group_ref": ("ball_group_kernel<2 scales> (fused ball query + grouping)", "hbm", pe_bytes),
         "coarse_pose": ("k_score (K x 196 x 196 point pairs, 6 lane-ops each) + assignment/sampling/top-K", "fp32",
                         6.0 * cfg.n_proposal2 * cfg.n_coarse * cfg.n_coarse * B),
-        "coarse_similarity": ("k_sgemm_nt<0> (fp32 SIMT, 197x197x256/instance)", "fp32",
-                              2.0 * (cfg.n_coarse + 1) ** 2 * cfg.feat_dim * B / 2),
+        "coarse_similarity": ("k_similarity_tc<0,3> (tcgen05 3xTF32, 197x197x256 per instance) + k_normalize_split x2",
+                              "tensor", 2.0 * (cfg.n_coarse + 1) ** 2 * cfg.feat_dim * B),
     }
 
     def roof(stage):

@@ -235,6 +235,11 @@ int upk_weighted_procrustes(const float* src, const float* ref, const float* wei
                             int n, float weight_thresh, float eps, float* R_out,
                             float* t_out, upk_stream_t stream);
 
+/* out[b,i,:] = (pts[b,i,:] - t[b]) @ R[b]: a cloud moved by a pose, `p1_ = (p1 - init_t) @ init_R` of the fine
+ * module (oneref_predator_fine_point_matching.py:65-72) and the scoring transforms of model_utils.py:483,:558. */
+int upk_transform_points(const float* pts, const float* R, const float* t, int b, int n, float* out,
+                         upk_stream_t stream);
+
 /* HOST function (no GPU): the 3x3 Procrustes rotation solver of kernel family (3),
  * compiled from the same source as the device code.  H[n,9] row-major -> R[n,9]. */
 int upk_host_procrustes_rotation(const double* H, int n, double* R_out);

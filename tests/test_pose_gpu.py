@@ -311,3 +311,14 @@ def test_sample_pts_feats_api(cuda):
     assert torch.equal(f, torch.gather(feats, 1, idx.long().unsqueeze(2).repeat(1, 1, 256)))
     p2, l2, f2 = MU().sample_pts_feats_wlrf(p, p * 2, f, 196)
     assert p2.shape == (2, 196, 3) and torch.equal(l2, p2 * 2)
+
+
+def test_transform_points_matches_torch(cuda):
+    g = torch.Generator().manual_seed(3)
+    pts = torch.randn(3, 777, 3, generator=g).to(cuda)
+    R = torch.linalg.qr(torch.randn(3, 3, 3, generator=g))[0].to(cuda)
+    t = torch.randn(3, 3, generator=g).to(cuda)
+    got = MU().transform_points(pts, R, t)
+    exp = (pts.double() - t.double().unsqueeze(1)) @ R.double()
+    assert (got.double() - exp).abs().max() <= 2e-6
+    assert MU().transform_points(pts[:0], R[:0], t[:0]).shape == (0, 777, 3)

@@ -170,6 +170,24 @@ k_fine_inliers(const float* __restrict__ pts1, const float* __restrict__ model,
   }
 }
 
+// X = (pts - t) @ R per instance: the query cloud moved into the reference frame by a pose
+// (fine module :65-72, compute_fine_Rt :558; torch does it with a broadcast subtract + a K=3 cuBLAS GEMM).
+__global__ void __launch_bounds__(256)
+k_transform_points(const float* __restrict__ pts, const float* __restrict__ Rm, const float* __restrict__ tv, int n,
+                   float* __restrict__ out) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const float* R = Rm + (size_t)b * 9;
+  const float* t = tv + (size_t)b * 3;
+  const float* p = pts + ((size_t)b * n + i) * 3;
+  const float d0 = p[0] - t[0], d1 = p[1] - t[1], d2 = p[2] - t[2];
+  float* o = out + ((size_t)b * n + i) * 3;
+  o[0] = fmaf(d2, R[6], fmaf(d1, R[3], d0 * R[0]));
+  o[1] = fmaf(d2, R[7], fmaf(d1, R[4], d0 * R[1]));
+  o[2] = fmaf(d2, R[8], fmaf(d1, R[5], d0 * R[2]));
+}
+
 struct FineWs {
   AssignWs a;
   float* w1; float* w2;
@@ -243,6 +261,17 @@ int upk_fine_pose(const float* atten, const float* score1, int score1_ld, const 
     if (dbg->soft) UPK_CUDA_TRY(cudaMemcpyAsync(dbg->soft, w.soft, sizeof(float) * (size_t)b * n1 * 3, cudaMemcpyDeviceToDevice, st));
     if (dbg->asum) UPK_CUDA_TRY(cudaMemcpyAsync(dbg->asum, w.asum, sizeof(float) * (size_t)b * n1, cudaMemcpyDeviceToDevice, st));
   }
+  UPK_RETURN_LAST_ERROR();
+}
+
+int upk_transform_points(const float* pts, const float* R, const float* t, int b, int n, float* out,
+                         upk_stream_t stream) {
+  if (b < 0 || n < 0) return UPK_ERR_INVALID_ARG;
+  if (b == 0 || n == 0) return UPK_OK;
+  if (!pts || !R || !t || !out) return UPK_ERR_INVALID_ARG;
+  dim3 grid(ceil_div(n, 256), b);
+  k_transform_points<<<grid, 256, 0, (cudaStream_t)stream>>>(pts, R, t, n, out);
+  count_launch();
   UPK_RETURN_LAST_ERROR();
 }
 

@@ -138,7 +138,10 @@ int upk_feature_similarity(const float* feat1, const float* feat2, int b, int n,
   if (sim_type != 0 && sim_type != 1) return UPK_ERR_INVALID_ARG;
   if (b == 0) return UPK_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (similarity_tc_eligible(n, m, c))  // large problems: tcgen05 tensor-core path (3xTF32)
+  const bool aligned16 = ((reinterpret_cast<uintptr_t>(feat1) | reinterpret_cast<uintptr_t>(feat2)) & 15) == 0;
+  // large problems: tcgen05 tensor-core path (3xTF32); its operand preparation reads the rows with 128-bit loads
+  if (similarity_tc_eligible(n, m, c) && aligned16 && workspace &&
+      workspace_bytes >= similarity_tc_workspace_bytes(b, n, m, c))
     return run_similarity_tc(feat1, feat2, b, n, m, c, temp, normalize, sim_type, workspace, workspace_bytes,
                              atten_out, st);
   const float* a = feat1;

@@ -144,32 +144,61 @@ k_normalize_split(const float* __restrict__ x, int rows_per_batch, int c, int no
       s = warp_sum(s);
       qn = fmaxf(sqrtf(s), 1e-12f);
     }
-    for (int k = threadIdx.x; k < c; k += 256) s_q[k] = normalize ? q[k] / qn : q[k];
+    const float qinv = 1.0f / qn;
+    for (int k = threadIdx.x; k < c; k += 256) s_q[k] = q[k] * qinv;
     __syncthreads();
   }
   if (r >= rows_per_batch) return;
   const size_t row = (size_t)bidx * rows_per_batch + r;
   const float* p = x + row * c;
-  float nrm = 1.f;
-  if (normalize) {
-    float s = 0.f;
-    for (int k = lane; k < c; k += 32) {
-      float v = p[k];
-      s = fmaf(v, v, s);
+  // 128-bit accesses (c % 4 == 0 is guaranteed by the tensor-core path, rows are 16-byte aligned with the
+  // workspace); the row stays in registers between the norm and the split for c <= 512
+  const int nv = c >> 2;
+  const float4* p4 = reinterpret_cast<const float4*>(p);
+  float4 keep[4];
+  float s = 0.f;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int k = lane + 32 * u;
+    if (k < nv) {
+      keep[u] = __ldg(p4 + k);
+      s = fmaf(keep[u].x, keep[u].x, fmaf(keep[u].y, keep[u].y, fmaf(keep[u].z, keep[u].z, fmaf(keep[u].w, keep[u].w, s))));
     }
+  }
+  for (int k = lane + 128; k < nv; k += 32) {
+    const float4 v = __ldg(p4 + k);
+    s = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, s))));
+  }
+  float inv = 1.f;
+  if (normalize) {
     s = warp_sum(s);
-    nrm = fmaxf(sqrtf(s), 1e-12f);
+    inv = 1.0f / fmaxf(sqrtf(s), 1e-12f);   // x * (1 / ||x||): within 1 ulp of F.normalize's division
   }
   float dot = 0.f;
-  for (int k = lane; k < c; k += 32) {
-    float v = normalize ? p[k] / nrm : p[k];
-    uint32_t h;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
-    float vh = __uint_as_float(h);
-    hi[row * c + k] = vh;
-    lo[row * c + k] = v - vh;
-    if (other) dot = fmaf(v, s_q[k], dot);
+  float4* hi4 = reinterpret_cast<float4*>(hi + row * c);
+  float4* lo4 = reinterpret_cast<float4*>(lo + row * c);
+  const float4* q4 = reinterpret_cast<const float4*>(s_q);
+  auto split = [&](float4 v, int k) {
+    v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+    float4 h;
+    uint32_t t;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.x)); h.x = __uint_as_float(t);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.y)); h.y = __uint_as_float(t);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.z)); h.z = __uint_as_float(t);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.w)); h.w = __uint_as_float(t);
+    hi4[k] = h;
+    lo4[k] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+    if (other) {
+      const float4 q = q4[k];
+      dot = fmaf(v.x, q.x, fmaf(v.y, q.y, fmaf(v.z, q.z, fmaf(v.w, q.w, dot))));
+    }
+  };
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int k = lane + 32 * u;
+    if (k < nv) split(keep[u], k);
   }
+  for (int k = lane + 128; k < nv; k += 32) split(__ldg(p4 + k), k);
   if (other) {
     dot = warp_sum(dot);
     if (MODE == 1) dot = sqrtf(fmaxf(2.0f - 2.0f * dot, 0.f));

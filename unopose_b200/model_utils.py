@@ -190,6 +190,20 @@ def compute_fine_Rt_overlap(atten, score, pts1, pts2, model_pts=None, dis_thres=
     return _fine(atten, score, pts1, pts2, model_pts, dis_thres, 0.001)
 
 
+def transform_points(pts, R, t):
+    """(pts (B,N,3) - t (B,3)) @ R (B,3,3): a cloud moved by a pose, as the fine module does with the coarse pose
+    (`p1_ = (p1 - init_t.unsqueeze(1)) @ init_R`, oneref_predator_fine_point_matching.py:65-72).  One kernel
+    instead of a broadcast subtract + a K=3 GEMM.  Evaluation path (no autograd edge)."""
+    _need_cuda(pts, "transform_points")
+    pts, R, t = _f32c(pts), _f32c(R), _f32c(t)
+    B, N = pts.shape[:2]
+    out = torch.empty_like(pts)
+    with torch.cuda.device(pts.device):
+        L.check(L.load().upk_transform_points(L.ptr(pts), L.ptr(R), L.ptr(t), B, N, L.ptr(out), L.stream_ptr(pts)),
+                "transform_points")
+    return out
+
+
 # --------------------------------------------------------------------------- a4
 def weighted_procrustes(src_points, ref_points, weights=None, weight_thresh=0.0, eps=1e-5,
                         return_transform=False, src_centroid=None, ref_centroid=None):

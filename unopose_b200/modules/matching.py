@@ -8,7 +8,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from ..model_utils import compute_coarse_Rt_overlap, compute_feature_similarity, compute_fine_Rt_overlap
+from ..model_utils import (compute_coarse_Rt_overlap, compute_feature_similarity, compute_fine_Rt_overlap,
+                           transform_points)
 from ..pointnet2.pointnet2_utils import QueryAndGroup, QueryAndLRFGroup, ball_query_and_group
 from .layers import Conv1d, SharedMLP
 from .transformer import GeometricTransformer, SparseToDenseTransformer
@@ -136,7 +137,10 @@ class FinePointMatchingOneRef(nn.Module):
     def matching_features(self, p1, f1, geo1, fps_idx1, p2, f2, geo2, fps_idx2, end_points):
         B, n1 = p1.size(0), p1.size(1)
         if "init_R" in end_points and "init_t" in end_points:
-            p1_ = (p1 - end_points["init_t"].unsqueeze(1)) @ end_points["init_R"]
+            if p1.is_cuda and not (torch.is_grad_enabled() and p1.requires_grad):
+                p1_ = transform_points(p1, end_points["init_R"], end_points["init_t"])
+            else:
+                p1_ = (p1 - end_points["init_t"].unsqueeze(1)) @ end_points["init_R"]
         else:
             p1_ = p1
         bg = self.bg_token.repeat(B, 1, 1)

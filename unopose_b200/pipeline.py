@@ -126,8 +126,8 @@ def run_hot_path(inp, cfg=HotPathConfig(), stages=None, overlap=True):
 
     def s_pe_q():
         # the fine module encodes the query cloud AFTER moving it by the coarse pose (fine module :65-72)
-        p1_ = (inp["pts"] - out["init_t"].unsqueeze(1)) @ out["init_R"]
-        pe_geometry("q", p1_.contiguous())
+        out["pts_moved"] = MU.transform_points(inp["pts"], out["init_R"], out["init_t"])
+        pe_geometry("q", out["pts_moved"])
 
     def s_pe_r():
         pe_geometry("r", out["tem_sub"])
