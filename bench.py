@@ -44,6 +44,9 @@ def parse():
     ap.add_argument("--depth", type=int, default=2,
                     help="steps in flight: consecutive steps (different resident sets) replay on alternating "
                          "streams, so one step's serial FPS chain (16 SMs) overlaps the next step's full-GPU kernels")
+    ap.add_argument("--no-zero-copy", action="store_true",
+                    help="e2e: copy the full per-point feature tensors instead of gathering the FPS-selected rows "
+                         "straight out of pinned host memory")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-torch-baseline", action="store_true")
     return ap.parse_args()
@@ -334,7 +337,8 @@ def main():
     # ---- end to end through the public API with HOST (pinned) buffers: H2D of every step input,
     #      D2H of the step result, both inside the timed region
     host_sets = [synthetic_inputs(5000 + 1000 * rank + 17 * s, B, cfg, pin=True) for s in range(2)]
-    fed = HostFedHotPath(cfg, B, dev, overlap=not args.no_overlap, use_graph=not args.no_graph)
+    fed = HostFedHotPath(cfg, B, dev, overlap=not args.no_overlap, use_graph=not args.no_graph,
+                         zero_copy=not args.no_zero_copy)
 
     def e2e_step(i):
         # prefetch the NEXT step's inputs (copy stream) while this step computes; every timed step
@@ -358,8 +362,11 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_e = float(t.item())
     res_host = fed.result
-    e2e = {"value": B * world / (ms_e * 1e-3), "unit": "instances/s", "h2d_bytes_per_step": input_bytes(host_sets[0]),
-           "d2h_bytes_per_step": res_host.numel() * 4, "ms_per_step": ms_e}
+    copied, pulled = fed.pcie_bytes_per_step(host_sets[0])
+    e2e = {"value": B * world / (ms_e * 1e-3), "unit": "instances/s", "h2d_bytes_per_step": copied + pulled,
+           "d2h_bytes_per_step": res_host.numel() * 4, "ms_per_step": ms_e,
+           "h2d_copied_bytes": copied, "h2d_zero_copy_gather_bytes": pulled,
+           "host_input_bytes": input_bytes(host_sets[0])}
 
     if rank != 0:
         if dist is not None:

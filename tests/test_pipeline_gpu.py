@@ -68,3 +68,37 @@ def test_host_fed_front_end(cuda):
         o = run_hot_path(to_device(hosts[i], cuda, non_blocking=False), cfg, overlap=False)
         exp = torch.cat([o["pred_R"].reshape(B, 9), o["pred_t"], o["pred_pose_score"].unsqueeze(1)], 1).cpu()
         assert torch.equal(rows[i], exp), i
+
+
+def test_zero_copy_gather_from_pinned_host(cuda):
+    """The host-fed front end gathers FPS-selected feature rows straight out of pinned host memory."""
+    from unopose_b200 import model_utils as MU
+    from unopose_b200.pipeline import HostFedHotPath, run_hot_path, synthetic_inputs, to_device
+
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(3, 500, 64, generator=g).pin_memory()
+    idx = torch.randint(0, 500, (3, 77), generator=g, dtype=torch.int32).to(cuda)
+    got = MU.gather_rows_pinned(x, idx)
+    exp = torch.gather(x.to(cuda), 1, idx.long().unsqueeze(2).expand(3, 77, 64))
+    assert torch.equal(got, exp)
+    with pytest.raises(RuntimeError):
+        MU.gather_rows_pinned(torch.randn(1, 4, 4), idx[:1, :2])          # not pinned
+    # through sample_pts_feats: pinned features, device points
+    pts = torch.randn(3, 500, 3, generator=g).to(cuda)
+    p1, f1, i1 = MU.sample_pts_feats(pts, x, 50, return_index=True)
+    p2, f2, i2 = MU.sample_pts_feats(pts, x.to(cuda), 50, return_index=True)
+    assert torch.equal(i1, i2) and torch.equal(p1, p2) and torch.equal(f1, f2)
+    # the whole front end, with and without zero-copy, yields the same gathered features
+    cfg = _cfg()
+    host = synthetic_inputs(21, 2, cfg, pin=True)
+    outs = []
+    for zc in (True, False):
+        fed = HostFedHotPath(cfg, 2, cuda, zero_copy=zc)
+        fed.stage(0, host)
+        fed.run(0)
+        o = fed.graphs[0].out
+        outs.append({k: o[k].clone() for k in ("tem_sub_feats", "sf1", "sf2", "pred_R")})
+        copied, pulled = fed.pcie_bytes_per_step(host)
+        assert (pulled > 0) == zc
+    for k in outs[0]:
+        assert torch.equal(outs[0][k], outs[1][k]), k

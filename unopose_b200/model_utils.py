@@ -293,7 +293,30 @@ class _GatherRows(torch.autograd.Function):
         return gx, None
 
 
+def gather_rows_pinned(x_host, idx):
+    """Zero-copy row gather: x_host is a PINNED host tensor (B,N,C) fp32, idx (B,m) int32 on the GPU ->
+    (B,m,C) on the GPU.  The kernel reads the selected rows straight out of the page-locked host memory
+    (unified virtual addressing: the host pointer is valid on the device), so only m of the N rows cross
+    PCIe.  The host buffer must stay unchanged until the stream has passed this point."""
+    if x_host.is_cuda or not x_host.is_pinned():
+        raise RuntimeError("gather_rows_pinned: x must be a pinned host tensor")
+    if x_host.dtype != torch.float32 or not x_host.is_contiguous():
+        raise RuntimeError("gather_rows_pinned: x must be a contiguous float tensor")
+    L.check_int(idx, "idx")
+    L.check_cuda(idx, "idx")
+    idx = idx.contiguous()
+    b, n, c = x_host.shape
+    m = idx.shape[1]
+    out = torch.empty((b, m, c), dtype=torch.float32, device=idx.device)
+    with torch.cuda.device(idx.device):
+        L.check(L.load().upk_gather_rows(x_host.data_ptr(), L.ptr(idx), b, n, m, c, L.ptr(out), L.stream_ptr(idx)),
+                "gather_rows(pinned host source)")
+    return out
+
+
 def _gather_rows(x, idx):
+    if not x.is_cuda and x.is_pinned():      # host-fed front end: features stay in pinned host memory
+        return gather_rows_pinned(x, idx)
     return _GatherRows.apply(x, idx)
 
 
