@@ -322,3 +322,50 @@ def test_transform_points_matches_torch(cuda):
     exp = (pts.double() - t.double().unsqueeze(1)) @ R.double()
     assert (got.double() - exp).abs().max() <= 2e-6
     assert MU().transform_points(pts[:0], R[:0], t[:0]).shape == (0, 777, 3)
+
+
+# ------------------------------------------------------------------ BASELINE.json configs 4 and 5 (full sizes)
+@pytest.mark.parametrize("H,B", [(1000, 8), (20000, 8), (100000, 1), (100000, 2)])
+def test_hypothesis_count_sweep_full_size(cuda, H, B):
+    """Config 4: 1k-100k hypotheses per instance at the coarse shape (196 x 196, K = 300).  Size-independent
+    properties: proper rotations, the planted pose is found, the selected pool index is in range and is the
+    arg-max of the kept scores, and the same uniforms give the same answer (bit-exact)."""
+    n, K = 196, 300
+    d = batch(400 + H % 97, B, n, 256, cuda)
+    atten = MU().compute_feature_similarity(d["f1"], d["f2"], "cosine", 0.1, True)
+    g = torch.Generator(device="cpu").manual_seed(H)
+    u = torch.rand(B, 3 * H, generator=g).to(cuda)
+    R, t, s, m = MU()._coarse(atten, d["score"], d["pts1"], d["pts2"], None, H, K, u=u, return_debug=True)
+    R2, t2, s2 = MU()._coarse(atten, d["score"], d["pts1"], d["pts2"], None, H, K, u=u)
+    assert torch.equal(R, R2) and torch.equal(t, t2) and torch.equal(s, s2)
+    assert (torch.det(R.double()) - 1).abs().max() < 1e-5
+    assert PO.rotation_geodesic_deg(R, d["R"]).max() < 3.0
+    assert ((m["pool"] >= 0) & (m["pool"] < H)).all()
+    assert (m["top"] >= 0).all() and (m["top"] < H).all() and (m["top"][:, 1:] > m["top"][:, :-1]).all()
+    best = m["scores"].max(1)[1]
+    assert torch.equal(m["pool"].long(), torch.gather(m["top"].long(), 1, best.unsqueeze(1)).squeeze(1))
+    if H <= 20000:   # the oracle (reference torch path) at the same uniforms: same selected hypothesis or a float-noise tie
+        Ro, to, so = PO.coarse_pose(atten, d["score"], d["pts1"], d["pts2"], None, H, K, u=u)
+        ang = PO.rotation_geodesic_deg(R, Ro)
+        same = ang <= ROT_TOL_DEG
+        assert same.float().mean() >= 0.75
+        assert torch.allclose(s[~same], so[~same], rtol=2e-4)
+
+
+def test_multi_instance_query_image_64_detections(cuda):
+    """Config 5: 64 detections in one call == four calls of 16 (instances are independent)."""
+    from unopose_b200.pipeline import HotPathConfig, run_hot_path, synthetic_inputs
+
+    cfg = HotPathConfig()
+    inp = synthetic_inputs(77, 64, cfg, device=cuda)
+    torch.manual_seed(5)
+    big = run_hot_path(inp, cfg)
+    torch.cuda.synchronize()
+    assert big["pred_R"].shape == (64, 3, 3) and torch.isfinite(big["pred_R"]).all()
+    assert PO.rotation_geodesic_deg(big["pred_R"].cpu(), inp["_gt_R"]).max() < 2.0
+    for c in range(4):
+        sl = slice(16 * c, 16 * c + 16)
+        part = {k: (v[sl].contiguous() if not k.startswith("_") else v) for k, v in inp.items()}
+        o = run_hot_path(part, cfg)
+        for k in ("tem_idx", "fps_idx1", "fps_idx2", "pe_r0", "pe_r1", "pe_idx_r0", "pe_idx_r1", "c_atten", "f_atten"):
+            assert torch.equal(o[k], big[k][sl]), (c, k)
