@@ -235,6 +235,14 @@ int upk_weighted_procrustes(const float* src, const float* ref, const float* wei
                             int n, float weight_thresh, float eps, float* R_out,
                             float* t_out, upk_stream_t stream);
 
+/* Global local-reference-frame coordinates of a cloud: `get_batch_lrf(pts)` of the reference models
+ * (oneref_grf_predator_pose_estimation_model.py:78-93), i.e. LRF(r)(centroid, pts) of model_utils.py:766-823.
+ * pts[b,n,3] -> out[b,n,3].  radius[b] or NULL (then r = max |p - centroid|, the `use_ref_rad = False` branch; pass
+ * ones for `use_ref_rad = True`).  frame_out (optional, [b,13]): the frame columns x|y|z row-major (9), the centre (3)
+ * and the radius (1). */
+int upk_global_lrf(const float* pts, const float* radius, int b, int n, float eps, float* out, float* frame_out,
+                   upk_stream_t stream);
+
 /* out[b,i,:] = (pts[b,i,:] - t[b]) @ R[b]: a cloud moved by a pose, `p1_ = (p1 - init_t) @ init_R` of the fine
  * module (oneref_predator_fine_point_matching.py:65-72) and the scoring transforms of model_utils.py:483,:558. */
 int upk_transform_points(const float* pts, const float* R, const float* t, int b, int n, float* out,

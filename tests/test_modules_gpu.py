@@ -80,3 +80,33 @@ def test_fine_module_forward(cuda):
     err_ref = PO.rotation_geodesic_deg(g["pred_R"], g["R_gt"])
     err_mine = PO.rotation_geodesic_deg(ep["pred_R"], g["R_gt"])
     assert (err_mine <= err_ref + 1.0).all(), (err_mine, err_ref)
+
+
+def test_global_lrf_kernel(cuda):
+    """upk_global_lrf (get_batch_lrf in one kernel) against the reference LRF output (golden, given radii) and
+    against the torch module on clouds of the path's sizes (radius = max norm)."""
+    from unopose_b200.model_utils import LRF
+    from unopose_b200.pointnet2.lrf import get_batch_lrf
+    from util_clouds import batch_clouds
+
+    g = _g(cuda)
+    out = get_batch_lrf(g["p1"], radius=g["lrf_r"])                      # golden: produced by the REFERENCE class
+    assert torch.allclose(out, g["lrf_global"].transpose(1, 2), atol=1e-4, rtol=1e-4)
+    for n, kind in ((2048, "surface"), (5000, "surface"), (777, "ball")):
+        pts = torch.from_numpy(batch_clouds(n, 4, n, kind)).to(cuda) * 0.37 + 0.11
+        for use_ref_rad in (False, True):
+            got, frame = get_batch_lrf(pts, use_ref_rad=use_ref_rad, return_frame=True)
+            c = pts.mean(1, keepdim=True)
+            r = torch.ones(4, device=cuda) if use_ref_rad else torch.norm(pts - c, dim=2).max(1)[0]
+            exp = LRF(r)(c.transpose(1, 2), pts.transpose(1, 2).contiguous()).transpose(1, 2)
+            assert torch.allclose(got, exp, atol=2e-4, rtol=1e-4), (n, kind, use_ref_rad)
+            F = frame[:, :9].reshape(4, 3, 3)                              # columns x | y | z: a proper rotation
+            assert (F.transpose(1, 2) @ F - torch.eye(3, device=cuda)).abs().max() < 1e-5
+            assert torch.allclose(frame[:, 9:12], c.squeeze(1), atol=1e-6) and torch.allclose(frame[:, 12], r, rtol=1e-6)
+    # rigid motion of the cloud leaves the frame coordinates unchanged (the frame is attached to the cloud)
+    pts = torch.from_numpy(batch_clouds(9, 2, 2048, "surface")).to(cuda)
+    Rg = torch.linalg.qr(torch.randn(2, 3, 3, device=cuda))[0]
+    Rg = Rg * torch.sign(torch.det(Rg)).view(2, 1, 1)
+    moved = pts @ Rg.transpose(1, 2) + torch.tensor([0.3, -0.2, 0.5], device=cuda)
+    assert torch.allclose(get_batch_lrf(pts), get_batch_lrf(moved), atol=5e-4)
+    assert get_batch_lrf(pts[:0]).shape == (0, 2048, 3)

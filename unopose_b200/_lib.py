@@ -49,6 +49,7 @@ _SIGNATURES = {
     "upk_fine_pose": [c_f, c_f, c_i, c_f, c_i, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_fl, c_fl,
                       c_f, c_sz, c_f, c_f, c_f, c_f, c_st],
     "upk_weighted_procrustes": [c_f, c_f, c_f, c_i, c_i, c_fl, c_fl, c_f, c_f, c_st],
+    "upk_global_lrf": [c_f, c_f, c_i, c_i, c_fl, c_f, c_f, c_st],
     "upk_transform_points": [c_f, c_f, c_f, c_i, c_i, c_f, c_st],
     "upk_host_procrustes_rotation": [c_f, c_i, c_f],
 }

@@ -1,0 +1,142 @@
+// Global (per-cloud) local reference frame: the whole `get_batch_lrf` of the reference models
+// (core/unopose/model/oneref_grf_predator_pose_estimation_model.py:78-93 -> LRF.forward,
+// core/unopose/utils/model_utils.py:777-823) in ONE kernel, one CTA per cloud:
+//   c = mean(p);  r = max |p - c|  (or a given radius);  cov = sum (c - p)(c - p)^T / N;
+//   z_raw = eigenvector of the smallest eigenvalue (in-register cyclic Jacobi, fp64);
+//   sign by the vote  #(z_raw.(c - p) > 1e-3) - #(z_raw.(c - p) < -1e-3) < 0  ->  z;
+//   x = normalise( sum (r - |q|)^2 (z.q)^2 (q - (z.q) z) ),  q = p - c;   y = x cross z;
+//   out = [x y z]^T q / r.
+// The reference spends ~25 torch launches here (two reductions, a bmm, a cuSOLVER SVD, ~15 elementwise
+// passes over (B,3,N)); the sums are accumulated in fp64 here (torch: fp32 trees).  The sign of z_raw is
+// immaterial: flipping it flips the vote, and the vote decides the final direction (unless it is exactly 0).
+#include <math.h>
+
+#include "common.cuh"
+#include "launch_count.h"
+#include "solver3.cuh"
+#include "../../include/unopose_b200.h"
+
+namespace upk {
+
+constexpr int LRF_THREADS = 512;
+
+template <int N>
+__device__ __forceinline__ void lrf_block_sum(double (&v)[N], double* s_buf /* N * 32 */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int i = 0; i < N; ++i) v[i] = warp_sum(v[i]);
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) s_buf[i * 32 + warp] = v[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    double t = 0.0;
+    for (int w = 0; w < nw; ++w) t += s_buf[i * 32 + w];  // fixed order, identical in all threads
+    v[i] = t;
+  }
+}
+
+// eigenvector of the smallest eigenvalue of a symmetric 3x3 matrix (same Jacobi sweeps as procrustes_rotation)
+__host__ __device__ __forceinline__ void sym3_min_eigenvector(double m00, double m11, double m22, double m01,
+                                                              double m02, double m12, double* v) {
+  double v0[3] = {1, 0, 0}, v1[3] = {0, 1, 0}, v2[3] = {0, 0, 1};
+  const double scale = fabs(m00) + fabs(m11) + fabs(m22);
+#pragma unroll 1
+  for (int sweep = 0; sweep < 10; ++sweep) {
+    double off = fabs(m01) + fabs(m02) + fabs(m12);
+    if (off <= 1e-22 * scale) break;
+    jacobi_rotate(m00, m11, m01, m02, m12, v0, v1);
+    jacobi_rotate(m00, m22, m02, m01, m12, v0, v2);
+    jacobi_rotate(m11, m22, m12, m01, m02, v1, v2);
+  }
+  const int i = (m00 <= m11) ? ((m00 <= m22) ? 0 : 2) : ((m11 <= m22) ? 1 : 2);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) v[k] = i == 0 ? v0[k] : (i == 1 ? v1[k] : v2[k]);
+}
+
+__global__ void __launch_bounds__(LRF_THREADS)
+k_global_lrf(const float* __restrict__ pts, const float* __restrict__ radius, int n, float eps,
+             float* __restrict__ out, float* __restrict__ frame_out) {
+  __shared__ double s_buf[6 * 32];
+  __shared__ float s_max[32];
+  const int b = blockIdx.x;
+  const float* P = pts + (size_t)b * n * 3;
+  // ---- centroid
+  double c3[3] = {0, 0, 0};
+  for (int i = threadIdx.x; i < n; i += LRF_THREADS) {
+    c3[0] += P[i * 3 + 0]; c3[1] += P[i * 3 + 1]; c3[2] += P[i * 3 + 2];
+  }
+  lrf_block_sum<3>(c3, s_buf);
+  const float cx = (float)(c3[0] / n), cy = (float)(c3[1] / n), cz = (float)(c3[2] / n);
+  // ---- radius (max norm of the centred cloud) and covariance of (c - p)
+  float mx = 0.f;
+  double cv[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = threadIdx.x; i < n; i += LRF_THREADS) {
+    const float x = cx - P[i * 3 + 0], y = cy - P[i * 3 + 1], z = cz - P[i * 3 + 2];
+    mx = fmaxf(mx, sqrtf(x * x + y * y + z * z));
+    cv[0] += (double)(x * x); cv[1] += (double)(y * y); cv[2] += (double)(z * z);
+    cv[3] += (double)(x * y); cv[4] += (double)(x * z); cv[5] += (double)(y * z);
+  }
+  mx = warp_max(mx);
+  lrf_block_sum<6>(cv, s_buf);   // (its barriers also order the s_max exchange below)
+  if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = 0.f;
+  for (int w = 0; w < LRF_THREADS / 32; ++w) mx = fmaxf(mx, s_max[w]);
+  const float r = radius ? radius[b] : mx;
+  double zr[3];
+  sym3_min_eigenvector(cv[0] / n, cv[1] / n, cv[2] / n, cv[3] / n, cv[4] / n, cv[5] / n, zr);
+  float z0 = (float)zr[0], z1 = (float)zr[1], z2 = (float)zr[2];
+  // ---- sign vote
+  double vote[1] = {0.0};
+  for (int i = threadIdx.x; i < n; i += LRF_THREADS) {
+    const float h = z0 * (cx - P[i * 3 + 0]) + z1 * (cy - P[i * 3 + 1]) + z2 * (cz - P[i * 3 + 2]);
+    vote[0] += (h > 1e-3f ? 1.0 : 0.0) - (h < -1e-3f ? 1.0 : 0.0);
+  }
+  lrf_block_sum<1>(vote, s_buf);
+  if (vote[0] < 0.0) { z0 = -z0; z1 = -z1; z2 = -z2; }
+  // ---- x axis: weighted sum of the in-plane components
+  double xd[3] = {0, 0, 0};
+  for (int i = threadIdx.x; i < n; i += LRF_THREADS) {
+    const float qx = P[i * 3 + 0] - cx, qy = P[i * 3 + 1] - cy, qz = P[i * 3 + 2] - cz;
+    const float h = z0 * qx + z1 * qy + z2 * qz;
+    const float d = sqrtf(qx * qx + qy * qy + qz * qz);
+    const float a = (r - d) * (r - d) * (h * h);
+    xd[0] += (double)(a * (qx - h * z0)); xd[1] += (double)(a * (qy - h * z1)); xd[2] += (double)(a * (qz - h * z2));
+  }
+  lrf_block_sum<3>(xd, s_buf);
+  const float x0f = (float)xd[0], x1f = (float)xd[1], x2f = (float)xd[2];
+  const float xn = sqrtf(x0f * x0f + x1f * x1f + x2f * x2f) + eps;
+  const float x0 = x0f / xn, x1 = x1f / xn, x2 = x2f / xn;
+  const float y0 = x1 * z2 - x2 * z1, y1 = x2 * z0 - x0 * z2, y2 = x0 * z1 - x1 * z0;   // y = x cross z
+  if (frame_out && threadIdx.x == 0) {
+    float* f = frame_out + (size_t)b * 13;   // columns x | y | z, centre, radius
+    f[0] = x0; f[1] = y0; f[2] = z0; f[3] = x1; f[4] = y1; f[5] = z1; f[6] = x2; f[7] = y2; f[8] = z2;
+    f[9] = cx; f[10] = cy; f[11] = cz; f[12] = r;
+  }
+  // ---- coordinates in the frame
+  float* O = out + (size_t)b * n * 3;
+  for (int i = threadIdx.x; i < n; i += LRF_THREADS) {
+    const float qx = (P[i * 3 + 0] - cx) / r, qy = (P[i * 3 + 1] - cy) / r, qz = (P[i * 3 + 2] - cz) / r;
+    O[i * 3 + 0] = x0 * qx + x1 * qy + x2 * qz;
+    O[i * 3 + 1] = y0 * qx + y1 * qy + y2 * qz;
+    O[i * 3 + 2] = z0 * qx + z1 * qy + z2 * qz;
+  }
+}
+
+}  // namespace upk
+
+using namespace upk;
+
+extern "C" int upk_global_lrf(const float* pts, const float* radius, int b, int n, float eps, float* out,
+                              float* frame_out, upk_stream_t stream) {
+  if (b < 0 || n <= 0) return UPK_ERR_INVALID_ARG;
+  if (b == 0) return UPK_OK;
+  if (!pts || !out) return UPK_ERR_INVALID_ARG;
+  k_global_lrf<<<b, LRF_THREADS, 0, (cudaStream_t)stream>>>(pts, radius, n, eps, out, frame_out);
+  count_launch();
+  UPK_RETURN_LAST_ERROR();
+}

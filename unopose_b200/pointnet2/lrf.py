@@ -78,3 +78,28 @@ class LRF(nn.Module):
         yp = torch.cross(xp, zp, dim=1)
         frame = torch.stack((xp, yp, zp), dim=2)                      # columns x,y,z
         return torch.einsum("bij,bin->bjn", frame, (xyz_group - xyz) / r)
+
+
+def get_batch_lrf(pts, use_ref_rad=False, radius=None, eps=1e-10, return_frame=False):
+    """pts (B,N,3) -> (B,N,3): coordinates in the cloud's global reference frame, the reference models'
+    ``get_batch_lrf`` (oneref_grf_predator_pose_estimation_model.py:78-93: centroid, radius, ``LRF``).
+    CUDA tensors run ONE kernel (upk_global_lrf); CPU tensors / tensors that require grad take the torch module
+    above.  `radius` (B,) overrides the radius choice."""
+    if radius is None and use_ref_rad:
+        radius = torch.ones(pts.shape[0], device=pts.device)
+    if not pts.is_cuda or (torch.is_grad_enabled() and pts.requires_grad):
+        centroids = torch.mean(pts, 1, True)
+        r = radius if radius is not None else torch.norm(pts - centroids, dim=2).max(1)[0]
+        out = LRF(r, eps)(centroids.transpose(1, 2), pts.transpose(1, 2)).transpose(1, 2).contiguous()
+        return (out, None) if return_frame else out
+    from .. import _lib as L
+
+    p = pts.float().contiguous()
+    B, N = p.shape[:2]
+    out = torch.empty_like(p)
+    frame = torch.empty((B, 13), dtype=torch.float32, device=p.device) if return_frame else None
+    rad = radius.float().contiguous() if radius is not None else None
+    with torch.cuda.device(p.device):
+        L.check(L.load().upk_global_lrf(L.ptr(p), L.ptr(rad), B, N, float(eps), L.ptr(out), L.ptr(frame),
+                                        L.stream_ptr(p)), "global_lrf")
+    return (out, frame) if return_frame else out
