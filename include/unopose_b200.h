@@ -229,6 +229,24 @@ int upk_fine_pose(const float* atten, const float* score1, int score1_ld,
                   size_t workspace_bytes, float* R_out, float* t_out, float* score_out,
                   const upk_fine_debug* dbg, upk_stream_t stream);
 
+/* Fused pass 1 (cosine logits): the similarity GEMM's epilogue also emits the exponent sums that the dual-softmax
+ * assignment of compute_fine_Rt[_overlap] needs (model_utils.py:542), so the fine solve reads `atten` twice
+ * instead of three times.  |cosine| <= 1 bounds every logit by 1/temp: one fixed reference exponent, no maxima.
+ *   upk_feature_similarity_stats == upk_feature_similarity(normalize = 1, sim_type = 0) + stats_out
+ *   upk_fine_pose_stats          == upk_fine_pose, given the stats of the SAME atten and temp
+ * Returns UPK_ERR_UNSUPPORTED when the tensor-core path does not apply (small shapes, c % 16 != 0, unaligned
+ * features, similarity mode != 3): callers then use the plain pair. */
+size_t upk_similarity_stats_bytes(int b, int n, int m);
+int upk_feature_similarity_stats(const float* feat1, const float* feat2, int b, int n, int m, int c, float temp,
+                                 void* workspace, size_t workspace_bytes, float* atten_out, float* stats_out,
+                                 size_t stats_bytes, upk_stream_t stream);
+int upk_fine_pose_stats(const float* atten, const float* stats, size_t stats_bytes, float temp,
+                        const float* score1, int score1_ld, const float* score2, int score2_ld,
+                        const float* pts1, const float* pts2, const float* model_pts, int n_model, int b, int n1,
+                        int n2, float dis_thres, float weight_thresh, void* workspace, size_t workspace_bytes,
+                        float* R_out, float* t_out, float* score_out, const upk_fine_debug* dbg,
+                        upk_stream_t stream);
+
 /* weighted_procrustes(src[b,n,3], ref[b,n,3], weights[b,n] or NULL, thresh, eps)
  * -> R[b,9], t[b,3] with ref ~= R src + t  (model_utils.py:667-743). */
 int upk_weighted_procrustes(const float* src, const float* ref, const float* weights, int b,

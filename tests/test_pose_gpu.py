@@ -369,3 +369,41 @@ def test_multi_instance_query_image_64_detections(cuda):
         o = run_hot_path(part, cfg)
         for k in ("tem_idx", "fps_idx1", "fps_idx2", "pe_r0", "pe_r1", "pe_idx_r0", "pe_idx_r1", "c_atten", "f_atten"):
             assert torch.equal(o[k], big[k][sl]), (c, k)
+
+
+@pytest.mark.parametrize("n1,n2,c", [(2048, 2048, 256), (700, 900, 64), (1023, 513, 32)])
+def test_fused_similarity_stats_path(cuda, n1, n2, c):
+    """compute_feature_similarity(return_stats=True) + compute_fine_Rt_overlap(stats=) (pass 1 fused into the
+    GEMM epilogue) against the separate three-pass path and the oracle."""
+    B = 2
+    g = torch.Generator().manual_seed(n1 + n2)
+    f2 = torch.randn(B, n2 + 1, c, generator=g)
+    perm = torch.stack([torch.randint(0, n2, (n1,), generator=g) for _ in range(B)])
+    f1 = torch.cat([f2[:, :1], torch.gather(f2[:, 1:], 1, perm.unsqueeze(2).expand(B, n1, c))
+                    + 0.5 * torch.randn(B, n1, c, generator=g)], 1)
+    _, score, p1, p2 = _ragged_fine_inputs(n1 * 3 + n2, B, n1, n2, cuda, 1.0)
+    f1, f2 = f1.to(cuda), f2.to(cuda)
+    atten, stats = MU().compute_feature_similarity(f1, f2, "cosine", 0.1, True, return_stats=True)
+    assert stats is not None and stats.shape == (B, n1 + 1, n2 + 1)
+    plain = MU().compute_feature_similarity(f1, f2, "cosine", 0.1, True)
+    # the logits themselves are untouched by the fusion (the stats path always peels the background row/column off
+    # the tiles; when the plain path does not, those 1-row/1-column entries come from a different fp32 dot order)
+    assert torch.equal(atten[:, 1:, 1:], plain[:, 1:, 1:]) and torch.allclose(atten, plain, atol=2e-5, rtol=0)
+    for sc in (score, None):
+        thr = 0.001 if sc is not None else 0.0
+        Rf, tf, sf, mf = MU()._fine(atten, sc, p1, p2, None, 0.15, thr, return_debug=True, stats=stats)
+        Rp, tp, sp, mp = MU()._fine(atten, sc, p1, p2, None, 0.15, thr, return_debug=True)
+        assert (mf["w1"] != mp["w1"]).float().mean() <= 1e-3 and (mf["w2"] != mp["w2"]).float().mean() <= 1e-3
+        same = mf["w1"] == mp["w1"]
+        assert torch.allclose(mf["asum"][same], mp["asum"][same], rtol=2e-4, atol=1e-9)
+        if torch.equal(mf["w1"], mp["w1"]) and torch.equal(mf["w2"], mp["w2"]):
+            assert PO.rotation_geodesic_deg(Rf, Rp).max() <= ROT_TOL_DEG
+            assert PO.relative_translation_error(tf, tp).max() <= T_TOL_REL
+            Ro, to, so = PO.fine_pose(atten, sc, p1, p2, None, 0.15)
+            assert PO.rotation_geodesic_deg(Rf, Ro).max() <= ROT_TOL_DEG
+            assert PO.relative_translation_error(tf, to).max() <= T_TOL_REL
+    # not applicable: L2 similarity / small geometry -> stats is None, plain path
+    a2, s2 = MU().compute_feature_similarity(f1[:, :200], f2[:, :200], "cosine", 0.1, True, return_stats=True)
+    assert s2 is None and a2.shape == (B, 200, 200)
+    with pytest.raises(RuntimeError):
+        MU().compute_fine_Rt_overlap(atten[:, :-1], score, p1[:, :-1], p2, stats=stats)

@@ -48,6 +48,9 @@ _SIGNATURES = {
     "upk_select_best": [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_st],
     "upk_fine_pose": [c_f, c_f, c_i, c_f, c_i, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_fl, c_fl,
                       c_f, c_sz, c_f, c_f, c_f, c_f, c_st],
+    "upk_feature_similarity_stats": [c_f, c_f, c_i, c_i, c_i, c_i, c_fl, c_f, c_sz, c_f, c_f, c_sz, c_st],
+    "upk_fine_pose_stats": [c_f, c_f, c_sz, c_fl, c_f, c_i, c_f, c_i, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_fl, c_fl,
+                            c_f, c_sz, c_f, c_f, c_f, c_f, c_st],
     "upk_weighted_procrustes": [c_f, c_f, c_f, c_i, c_i, c_fl, c_fl, c_f, c_f, c_st],
     "upk_global_lrf": [c_f, c_f, c_i, c_i, c_fl, c_f, c_f, c_st],
     "upk_transform_points": [c_f, c_f, c_f, c_i, c_i, c_f, c_st],
@@ -60,6 +63,7 @@ _SIZE_FUNCS = {
     "upk_coarse_pose_workspace_bytes": [c_i, c_i, c_i, c_i, c_i],
     "upk_coarse_assignment_workspace_bytes": [c_i, c_i, c_i],
     "upk_fine_pose_workspace_bytes": [c_i, c_i, c_i],
+    "upk_similarity_stats_bytes": [c_i, c_i, c_i],
 }
 
 

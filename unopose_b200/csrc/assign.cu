@@ -57,6 +57,7 @@ void carve_assign(Carver& cv, int b, const AssignGeom& g, AssignWs& ws) {
   ws.ai0 = cv.take<float>((size_t)b * g.R);
   ws.a0j = cv.take<float>((size_t)b * g.C);
   ws.flags = cv.take<int>((size_t)b);
+  ws.bsum = cv.take<float>((size_t)b * 2);
 }
 
 template <int TR, int TC>

@@ -316,6 +316,54 @@ k_fine_stats_merge(const float* __restrict__ atten, const float2* __restrict__ r
   *om = sc / s;
 }
 
+// ---- fused-statistics path: pass 1 came out of the similarity GEMM's epilogue (similarity_tc.cu, STATS) as
+// per-tile partial sums of 2^(v log2e - gref) over the main block; the background row / column are added here.
+__global__ void __launch_bounds__(256)
+k_fine_border_sums(const float* __restrict__ atten, int R, int C, float gref, float* __restrict__ bsum) {
+  __shared__ float s_part[2][8];
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* A = atten + (size_t)b * R * C;
+  float r0 = 0.f, c0 = 0.f;
+  for (int j = threadIdx.x; j < C; j += 256) r0 += ex2_approx(fmaf(A[j], kL2E, -gref));               // row 0
+  for (int i = threadIdx.x; i < R; i += 256) c0 += ex2_approx(fmaf(A[(size_t)i * C], kL2E, -gref));   // column 0
+  r0 = warp_sum(r0);
+  c0 = warp_sum(c0);
+  if (lane == 0) { s_part[0][warp] = r0; s_part[1][warp] = c0; }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += s_part[threadIdx.x][w];
+    bsum[b * 2 + threadIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_fine_stats_merge_fused(const float* __restrict__ atten, const float* __restrict__ rowpart,
+                         const float* __restrict__ colpart, int npr, int npc, float gref,
+                         const float* __restrict__ bsum, int R, int C, const float* __restrict__ score1, int ld1,
+                         const float* __restrict__ score2, int ld2, float* __restrict__ rml,
+                         float* __restrict__ rmul, float* __restrict__ cml, float* __restrict__ cmul) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= R + C) return;
+  const bool is_row = i < R;
+  const int k = is_row ? i : i - R;
+  const float* A = atten + (size_t)b * R * C;
+  float sc = 1.f, s;
+  if (is_row) { if (k > 0 && score1) sc = score1[(size_t)b * ld1 + k - 1]; }
+  else if (k > 0 && score2) sc = score2[(size_t)b * ld2 + k - 1];
+  if (k == 0) {
+    s = bsum[b * 2 + (is_row ? 0 : 1)];
+  } else {
+    const float* p = is_row ? rowpart + ((size_t)b * R + k) * npr : colpart + ((size_t)b * C + k) * npc;
+    const int n = is_row ? npr : npc;
+    s = ex2_approx(fmaf(is_row ? A[(size_t)k * C] : A[k], kL2E, -gref));   // the background column / row entry
+    for (int q = 0; q < n; ++q) s += p[q];
+  }
+  if (is_row) { rml[(size_t)b * R + k] = gref; rmul[(size_t)b * R + k] = sc / s; }
+  else { cml[(size_t)b * C + k] = gref; cmul[(size_t)b * C + k] = sc / s; }
+}
+
 // ------------------------------------------------------------------ passes 2 and 3: shared pieces
 struct ColConst2 {
   unsigned long long ncml[F2_CPT / 2];  // packed -cml_j
@@ -586,6 +634,23 @@ int run_fine_labels2(const float* atten, const float* score1, int ld1, const flo
   k_fine_stats<<<grid, F2_THREADS, 0, st>>>(atten, g.R, g.C, f.nstrip, f.nrt, ws.rowpart, ws.colpart, ws.flags);
   k_fine_stats_merge<<<mg, 256, 0, st>>>(atten, ws.rowpart, ws.colpart, g.R, g.C, f.nstrip, f.nrt, score1, ld1,
                                          score2, ld2, ws.flags, ws.rmax, ws.rsum, ws.cmax, ws.csum);
+  k_fine_labels<<<grid, F2_THREADS, 0, st>>>(atten, g.R, g.C, f.nstrip, f.nrt, ws.rmax, ws.rsum, ws.cmax, ws.csum,
+                                             ws.rowpm, ws.colpm, ws.ai0, ws.a0j);
+  count_launch(3);
+  return launch_labels_merge(ws.rowpm, ws.colpm, ws.ai0, ws.a0j, b, g.R, g.C, f.nrt, f.nstrip, w1, w2, st);
+}
+
+int run_fine_labels2_fused(const float* atten, const float* stats, float temp, const float* score1, int ld1,
+                           const float* score2, int ld2, int b, const AssignGeom& g, const AssignWs& ws, float* w1,
+                           float* w2, cudaStream_t st) {
+  const FineGeom2 f = fine_geom2(g.R, g.C);
+  const SimStatsGeom sg = sim_stats_geom(b, g.R, g.C);
+  const float gref = sim_stats_gref(temp);
+  const dim3 grid(f.nstrip, f.nrt, b);
+  const dim3 mg(ceil_div(g.R + g.C, 256), b);
+  k_fine_border_sums<<<b, 256, 0, st>>>(atten, g.R, g.C, gref, ws.bsum);
+  k_fine_stats_merge_fused<<<mg, 256, 0, st>>>(atten, stats, stats + sg.col_off_floats, sg.npr, sg.npc, gref, ws.bsum,
+                                               g.R, g.C, score1, ld1, score2, ld2, ws.rmax, ws.rsum, ws.cmax, ws.csum);
   k_fine_labels<<<grid, F2_THREADS, 0, st>>>(atten, g.R, g.C, f.nstrip, f.nrt, ws.rmax, ws.rsum, ws.cmax, ws.csum,
                                              ws.rowpm, ws.colpm, ws.ai0, ws.a0j);
   count_launch(3);

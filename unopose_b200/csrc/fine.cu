@@ -229,10 +229,12 @@ int upk_weighted_procrustes(const float* src, const float* ref, const float* wei
   UPK_RETURN_LAST_ERROR();
 }
 
-int upk_fine_pose(const float* atten, const float* score1, int score1_ld, const float* score2, int score2_ld,
-                  const float* pts1, const float* pts2, const float* model_pts, int n_model, int b, int n1,
-                  int n2, float dis_thres, float weight_thresh, void* workspace, size_t workspace_bytes,
-                  float* R_out, float* t_out, float* score_out, const upk_fine_debug* dbg, upk_stream_t stream) {
+static int fine_pose_impl(const float* atten, const float* stats, size_t stats_bytes, float temp,
+                          const float* score1, int score1_ld, const float* score2, int score2_ld,
+                          const float* pts1, const float* pts2, const float* model_pts, int n_model, int b, int n1,
+                          int n2, float dis_thres, float weight_thresh, void* workspace, size_t workspace_bytes,
+                          float* R_out, float* t_out, float* score_out, const upk_fine_debug* dbg,
+                          upk_stream_t stream) {
   if (b < 0 || n1 <= 0 || n2 <= 0) return UPK_ERR_INVALID_ARG;
   if (b == 0) return UPK_OK;
   if (!atten || !pts1 || !pts2 || !workspace || !R_out || !t_out || !score_out) return UPK_ERR_INVALID_ARG;
@@ -245,7 +247,13 @@ int upk_fine_pose(const float* atten, const float* score1, int score1_ld, const 
   if (cv.bytes() > workspace_bytes) return UPK_ERR_INVALID_ARG;
   if (!model_pts) { model_pts = pts2; n_model = n2; }
   int rc;
-  if ((rc = run_assignment_labels(atten, score1, score1_ld, score2, score2_ld, b, g, w.a, w.w1, w.w2, st))) return rc;
+  if (stats) {   // pass 1 came out of the similarity GEMM's epilogue (upk_feature_similarity_stats)
+    if (g.TR == 32 || stats_bytes < sim_stats_geom(b, n1 + 1, n2 + 1).total_bytes || !(temp > 0.f)) return UPK_ERR_INVALID_ARG;
+    rc = run_fine_labels2_fused(atten, stats, temp, score1, score1_ld, score2, score2_ld, b, g, w.a, w.w1, w.w2, st);
+  } else {
+    rc = run_assignment_labels(atten, score1, score1_ld, score2, score2_ld, b, g, w.a, w.w1, w.w2, st);
+  }
+  if (rc) return rc;
   if ((rc = run_fine_rowsums(atten, score1, score1_ld, score2, score2_ld, b, g, w.a, w.w1, w.w2, pts2,
                              w.rowpart4, w.soft, w.asum, st)))
     return rc;
@@ -262,6 +270,27 @@ int upk_fine_pose(const float* atten, const float* score1, int score1_ld, const 
     if (dbg->asum) UPK_CUDA_TRY(cudaMemcpyAsync(dbg->asum, w.asum, sizeof(float) * (size_t)b * n1, cudaMemcpyDeviceToDevice, st));
   }
   UPK_RETURN_LAST_ERROR();
+}
+
+int upk_fine_pose(const float* atten, const float* score1, int score1_ld, const float* score2, int score2_ld,
+                  const float* pts1, const float* pts2, const float* model_pts, int n_model, int b, int n1,
+                  int n2, float dis_thres, float weight_thresh, void* workspace, size_t workspace_bytes,
+                  float* R_out, float* t_out, float* score_out, const upk_fine_debug* dbg, upk_stream_t stream) {
+  return fine_pose_impl(atten, nullptr, 0, 0.f, score1, score1_ld, score2, score2_ld, pts1, pts2, model_pts, n_model,
+                        b, n1, n2, dis_thres, weight_thresh, workspace, workspace_bytes, R_out, t_out, score_out, dbg,
+                        stream);
+}
+
+int upk_fine_pose_stats(const float* atten, const float* stats, size_t stats_bytes, float temp,
+                        const float* score1, int score1_ld, const float* score2, int score2_ld,
+                        const float* pts1, const float* pts2, const float* model_pts, int n_model, int b, int n1,
+                        int n2, float dis_thres, float weight_thresh, void* workspace, size_t workspace_bytes,
+                        float* R_out, float* t_out, float* score_out, const upk_fine_debug* dbg,
+                        upk_stream_t stream) {
+  if (!stats) return UPK_ERR_INVALID_ARG;
+  return fine_pose_impl(atten, stats, stats_bytes, temp, score1, score1_ld, score2, score2_ld, pts1, pts2, model_pts,
+                        n_model, b, n1, n2, dis_thres, weight_thresh, workspace, workspace_bytes, R_out, t_out,
+                        score_out, dbg, stream);
 }
 
 int upk_transform_points(const float* pts, const float* R, const float* t, int b, int n, float* out,

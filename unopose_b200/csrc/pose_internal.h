@@ -42,6 +42,7 @@ struct AssignWs {
   float* colpm;     // [b][C][ntr]  partial col max of A over rows >= 1
   float* ai0;       // [b][R]  A[i][0]
   float* a0j;       // [b][C]  A[0][j]
+  float* bsum;      // [b][2] fused-statistics path: exponent sums of the background row / column
   int* flags;       // [b]  large geometry: pass 1's single-reference sums were not trustworthy -> exact redo
 };
 void carve_assign(Carver& cv, int b, const AssignGeom& g, AssignWs& ws);
@@ -85,6 +86,20 @@ int similarity_mode();  // 3 = 3xTF32 tcgen05 (default), 1 = 1xTF32 tcgen05, 0 =
 bool similarity_tc_eligible(int n, int m, int c);
 size_t similarity_tc_workspace_bytes(int b, int n, int m, int c);
 int run_similarity_tc(const float* f1, const float* f2, int b, int n, int m, int c, float temp, int normalize,
-                      int sim_type, void* workspace, size_t workspace_bytes, float* out, cudaStream_t st);
+                      int sim_type, void* workspace, size_t workspace_bytes, float* out, cudaStream_t st,
+                      float* stats_row = nullptr, float* stats_col = nullptr, float stats_gref = 0.f);
+
+// Exponent-sum partials produced by the similarity GEMM's epilogue (cosine logits; fused pass 1 of the fine
+// assignment): rowpart [b][n][npr] then colpart [b][m][npc] (256-byte aligned), all relative to the ONE
+// reference exponent sim_stats_gref(temp).
+struct SimStatsGeom {
+  int npr, npc;        // partials per row (2 per 256-column tile) / per column (4 per 128-row tile)
+  size_t row_floats, col_off_floats, total_bytes;
+};
+SimStatsGeom sim_stats_geom(int b, int n, int m);
+float sim_stats_gref(float temp);
+int run_fine_labels2_fused(const float* atten, const float* stats, float temp, const float* score1, int ld1,
+                           const float* score2, int ld2, int b, const AssignGeom& g, const AssignWs& ws, float* w1,
+                           float* w2, cudaStream_t st);
 
 }  // namespace upk

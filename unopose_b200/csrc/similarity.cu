@@ -165,4 +165,26 @@ int upk_feature_similarity(const float* feat1, const float* feat2, int b, int n,
   UPK_RETURN_LAST_ERROR();
 }
 
+size_t upk_similarity_stats_bytes(int b, int n, int m) {
+  if (b <= 0 || n <= 1 || m <= 1) return 0;
+  return sim_stats_geom(b, n, m).total_bytes;
+}
+
+int upk_feature_similarity_stats(const float* feat1, const float* feat2, int b, int n, int m, int c, float temp,
+                                 void* workspace, size_t workspace_bytes, float* atten_out, float* stats_out,
+                                 size_t stats_bytes, upk_stream_t stream) {
+  if (b < 0 || n <= 1 || m <= 1 || c <= 0 || !(temp > 0.f)) return UPK_ERR_INVALID_ARG;
+  if (b == 0) return UPK_OK;
+  const bool aligned16 = ((reinterpret_cast<uintptr_t>(feat1) | reinterpret_cast<uintptr_t>(feat2)) & 15) == 0;
+  if (!similarity_tc_eligible(n, m, c) || similarity_mode() != 3 || !aligned16) return UPK_ERR_UNSUPPORTED;
+  const SimStatsGeom sg = sim_stats_geom(b, n, m);
+  if (!stats_out || stats_bytes < sg.total_bytes || !workspace ||
+      workspace_bytes < similarity_tc_workspace_bytes(b, n, m, c))
+    return UPK_ERR_INVALID_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  UPK_CUDA_TRY(cudaMemsetAsync(stats_out, 0, sg.total_bytes, st));   // partials of ragged last tiles stay 0
+  return run_similarity_tc(feat1, feat2, b, n, m, c, temp, /*normalize=*/1, /*cosine*/0, workspace, workspace_bytes,
+                           atten_out, st, stats_out, stats_out + sg.col_off_floats, sim_stats_gref(temp));
+}
+
 }  // extern "C"

@@ -22,6 +22,7 @@
 
 #include "common.cuh"
 #include "launch_count.h"
+#include "pose_internal.h"
 #include "../../include/unopose_b200.h"
 
 namespace upk {
@@ -210,11 +211,18 @@ k_normalize_split(const float* __restrict__ x, int rows_per_batch, int c, int no
 }
 
 // ---------------------------------------------------------------- the GEMM
-template <int MODE, int NTERMS>  // MODE 0: dot/temp, 1: sqrt(clamp(2-2dot,0))/temp ; NTERMS 3 = 3xTF32, 1 = TF32
+// STATS (cosine logits only): the epilogue also produces pass 1 of the dual-softmax assignment, the sums of
+// exponentials per row and per column.  |logit| <= 1/temp, so ONE fixed reference exponent gref = log2e/temp (+ a
+// small margin) serves every row and column: e = 2^(v log2e - gref) <= 1, >= 2^(-2 log2e/temp).  Row sums are
+// thread-local at TMEM-load time (a thread holds 32 columns of its row), column sums are thread-local at store time
+// (a lane then walks the 32 rows of its column through the transpose buffer); no shuffles, no atomics:
+//   rowpart[(b*M + row) * (2 nt) + 2 ni + half]   colpart[(b*N + col) * (4 mt) + 4 mi + q]
+template <int MODE, int NTERMS, bool STATS = false>  // MODE 0: dot/temp, 1: sqrt(clamp(2-2dot,0))/temp ; NTERMS 3 = 3xTF32, 1 = TF32
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_similarity_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-                int batch, int M, int N, int K, float temp, int off, float* __restrict__ C) {
+                int batch, int M, int N, int K, float temp, int off, float* __restrict__ C,
+                float* __restrict__ rowpart, float* __restrict__ colpart, float gref) {
   // `off` (0 or 1): the tiles cover rows/columns [off, M) x [off, N); with off = 1 the background row 0 and
   // column 0 are produced by k_similarity_border, so the 2049 x 2049 fine shape is exactly 16 x 8 tiles
   extern __shared__ unsigned char smem_raw[];
@@ -316,6 +324,7 @@ k_similarity_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
       const int row0 = off + mi * TC_BM + q * 32;
       const int nrows = min(32, M - row0);
       float* Cb = C + ((size_t)b * M + row0) * N;
+      float rsum = 0.f;   // STATS: this thread's row (row0 + lane), its 128 columns of the tile
 #pragma unroll 1
       for (int cb = half * 4; cb < half * 4 + 4; ++cb) {
         const int col0 = off + ni * TC_BN + cb * 32;
@@ -326,21 +335,46 @@ k_similarity_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         for (int j = 0; j < 32; ++j) {
           float v = __uint_as_float(r[j]);
           if (MODE == 1) v = sqrtf(fmaxf(2.0f - 2.0f * v, 0.f));
-          tr[lane * 33 + j] = v * inv_temp;
+          v *= inv_temp;
+          tr[lane * 33 + j] = v;
+          if (STATS) {
+            float e;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(v, 1.4426950408889634f, -gref)));
+            rsum += (col0 + j < N) ? e : 0.f;
+          }
         }
         __syncwarp();
         if (col0 + lane < N && nrows > 0) {
           float* dst = Cb + col0 + lane;
           const float* src = tr + lane;
+          float csum = 0.f;   // STATS: this lane's column (col0 + lane), the 32 rows of this warp
           if (nrows == 32) {
 #pragma unroll
-            for (int rr = 0; rr < 32; ++rr) dst[(size_t)rr * N] = src[rr * 33];
+            for (int rr = 0; rr < 32; ++rr) {
+              const float v = src[rr * 33];
+              dst[(size_t)rr * N] = v;
+              if (STATS) {
+                float e;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(v, 1.4426950408889634f, -gref)));
+                csum += e;
+              }
+            }
           } else {
-            for (int rr = 0; rr < nrows; ++rr) dst[(size_t)rr * N] = src[rr * 33];
+            for (int rr = 0; rr < nrows; ++rr) {
+              const float v = src[rr * 33];
+              dst[(size_t)rr * N] = v;
+              if (STATS) {
+                float e;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(v, 1.4426950408889634f, -gref)));
+                csum += e;
+              }
+            }
           }
+          if (STATS) colpart[((size_t)b * N + col0 + lane) * (4 * mt) + 4 * mi + q] = csum;
         }
         __syncwarp();
       }
+      if (STATS && lane < nrows) rowpart[((size_t)b * M + row0 + lane) * (2 * nt) + 2 * ni + half] = rsum;
       tc_fence_before();
       if (lane == 0) mbar_arrive(&sm.tempty[acc]);
     }
@@ -401,13 +435,29 @@ size_t similarity_tc_workspace_bytes(int b, int n, int m, int c) {
   return 2 * a + 2 * bb + 1024;
 }
 
+SimStatsGeom sim_stats_geom(int b, int n, int m) {
+  SimStatsGeom g;
+  g.npr = 2 * ((m - 1 + TC_BN - 1) / TC_BN);
+  g.npc = 4 * ((n - 1 + TC_BM - 1) / TC_BM);
+  g.row_floats = (size_t)b * n * g.npr;
+  g.col_off_floats = (g.row_floats + 63) & ~(size_t)63;
+  g.total_bytes = (g.col_off_floats + (size_t)b * m * g.npc) * sizeof(float);
+  return g;
+}
+
+// reference exponent (log2 units) of the fused statistics: |cosine| <= 1 up to rounding, so v log2e <= gref
+float sim_stats_gref(float temp) { return 1.4426950408889634f / temp + 0.01f; }
+
 bool similarity_tc_eligible(int n, int m, int c) {
   return similarity_mode() != 0 && c % TC_BK == 0 && c >= TC_BK && (long long)n * m >= 128LL * 128LL &&
          get_encode() != nullptr;
 }
 
+// stats_row / stats_col (optional, both or neither; requires sim_type 0 and that the tiles start at (1,1)):
+// per-tile partial sums of 2^(v log2e - stats_gref), layouts of SimStatsGeom.
 int run_similarity_tc(const float* f1, const float* f2, int b, int n, int m, int c, float temp, int normalize,
-                      int sim_type, void* workspace, size_t workspace_bytes, float* out, cudaStream_t st) {
+                      int sim_type, void* workspace, size_t workspace_bytes, float* out, cudaStream_t st,
+                      float* stats_row, float* stats_col, float stats_gref) {
   if (workspace_bytes < similarity_tc_workspace_bytes(b, n, m, c)) return UPK_ERR_INVALID_ARG;
   char* w = (char*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
   size_t a = (((size_t)b * n * c * sizeof(float)) + 1023) & ~(size_t)1023;
@@ -420,7 +470,8 @@ int run_similarity_tc(const float* f1, const float* f2, int b, int n, int m, int
   // peeled entries are produced by the operand-preparation kernels
   const int tiles0 = ((n + TC_BM - 1) / TC_BM) * ((m + TC_BN - 1) / TC_BN);
   const int tiles1 = ((n - 1 + TC_BM - 1) / TC_BM) * ((m - 1 + TC_BN - 1) / TC_BN);
-  const int off = (n > 1 && m > 1 && tiles1 < tiles0) ? 1 : 0;
+  const int off = (n > 1 && m > 1 && (tiles1 < tiles0 || stats_row)) ? 1 : 0;   // the statistics assume the peel
+  if (stats_row && (!off || sim_type != 0 || !stats_col)) return UPK_ERR_UNSUPPORTED;
   const dim3 g1((n + 7) / 8, b), g2((m + 7) / 8, b);
   const size_t qs = off ? (size_t)c * sizeof(float) : 0;
   if (sim_type == 0) {
@@ -444,16 +495,19 @@ int run_similarity_tc(const float* f1, const float* f2, int b, int n, int m, int
   const int grid = tiles < sms ? tiles : sms;
   const size_t smem = sizeof(TcSmem) + 1024;
   const int terms = similarity_mode() == 1 ? 1 : 3;
-#define UPK_LAUNCH_TC(MODE, NT)                                                                              \
+#define UPK_LAUNCH_TC(MODE, NT, ST)                                                                          \
   do {                                                                                                       \
-    auto kern = k_similarity_tc<MODE, NT>;                                                                   \
+    auto kern = k_similarity_tc<MODE, NT, ST>;                                                               \
     UPK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
-    kern<<<grid, TC_THREADS, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, b, n, m, c, temp, off, out);            \
+    kern<<<grid, TC_THREADS, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, b, n, m, c, temp, off, out, stats_row,  \
+                                         stats_col, stats_gref);                                             \
   } while (0)
-  if (sim_type == 0) {
-    if (terms == 3) UPK_LAUNCH_TC(0, 3); else UPK_LAUNCH_TC(0, 1);
+  if (stats_row) {   // cosine logits + fused exponent sums (3xTF32 only: the statistics need fp32-level logits)
+    UPK_LAUNCH_TC(0, 3, true);
+  } else if (sim_type == 0) {
+    if (terms == 3) UPK_LAUNCH_TC(0, 3, false); else UPK_LAUNCH_TC(0, 1, false);
   } else {
-    if (terms == 3) UPK_LAUNCH_TC(1, 3); else UPK_LAUNCH_TC(1, 1);
+    if (terms == 3) UPK_LAUNCH_TC(1, 3, false); else UPK_LAUNCH_TC(1, 1, false);
   }
 #undef UPK_LAUNCH_TC
   count_launch();

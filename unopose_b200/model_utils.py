@@ -31,8 +31,23 @@ def _workspace(nbytes, device):
 
 
 # --------------------------------------------------------------------------- a1
-def compute_feature_similarity(feat1, feat2, type="cosine", temp=1.0, normalize_feat=True):
-    """(B,N,C),(B,M,C) -> (B,N,M).  Reference: model_utils.py:260-282."""
+class SimilarityStats:
+    """Exponent sums emitted by the similarity GEMM's epilogue for `compute_fine_Rt[_overlap](..., stats=)`:
+    valid only for the atten tensor they were produced with (same values, same temp)."""
+
+    __slots__ = ("buf", "temp", "shape")
+
+    def __init__(self, buf, temp, shape):
+        self.buf, self.temp, self.shape = buf, float(temp), tuple(shape)
+
+
+def compute_feature_similarity(feat1, feat2, type="cosine", temp=1.0, normalize_feat=True, return_stats=False):
+    """(B,N,C),(B,M,C) -> (B,N,M).  Reference: model_utils.py:260-282.
+
+    return_stats=True (extension): -> (atten, stats); for normalised cosine logits on the tensor-core path the
+    GEMM epilogue also emits the exponent sums of the dual-softmax assignment, which
+    `compute_fine_Rt[_overlap](atten, ..., stats=stats)` consumes instead of a first pass over `atten`
+    (stats is None when the fused path does not apply)."""
     if type not in ("cosine", "L2"):
         raise AssertionError(type)
     _need_cuda(feat1, "compute_feature_similarity")
@@ -43,11 +58,21 @@ def compute_feature_similarity(feat1, feat2, type="cosine", temp=1.0, normalize_
     out = torch.empty((b, n, m), dtype=torch.float32, device=f1.device)
     nbytes = lib.upk_feature_similarity_workspace_bytes(b, n, m, c, int(bool(normalize_feat)))
     ws = _workspace(nbytes, f1.device)
+    if return_stats and type == "cosine" and normalize_feat and b > 0 and n * m > 512 * 512:
+        sbytes = lib.upk_similarity_stats_bytes(b, n, m)
+        buf = torch.empty(max(int(sbytes) // 4, 1), dtype=torch.float32, device=f1.device)
+        with torch.cuda.device(f1.device):
+            rc = lib.upk_feature_similarity_stats(L.ptr(f1), L.ptr(f2), b, n, m, c, float(temp), L.ptr(ws), ws.numel(),
+                                                  L.ptr(out), L.ptr(buf), buf.numel() * 4, L.stream_ptr(f1))
+        if rc == 0:
+            return out, SimilarityStats(buf, temp, (b, n, m))
+        if rc != -2:                       # anything but "unsupported here": a real failure
+            L.check(rc, "feature_similarity_stats")
     with torch.cuda.device(f1.device):
         L.check(lib.upk_feature_similarity(L.ptr(f1), L.ptr(f2), b, n, m, c, float(temp), int(bool(normalize_feat)),
                                            0 if type == "cosine" else 1, L.ptr(ws), ws.numel(), L.ptr(out),
                                            L.stream_ptr(f1)), "feature_similarity")
-    return out
+    return (out, None) if return_stats else out
 
 
 def pairwise_distance(x, y, normalized=False, channel_first=False):
@@ -138,7 +163,7 @@ def compute_coarse_Rt_overlap(atten, score, pts1, pts2, model_pts=None, n_propos
 
 
 # --------------------------------------------------------------------------- a8
-def _fine(atten, score, pts1, pts2, model_pts, dis_thres, weight_thresh, return_debug=False):
+def _fine(atten, score, pts1, pts2, model_pts, dis_thres, weight_thresh, return_debug=False, stats=None):
     _need_cuda(pts1, "compute_fine_Rt")
     B, N1 = pts1.shape[:2]
     N2 = pts2.shape[1]
@@ -169,25 +194,33 @@ def _fine(atten, score, pts1, pts2, model_pts, dis_thres, weight_thresh, return_
                      soft=torch.empty((B, N1, 3), device=dev), asum=torch.empty((B, N1), device=dev),
                      nn=torch.empty((B, N1), device=dev))
         dbg = L.FineDebug(**{k: v.data_ptr() for k, v in dbg_t.items()})
-    with torch.cuda.device(dev):
-        L.check(lib.upk_fine_pose(
-            L.ptr(atten), L.ptr(s1), ld, (s2.data_ptr() if s2 is not None else None), ld,
+    tail = (L.ptr(s1), ld, (s2.data_ptr() if s2 is not None else None), ld,
             L.ptr(pts1), L.ptr(pts2), L.ptr(model_pts), n_model, B, N1, N2, float(dis_thres),
             float(weight_thresh), L.ptr(ws), ws.numel(), L.ptr(R), L.ptr(t), L.ptr(sc),
-            ctypes.addressof(dbg) if dbg is not None else None, L.stream_ptr(pts1)), "fine_pose")
+            ctypes.addressof(dbg) if dbg is not None else None, L.stream_ptr(pts1))
+    with torch.cuda.device(dev):
+        if stats is not None:
+            if stats.shape != (B, N1 + 1, N2 + 1):
+                raise RuntimeError("compute_fine_Rt: stats belong to a different atten tensor")
+            L.check(lib.upk_fine_pose_stats(L.ptr(atten), L.ptr(stats.buf), stats.buf.numel() * 4, stats.temp, *tail),
+                    "fine_pose_stats")
+        else:
+            L.check(lib.upk_fine_pose(L.ptr(atten), *tail), "fine_pose")
     if return_debug:
         return R, t, sc, dbg_t
     return R, t, sc
 
 
-def compute_fine_Rt(atten, pts1, pts2, model_pts=None, dis_thres=0.15):
-    """Reference: model_utils.py:493-524 (weight_thresh 0.0)."""
-    return _fine(atten, None, pts1, pts2, model_pts, dis_thres, 0.0)
+def compute_fine_Rt(atten, pts1, pts2, model_pts=None, dis_thres=0.15, stats=None):
+    """Reference: model_utils.py:493-524 (weight_thresh 0.0).  `stats`: see compute_feature_similarity."""
+    return _fine(atten, None, pts1, pts2, model_pts, dis_thres, 0.0, stats=stats)
 
 
-def compute_fine_Rt_overlap(atten, score, pts1, pts2, model_pts=None, dis_thres=0.15):
-    """Reference: model_utils.py:527-566 (weight_thresh 0.001; the variant the model calls, fine module :120)."""
-    return _fine(atten, score, pts1, pts2, model_pts, dis_thres, 0.001)
+def compute_fine_Rt_overlap(atten, score, pts1, pts2, model_pts=None, dis_thres=0.15, stats=None):
+    """Reference: model_utils.py:527-566 (weight_thresh 0.001; the variant the model calls, fine module :120).
+    `stats` (extension): the SimilarityStats returned with THIS atten by compute_feature_similarity(...,
+    return_stats=True); the solve then reads atten twice instead of three times."""
+    return _fine(atten, score, pts1, pts2, model_pts, dis_thres, 0.001, stats=stats)
 
 
 def transform_points(pts, R, t):

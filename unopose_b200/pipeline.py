@@ -133,11 +133,13 @@ def run_hot_path(inp, cfg=HotPathConfig(), stages=None, overlap=True):
         pe_geometry("r", out["tem_sub"])
 
     def s_fine_sim():
-        out["f_atten"] = MU.compute_feature_similarity(inp["f_f1"], inp["f_f2"], "cosine", cfg.temp, True)
+        # the GEMM epilogue also emits the exponent sums of the fine assignment (fused pass 1)
+        out["f_atten"], out["f_stats"] = MU.compute_feature_similarity(inp["f_f1"], inp["f_f2"], "cosine", cfg.temp, True,
+                                                                       return_stats=True)
 
     def s_fine_pose():
         out["pred_R"], out["pred_t"], out["pred_pose_score"] = MU.compute_fine_Rt_overlap(
-            out["f_atten"], inp["f_score"], inp["f_pts1"], inp["f_pts2"], None, cfg.dis_thres)
+            out["f_atten"], inp["f_score"], inp["f_pts1"], inp["f_pts2"], None, cfg.dis_thres, stats=out.get("f_stats"))
 
     ref_chain = [("fps_template+gather", s_template), ("fps_sparse_ref+gather", s_sparse_r),
                  ("ball_query+group_ref", s_pe_r)]
