@@ -44,6 +44,7 @@ def main():
     idx256 = X.ball_query(pts, pts, 0.2, 256)
     c_att = MU.compute_feature_similarity(inp["c_f1"], inp["c_f2"], "cosine", cfg.temp, True)
     f_att = MU.compute_feature_similarity(inp["f_f1"], inp["f_f2"], "cosine", cfg.temp, True)
+    f_att2, f_stats = MU.compute_feature_similarity(inp["f_f1"], inp["f_f2"], "cosine", cfg.temp, True, return_stats=True)
     ops = {
         "fps5000": lambda: X.furthest_point_sampling(tem, 2048),
         "fps2048": lambda: X.furthest_point_sampling(pts, 196),
@@ -59,6 +60,10 @@ def main():
                                                       cfg.n_proposal1, cfg.n_proposal2),
         "fpose": lambda: MU.compute_fine_Rt_overlap(f_att, inp["f_score"], inp["f_pts1"], inp["f_pts2"], None,
                                                     cfg.dis_thres),
+        "fsim_stats": lambda: MU.compute_feature_similarity(inp["f_f1"], inp["f_f2"], "cosine", cfg.temp, True,
+                                                            return_stats=True),
+        "fpose_stats": lambda: MU.compute_fine_Rt_overlap(f_att2, inp["f_score"], inp["f_pts1"], inp["f_pts2"], None,
+                                                          cfg.dis_thres, stats=f_stats),
     }
     sel = [s for s in a.only.split(",") if s] or list(ops)
     for name in sel:

@@ -407,3 +407,16 @@ def test_fused_similarity_stats_path(cuda, n1, n2, c):
     assert s2 is None and a2.shape == (B, 200, 200)
     with pytest.raises(RuntimeError):
         MU().compute_fine_Rt_overlap(atten[:, :-1], score, p1[:, :-1], p2, stats=stats)
+
+
+def test_coarse_large_geometry(cuda):
+    """A coarse solve on a geometry above the small-tile limit (600 x 600 > 512^2): exact tile pipeline at 64 x 256."""
+    B, n, H, K = 2, 600, 2000, 100
+    d = batch(900, B, n, 64, cuda)
+    atten = PO.feature_similarity(d["f1"], d["f2"], "cosine", 0.1, True)
+    u = torch.rand(B, 3 * H, generator=torch.Generator().manual_seed(1)).to(cuda)
+    R, t, s, m = MU()._coarse(atten, d["score"], d["pts1"], d["pts2"], None, H, K, u=u, return_debug=True)
+    Ro, to, so, o = PO.coarse_pose(atten, d["score"], d["pts1"], d["pts2"], None, H, K, u=u, debug=True)
+    assert torch.equal(m["w1"], o["w1"]) and torch.equal(m["w2"], o["w2"])
+    assert torch.allclose(m["cdf"], o["cdf"], rtol=5e-5, atol=1e-7)
+    assert PO.rotation_geodesic_deg(R, d["R"]).max() < 3.0

@@ -437,10 +437,12 @@ static int stats_labels_t(const float* atten, const float* score1, int ld1, cons
 
 int run_assignment_labels(const float* atten, const float* score1, int ld1, const float* score2, int ld2,
                           int b, const AssignGeom& g, const AssignWs& ws, float* w1, float* w2,
-                          cudaStream_t st) {
+                          cudaStream_t st, bool for_fine_solve) {
   if (g.TR == 32) return stats_labels_t<32, 128>(atten, score1, ld1, score2, ld2, b, g, ws, w1, w2, st);
-  // large geometry: the streaming passes of assign_fine.cu
-  return run_fine_labels2(atten, score1, ld1, score2, ld2, b, g, ws, w1, w2, st);
+  // large geometry, fine solve: the streaming passes of assign_fine.cu
+  if (for_fine_solve) return run_fine_labels2(atten, score1, ld1, score2, ld2, b, g, ws, w1, w2, st);
+  // large geometry, coarse solve (never the case at the UNOPose shapes): the exact tile pipeline at 64 x 256
+  return stats_labels_t<64, 256>(atten, score1, ld1, score2, ld2, b, g, ws, w1, w2, st);
 }
 
 int launch_labels_merge(const float* rowpm, const float* colpm, const float* ai0, const float* a0j, int b, int R,

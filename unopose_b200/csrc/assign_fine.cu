@@ -355,10 +355,12 @@ k_fine_stats_merge_fused(const float* __restrict__ atten, const float* __restric
   if (k == 0) {
     s = bsum[b * 2 + (is_row ? 0 : 1)];
   } else {
-    const float* p = is_row ? rowpart + ((size_t)b * R + k) * npr : colpart + ((size_t)b * C + k) * npc;
+    // partial-major layouts: consecutive threads read consecutive words
+    const float* p = is_row ? rowpart + (size_t)b * npr * R + k : colpart + (size_t)b * npc * C + k;
     const int n = is_row ? npr : npc;
+    const size_t step = is_row ? (size_t)R : (size_t)C;
     s = ex2_approx(fmaf(is_row ? A[(size_t)k * C] : A[k], kL2E, -gref));   // the background column / row entry
-    for (int q = 0; q < n; ++q) s += p[q];
+    for (int q = 0; q < n; ++q) s += p[q * step];
   }
   if (is_row) { rml[(size_t)b * R + k] = gref; rmul[(size_t)b * R + k] = sc / s; }
   else { cml[(size_t)b * C + k] = gref; cmul[(size_t)b * C + k] = sc / s; }

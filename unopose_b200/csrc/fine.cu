@@ -251,7 +251,7 @@ static int fine_pose_impl(const float* atten, const float* stats, size_t stats_b
     if (g.TR == 32 || stats_bytes < sim_stats_geom(b, n1 + 1, n2 + 1).total_bytes || !(temp > 0.f)) return UPK_ERR_INVALID_ARG;
     rc = run_fine_labels2_fused(atten, stats, temp, score1, score1_ld, score2, score2_ld, b, g, w.a, w.w1, w.w2, st);
   } else {
-    rc = run_assignment_labels(atten, score1, score1_ld, score2, score2_ld, b, g, w.a, w.w1, w.w2, st);
+    rc = run_assignment_labels(atten, score1, score1_ld, score2, score2_ld, b, g, w.a, w.w1, w.w2, st, true);
   }
   if (rc) return rc;
   if ((rc = run_fine_rowsums(atten, score1, score1_ld, score2, score2_ld, b, g, w.a, w.w1, w.w2, pts2,

@@ -47,10 +47,13 @@ struct AssignWs {
 };
 void carve_assign(Carver& cv, int b, const AssignGeom& g, AssignWs& ws);
 
-// stats + labels: fills ws.{rmax,rsum,cmax,csum} and w1 [b][R-1], w2 [b][C-1]
+// stats + labels: fills ws.{rmax,rsum,cmax,csum} and w1 [b][R-1], w2 [b][C-1].
+// for_fine_solve = false (the coarse solver): natural-log maxima / sums from the exact tile pipeline, which is what
+// run_coarse_P consumes.  for_fine_solve = true on a large geometry: the streaming passes of assign_fine.cu, which
+// leave log2-domain constants (rml, rmul, cml, cmul) in the same buffers for run_fine_rowsums.
 int run_assignment_labels(const float* atten, const float* score1, int ld1, const float* score2, int ld2,
                           int b, const AssignGeom& g, const AssignWs& ws, float* w1, float* w2,
-                          cudaStream_t st);
+                          cudaStream_t st, bool for_fine_solve = false);
 
 // coarse: P = (A w1 w2)^1.5 over the foreground block -> pmat [b][N1*N2], row-sum partials (double)
 int run_coarse_P(const float* atten, const float* score1, int ld1, const float* score2, int ld2, int b,
@@ -90,7 +93,7 @@ int run_similarity_tc(const float* f1, const float* f2, int b, int n, int m, int
                       float* stats_row = nullptr, float* stats_col = nullptr, float stats_gref = 0.f);
 
 // Exponent-sum partials produced by the similarity GEMM's epilogue (cosine logits; fused pass 1 of the fine
-// assignment): rowpart [b][n][npr] then colpart [b][m][npc] (256-byte aligned), all relative to the ONE
+// assignment): rowpart [b][npr][n] then colpart [b][npc][m] (256-byte aligned), all relative to the ONE
 // reference exponent sim_stats_gref(temp).
 struct SimStatsGeom {
   int npr, npc;        // partials per row (2 per 256-column tile) / per column (4 per 128-row tile)

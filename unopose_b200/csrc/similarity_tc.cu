@@ -216,7 +216,7 @@ k_normalize_split(const float* __restrict__ x, int rows_per_batch, int c, int no
 // small margin) serves every row and column: e = 2^(v log2e - gref) <= 1, >= 2^(-2 log2e/temp).  Row sums are
 // thread-local at TMEM-load time (a thread holds 32 columns of its row), column sums are thread-local at store time
 // (a lane then walks the 32 rows of its column through the transpose buffer); no shuffles, no atomics:
-//   rowpart[(b*M + row) * (2 nt) + 2 ni + half]   colpart[(b*N + col) * (4 mt) + 4 mi + q]
+//   rowpart[(b * 2 nt + 2 ni + half) * M + row]   colpart[(b * 4 mt + 4 mi + q) * N + col]   (partial-major: coalesced)
 template <int MODE, int NTERMS, bool STATS = false>  // MODE 0: dot/temp, 1: sqrt(clamp(2-2dot,0))/temp ; NTERMS 3 = 3xTF32, 1 = TF32
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_similarity_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -370,11 +370,11 @@ k_similarity_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
               }
             }
           }
-          if (STATS) colpart[((size_t)b * N + col0 + lane) * (4 * mt) + 4 * mi + q] = csum;
+          if (STATS) colpart[((size_t)b * (4 * mt) + 4 * mi + q) * N + col0 + lane] = csum;   // lanes: consecutive columns
         }
         __syncwarp();
       }
-      if (STATS && lane < nrows) rowpart[((size_t)b * M + row0 + lane) * (2 * nt) + 2 * ni + half] = rsum;
+      if (STATS && lane < nrows) rowpart[((size_t)b * (2 * nt) + 2 * ni + half) * M + row0 + lane] = rsum;  // consecutive rows
       tc_fence_before();
       if (lane == 0) mbar_arrive(&sm.tempty[acc]);
     }
