@@ -1,0 +1,33 @@
+"""CPU: the reference arm of bench.py (`--impl reference`, the oracle's CPU path on the host cores) prints one
+JSON line with the contract's keys; the product arm refuses to run without a GPU (no CPU fallback)."""
+import json
+import os
+import subprocess
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(*args):
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True, text=True,
+                          timeout=600, cwd=ROOT)
+
+
+def test_reference_arm_prints_contract_line():
+    r = _run("--impl", "reference", "--steps", "1", "--warmup", "1", "--cpu-sample", "1")
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "instances_posed_per_s" and line["unit"] == "instances/s"
+    assert line["value"] > 0 and line["higher_is_better"] is True and line["gpu_launches"] == 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    assert "workload" in line["config"]
+
+
+def test_product_arm_needs_a_gpu():
+    if torch.cuda.is_available():
+        return
+    r = _run("--steps", "1", "--warmup", "1")
+    assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
