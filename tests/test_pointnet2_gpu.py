@@ -221,3 +221,26 @@ def test_python_wrappers_autograd(cuda):
     assert qg(xyz, xyz).shape == (2, 3, 512, 16)
     ql = P.QueryAndLRFGroup(0.3, 16, use_xyz=True)
     assert ql(xyz, xyz, xyz.transpose(1, 2).contiguous()).shape == (2, 6, 512, 16)
+
+
+def test_ball_query_group_randomised_shapes(cuda):
+    """40 seeded random (n, m, radii, nsamples, cloud kind) cases of the fused kernel against the C oracle."""
+    rng = np.random.default_rng(2024)
+    for case in range(40):
+        n = int(rng.integers(1, 5200))
+        m = int(rng.integers(1, 700))
+        kind = "surface" if case % 2 else "ball"
+        nsc = int(rng.integers(1, 3))
+        scales = [(float(rng.uniform(0.02, 0.6)), int(rng.integers(1, 300))) for _ in range(nsc)]
+        xyz = batch_clouds(1000 + case, 2, n, kind)
+        if case % 5 == 0:                                    # quantised coordinates: many exact distance ties at r
+            xyz = (np.round(xyz * 8) / 8).astype(np.float32)
+            scales = [(0.125 * int(rng.integers(1, 4)), ns) for _, ns in scales]
+        q = np.ascontiguousarray(xyz[:, rng.integers(0, n, m)]) if case % 3 else np.ascontiguousarray(
+            batch_clouds(7 + case, 2, m, "ball"))
+        outs = _ext().ball_query_group(T(q, cuda), T(xyz, cuda), scales)
+        xyz_cf = np.ascontiguousarray(xyz.transpose(0, 2, 1))
+        for (r, ns), (idx, g) in zip(scales, outs):
+            exp = O.ball_query(q, xyz, r, ns)
+            assert np.array_equal(idx.cpu().numpy(), exp), (case, n, m, r, ns)
+            assert np.array_equal(g.cpu().numpy(), O.group_points(xyz_cf, exp)), (case, n, m, r, ns)
