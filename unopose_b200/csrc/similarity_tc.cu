@@ -229,6 +229,7 @@ k_similarity_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   TcSmem& sm = *reinterpret_cast<TcSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt = (M - off + TC_BM - 1) / TC_BM, nt = (N - off + TC_BN - 1) / TC_BN;
+  const int mts = 2 * ((M - off + 2 * TC_BM - 1) / (2 * TC_BM));   // statistics layout: 128-row tiles rounded to pairs
   const int total = batch * mt * nt;
   const int kchunks = K / TC_BK;
 
@@ -370,7 +371,7 @@ k_similarity_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
               }
             }
           }
-          if (STATS) colpart[((size_t)b * (4 * mt) + 4 * mi + q) * N + col0 + lane] = csum;   // lanes: consecutive columns
+          if (STATS) colpart[((size_t)b * (4 * mts) + 4 * mi + q) * N + col0 + lane] = csum;   // lanes: consecutive columns
         }
         __syncwarp();
       }
@@ -383,6 +384,214 @@ k_similarity_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// ---------------------------------------------------------------- the GEMM, CTA-pair version
+// tcgen05.mma.cta_group::2: the two CTAs of a cluster (one TPC) compute ONE 256 x 256 output tile.  Each CTA stages
+// its 128 rows of A and HALF of the B tile (128 of the 256 B rows); the MMA issued by the leader CTA reads both
+// halves from both shared memories and writes 128 accumulator rows into each CTA's TMEM.  Per K-chunk an SM now
+// pulls 32 KB of operands (A 16 KB + B/2 16 KB, hi + lo) instead of 48 KB for the same 128 x 256 outputs: the
+// single-CTA kernel is limited by SM <-> L2 traffic once its epilogue stores are added (profiles/, 62 % tensor pipe).
+// Protocol (CUTLASS sm100 2-SM pipelines): only the leader's `full` barriers are used, its producer posts
+// expect_tx for BOTH CTAs' bytes and both producers' TMA loads (.cta_group::2) complete on it; the leader's MMA
+// warp releases smem stages and publishes accumulators with multicast commits to both CTAs; both CTAs' epilogue
+// warps arrive on the leader's `tempty`.  cosine logits, 3xTF32 only.
+constexpr int TC2_STAGES = 5;                      // 32 KB per stage and CTA
+constexpr uint32_t TC2_STAGE_BYTES = 4 * TC_BM * TC_BK * 4;   // A_hi, A_lo, Bhalf_hi, Bhalf_lo: 4 x 8 KB
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;     // shared::cluster address of the same offset in CTA 0 of the pair
+
+struct __align__(1024) Tc2Smem {
+  float a_hi[TC2_STAGES][TC_BM * TC_BK];
+  float a_lo[TC2_STAGES][TC_BM * TC_BK];
+  float b_hi[TC2_STAGES][TC_BM * TC_BK];   // this CTA's half (128 rows) of the 256-row B tile
+  float b_lo[TC2_STAGES][TC_BM * TC_BK];
+  float epi[TC_EPI_WARPS][32][33];
+  unsigned long long full[TC2_STAGES], empty[TC2_STAGES], tfull[2], tempty[2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void tma_load_3d_2sm(const CUtensorMap* map, void* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((unsigned long long)map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(void* bar) {   // arrives on `bar` (same offset) in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((unsigned short)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  const uint32_t z = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(z) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(void* bar) {   // arrive on CTA 0's barrier at this offset
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// instruction descriptor of the pair: D=F32, A=B=TF32, K-major, N=256, M=256
+constexpr uint32_t kIdescTf32_2sm = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
+                                    ((uint32_t)((2 * TC_BM) >> 4) << 24);
+
+template <bool STATS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+k_similarity_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                 int batch, int M, int N, int K, float temp, int off, float* __restrict__ C,
+                 float* __restrict__ rowpart, float* __restrict__ colpart, float gref) {
+  extern __shared__ unsigned char smem_raw[];
+  Tc2Smem& sm = *reinterpret_cast<Tc2Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const bool leader = rank == 0;
+  const int mt2 = (M - off + 2 * TC_BM - 1) / (2 * TC_BM);    // 256-row tiles of the pair
+  const int mt = 2 * mt2;                                     // 128-row tiles (statistics layout)
+  const int nt = (N - off + TC_BN - 1) / TC_BN;
+  const int total = batch * mt2 * nt;
+  const int kchunks = K / TC_BK;
+  const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC2_STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&sm.tfull[a], 1); mbar_init(&sm.tempty[a], 2 * TC_EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {   // the same warp of both CTAs, same destination address
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // both CTAs' barriers exist before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = sm.tmem_base;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs) =====
+    int s = 0;
+    uint32_t ph = 0;
+    for (int t = cid; t < total; t += ncl) {
+      const int b = t / (mt2 * nt), rem = t - b * mt2 * nt;
+      const int mi2 = rem / nt, ni = rem - mi2 * nt;
+      const int arow = off + mi2 * 2 * TC_BM + (int)rank * TC_BM;
+      const int brow = off + ni * TC_BN + (int)rank * TC_BM;
+      for (int kc = 0; kc < kchunks; ++kc) {
+        mbar_wait(&sm.empty[s], ph ^ 1);
+        if (lane == 0) {
+          if (leader) mbar_expect_tx(&sm.full[s], 2 * TC2_STAGE_BYTES);   // both CTAs' loads land on this barrier
+          tma_load_3d_2sm(&map_a_hi, &sm.full[s], sm.a_hi[s], kc * TC_BK, arow, b);
+          tma_load_3d_2sm(&map_b_hi, &sm.full[s], sm.b_hi[s], kc * TC_BK, brow, b);
+          tma_load_3d_2sm(&map_a_lo, &sm.full[s], sm.a_lo[s], kc * TC_BK, arow, b);
+          tma_load_3d_2sm(&map_b_lo, &sm.full[s], sm.b_lo[s], kc * TC_BK, brow, b);
+        }
+        __syncwarp();
+        if (++s == TC2_STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (leader CTA only) =====
+    if (leader) {
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int t = cid; t < total; t += ncl, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_ph = (it >> 1) & 1;
+        mbar_wait(&sm.tempty[acc], acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * TC_BN;
+        for (int kc = 0; kc < kchunks; ++kc) {
+          mbar_wait(&sm.full[s], ph);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint64_t ahi = make_desc_sw128(sm.a_hi[s]), alo = make_desc_sw128(sm.a_lo[s]);
+            const uint64_t bhi = make_desc_sw128(sm.b_hi[s]), blo = make_desc_sw128(sm.b_lo[s]);
+#pragma unroll
+            for (int kk = 0; kk < TC_BK / 8; ++kk) {
+              const uint64_t adv = (uint64_t)(kk * 8 * 4 >> 4);
+              tc_mma_tf32_2sm(d_tmem, alo + adv, bhi + adv, kIdescTf32_2sm, (kc | kk) ? 1u : 0u);
+              tc_mma_tf32_2sm(d_tmem, ahi + adv, blo + adv, kIdescTf32_2sm, 1u);
+              tc_mma_tf32_2sm(d_tmem, ahi + adv, bhi + adv, kIdescTf32_2sm, 1u);
+            }
+            tc_commit_2sm(&sm.empty[s]);                          // stage reusable in both CTAs
+            if (kc == kchunks - 1) tc_commit_2sm(&sm.tfull[acc]);   // accumulators complete in both CTAs
+          }
+          __syncwarp();
+          if (++s == TC2_STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===== epilogue warps (both CTAs; this CTA's 128 rows of the 256-row tile) =====
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    float* tr = &sm.epi[warp - 2][0][0];
+    const float inv_temp = 1.0f / temp;
+    int it = 0;
+    for (int t = cid; t < total; t += ncl, ++it) {
+      const int b = t / (mt2 * nt), rem = t - b * mt2 * nt;
+      const int mi2 = rem / nt, ni = rem - mi2 * nt;
+      const int mi = 2 * mi2 + (int)rank;
+      const int acc = it & 1;
+      const uint32_t acc_ph = (it >> 1) & 1;
+      mbar_wait(&sm.tfull[acc], acc_ph);
+      tc_fence_after();
+      const int row0 = off + mi * TC_BM + q * 32;
+      const int nrows = min(32, M - row0);
+      float* Cb = C + ((size_t)b * M + row0) * N;
+      float rsum = 0.f;
+#pragma unroll 1
+      for (int cb = half * 4; cb < half * 4 + 4; ++cb) {
+        const int col0 = off + ni * TC_BN + cb * 32;
+        if (col0 >= N) break;
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + acc * TC_BN + cb * 32 + ((uint32_t)(q * 32) << 16), r);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float v = __uint_as_float(r[j]) * inv_temp;
+          tr[lane * 33 + j] = v;
+          if (STATS) {
+            float e;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(v, 1.4426950408889634f, -gref)));
+            rsum += (col0 + j < N) ? e : 0.f;
+          }
+        }
+        __syncwarp();
+        if (col0 + lane < N && nrows > 0) {
+          float* dst = Cb + col0 + lane;
+          const float* src = tr + lane;
+          float csum = 0.f;
+          for (int rr = 0; rr < nrows; ++rr) {
+            const float v = src[rr * 33];
+            dst[(size_t)rr * N] = v;
+            if (STATS) {
+              float e;
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(v, 1.4426950408889634f, -gref)));
+              csum += e;
+            }
+          }
+          if (STATS) colpart[((size_t)b * (4 * mt) + 4 * mi + q) * N + col0 + lane] = csum;
+        }
+        __syncwarp();
+      }
+      if (STATS && lane < nrows) rowpart[((size_t)b * (2 * nt) + 2 * ni + half) * M + row0 + lane] = rsum;
+      tc_fence_before();
+      if (lane == 0) mbar_arrive_leader(&sm.tempty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // nobody tears down while the peer may still signal or read
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
 }
 
@@ -438,7 +647,7 @@ size_t similarity_tc_workspace_bytes(int b, int n, int m, int c) {
 SimStatsGeom sim_stats_geom(int b, int n, int m) {
   SimStatsGeom g;
   g.npr = 2 * ((m - 1 + TC_BN - 1) / TC_BN);
-  g.npc = 4 * ((n - 1 + TC_BM - 1) / TC_BM);
+  g.npc = 4 * 2 * ((n - 1 + 2 * TC_BM - 1) / (2 * TC_BM));   // 4 per 128-row tile, tiles rounded up to CTA pairs
   g.row_floats = (size_t)b * n * g.npr;
   g.col_off_floats = (g.row_floats + 63) & ~(size_t)63;
   g.total_bytes = (g.col_off_floats + (size_t)b * m * g.npc) * sizeof(float);
@@ -488,6 +697,9 @@ int run_similarity_tc(const float* f1, const float* f2, int b, int n, int m, int
   if ((rc = make_map(&ma_lo, a_lo, b, n, c, TC_BM))) return rc;
   if ((rc = make_map(&mb_hi, b_hi, b, m, c, TC_BN))) return rc;
   if ((rc = make_map(&mb_lo, b_lo, b, m, c, TC_BN))) return rc;
+  // CTA-pair kernel (cosine, 3xTF32, enough tiles to fill the clusters; UPK_TC_2SM=0 disables it)
+  static int use_2sm = -1;
+  if (use_2sm < 0) { const char* e = getenv("UPK_TC_2SM"); use_2sm = e ? atoi(e) : 1; }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -502,7 +714,23 @@ int run_similarity_tc(const float* f1, const float* f2, int b, int n, int m, int
     kern<<<grid, TC_THREADS, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, b, n, m, c, temp, off, out, stats_row,  \
                                          stats_col, stats_gref);                                             \
   } while (0)
-  if (stats_row) {   // cosine logits + fused exponent sums (3xTF32 only: the statistics need fp32-level logits)
+  const int tiles2 = b * ((n - off + 2 * TC_BM - 1) / (2 * TC_BM)) * ((m - off + TC_BN - 1) / TC_BN);
+  if (use_2sm && sim_type == 0 && terms == 3 && tiles2 >= sms / 2) {
+    CUtensorMap mb_hi2, mb_lo2;   // the pair's CTAs each fetch 128 of the 256 B rows of a tile
+    if ((rc = make_map(&mb_hi2, b_hi, b, m, c, TC_BM))) return rc;
+    if ((rc = make_map(&mb_lo2, b_lo, b, m, c, TC_BM))) return rc;
+    const int grid2 = 2 * (tiles2 < sms / 2 ? tiles2 : sms / 2);
+    const size_t smem2 = sizeof(Tc2Smem) + 1024;
+    if (stats_row) {
+      UPK_CUDA_TRY(cudaFuncSetAttribute(k_similarity_tc2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      k_similarity_tc2<true><<<grid2, TC_THREADS, smem2, st>>>(ma_hi, ma_lo, mb_hi2, mb_lo2, b, n, m, c, temp, off, out,
+                                                              stats_row, stats_col, stats_gref);
+    } else {
+      UPK_CUDA_TRY(cudaFuncSetAttribute(k_similarity_tc2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      k_similarity_tc2<false><<<grid2, TC_THREADS, smem2, st>>>(ma_hi, ma_lo, mb_hi2, mb_lo2, b, n, m, c, temp, off, out,
+                                                               nullptr, nullptr, 0.f);
+    }
+  } else if (stats_row) {   // cosine logits + fused exponent sums (3xTF32 only: the statistics need fp32-level logits)
     UPK_LAUNCH_TC(0, 3, true);
   } else if (sim_type == 0) {
     if (terms == 3) UPK_LAUNCH_TC(0, 3, false); else UPK_LAUNCH_TC(0, 1, false);
