@@ -383,8 +383,8 @@ def main():
     pe_bytes = sum((12.0 * 2 * cfg.n_fine + 4.0 * cfg.n_fine * ns + 16.0 * cfg.n_fine * ns) for _, ns in cfg.pe) * B
     fps_ops = lambda n, m: 10.0 * (m - 1) * n * B   # 10 lane-ops per distance update
     models = {
-        "fine_similarity": ("k_similarity_tc<0,3,stats> (tcgen05 3xTF32, 2048x2048x256 tiles per instance, background row/column "
-                            "peeled, exponent sums of the assignment in the epilogue) + k_normalize_split x2",
+        "fine_similarity": ("k_similarity_tc2<stats> (tcgen05.mma.cta_group::2 3xTF32, CTA pairs on 256x256 tiles, background "
+                            "row/column peeled, exponent sums of the assignment in the epilogue) + k_normalize_split x2",
                             "tensor", 2.0 * n1 * n1 * cfg.feat_dim * B),
         "fine_pose": ("k_fine_labels + k_fine_rows (2 reads of the 2049^2 fp32 matrix; pass 1 = exponent sums, fused "
                       "into the similarity GEMM's epilogue) + Kabsch + inliers", "hbm", 2.0 * n1 * n1 * 4 * B),
