@@ -123,6 +123,8 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
 // background row / column of the output, i.e. its dot product with row 0 of the OTHER operand
 // (`other`, normalised on the fly with the same operations, so the values equal the split ones):
 //   first operand  (is_a = 1): C[b][row][0]      second operand (is_a = 0): C[b][0][row]
+constexpr int NS_RPW = 4;   // rows per warp -> 32 rows per CTA
+
 template <int MODE>
 __global__ void __launch_bounds__(256)
 k_normalize_split(const float* __restrict__ x, int rows_per_batch, int c, int normalize,
@@ -131,7 +133,6 @@ k_normalize_split(const float* __restrict__ x, int rows_per_batch, int c, int no
                   float temp, float* __restrict__ C, int M, int N) {
   extern __shared__ float s_q[];   // BORDER: the normalised row 0 of the other operand (c floats)
   const int bidx = blockIdx.y;
-  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (other) {
     const float* q = other + (size_t)bidx * other_rows_per_batch * c;
@@ -149,6 +150,10 @@ k_normalize_split(const float* __restrict__ x, int rows_per_batch, int c, int no
     for (int k = threadIdx.x; k < c; k += 256) s_q[k] = q[k] * qinv;
     __syncthreads();
   }
+  // NS_RPW rows per warp: the border prologue above (norm + staging of the other operand's row 0) is per CTA
+#pragma unroll 1
+  for (int rw = 0; rw < NS_RPW; ++rw) {
+  const int r = (blockIdx.x * 8 + (threadIdx.x >> 5)) * NS_RPW + rw;
   if (r >= rows_per_batch) return;
   const size_t row = (size_t)bidx * rows_per_batch + r;
   const float* p = x + row * c;
@@ -208,6 +213,7 @@ k_normalize_split(const float* __restrict__ x, int rows_per_batch, int c, int no
       if (is_a || r > 0) *o = dot * (1.0f / temp);   // C[0][0] is written once, by the first operand's row 0
     }
   }
+  }   // rows of this warp
 }
 
 // ---------------------------------------------------------------- the GEMM
@@ -681,7 +687,7 @@ int run_similarity_tc(const float* f1, const float* f2, int b, int n, int m, int
   const int tiles1 = ((n - 1 + TC_BM - 1) / TC_BM) * ((m - 1 + TC_BN - 1) / TC_BN);
   const int off = (n > 1 && m > 1 && (tiles1 < tiles0 || stats_row)) ? 1 : 0;   // the statistics assume the peel
   if (stats_row && (!off || sim_type != 0 || !stats_col)) return UPK_ERR_UNSUPPORTED;
-  const dim3 g1((n + 7) / 8, b), g2((m + 7) / 8, b);
+  const dim3 g1((n + 8 * NS_RPW - 1) / (8 * NS_RPW), b), g2((m + 8 * NS_RPW - 1) / (8 * NS_RPW), b);
   const size_t qs = off ? (size_t)c * sizeof(float) : 0;
   if (sim_type == 0) {
     k_normalize_split<0><<<g1, 256, qs, st>>>(f1, n, c, normalize, a_hi, a_lo, off ? f2 : nullptr, m, 1, temp, out, n, m);
