@@ -167,54 +167,60 @@ ball_group_kernel(const float* __restrict__ new_xyz, const float* __restrict__ x
       int* const row_i = STAGED ? row_o + ((out.ns + 3) & ~3) : (TWO ? idx_i + (size_t)j * in.ns : nullptr);
       const uint2 w2 = *reinterpret_cast<const uint2*>(s_mask + qi * BG_MPITCH + 2 * lane);
       const int kb = 64 * lane;  // tile-local index of bit 0 of my first word
+      // outer hits: slots from a warp prefix scan of the per-lane bit counts, emitted in ascending index;
+      // the inner radius is re-tested on each outer hit in the same loop (same expression, same operands)
+      const unsigned vo = (unsigned)(__popc(w2.x) + __popc(w2.y));
+      const unsigned incl_o = bg_incl_scan(vo, lane);
+      const unsigned tot_o = __shfl_sync(kFull, incl_o, 31);
       uint2 win = make_uint2(0u, 0u);
-      if (TWO) {
-        const float qx = -new_xyz[j * 3 + 0], qy = -new_xyz[j * 3 + 1], qz = -new_xyz[j * 3 + 2];
-        unsigned u = w2.x;
-        while (u) {
-          const int bit = __ffs(u) - 1;
-          u &= u - 1;
-          if (bg_d2(sx[kb + bit], sy[kb + bit], sz[kb + bit], qx, qy, qz) < in.r2) win.x |= 1u << bit;
-        }
-        u = w2.y;
-        while (u) {
-          const int bit = __ffs(u) - 1;
-          u &= u - 1;
-          if (bg_d2(sx[kb + 32 + bit], sy[kb + 32 + bit], sz[kb + 32 + bit], qx, qy, qz) < in.r2) win.y |= 1u << bit;
-        }
-      }
-      const unsigned v = (unsigned)(__popc(w2.x) + __popc(w2.y)) | ((unsigned)(__popc(win.x) + __popc(win.y)) << 16);
-      const unsigned incl = bg_incl_scan(v, lane);
-      const unsigned tot = __shfl_sync(kFull, incl, 31);
-      const unsigned excl = incl - v;
-      int first_o = 0, first_i = 0;
-      if (cnt_o == 0 && (tot & 0xffffu)) {  // first hit overall = lowest bit of the lowest lane that has one
-        const unsigned any = __ballot_sync(kFull, (w2.x | w2.y) != 0u);
-        const int mine = t0 + kb + (w2.x ? __ffs(w2.x) - 1 : 32 + __ffs(w2.y) - 1);
-        first_o = __shfl_sync(kFull, mine, __ffs(any) - 1);
-        if (!STAGED && lane == 0) s_first[0][qi] = first_o;
-      }
-      if (TWO && cnt_i == 0 && (tot >> 16)) {
-        const unsigned any = __ballot_sync(kFull, (win.x | win.y) != 0u);
-        const int mine = t0 + kb + (win.x ? __ffs(win.x) - 1 : 32 + __ffs(win.y) - 1);
-        first_i = __shfl_sync(kFull, mine, __ffs(any) - 1);
-        if (!STAGED && lane == 0) s_first[1][qi] = first_i;
-      }
-      int so = cnt_o + (int)(excl & 0xffffu), si = cnt_i + (int)(excl >> 16);
+      float qx = 0.f, qy = 0.f, qz = 0.f;
+      if (TWO) { qx = -new_xyz[j * 3 + 0]; qy = -new_xyz[j * 3 + 1]; qz = -new_xyz[j * 3 + 2]; }
+      int so = cnt_o + (int)(incl_o - vo);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         unsigned u = h ? w2.y : w2.x;
-        const unsigned ui = h ? win.y : win.x;
+        unsigned wi = 0u;
         while (u) {
           const int bit = __ffs(u) - 1;
           u &= u - 1;
-          const int k = t0 + kb + 32 * h + bit;
-          if (so < out.ns) row_o[so] = k;
+          const int kl = kb + 32 * h + bit;
+          if (so < out.ns) row_o[so] = t0 + kl;
           ++so;
-          if (TWO && ((ui >> bit) & 1u)) {
-            if (si < in.ns) row_i[si] = k;
+          if (TWO && bg_d2(sx[kl], sy[kl], sz[kl], qx, qy, qz) < in.r2) wi |= 1u << bit;
+        }
+        if (h) win.y = wi; else win.x = wi;
+      }
+      unsigned tot_i = 0u;
+      if (TWO) {
+        const unsigned vi = (unsigned)(__popc(win.x) + __popc(win.y));
+        const unsigned incl_i = bg_incl_scan(vi, lane);
+        tot_i = __shfl_sync(kFull, incl_i, 31);
+        int si = cnt_i + (int)(incl_i - vi);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          unsigned u = h ? win.y : win.x;
+          while (u) {
+            const int bit = __ffs(u) - 1;
+            u &= u - 1;
+            if (si < in.ns) row_i[si] = t0 + kb + 32 * h + bit;
             ++si;
           }
+        }
+      }
+      const unsigned tot = tot_o | (tot_i << 16);
+      int first_o = 0, first_i = 0;
+      if (!STAGED) {   // first hit overall = lowest bit of the lowest lane that has one (kept across tiles)
+        if (cnt_o == 0 && tot_o) {
+          const unsigned any = __ballot_sync(kFull, (w2.x | w2.y) != 0u);
+          const int mine = t0 + kb + (w2.x ? __ffs(w2.x) - 1 : 32 + __ffs(w2.y) - 1);
+          first_o = __shfl_sync(kFull, mine, __ffs(any) - 1);
+          if (lane == 0) s_first[0][qi] = first_o;
+        }
+        if (TWO && cnt_i == 0 && tot_i) {
+          const unsigned any = __ballot_sync(kFull, (win.x | win.y) != 0u);
+          const int mine = t0 + kb + (win.x ? __ffs(win.x) - 1 : 32 + __ffs(win.y) - 1);
+          first_i = __shfl_sync(kFull, mine, __ffs(any) - 1);
+          if (lane == 0) s_first[1][qi] = first_i;
         }
       }
       cnt_o += (int)(tot & 0xffffu);
@@ -228,6 +234,8 @@ ball_group_kernel(const float* __restrict__ new_xyz, const float* __restrict__ x
       }
       // ---- STAGED completion of this query: pad, write idx and the grouped rows with 128-bit stores
       __syncwarp();
+      first_o = row_o[0];   // slot 0 holds the first hit in ascending index (only read when cnt > 0)
+      if (TWO) first_i = row_i[0];
 #pragma unroll 1
       for (int sc = 0; sc < (TWO ? 2 : 1); ++sc) {
         const BgScale S = sc == 0 ? out : in;
