@@ -222,7 +222,7 @@ k_normalize_split(const float* __restrict__ x, int rows_per_batch, int c, int no
 // small margin) serves every row and column: e = 2^(v log2e - gref) <= 1, >= 2^(-2 log2e/temp).  Row sums are
 // thread-local at TMEM-load time (a thread holds 32 columns of its row), column sums are thread-local at store time
 // (a lane then walks the 32 rows of its column through the transpose buffer); no shuffles, no atomics:
-//   rowpart[(b * 2 nt + 2 ni + half) * M + row]   colpart[(b * 4 mt + 4 mi + q) * N + col]   (partial-major: coalesced)
+//   rowpart[(b * 4 nt + 4 ni + column slice) * M + row]   colpart[(b * 4 mt + 4 mi + q) * N + col]   (partial-major: coalesced)
 template <int MODE, int NTERMS, bool STATS = false>  // MODE 0: dot/temp, 1: sqrt(clamp(2-2dot,0))/temp ; NTERMS 3 = 3xTF32, 1 = TF32
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_similarity_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -381,7 +381,7 @@ k_similarity_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         }
         __syncwarp();
       }
-      if (STATS && lane < nrows) rowpart[((size_t)b * (2 * nt) + 2 * ni + half) * M + row0 + lane] = rsum;  // consecutive rows
+      if (STATS && lane < nrows) rowpart[((size_t)b * (4 * nt) + 4 * ni + 2 * half) * M + row0 + lane] = rsum;  // consecutive rows
       tc_fence_before();
       if (lane == 0) mbar_arrive(&sm.tempty[acc]);
     }
@@ -404,6 +404,9 @@ k_similarity_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 // warp releases smem stages and publishes accumulators with multicast commits to both CTAs; both CTAs' epilogue
 // warps arrive on the leader's `tempty`.  cosine logits, 3xTF32 only.
 constexpr int TC2_STAGES = 5;                      // 32 KB per stage and CTA
+constexpr int TC2_EPI_WARPS = 8;                   // EPI/4 warps per TMEM lane quarter, 256/(EPI/4) columns each (measured: 4 -> 166 us, 8 -> 146 us, 16 -> 160 us)
+constexpr int TC2_CPW = 32 / TC2_EPI_WARPS;        // 32-column chunks per epilogue warp and tile
+constexpr int TC2_THREADS = 64 + TC2_EPI_WARPS * 32;
 constexpr uint32_t TC2_STAGE_BYTES = 4 * TC_BM * TC_BK * 4;   // A_hi, A_lo, Bhalf_hi, Bhalf_lo: 4 x 8 KB
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;     // shared::cluster address of the same offset in CTA 0 of the pair
 
@@ -412,7 +415,7 @@ struct __align__(1024) Tc2Smem {
   float a_lo[TC2_STAGES][TC_BM * TC_BK];
   float b_hi[TC2_STAGES][TC_BM * TC_BK];   // this CTA's half (128 rows) of the 256-row B tile
   float b_lo[TC2_STAGES][TC_BM * TC_BK];
-  float epi[TC_EPI_WARPS][32][33];
+  float epi[TC2_EPI_WARPS][32][33];
   unsigned long long full[TC2_STAGES], empty[TC2_STAGES], tfull[2], tempty[2];
   uint32_t tmem_base;
 };
@@ -447,7 +450,7 @@ constexpr uint32_t kIdescTf32_2sm = (1u << 4) | (2u << 7) | (2u << 10) | ((uint3
                                     ((uint32_t)((2 * TC_BM) >> 4) << 24);
 
 template <bool STATS>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
 k_similarity_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                  const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                  int batch, int M, int N, int K, float temp, int off, float* __restrict__ C,
@@ -467,7 +470,7 @@ k_similarity_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC2_STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&sm.tfull[a], 1); mbar_init(&sm.tempty[a], 2 * TC_EPI_WARPS); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&sm.tfull[a], 1); mbar_init(&sm.tempty[a], 2 * TC2_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {   // the same warp of both CTAs, same destination address
@@ -538,7 +541,7 @@ k_similarity_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   } else {
     // ===== epilogue warps (both CTAs; this CTA's 128 rows of the 256-row tile) =====
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int cq = (warp - 2) >> 2;          // column slice of the tile handled by this warp
     float* tr = &sm.epi[warp - 2][0][0];
     const float inv_temp = 1.0f / temp;
     int it = 0;
@@ -555,7 +558,7 @@ k_similarity_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       float* Cb = C + ((size_t)b * M + row0) * N;
       float rsum = 0.f;
 #pragma unroll 1
-      for (int cb = half * 4; cb < half * 4 + 4; ++cb) {
+      for (int cb = cq * TC2_CPW; cb < cq * TC2_CPW + TC2_CPW; ++cb) {
         const int col0 = off + ni * TC_BN + cb * 32;
         if (col0 >= N) break;
         uint32_t r[32];
@@ -588,7 +591,7 @@ k_similarity_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         }
         __syncwarp();
       }
-      if (STATS && lane < nrows) rowpart[((size_t)b * (2 * nt) + 2 * ni + half) * M + row0 + lane] = rsum;
+      if (STATS && lane < nrows) rowpart[((size_t)b * (4 * nt) + 4 * ni + cq * (16 / TC2_EPI_WARPS)) * M + row0 + lane] = rsum;
       tc_fence_before();
       if (lane == 0) mbar_arrive_leader(&sm.tempty[acc]);
     }
@@ -652,7 +655,7 @@ size_t similarity_tc_workspace_bytes(int b, int n, int m, int c) {
 
 SimStatsGeom sim_stats_geom(int b, int n, int m) {
   SimStatsGeom g;
-  g.npr = 2 * ((m - 1 + TC_BN - 1) / TC_BN);
+  g.npr = 4 * ((m - 1 + TC_BN - 1) / TC_BN);   // up to 4 column slices per 256-column tile (the CTA-pair kernel's epilogue)
   g.npc = 4 * 2 * ((n - 1 + 2 * TC_BM - 1) / (2 * TC_BM));   // 4 per 128-row tile, tiles rounded up to CTA pairs
   g.row_floats = (size_t)b * n * g.npr;
   g.col_off_floats = (g.row_floats + 63) & ~(size_t)63;
@@ -729,11 +732,11 @@ int run_similarity_tc(const float* f1, const float* f2, int b, int n, int m, int
     const size_t smem2 = sizeof(Tc2Smem) + 1024;
     if (stats_row) {
       UPK_CUDA_TRY(cudaFuncSetAttribute(k_similarity_tc2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-      k_similarity_tc2<true><<<grid2, TC_THREADS, smem2, st>>>(ma_hi, ma_lo, mb_hi2, mb_lo2, b, n, m, c, temp, off, out,
+      k_similarity_tc2<true><<<grid2, TC2_THREADS, smem2, st>>>(ma_hi, ma_lo, mb_hi2, mb_lo2, b, n, m, c, temp, off, out,
                                                               stats_row, stats_col, stats_gref);
     } else {
       UPK_CUDA_TRY(cudaFuncSetAttribute(k_similarity_tc2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-      k_similarity_tc2<false><<<grid2, TC_THREADS, smem2, st>>>(ma_hi, ma_lo, mb_hi2, mb_lo2, b, n, m, c, temp, off, out,
+      k_similarity_tc2<false><<<grid2, TC2_THREADS, smem2, st>>>(ma_hi, ma_lo, mb_hi2, mb_lo2, b, n, m, c, temp, off, out,
                                                                nullptr, nullptr, 0.f);
     }
   } else if (stats_row) {   // cosine logits + fused exponent sums (3xTF32 only: the statistics need fp32-level logits)
