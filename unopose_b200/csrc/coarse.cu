@@ -237,47 +237,69 @@ k_topk_smallest(const float* __restrict__ vals, int H, int K, int* __restrict__ 
 // points per step with packed f32x2 arithmetic (4.5 issue slots per point pair); the (B*K,N1,N2) distance tensor never exists.
 constexpr int SC_THREADS = 224;  // 7 warps: one query point per thread at n1 = 196
 
+// SC_HPC kept hypotheses per CTA: the staged model and every LDS.128 of the scan serve both
+constexpr int SC_HPC = 2;
+
 __global__ void __launch_bounds__(SC_THREADS)
 k_score(const float* __restrict__ pts1, const float* __restrict__ model, const float* __restrict__ w1,
         const float* __restrict__ Rs, const float* __restrict__ ts, const int* __restrict__ top,
-        int n1, int nm, int H, int K, int k0, float* __restrict__ scores) {
+        int n1, int nm, int H, int K, int k0, int k1, float* __restrict__ scores) {
   extern __shared__ __align__(16) float sm_model[];  // 4 x nm_pad (SoA x | y | z | |y|^2)
-  __shared__ double s_red[2][SC_THREADS / 32];
+  __shared__ double s_red[2 * SC_HPC][SC_THREADS / 32];
   const int b = blockIdx.y;
-  const int k = k0 + blockIdx.x;
+  const int ka = k0 + blockIdx.x * SC_HPC;
+  const int kb = min(ka + 1, k1 - 1);               // odd tail: the second slot repeats the first hypothesis
   const int nm_pad = (nm + 3) & ~3;
   float* mx = sm_model; float* my = mx + nm_pad; float* mz = my + nm_pad; float* mn = mz + nm_pad;
   stage_model_soa(model + (size_t)b * nm * 3, nm, nm_pad, mx, my, mz, mn);
-  const int h = top ? top[(size_t)b * K + k] : k;
-  const float* R = Rs + ((size_t)b * H + h) * 9;
-  const float* t = ts + ((size_t)b * H + h) * 3;
-  const float r00 = R[0], r01 = R[1], r02 = R[2], r10 = R[3], r11 = R[4], r12 = R[5], r20 = R[6],
-              r21 = R[7], r22 = R[8];
-  const float t0 = t[0], t1 = t[1], t2 = t[2];
+  const int ha = top ? top[(size_t)b * K + ka] : ka, hb = top ? top[(size_t)b * K + kb] : kb;
+  const float* Ra = Rs + ((size_t)b * H + ha) * 9;
+  const float* ta = ts + ((size_t)b * H + ha) * 3;
+  const float* Rb = Rs + ((size_t)b * H + hb) * 9;
+  const float* tb = ts + ((size_t)b * H + hb) * 3;
+  float ra[9], rb[9], tta[3], ttb[3];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) { ra[i] = Ra[i]; rb[i] = Rb[i]; }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { tta[i] = ta[i]; ttb[i] = tb[i]; }
   __syncthreads();
-  double num = 0.0, den = 0.0;
+  double num = 0.0, den_a = 0.0, den_b = 0.0;
   for (int i = threadIdx.x; i < n1; i += SC_THREADS) {
     const float* p = pts1 + ((size_t)b * n1 + i) * 3;
-    float d0 = p[0] - t0, d1 = p[1] - t1, d2 = p[2] - t2;
-    float x0 = fmaf(d2, r20, fmaf(d1, r10, d0 * r00));
-    float x1 = fmaf(d2, r21, fmaf(d1, r11, d0 * r01));
-    float x2 = fmaf(d2, r22, fmaf(d1, r12, d0 * r02));
-    float xx = __fadd_rn(__fadd_rn(__fmul_rn(x0, x0), __fmul_rn(x1, x1)), __fmul_rn(x2, x2));
-    float best = nn_min_expansion(mx, my, mz, mn, nm_pad, x0, x1, x2, xx);
-    float dist = sqrtf(fmaxf(best, 0.f));
-    float w = w1[(size_t)b * n1 + i];
+    const float p0 = p[0], p1 = p[1], p2 = p[2];
+    float xa[4], xb[4];
+    {
+      const float d0 = p0 - tta[0], d1 = p1 - tta[1], d2 = p2 - tta[2];
+      xa[0] = fmaf(d2, ra[6], fmaf(d1, ra[3], d0 * ra[0]));
+      xa[1] = fmaf(d2, ra[7], fmaf(d1, ra[4], d0 * ra[1]));
+      xa[2] = fmaf(d2, ra[8], fmaf(d1, ra[5], d0 * ra[2]));
+      xa[3] = __fadd_rn(__fadd_rn(__fmul_rn(xa[0], xa[0]), __fmul_rn(xa[1], xa[1])), __fmul_rn(xa[2], xa[2]));
+    }
+    {
+      const float d0 = p0 - ttb[0], d1 = p1 - ttb[1], d2 = p2 - ttb[2];
+      xb[0] = fmaf(d2, rb[6], fmaf(d1, rb[3], d0 * rb[0]));
+      xb[1] = fmaf(d2, rb[7], fmaf(d1, rb[4], d0 * rb[1]));
+      xb[2] = fmaf(d2, rb[8], fmaf(d1, rb[5], d0 * rb[2]));
+      xb[3] = __fadd_rn(__fadd_rn(__fmul_rn(xb[0], xb[0]), __fmul_rn(xb[1], xb[1])), __fmul_rn(xb[2], xb[2]));
+    }
+    float best_a, best_b;
+    nn_min_expansion2(mx, my, mz, mn, nm_pad, xa, xb, best_a, best_b);
+    const float w = w1[(size_t)b * n1 + i];
     num += (double)w;
-    den += (double)(dist * w);
+    den_a += (double)(sqrtf(fmaxf(best_a, 0.f)) * w);
+    den_b += (double)(sqrtf(fmaxf(best_b, 0.f)) * w);
   }
   num = warp_sum(num);
-  den = warp_sum(den);
+  den_a = warp_sum(den_a);
+  den_b = warp_sum(den_b);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) { s_red[0][warp] = num; s_red[1][warp] = den; }
+  if (lane == 0) { s_red[0][warp] = num; s_red[1][warp] = den_a; s_red[2][warp] = den_b; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    double n = 0.0, d = 0.0;
-    for (int w = 0; w < SC_THREADS / 32; ++w) { n += s_red[0][w]; d += s_red[1][w]; }
-    scores[(size_t)b * K + k] = (float)n / ((float)d + 1e-8f);
+    double n = 0.0, da = 0.0, db = 0.0;
+    for (int w = 0; w < SC_THREADS / 32; ++w) { n += s_red[0][w]; da += s_red[1][w]; db += s_red[2][w]; }
+    scores[(size_t)b * K + ka] = (float)n / ((float)da + 1e-8f);
+    if (ka + 1 < k1) scores[(size_t)b * K + ka + 1] = (float)n / ((float)db + 1e-8f);
   }
 }
 
@@ -355,8 +377,8 @@ static int launch_score(const float* pts1, const float* model, const float* w1, 
   if (smem > 200 * 1024) return UPK_ERR_UNSUPPORTED;
   if (smem > 40 * 1024)
     UPK_CUDA_TRY(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(k1 - k0, b);
-  k_score<<<grid, SC_THREADS, smem, st>>>(pts1, model, w1, Rs, ts, top, n1, nm, H, K, k0, scores);
+  dim3 grid(ceil_div(k1 - k0, SC_HPC), b);
+  k_score<<<grid, SC_THREADS, smem, st>>>(pts1, model, w1, Rs, ts, top, n1, nm, H, K, k0, k1, scores);
   count_launch();
   UPK_RETURN_LAST_ERROR();
 }

@@ -116,6 +116,45 @@ __device__ __forceinline__ float nn_min_expansion(const float* __restrict__ mx, 
   return best;
 }
 
+// Two query points against the same staged model in one sweep (the two hypotheses a k_score thread evaluates):
+// the four LDS.128 of a step are shared, the two dependency chains interleave.  Same arithmetic per point as
+// nn_min_expansion.
+__device__ __forceinline__ void nn_min_expansion2(const float* __restrict__ mx, const float* __restrict__ my,
+                                                  const float* __restrict__ mz, const float* __restrict__ mn,
+                                                  int nm_pad, const float (&xa)[4], const float (&xb)[4],
+                                                  float& best_a, float& best_b) {
+  const unsigned long long A0 = pack2(xa[0], xa[0]), A1 = pack2(xa[1], xa[1]), A2 = pack2(xa[2], xa[2]);
+  const unsigned long long AX = pack2(xa[3], xa[3]);
+  const unsigned long long B0 = pack2(xb[0], xb[0]), B1 = pack2(xb[1], xb[1]), B2 = pack2(xb[2], xb[2]);
+  const unsigned long long BX = pack2(xb[3], xb[3]);
+  const unsigned long long M2 = pack2(-2.0f, -2.0f);
+  float ba = INFINITY, bb = INFINITY;
+#pragma unroll 2
+  for (int j = 0; j < nm_pad; j += 4) {
+    const ulonglong2 qx = *reinterpret_cast<const ulonglong2*>(mx + j);
+    const ulonglong2 qy = *reinterpret_cast<const ulonglong2*>(my + j);
+    const ulonglong2 qz = *reinterpret_cast<const ulonglong2*>(mz + j);
+    const ulonglong2 qn = *reinterpret_cast<const ulonglong2*>(mn + j);
+    unsigned long long ta = fma2(A2, qz.x, fma2(A1, qy.x, mul2(A0, qx.x)));
+    unsigned long long tb = fma2(A2, qz.y, fma2(A1, qy.y, mul2(A0, qx.y)));
+    unsigned long long ua = fma2(B2, qz.x, fma2(B1, qy.x, mul2(B0, qx.x)));
+    unsigned long long ub = fma2(B2, qz.y, fma2(B1, qy.y, mul2(B0, qx.y)));
+    ta = add2(fma2(M2, ta, AX), qn.x);
+    tb = add2(fma2(M2, tb, AX), qn.y);
+    ua = add2(fma2(M2, ua, BX), qn.x);
+    ub = add2(fma2(M2, ub, BX), qn.y);
+    float d0, d1, d2, d3, e0, e1, e2, e3;
+    unpack2(ta, d0, d1);
+    unpack2(tb, d2, d3);
+    unpack2(ua, e0, e1);
+    unpack2(ub, e2, e3);
+    ba = fminf(fminf(ba, d0), fminf(d1, fminf(d2, d3)));
+    bb = fminf(fminf(bb, e0), fminf(e1, fminf(e2, e3)));
+  }
+  best_a = ba;
+  best_b = bb;
+}
+
 // stage a model cloud (AoS global) into the SoA layout nn_min_expansion expects; call with all threads
 __device__ __forceinline__ void stage_model_soa(const float* __restrict__ model, int nm, int nm_pad, float* mx,
                                                 float* my, float* mz, float* mn) {
