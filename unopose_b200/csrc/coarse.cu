@@ -240,7 +240,7 @@ constexpr int SC_THREADS = 224;  // 7 warps: one query point per thread at n1 = 
 // SC_HPC kept hypotheses per CTA: the staged model and every LDS.128 of the scan serve both
 constexpr int SC_HPC = 2;
 
-__global__ void __launch_bounds__(SC_THREADS)
+__global__ void __launch_bounds__(SC_THREADS, 4)
 k_score(const float* __restrict__ pts1, const float* __restrict__ model, const float* __restrict__ w1,
         const float* __restrict__ Rs, const float* __restrict__ ts, const int* __restrict__ top,
         int n1, int nm, int H, int K, int k0, int k1, float* __restrict__ scores) {
