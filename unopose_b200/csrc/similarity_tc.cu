@@ -230,7 +230,7 @@ k_similarity_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 int batch, int M, int N, int K, float temp, int off, float* __restrict__ C,
                 float* __restrict__ rowpart, float* __restrict__ colpart, float gref) {
   // `off` (0 or 1): the tiles cover rows/columns [off, M) x [off, N); with off = 1 the background row 0 and
-  // column 0 are produced by k_similarity_border, so the 2049 x 2049 fine shape is exactly 16 x 8 tiles
+  // column 0 are produced by k_normalize_split (BORDER), so the 2049 x 2049 fine shape is exactly 16 x 8 tiles
   extern __shared__ unsigned char smem_raw[];
   TcSmem& sm = *reinterpret_cast<TcSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
