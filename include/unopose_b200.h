@@ -266,6 +266,31 @@ int upk_global_lrf(const float* pts, const float* radius, int b, int n, float ep
 int upk_transform_points(const float* pts, const float* R, const float* t, int b, int n, float* out,
                          upk_stream_t stream);
 
+/* ------------------------------------------------------------------------- *
+ * (f2) GeometricStructureEmbedding — replaces the torch-op sequence of
+ *      core/unopose/model/transformer.py:287-350 (+ SinusoidalPositionalEmbedding, :261-284)
+ * ------------------------------------------------------------------------- */
+
+/* 1 if the fused kernel handles (hidden_dim c, angle_k): c a multiple of 32 in [32,256], 1 <= angle_k <= 8. */
+int upk_geometric_embedding_supported(int c, int angle_k);
+size_t upk_geometric_embedding_workspace_bytes(int b, int n, int c, int angle_k);
+
+/* get_embedding_indices(points[b,n,3]) -> d_idx[b,n,n], a_idx[b,n,n,angle_k]   (transformer.py:303-336)
+ * d = sqrt(clamp(x2 - 2xy + y2, 0)) / sigma_d (the expansion form of pairwise_distance, model_utils.py:230-257);
+ * neighbours = the angle_k nearest after the nearest (ties: lower index); angle = atan2(|ref x anc|, ref.anc) * factor_a. */
+int upk_geometric_embedding_indices(const float* points, int b, int n, int angle_k, float sigma_d, float factor_a,
+                                    float* d_idx, float* a_idx, upk_stream_t stream);
+
+/* forward(points[b,n,3]) -> out[b,n,n,c]   (transformer.py:338-350)
+ * out = proj_d(emb(d_idx)) + red_k proj_a(emb(a_idx)), red = max (reduction_mean = 0) or mean (1).
+ * div_term[c/2] is the module's `embedding.div_term` buffer; w_d/w_a [c,c] row-major (out, in) and b_d/b_a [c] are
+ * `proj_d` / `proj_a`.  The sinusoid rows are generated in shared memory as the A operand of tcgen05.mma (3xTF32);
+ * only `out` is written (the "a" phase adds into what the "d" phase stored). */
+int upk_geometric_embedding(const float* points, int b, int n, int c, int angle_k, float sigma_d, float factor_a,
+                            const float* div_term, const float* w_d, const float* b_d, const float* w_a,
+                            const float* b_a, int reduction_mean, void* workspace, size_t workspace_bytes,
+                            float* out, upk_stream_t stream);
+
 /* HOST function (no GPU): the 3x3 Procrustes rotation solver of kernel family (3),
  * compiled from the same source as the device code.  H[n,9] row-major -> R[n,9]. */
 int upk_host_procrustes_rotation(const double* H, int n, double* R_out);

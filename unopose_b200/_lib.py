@@ -53,6 +53,9 @@ _SIGNATURES = {
                             c_f, c_sz, c_f, c_f, c_f, c_f, c_st],
     "upk_weighted_procrustes": [c_f, c_f, c_f, c_i, c_i, c_fl, c_fl, c_f, c_f, c_st],
     "upk_global_lrf": [c_f, c_f, c_i, c_i, c_fl, c_f, c_f, c_st],
+    "upk_geometric_embedding_supported": [c_i, c_i],
+    "upk_geometric_embedding_indices": [c_f, c_i, c_i, c_i, c_fl, c_fl, c_f, c_f, c_st],
+    "upk_geometric_embedding": [c_f, c_i, c_i, c_i, c_i, c_fl, c_fl, c_f, c_f, c_f, c_f, c_f, c_i, c_f, c_sz, c_f, c_st],
     "upk_transform_points": [c_f, c_f, c_f, c_i, c_i, c_f, c_st],
     "upk_host_procrustes_rotation": [c_f, c_i, c_f],
 }
@@ -64,6 +67,7 @@ _SIZE_FUNCS = {
     "upk_coarse_assignment_workspace_bytes": [c_i, c_i, c_i],
     "upk_fine_pose_workspace_bytes": [c_i, c_i, c_i],
     "upk_similarity_stats_bytes": [c_i, c_i, c_i],
+    "upk_geometric_embedding_workspace_bytes": [c_i, c_i, c_i, c_i],
 }
 
 

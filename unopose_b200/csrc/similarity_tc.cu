@@ -23,11 +23,12 @@
 #include "common.cuh"
 #include "launch_count.h"
 #include "pose_internal.h"
+#include "tc_ptx.cuh"
 #include "../../include/unopose_b200.h"
 
 namespace upk {
 
-constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 16, TC_STAGES = 3;  // 64-byte K rows (SWIZZLE_64B), 48 KB / stage
+constexpr int TC_STAGES = 3;  // 48 KB / stage
 constexpr int TC_EPI_WARPS = 8;  // two warps per TMEM lane quarter, each takes half of the 256 columns
 constexpr int TC_THREADS = 64 + TC_EPI_WARPS * 32;
 constexpr uint32_t TC_STAGE_BYTES = (2 * TC_BM * TC_BK + 2 * TC_BN * TC_BK) * 4;  // 49152
@@ -42,80 +43,6 @@ struct __align__(1024) TcSmem {
   uint32_t tmem_base;
 };
 
-// ---------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(void* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(void* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(void* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t ok = 0;
-  while (!ok) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}"
-        : "=r"(ok)
-        : "r"(addr), "r"(parity)
-        : "memory");
-  }
-}
-__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, void* bar, void* dst, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(dst)), "l"((unsigned long long)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(void* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
-}
-// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout) for rows of
-// TC_BK fp32 = 64 bytes, SWIZZLE_64B: 8-row groups of 512 B.
-// start>>4 | LBO(=1)<<16 | SBO(=512B>>4)<<32 | version(=1)<<46 | layout SWIZZLE_64B(=4)<<61
-static_assert(TC_BK * 4 == 64, "descriptor below assumes 64-byte K rows");
-__device__ __forceinline__ uint64_t make_desc_sw128(const void* smem) {
-  uint64_t d = (uint64_t)((smem_u32(smem) & 0x3ffff) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(512 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)4 << 61;
-  return d;
-}
-// instruction descriptor: D=F32, A=B=TF32, both K-major, N=256, M=128 (cute::UMMA::InstrDescriptor)
-constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
-                                ((uint32_t)(TC_BM >> 4) << 24);
-
-__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 // ---------------------------------------------------------------- operand preparation
 // out_hi = rna_tf32(x / max(||x||, 1e-12)) ; out_lo = x_n - out_hi.   One warp per row.
@@ -634,6 +561,11 @@ static int make_map(CUtensorMap* map, const float* base, int batch, int rows, in
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? UPK_OK : UPK_ERR_INVALID_ARG;
+}
+
+// the same encoder for the other tensor-core translation units (geoembed.cu); `map` is a CUtensorMap*
+int tc_make_map(void* map, const float* base, int batch, int rows, int K, int box_rows) {
+  return make_map((CUtensorMap*)map, base, batch, rows, K, box_rows);
 }
 
 static int g_sim_mode = -1;  // 3 = 3xTF32 tensor cores (default), 1 = 1xTF32, 0 = fp32 SIMT

@@ -1,7 +1,8 @@
 """Transformer blocks of the matching modules — PyTorch host code with the reference's parameter
 names (core/unopose/model/transformer.py).  These layers sit inside the matching modules but are dense
-cuBLAS work ("next" row f2 of SURVEY.md §8); only `SparseToDenseTransformer._sample_feats` touches the
-hot path (a row gather, `transformer.py:655-662`).
+cuBLAS work; `SparseToDenseTransformer._sample_feats` touches the hot path (a row gather,
+`transformer.py:655-662`) and `GeometricStructureEmbedding` runs the fused tcgen05 kernels of "next" row f2
+ on CUDA.
 """
 import math
 
@@ -253,8 +254,21 @@ class GeometricStructureEmbedding(nn.Module):
         if self.reduction_a not in ("max", "mean"):
             raise ValueError(f"Unsupported reduction mode: {self.reduction_a}.")
 
+    def _fused(self, points):
+        """CUDA inference goes to the fused kernels (modules/geo.py); CPU tensors, autograd and hidden sizes the
+        kernel does not cover take the torch-op sequence below (cuBLAS on CUDA)."""
+        if not points.is_cuda:
+            return False
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            return False
+        from . import geo
+        return geo.supported(self.proj_d.weight.shape[0], self.angle_k)
+
     @torch.no_grad()
     def get_embedding_indices(self, points):
+        if self._fused(points):
+            from . import geo
+            return geo.geometric_embedding_indices(points, self.sigma_d, self.factor_a, self.angle_k)
         B, N, _ = points.shape
         dist = torch.sqrt(pairwise_distance(points, points))
         knn = dist.topk(k=self.angle_k + 1, dim=2, largest=False)[1][:, :, 1:]               # (B,N,k)
@@ -266,6 +280,11 @@ class GeometricStructureEmbedding(nn.Module):
         return dist / self.sigma_d, torch.atan2(sin, cos) * self.factor_a
 
     def forward(self, points):
+        if self._fused(points):
+            from . import geo
+            return geo.geometric_embedding(points, self.embedding.div_term, self.proj_d.weight, self.proj_d.bias,
+                                           self.proj_a.weight, self.proj_a.bias, self.sigma_d, self.factor_a,
+                                           self.angle_k, self.reduction_a)
         d_idx, a_idx = self.get_embedding_indices(points)
         d = self.proj_d(self.embedding(d_idx))
         a = self.proj_a(self.embedding(a_idx))
