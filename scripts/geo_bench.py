@@ -38,10 +38,31 @@ def main():
     t_i = timeit(lambda: geo.geometric_embedding_indices(pts, 0.2, fa, 3))
     with torch.no_grad():
         t_r = timeit(lambda: G.geometric_embedding(pts, dterm, w_d, b_d, w_a, b_a, 0.2, 15, 3), it=3, warm=1)
-    flops = 2.0 * B * N * N * 4 * C * C
-    print(json.dumps({"B": B, "N": N, "C": C, "fused_ms": t_f, "indices_ms": t_i, "torch_ms": t_r,
-                      "algorithmic_tflops": flops / t_f * 1e-9, "issued_tf32_tflops": 3 * flops / t_f * 1e-9 * (1275.0 / 1213.0),
-                      "out_GBps": B * N * N * C * 4 * 3 / t_f * 1e-6}))
+    # algorithmic work: per pair 1 distance row + k angle rows, each a C x C projection
+    k = 3
+    flops = 2.0 * B * N * N * (1 + k) * C * C
+    pairs = B * N * N
+    tiles = -(-pairs // 128) + -(-pairs // (4 * (32 // k)))          # 128-row MMA tiles actually issued
+    issued = 3.0 * tiles * 128 * 2 * C * C                           # 3xTF32
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    try:
+        peaks = json.load(open(os.path.join(root, "MEASURED_PEAKS.json")))
+        peak, src = float(peaks["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json, sustained dense bf16)"
+    except Exception:
+        peak, src = 1405.0, "fallback"
+    ach = flops / t_f * 1e-9
+    print(json.dumps({
+        "metric": "geometric_embeddings_per_s", "value": B / t_f * 1e3, "unit": "clouds/s",
+        "config": {"workload": "GeometricStructureEmbedding forward, N=%d (196 + background point), hidden %d, angle_k %d, max"
+                               % (N, C, k), "clouds_per_call": B},
+        "fused_ms": t_f, "indices_ms": t_i, "reference_torch_gpu_ms": t_r, "speedup_vs_reference_torch_gpu": t_r / t_f,
+        "roofline": {"kernel": "k_geo_embed<0> + k_geo_embed<1> (tcgen05 3xTF32, sinusoid operand generated in smem) + "
+                               "k_geo_indices + 2 x k_split_tf32", "bound": "tensor", "achieved": ach, "peak": peak,
+                     "unit": "TFLOP/s", "frac": ach / peak, "peak_source": src, "issued_tf32_tflops": issued / t_f * 1e-9,
+                     "tf32_issue_peak": peak / 2, "frac_of_tf32_issue_peak": issued / t_f * 1e-9 / (peak / 2),
+                     "traffic": None,
+                     "note": "achieved = ALGORITHMIC flops 2 (1+k) C^2 per pair / whole-call time; 3 MMAs per product"},
+        "out_bytes": B * N * N * C * 4}))
 
 
 if __name__ == "__main__":

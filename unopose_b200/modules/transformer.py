@@ -59,9 +59,15 @@ class _DotAttention(nn.Module):
         q, k, v = _heads(self.proj_q(x_q), h), _heads(self.proj_k(x_kv), h), _heads(self.proj_v(x_kv), h)
         scores = q @ k.transpose(-1, -2)
         if embed_qk is not None:
-            b, n, m, _ = embed_qk.shape
-            p = self.proj_p(embed_qk).reshape(b, n, m, h, self.head_dim)
-            scores = scores + torch.einsum("bhnc,bnmhc->bhnm", q, p)
+            # q.(W_p e + b_p) = (W_p^T q).e + q.b_p: the reference projects the (B,N,M,C) embedding with W_p
+            # (transformer.py:392,394: 2 N M C^2 FLOPs and a second (B,N,M,C) tensor per layer call); projecting the
+            # (B,h,N,c) queries instead costs 2 N C^2 and one pass over the embedding (32x fewer FLOPs at h = 8, c = 32).
+            c = self.head_dim
+            wp = self.proj_p.weight.view(h, c, -1)                                  # (h, c, C)
+            q2 = torch.einsum("bhnc,hck->bnkh", q, wp)                              # (B, N, C, h)
+            sp = torch.matmul(embed_qk, q2)                                         # (B, N, M, C) @ (B, N, C, h)
+            qb = torch.einsum("bhnc,hc->bhn", q, self.proj_p.bias.view(h, c))
+            scores = scores + sp.permute(0, 3, 1, 2) + qb.unsqueeze(-1)
         scores = scores / self.head_dim ** 0.5
         if key_masks is not None:
             scores = scores.masked_fill(key_masks[:, None, None, :], float("-inf"))
