@@ -291,6 +291,24 @@ int upk_geometric_embedding(const float* points, int b, int n, int c, int angle_
                             const float* b_a, int reduction_mean, void* workspace, size_t workspace_bytes,
                             float* out, upk_stream_t stream);
 
+/* ------------------------------------------------------------------------- *
+ * (f1) SharedMLP + max over the ball — the MLP half of PositionalEncoding
+ *      (oneref_predator_fine_point_matching.py:167-176: `self.mlp1(group(...)).max(dim=3)[0]`;
+ *       SharedMLP: pointnet2/pytorch_utils.py:25-48, three 1x1 Conv2d + BatchNorm2d + ReLU)
+ * ------------------------------------------------------------------------- */
+
+/* 1 if the fused kernel handles the geometry: cin <= 16, c1 in {16,32}, c2 in {32,64}, c3 in {32,...,128 step 32},
+ * nsample >= 32 with nsample % 128 == 0 or 128 % nsample == 0, (m * nsample) % 128 == 0. */
+int upk_shared_mlp_max_supported(int cin, int c1, int c2, int c3, int m, int nsample);
+
+/* x[b,cin,m,nsample] -> out[b,c3,m] = max_s relu(W3 relu(W2 relu(W1 x + b1) + b2) + b3).
+ * W_l [c_l, c_{l-1}] row-major and b_l [c_l] are the conv weights with the eval-mode batch norm FOLDED IN by the caller
+ * (W' = W * gamma / sqrt(var + eps) per output row, b' = beta - mean * gamma / sqrt(var + eps)).  The three GEMMs run
+ * on tcgen05 (3xTF32) with the activations kept in shared memory / TMEM between layers. */
+int upk_shared_mlp_max(const float* x, int b, int cin, int m, int nsample, int c1, int c2, int c3,
+                       const float* w1, const float* b1, const float* w2, const float* b2, const float* w3,
+                       const float* b3, float* out, upk_stream_t stream);
+
 /* HOST function (no GPU): the 3x3 Procrustes rotation solver of kernel family (3),
  * compiled from the same source as the device code.  H[n,9] row-major -> R[n,9]. */
 int upk_host_procrustes_rotation(const double* H, int n, double* R_out);

@@ -21,7 +21,7 @@ run(); torch.cuda.synchronize()
 from torch.profiler import profile, ProfilerActivity, record_function
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     run(); torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=28, max_name_column_width=70))
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=14, max_name_column_width=70))
 # PE alone
 def t(fn, it=3):
     fn(); torch.cuda.synchronize()

@@ -1,0 +1,315 @@
+// (f1) The MLP half of PositionalEncoding, fused: SharedMLP([cin, C1, C2, C3]) -> max over the ball
+//      (core/unopose/model/oneref_predator_fine_point_matching.py:138-178: `self.mlp1(...).max(dim=3)[0]`;
+//       SharedMLP = three 1x1 Conv2d + BatchNorm2d + ReLU, pointnet2/pytorch_utils.py:25-48).
+//
+// The reference runs, per layer, a cuDNN/cuBLAS GEMM, a batch-norm kernel and a ReLU kernel over activations of up to
+// (B,128,2048,256) fp32 = 4.3 GB at B = 16, then a max reduction: ~10 full passes over GB-sized tensors.  Here a CTA
+// keeps a 128-sample tile ON CHIP through all three layers: the host folds the eval-mode batch norm into the conv
+// (W' = W g/sqrt(v+eps), b' = beta - mean g/sqrt(v+eps)); the three GEMMs run on tcgen05 (3xTF32, accumulators in
+// TMEM); each layer's epilogue (bias, ReLU, hi/lo split) writes the NEXT layer's A operand straight into shared memory
+// in the UMMA SWIZZLE_64B layout; the last epilogue reduces the max over the ball.  HBM sees the (B,cin,m,ns) input
+// once and the (B,C3,m) output.
+//
+// CTA anatomy (320 threads, persistent): warp 1 issues every MMA; two groups of 4 warps (2..5, 6..9) each own a tile
+// slot (64 KB of operand smem, 224 TMEM columns) and walk their tile through
+//   load+split A1 -> [L1] -> epilogue 1 -> [L2] -> epilogue 2 -> [L3] -> epilogue 3 (max)
+// handing over with two mbarriers per group (a_ready: 4 warp arrivals, d_ready: tcgen05.commit); the groups run half a
+// tile apart so one group's epilogues overlap the other's MMAs.  The folded weights (84 KB, hi + lo) stay resident.
+#include <cuda.h>
+#include <math.h>
+
+#include "common.cuh"
+#include "launch_count.h"
+#include "pose_internal.h"
+#include "tc_ptx.cuh"
+#include "../../include/unopose_b200.h"
+
+namespace upk {
+
+constexpr int PM_C1 = 32, PM_C2 = 64, PM_C3 = 128;      // maxima (= the UNOPose SharedMLP [cin, 32, 64, 128])
+constexpr int PM_THREADS = 320;
+constexpr int PM_TILE = TC_BM * TC_BK;                   // floats of one 128-row x 16-wide operand chunk (8 KB)
+
+struct __align__(1024) PmSmem {
+  float w1_hi[PM_C1 * TC_BK], w1_lo[PM_C1 * TC_BK];                      // [row][16], cols >= cin zero
+  float w2_hi[PM_C1 / 16][PM_C2 * TC_BK], w2_lo[PM_C1 / 16][PM_C2 * TC_BK];   // chunk-major K
+  float w3_hi[PM_C2 / 16][PM_C3 * TC_BK], w3_lo[PM_C2 / 16][PM_C3 * TC_BK];
+  float a_hi[2][4][PM_TILE], a_lo[2][4][PM_TILE];                        // per group: A1 = chunk 0, A2 = 0..1, A3 = 0..3
+  float red[2][4][PM_C3];
+  float b1[PM_C1], b2[PM_C2], b3[PM_C3];
+  unsigned long long a_ready[2], d_ready[2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ float pm_tf32(float v) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+  return __uint_as_float(u);
+}
+
+// element (row, k) of a K-major [rows][16]-chunked SWIZZLE_64B operand: chunk k / 16, float offset inside the chunk
+__device__ __forceinline__ int pm_off(int row, int k16) {
+  return row * 16 + ((((k16 >> 2) ^ ((row >> 1) & 3)) << 2) | (k16 & 3));
+}
+
+__device__ __forceinline__ void pm_stage_weights(const float* __restrict__ w, int cout, int cin, int chunks,
+                                                 float* hi, float* lo, int chunk_floats) {
+  const int kpad = chunks * 16;
+  for (int i = threadIdx.x; i < cout * kpad; i += PM_THREADS) {
+    const int row = i / kpad, k = i - row * kpad;
+    const float v = k < cin ? w[row * cin + k] : 0.f;
+    const float h = pm_tf32(v);
+    const int o = (k >> 4) * chunk_floats + pm_off(row, k & 15);
+    hi[o] = h;
+    lo[o] = v - h;
+  }
+}
+
+__device__ __forceinline__ void pm_group_handoff(void* bar, int lane) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
+}
+
+// relu(acc + bias) of 16 consecutive channels -> one 64-byte operand row segment (4 swizzled 16-byte pieces), hi and lo
+__device__ __forceinline__ void pm_store16(const uint32_t* r, const float* bias, float* hi_chunk, float* lo_chunk,
+                                           int row, int sw) {
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    float v[4], h[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float a = __uint_as_float(r[4 * p + e]) + bias[4 * p + e];
+      v[e] = a > 0.f ? a : 0.f;
+      h[e] = pm_tf32(v[e]);
+    }
+    const int o = row * 16 + ((p ^ sw) << 2);
+    *reinterpret_cast<float4*>(hi_chunk + o) = make_float4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<float4*>(lo_chunk + o) = make_float4(v[0] - h[0], v[1] - h[1], v[2] - h[2], v[3] - h[3]);
+  }
+}
+
+// x [b][cin][m][ns] -> out [b][c3][m] = max_s relu(W3' relu(W2' relu(W1' x + b1') + b2') + b3')
+// rows_per_batch = m * ns (multiple of 128); ns >= 32 with ns % 128 == 0 or 128 % ns == 0.
+// `out` must be zero-filled when ns > 128 (several tiles per ball merge with atomicMax on the non-negative bit patterns).
+__global__ void __launch_bounds__(PM_THREADS, 1)
+k_shared_mlp_max(const float* __restrict__ x, int cin, int c1, int c2, int c3, int m, int ns, long long total_tiles,
+                 const float* __restrict__ w1, const float* __restrict__ bb1, const float* __restrict__ w2,
+                 const float* __restrict__ bb2, const float* __restrict__ w3, const float* __restrict__ bb3,
+                 float* out) {
+  extern __shared__ unsigned char smem_raw[];
+  PmSmem& sm = *reinterpret_cast<PmSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long rpb = (long long)m * ns;
+
+  if (threadIdx.x == 0) {
+    for (int g = 0; g < 2; ++g) { mbar_init(&sm.a_ready[g], 4); mbar_init(&sm.d_ready[g], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  pm_stage_weights(w1, c1, cin, 1, sm.w1_hi, sm.w1_lo, PM_C1 * TC_BK);
+  pm_stage_weights(w2, c2, c1, c1 / 16, &sm.w2_hi[0][0], &sm.w2_lo[0][0], PM_C2 * TC_BK);
+  pm_stage_weights(w3, c3, c2, c2 / 16, &sm.w3_hi[0][0], &sm.w3_lo[0][0], PM_C3 * TC_BK);
+  for (int t = threadIdx.x; t < c1; t += PM_THREADS) sm.b1[t] = bb1[t];
+  for (int t = threadIdx.x; t < c2; t += PM_THREADS) sm.b2[t] = bb2[t];
+  for (int t = threadIdx.x; t < c3; t += PM_THREADS) sm.b3[t] = bb3[t];
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the staged weights are read by the UMMA (async proxy)
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sm.tmem_base;
+
+  if (warp == 1) {
+    // ===== MMA issuer: layer by layer, alternating between the two tile slots =====
+    uint32_t par_a[2] = {0u, 0u};
+    const uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BM >> 4) << 24);
+    for (long long j = 0;; ++j) {
+      bool any = false;
+#pragma unroll 1
+      for (int L = 0; L < 3; ++L) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          const long long t = blockIdx.x + (2 * j + g) * (long long)gridDim.x;
+          if (t >= total_tiles) continue;
+          any = true;
+          mbar_wait(&sm.a_ready[g], par_a[g]);
+          par_a[g] ^= 1u;
+          tc_fence_after();
+          if (lane == 0) {
+            const int n_out = L == 0 ? c1 : (L == 1 ? c2 : c3);
+            const int chunks = L == 0 ? 1 : (L == 1 ? c1 / 16 : c2 / 16);
+            const int ksteps = L == 0 ? (cin > 8 ? 2 : 1) : 2;
+            const uint32_t idesc = idesc_base | ((uint32_t)(n_out >> 3) << 17);
+            const uint32_t d_tmem = tmem_base + g * 256 + (L == 0 ? 0 : (L == 1 ? PM_C1 : PM_C1 + PM_C2));
+            for (int kc = 0; kc < chunks; ++kc) {
+              const float* bh = L == 0 ? sm.w1_hi : (L == 1 ? sm.w2_hi[kc] : sm.w3_hi[kc]);
+              const float* bl = L == 0 ? sm.w1_lo : (L == 1 ? sm.w2_lo[kc] : sm.w3_lo[kc]);
+              const uint64_t ahi = make_desc_sw128(sm.a_hi[g][kc]), alo = make_desc_sw128(sm.a_lo[g][kc]);
+              const uint64_t bhi = make_desc_sw128(bh), blo = make_desc_sw128(bl);
+              for (int kk = 0; kk < ksteps; ++kk) {
+                const uint64_t adv = (uint64_t)(kk * 8 * 4 >> 4);
+                tc_mma_tf32(d_tmem, alo + adv, bhi + adv, idesc, (kc | kk) ? 1u : 0u);
+                tc_mma_tf32(d_tmem, ahi + adv, blo + adv, idesc, 1u);
+                tc_mma_tf32(d_tmem, ahi + adv, bhi + adv, idesc, 1u);
+              }
+            }
+            tc_commit(&sm.d_ready[g]);
+          }
+          __syncwarp();
+        }
+      }
+      if (!any) break;
+    }
+  } else if (warp >= 2) {
+    // ===== tile-slot groups: thread = one sample (row of the tile = TMEM lane) =====
+    const int g = (warp - 2) >> 2;
+    const int q = warp & 3;                       // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;
+    const int sw = (row >> 1) & 3;
+    const int gt = threadIdx.x - 64 - 128 * g;    // 0..127 inside the group (column owner in the final reduction)
+    float* tr = &sm.a_hi[g][2][0] + (q & 1) * 1024 + (q >> 1) * PM_TILE;   // 32x32 transpose buffer (XOR-swizzled), free after L3
+    const uint32_t tq = tmem_base + g * 256 + ((uint32_t)(q * 32) << 16);
+    const int cpt = ns >= 128 ? 1 : 128 / ns;     // balls per tile
+    const int qpc = 4 / cpt;                      // TMEM quarters per ball
+    uint32_t par_d = 0;
+    // the cin input channels of this thread's sample, loaded one tile AHEAD (the global-load latency would otherwise
+    // sit at the head of every tile's serial load -> L1 -> ... -> L3 chain)
+    float v[16];
+    auto load_tile = [&](long long t) {
+      const long long R0 = t * 128;
+      const long long b = R0 / rpb, rib = R0 - b * rpb;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) v[c] = c < cin ? __ldg(x + ((size_t)b * cin + c) * rpb + rib + row) : 0.f;
+    };
+    {
+      const long long t0 = blockIdx.x + (long long)g * gridDim.x;
+      if (t0 < total_tiles) load_tile(t0);
+    }
+    for (long long j = 0;; ++j) {
+      const long long t = blockIdx.x + (2 * j + g) * (long long)gridDim.x;
+      if (t >= total_tiles) break;
+      const long long R0 = t * 128;
+      const long long b = R0 / rpb, rib = R0 - b * rpb;
+      // ---- A1 (coalesced loads: consecutive rows are consecutive floats per channel)
+      {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          float h[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) h[e] = pm_tf32(v[4 * p + e]);
+          const int o = row * 16 + ((p ^ sw) << 2);
+          *reinterpret_cast<float4*>(&sm.a_hi[g][0][o]) = make_float4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<float4*>(&sm.a_lo[g][0][o]) =
+              make_float4(v[4 * p] - h[0], v[4 * p + 1] - h[1], v[4 * p + 2] - h[2], v[4 * p + 3] - h[3]);
+        }
+        const long long tn = t + 2 * (long long)gridDim.x;
+        if (tn < total_tiles) load_tile(tn);
+      }
+      pm_group_handoff(&sm.a_ready[g], lane);
+      // ---- epilogue 1: D1 (c1 columns) -> A2
+      mbar_wait(&sm.d_ready[g], par_d);
+      par_d ^= 1u;
+      tc_fence_after();
+      {
+        uint32_t r[32];
+        tmem_ld_32x32(tq, r);
+#pragma unroll
+        for (int kc = 0; kc < PM_C1 / 16; ++kc)
+          if (kc * 16 < c1) pm_store16(r + 16 * kc, sm.b1 + 16 * kc, sm.a_hi[g][kc], sm.a_lo[g][kc], row, sw);
+      }
+      pm_group_handoff(&sm.a_ready[g], lane);
+      // ---- epilogue 2: D2 (c2 columns) -> A3
+      mbar_wait(&sm.d_ready[g], par_d);
+      par_d ^= 1u;
+      tc_fence_after();
+#pragma unroll 1
+      for (int cb = 0; cb * 32 < c2; ++cb) {
+        uint32_t r[32];
+        tmem_ld_32x32(tq + PM_C1 + cb * 32, r);
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const int kc = 2 * cb + h2;
+          if (kc * 16 < c2) pm_store16(r + 16 * h2, sm.b2 + 16 * kc, sm.a_hi[g][kc], sm.a_lo[g][kc], row, sw);
+        }
+      }
+      pm_group_handoff(&sm.a_ready[g], lane);
+      // ---- epilogue 3: D3 (c3 columns) -> relu -> max over the 32 samples of this quarter -> red[q][col]
+      mbar_wait(&sm.d_ready[g], par_d);
+      par_d ^= 1u;
+      tc_fence_after();
+#pragma unroll 1
+      for (int cb = 0; cb * 32 < c3; ++cb) {
+        uint32_t r[32];
+        tmem_ld_32x32(tq + PM_C1 + PM_C2 + cb * 32, r);
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) {
+          const float a = __uint_as_float(r[jj]) + sm.b3[cb * 32 + jj];
+          tr[lane * 32 + (jj ^ lane)] = a > 0.f ? a : 0.f;
+        }
+        __syncwarp();
+        float mx = 0.f;
+#pragma unroll
+        for (int rr = 0; rr < 32; ++rr) mx = fmaxf(mx, tr[rr * 32 + (lane ^ rr)]);
+        sm.red[g][q][cb * 32 + lane] = mx;
+        __syncwarp();
+      }
+      tc_fence_before();
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");     // the four quarters of this group's tile
+      if (gt < c3) {
+        for (int s = 0; s < cpt; ++s) {
+          float mx = sm.red[g][s * qpc][gt];
+          for (int qq = 1; qq < qpc; ++qq) mx = fmaxf(mx, sm.red[g][s * qpc + qq][gt]);
+          const long long ball = (rib + (long long)s * (128 / cpt)) / ns;
+          float* dst = out + ((size_t)b * c3 + gt) * m + ball;
+          if (ns <= 128) *dst = mx;
+          else atomicMax(reinterpret_cast<int*>(dst), __float_as_int(mx));
+        }
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");     // red[] is rewritten by the next tile
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+}  // namespace upk
+
+using namespace upk;
+
+extern "C" int upk_shared_mlp_max_supported(int cin, int c1, int c2, int c3, int m, int ns) {
+  if (cin < 1 || cin > 16) return 0;
+  if (c1 < 16 || c1 > PM_C1 || c1 % 16) return 0;
+  if (c2 < 32 || c2 > PM_C2 || c2 % 32) return 0;
+  if (c3 < 32 || c3 > PM_C3 || c3 % 32) return 0;
+  if (ns < 32 || !((ns % 128 == 0) || (128 % ns == 0))) return 0;
+  if (m < 1 || ((long long)m * ns) % 128) return 0;
+  return 1;
+}
+
+extern "C" int upk_shared_mlp_max(const float* x, int b, int cin, int m, int ns, int c1, int c2, int c3,
+                                  const float* w1, const float* b1, const float* w2, const float* b2,
+                                  const float* w3, const float* b3, float* out, upk_stream_t stream) {
+  if (b < 0) return UPK_ERR_INVALID_ARG;
+  if (!upk_shared_mlp_max_supported(cin, c1, c2, c3, m, ns)) return UPK_ERR_UNSUPPORTED;
+  if (b == 0) return UPK_OK;
+  if (!x || !w1 || !b1 || !w2 || !b2 || !w3 || !b3 || !out) return UPK_ERR_INVALID_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (ns > 128) UPK_CUDA_TRY(cudaMemsetAsync(out, 0, (size_t)b * c3 * m * sizeof(float), st));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long tiles = (long long)b * m * ns / 128;
+  const size_t smem = sizeof(PmSmem) + 1024;
+  UPK_CUDA_TRY(cudaFuncSetAttribute(k_shared_mlp_max, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_shared_mlp_max<<<(int)(tiles < sms ? tiles : sms), PM_THREADS, smem, st>>>(x, cin, c1, c2, c3, m, ns, tiles, w1, b1,
+                                                                             w2, b2, w3, b3, out);
+  count_launch();
+  UPK_RETURN_LAST_ERROR();
+}

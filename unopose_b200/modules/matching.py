@@ -92,6 +92,16 @@ class PositionalEncoding(nn.Module):
         self.mlp2 = SharedMLP([input_dim, 32, 64, 128], bn=bn)
         self.mlp3 = Conv1d(256, out_dim, activation=None, bn=None)
 
+    @staticmethod
+    def _mlp_max(mlp, x):
+        """mlp(x).max over the ball: CUDA inference in eval mode runs the fused tcgen05 kernel (modules/pe.py: the
+        three layers of a 128-sample tile stay on chip); otherwise the torch layers (cuDNN/cuBLAS)."""
+        if x.is_cuda and not mlp.training and not torch.is_grad_enabled():
+            from . import pe
+            if pe.supported(mlp, x):
+                return pe.shared_mlp_max(x, mlp)
+        return mlp(x).max(dim=3)[0]
+
     def forward(self, pts1, pts2=None):
         if pts2 is None:
             pts2 = pts1
@@ -105,8 +115,8 @@ class PositionalEncoding(nn.Module):
                     not (torch.is_grad_enabled() and pts1.requires_grad):
                 # both scales from ONE scan of the cloud (fused ball query + grouping kernel)
                 pre1, pre2 = ball_query_and_group(pts1, pts2, [(g1.radius, g1.nsample), (g2.radius, g2.nsample)])
-            f1 = self.mlp1(g1(pts1, pts2, feats, pre=pre1)).max(dim=3)[0]
-            f2 = self.mlp2(g2(pts1, pts2, feats, pre=pre2)).max(dim=3)[0]
+            f1 = self._mlp_max(self.mlp1, g1(pts1, pts2, feats, pre=pre1))
+            f2 = self._mlp_max(self.mlp2, g2(pts1, pts2, feats, pre=pre2))
             return self.mlp3(torch.cat([f1, f2], dim=1)).transpose(1, 2)
 
 
