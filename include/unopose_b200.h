@@ -261,6 +261,16 @@ int upk_weighted_procrustes(const float* src, const float* ref, const float* wei
 int upk_global_lrf(const float* pts, const float* radius, int b, int n, float eps, float* out, float* frame_out,
                    upk_stream_t stream);
 
+/* QueryAndLRFGroup's frame stage in one kernel: LRF_batch (pointnet2_utils.py:429-481) + the feature assembly of
+ * QueryAndLRFGroup.forward (:556-571).  grouped[b,3,n,ns] are the ABSOLUTE neighbour coordinates (grouping_operation /
+ * upk_ball_query_group output), centres[b,n,3] the points the frames are anchored at (`xyz`), new_xyz[b,n,3] the points
+ * subtracted for the raw offsets.  out[b,6,n,ns] = [grouped - new_xyz (/ r_lrf if normalize_xyz) | frame coordinates / r_lrf]
+ * when use_xyz, else out[b,3,n,ns] = frame coordinates.  Replaces a cuSOLVER batched SVD + ~15 elementwise passes; when
+ * the +-1e-3 sign vote of a frame's z axis is exactly 0 the reference's z sign is whatever its SVD returned — here it is
+ * the Jacobi solver's, deterministically. */
+int upk_lrf_group(const float* centres, const float* new_xyz, const float* grouped, int b, int n, int ns,
+                  float r_lrf, float eps, int use_xyz, int normalize_xyz, float* out, upk_stream_t stream);
+
 /* out[b,i,:] = (pts[b,i,:] - t[b]) @ R[b]: a cloud moved by a pose, `p1_ = (p1 - init_t) @ init_R` of the fine
  * module (oneref_predator_fine_point_matching.py:65-72) and the scoring transforms of model_utils.py:483,:558. */
 int upk_transform_points(const float* pts, const float* R, const float* t, int b, int n, float* out,

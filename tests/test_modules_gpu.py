@@ -110,3 +110,42 @@ def test_global_lrf_kernel(cuda):
     moved = pts @ Rg.transpose(1, 2) + torch.tensor([0.3, -0.2, 0.5], device=cuda)
     assert torch.allclose(get_batch_lrf(pts), get_batch_lrf(moved), atol=5e-4)
     assert get_batch_lrf(pts[:0]).shape == (0, 2048, 3)
+
+
+def test_lrf_group_kernel_vs_torch_lrf_batch(cuda):
+    """upk_lrf_group (frames + feature assembly of QueryAndLRFGroup in one kernel) against the torch LRF_batch on the
+    same device.  Centres whose sign vote is decisive must agree as they are; where the vote ties, the torch path keeps
+    cuSOLVER's raw SVD sign and the kernel its Jacobi solver's, so (y, z) may be negated together."""
+    from unopose_b200.pointnet2 import pointnet2_utils as PU
+    from unopose_b200.pointnet2.lrf import LRF_batch
+    from util_clouds import batch_clouds
+
+    pts = torch.from_numpy(batch_clouds(21, 3, 2048, "surface")).to(cuda).contiguous()
+    for r, ns in ((0.1, 64), (0.2, 256)):
+        idx, grouped = PU.ball_query_and_group(pts, pts, [(r, ns)])[0]
+        got = PU.lrf_group(pts, pts, grouped, r, use_xyz=True)
+        assert got.shape == (3, 6, 2048, ns)
+        assert torch.equal(got[:, :3], grouped - pts.transpose(1, 2).unsqueeze(-1))
+        only = PU.lrf_group(pts, pts, grouped, r, use_xyz=False)
+        assert torch.equal(only, got[:, 3:])
+        ref = LRF_batch(r_lrf=r)(pts, grouped.transpose(1, 2)).transpose(1, 2)            # (B,3,N,ns)
+        same = (got[:, 3:] - ref).abs().amax(dim=(1, 3))                                  # (B,N)
+        flip = torch.stack([got[:, 3] - ref[:, 0], got[:, 4] + ref[:, 1], got[:, 5] + ref[:, 2]], 1).abs().amax(dim=(1, 3))
+        assert (torch.minimum(same, flip) < 2e-3).float().mean() > 0.99
+        # decisive votes: recompute the vote from the torch frame's z axis (row 2 of the frame coordinates * r = height)
+        h = -ref[:, 2] * r                                                                # z.(p - p_j)
+        vote = (h > 1e-3).sum(-1) - (h < -1e-3).sum(-1)
+        decisive = vote.abs() >= 2
+        assert decisive.float().mean() > 0.3
+        assert (same[decisive] < 2e-3).float().mean() > 0.99
+    # the grouper takes the kernel path under no_grad and the torch path with autograd on
+    grp = PU.QueryAndLRFGroup(0.1, 64, use_xyz=True)
+    feats = pts.transpose(1, 2).contiguous()
+    with torch.no_grad():
+        a = grp(pts, pts, feats)
+    with torch.enable_grad():
+        b = grp(pts, pts, feats)
+    assert torch.equal(a[:, :3], b[:, :3])
+    d = (a[:, 3:] - b[:, 3:]).abs().amax(dim=(1, 3))
+    f = torch.stack([a[:, 3] - b[:, 3], a[:, 4] + b[:, 4], a[:, 5] + b[:, 5]], 1).abs().amax(dim=(1, 3))
+    assert (torch.minimum(d, f) < 2e-3).float().mean() > 0.99

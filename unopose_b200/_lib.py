@@ -58,6 +58,7 @@ _SIGNATURES = {
     "upk_geometric_embedding": [c_f, c_i, c_i, c_i, c_i, c_fl, c_fl, c_f, c_f, c_f, c_f, c_f, c_i, c_f, c_sz, c_f, c_st],
     "upk_shared_mlp_max_supported": [c_i, c_i, c_i, c_i, c_i, c_i],
     "upk_shared_mlp_max": [c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_st],
+    "upk_lrf_group": [c_f, c_f, c_f, c_i, c_i, c_i, c_fl, c_fl, c_i, c_i, c_f, c_st],
     "upk_transform_points": [c_f, c_f, c_f, c_i, c_i, c_f, c_st],
     "upk_host_procrustes_rotation": [c_f, c_i, c_f],
 }

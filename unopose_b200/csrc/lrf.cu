@@ -127,6 +127,84 @@ k_global_lrf(const float* __restrict__ pts, const float* __restrict__ radius, in
   }
 }
 
+// ---------------------------------------------------------------- per-centre frames of QueryAndLRFGroup
+// LRF_batch (core/unopose/model/pointnet2/pointnet2_utils.py:429-481) + the feature assembly of
+// QueryAndLRFGroup.forward (:556-571) in one kernel, one warp per centre:
+//   grouped [b][3][n][ns] (absolute neighbour coordinates), centres [b][n][3] (the `xyz` the frames are anchored at),
+//   new_xyz [b][n][3] (subtracted for the raw offsets)  ->  out [b][3 or 6][n][ns] = [grouped - new_xyz (/r) | frame coordinates]
+// The reference spends a cuSOLVER batched SVD (4.1 ms per call at B = 16, n = 2048) and ~15 elementwise passes over
+// (B,n,3,ns) here.  Sums in fp64.  z = eigenvector of the smallest covariance eigenvalue, sign by the +-1e-3 vote;
+// when the vote is exactly 0 the reference keeps whatever sign its SVD returned (LAPACK and cuSOLVER disagree) —
+// here that case keeps the sign of the Jacobi solver, deterministically.
+constexpr int LG_WARPS = 8;
+
+__global__ void __launch_bounds__(LG_WARPS * 32)
+k_lrf_group(const float* __restrict__ centres, const float* __restrict__ new_xyz, const float* __restrict__ grouped,
+            int n, int ns, float r, float eps, int use_xyz, int normalize_xyz, float* __restrict__ out) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * LG_WARPS + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i >= n) return;
+  const size_t plane = (size_t)n * ns;
+  const float* gx = grouped + ((size_t)b * 3 * n + i) * ns;
+  const float* gy = gx + plane;
+  const float* gz = gy + plane;
+  const float* C = centres + ((size_t)b * n + i) * 3;
+  const float cx = C[0], cy = C[1], cz = C[2];
+  // covariance of (p - p_j)
+  double cv[6] = {0, 0, 0, 0, 0, 0};
+  for (int j = lane; j < ns; j += 32) {
+    const float x = cx - gx[j], y = cy - gy[j], z = cz - gz[j];
+    cv[0] += (double)(x * x); cv[1] += (double)(y * y); cv[2] += (double)(z * z);
+    cv[3] += (double)(x * y); cv[4] += (double)(x * z); cv[5] += (double)(y * z);
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) cv[k] = warp_sum(cv[k]) / ns;
+  double zr[3];
+  sym3_min_eigenvector(cv[0], cv[1], cv[2], cv[3], cv[4], cv[5], zr);   // identical in every lane
+  float z0 = (float)zr[0], z1 = (float)zr[1], z2 = (float)zr[2];
+  int vote = 0;
+  for (int j = lane; j < ns; j += 32) {
+    const float h = z0 * (cx - gx[j]) + z1 * (cy - gy[j]) + z2 * (cz - gz[j]);
+    vote += (h > 1e-3f ? 1 : 0) - (h < -1e-3f ? 1 : 0);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) vote += __shfl_xor_sync(0xffffffffu, vote, o);
+  if (vote < 0) { z0 = -z0; z1 = -z1; z2 = -z2; }
+  // x axis: sum (r - |q|)^2 (z.q)^2 (q - (z.q) z),  q = p_j - p
+  double xd[3] = {0, 0, 0};
+  for (int j = lane; j < ns; j += 32) {
+    const float qx = gx[j] - cx, qy = gy[j] - cy, qz = gz[j] - cz;
+    const float h = z0 * qx + z1 * qy + z2 * qz;
+    const float d = sqrtf(qx * qx + qy * qy + qz * qz);
+    const float a = (r - d) * (r - d) * (h * h);
+    xd[0] += (double)(a * (qx - h * z0)); xd[1] += (double)(a * (qy - h * z1)); xd[2] += (double)(a * (qz - h * z2));
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) xd[k] = warp_sum(xd[k]);
+  const float x0f = (float)xd[0], x1f = (float)xd[1], x2f = (float)xd[2];
+  const float xn = sqrtf(x0f * x0f + x1f * x1f + x2f * x2f) + eps;
+  const float x0 = x0f / xn, x1 = x1f / xn, x2 = x2f / xn;
+  const float y0 = x1 * z2 - x2 * z1, y1 = x2 * z0 - x0 * z2, y2 = x0 * z1 - x1 * z0;   // y = x cross z
+  const int cout = use_xyz ? 6 : 3;
+  float* O = out + ((size_t)b * cout * n + i) * ns;
+  float* L = O + (use_xyz ? 3 * plane : 0);
+  const float* Q = new_xyz + ((size_t)b * n + i) * 3;
+  const float nx = Q[0], ny = Q[1], nz = Q[2];
+  for (int j = lane; j < ns; j += 32) {
+    const float px = gx[j], py = gy[j], pz = gz[j];
+    if (use_xyz) {
+      float ox = px - nx, oy = py - ny, oz = pz - nz;
+      if (normalize_xyz) { ox /= r; oy /= r; oz /= r; }
+      O[j] = ox; O[plane + j] = oy; O[2 * plane + j] = oz;
+    }
+    const float qx = (px - cx) / r, qy = (py - cy) / r, qz = (pz - cz) / r;
+    L[j] = x0 * qx + x1 * qy + x2 * qz;
+    L[plane + j] = y0 * qx + y1 * qy + y2 * qz;
+    L[2 * plane + j] = z0 * qx + z1 * qy + z2 * qz;
+  }
+}
+
 }  // namespace upk
 
 using namespace upk;
@@ -137,6 +215,17 @@ extern "C" int upk_global_lrf(const float* pts, const float* radius, int b, int 
   if (b == 0) return UPK_OK;
   if (!pts || !out) return UPK_ERR_INVALID_ARG;
   k_global_lrf<<<b, LRF_THREADS, 0, (cudaStream_t)stream>>>(pts, radius, n, eps, out, frame_out);
+  count_launch();
+  UPK_RETURN_LAST_ERROR();
+}
+
+extern "C" int upk_lrf_group(const float* centres, const float* new_xyz, const float* grouped, int b, int n, int ns,
+                             float r_lrf, float eps, int use_xyz, int normalize_xyz, float* out, upk_stream_t stream) {
+  if (b < 0 || n <= 0 || ns <= 0 || !(r_lrf > 0.f)) return UPK_ERR_INVALID_ARG;
+  if (b == 0) return UPK_OK;
+  if (!centres || !new_xyz || !grouped || !out) return UPK_ERR_INVALID_ARG;
+  k_lrf_group<<<dim3(ceil_div(n, LG_WARPS), b), LG_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      centres, new_xyz, grouped, n, ns, r_lrf, eps, use_xyz ? 1 : 0, normalize_xyz ? 1 : 0, out);
   count_launch();
   UPK_RETURN_LAST_ERROR();
 }

@@ -4,6 +4,8 @@ Public names, call signatures, dtypes and autograd behaviour follow the
 reference (file:line cited per item); the work is done by the sm_100a kernels
 behind ``unopose_b200.pointnet2._ext``.
 """
+import os
+
 import torch
 import torch.nn as nn
 from torch.autograd import Function
@@ -135,6 +137,29 @@ def ball_query_and_group(xyz, new_xyz, scales):
         return _ext.ball_query_group(new_xyz.contiguous(), xyz.contiguous(), list(scales), group=True)
 
 
+# UPK_LRF_SVD=torch keeps torch.svd inside the groupers (bit-for-bit the reference's GPU behaviour where the sign vote
+# of a frame ties and the raw SVD sign decides); default: the fused kernel with its deterministic tie rule
+_LRF_KERNEL = os.environ.get("UPK_LRF_SVD", "kernel") != "torch"
+
+
+def lrf_group(xyz, new_xyz, grouped_xyz, radius, eps=1e-10, use_xyz=True, normalize_xyz=False):
+    """LRF_batch + the feature assembly of QueryAndLRFGroup.forward (pointnet2_utils.py:429-481, :556-571) in one kernel.
+    xyz, new_xyz (B,n,3); grouped_xyz (B,3,n,ns) ABSOLUTE neighbour coordinates -> (B,6 or 3,n,ns)."""
+    from .. import _lib as L
+
+    L.check_cuda(xyz, "xyz")
+    c = xyz.float().contiguous()
+    q = new_xyz.float().contiguous()
+    g = grouped_xyz.float().contiguous()
+    B, _, n, ns = g.shape
+    out = torch.empty((B, 6 if use_xyz else 3, n, ns), dtype=torch.float32, device=g.device)
+    with torch.cuda.device(g.device):
+        L.check(L.load().upk_lrf_group(L.ptr(c), L.ptr(q), L.ptr(g), B, n, ns, float(radius), float(eps),
+                                       1 if use_xyz else 0, 1 if normalize_xyz else 0, L.ptr(out), L.stream_ptr(g)),
+                "lrf_group")
+    return out
+
+
 def _uniform_resample_(idx, nsample):
     """sample_uniformly branch of the reference groupers (pointnet2_utils.py:342-351,
     :542-551): per ball, unique indices padded with random re-draws.  Host loop,
@@ -244,6 +269,12 @@ class QueryAndLRFGroup(nn.Module):
             idx = ball_query(self.radius, self.nsample, xyz, new_xyz)
             unique_cnt = _uniform_resample_(idx, self.nsample) if self.sample_uniformly else None
             grouped_xyz = grouping_operation(xyz.transpose(1, 2).contiguous(), idx)  # (B,3,npoint,nsample)
+        if (pre is not None and _LRF_KERNEL and not torch.is_grad_enabled() and xyz.shape[1] == new_xyz.shape[1]
+                and not (features is not None and self.use_feature) and not self.ret_grouped_xyz
+                and not self.ret_unique_cnt and (features is not None or self.use_xyz)):
+            # frames + feature assembly in ONE kernel (upk_lrf_group) instead of a cuSOLVER SVD and ~15 passes
+            return lrf_group(xyz, new_xyz, grouped_xyz, self.radius, self.lrf.eps,
+                             use_xyz=(features is not None and self.use_xyz), normalize_xyz=self.normalize_xyz)
         lrf_features = self.lrf(xyz, grouped_xyz.transpose(1, 2))  # (B,npoint,3,nsample)
         lrf_features = lrf_features.transpose(1, 2).contiguous()
         grouped_xyz = grouped_xyz - new_xyz.transpose(1, 2).unsqueeze(-1)
