@@ -49,6 +49,7 @@ def parse():
                          "straight out of pinned host memory")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-torch-baseline", action="store_true")
+    ap.add_argument("--no-widened", action="store_true", help="skip the informational timings of the f1/f2 kernels")
     return ap.parse_args()
 
 
@@ -166,6 +167,48 @@ def workload_config(cfg, batch):
 
 
 # ----------------------------------------------------------------------------- our arm
+def widened_leg(B, dev):
+    """Device time of the kernels of the SURVEY.md §8 "next" rows at the real config (outside the headline step):
+    f2 GeometricStructureEmbedding (N = 197, hidden 256, k = 3) and f1 PositionalEncoding (2048 points, two scales)."""
+    import math
+
+    import torch
+
+    from unopose_b200.modules import geo
+    from unopose_b200.modules.matching import PositionalEncoding
+
+    def timeit(fn, it=5, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(it):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / it
+
+    g = torch.Generator(device="cpu").manual_seed(5)
+    N, C, k = 197, 256, 3
+    p = torch.randn(B, N - 1, 3, generator=g)
+    pts = torch.cat([torch.ones(B, 1, 3), p / p.norm(dim=2).max(dim=1)[0].view(B, 1, 1)], 1).to(dev)
+    dterm = torch.exp(torch.arange(0, C, 2).float() * (-math.log(10000.0) / C)).to(dev)
+    w = [((torch.rand(*s, generator=g) * 2 - 1) / math.sqrt(C)).to(dev) for s in ((C, C), (C,), (C, C), (C,))]
+    fa = 180.0 / (15 * math.pi)
+    t_geo = timeit(lambda: geo.geometric_embedding(pts, dterm, w[0], w[1], w[2], w[3], 0.2, fa, k))
+    flops = 2.0 * B * N * N * (1 + k) * C * C
+    pe = PositionalEncoding(256, r1=0.1, r2=0.2, nsample1=64, nsample2=256, use_lrf=True, use_xyz=True).to(dev).eval()
+    cloud = torch.randn(B, 2048, 3, generator=g)
+    cloud = (cloud / cloud.norm(dim=2).max(dim=1)[0].view(B, 1, 1)).to(dev)
+    with torch.no_grad():
+        t_pe = timeit(lambda: pe(cloud), it=3, warm=1)
+    return {"geometric_embedding": {"ms_per_call": t_geo, "clouds_per_call": B, "algorithmic_tflops": flops / t_geo * 1e-9,
+                                    "issued_tf32_tflops": 3 * flops / t_geo * 1e-9 * 1275.0 / 1213.0},
+            "positional_encoding": {"ms_per_call": t_pe, "clouds_per_call": B,
+                                    "what": "fused ball query/grouping + k_lrf_group + k_shared_mlp_max x2 + Conv1d (cuBLAS)"}}
+
+
 def main():
     args = parse()
     from unopose_b200.pipeline import HotPathConfig
@@ -463,6 +506,11 @@ def main():
             line["gpu_torch_baseline"] = gpu_torch_leg(cfg, sets, B, dev)
         except Exception as ex:  # reported, never fatal
             line["gpu_torch_baseline"] = {"unavailable": repr(ex)[:200]}
+    if world == 1 and not args.no_widened:
+        try:
+            line["widened_rows"] = widened_leg(B, dev)
+        except Exception as ex:  # informational (SURVEY.md §8 "next" rows f1/f2), never fatal
+            line["widened_rows"] = {"unavailable": repr(ex)[:200]}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
