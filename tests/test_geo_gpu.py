@@ -35,7 +35,8 @@ def _check_indices(d, a, d_ref, a_ref, pts, k):
 
 
 @pytest.mark.parametrize("B,N,C,k,red", [(1, 197, 256, 3, "max"), (3, 50, 64, 2, "mean"), (2, 33, 32, 3, "max"),
-                                          (2, 70, 128, 1, "max"), (1, 41, 96, 4, "mean")])
+                                          (2, 70, 128, 1, "max"), (1, 41, 96, 4, "mean"), (1, 40, 64, 5, "max"),
+                                          (1, 36, 32, 8, "mean")])
 def test_fused_embedding_vs_oracle(cuda, B, N, C, k, red):
     from unopose_b200.modules import geo
 
