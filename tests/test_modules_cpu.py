@@ -76,3 +76,67 @@ def test_training_branch_is_explicitly_unsupported():
     m = CoarsePointMatchingOneRef(Cfg(g["cfg_coarse"])).train()
     with pytest.raises(NotImplementedError):
         m(g["sp1"], g["sf1"], g["geo1"], g["sp2"], g["sf2"], g["geo2"], g["radius"], {})
+
+
+def test_batch_norm_folding_of_shared_mlp():
+    """modules/pe.py::fold_shared_mlp (what the fused MLP kernel is fed): relu(W' x + b') per layer == the eval-mode
+    conv + batch norm + ReLU stack (pointnet2/pytorch_utils.py:25-48)."""
+    from unopose_b200.modules.layers import SharedMLP
+    from unopose_b200.modules.pe import fold_shared_mlp
+
+    torch.manual_seed(3)
+    mlp = SharedMLP([6, 32, 64, 128], bn=True)
+    for layer in mlp:
+        bn = layer.normlayer.bn
+        bn.running_mean.normal_(0, 0.3)
+        bn.running_var.uniform_(0.5, 2.0)
+        bn.weight.data.uniform_(0.5, 1.5)
+        bn.bias.data.normal_(0, 0.2)
+    mlp.eval()
+    x = torch.randn(2, 6, 5, 7)
+    with torch.no_grad():
+        ref = mlp(x)
+        h = x
+        for w, b in fold_shared_mlp(mlp):
+            h = torch.relu(torch.einsum("oc,bcmn->bomn", w, h) + b.view(1, -1, 1, 1))
+    assert torch.allclose(h, ref, atol=1e-5, rtol=1e-5)
+    plain = SharedMLP([3, 32, 64, 128], bn=False).eval()     # no batch norm: conv bias passes through
+    with torch.no_grad():
+        h = x[:, :3]
+        for w, b in fold_shared_mlp(plain):
+            h = torch.relu(torch.einsum("oc,bcmn->bomn", w, h) + b.view(1, -1, 1, 1))
+        assert torch.allclose(h, plain(x[:, :3]), atol=1e-6, rtol=1e-5)
+
+
+def test_rpe_score_term_equals_reference_formulation():
+    """modules/transformer.py::_DotAttention projects the queries by W_p; the reference projects the (B,N,M,C)
+    embedding (transformer.py:392-395).  Same scores and outputs."""
+    from unopose_b200.modules.transformer import _DotAttention, _heads, _merge
+
+    torch.manual_seed(4)
+    att = _DotAttention(64, 4, relative=True).eval()
+    x = torch.randn(2, 9, 64)
+    emb = torch.randn(2, 9, 9, 64)
+    with torch.no_grad():
+        out, attn = att(x, x, emb)
+        h = att.num_heads
+        q, k, v = _heads(att.proj_q(x), h), _heads(att.proj_k(x), h), _heads(att.proj_v(x), h)
+        p = att.proj_p(emb).reshape(2, 9, 9, h, att.head_dim)
+        scores = (q @ k.transpose(-1, -2) + torch.einsum("bhnc,bnmhc->bhnm", q, p)) / att.head_dim ** 0.5
+        ref_attn = torch.softmax(scores, dim=-1)
+    assert torch.allclose(attn, ref_attn, atol=1e-6, rtol=1e-5)
+    assert torch.allclose(out, _merge(ref_attn @ v), atol=1e-6, rtol=1e-5)
+
+
+def test_fused_kernel_eligibility_is_answered_without_a_gpu():
+    from unopose_b200 import _lib
+
+    lib = _lib.load()
+    assert lib.upk_geometric_embedding_supported(256, 3) == 1 and lib.upk_geometric_embedding_supported(32, 8) == 1
+    assert lib.upk_geometric_embedding_supported(48, 3) == 0 and lib.upk_geometric_embedding_supported(256, 9) == 0
+    assert lib.upk_shared_mlp_max_supported(6, 32, 64, 128, 2048, 256) == 1
+    assert lib.upk_shared_mlp_max_supported(6, 32, 64, 128, 2048, 64) == 1
+    assert lib.upk_shared_mlp_max_supported(6, 32, 64, 128, 2048, 48) == 0      # 48 neither divides 128 nor is a multiple
+    assert lib.upk_shared_mlp_max_supported(17, 32, 64, 128, 2048, 64) == 0
+    assert lib.upk_shared_mlp_max_supported(6, 32, 64, 256, 2048, 64) == 0
+    assert lib.upk_geometric_embedding_workspace_bytes(16, 197, 256, 3) > 16 * 197 * 197 * 4 * 4

@@ -12,11 +12,20 @@ import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
-# The torch layers are the fp32 comparison: cuDNN would otherwise run the 1x1 convs in TF32 (torch's default
-# `cudnn.allow_tf32 = True`, which the reference never changes: its GPU path has 5e-4 relative error here; ours keeps
-# fp32-level accuracy with 3xTF32, i.e. it is the more exact of the two and matches the reference's CPU path).
-torch.backends.cudnn.allow_tf32 = False
-torch.backends.cuda.matmul.allow_tf32 = False
+
+
+@pytest.fixture(autouse=True)
+def _fp32_torch_layers():
+    """The torch layers are the fp32 comparison: cuDNN would otherwise run the 1x1 convs in TF32 (torch's default
+    `cudnn.allow_tf32 = True`, which the reference never changes: its GPU path has 5e-4 relative error here; ours keeps
+    fp32-level accuracy with 3xTF32, i.e. it is the more exact of the two and matches the reference's CPU path)."""
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
