@@ -420,3 +420,25 @@ def test_coarse_large_geometry(cuda):
     assert torch.equal(m["w1"], o["w1"]) and torch.equal(m["w2"], o["w2"])
     assert torch.allclose(m["cdf"], o["cdf"], rtol=5e-5, atol=1e-7)
     assert PO.rotation_geodesic_deg(R, d["R"]).max() < 3.0
+
+
+@pytest.mark.skipif(os.environ.get("UPK_TEST_EXPERIMENTAL") != "1",
+                    reason="3xFP16 similarity mode is opt-in and not yet validated on hardware (DESIGN.md §9)")
+def test_experimental_fp16_split_similarity(cuda):
+    """UPK_SIMILARITY_MODE=16: the CTA-pair GEMM with fp16 operands (3 products, 2^12 operand scale) must reproduce the
+    3xTF32 logits to fp32-GEMM accuracy."""
+    from unopose_b200 import _lib
+    from unopose_b200 import model_utils as MU
+
+    torch.manual_seed(0)
+    f1 = torch.randn(16, 2049, 256, device=cuda)
+    f2 = f1[:, torch.randperm(2049, device=cuda)] + 0.5 * torch.randn(16, 2049, 256, device=cuda)
+    ref = MU.compute_feature_similarity(f1, f2, "cosine", 0.1, True)
+    prev = _lib.load().upk_set_similarity_mode(16)
+    try:
+        got, stats = MU.compute_feature_similarity(f1, f2, "cosine", 0.1, True, return_stats=True)
+    finally:
+        _lib.load().upk_set_similarity_mode(prev)
+    ex = (torch.nn.functional.normalize(f1[:1].double(), dim=2) @ torch.nn.functional.normalize(f2[:1].double(), dim=2).transpose(1, 2)) / 0.1
+    assert (got[:1].double() - ex).abs().max() < 2e-5
+    assert (got - ref).abs().max() < 2e-5

@@ -176,7 +176,8 @@ int upk_feature_similarity_stats(const float* feat1, const float* feat2, int b, 
   if (b < 0 || n <= 1 || m <= 1 || c <= 0 || !(temp > 0.f)) return UPK_ERR_INVALID_ARG;
   if (b == 0) return UPK_OK;
   const bool aligned16 = ((reinterpret_cast<uintptr_t>(feat1) | reinterpret_cast<uintptr_t>(feat2)) & 15) == 0;
-  if (!similarity_tc_eligible(n, m, c) || similarity_mode() != 3 || !aligned16) return UPK_ERR_UNSUPPORTED;
+  if (!similarity_tc_eligible(n, m, c) || (similarity_mode() != 3 && similarity_mode() != 16) || !aligned16)
+    return UPK_ERR_UNSUPPORTED;
   const SimStatsGeom sg = sim_stats_geom(b, n, m);
   if (!stats_out || stats_bytes < sg.total_bytes || !workspace ||
       workspace_bytes < similarity_tc_workspace_bytes(b, n, m, c))

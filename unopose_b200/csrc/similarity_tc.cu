@@ -17,6 +17,7 @@
 // Pipelines: 3 smem stages (48 KB each) between TMA and MMA; 2 TMEM accumulators (2 x 256 columns)
 // between MMA and epilogue, so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <math.h>
 #include <stdlib.h>
 
@@ -52,7 +53,13 @@ struct __align__(1024) TcSmem {
 //   first operand  (is_a = 1): C[b][row][0]      second operand (is_a = 0): C[b][0][row]
 constexpr int NS_RPW = 4;   // rows per warp -> 32 rows per CTA
 
-template <int MODE>
+// F16 (experimental 3xFP16 split, UPK_SIMILARITY_MODE=16): hi = fp16(x_n * 2^12), lo = fp16(x_n * 2^12 - hi), stored as
+// halves (the outputs are then __half arrays of the same element count).  The 2^12 scale keeps the residuals out of
+// fp16's subnormal range; fp16 and tf32 both carry 11 significand bits, so the three-product sum has the accuracy of
+// 3xTF32 (scripts/dev/split_precision.py) at twice the MMA rate and half the operand bytes.
+constexpr float kF16Scale = 4096.0f;
+
+template <int MODE, bool F16 = false>
 __global__ void __launch_bounds__(256)
 k_normalize_split(const float* __restrict__ x, int rows_per_batch, int c, int normalize,
                   float* __restrict__ hi, float* __restrict__ lo,
@@ -119,8 +126,22 @@ k_normalize_split(const float* __restrict__ x, int rows_per_batch, int c, int no
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.y)); h.y = __uint_as_float(t);
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.z)); h.z = __uint_as_float(t);
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.w)); h.w = __uint_as_float(t);
+    if (F16) {
+      const float sx = v.x * kF16Scale, sy = v.y * kF16Scale, sz = v.z * kF16Scale, sw = v.w * kF16Scale;
+      const __half hx = __float2half_rn(sx), hy = __float2half_rn(sy), hz = __float2half_rn(sz), hw = __float2half_rn(sw);
+      const __half lx = __float2half_rn(sx - __half2float(hx)), ly = __float2half_rn(sy - __half2float(hy));
+      const __half lz = __float2half_rn(sz - __half2float(hz)), lw = __float2half_rn(sw - __half2float(hw));
+      uint2 ph, pl;
+      ph.x = (uint32_t)__half_as_ushort(hx) | ((uint32_t)__half_as_ushort(hy) << 16);
+      ph.y = (uint32_t)__half_as_ushort(hz) | ((uint32_t)__half_as_ushort(hw) << 16);
+      pl.x = (uint32_t)__half_as_ushort(lx) | ((uint32_t)__half_as_ushort(ly) << 16);
+      pl.y = (uint32_t)__half_as_ushort(lz) | ((uint32_t)__half_as_ushort(lw) << 16);
+      reinterpret_cast<uint2*>(reinterpret_cast<__half*>(hi) + row * c)[k] = ph;
+      reinterpret_cast<uint2*>(reinterpret_cast<__half*>(lo) + row * c)[k] = pl;
+    } else {
     hi4[k] = h;
     lo4[k] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+    }
     if (other) {
       const float4 q = q4[k];
       dot = fmaf(v.x, q.x, fmaf(v.y, q.y, fmaf(v.z, q.z, fmaf(v.w, q.w, dot))));
@@ -376,7 +397,20 @@ __device__ __forceinline__ void cluster_sync_all() {
 constexpr uint32_t kIdescTf32_2sm = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
                                     ((uint32_t)((2 * TC_BM) >> 4) << 24);
 
-template <bool STATS>
+__device__ __forceinline__ void tc_mma_f16_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  const uint32_t z = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(z) : "memory");
+}
+constexpr uint32_t kIdescF16_2sm = kIdescF16Base | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)((2 * TC_BM) >> 4) << 24);
+
+// F16: the operands are fp16 (k_normalize_split<.., true>): a 64-byte stage row holds 32 K elements instead of 16, one
+// tcgen05.mma.kind::f16 covers K = 16; the accumulator carries the 2^24 scale of the two operands.
+template <bool STATS, bool F16 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
 k_similarity_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                  const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -392,7 +426,8 @@ k_similarity_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   const int mt = 2 * mt2;                                     // 128-row tiles (statistics layout)
   const int nt = (N - off + TC_BN - 1) / TC_BN;
   const int total = batch * mt2 * nt;
-  const int kchunks = K / TC_BK;
+  constexpr int KE = F16 ? 2 * TC_BK : TC_BK;   // K elements per 64-byte stage row
+  const int kchunks = K / KE;
   const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
 
   if (threadIdx.x == 0) {
@@ -423,10 +458,10 @@ k_similarity_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         mbar_wait(&sm.empty[s], ph ^ 1);
         if (lane == 0) {
           if (leader) mbar_expect_tx(&sm.full[s], 2 * TC2_STAGE_BYTES);   // both CTAs' loads land on this barrier
-          tma_load_3d_2sm(&map_a_hi, &sm.full[s], sm.a_hi[s], kc * TC_BK, arow, b);
-          tma_load_3d_2sm(&map_b_hi, &sm.full[s], sm.b_hi[s], kc * TC_BK, brow, b);
-          tma_load_3d_2sm(&map_a_lo, &sm.full[s], sm.a_lo[s], kc * TC_BK, arow, b);
-          tma_load_3d_2sm(&map_b_lo, &sm.full[s], sm.b_lo[s], kc * TC_BK, brow, b);
+          tma_load_3d_2sm(&map_a_hi, &sm.full[s], sm.a_hi[s], kc * KE, arow, b);
+          tma_load_3d_2sm(&map_b_hi, &sm.full[s], sm.b_hi[s], kc * KE, brow, b);
+          tma_load_3d_2sm(&map_a_lo, &sm.full[s], sm.a_lo[s], kc * KE, arow, b);
+          tma_load_3d_2sm(&map_b_lo, &sm.full[s], sm.b_lo[s], kc * KE, brow, b);
         }
         __syncwarp();
         if (++s == TC2_STAGES) { s = 0; ph ^= 1; }
@@ -453,9 +488,15 @@ k_similarity_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
 #pragma unroll
             for (int kk = 0; kk < TC_BK / 8; ++kk) {
               const uint64_t adv = (uint64_t)(kk * 8 * 4 >> 4);
+              if (F16) {
+                tc_mma_f16_2sm(d_tmem, alo + adv, bhi + adv, kIdescF16_2sm, (kc | kk) ? 1u : 0u);
+                tc_mma_f16_2sm(d_tmem, ahi + adv, blo + adv, kIdescF16_2sm, 1u);
+                tc_mma_f16_2sm(d_tmem, ahi + adv, bhi + adv, kIdescF16_2sm, 1u);
+              } else {
               tc_mma_tf32_2sm(d_tmem, alo + adv, bhi + adv, kIdescTf32_2sm, (kc | kk) ? 1u : 0u);
               tc_mma_tf32_2sm(d_tmem, ahi + adv, blo + adv, kIdescTf32_2sm, 1u);
               tc_mma_tf32_2sm(d_tmem, ahi + adv, bhi + adv, kIdescTf32_2sm, 1u);
+              }
             }
             tc_commit_2sm(&sm.empty[s]);                          // stage reusable in both CTAs
             if (kc == kchunks - 1) tc_commit_2sm(&sm.tfull[acc]);   // accumulators complete in both CTAs
@@ -470,7 +511,7 @@ k_similarity_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     const int q = warp & 3;
     const int cq = (warp - 2) >> 2;          // column slice of the tile handled by this warp
     float* tr = &sm.epi[warp - 2][0][0];
-    const float inv_temp = 1.0f / temp;
+    const float inv_temp = F16 ? 1.0f / (temp * kF16Scale * kF16Scale) : 1.0f / temp;
     int it = 0;
     for (int t = cid; t < total; t += ncl, ++it) {
       const int b = t / (mt2 * nt), rem = t - b * mt2 * nt;
@@ -550,6 +591,20 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
+// fp16 operands (experimental 3xFP16 mode): same 64-byte rows, 32 halves wide
+static int make_map_f16(CUtensorMap* map, const void* base, int batch, int rows, int K, int box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return UPK_ERR_UNSUPPORTED;
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)batch};
+  cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)rows * K * 2};
+  cuuint32_t box[3] = {(cuuint32_t)(2 * TC_BK), (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? UPK_OK : UPK_ERR_INVALID_ARG;
+}
+
 static int make_map(CUtensorMap* map, const float* base, int batch, int rows, int K, int box_rows) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) return UPK_ERR_UNSUPPORTED;
@@ -568,13 +623,13 @@ int tc_make_map(void* map, const float* base, int batch, int rows, int K, int bo
   return make_map((CUtensorMap*)map, base, batch, rows, K, box_rows);
 }
 
-static int g_sim_mode = -1;  // 3 = 3xTF32 tensor cores (default), 1 = 1xTF32, 0 = fp32 SIMT
+static int g_sim_mode = -1;  // 3 = 3xTF32 tensor cores (default), 1 = 1xTF32, 0 = fp32 SIMT, 16 = experimental 3xFP16 (CTA-pair shapes)
 
 int similarity_mode() {
   if (g_sim_mode < 0) {
     const char* e = getenv("UPK_SIMILARITY_MODE");
     g_sim_mode = e ? atoi(e) : 3;
-    if (g_sim_mode != 0 && g_sim_mode != 1 && g_sim_mode != 3) g_sim_mode = 3;
+    if (g_sim_mode != 0 && g_sim_mode != 1 && g_sim_mode != 3 && g_sim_mode != 16) g_sim_mode = 3;
   }
   return g_sim_mode;
 }
@@ -624,6 +679,38 @@ int run_similarity_tc(const float* f1, const float* f2, int b, int n, int m, int
   if (stats_row && (!off || sim_type != 0 || !stats_col)) return UPK_ERR_UNSUPPORTED;
   const dim3 g1((n + 8 * NS_RPW - 1) / (8 * NS_RPW), b), g2((m + 8 * NS_RPW - 1) / (8 * NS_RPW), b);
   const size_t qs = off ? (size_t)c * sizeof(float) : 0;
+  // CTA-pair kernel (cosine, 3xTF32, enough tiles to fill the clusters; UPK_TC_2SM=0 disables it)
+  static int use_2sm = -1;
+  if (use_2sm < 0) { const char* e = getenv("UPK_TC_2SM"); use_2sm = e ? atoi(e) : 1; }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int tiles2 = b * ((n - off + 2 * TC_BM - 1) / (2 * TC_BM)) * ((m - off + TC_BN - 1) / TC_BN);
+  int rc;
+  // EXPERIMENTAL (UPK_SIMILARITY_MODE=16, opt-in, not yet validated on hardware): 3xFP16 split on the CTA-pair kernel
+  if (similarity_mode() == 16 && use_2sm && sim_type == 0 && tiles2 >= sms / 2 && c % (2 * TC_BK) == 0) {
+    k_normalize_split<0, true><<<g1, 256, qs, st>>>(f1, n, c, normalize, a_hi, a_lo, off ? f2 : nullptr, m, 1, temp, out, n, m);
+    k_normalize_split<0, true><<<g2, 256, qs, st>>>(f2, m, c, normalize, b_hi, b_lo, off ? f1 : nullptr, n, 0, temp, out, n, m);
+    count_launch(2);
+    CUtensorMap fa_hi, fa_lo, fb_hi, fb_lo;
+    if ((rc = make_map_f16(&fa_hi, a_hi, b, n, c, TC_BM))) return rc;
+    if ((rc = make_map_f16(&fa_lo, a_lo, b, n, c, TC_BM))) return rc;
+    if ((rc = make_map_f16(&fb_hi, b_hi, b, m, c, TC_BM))) return rc;
+    if ((rc = make_map_f16(&fb_lo, b_lo, b, m, c, TC_BM))) return rc;
+    const int grid2 = 2 * (tiles2 < sms / 2 ? tiles2 : sms / 2);
+    const size_t smem2 = sizeof(Tc2Smem) + 1024;
+    if (stats_row) {
+      UPK_CUDA_TRY(cudaFuncSetAttribute(k_similarity_tc2<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      k_similarity_tc2<true, true><<<grid2, TC2_THREADS, smem2, st>>>(fa_hi, fa_lo, fb_hi, fb_lo, b, n, m, c, temp, off, out,
+                                                                    stats_row, stats_col, stats_gref);
+    } else {
+      UPK_CUDA_TRY(cudaFuncSetAttribute(k_similarity_tc2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      k_similarity_tc2<false, true><<<grid2, TC2_THREADS, smem2, st>>>(fa_hi, fa_lo, fb_hi, fb_lo, b, n, m, c, temp, off, out,
+                                                                     nullptr, nullptr, 0.f);
+    }
+    count_launch();
+    UPK_RETURN_LAST_ERROR();
+  }
   if (sim_type == 0) {
     k_normalize_split<0><<<g1, 256, qs, st>>>(f1, n, c, normalize, a_hi, a_lo, off ? f2 : nullptr, m, 1, temp, out, n, m);
     k_normalize_split<0><<<g2, 256, qs, st>>>(f2, m, c, normalize, b_hi, b_lo, off ? f1 : nullptr, n, 0, temp, out, n, m);
@@ -633,17 +720,10 @@ int run_similarity_tc(const float* f1, const float* f2, int b, int n, int m, int
   }
   count_launch(2);
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-  int rc;
   if ((rc = make_map(&ma_hi, a_hi, b, n, c, TC_BM))) return rc;
   if ((rc = make_map(&ma_lo, a_lo, b, n, c, TC_BM))) return rc;
   if ((rc = make_map(&mb_hi, b_hi, b, m, c, TC_BN))) return rc;
   if ((rc = make_map(&mb_lo, b_lo, b, m, c, TC_BN))) return rc;
-  // CTA-pair kernel (cosine, 3xTF32, enough tiles to fill the clusters; UPK_TC_2SM=0 disables it)
-  static int use_2sm = -1;
-  if (use_2sm < 0) { const char* e = getenv("UPK_TC_2SM"); use_2sm = e ? atoi(e) : 1; }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int tiles = b * (off ? tiles1 : tiles0);
   const int grid = tiles < sms ? tiles : sms;
   const size_t smem = sizeof(TcSmem) + 1024;
@@ -655,7 +735,6 @@ int run_similarity_tc(const float* f1, const float* f2, int b, int n, int m, int
     kern<<<grid, TC_THREADS, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, b, n, m, c, temp, off, out, stats_row,  \
                                          stats_col, stats_gref);                                             \
   } while (0)
-  const int tiles2 = b * ((n - off + 2 * TC_BM - 1) / (2 * TC_BM)) * ((m - off + TC_BN - 1) / TC_BN);
   if (use_2sm && sim_type == 0 && terms == 3 && tiles2 >= sms / 2) {
     CUtensorMap mb_hi2, mb_lo2;   // the pair's CTAs each fetch 128 of the 256 B rows of a tile
     if ((rc = make_map(&mb_hi2, b_hi, b, m, c, TC_BM))) return rc;
@@ -687,6 +766,6 @@ int run_similarity_tc(const float* f1, const float* f2, int b, int n, int m, int
 
 extern "C" int upk_set_similarity_mode(int mode) {
   int prev = upk::similarity_mode();
-  if (mode == 0 || mode == 1 || mode == 3) upk::g_sim_mode = mode;
+  if (mode == 0 || mode == 1 || mode == 3 || mode == 16) upk::g_sim_mode = mode;
   return prev;
 }

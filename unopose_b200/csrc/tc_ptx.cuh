@@ -82,4 +82,17 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// kind::f16 (fp16 operands, fp32 accumulate): K = 16 per instruction, i.e. the same 32 bytes per operand row as a
+// kind::tf32 K = 8 step, at twice the MACs per cycle.  Used by the experimental 3xFP16 split (similarity_tc.cu).
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+// instruction descriptor fields for kind::f16 with fp16 A and B (format code 0), fp32 D, both K-major
+constexpr uint32_t kIdescF16Base = (1u << 4);
+
 }  // namespace upk
