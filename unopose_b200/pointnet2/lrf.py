@@ -1,4 +1,5 @@
-"""Per-centre local reference frames (host-side torch code; "next" row f1 of SURVEY.md §8).
+"""Per-centre local reference frames: the torch implementation (CPU tensors, autograd, `UPK_LRF_SVD=torch`); CUDA
+inference goes through `pointnet2_utils.lrf_group` (one kernel).
 
 ``LRF_batch`` follows the maths of the reference class of the same name
 (core/unopose/model/pointnet2/pointnet2_utils.py:429-481): z axis = covariance
