@@ -658,6 +658,47 @@ bool similarity_tc_eligible(int n, int m, int c) {
          get_encode() != nullptr;
 }
 
+// EXPERIMENTAL (UPK_SIMILARITY_MODE=16, opt-in, not yet validated on hardware): 3xFP16 split on the CTA-pair kernel.
+// Returns 1 if the geometry is not handled here (the caller continues with the 3xTF32 path), else a launch status.
+static int run_similarity_f16(const float* f1, const float* f2, int b, int n, int m, int c, float temp, int normalize,
+                              int sim_type, void* a_hi, void* a_lo, void* b_hi, void* b_lo, float* out, cudaStream_t st,
+                              float* stats_row, float* stats_col, float stats_gref) {
+  const char* e = getenv("UPK_TC_2SM");
+  if (e && atoi(e) == 0) return 1;
+  if (sim_type != 0 || n <= 1 || m <= 1 || c % (2 * TC_BK) != 0) return 1;
+  const int off = 1;   // background row / column peeled, as on the CTA-pair 3xTF32 path at these shapes
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int tiles2 = b * ((n - off + 2 * TC_BM - 1) / (2 * TC_BM)) * ((m - off + TC_BN - 1) / TC_BN);
+  if (tiles2 < sms / 2) return 1;
+  if (stats_row && !stats_col) return UPK_ERR_UNSUPPORTED;
+  const dim3 g1((n + 8 * NS_RPW - 1) / (8 * NS_RPW), b), g2((m + 8 * NS_RPW - 1) / (8 * NS_RPW), b);
+  const size_t qs = (size_t)c * sizeof(float);
+  k_normalize_split<0, true><<<g1, 256, qs, st>>>(f1, n, c, normalize, (float*)a_hi, (float*)a_lo, f2, m, 1, temp, out, n, m);
+  k_normalize_split<0, true><<<g2, 256, qs, st>>>(f2, m, c, normalize, (float*)b_hi, (float*)b_lo, f1, n, 0, temp, out, n, m);
+  count_launch(2);
+  CUtensorMap fa_hi, fa_lo, fb_hi, fb_lo;
+  int rc;
+  if ((rc = make_map_f16(&fa_hi, a_hi, b, n, c, TC_BM))) return rc;
+  if ((rc = make_map_f16(&fa_lo, a_lo, b, n, c, TC_BM))) return rc;
+  if ((rc = make_map_f16(&fb_hi, b_hi, b, m, c, TC_BM))) return rc;
+  if ((rc = make_map_f16(&fb_lo, b_lo, b, m, c, TC_BM))) return rc;
+  const int grid2 = 2 * (tiles2 < sms / 2 ? tiles2 : sms / 2);
+  const size_t smem2 = sizeof(Tc2Smem) + 1024;
+  if (stats_row) {
+    UPK_CUDA_TRY(cudaFuncSetAttribute(k_similarity_tc2<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    k_similarity_tc2<true, true><<<grid2, TC2_THREADS, smem2, st>>>(fa_hi, fa_lo, fb_hi, fb_lo, b, n, m, c, temp, off, out,
+                                                                  stats_row, stats_col, stats_gref);
+  } else {
+    UPK_CUDA_TRY(cudaFuncSetAttribute(k_similarity_tc2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    k_similarity_tc2<false, true><<<grid2, TC2_THREADS, smem2, st>>>(fa_hi, fa_lo, fb_hi, fb_lo, b, n, m, c, temp, off, out,
+                                                                   nullptr, nullptr, 0.f);
+  }
+  count_launch();
+  UPK_RETURN_LAST_ERROR();
+}
+
 // stats_row / stats_col (optional, both or neither; requires sim_type 0 and that the tiles start at (1,1)):
 // per-tile partial sums of 2^(v log2e - stats_gref), layouts of SimStatsGeom.
 int run_similarity_tc(const float* f1, const float* f2, int b, int n, int m, int c, float temp, int normalize,
@@ -671,6 +712,11 @@ int run_similarity_tc(const float* f1, const float* f2, int b, int n, int m, int
   float* a_lo = (float*)(w + a);
   float* b_hi = (float*)(w + 2 * a);
   float* b_lo = (float*)(w + 2 * a + bb);
+  if (similarity_mode() == 16) {   // experimental, opt-in (see run_similarity_f16); 1 = not applicable, fall through
+    const int rc16 = run_similarity_f16(f1, f2, b, n, m, c, temp, normalize, sim_type, a_hi, a_lo, b_hi, b_lo, out, st,
+                                        stats_row, stats_col, stats_gref);
+    if (rc16 != 1) return rc16;
+  }
   // peel the first row and column off when that saves tiles (2049 = 2048 + the background token); the
   // peeled entries are produced by the operand-preparation kernels
   const int tiles0 = ((n + TC_BM - 1) / TC_BM) * ((m + TC_BN - 1) / TC_BN);
@@ -679,38 +725,6 @@ int run_similarity_tc(const float* f1, const float* f2, int b, int n, int m, int
   if (stats_row && (!off || sim_type != 0 || !stats_col)) return UPK_ERR_UNSUPPORTED;
   const dim3 g1((n + 8 * NS_RPW - 1) / (8 * NS_RPW), b), g2((m + 8 * NS_RPW - 1) / (8 * NS_RPW), b);
   const size_t qs = off ? (size_t)c * sizeof(float) : 0;
-  // CTA-pair kernel (cosine, 3xTF32, enough tiles to fill the clusters; UPK_TC_2SM=0 disables it)
-  static int use_2sm = -1;
-  if (use_2sm < 0) { const char* e = getenv("UPK_TC_2SM"); use_2sm = e ? atoi(e) : 1; }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int tiles2 = b * ((n - off + 2 * TC_BM - 1) / (2 * TC_BM)) * ((m - off + TC_BN - 1) / TC_BN);
-  int rc;
-  // EXPERIMENTAL (UPK_SIMILARITY_MODE=16, opt-in, not yet validated on hardware): 3xFP16 split on the CTA-pair kernel
-  if (similarity_mode() == 16 && use_2sm && sim_type == 0 && tiles2 >= sms / 2 && c % (2 * TC_BK) == 0) {
-    k_normalize_split<0, true><<<g1, 256, qs, st>>>(f1, n, c, normalize, a_hi, a_lo, off ? f2 : nullptr, m, 1, temp, out, n, m);
-    k_normalize_split<0, true><<<g2, 256, qs, st>>>(f2, m, c, normalize, b_hi, b_lo, off ? f1 : nullptr, n, 0, temp, out, n, m);
-    count_launch(2);
-    CUtensorMap fa_hi, fa_lo, fb_hi, fb_lo;
-    if ((rc = make_map_f16(&fa_hi, a_hi, b, n, c, TC_BM))) return rc;
-    if ((rc = make_map_f16(&fa_lo, a_lo, b, n, c, TC_BM))) return rc;
-    if ((rc = make_map_f16(&fb_hi, b_hi, b, m, c, TC_BM))) return rc;
-    if ((rc = make_map_f16(&fb_lo, b_lo, b, m, c, TC_BM))) return rc;
-    const int grid2 = 2 * (tiles2 < sms / 2 ? tiles2 : sms / 2);
-    const size_t smem2 = sizeof(Tc2Smem) + 1024;
-    if (stats_row) {
-      UPK_CUDA_TRY(cudaFuncSetAttribute(k_similarity_tc2<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-      k_similarity_tc2<true, true><<<grid2, TC2_THREADS, smem2, st>>>(fa_hi, fa_lo, fb_hi, fb_lo, b, n, m, c, temp, off, out,
-                                                                    stats_row, stats_col, stats_gref);
-    } else {
-      UPK_CUDA_TRY(cudaFuncSetAttribute(k_similarity_tc2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-      k_similarity_tc2<false, true><<<grid2, TC2_THREADS, smem2, st>>>(fa_hi, fa_lo, fb_hi, fb_lo, b, n, m, c, temp, off, out,
-                                                                     nullptr, nullptr, 0.f);
-    }
-    count_launch();
-    UPK_RETURN_LAST_ERROR();
-  }
   if (sim_type == 0) {
     k_normalize_split<0><<<g1, 256, qs, st>>>(f1, n, c, normalize, a_hi, a_lo, off ? f2 : nullptr, m, 1, temp, out, n, m);
     k_normalize_split<0><<<g2, 256, qs, st>>>(f2, m, c, normalize, b_hi, b_lo, off ? f1 : nullptr, n, 0, temp, out, n, m);
@@ -720,10 +734,17 @@ int run_similarity_tc(const float* f1, const float* f2, int b, int n, int m, int
   }
   count_launch(2);
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  int rc;
   if ((rc = make_map(&ma_hi, a_hi, b, n, c, TC_BM))) return rc;
   if ((rc = make_map(&ma_lo, a_lo, b, n, c, TC_BM))) return rc;
   if ((rc = make_map(&mb_hi, b_hi, b, m, c, TC_BN))) return rc;
   if ((rc = make_map(&mb_lo, b_lo, b, m, c, TC_BN))) return rc;
+  // CTA-pair kernel (cosine, 3xTF32, enough tiles to fill the clusters; UPK_TC_2SM=0 disables it)
+  static int use_2sm = -1;
+  if (use_2sm < 0) { const char* e = getenv("UPK_TC_2SM"); use_2sm = e ? atoi(e) : 1; }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int tiles = b * (off ? tiles1 : tiles0);
   const int grid = tiles < sms ? tiles : sms;
   const size_t smem = sizeof(TcSmem) + 1024;
@@ -735,6 +756,7 @@ int run_similarity_tc(const float* f1, const float* f2, int b, int n, int m, int
     kern<<<grid, TC_THREADS, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, b, n, m, c, temp, off, out, stats_row,  \
                                          stats_col, stats_gref);                                             \
   } while (0)
+  const int tiles2 = b * ((n - off + 2 * TC_BM - 1) / (2 * TC_BM)) * ((m - off + TC_BN - 1) / TC_BN);
   if (use_2sm && sim_type == 0 && terms == 3 && tiles2 >= sms / 2) {
     CUtensorMap mb_hi2, mb_lo2;   // the pair's CTAs each fetch 128 of the 256 B rows of a tile
     if ((rc = make_map(&mb_hi2, b_hi, b, m, c, TC_BM))) return rc;
