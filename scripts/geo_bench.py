@@ -9,8 +9,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import geo_oracle as G  # noqa: E402  (dev tool: the oracle is the timed baseline here)
-from unopose_b200.modules import geo  # noqa: E402
+from unopose_b200.modules import GeometricStructureEmbedding, geo  # noqa: E402
 
 
 def timeit(fn, it=10, warm=3):
@@ -31,13 +30,21 @@ def main():
     N = int(sys.argv[2]) if len(sys.argv) > 2 else 197
     C = int(sys.argv[3]) if len(sys.argv) > 3 else 256
     dev = torch.device("cuda:0")
-    pts, dterm, w_d, b_d, w_a, b_a = G.make_inputs(1, B, N, C, dev)
+    torch.manual_seed(1)
+    mod = GeometricStructureEmbedding(dict(sigma_d=0.2, sigma_a=15, angle_k=3, reduction_a="max", hidden_dim=C)).to(dev).eval()
+    p = torch.randn(B, N - 1, 3, device=dev)
+    pts = torch.cat([torch.ones(B, 1, 3, device=dev), p / p.norm(dim=2).max(dim=1)[0].view(B, 1, 1)], 1)
+    dterm, w_d, b_d, w_a, b_a = (mod.embedding.div_term, mod.proj_d.weight.detach(), mod.proj_d.bias.detach(),
+                                 mod.proj_a.weight.detach(), mod.proj_a.bias.detach())
     fa = 180.0 / (15 * math.pi)
     torch.backends.cuda.matmul.allow_tf32 = False
     t_f = timeit(lambda: geo.geometric_embedding(pts, dterm, w_d, b_d, w_a, b_a, 0.2, fa, 3))
     t_i = timeit(lambda: geo.geometric_embedding_indices(pts, 0.2, fa, 3))
-    with torch.no_grad():
-        t_r = timeit(lambda: G.geometric_embedding(pts, dterm, w_d, b_d, w_a, b_a, 0.2, 15, 3), it=3, warm=1)
+
+    def torch_sequence():     # the reference's op sequence = the module's non-fused branch (taken when autograd is on)
+        with torch.enable_grad():
+            return mod(pts).detach()
+    t_r = timeit(torch_sequence, it=3, warm=1)
     # algorithmic work: per pair 1 distance row + k angle rows, each a C x C projection
     k = 3
     flops = 2.0 * B * N * N * (1 + k) * C * C
