@@ -8,7 +8,12 @@ import torch
 from .. import _lib as L
 
 
-def supported(hidden_dim, angle_k):
+MAX_POINTS = 4096   # the index kernel stages the cloud and one distance row per warp in shared memory (48 B per point)
+
+
+def supported(hidden_dim, angle_k, n_points=None):
+    if n_points is not None and not (angle_k < n_points <= MAX_POINTS):
+        return False
     return bool(L.load().upk_geometric_embedding_supported(int(hidden_dim), int(angle_k)))
 
 

@@ -268,7 +268,7 @@ class GeometricStructureEmbedding(nn.Module):
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             return False
         from . import geo
-        return geo.supported(self.proj_d.weight.shape[0], self.angle_k)
+        return geo.supported(self.proj_d.weight.shape[0], self.angle_k, points.shape[1])
 
     @torch.no_grad()
     def get_embedding_indices(self, points):
