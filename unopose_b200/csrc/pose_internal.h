@@ -95,6 +95,8 @@ int run_similarity_tc(const float* f1, const float* f2, int b, int n, int m, int
 // TMA descriptor of a (batch, rows, K) fp32 K-major operand, boxes of TC_BK x box_rows, SWIZZLE_64B
 // (`map` is a CUtensorMap*; UPK_ERR_UNSUPPORTED if the driver entry point is unavailable)
 int tc_make_map(void* map, const float* base, int batch, int rows, int K, int box_rows);
+// same for fp16 operands (32 halves per 64-byte box row); experimental 3xFP16 paths
+int tc_make_map_f16(void* map, const void* base, int batch, int rows, int K, int box_rows);
 
 // Exponent-sum partials produced by the similarity GEMM's epilogue (cosine logits; fused pass 1 of the fine
 // assignment): rowpart [b][npr][n] then colpart [b][npc][m] (256-byte aligned), all relative to the ONE

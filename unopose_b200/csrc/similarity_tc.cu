@@ -623,6 +623,10 @@ int tc_make_map(void* map, const float* base, int batch, int rows, int K, int bo
   return make_map((CUtensorMap*)map, base, batch, rows, K, box_rows);
 }
 
+int tc_make_map_f16(void* map, const void* base, int batch, int rows, int K, int box_rows) {
+  return make_map_f16((CUtensorMap*)map, base, batch, rows, K, box_rows);
+}
+
 static int g_sim_mode = -1;  // 3 = 3xTF32 tensor cores (default), 1 = 1xTF32, 0 = fp32 SIMT, 16 = experimental 3xFP16 (CTA-pair shapes)
 
 int similarity_mode() {
