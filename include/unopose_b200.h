@@ -129,8 +129,10 @@ int upk_three_interpolate_grad(const float* grad_out, const int* idx,
  * workspace (two normalised copies).  sim_type 0 = "cosine": f1.f2^T / temp;
  * 1 = "L2": sqrt(clamp(2 - 2 f1.f2^T, 0)) / temp. */
 size_t upk_feature_similarity_workspace_bytes(int b, int n, int m, int c, int normalize);
-/* Arithmetic of the tensor-core path (n*m >= 128^2, c % 16 == 0): 3 = tcgen05 tensor cores with the
- * 3xTF32 split (fp32-level accuracy; default), 1 = single TF32 pass, 0 = fp32 SIMT everywhere.
+/* Arithmetic of the tensor-core path (n*m >= 128^2, c % 16 == 0): 16 (default) = tcgen05 tensor cores with a
+ * three-product split of fp32 operands, fp32-level accuracy either way: 3xFP16 (operands scaled by 2^12) for
+ * normalised cosine logits on the CTA-pair shapes (enough 256x256 tiles to fill the GPU, c % 32 == 0), 3xTF32
+ * elsewhere; 3 = 3xTF32 everywhere; 1 = single TF32 pass; 0 = fp32 SIMT everywhere.
  * Also settable with the environment variable UPK_SIMILARITY_MODE.  Returns the previous mode. */
 int upk_set_similarity_mode(int mode);
 int upk_feature_similarity(const float* feat1, const float* feat2, int b, int n, int m,

@@ -422,23 +422,28 @@ def test_coarse_large_geometry(cuda):
     assert PO.rotation_geodesic_deg(R, d["R"]).max() < 3.0
 
 
-@pytest.mark.skipif(os.environ.get("UPK_TEST_EXPERIMENTAL") != "1",
-                    reason="3xFP16 similarity mode is opt-in and not yet validated on hardware (DESIGN.md §9)")
-def test_experimental_fp16_split_similarity(cuda):
-    """UPK_SIMILARITY_MODE=16: the CTA-pair GEMM with fp16 operands (3 products, 2^12 operand scale) must reproduce the
-    3xTF32 logits to fp32-GEMM accuracy."""
+def test_fp16_split_similarity_matches_tf32_split_and_fp64(cuda):
+    """The default arithmetic of the fine-shape GEMM is the 3xFP16 split (fp16 operands scaled by 2^12, three products,
+    CTA-pair kernel); it must reproduce the 3xTF32 logits and an fp64 evaluation to fp32-GEMM accuracy, and fall back
+    to 3xTF32 for operands that are not normalised (the 2^12 scale would overflow fp16)."""
     from unopose_b200 import _lib
     from unopose_b200 import model_utils as MU
 
     torch.manual_seed(0)
     f1 = torch.randn(16, 2049, 256, device=cuda)
     f2 = f1[:, torch.randperm(2049, device=cuda)] + 0.5 * torch.randn(16, 2049, 256, device=cuda)
-    ref = MU.compute_feature_similarity(f1, f2, "cosine", 0.1, True)
-    prev = _lib.load().upk_set_similarity_mode(16)
+    lib = _lib.load()
+    prev = lib.upk_set_similarity_mode(3)
     try:
+        ref = MU.compute_feature_similarity(f1, f2, "cosine", 0.1, True)
+        lib.upk_set_similarity_mode(16)
         got, stats = MU.compute_feature_similarity(f1, f2, "cosine", 0.1, True, return_stats=True)
+        big = MU.compute_feature_similarity(40.0 * f1[:2], f2[:2], "cosine", 1.0, False)   # |x| up to ~200: no fp16
     finally:
-        _lib.load().upk_set_similarity_mode(prev)
+        lib.upk_set_similarity_mode(prev)
+    assert prev == 16 or os.environ.get("UPK_SIMILARITY_MODE") is not None
     ex = (torch.nn.functional.normalize(f1[:1].double(), dim=2) @ torch.nn.functional.normalize(f2[:1].double(), dim=2).transpose(1, 2)) / 0.1
     assert (got[:1].double() - ex).abs().max() < 2e-5
     assert (got - ref).abs().max() < 2e-5
+    exb = 40.0 * f1[:2].double() @ f2[:2].double().transpose(1, 2)
+    assert torch.isfinite(big).all() and (big.double() - exb).abs().max() < 2e-6 * exb.abs().max()

@@ -85,7 +85,7 @@ int launch_fine_rows_merge(const float4* rowpart4, const float* w1, int b, int n
                            float* asum, cudaStream_t st);
 
 // tensor-core similarity path (similarity_tc.cu)
-int similarity_mode();  // 3 = 3xTF32 tcgen05 (default), 1 = 1xTF32 tcgen05, 0 = fp32 SIMT
+int similarity_mode();  // 16 = 3xFP16/3xTF32 tcgen05 (default), 3 = 3xTF32, 1 = 1xTF32 tcgen05, 0 = fp32 SIMT
 bool similarity_tc_eligible(int n, int m, int c);
 size_t similarity_tc_workspace_bytes(int b, int n, int m, int c);
 int run_similarity_tc(const float* f1, const float* f2, int b, int n, int m, int c, float temp, int normalize,
