@@ -325,6 +325,12 @@ int upk_shared_mlp_max(const float* x, int b, int cin, int m, int nsample, int c
  * compiled from the same source as the device code.  H[n,9] row-major -> R[n,9]. */
 int upk_host_procrustes_rotation(const double* H, int n, double* R_out);
 
+/* HOST function (no GPU): the z axis (least-variance eigenvector, raw sign) of the local-reference-frame kernels
+ * (upk_lrf_group, upk_global_lrf), compiled from the same source as the device code.  The raw sign is the one
+ * cuSOLVER's batched SVD returns for the last column of V (the reference keeps it when the sign vote ties,
+ * core/unopose/model/pointnet2/pointnet2_utils.py:451-456).  cov[n,6] = (xx, yy, zz, xy, xz, yz) -> z[n,3]. */
+int upk_host_lrf_z_axis(const double* cov, int n, double* z_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -114,8 +114,10 @@ def test_global_lrf_kernel(cuda):
 
 def test_lrf_group_kernel_vs_torch_lrf_batch(cuda):
     """upk_lrf_group (frames + feature assembly of QueryAndLRFGroup in one kernel) against the torch LRF_batch on the
-    same device.  Centres whose sign vote is decisive must agree as they are; where the vote ties, the torch path keeps
-    cuSOLVER's raw SVD sign and the kernel its Jacobi solver's, so (y, z) may be negated together."""
+    same device = the reference's GPU path (torch.svd -> cuSOLVER).  The kernel's solver reproduces cuSOLVER's raw sign
+    of the least-variance eigenvector (profiles/r2_lrf_sign.json), so centres whose sign vote TIES must agree too —
+    as they are, not up to a (y, z) flip.  The only exception: covariances singular to fp32 precision (balls of 1-3
+    distinct points), whose null direction has a rounding-noise sign in every implementation."""
     from unopose_b200.pointnet2 import pointnet2_utils as PU
     from unopose_b200.pointnet2.lrf import LRF_batch
     from util_clouds import batch_clouds
@@ -132,12 +134,23 @@ def test_lrf_group_kernel_vs_torch_lrf_batch(cuda):
         same = (got[:, 3:] - ref).abs().amax(dim=(1, 3))                                  # (B,N)
         flip = torch.stack([got[:, 3] - ref[:, 0], got[:, 4] + ref[:, 1], got[:, 5] + ref[:, 2]], 1).abs().amax(dim=(1, 3))
         assert (torch.minimum(same, flip) < 2e-3).float().mean() > 0.99
-        # decisive votes: recompute the vote from the torch frame's z axis (row 2 of the frame coordinates * r = height)
+        # covariance rank per centre (float64 eigenvalues of the fp32 covariance the reference hands to torch.svd)
+        x = pts.unsqueeze(3) - grouped.transpose(1, 2)
+        cov = torch.einsum("bnim,bnjm->bnij", x, x) / ns
+        w = torch.linalg.eigvalsh(cov.double())
+        full = w[..., 0] > 1e-6 * w[..., 2]
         h = -ref[:, 2] * r                                                                # z.(p - p_j)
         vote = (h > 1e-3).sum(-1) - (h < -1e-3).sum(-1)
-        decisive = vote.abs() >= 2
-        assert decisive.float().mean() > 0.3
-        assert (same[decisive] < 2e-3).float().mean() > 0.99
+        tied = vote == 0
+        print("LRF r=%.1f ns=%d: tie rate %.4f, full-rank %.4f, agree(all) %.4f, agree(full-rank) %.5f, "
+              "agree(tied & full-rank) %.5f" % (r, ns, tied.float().mean(), full.float().mean(),
+                                                (same < 2e-3).float().mean(), (same[full] < 2e-3).float().mean(),
+                                                (same[full & tied] < 2e-3).float().mean() if (full & tied).any() else 1.0))
+        assert full.float().mean() > 0.9
+        assert (same[full] < 2e-3).float().mean() >= 0.999           # incl. every tied vote: same sign as cuSOLVER
+        if (full & tied).sum() > 20:
+            assert (same[full & tied] < 2e-3).float().mean() >= 0.995
+        assert (same < 2e-3).float().mean() > 0.98                   # singular balls: a coin flip each
     # the grouper takes the kernel path under no_grad and the torch path with autograd on
     grp = PU.QueryAndLRFGroup(0.1, 64, use_xyz=True)
     feats = pts.transpose(1, 2).contiguous()

@@ -83,3 +83,32 @@ def test_degenerate_inputs_give_valid_rotations():
     # rank 1: the rotation still maximises tr(R H) = sigma_1
     tr = np.trace(R[:100] @ H[:100], axis1=1, axis2=2)
     assert np.allclose(tr, np.linalg.svd(H[:100], compute_uv=False)[:, 0], rtol=1e-9)
+
+
+def test_lrf_z_axis_sign_matches_cusolver_recording():
+    """The local-reference-frame kernels keep the RAW sign of the least-variance eigenvector when the +-1e-3 sign vote
+    ties, like the reference (pointnet2_utils.py:451-456), whose raw sign is whatever torch.svd returns: cuSOLVER's
+    batched Jacobi on a GPU.  tests/golden/lrf_svd_sign.npz holds (covariance, V) pairs recorded from torch.svd on a
+    B200 (scripts/r2_parity_probe.py: random centres `_all` and centres whose vote ties, at both PositionalEncoding
+    scales); the host build of the kernels' solver must return the same direction AND sign as V[:, -1] for every
+    covariance that is not singular to fp32 precision."""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "lrf_svd_sign.npz"))
+    lib = _lib.load()
+    checked = 0
+    for key in sorted(k[:-4] for k in g.files if k.endswith("_cov")):
+        cov, v = g[key + "_cov"].astype(np.float64), g[key + "_v"].astype(np.float64)
+        c6 = np.ascontiguousarray(np.stack([cov[:, 0, 0], cov[:, 1, 1], cov[:, 2, 2], cov[:, 0, 1], cov[:, 0, 2],
+                                            cov[:, 1, 2]], 1))
+        z = np.empty((len(cov), 3))
+        assert lib.upk_host_lrf_z_axis(c6.ctypes.data, len(cov), z.ctypes.data) == 0
+        w = np.linalg.eigvalsh(cov)
+        full = w[:, 0] > 1e-7 * w[:, 2]
+        # well-separated smallest eigenvalue: direction defined to fp32 accuracy
+        sep = full & ((w[:, 1] - w[:, 0]) > 1e-3 * w[:, 2])
+        dot = (z * v[:, :, 2]).sum(1)
+        assert (dot[full] > 0).all(), key
+        assert (dot[sep] > 1 - 1e-4).all(), key
+        checked += int(full.sum())
+    assert checked > 1500

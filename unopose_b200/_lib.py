@@ -61,6 +61,7 @@ _SIGNATURES = {
     "upk_lrf_group": [c_f, c_f, c_f, c_i, c_i, c_i, c_fl, c_fl, c_i, c_i, c_f, c_st],
     "upk_transform_points": [c_f, c_f, c_f, c_i, c_i, c_f, c_st],
     "upk_host_procrustes_rotation": [c_f, c_i, c_f],
+    "upk_host_lrf_z_axis": [c_f, c_i, c_f],
 }
 
 # size_t-returning workspace queries
