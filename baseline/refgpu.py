@@ -1,0 +1,149 @@
+"""Loader for the staged, UNMODIFIED reference (baseline/_ref/, see stage_reference.py) — test / bench infrastructure.
+
+`load()` imports the reference's own `core.unopose.utils.model_utils`, `core.unopose.model.pointnet2.pointnet2_utils`,
+`transformer` and the two matching modules from baseline/_ref with
+
+  * `core.unopose.model.pointnet2._ext` = the reference's extension compiled unmodified for sm_100a
+    (oracle/_ref/ref_pointnet2_ext.so, oracle/build_ref_ext.py) — its stock GPU code path;
+  * `detectron2.utils.logger` stubbed (two no-op log helpers pulled in by loss_utils.py:4; detectron2 is not installed).
+
+`patched(ns)` is a context manager that swaps in unopose_b200 exactly the way INTEGRATION.md §1-2 tells a maintainer
+to (the `_ext` module and the pose-function names), leaving every other line of the reference's Python as it is, and
+restores the stock functions on exit.  Never imported by the product (unopose_b200/).
+"""
+import contextlib
+import importlib
+import os
+import sys
+import types
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_ROOT = os.path.join(HERE, "_ref")
+ROOT = os.path.dirname(HERE)
+
+POSE_NAMES = ("compute_feature_similarity", "compute_coarse_Rt", "compute_coarse_Rt_overlap", "compute_fine_Rt",
+              "compute_fine_Rt_overlap", "weighted_procrustes", "WeightedProcrustes", "sample_pts_feats",
+              "sample_pts_feats_wlrf", "gather_pts_feats", "gather_pts_feats_wlrf")
+
+_ns = None
+
+
+def available():
+    return os.path.exists(os.path.join(REF_ROOT, "core", "unopose", "utils", "model_utils.py"))
+
+
+def _stub_detectron2():
+    if "detectron2.utils.logger" in sys.modules:
+        return
+    d2l = types.ModuleType("detectron2.utils.logger")
+    d2l.log_first_n = d2l.log_every_n = lambda *a, **k: None
+    sys.modules.setdefault("detectron2", types.ModuleType("detectron2"))
+    sys.modules.setdefault("detectron2.utils", types.ModuleType("detectron2.utils"))
+    sys.modules["detectron2.utils.logger"] = d2l
+
+
+def load(need_ext=True):
+    """-> namespace(model_utils, pointnet2_utils, transformer, coarse_mod, fine_mod, ext) of the stock reference."""
+    global _ns
+    if _ns is not None:
+        return _ns
+    if not available():
+        raise RuntimeError("reference not staged: run `python baseline/stage_reference.py` where /root/reference exists")
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    if REF_ROOT not in sys.path:
+        sys.path.insert(0, REF_ROOT)
+    _stub_detectron2()
+    ext = None
+    if need_ext:
+        from oracle import ref_ext
+
+        ext = ref_ext.load()
+        if ext is None:
+            raise RuntimeError("oracle/_ref/ref_pointnet2_ext.so missing (python oracle/build_ref_ext.py)")
+        sys.modules["core.unopose.model.pointnet2._ext"] = ext
+    else:
+        import builtins
+
+        builtins.__POINTNET2_SETUP__ = True
+    pu = importlib.import_module("core.unopose.model.pointnet2.pointnet2_utils")
+    if ext is not None:
+        pu._ext = ext
+    mu = importlib.import_module("core.unopose.utils.model_utils")
+    tr = importlib.import_module("core.unopose.model.transformer")
+    cm = importlib.import_module("core.unopose.model.oneref_predator_coarse_point_matching")
+    fm = importlib.import_module("core.unopose.model.oneref_predator_fine_point_matching")
+    assert os.path.realpath(mu.__file__).startswith(os.path.realpath(REF_ROOT)), mu.__file__
+    _ns = types.SimpleNamespace(model_utils=mu, pointnet2_utils=pu, transformer=tr, coarse_mod=cm, fine_mod=fm, ext=ext)
+    return _ns
+
+
+@contextlib.contextmanager
+def patched(ns=None, record=None):
+    """INTEGRATION.md §1-2 applied to the loaded reference: `_ext` -> unopose_b200.pointnet2._ext, pose functions ->
+    unopose_b200.model_utils (in model_utils itself and in the module globals that bound the names at import time).
+    `record` (a list) receives (name, output) of every `_ext` call made while patched."""
+    ns = ns or load()
+    import unopose_b200.model_utils as new_mu
+    import unopose_b200.pointnet2._ext as new_ext
+
+    ext = new_ext if record is None else recording_ext(new_ext, record)
+    saved = []
+
+    def swap(mod, name, val):
+        saved.append((mod, name, getattr(mod, name)))
+        setattr(mod, name, val)
+
+    swap(ns.pointnet2_utils, "_ext", ext)
+    for mod in (ns.model_utils, ns.coarse_mod, ns.fine_mod, ns.transformer):
+        for name in POSE_NAMES:
+            if hasattr(mod, name):
+                swap(mod, name, getattr(new_mu, name))
+    try:
+        yield ns
+    finally:
+        for mod, name, val in reversed(saved):
+            setattr(mod, name, val)
+
+
+def recording_ext(ext, record):
+    """Proxy of an `_ext` module that appends (function name, output) of every call to `record`."""
+    proxy = types.SimpleNamespace()
+    for name in ("gather_points", "gather_points_grad", "furthest_point_sampling", "three_nn", "three_interpolate",
+                 "three_interpolate_grad", "ball_query", "group_points", "group_points_grad"):
+        fn = getattr(ext, name)
+
+        def wrap(*a, _fn=fn, _name=name):
+            out = _fn(*a)
+            record.append((_name, out))
+            return out
+
+        setattr(proxy, name, wrap)
+    return proxy
+
+
+@contextlib.contextmanager
+def recording(ns, record):
+    """Record the stock reference's `_ext` calls (same format as patched(record=...))."""
+    saved = ns.pointnet2_utils._ext
+    ns.pointnet2_utils._ext = recording_ext(saved, record)
+    try:
+        yield ns
+    finally:
+        ns.pointnet2_utils._ext = saved
+
+
+class Cfg(dict):
+    """dict with attribute access and .get, like the OmegaConf nodes the reference passes to its modules."""
+    __getattr__ = dict.__getitem__
+
+
+def real_cfgs():
+    """Module configs of configs/main_cfg.py:128-181 (values copied as data: shapes of the hot path)."""
+    coarse = Cfg(nblock=3, input_dim=256, hidden_dim=256, out_dim=256, temp=0.1, sim_type="cosine", normalize_feat=True,
+                 loss_predator_thres=0.15, loss_dis_thres=0.3, nproposal1=6000, nproposal2=300)
+    fine = Cfg(nblock=3, input_dim=256, hidden_dim=256, out_dim=256, pe_radius1=0.1, pe_radius2=0.2, focusing_factor=3,
+               temp=0.1, sim_type="cosine", normalize_feat=True, loss_predator_thres=0.15, loss_dis_thres=0.3,
+               use_lrf=True, use_xyz=True, nsample1=64, nsample2=256)
+    geo = Cfg(sigma_d=0.2, sigma_a=15, angle_k=3, reduction_a="max", hidden_dim=256)
+    return coarse, fine, geo

@@ -140,3 +140,42 @@ def test_fused_kernel_eligibility_is_answered_without_a_gpu():
     assert lib.upk_shared_mlp_max_supported(17, 32, 64, 128, 2048, 64) == 0
     assert lib.upk_shared_mlp_max_supported(6, 32, 64, 256, 2048, 64) == 0
     assert lib.upk_geometric_embedding_workspace_bytes(16, 197, 256, 3) > 16 * 197 * 197 * 4 * 4
+
+
+def _real_inputs():
+    import numpy as np
+
+    from unopose_b200.synthetic import matching_batch
+
+    g = np.load(os.path.join(GOLD, "modules_real.npz"))
+    d = matching_batch(int(g["seed_inputs"]), 1, 196, 256, kind="ball")
+    T = torch.from_numpy
+    return g, T(d["pts1"]), T(d["pts2"]), T(d["f1"][:, 1:].copy()), T(d["f2"][:, 1:].copy())
+
+
+REAL_C = Cfg(nblock=3, input_dim=256, hidden_dim=256, out_dim=256, temp=0.1, sim_type="cosine", normalize_feat=True,
+             nproposal1=6000, nproposal2=300)
+REAL_G = Cfg(sigma_d=0.2, sigma_a=15, angle_k=3, reduction_a="max", hidden_dim=256)
+
+
+def test_real_config_modules_match_reference_features():
+    """GeometricStructureEmbedding + CoarsePointMatchingOneRef at the REAL config (hidden 256, 3 blocks, 196 points)
+    against the reference modules' outputs (tests/golden/make_real_golden.py); weights are key-addressed
+    (tests/util_state.py), inputs regenerated from the seed.  CPU: the torch branches of the product modules."""
+    from unopose_b200.modules import CoarsePointMatchingOneRef, GeometricStructureEmbedding
+    from util_state import keyed_state_dict
+
+    g, sp1, sp2, sf1, sf2 = _real_inputs()
+    geo = GeometricStructureEmbedding(REAL_G).eval()
+    geo.load_state_dict(keyed_state_dict(geo.state_dict(), int(g["seed_weights"])))
+    m = CoarsePointMatchingOneRef(REAL_C).eval()
+    m.load_state_dict(keyed_state_dict(m.state_dict(), int(g["seed_weights"])))
+    bgp = torch.ones(1, 1, 3)
+    with torch.no_grad():
+        geo1 = geo(torch.cat([bgp, sp1], 1))
+        geo2 = geo(torch.cat([bgp, sp2], 1))
+        g1, g2, score = m.matching_features(sf1, geo1, sf2, geo2)
+    assert torch.allclose(geo1[:, ::7, ::5], torch.from_numpy(g["geo1_sample"]), atol=2e-5, rtol=1e-5)
+    assert abs(float(geo1.mean()) - float(g["geo1_mean"])) < 1e-6
+    assert torch.allclose(g1, torch.from_numpy(g["coarse_g1"]), atol=2e-5, rtol=1e-4)
+    assert torch.allclose(g2, torch.from_numpy(g["coarse_g2"]), atol=2e-5, rtol=1e-4)

@@ -162,3 +162,32 @@ def test_lrf_group_kernel_vs_torch_lrf_batch(cuda):
     d = (a[:, 3:] - b[:, 3:]).abs().amax(dim=(1, 3))
     f = torch.stack([a[:, 3] - b[:, 3], a[:, 4] + b[:, 4], a[:, 5] + b[:, 5]], 1).abs().amax(dim=(1, 3))
     assert (torch.minimum(d, f) < 2e-3).float().mean() > 0.99
+
+
+def test_real_config_modules_match_reference_features_gpu(cuda):
+    """Same as tests/test_modules_cpu.py::test_real_config_modules_match_reference_features, on the GPU: the geometric
+    embedding runs the fused tcgen05 kernels (f2), the coarse module its CUDA path, at the REAL config, against the
+    reference modules' outputs (tests/golden/modules_real.npz)."""
+    import numpy as np
+
+    from test_modules_cpu import REAL_C, REAL_G, _real_inputs
+    from unopose_b200.modules import CoarsePointMatchingOneRef, GeometricStructureEmbedding
+    from util_state import keyed_state_dict
+
+    g, sp1, sp2, sf1, sf2 = _real_inputs()
+    sp1, sp2, sf1, sf2 = (x.to(cuda) for x in (sp1, sp2, sf1, sf2))
+    geo = GeometricStructureEmbedding(REAL_G).eval()
+    geo.load_state_dict(keyed_state_dict(geo.state_dict(), int(g["seed_weights"])))
+    m = CoarsePointMatchingOneRef(REAL_C, return_feat=True).eval()
+    m.load_state_dict(keyed_state_dict(m.state_dict(), int(g["seed_weights"])))
+    geo, m = geo.to(cuda), m.to(cuda)
+    bgp = torch.ones(1, 1, 3, device=cuda)
+    with torch.no_grad():
+        geo1 = geo(torch.cat([bgp, sp1], 1))
+        geo2 = geo(torch.cat([bgp, sp2], 1))
+        ep, g1, g2 = m(sp1, sf1, geo1, sp2, sf2, geo2, torch.ones(1, device=cuda), {})
+    T = lambda k: torch.from_numpy(np.asarray(g[k])).to(cuda)
+    assert torch.allclose(geo1[:, ::7, ::5], T("geo1_sample"), atol=5e-5, rtol=1e-4)
+    assert torch.allclose(g1, T("coarse_g1"), atol=2e-4, rtol=1e-3)
+    assert torch.allclose(g2, T("coarse_g2"), atol=2e-4, rtol=1e-3)
+    assert (torch.det(ep["init_R"].double()) - 1).abs().max() < 1e-5
