@@ -474,3 +474,22 @@ def test_against_reference_golden_at_real_sizes(cuda):
             assert abs(float(s[b]) - float(g["coarse_s"][b])) <= 2e-4 * float(g["coarse_s"][b])
         else:   # a near-tied hypothesis won (LAPACK vs our solver noise): scores equal to float noise
             assert abs(float(s[b]) - float(g["coarse_s"][b])) <= 1e-4 * float(g["coarse_s"][b])
+
+
+@pytest.mark.parametrize("B,n,c", [(2, 196, 256), (16, 196, 256), (3, 64, 32), (5, 300, 64), (130, 100, 32)])
+def test_coarse_cdf_bit_exact_vs_torch(cuda, B, n, c):
+    """The masks AND the sampling CDF of the coarse solver are bit-identical to the reference's GPU torch path (the
+    cluster kernel of coarse_assign.cu reproduces the summation order of ATen's softmax / cumsum CUDA kernels), so
+    every uniform draw selects the same correspondence as the reference: zero flipped draws.  B >= 2: for a single
+    row torch's cumsum goes through cub::DeviceScan, whose float addition order is not reproducible by design."""
+    H, K = 3000, 100
+    d = batch(500 + n, B, n, c, cuda)
+    atten = PO.feature_similarity(d["f1"], d["f2"], "cosine", 0.1, True)
+    u = torch.rand(B, 3 * H, generator=torch.Generator().manual_seed(B)).to(cuda)
+    for score in (d["score"], None):
+        R, t, s, m = MU()._coarse(atten, score, d["pts1"], d["pts2"], None, H, K, u=u, return_debug=True)
+        Ro, to, so, o = PO.coarse_pose(atten, score, d["pts1"], d["pts2"], None, H, K, u=u, debug=True)
+        assert torch.equal(m["w1"], o["w1"]) and torch.equal(m["w2"], o["w2"])
+        nbits = int((m["cdf"].view(torch.int32) != o["cdf"].view(torch.int32)).sum())
+        assert nbits == 0, (nbits, float((m["cdf"] - o["cdf"]).abs().max()))
+        assert torch.equal(m["idx1"].reshape(B, -1).long(), o["idx1"]) and torch.equal(m["idx2"].reshape(B, -1).long(), o["idx2"])

@@ -415,11 +415,16 @@ int upk_coarse_pose(const float* atten, const float* score1, int score1_ld, cons
   if (cv.bytes() > workspace_bytes) return UPK_ERR_INVALID_ARG;
   if (!model_pts) { model_pts = pts2; n_model = n2; }
   int rc;
-  // (a single-CTA-per-instance fused variant of these three steps, matrix resident in smem, was
-  //  measured at 70 us against ~50 us for the tile pipeline at B = 16: too little parallelism)
-  if ((rc = run_assignment_labels(atten, score1, score1_ld, score2, score2_ld, b, g, w.a, w.w1, w.w2, st))) return rc;
-  if ((rc = run_coarse_P(atten, score1, score1_ld, score2, score2_ld, b, g, w.a, w.w1, w.w2, w.pmat, w.prow, st))) return rc;
-  if ((rc = run_cdf(w.pmat, w.prow, b, n1, n2, g.ntc, w.cdf, st))) return rc;
+  // masks + sampling CDF: one cluster kernel (8 CTAs per instance, DSMEM), bit-exact with torch's CUDA kernels.
+  // (a single-CTA-per-instance fused variant was measured at 70 us against ~50 us for the six launches of the tile
+  //  pipeline at B = 16: too little parallelism)
+  rc = run_coarse_assign_exact(atten, score1, score1_ld, score2, score2_ld, b, n1 + 1, n2 + 1, w.w1, w.w2, w.cdf, st);
+  if (rc == UPK_ERR_UNSUPPORTED) {   // geometry outside the cluster kernel: the tile pipeline (close to, not bit-identical with torch)
+    if ((rc = run_assignment_labels(atten, score1, score1_ld, score2, score2_ld, b, g, w.a, w.w1, w.w2, st))) return rc;
+    if ((rc = run_coarse_P(atten, score1, score1_ld, score2, score2_ld, b, g, w.a, w.w1, w.w2, w.pmat, w.prow, st))) return rc;
+    rc = run_cdf(w.pmat, w.prow, b, n1, n2, g.ntc, w.cdf, st);
+  }
+  if (rc) return rc;
   {
     dim3 grid(ceil_div(n_hyp, HY_THREADS), b);
     k_hypotheses<<<grid, HY_THREADS, 0, st>>>(w.cdf, u, pts1, pts2, n1, n2, n_hyp, 0, n_hyp,
@@ -476,7 +481,8 @@ int upk_coarse_assignment(const float* atten, const float* score1, int score1_ld
   float* pmat = cv.take<float>((size_t)b * n1 * n2);
   double* prow = cv.take<double>((size_t)b * n1 * g.ntc);
   if (cv.bytes() > workspace_bytes) return UPK_ERR_INVALID_ARG;
-  int rc;
+  int rc = run_coarse_assign_exact(atten, score1, score1_ld, score2, score2_ld, b, n1 + 1, n2 + 1, w1_out, w2_out, cdf_out, st);
+  if (rc != UPK_ERR_UNSUPPORTED) return rc;
   if ((rc = run_assignment_labels(atten, score1, score1_ld, score2, score2_ld, b, g, a, w1_out, w2_out, st))) return rc;
   if ((rc = run_coarse_P(atten, score1, score1_ld, score2, score2_ld, b, g, a, w1_out, w2_out, pmat, prow, st))) return rc;
   return run_cdf(pmat, prow, b, n1, n2, g.ntc, cdf_out, st);
