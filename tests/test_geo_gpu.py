@@ -45,6 +45,9 @@ def test_fused_embedding_vs_oracle(cuda, B, N, C, k, red):
     d, a = geo.geometric_embedding_indices(pts, 0.2, fa, k)
     d_ref, a_ref = G.embedding_indices(pts, 0.2, 15, k)
     bad = _check_indices(d, a, d_ref, a_ref, pts, k)
+    # the distance indices are BIT-identical to the reference's GPU path, diagonal (cancellation noise) included: the
+    # kernel rounds x.y like cuBLAS (fma chain) and |x|^2 like ATen's GPU reduction, (x0^2 + x2^2) + x1^2
+    assert torch.equal(d, d_ref), int((d != d_ref).sum())
     out = geo.geometric_embedding(pts, dterm, w_d, b_d, w_a, b_a, 0.2, fa, k, red)
     # (1) given OUR indices, the oracle's embedding (cuBLAS SGEMM on this device; fp64 on the host as the judge)
     ref = G.embed_from_indices(d, a, dterm, w_d, b_d, w_a, b_a, red)

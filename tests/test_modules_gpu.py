@@ -187,7 +187,10 @@ def test_real_config_modules_match_reference_features_gpu(cuda):
         geo2 = geo(torch.cat([bgp, sp2], 1))
         ep, g1, g2 = m(sp1, sf1, geo1, sp2, sf2, geo2, torch.ones(1, device=cuda), {})
     T = lambda k: torch.from_numpy(np.asarray(g[k])).to(cuda)
-    assert torch.allclose(geo1[:, ::7, ::5], T("geo1_sample"), atol=5e-5, rtol=1e-4)
+    # the golden ran on the CPU; the diagonal d_ii (sqrt of cancellation noise) follows the GPU path's rounding here
+    offd = (torch.arange(0, 197, 7, device=cuda).view(-1, 1) != torch.arange(0, 197, 5, device=cuda).view(1, -1))
+    dg = (geo1[:, ::7, ::5] - T("geo1_sample")).abs().amax(dim=3)
+    assert dg[:, offd].max() <= 5e-5 and dg.max() <= 2e-2
     assert torch.allclose(g1, T("coarse_g1"), atol=2e-4, rtol=1e-3)
     assert torch.allclose(g2, T("coarse_g2"), atol=2e-4, rtol=1e-3)
     assert (torch.det(ep["init_R"].double()) - 1).abs().max() < 1e-5

@@ -273,14 +273,14 @@ k_score(const float* __restrict__ pts1, const float* __restrict__ model, const f
       xa[0] = fmaf(d2, ra[6], fmaf(d1, ra[3], d0 * ra[0]));
       xa[1] = fmaf(d2, ra[7], fmaf(d1, ra[4], d0 * ra[1]));
       xa[2] = fmaf(d2, ra[8], fmaf(d1, ra[5], d0 * ra[2]));
-      xa[3] = __fadd_rn(__fadd_rn(__fmul_rn(xa[0], xa[0]), __fmul_rn(xa[1], xa[1])), __fmul_rn(xa[2], xa[2]));
+      xa[3] = sumsq3_torch(xa[0], xa[1], xa[2]);
     }
     {
       const float d0 = p0 - ttb[0], d1 = p1 - ttb[1], d2 = p2 - ttb[2];
       xb[0] = fmaf(d2, rb[6], fmaf(d1, rb[3], d0 * rb[0]));
       xb[1] = fmaf(d2, rb[7], fmaf(d1, rb[4], d0 * rb[1]));
       xb[2] = fmaf(d2, rb[8], fmaf(d1, rb[5], d0 * rb[2]));
-      xb[3] = __fadd_rn(__fadd_rn(__fmul_rn(xb[0], xb[0]), __fmul_rn(xb[1], xb[1])), __fmul_rn(xb[2], xb[2]));
+      xb[3] = sumsq3_torch(xb[0], xb[1], xb[2]);
     }
     float best_a, best_b;
     nn_min_expansion2(mx, my, mz, mn, nm_pad, xa, xb, best_a, best_b);

@@ -40,6 +40,16 @@ __device__ __forceinline__ float sqdist_ref(float dx, float dy, float dz) {
   return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
 }
 
+// torch.sum(v ** 2, dim=-1) over a last dimension of 3 ON THE GPU: the products are rounded separately and ATen's
+// reduction kernel adds them as (v0^2 + v2^2) + v1^2 — read off a B200 run (scripts/dev/diag_bmm_k3.py: 0 of 1.2 M
+// values differ with this order, 22 % with (v0^2 + v1^2) + v2^2, which is what CPU torch computes).  Together with
+// cuBLAS's K = 3 dot product, fma(x2, y2, fma(x1, y1, x0 * y0)) (same experiment, 0 mismatches over four shapes), this
+// makes the expansion-form squared distances of pairwise_distance (model_utils.py:246-256) bit-identical to the
+// reference's GPU path for identical operands.
+__device__ __forceinline__ float sumsq3_torch(float x, float y, float z) {
+  return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(z, z)), __fmul_rn(y, y));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
@@ -162,8 +172,7 @@ __device__ __forceinline__ void stage_model_soa(const float* __restrict__ model,
     float x = 1e15f, y = 1e15f, z = 1e15f;
     if (j < nm) { x = model[j * 3 + 0]; y = model[j * 3 + 1]; z = model[j * 3 + 2]; }
     mx[j] = x; my[j] = y; mz[j] = z;
-    // y2 = sum(y**2, -1): products rounded separately, then summed
-    mn[j] = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+    mn[j] = sumsq3_torch(x, y, z);   // y2 = torch.sum(y ** 2, -1)
   }
 }
 

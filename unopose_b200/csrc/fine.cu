@@ -128,7 +128,7 @@ k_fine_inliers(const float* __restrict__ pts1, const float* __restrict__ model,
     x0 = fmaf(d2, R[6], fmaf(d1, R[3], d0 * R[0]));
     x1 = fmaf(d2, R[7], fmaf(d1, R[4], d0 * R[1]));
     x2 = fmaf(d2, R[8], fmaf(d1, R[5], d0 * R[2]));
-    xx = __fadd_rn(__fadd_rn(__fmul_rn(x0, x0), __fmul_rn(x1, x1)), __fmul_rn(x2, x2));
+    xx = sumsq3_torch(x0, x1, x2);
   }
   float best = INFINITY;
   const float* mb = model + (size_t)b * nm * 3;

@@ -200,14 +200,16 @@ k_lrf_group(const float* __restrict__ centres, const float* __restrict__ new_xyz
   float* L = O + (use_xyz ? 3 * plane : 0);
   const float* Q = new_xyz + ((size_t)b * n + i) * 3;
   const float nx = Q[0], ny = Q[1], nz = Q[2];
+  // `x / self.r_lrf` with a Python scalar: ATen's CUDA division multiplies by the fp32 reciprocal
+  const float inv_r = __fdiv_rn(1.0f, r);
   for (int j = lane; j < ns; j += 32) {
     const float px = gx[j], py = gy[j], pz = gz[j];
     if (use_xyz) {
       float ox = px - nx, oy = py - ny, oz = pz - nz;
-      if (normalize_xyz) { ox /= r; oy /= r; oz /= r; }
+      if (normalize_xyz) { ox *= inv_r; oy *= inv_r; oz *= inv_r; }
       O[j] = ox; O[plane + j] = oy; O[2 * plane + j] = oz;
     }
-    const float qx = (px - cx) / r, qy = (py - cy) / r, qz = (pz - cz) / r;
+    const float qx = (px - cx) * inv_r, qy = (py - cy) * inv_r, qz = (pz - cz) * inv_r;
     L[j] = x0 * qx + x1 * qy + x2 * qz;
     L[plane + j] = y0 * qx + y1 * qy + y2 * qz;
     L[2 * plane + j] = z0 * qx + z1 * qy + z2 * qz;
