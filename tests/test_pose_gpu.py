@@ -21,6 +21,13 @@ ROT_TOL_DEG = 1e-3
 T_TOL_REL = 1e-5
 
 
+def _t_close(t, to):
+    """North-star translation tolerance: 1e-5 relative.  For a near-zero translation (|t| << the unit cloud radius) the
+    relative measure is dominated by the fp32 rounding of the REFERENCE's own SVD (c_ref - R c_src with |c| ~ 1 and
+    1e-7 noise on R), so an absolute floor of 5e-7 applies there."""
+    return bool(PO.relative_translation_error(t, to) <= T_TOL_REL) or bool((t.double() - to.double()).norm() <= 5e-7)
+
+
 def MU():
     from unopose_b200 import model_utils
 
@@ -112,29 +119,57 @@ def test_coarse_stagewise(cuda, seed, n, H, K):
     assert torch.equal(s, m["scores"].max(1)[0])
 
 
-def test_coarse_end_to_end_vs_oracle(cuda):
-    """Whole solver vs the oracle on the same device with the same draws: the selected pool index
-    must agree (bit-exact) in the overwhelming majority of instances, and R/t must then meet the
-    tolerance.  A disagreement is only tolerated when the two winners score within 1e-4 relative
-    (float noise deciding between near-identical hypotheses, SURVEY.md §7.3 #1/#2)."""
-    n, H, K, B = 196, 5000, 300, 4
+def _coarse_agreement(cuda, seeds, B, n, H, K, chunk_oracle=False):
+    """Whole coarse solver vs the oracle (= the reference's torch path on this GPU) with the same atten and draws.
+    Returns (agree, total, records of the disagreements); asserts what must hold for EVERY instance."""
     agree = total = 0
-    for seed in range(5):
-        d = batch(100 + seed, B, n, 256, cuda)
+    bad = []
+    for seed in seeds:
+        d = batch(seed, B, n, 256, cuda)
         atten = PO.feature_similarity(d["f1"], d["f2"], "cosine", 0.1, True)
         u = torch.rand(B, 3 * H, generator=torch.Generator().manual_seed(seed)).to(cuda)
         R, t, s, m = MU()._coarse(atten, d["score"], d["pts1"], d["pts2"], None, H, K, u=u, return_debug=True)
-        Ro, to, so, o = PO.coarse_pose(atten, d["score"], d["pts1"], d["pts2"], None, H, K, u=u, debug=True)
+        if chunk_oracle:   # one instance at a time (memory); the draws are compared per instance below
+            per = [PO.coarse_pose(atten[b:b + 1], d["score"][b:b + 1], d["pts1"][b:b + 1], d["pts2"][b:b + 1], None, H, K,
+                                  u=u[b:b + 1], debug=True) for b in range(B)]
+            per = [(x[0][0], x[1][0], x[2][0], {k: v[0] for k, v in x[3].items()}) for x in per]
+        else:
+            Ro, to, so, o = PO.coarse_pose(atten, d["score"], d["pts1"], d["pts2"], None, H, K, u=u, debug=True)
+            per = [(Ro[b], to[b], so[b], {k: v[b] for k, v in o.items()}) for b in range(B)]
+            # same CDF bits -> every draw picks the same correspondence as the reference
+            assert torch.equal(m["idx1"].reshape(B, -1).long(), o["idx1"]) and torch.equal(m["idx2"].reshape(B, -1).long(), o["idx2"])
         for b in range(B):
+            Ro, to, so, o = per[b]
             total += 1
-            if int(m["pool"][b]) == int(o["pool"][b]):
+            mine, theirs = int(m["pool"][b]), int(o["pool"])
+            if mine == theirs:
                 agree += 1
-                assert PO.rotation_geodesic_deg(R[b], Ro[b]) <= ROT_TOL_DEG
-                assert PO.relative_translation_error(t[b], to[b]) <= T_TOL_REL
-                assert abs(float(s[b]) - float(so[b])) <= 2e-4 * abs(float(so[b]))
+                assert PO.rotation_geodesic_deg(R[b], Ro) <= ROT_TOL_DEG
+                assert _t_close(t[b], to)
+                assert abs(float(s[b]) - float(so)) <= 2e-4 * abs(float(so))
             else:
-                assert abs(float(s[b]) - float(so[b])) <= 1e-4 * abs(float(so[b]))
-    assert agree >= 0.9 * total, (agree, total)
+                # float noise (our fp64 Jacobi vs cuSOLVER's fp32 SVD, ~1e-7 on R) decided between two near-tied
+                # hypotheses: our winner must be one the oracle kept, scored within 1e-4 of its winner BY THE ORACLE,
+                # and our R / t for it must be the oracle's R / t for the same pool index
+                otop = o["top"].tolist()
+                assert mine in otop
+                k = otop.index(mine)
+                gap = float((o["scores"].max() - o["scores"][k]) / o["scores"].max())
+                rank = int((o["scores"] > o["scores"][k]).sum())
+                assert gap <= 1e-4, gap
+                assert PO.rotation_geodesic_deg(R[b], o["Rs"][mine]) <= ROT_TOL_DEG
+                assert _t_close(t[b], o["ts"][mine])
+                bad.append(dict(seed=seed, b=b, oracle_rank_of_our_winner=rank, oracle_score_gap_rel=gap,
+                                rot_deg_between_winners=float(PO.rotation_geodesic_deg(R[b], Ro))))
+    return agree, total, bad
+
+
+def test_coarse_end_to_end_vs_oracle(cuda):
+    """Selected pool index vs the reference's GPU torch path, same draws: measured on B200 (profiles/r2_parity_coarse.json)
+    117 of 118 instances agree at H = 5000; the threshold is the measured count minus one instance."""
+    agree, total, bad = _coarse_agreement(cuda, range(100, 110), 4, 196, 5000, 300)
+    print("coarse pool-index agreement: %d / %d, disagreements: %s" % (agree, total, bad))
+    assert total == 40 and agree >= 38, (agree, total, bad)
 
 
 def test_coarse_api_rng_and_variants(cuda):
@@ -344,12 +379,16 @@ def test_hypothesis_count_sweep_full_size(cuda, H, B):
     assert (m["top"] >= 0).all() and (m["top"] < H).all() and (m["top"][:, 1:] > m["top"][:, :-1]).all()
     best = m["scores"].max(1)[1]
     assert torch.equal(m["pool"].long(), torch.gather(m["top"].long(), 1, best.unsqueeze(1)).squeeze(1))
-    if H <= 20000:   # the oracle (reference torch path) at the same uniforms: same selected hypothesis or a float-noise tie
-        Ro, to, so = PO.coarse_pose(atten, d["score"], d["pts1"], d["pts2"], None, H, K, u=u)
-        ang = PO.rotation_geodesic_deg(R, Ro)
-        same = ang <= ROT_TOL_DEG
-        assert same.float().mean() >= 0.75
-        assert torch.allclose(s[~same], so[~same], rtol=2e-4)
+
+
+@pytest.mark.parametrize("H,B,seeds", [(1000, 8, (300,)), (6000, 8, (301,)), (20000, 8, (302,)), (50000, 4, (303,)),
+                                       (100000, 2, (304, 305))])
+def test_hypothesis_count_sweep_vs_oracle(cuda, H, B, seeds):
+    """Config 4 against the oracle at every H of the sweep, 100 000 included.
+    Measured on B200: all agree (profiles/r2_parity_coarse.json); threshold = measured minus one instance."""
+    agree, total, bad = _coarse_agreement(cuda, seeds, B, 196, H, 300, chunk_oracle=B * H > 400000)
+    print("H=%d: %d / %d agree, %s" % (H, agree, total, bad))
+    assert agree >= total - 1, (agree, total, bad)
 
 
 def test_multi_instance_query_image_64_detections(cuda):
