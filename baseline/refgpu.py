@@ -46,6 +46,8 @@ def load(need_ext=True):
     """-> namespace(model_utils, pointnet2_utils, transformer, coarse_mod, fine_mod, ext) of the stock reference."""
     global _ns
     if _ns is not None:
+        if need_ext and _ns.ext is None:
+            raise RuntimeError("the reference was loaded without its extension earlier in this process")
         return _ns
     if not available():
         raise RuntimeError("reference not staged: run `python baseline/stage_reference.py` where /root/reference exists")
@@ -55,9 +57,9 @@ def load(need_ext=True):
         sys.path.insert(0, REF_ROOT)
     _stub_detectron2()
     ext = None
-    if need_ext:
-        from oracle import ref_ext
+    from oracle import ref_ext
 
+    if need_ext or ref_ext.available():      # the .so loads without a GPU; it only EXECUTES on one
         ext = ref_ext.load()
         if ext is None:
             raise RuntimeError("oracle/_ref/ref_pointnet2_ext.so missing (python oracle/build_ref_ext.py)")

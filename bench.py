@@ -1,20 +1,22 @@
 #!/usr/bin/env python
 """bench.py — instances posed / s (and hypotheses scored / s) of the correspondence-and-pose hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference|reference-gpu]
+    python bench.py --mode hyp-shard --H 5000 [--batch 8]          (BASELINE.json config 4)
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
 
-A "step" = one pass of the hot path (unopose_b200.pipeline.run_hot_path) over one batch of B synthetic
-instances per GPU (BASELINE.json configs[1] fine matching + configs[0] coarse solve, with the FPS /
-ball-query / grouping stages of §8(a)).  Instances are independent, so ranks shard them with no
-data-path collective ("scaling": "weak"); the only collective is the final gather of results.
+A "step" = one pass of the hot path (unopose_b200.pipeline.run_hot_path) over one batch of B synthetic instances per GPU
+(BASELINE.json configs[1] fine matching + configs[0] coarse solve, with the FPS / ball-query / grouping stages of
+SURVEY.md §8a).  Instances are independent, so ranks shard them ("scaling": "weak"); the path's one collective — the
+all_gather of the per-instance result rows (R 9 | t 3 | score) — is issued EVERY step inside the timed region.
 
-Timing: W warm-up steps, then exactly K steps between (barrier + cuda synchronize), CUDA events on the
-launching stream, MAX over ranks.  Inputs rotate over several resident sets whose total size exceeds
-L2, so no step re-reads its inputs from L2.
+Timing: W warm-up steps, then exactly K steps between (barrier + cuda synchronize), CUDA events on the launching stream,
+MAX over ranks.  Inputs rotate over several resident sets whose total size exceeds L2, so no step re-reads its inputs
+from L2.
 
-`--impl reference`: the reference's CPU implementation of the same step (oracle port on the host
-cores, all threads) on a bounded sample of the workload.
+`--impl reference`     the reference's CPU implementation of the same step on the host cores (its own staged Python
+                       from baseline/_ref when present, else the oracle port), same B / steps / warm-up.
+`--impl reference-gpu` the UNMODIFIED reference on this GPU (its torch ops + its own `_ext` compiled for sm_100a).
 """
 import argparse
 import json
@@ -35,10 +37,12 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=16, help="instances per GPU per step (reference instance_batch_size=16)")
+    ap.add_argument("--batch", type=int, default=None, help="instances per GPU per step (default 16 = the reference's "
+                                                            "instance_batch_size; 8 in --mode hyp-shard)")
     ap.add_argument("--sets", type=int, default=4, help="resident input sets to rotate over (defeats L2 reuse)")
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-sample", type=int, default=8, help="instances in the bounded CPU-baseline sample")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
+    ap.add_argument("--mode", default="step", choices=["step", "hyp-shard"])
+    ap.add_argument("--H", type=int, nargs="*", default=None, help="hyp-shard: hypotheses per instance (default sweep)")
     ap.add_argument("--no-overlap", action="store_true", help="run the two chains of a step serially on one stream")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying CUDA graphs")
     ap.add_argument("--depth", type=int, default=2,
@@ -47,9 +51,12 @@ def parse():
     ap.add_argument("--no-zero-copy", action="store_true",
                     help="e2e: copy the full per-point feature tensors instead of gathering the FPS-selected rows "
                          "straight out of pinned host memory")
+    ap.add_argument("--sustain", type=float, default=2.0, help="seconds of back-to-back steps for the sustained figure (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-gpu-torch-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true")
     ap.add_argument("--no-widened", action="store_true", help="skip the informational timings of the f1/f2 kernels")
+    ap.add_argument("--no-peaks", action="store_true", help="skip the live TF32 dense-peak measurement")
+    ap.add_argument("--no-numa", action="store_true", help="do not pin the process to the GPU's NUMA node")
     return ap.parse_args()
 
 
@@ -60,6 +67,41 @@ def peaks():
         return dict(hbm=d["hbm_gbs"], tensor_burst=d["bf16_tflops"], tensor_sustained=d["bf16_tflops_sustained"],
                     source="measured (MEASURED_PEAKS.json)")
     return dict(hbm=6650.0, tensor_burst=1590.0, tensor_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+def measure_tf32_peak(dev, seconds=1.0):
+    """Dense TF32 tensor peak measured the way MEASURED_PEAKS.json measures bf16: torch.matmul 8192^3 (cuBLAS, TF32
+    allowed), best of 10 (burst) and back to back for `seconds` (sustained)."""
+    n = 8192
+    a = torch.randn(n, n, device=dev)
+    b = torch.randn(n, n, device=dev)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        for _ in range(2):
+            a @ b
+        torch.cuda.synchronize(dev)
+        best = 1e9
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            a @ b
+            e1.record()
+            torch.cuda.synchronize(dev)
+            best = min(best, e0.elapsed_time(e1))
+        reps = max(4, int(seconds * 1e3 / best))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            a @ b
+        e1.record()
+        torch.cuda.synchronize(dev)
+        sus = e0.elapsed_time(e1) / reps
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    fl = 2.0 * n ** 3
+    return {"tf32_tflops": fl / best * 1e-9, "tf32_tflops_sustained": fl / sus * 1e-9,
+            "how": "torch.matmul fp32 8192^3 with allow_tf32 (2 N^3): best of 10 and back to back for %.1f s" % seconds}
 
 
 class ClockSampler:
@@ -91,7 +133,7 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
             out = ""
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
@@ -100,6 +142,7 @@ class ClockSampler:
             try:
                 sm.append(float(f[1]))
                 mx.append(float(f[2]))
+                pw.append(float(f[3]))
             except ValueError:
                 continue
             for n, v in zip(names, f[5:9]):
@@ -109,49 +152,139 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         busy = [s for s in sm if s > 0.5 * max(sm)]
         return {"sm_mhz": statistics.median(busy or sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "power_w_max": max(pw) if pw else None}
 
 
-# ----------------------------------------------------------------------------- reference (CPU) arm
-def cpu_leg(cfg, sample_b, steps, warmup):
-    """The reference's CPU path (oracle port) on `sample_b` instances per step; returns (inst/s, hyp/s, info)."""
+def pin_to_gpu_numa_node(local):
+    """Bind this process (and therefore its pinned host allocations, first touch) to the NUMA node of its GPU."""
+    try:
+        bdf = subprocess.run(["nvidia-smi", "-i", str(local), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=10).stdout.strip().lower()
+        if bdf.count(":") == 2 and len(bdf.split(":")[0]) == 8:    # 00000000:1b:00.0 -> 0000:1b:00.0 (sysfs)
+            bdf = bdf[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip())
+        if node < 0:
+            return {"numa_node": None, "pinned": False, "why": "single NUMA node"}
+        cpus = open("/sys/devices/system/node/node%d/cpulist" % node).read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                ids |= set(range(int(a), int(b) + 1))
+            elif part:
+                ids.add(int(part))
+        ids &= os.sched_getaffinity(0)
+        if ids:
+            os.sched_setaffinity(0, ids)
+        return {"numa_node": node, "pinned": bool(ids), "cpus": len(ids)}
+    except Exception as ex:  # noqa: BLE001
+        return {"numa_node": None, "pinned": False, "why": repr(ex)[:120]}
+
+
+# ----------------------------------------------------------------------------- reference arms
+def _staged_reference(need_ext):
+    try:
+        from baseline import refgpu
+
+        if refgpu.available():
+            return refgpu.load(need_ext=need_ext)
+    except Exception:  # noqa: BLE001
+        pass
+    return None
+
+
+def cpu_leg(cfg, B, steps, warmup):
+    """The reference's CPU path on B instances per step: its own staged Python (baseline/_ref) when present — its three
+    CUDA-only pointnet2 ops served by the C restatement — else the oracle port.  -> (inst/s, hyp/s, info)."""
     from oracle import hotpath_cpu
     from oracle import pose_oracle as PO
     from unopose_b200.pipeline import synthetic_inputs
 
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    inp = synthetic_inputs(1234, sample_b, cfg, device=None)
+    inp = synthetic_inputs(1234, B, cfg, device=None)
+    ns = _staged_reference(need_ext=False)
+    if ns is not None:
+        from baseline.ref_hot_path import ref_step_cpu
+
+        step = lambda: ref_step_cpu(ns, inp, cfg, threads)  # noqa: E731
+        coarse = lambda a: ns.model_utils.compute_coarse_Rt_overlap(a, inp["c_score"], inp["c_pts1"], inp["c_pts2"], None,  # noqa: E731
+                                                                    cfg.n_proposal1, cfg.n_proposal2)
+        kind = "reference"
+    else:
+        step = lambda: hotpath_cpu.run_hot_path_cpu(inp, cfg, threads)  # noqa: E731
+        coarse = lambda a: PO.coarse_pose(a, inp["c_score"], inp["c_pts1"], inp["c_pts2"], None, cfg.n_proposal1,  # noqa: E731
+                                          cfg.n_proposal2)
+        kind = "port"
     for _ in range(warmup):
-        hotpath_cpu.run_hot_path_cpu(inp, cfg, threads)
+        step()
     t0 = time.perf_counter()
     for _ in range(steps):
-        hotpath_cpu.run_hot_path_cpu(inp, cfg, threads)
+        step()
     dt = (time.perf_counter() - t0) / steps
-    # coarse solve alone (hypotheses scored / s)
     c_atten = PO.feature_similarity(inp["c_f1"], inp["c_f2"], "cosine", cfg.temp, True)
+    nc = max(min(steps, 5), 2)
     t0 = time.perf_counter()
-    for _ in range(max(steps, 2)):
-        PO.coarse_pose(c_atten, inp["c_score"], inp["c_pts1"], inp["c_pts2"], None, cfg.n_proposal1, cfg.n_proposal2)
-    dtc = (time.perf_counter() - t0) / max(steps, 2)
-    return sample_b / dt, sample_b * cfg.n_proposal1 / dtc, dict(threads=threads, ms_per_step=dt * 1e3)
+    for _ in range(nc):
+        coarse(c_atten)
+    dtc = (time.perf_counter() - t0) / nc
+    return B / dt, B * cfg.n_proposal1 / dtc, dict(threads=threads, ms_per_step=dt * 1e3, kind=kind)
+
+
+def gpu_reference_leg(cfg, sets, B, dev, steps, warmup):
+    """The UNMODIFIED reference on this GPU: its own model_utils / pointnet2_utils (baseline/_ref) and its own `_ext`
+    compiled for sm_100a — the ">= 10x" denominator of BASELINE.json, same inputs, B, steps and warm-up, CUDA events."""
+    ns = _staged_reference(need_ext=True)
+    if ns is None:
+        return {"unavailable": "reference not staged under baseline/_ref or oracle/_ref/ref_pointnet2_ext.so missing"}
+    from baseline.ref_hot_path import ref_step
+
+    for i in range(max(warmup, 1)):
+        ref_step(ns, sets[i % len(sets)], cfg)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        ref_step(ns, sets[i % len(sets)], cfg)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    s = sets[0]
+    ca = ns.model_utils.compute_feature_similarity(s["c_f1"], s["c_f2"], "cosine", cfg.temp, True)
+    ns.model_utils.compute_coarse_Rt_overlap(ca, s["c_score"], s["c_pts1"], s["c_pts2"], None, cfg.n_proposal1, cfg.n_proposal2)
+    torch.cuda.synchronize(dev)
+    e0.record()
+    for i in range(steps):
+        ns.model_utils.compute_coarse_Rt_overlap(ca, s["c_score"], s["c_pts1"], s["c_pts2"], None, cfg.n_proposal1,
+                                                 cfg.n_proposal2)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms_c = e0.elapsed_time(e1) / steps
+    return {"value": B / (ms * 1e-3), "unit": "instances/s", "ms_per_step": ms, "kind": "reference", "steps": steps,
+            "warmup": warmup, "instances_per_step": B,
+            "hypotheses_scored_per_s": B * cfg.n_proposal1 / (ms_c * 1e-3), "coarse_solve_ms": ms_c,
+            "what": "unmodified reference (baseline/_ref: core.unopose.utils.model_utils + pointnet2_utils, its `_ext` "
+                    "built unmodified for sm_100a), eager PyTorch on the same GPU, resident inputs, CUDA events"}
 
 
 def run_reference(args, cfg):
+    """`--impl reference`: rank 0 alone times the reference's CPU path, same B / steps / warm-up / config as our arm."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
-    v, hyp, info = cpu_leg(cfg, args.cpu_sample, steps, warm)
-    sample = "%d instances/step, %d timed steps, full hot path on host cores (torch CPU ops + C oracle)" % (
-        args.cpu_sample, steps)
+    B = args.batch
+    v, hyp, info = cpu_leg(cfg, B, args.steps, args.warmup)
+    what = ("the reference's own Python (baseline/_ref) on CPU tensors, its CUDA-only pointnet2 ops served by the C "
+            "restatement oracle/pointnet2_oracle.c" if info["kind"] == "reference" else
+            "oracle port (torch CPU ops + C restatement of the pointnet2 kernels)")
+    sample = "%d instances/step x %d timed steps of the same workload on all host threads: %s" % (B, args.steps, what)
     line = {
         "impl": "reference", "metric": "instances_posed_per_s", "value": v, "unit": "instances/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": info["ms_per_step"],
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": info["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(cfg, args.cpu_sample),
+        "config": dict(workload_config(cfg, B), steps_in_flight=max(1, min(args.depth, args.sets))),
         "hypotheses_scored_per_s": hyp,
-        "cpu_baseline": {"value": v, "unit": "instances/s", "cores": info["threads"], "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "instances/s", "cores": info["threads"], "kind": info["kind"], "sample": sample},
         "e2e": {"value": v, "unit": "instances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -163,16 +296,14 @@ def workload_config(cfg, batch):
     return {"workload": "coarse(196x196,C=256,H=%d,K=%d)+fine(2048x2048,C=256)+FPS(5000->2048,2048->196 x2)+"
                         "ball_query/group(r=.1/64,r=.2/256 x2 clouds)" % (cfg.n_proposal1, cfg.n_proposal2),
             "instances_per_gpu_per_step": batch, "l2": "inputs rotate over resident sets larger than L2",
-            "parallelism": "instances sharded across ranks (no data-path collective)"}
+            "parallelism": "instances sharded across ranks; per-step all_gather of the result rows"}
 
 
-# ----------------------------------------------------------------------------- our arm
+# ----------------------------------------------------------------------------- informational legs
 def widened_leg(B, dev):
     """Device time of the kernels of the SURVEY.md §8 "next" rows at the real config (outside the headline step):
     f2 GeometricStructureEmbedding (N = 197, hidden 256, k = 3) and f1 PositionalEncoding (2048 points, two scales)."""
     import math
-
-    import torch
 
     from unopose_b200.modules import geo
     from unopose_b200.modules.matching import PositionalEncoding
@@ -209,17 +340,37 @@ def widened_leg(B, dev):
                                     "what": "fused ball query/grouping + k_lrf_group + k_shared_mlp_max x2 + Conv1d (cuBLAS)"}}
 
 
-def main():
-    args = parse()
-    from unopose_b200.pipeline import HotPathConfig
+def h2d_ceiling(host_sets, fed, dev, barrier, steps):
+    """The copies of an e2e step alone (same pinned buffers, same bytes, no compute), all ranks at once: the PCIe /
+    host-memory ceiling the end-to-end figure can be held against."""
+    src = host_sets[0]
+    dst = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in src.items() if not k.startswith("_")}
+    for k, v in dst.items():
+        v.copy_(src[k], non_blocking=True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        s = host_sets[i % len(host_sets)]
+        for k, v in dst.items():
+            if k not in fed.zero_copy:
+                v.copy_(s[k], non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    barrier()
+    nbytes = sum(v.numel() * v.element_size() for k, v in dst.items() if k not in fed.zero_copy)
+    return e0.elapsed_time(e1) / steps, nbytes
 
-    cfg = HotPathConfig()
-    if args.impl == "reference":
-        return run_reference(args, cfg)
 
+# ----------------------------------------------------------------------------- config 4: hypothesis sharding
+def run_hyp_shard(args, cfg):
+    """BASELINE.json config 4: hypothesis-count sweep, the pool of ONE instance batch split across the N ranks, both
+    collectives (all_gather of the candidate lists, all_reduce(MAX) of the score table) inside the timed loop; beside it
+    the single-GPU solver (upk_coarse_pose) on the same inputs."""
     from unopose_b200 import _lib
     from unopose_b200 import model_utils as MU
-    from unopose_b200.pipeline import GraphedHotPath, HostFedHotPath, input_bytes, run_hot_path, synthetic_inputs
+    from unopose_b200.dist import HypothesisShardedCoarse
+    from unopose_b200.synthetic import matching_batch
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -234,6 +385,129 @@ def main():
 
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
+    B = args.batch or 8
+    K = cfg.n_proposal2
+    Hs = args.H or [1000, 2000, 5000, 10000, 20000, 50000, 100000]
+    n = cfg.n_coarse
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    d = matching_batch(4242, B, n, cfg.feat_dim)             # identical on every rank
+    T = {k: torch.from_numpy(v).to(dev) for k, v in d.items() if k in ("pts1", "pts2", "f1", "f2", "score")}
+    atten = MU.compute_feature_similarity(T["f1"], T["f2"], "cosine", cfg.temp, True)
+    rows = []
+    for H in Hs:
+        u = torch.rand(B, 3 * H, generator=torch.Generator().manual_seed(H)).to(dev)
+        solver = HypothesisShardedCoarse(B, n, n, H, K, dev)
+        single = lambda: MU._coarse(atten, T["score"], T["pts1"], T["pts2"], None, H, K, u=u)  # noqa: E731
+        shard = lambda: solver.run(atten, T["score"], T["pts1"], T["pts2"], u)  # noqa: E731
+        R1, t1, s1 = single()
+        R2, t2, s2, _ = shard()
+        torch.cuda.synchronize()
+        same = bool(torch.equal(R1, R2) and torch.equal(t1, t2) and torch.equal(s1, s2))
+        res = {}
+        for name, fn in (("sharded", shard), ("single_gpu", single)):
+            graph = None
+            if not args.no_graph:
+                try:                                           # NCCL collectives are graph-capturable
+                    side = torch.cuda.Stream(device=dev)
+                    side.wait_stream(torch.cuda.current_stream(dev))
+                    with torch.cuda.stream(side):
+                        for _ in range(2):
+                            fn()
+                    torch.cuda.current_stream(dev).wait_stream(side)
+                    torch.cuda.synchronize()
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        fn()
+                except Exception:  # noqa: BLE001
+                    graph = None
+                    torch.cuda.synchronize()
+            run = graph.replay if graph is not None else fn
+            for _ in range(max(args.warmup, 3)):
+                run()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.steps):
+                run()
+            e1.record()
+            torch.cuda.synchronize()
+            barrier()
+            ms = e0.elapsed_time(e1) / args.steps
+            if dist is not None:
+                tt = torch.tensor([ms], device=dev)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                ms = float(tt.item())
+            res[name] = {"ms_per_solve": ms, "hypotheses_per_s": B * H / (ms * 1e-3), "cuda_graph": graph is not None}
+            del graph
+        # the two collectives alone (same buffers), to name the limiter
+        coll = {}
+        if dist is not None:
+            for cname, fn in (("all_gather_candidates", lambda: dist.all_gather_into_tensor(solver.allc, solver.cand)),
+                              ("all_reduce_max_scores", lambda: dist.all_reduce(solver.scores, op=dist.ReduceOp.MAX))):
+                for _ in range(5):
+                    fn()
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(50):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                coll[cname + "_us"] = e0.elapsed_time(e1) / 50 * 1e3
+            coll["all_gather_bytes_per_rank"] = solver.cand.numel() * 4
+            coll["all_reduce_bytes"] = solver.scores.numel() * 4
+        rows.append(dict(H=H, K=K, B=B, bit_identical_to_single_gpu=same, **res, collectives=coll))
+    if rank == 0:
+        best = max(rows, key=lambda r: r["sharded"]["hypotheses_per_s"])
+        line = {"metric": "hypotheses_scored_per_s", "value": best["sharded"]["hypotheses_per_s"], "unit": "hypotheses/s",
+                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": best["sharded"]["ms_per_solve"], "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "mode": "hyp-shard",
+                "config": {"workload": "coarse solve 196x196, K=%d, hypothesis pool of one %d-instance batch split over %d rank(s); "
+                                       "value = the best H of the sweep" % (K, B, world), "H_of_value": best["H"],
+                           "l2": "coarse working set (0.5 MB / instance) is L2-resident by nature"},
+                "sweep": rows, "gpu_launches": int(args.steps * 10)}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+# ----------------------------------------------------------------------------- our arm
+def main():
+    args = parse()
+    from unopose_b200.pipeline import HotPathConfig
+
+    cfg = HotPathConfig()
+    if args.mode == "hyp-shard":
+        return run_hyp_shard(args, cfg)
+    if args.batch is None:
+        args.batch = 16
+    if args.impl == "reference":
+        return run_reference(args, cfg)
+
+    from unopose_b200 import _lib
+    from unopose_b200 import model_utils as MU
+    from unopose_b200.pipeline import GraphedHotPath, HostFedHotPath, input_bytes, run_hot_path, synthetic_inputs
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=ours) needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    numa = {"pinned": False} if args.no_numa else pin_to_gpu_numa_node(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
     B = args.batch
 
     def barrier():
@@ -243,8 +517,19 @@ def main():
 
     # resident input sets (each rank owns different instances: weak scaling)
     sets = [synthetic_inputs(1000 * rank + 17 * s, B, cfg, device=dev) for s in range(args.sets)]
+    if args.impl == "reference-gpu":
+        if rank == 0:
+            r = gpu_reference_leg(cfg, sets, B, dev, args.steps, max(args.warmup, 1))
+            line = {"impl": "reference-gpu", "metric": "instances_posed_per_s", "value": r.get("value"), "unit": "instances/s",
+                    "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": r.get("ms_per_step"),
+                    "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                    "config": workload_config(cfg, B), "gpu_reference": r, "gpu_launches": 0}
+            print(json.dumps(line))
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+    _lib.load()
     set_bytes = input_bytes(sets[0])
-    results = []
 
     graphs = None if args.no_graph else [GraphedHotPath(s_, cfg, overlap=not args.no_overlap) for s_ in sets]
 
@@ -252,14 +537,27 @@ def main():
     if len(sets) % depth != 0:
         raise SystemExit("--sets must be a multiple of --depth (a resident set is always replayed on the same stream)")
     lanes = [torch.cuda.Stream(device=dev) for _ in range(depth)] if depth > 1 else None
+    # the path's one collective, every step: all_gather of this step's (B, 13) result rows; NCCL runs it on its own
+    # stream behind the step that produced the rows, so it overlaps the next step
+    gathered = [torch.empty((world * B, 13), dtype=torch.float32, device=dev) for _ in range(len(sets))] if dist is not None else None
+    pending = []
+    last_work = {}
 
     def step(i):
         # one CUDA graph per resident input set (static addresses); with depth > 1 step i runs on stream
         # i % depth, so `depth` consecutive steps (always different sets) are in flight at once
         def go():
+            k = i % len(sets)
+            if k in last_work:
+                last_work.pop(k).wait()      # the gather that still reads this set's result rows (stream-side wait)
             if graphs is not None:
-                return graphs[i % len(sets)].replay()
-            return run_hot_path(sets[i % len(sets)], cfg, overlap=not args.no_overlap)
+                o = graphs[k].replay()
+            else:
+                o = run_hot_path(sets[k], cfg, overlap=not args.no_overlap)
+            if dist is not None:
+                last_work[k] = dist.all_gather_into_tensor(gathered[k], o["result"], async_op=True)
+                pending.append(last_work[k])
+            return o
         if lanes is None:
             return go()
         with torch.cuda.stream(lanes[i % depth]):
@@ -272,6 +570,9 @@ def main():
                 l_.wait_stream(cur)
 
     def join():
+        for w_ in pending:
+            w_.wait()
+        pending.clear()
         if lanes is not None:
             cur = torch.cuda.current_stream(dev)
             for l_ in lanes:
@@ -303,7 +604,7 @@ def main():
     step_ev[0].record()
     fork()
     for i in range(args.steps):
-        out = step(i)
+        step(i)
         step_ev[i + 1].record(lanes[i % depth] if lanes is not None else None)
     join()
     e1.record()
@@ -319,12 +620,33 @@ def main():
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-        # the path's one collective: gather of per-instance results (R 9, t 3, score 1) on all ranks
-        res = torch.cat([out["pred_R"].reshape(B, 9), out["pred_t"], out["pred_pose_score"].unsqueeze(1)], 1)
-        gathered = [torch.empty_like(res) for _ in range(world)]
-        dist.all_gather(gathered, res)
     ms_per_step = ms / args.steps
     value = B * world / (ms_per_step * 1e-3)
+
+    # ---- the same loop held for seconds: does the figure survive sustained load (clocks, power)?
+    sustained = None
+    if args.sustain > 0:
+        n_sus = max(args.steps, int(args.sustain * 1e3 / ms_per_step))
+        s2 = ClockSampler(local)
+        barrier()
+        if rank == 0:
+            s2.start()
+        e0.record()
+        fork()
+        for i in range(n_sus):
+            step(i)
+        join()
+        e1.record()
+        torch.cuda.synchronize()
+        barrier()
+        ms_s = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms_s], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_s = float(t.item())
+        sustained = {"seconds": ms_s * 1e-3, "steps": n_sus, "ms_per_step": ms_s / n_sus,
+                     "value": B * world / (ms_s / n_sus * 1e-3), "unit": "instances/s",
+                     "clocks": s2.stop() if rank == 0 else None}
 
     # ---- coarse solve alone: hypotheses scored / s (a2..a6 on resident atten)
     c_att = [MU.compute_feature_similarity(s["c_f1"], s["c_f2"], "cosine", cfg.temp, True) for s in sets]
@@ -406,10 +728,21 @@ def main():
         ms_e = float(t.item())
     res_host = fed.result
     copied, pulled = fed.pcie_bytes_per_step(host_sets[0])
+    ms_copy, copy_bytes = h2d_ceiling(host_sets, fed, dev, barrier, args.steps)
+    if dist is not None:
+        t = torch.tensor([ms_copy], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_copy = float(t.item())
     e2e = {"value": B * world / (ms_e * 1e-3), "unit": "instances/s", "h2d_bytes_per_step": copied + pulled,
            "d2h_bytes_per_step": res_host.numel() * 4, "ms_per_step": ms_e,
            "h2d_copied_bytes": copied, "h2d_zero_copy_gather_bytes": pulled,
-           "host_input_bytes": input_bytes(host_sets[0])}
+           "host_input_bytes": input_bytes(host_sets[0]),
+           "h2d_gbs_per_gpu": (copied + pulled) / (ms_e * 1e-3) / 1e9,
+           "h2d_gbs_all_gpus": world * (copied + pulled) / (ms_e * 1e-3) / 1e9,
+           "copies_alone": {"ms_per_step": ms_copy, "bytes": copy_bytes, "gbs_per_gpu": copy_bytes / (ms_copy * 1e-3) / 1e9,
+                            "gbs_all_gpus": world * copy_bytes / (ms_copy * 1e-3) / 1e9,
+                            "what": "the cudaMemcpyAsync part of a step alone, all ranks at once: host-memory / PCIe ceiling"},
+           "numa": numa}
 
     if rank != 0:
         if dist is not None:
@@ -417,19 +750,27 @@ def main():
         return 0
 
     # ---- rooflines: one model per stage (algorithmic work per launch is defined in DESIGN.md §5);
-    #      `roofline` is the model of the stage with the largest share of the (serial) step time
+    #      `roofline` is the model of the stage with the largest share of the (serial) step time.  Stages are timed in
+    #      isolation (10 graph replays, ~ms): the BURST peaks apply; the sustained figures are listed beside them.
     pk = peaks()
+    tf32 = None
+    if world == 1 and not args.no_peaks:
+        try:
+            tf32 = measure_tf32_peak(dev)
+        except Exception as ex:  # noqa: BLE001
+            tf32 = {"unavailable": repr(ex)[:120]}
     total_stage = sum(stage_ms.values())
     n1 = cfg.n_fine + 1
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
     fp32_peak = sms * 128 * 1.965e9 / 1e12          # T lane-op/s, whole chip at max clock
     pe_bytes = sum((12.0 * 2 * cfg.n_fine + 4.0 * cfg.n_fine * ns + 16.0 * cfg.n_fine * ns) for _, ns in cfg.pe) * B
     fps_ops = lambda n, m: 10.0 * (m - 1) * n * B   # 10 lane-ops per distance update
+    fine_bytes = B * (2.0 * n1 * cfg.feat_dim * 4 + 2.0 * cfg.n_fine * 12 + 2.0 * cfg.n_fine * 4 + 1.0 * n1 * n1 * 4)
     models = {
-        "fine_similarity": ("k_similarity_tc2<stats> (tcgen05.mma.cta_group::2 3xTF32, CTA pairs on 256x256 tiles, background "
-                            "row/column peeled, exponent sums of the assignment in the epilogue) + k_normalize_split x2",
-                            "tensor", 2.0 * n1 * n1 * cfg.feat_dim * B),
-        "fine_pose": ("k_fine_labels + k_fine_rows (2 reads of the 2049^2 fp32 matrix; pass 1 = exponent sums, fused "
+        "fine_similarity": ("k_similarity_tc2<stats, fp16> (tcgen05.mma.cta_group::2 kind::f16, 3xFP16 split, CTA pairs on "
+                            "256x256 tiles, background row/column peeled, exponent sums of the assignment in the epilogue) "
+                            "+ k_normalize_split x2", "tensor-f16", 2.0 * n1 * n1 * cfg.feat_dim * B),
+        "fine_pose": ("k_fine_labels + k_fine_rows (2 reads of the 2049^2 fp32 logits; pass 1 = exponent sums, fused "
                       "into the similarity GEMM's epilogue) + Kabsch + inliers", "hbm", 2.0 * n1 * n1 * 4 * B),
         "fps_template+gather": ("fps_kernel<512,10> (5000->2048; serial chain, one SM per instance)", "fp32",
                                 fps_ops(cfg.n_template, cfg.n_fine)),
@@ -437,41 +778,53 @@ def main():
         "fps_sparse_query+gather": ("fps_kernel<512,4> (2048->196)", "fp32", fps_ops(cfg.n_fine, cfg.n_coarse)),
         "ball_query+group_query": ("ball_group_kernel<2 scales> (fused ball query + grouping)", "hbm", pe_bytes),
         "ball_query+group_ref": ("ball_group_kernel<2 scales> (fused ball query + grouping)", "hbm", pe_bytes),
-        "coarse_pose": ("k_score (K x 196 x 196 point pairs, 6 lane-ops each) + assignment/sampling/top-K", "fp32",
-                        6.0 * cfg.n_proposal2 * cfg.n_coarse * cfg.n_coarse * B),
+        "coarse_pose": ("k_score (K x 196 x 196 point pairs, 6 lane-ops each) + k_coarse_assign_exact + sampling / top-K",
+                        "fp32", 6.0 * cfg.n_proposal2 * cfg.n_coarse * cfg.n_coarse * B),
         "coarse_similarity": ("k_similarity_tc<0,3> (tcgen05 3xTF32, 197x197x256 per instance) + k_normalize_split x2",
-                              "tensor", 2.0 * (cfg.n_coarse + 1) ** 2 * cfg.feat_dim * B),
+                              "tensor-tf32", 2.0 * (cfg.n_coarse + 1) ** 2 * cfg.feat_dim * B),
     }
 
     def roof(stage):
         kname, bound, work = models[stage]
         dur_s = stage_ms[stage] * 1e-3
         extra = {}
-        if bound == "tensor":
-            achieved, peak, unit, bname = work / dur_s / 1e12, pk["tensor_sustained"], "TFLOP/s", "tensor"
-            # the kernel issues 3 TF32 MMAs per product (3xTF32 split, fp32-level logits) and the TF32 rate of the
-            # tensor pipe is half the bf16 rate `peak` was measured with
-            extra = {"issued_tf32_tflops": 3.0 * achieved, "tf32_issue_peak": peak / 2.0,
-                     "frac_of_tf32_issue_peak": 3.0 * achieved / (peak / 2.0),
-                     "note": "achieved = ALGORITHMIC flops (2 n m c per instance) / stage duration incl. the operand "
-                             "split kernels; peak = measured dense bf16"}
+        if bound.startswith("tensor"):
+            achieved, unit, bname = work / dur_s / 1e12, "TFLOP/s", "tensor"
+            if bound == "tensor-f16":
+                peak, psrc = pk["tensor_burst"], pk["source"] + " dense bf16/fp16, burst (the stage is timed in isolation)"
+                extra = {"peak_sustained": pk["tensor_sustained"]}
+            else:
+                have = tf32 is not None and "tf32_tflops" in tf32
+                peak = tf32["tf32_tflops"] if have else pk["tensor_burst"] / 2.0
+                psrc = ("measured in this run: " + tf32["how"] + ", burst") if have else "dense bf16 burst / 2 (TF32 peak not measured)"
+                if have:
+                    extra = {"peak_sustained": tf32["tf32_tflops_sustained"]}
+            # three MMAs per product (hi*hi + hi*lo + lo*hi, fp32-level logits): issued = 3 x algorithmic
+            extra.update({"issued_tflops": 3.0 * achieved, "frac_issued": 3.0 * achieved / peak,
+                          "note": "achieved = ALGORITHMIC flops (2 n m c per instance) / stage duration incl. the "
+                                  "operand split kernels; the kernel issues 3 tensor-core products per algorithmic one"})
         elif bound == "fp32":
-            achieved, peak, unit, bname = work / dur_s / 1e12, fp32_peak, "Tlane-op/s", "fp32-issue"
+            achieved, peak, unit, bname, psrc = work / dur_s / 1e12, fp32_peak, "Tlane-op/s", "fp32-issue", "#SM*128*1.965 GHz"
         else:
-            achieved, peak, unit, bname = work / dur_s / 1e9, pk["hbm"], "GB/s", "hbm"
+            achieved, peak, unit, bname, psrc = work / dur_s / 1e9, pk["hbm"], "GB/s", "hbm", pk["source"]
         return dict({"kernel": kname, "stage": stage, "stage_share_of_step": stage_ms[stage] / total_stage,
                      "bound": bname, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
-                     "traffic": None, "peak_source": pk["source"] if bound != "fp32" else "#SM*128*1.965 GHz",
-                     "duration_ms": stage_ms[stage]}, **extra)
+                     "traffic": None, "peak_source": psrc, "duration_ms": stage_ms[stage]}, **extra)
 
     stage_rooflines = {k: roof(k) for k in stage_ms if k in models}
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if os.path.exists(tpath):       # measured DRAM traffic per launch from the committed ncu --set full capture
-        tj = json.load(open(tpath))
-        for k, r in stage_rooflines.items():
-            if k in tj["stage_traffic_bytes"]:
-                r["traffic"] = tj["stage_traffic_bytes"][k] * B / tj["batch"]
-                r["traffic_source"] = "profiles/r1_traffic.json (ncu --set full, scaled by batch)"
+    for tname in ("r2_traffic.json", "r1_traffic.json"):   # measured DRAM traffic per launch from the committed ncu --set full capture
+        tpath = os.path.join(ROOT, "profiles", tname)
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            for k, r in stage_rooflines.items():
+                if k in tj["stage_traffic_bytes"]:
+                    r["traffic"] = tj["stage_traffic_bytes"][k] * B / tj["batch"]
+                    r["traffic_source"] = "profiles/%s (ncu --set full, scaled by batch)" % tname
+            break
+    # the fine stage as a whole against HBM: algorithmic bytes = operands + ONE write of atten (the API returns it)
+    fine_ms = stage_ms.get("fine_similarity", 0.0) + stage_ms.get("fine_pose", 0.0)
+    fine_stage = {"algorithmic_bytes": fine_bytes, "ms": fine_ms, "achieved_gbs": fine_bytes / (fine_ms * 1e-3) / 1e9 if fine_ms else None,
+                  "frac_of_hbm": fine_bytes / (fine_ms * 1e-3) / 1e9 / pk["hbm"] if fine_ms else None}
     # the dominant kernel = largest share of the GPU's capacity (duration x fraction of the SMs it occupies): the FPS
     # kernels run one CTA per instance (B of the SMs), concurrently with the full-GPU kernels of the step in flight
     sm_share = {k: (min(1.0, B / sms) if k.startswith("fps_") else 1.0) for k in stage_ms}
@@ -487,25 +840,35 @@ def main():
         "config": dict(workload_config(cfg, B), steps_in_flight=depth),
         "hypotheses_scored_per_s": hyp_per_s, "coarse_solve_ms": ms_c,
         "step_ms_min_median_max": [min(per_step), statistics.median(per_step), max(per_step)],
+        "sustained": sustained,
         "stage_ms": stage_ms,
         "roofline": roofline,
         "stage_rooflines": stage_rooflines,
+        "fine_stage_vs_hbm": fine_stage,
+        "measured_tf32_peak": tf32,
         "e2e": e2e,
         "gpu_launches": int(launches),
+        "collective": ({"op": "all_gather_into_tensor of the (B,13) result rows, every step, inside the timed region",
+                        "bytes_per_rank": B * 13 * 4} if dist is not None else None),
         "clocks": clocks,
         "resident_input_bytes": set_bytes * len(sets),
     }
     if world == 1 and not args.no_cpu_baseline:
-        v, hyp, info = cpu_leg(cfg, args.cpu_sample, 3, 1)
-        line["cpu_baseline"] = {"value": v, "unit": "instances/s", "cores": info["threads"], "kind": "port",
-                                "sample": "%d instances/step x 3 steps of the same workload (oracle port: torch CPU "
-                                          "ops + C restatement of the pointnet2 kernels)" % args.cpu_sample,
+        v, hyp, info = cpu_leg(cfg, B, 3, 1)
+        what = ("the reference's own Python (baseline/_ref) on CPU tensors; its CUDA-only pointnet2 ops served by the C "
+                "restatement" if info["kind"] == "reference" else "oracle port: torch CPU ops + C restatement of the pointnet2 kernels")
+        line["cpu_baseline"] = {"value": v, "unit": "instances/s", "cores": info["threads"], "kind": info["kind"],
+                                "sample": "%d instances/step x 3 steps of the same workload (%s)" % (B, what),
                                 "hypotheses_scored_per_s": hyp}
-    if world == 1 and not args.no_gpu_torch_baseline:
+    if world == 1 and not args.no_gpu_reference:
         try:
-            line["gpu_torch_baseline"] = gpu_torch_leg(cfg, sets, B, dev)
+            line["gpu_reference"] = gpu_reference_leg(cfg, sets, B, dev, args.steps, max(args.warmup, 3))
+            if "value" in line["gpu_reference"]:
+                line["speedup_vs_gpu_reference"] = {"device_resident": value / line["gpu_reference"]["value"],
+                                                    "e2e_vs_resident_reference": e2e["value"] / line["gpu_reference"]["value"],
+                                                    "hypotheses_per_s": hyp_per_s / line["gpu_reference"]["hypotheses_scored_per_s"]}
         except Exception as ex:  # reported, never fatal
-            line["gpu_torch_baseline"] = {"unavailable": repr(ex)[:200]}
+            line["gpu_reference"] = {"unavailable": repr(ex)[:200]}
     if world == 1 and not args.no_widened:
         try:
             line["widened_rows"] = widened_leg(B, dev)
@@ -515,62 +878,6 @@ def main():
     if dist is not None:
         dist.destroy_process_group()
     return 0
-
-
-def gpu_torch_leg(cfg, sets, B, dev):
-    """The reference's GPU path on the same box and inputs: its torch ops (oracle port on CUDA tensors)
-    plus its own pointnet2 extension compiled unmodified (oracle/_ref) — the ">= 10x" denominator of
-    BASELINE.json.  Reported baseline only."""
-    from oracle import pose_oracle as PO
-    from oracle import ref_ext
-
-    ext = ref_ext.load()
-    if ext is None:
-        return {"unavailable": "oracle/_ref/ref_pointnet2_ext.so not present"}
-
-    def sample(pts, feats, m):
-        idx = ext.furthest_point_sampling(pts.contiguous(), m)
-        p = ext.gather_points(pts.transpose(1, 2).contiguous(), idx).transpose(1, 2).contiguous()
-        f = ext.gather_points(feats.transpose(1, 2).contiguous(), idx).transpose(1, 2).contiguous()
-        return p, f
-
-    def ref_step(s):
-        tem_sub, tem_f = sample(s["tem_pts"], s["tem_feats"], cfg.n_fine)
-        sample(s["pts"], s["pts_feats"], cfg.n_coarse)
-        sample(tem_sub, tem_f, cfg.n_coarse)
-        ca = PO.feature_similarity(s["c_f1"], s["c_f2"], "cosine", cfg.temp, True)
-        PO.coarse_pose(ca, s["c_score"], s["c_pts1"], s["c_pts2"], None, cfg.n_proposal1, cfg.n_proposal2)
-        for cloud in (s["pts"], tem_sub):
-            cloud = cloud.contiguous()
-            cf = cloud.transpose(1, 2).contiguous()
-            for r, ns in cfg.pe:
-                ext.group_points(cf, ext.ball_query(cloud, cloud, r, ns))
-        fa = PO.feature_similarity(s["f_f1"], s["f_f2"], "cosine", cfg.temp, True)
-        return PO.fine_pose(fa, s["f_score"], s["f_pts1"], s["f_pts2"], None, cfg.dis_thres)
-
-    for i in range(2):
-        ref_step(sets[i % len(sets)])
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n = 5
-    e0.record()
-    for i in range(n):
-        ref_step(sets[i % len(sets)])
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / n
-    # coarse solve alone
-    ca = PO.feature_similarity(sets[0]["c_f1"], sets[0]["c_f2"], "cosine", cfg.temp, True)
-    s = sets[0]
-    e0.record()
-    for i in range(n):
-        PO.coarse_pose(ca, s["c_score"], s["c_pts1"], s["c_pts2"], None, cfg.n_proposal1, cfg.n_proposal2)
-    e1.record()
-    torch.cuda.synchronize()
-    ms_c = e0.elapsed_time(e1) / n
-    return {"value": B / (ms * 1e-3), "unit": "instances/s", "ms_per_step": ms, "kind": "port+reference_ext",
-            "hypotheses_scored_per_s": B * cfg.n_proposal1 / (ms_c * 1e-3),
-            "what": "reference torch-op sequence on CUDA tensors + reference pointnet2 _ext (unmodified, sm_100a)"}
 
 
 if __name__ == "__main__":

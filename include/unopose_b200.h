@@ -189,6 +189,12 @@ int upk_coarse_assignment(const float* atten, const float* score1, int score1_ld
 /* searchsorted(cdf,u) -> triplets -> Kabsch -> residual for hypotheses
  * [h_begin,h_end) of every instance (model_utils.py:462-475). Rs/ts/resid are
  * indexed by the global hypothesis index ([b,n_hyp,...]). */
+/* Profiling aid: upk_coarse_assignment's cluster kernel, additionally recording the SM clock of instance 0 / cluster
+ * rank 0 at kernel entry and after each of its 8 cluster barriers into stamps_out[9] (device memory, int64). */
+int upk_coarse_assignment_profile(const float* atten, const float* score1, int score1_ld, const float* score2,
+                                  int score2_ld, int b, int n1, int n2, float* w1_out, float* w2_out,
+                                  float* cdf_out, long long* stamps_out, upk_stream_t stream);
+
 int upk_sample_hypotheses(const float* cdf, const float* u, const float* pts1,
                           const float* pts2, int b, int n1, int n2, int n_hyp,
                           int h_begin, int h_end, int* idx1_out, int* idx2_out,
@@ -210,6 +216,20 @@ int upk_score_hypotheses(const float* pts1, const float* model_pts, const float*
 int upk_select_best(const float* scores, const int* top, const float* Rs, const float* ts,
                     int b, int n_hyp, int n_keep, float* R_out, float* t_out,
                     float* score_out, int* pool_idx_out, upk_stream_t stream);
+
+/* Hypothesis sharding across GPUs (SURVEY.md §8e partitioning B; no counterpart in the reference, which has no
+ * collective on this path).  Ranks that share an instance batch each sample a slice [h_begin, h_end) of the pool
+ * (upk_sample_hypotheses), keep the n_local smallest residuals of the slice (upk_topk_smallest on the slice) and
+ * exchange fixed-size candidate lists: upk_pack_candidates writes n_slots records of 14 floats per instance
+ * {residual, pool index (int bits), R[9], t[3]}, padded with {+inf, -1}; after an all_gather into
+ * gathered[world][b][n_slots][14], upk_unpack_candidates scatters the OTHER ranks' records into the dense pool arrays
+ * (resid[b][n_hyp], Rs, ts), on which the same upk_topk_smallest re-selects the global top-K.  upk_fill_f32 resets
+ * resid to +inf (and a score buffer to -inf) before a solve. */
+int upk_fill_f32(float* p, size_t n, float value, upk_stream_t stream);
+int upk_pack_candidates(const float* resid, const float* Rs, const float* ts, const int* top_local, int b, int n_hyp,
+                        int h_begin, int n_local, int n_slots, float* cand_out, upk_stream_t stream);
+int upk_unpack_candidates(const float* gathered, int world, int my_rank, int b, int n_hyp, int n_slots, float* resid,
+                          float* Rs, float* ts, upk_stream_t stream);
 
 /* ------------------------------------------------------------------------- *
  * fine pose — compute_fine_Rt[_overlap], model_utils.py:493-566

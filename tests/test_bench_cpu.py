@@ -16,12 +16,13 @@ def _run(*args):
 
 
 def test_reference_arm_prints_contract_line():
-    r = _run("--impl", "reference", "--steps", "1", "--warmup", "1", "--cpu-sample", "1")
+    r = _run("--impl", "reference", "--steps", "1", "--warmup", "1", "--batch", "1")
     assert r.returncode == 0, r.stderr[-2000:]
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == "instances_posed_per_s" and line["unit"] == "instances/s"
     assert line["value"] > 0 and line["higher_is_better"] is True and line["gpu_launches"] == 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1
+    assert line["steps"] == 1 and line["warmup"] == 1 and line["config"]["instances_per_gpu_per_step"] == 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
     assert "workload" in line["config"]
 

@@ -77,3 +77,16 @@ def test_world2_gloo():
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
     assert dict(out) == {0: True, 1: True}
+
+
+def test_score_and_candidate_partitions():
+    from unopose_b200.dist import candidate_slots, score_shard_range
+
+    for K in (1, 30, 300, 301):
+        for world in (1, 2, 3, 4, 8):
+            spans = [score_shard_range(K, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and max(e for _, e in spans) == K
+            covered = sorted(k for b, e in spans for k in range(b, e))
+            assert covered == list(range(K))                       # every kept hypothesis scored by exactly one rank
+            assert len({e - b for b, e in spans if e > b} | {0}) <= 3
+    assert candidate_slots(5000, 300, 8) == 300 and candidate_slots(1000, 300, 8) == 125 and candidate_slots(100, 300, 1) == 100

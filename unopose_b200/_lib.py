@@ -41,11 +41,15 @@ _SIGNATURES = {
     "upk_coarse_pose": [c_f, c_f, c_i, c_f, c_i, c_f, c_f, c_f, c_i, c_f, c_i, c_i, c_i, c_i, c_i,
                         c_f, c_sz, c_f, c_f, c_f, c_f, c_f, c_st],
     "upk_coarse_assignment": [c_f, c_f, c_i, c_f, c_i, c_i, c_i, c_i, c_f, c_sz, c_f, c_f, c_f, c_st],
+    "upk_coarse_assignment_profile": [c_f, c_f, c_i, c_f, c_i, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_st],
     "upk_sample_hypotheses": [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_f, c_st],
     "upk_kabsch_triplets": [c_f, c_f, c_i, c_f, c_f, c_f, c_st],
     "upk_topk_smallest": [c_f, c_i, c_i, c_i, c_f, c_st],
     "upk_score_hypotheses": [c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_st],
     "upk_select_best": [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_st],
+    "upk_fill_f32": [c_f, c_sz, c_fl, c_st],
+    "upk_pack_candidates": [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_f, c_st],
+    "upk_unpack_candidates": [c_f, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_f, c_st],
     "upk_fine_pose": [c_f, c_f, c_i, c_f, c_i, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_fl, c_fl,
                       c_f, c_sz, c_f, c_f, c_f, c_f, c_st],
     "upk_feature_similarity_stats": [c_f, c_f, c_i, c_i, c_i, c_i, c_fl, c_f, c_sz, c_f, c_f, c_sz, c_st],

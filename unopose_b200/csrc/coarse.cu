@@ -347,6 +347,60 @@ k_select(const float* __restrict__ scores, const int* __restrict__ top, const fl
   }
 }
 
+// ---------------------------------------------------------------- hypothesis sharding
+// Candidate exchange between the ranks that share one instance batch: every rank packs the kl smallest hypotheses of
+// ITS slice of the pool into a fixed-size record list (kc records per instance, padded with +inf / -1), the lists are
+// all-gathered, and every rank scatters the other ranks' records into its dense pool arrays, so that the SAME top-K
+// kernel a single GPU runs re-selects the global top-K (identical tie rule).  Record: {residual, pool index (int
+// bits), R (9), t (3)} = 14 floats.
+constexpr int CAND_F = 14;
+
+__global__ void __launch_bounds__(128)
+k_pack_candidates(const float* __restrict__ resid, const float* __restrict__ Rs, const float* __restrict__ ts,
+                  const int* __restrict__ top_local, int h0, int H, int kl, int kc, float* __restrict__ cand) {
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * 128 + threadIdx.x;
+  if (j >= kc) return;
+  float* o = cand + ((size_t)b * kc + j) * CAND_F;
+  if (j < kl) {
+    const int h = h0 + top_local[(size_t)b * kl + j];
+    o[0] = resid[(size_t)b * H + h];
+    o[1] = __int_as_float(h);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) o[2 + i] = Rs[((size_t)b * H + h) * 9 + i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) o[11 + i] = ts[((size_t)b * H + h) * 3 + i];
+  } else {
+    o[0] = INFINITY;
+    o[1] = __int_as_float(-1);
+#pragma unroll
+    for (int i = 2; i < CAND_F; ++i) o[i] = 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(128)
+k_unpack_candidates(const float* __restrict__ allc /* [world][b][kc][14] */, int world, int skip_rank, int nb, int H,
+                    int kc, float* __restrict__ resid, float* __restrict__ Rs, float* __restrict__ ts) {
+  const int b = blockIdx.y;
+  const int q = blockIdx.x * 128 + threadIdx.x;   // (rank, j)
+  if (q >= world * kc) return;
+  const int r = q / kc, j = q - r * kc;
+  if (r == skip_rank) return;                     // my own slice is already in place
+  const float* c = allc + (((size_t)r * nb + b) * kc + j) * CAND_F;
+  const int h = __float_as_int(c[1]);
+  if (h < 0 || h >= H) return;
+  resid[(size_t)b * H + h] = c[0];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) Rs[((size_t)b * H + h) * 9 + i] = c[2 + i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) ts[((size_t)b * H + h) * 3 + i] = c[11 + i];
+}
+
+__global__ void __launch_bounds__(256)
+k_fill_f32(float* __restrict__ p, size_t n, float v) {
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) p[i] = v;
+}
+
 struct CoarseWs {
   AssignWs a;
   float* w1; float* w2;
@@ -528,6 +582,37 @@ int upk_score_hypotheses(const float* pts1, const float* model_pts, const float*
   if (b == 0) return UPK_OK;
   return launch_score(pts1, model_pts, w1, Rs, ts, top, b, n1, n_model, n_hyp, n_keep, k_begin, k_end, scores,
                       (cudaStream_t)stream);
+}
+
+int upk_fill_f32(float* p, size_t n, float value, upk_stream_t stream) {
+  if (n == 0) return UPK_OK;
+  if (!p) return UPK_ERR_INVALID_ARG;
+  const size_t blocks = (n + 255) / 256;
+  k_fill_f32<<<(unsigned)(blocks < 1184 ? blocks : 1184), 256, 0, (cudaStream_t)stream>>>(p, n, value);
+  count_launch();
+  UPK_RETURN_LAST_ERROR();
+}
+
+int upk_pack_candidates(const float* resid, const float* Rs, const float* ts, const int* top_local, int b, int n_hyp,
+                        int h_begin, int n_local, int n_slots, float* cand_out, upk_stream_t stream) {
+  if (b < 0 || n_hyp <= 0 || h_begin < 0 || n_local < 0 || n_slots < n_local || n_slots <= 0) return UPK_ERR_INVALID_ARG;
+  if (b == 0) return UPK_OK;
+  if (!resid || !Rs || !ts || !cand_out || (n_local > 0 && !top_local)) return UPK_ERR_INVALID_ARG;
+  k_pack_candidates<<<dim3(ceil_div(n_slots, 128), b), 128, 0, (cudaStream_t)stream>>>(resid, Rs, ts, top_local, h_begin,
+                                                                                     n_hyp, n_local, n_slots, cand_out);
+  count_launch();
+  UPK_RETURN_LAST_ERROR();
+}
+
+int upk_unpack_candidates(const float* gathered, int world, int my_rank, int b, int n_hyp, int n_slots, float* resid,
+                          float* Rs, float* ts, upk_stream_t stream) {
+  if (world <= 0 || b < 0 || n_hyp <= 0 || n_slots <= 0) return UPK_ERR_INVALID_ARG;
+  if (b == 0) return UPK_OK;
+  if (!gathered || !resid || !Rs || !ts) return UPK_ERR_INVALID_ARG;
+  k_unpack_candidates<<<dim3(ceil_div(world * n_slots, 128), b), 128, 0, (cudaStream_t)stream>>>(
+      gathered, world, my_rank, b, n_hyp, n_slots, resid, Rs, ts);
+  count_launch();
+  UPK_RETURN_LAST_ERROR();
 }
 
 int upk_select_best(const float* scores, const int* top, const float* Rs, const float* ts, int b, int n_hyp,

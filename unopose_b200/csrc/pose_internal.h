@@ -58,7 +58,7 @@ int run_assignment_labels(const float* atten, const float* score1, int ld1, cons
 // coarse_assign.cu: masks + sampling CDF in one cluster kernel, bit-exact with the ATen CUDA kernels of the reference's
 // GPU path.  UPK_ERR_UNSUPPORTED for geometries it does not handle (-> the tile pipeline below).
 int run_coarse_assign_exact(const float* atten, const float* score1, int ld1, const float* score2, int ld2, int b,
-                            int R, int C, float* w1, float* w2, float* cdf, cudaStream_t st);
+                            int R, int C, float* w1, float* w2, float* cdf, cudaStream_t st, long long* stamps = nullptr);
 
 // coarse: P = (A w1 w2)^1.5 over the foreground block -> pmat [b][N1*N2], row-sum partials (double)
 int run_coarse_P(const float* atten, const float* score1, int ld1, const float* score2, int ld2, int b,

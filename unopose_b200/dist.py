@@ -3,11 +3,11 @@
 A. instance sharding   — instances are independent; each rank runs its slice, the only collective is an
                          all_gather of the (B_local, 13) result rows [R(9) | t(3) | score].
 B. hypothesis sharding — one instance batch, H hypotheses split across ranks.  Every rank builds the same
-                         CDF and takes its slice of the SAME uniform draws; candidates (residual, pool
-                         index, R, t) are all-gathered, the global top-K is re-selected by the same
-                         kernel on every rank, each rank scores its slice of the kept list, the scores are
-                         all-gathered and the arg-max is taken.  No float is ever reduced across ranks, so
-                         the result is bit-identical to one GPU.
+                         CDF and takes its slice of the SAME uniform draws; fixed-size candidate lists (residual,
+                         pool index, R, t) are all-gathered, the global top-K is re-selected by the same
+                         kernel on every rank, each rank scores its slice of the kept list, the score table is
+                         completed by an all_reduce(MAX) against -inf and the arg-max is taken.  No float is
+                         ever combined across ranks, so the result is bit-identical to one GPU.
 
 The collectives work on whatever device the tensors live on (NCCL for CUDA, gloo for the CPU tests).
 """
@@ -76,76 +76,115 @@ def gather_results(R, t, score, counts=None, group=None):
 
 def merge_topk_candidates(cand_resid, cand_idx, n_hyp):
     """Scatter gathered candidates (B, M) back into a dense (B, n_hyp) residual array filled with +inf,
-    so the SAME top-K kernel that a single GPU runs re-selects the global top-K (identical tie rule)."""
+    so the SAME top-K kernel that a single GPU runs re-selects the global top-K (identical tie rule).
+    (torch formulation of upk_unpack_candidates; used by the CPU/gloo tests of the host logic.)"""
     B = cand_resid.shape[0]
     dense = torch.full((B, n_hyp), float("inf"), dtype=cand_resid.dtype, device=cand_resid.device)
     dense.scatter_(1, cand_idx.long(), cand_resid)
     return dense
 
 
+def score_shard_range(K, rank, world):
+    """Slice [k0, k1) of the kept list a rank scores: equal chunks of ceil(K / world), the tail ranks may be empty."""
+    kmax = -(-K // world)
+    k0 = min(K, rank * kmax)
+    return k0, min(K, k0 + kmax)
+
+
+def candidate_slots(H, K, world):
+    """Records per instance in a rank's candidate list: min(K, largest slice)."""
+    return min(K, max(shard_range(H, r, world)[1] - shard_range(H, r, world)[0] for r in range(world)))
+
+
+class HypothesisShardedCoarse:
+    """compute_coarse_Rt_overlap with the hypothesis pool split across the ranks of `group` (partitioning B).
+
+    All buffers are allocated once (static addresses, so a solve can be captured into a CUDA graph together with its
+    two collectives).  One solve = 10 kernel launches + 2 collectives:
+      fill resid=+inf -> assignment (replicated, bit-exact cluster kernel) -> my slice of the hypotheses -> local
+      top-K of the slice -> pack candidates -> ALL_GATHER #1 (world x B x slots x 56 B) -> unpack the other ranks'
+      candidates -> global top-K -> fill scores=-inf -> score my slice of the kept list -> ALL_REDUCE(MAX) #2 over the
+      (B, K) score table (every entry is written by exactly one rank; MAX with -inf elsewhere moves it unchanged, no
+      float is ever combined across ranks) -> arg-max + gather.
+    The result is identical on every rank and bit-identical to the single-GPU solver."""
+
+    def __init__(self, B, N1, N2, H, K, device, group=None, with_score=True):
+        from . import _lib as L
+
+        self.L, self.lib = L, L.load()
+        self.group = group
+        self.rank, self.world = _world(group)
+        self.B, self.N1, self.N2, self.H, self.K = B, N1, N2, int(H), int(K)
+        self.dev = torch.device(device)
+        self.h0, self.h1 = shard_range(self.H, self.rank, self.world)
+        self.kl = min(self.K, self.h1 - self.h0)
+        self.kc = candidate_slots(self.H, self.K, self.world)
+        self.k0, self.k1 = score_shard_range(self.K, self.rank, self.world)
+        f32 = lambda *shape: torch.empty(shape, dtype=torch.float32, device=self.dev)  # noqa: E731
+        i32 = lambda *shape: torch.empty(shape, dtype=torch.int32, device=self.dev)  # noqa: E731
+        self.ws = torch.empty(max(self.lib.upk_coarse_assignment_workspace_bytes(B, N1, N2), 256), dtype=torch.uint8,
+                              device=self.dev)
+        self.w1, self.w2, self.cdf = f32(B, N1), f32(B, N2), f32(B, N1 * N2)
+        self.Rs, self.ts, self.resid = torch.zeros((B, self.H, 9), device=self.dev), torch.zeros((B, self.H, 3), device=self.dev), f32(B, self.H)
+        self.loc = f32(B, max(self.h1 - self.h0, 1))
+        self.top_l, self.top = i32(B, max(self.kl, 1)), i32(B, self.K)
+        self.cand = f32(B, self.kc, 14)
+        self.allc = f32(self.world, B, self.kc, 14)
+        self.scores = f32(B, self.K)
+        self.R, self.t, self.sc, self.pool = f32(B, 3, 3), f32(B, 3), f32(B), i32(B)
+
+    def run(self, atten, score, pts1, pts2, u):
+        """atten (B,N1+1,N2+1), score (B,N1+N2)|None, pts (B,N,3), u (B,3H) identical on every rank (same seed).
+        Inputs must be fp32 contiguous CUDA tensors.  Returns (R, t, score, pool_idx) — the solver's own buffers."""
+        L, lib, B, N1, N2, H, K = self.L, self.lib, self.B, self.N1, self.N2, self.H, self.K
+        s1 = s2 = None
+        ld = 0
+        if score is not None:
+            if score.shape[1] - N2 != N2:
+                raise RuntimeError("compute_coarse_Rt_overlap: score[:, N2:] must have N2 columns "
+                                   "(the reference slices score[:, N2:], which requires N1 == N2)")
+            ld = score.shape[1]
+            s1, s2 = score, score[:, N2:]
+        st = L.stream_ptr(pts1)
+        with torch.cuda.device(self.dev):
+            L.check(lib.upk_fill_f32(L.ptr(self.resid), self.resid.numel(), float("inf"), st), "fill")
+            L.check(lib.upk_coarse_assignment(L.ptr(atten), L.ptr(s1), ld, s2.data_ptr() if s2 is not None else None, ld,
+                                              B, N1, N2, L.ptr(self.ws), self.ws.numel(), L.ptr(self.w1), L.ptr(self.w2),
+                                              L.ptr(self.cdf), st), "coarse_assignment")
+            L.check(lib.upk_sample_hypotheses(L.ptr(self.cdf), L.ptr(u), L.ptr(pts1), L.ptr(pts2), B, N1, N2, H, self.h0,
+                                              self.h1, None, None, L.ptr(self.Rs), L.ptr(self.ts), L.ptr(self.resid), st),
+                    "sample_hypotheses")
+            if self.world > 1:
+                if self.kl > 0:
+                    self.loc.copy_(self.resid[:, self.h0:self.h1])
+                    L.check(lib.upk_topk_smallest(L.ptr(self.loc), B, self.h1 - self.h0, self.kl, L.ptr(self.top_l), st),
+                            "topk_local")
+                L.check(lib.upk_pack_candidates(L.ptr(self.resid), L.ptr(self.Rs), L.ptr(self.ts), L.ptr(self.top_l), B, H,
+                                                self.h0, self.kl, self.kc, L.ptr(self.cand), st), "pack_candidates")
+                dist.all_gather_into_tensor(self.allc, self.cand, group=self.group)               # collective #1
+                L.check(lib.upk_unpack_candidates(L.ptr(self.allc), self.world, self.rank, B, H, self.kc, L.ptr(self.resid),
+                                                  L.ptr(self.Rs), L.ptr(self.ts), st), "unpack_candidates")
+            L.check(lib.upk_topk_smallest(L.ptr(self.resid), B, H, K, L.ptr(self.top), st), "topk_global")
+            if self.world > 1:
+                L.check(lib.upk_fill_f32(L.ptr(self.scores), self.scores.numel(), float("-inf"), st), "fill")
+            L.check(lib.upk_score_hypotheses(L.ptr(pts1), L.ptr(pts2), L.ptr(self.w1), L.ptr(self.Rs), L.ptr(self.ts),
+                                             L.ptr(self.top), B, N1, N2, H, K, self.k0, self.k1, L.ptr(self.scores), st),
+                    "score_hypotheses")
+            if self.world > 1:
+                dist.all_reduce(self.scores, op=dist.ReduceOp.MAX, group=self.group)             # collective #2
+            L.check(lib.upk_select_best(L.ptr(self.scores), L.ptr(self.top), L.ptr(self.Rs), L.ptr(self.ts), B, H, K,
+                                        L.ptr(self.R), L.ptr(self.t), L.ptr(self.sc), L.ptr(self.pool), st), "select_best")
+        return self.R, self.t, self.sc, self.pool
+
+
 def coarse_pose_hypothesis_sharded(atten, score, pts1, pts2, n_proposal1, n_proposal2, u, group=None):
-    """compute_coarse_Rt_overlap with the hypotheses split across the ranks of `group` (partitioning B).
-    `u` (B, 3*n_proposal1) must be identical on every rank (draw it from the same seed).  Returns
-    (R, t, score, pool_idx), identical on every rank and bit-identical to the single-GPU solver."""
-    import ctypes  # noqa: F401
-
-    from . import _lib as L
-
-    rank, world = _world(group)
+    """One-shot form of HypothesisShardedCoarse (allocates its buffers per call).  `u` (B, 3*n_proposal1) must be
+    identical on every rank (draw it from the same seed).  Returns (R, t, score, pool_idx), identical on every rank and
+    bit-identical to the single-GPU solver."""
     B, N1, _ = pts1.shape
-    N2 = pts2.shape[1]
-    H, K = int(n_proposal1), int(n_proposal2)
-    dev = pts1.device
-    lib = L.load()
     atten, pts1, pts2, u = (x.float().contiguous() for x in (atten, pts1, pts2, u))
-    s1 = s2 = None
-    ld = 0
     if score is not None:
         score = score.float().contiguous()
-        ld = score.shape[1]
-        s1, s2 = score, score[:, N2:]
-    st = lambda: L.stream_ptr(pts1)
-    f32 = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
-        # replicated: masks + CDF
-        ws = torch.empty(max(lib.upk_coarse_assignment_workspace_bytes(B, N1, N2), 256), dtype=torch.uint8, device=dev)
-        w1, w2, cdf = f32(B, N1), f32(B, N2), f32(B, N1 * N2)
-        L.check(lib.upk_coarse_assignment(L.ptr(atten), L.ptr(s1), ld, s2.data_ptr() if s2 is not None else None, ld,
-                                          B, N1, N2, L.ptr(ws), ws.numel(), L.ptr(w1), L.ptr(w2), L.ptr(cdf), st()),
-                "coarse_assignment")
-        # my slice of the hypothesis pool
-        h0, h1 = shard_range(H, rank, world)
-        Rs, ts = torch.zeros((B, H, 9), device=dev), torch.zeros((B, H, 3), device=dev)
-        resid = torch.full((B, H), float("inf"), device=dev)
-        L.check(lib.upk_sample_hypotheses(L.ptr(cdf), L.ptr(u), L.ptr(pts1), L.ptr(pts2), B, N1, N2, H, h0, h1,
-                                          None, None, L.ptr(Rs), L.ptr(ts), L.ptr(resid), st()), "sample_hypotheses")
-        if world > 1:
-            # local candidates: the K smallest of my slice (the global top-K is inside the union)
-            sizes = [min(K, shard_range(H, r, world)[1] - shard_range(H, r, world)[0]) for r in range(world)]
-            kl = sizes[rank]
-            loc = resid[:, h0:h1].contiguous()
-            top_l = torch.empty((B, kl), dtype=torch.int32, device=dev)
-            L.check(lib.upk_topk_smallest(L.ptr(loc), B, h1 - h0, kl, L.ptr(top_l), st()), "topk_local")
-            idx = top_l.long() + h0
-            cand = torch.cat([torch.gather(resid, 1, idx).unsqueeze(2), idx.to(torch.float32).unsqueeze(2),
-                              torch.gather(Rs, 1, idx.unsqueeze(2).expand(-1, -1, 9)),
-                              torch.gather(ts, 1, idx.unsqueeze(2).expand(-1, -1, 3))], dim=2)  # (B,kl,14)
-            allc = all_gather_ragged(cand, sizes, dim=1, group=group)                          # collective #1
-            gi = allc[:, :, 1].long()
-            resid = merge_topk_candidates(allc[:, :, 0].contiguous(), gi, H)
-            Rs.scatter_(1, gi.unsqueeze(2).expand(-1, -1, 9), allc[:, :, 2:11].contiguous())
-            ts.scatter_(1, gi.unsqueeze(2).expand(-1, -1, 3), allc[:, :, 11:14].contiguous())
-        top = torch.empty((B, K), dtype=torch.int32, device=dev)
-        L.check(lib.upk_topk_smallest(L.ptr(resid), B, H, K, L.ptr(top), st()), "topk_global")
-        k0, k1 = shard_range(K, rank, world)
-        scores = torch.zeros((B, K), device=dev)
-        L.check(lib.upk_score_hypotheses(L.ptr(pts1), L.ptr(pts2), L.ptr(w1), L.ptr(Rs), L.ptr(ts), L.ptr(top), B,
-                                         N1, N2, H, K, k0, k1, L.ptr(scores), st()), "score_hypotheses")
-        if world > 1:
-            ksz = [shard_range(K, r, world)[1] - shard_range(K, r, world)[0] for r in range(world)]
-            scores = all_gather_ragged(scores[:, k0:k1].contiguous(), ksz, dim=1, group=group)   # collective #2
-        R, t, sc = f32(B, 3, 3), f32(B, 3), f32(B)
-        pool = torch.empty((B,), dtype=torch.int32, device=dev)
-        L.check(lib.upk_select_best(L.ptr(scores.contiguous()), L.ptr(top), L.ptr(Rs), L.ptr(ts), B, H, K, L.ptr(R),
-                                    L.ptr(t), L.ptr(sc), L.ptr(pool), st()), "select_best")
-    return R, t, sc, pool
+    solver = HypothesisShardedCoarse(B, N1, pts2.shape[1], n_proposal1, n_proposal2, pts1.device, group)
+    R, t, sc, pool = solver.run(atten, score, pts1, pts2, u)
+    return R.clone(), t.clone(), sc.clone(), pool.clone()

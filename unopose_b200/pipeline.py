@@ -140,6 +140,9 @@ def run_hot_path(inp, cfg=HotPathConfig(), stages=None, overlap=True):
     def s_fine_pose():
         out["pred_R"], out["pred_t"], out["pred_pose_score"] = MU.compute_fine_Rt_overlap(
             out["f_atten"], inp["f_score"], inp["f_pts1"], inp["f_pts2"], None, cfg.dis_thres, stats=out.get("f_stats"))
+        # the unit exchanged between ranks / copied back to the host: (B, 13) rows [R(9) | t(3) | score]
+        B = out["pred_R"].shape[0]
+        out["result"] = torch.cat([out["pred_R"].reshape(B, 9), out["pred_t"], out["pred_pose_score"].unsqueeze(1)], 1)
 
     ref_chain = [("fps_template+gather", s_template), ("fps_sparse_ref+gather", s_sparse_r),
                  ("ball_query+group_ref", s_pe_r)]
@@ -265,8 +268,6 @@ class HostFedHotPath:
         else:
             o = run_hot_path(self.bufs[slot], self.cfg, overlap=self.overlap)
         self.free[slot].record(main)
-        B = self.batch
-        r = torch.cat([o["pred_R"].reshape(B, 9), o["pred_t"], o["pred_pose_score"].unsqueeze(1)], 1)
-        self.result.copy_(r, non_blocking=True)
+        self.result.copy_(o["result"], non_blocking=True)
         main.synchronize()    # the caller reads the result every step
         return self.result
