@@ -269,6 +269,24 @@ int upk_fine_pose_stats(const float* atten, const float* stats, size_t stats_byt
                         float* R_out, float* t_out, float* score_out, const upk_fine_debug* dbg,
                         upk_stream_t stream);
 
+/* Pitched variants.  atten[b][i][j] lives at atten + (b * n + i) * atten_ld + j (atten_ld >= m floats per row).  With
+ * atten_ld % 4 == 0 and element (0, 1, 1) 16-byte aligned — the layout unopose_b200.model_utils.compute_feature_similarity
+ * allocates for the fine shape: 3 pad floats in front of every row of 2049 — the GEMM stores its tiles with TMA tensor
+ * stores and the assignment passes read them with 128-bit loads; any other pitch takes the 4-byte paths.
+ *   upk_feature_similarity_stats_ld: stats_out may be NULL (logits only).  UPK_ERR_UNSUPPORTED when the tensor-core path
+ *     does not apply, or (with stats_out) when temp is so small that the single-reference exponent sums would underflow
+ *     (2 log2e / temp > 60): callers then use upk_feature_similarity + upk_fine_pose.
+ *   upk_fine_pose_ld: stats may be NULL (three-pass solve). */
+int upk_feature_similarity_stats_ld(const float* feat1, const float* feat2, int b, int n, int m, int c, float temp,
+                                    void* workspace, size_t workspace_bytes, float* atten_out, int atten_ld,
+                                    float* stats_out, size_t stats_bytes, upk_stream_t stream);
+int upk_fine_pose_ld(const float* atten, int atten_ld, const float* stats, size_t stats_bytes, float temp,
+                     const float* score1, int score1_ld, const float* score2, int score2_ld,
+                     const float* pts1, const float* pts2, const float* model_pts, int n_model, int b, int n1,
+                     int n2, float dis_thres, float weight_thresh, void* workspace, size_t workspace_bytes,
+                     float* R_out, float* t_out, float* score_out, const upk_fine_debug* dbg,
+                     upk_stream_t stream);
+
 /* weighted_procrustes(src[b,n,3], ref[b,n,3], weights[b,n] or NULL, thresh, eps)
  * -> R[b,9], t[b,3] with ref ~= R src + t  (model_utils.py:667-743). */
 int upk_weighted_procrustes(const float* src, const float* ref, const float* weights, int b,

@@ -20,3 +20,21 @@ for it in range(3):
     print("rc", rc, "phases (cycles):", [s[i + 1] - s[i] for i in range(8)], "total", s[8] - s[0])
 names = ["load+rowstats+colmax", "cmax+expcol", "colsum gather+chain", "A+labels", "w2+P->global", "scan carry-free", "carry chain", "finalize"]
 print(names)
+# event timing of the kernel alone (stage-wise entry), 50 launches back to back
+ws = torch.empty(max(lib.upk_coarse_assignment_workspace_bytes(B, n, n), 256), dtype=torch.uint8, device=dev)
+def run():
+    L.check(lib.upk_coarse_assignment(L.ptr(att), L.ptr(sc), sc.shape[1], sc[:, n:].data_ptr(), sc.shape[1], B, n, n, L.ptr(ws), ws.numel(),
+                                      L.ptr(w1), L.ptr(w2), L.ptr(cdf), L.stream_ptr(att)), "ca")
+for _ in range(5): run()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+for Bx in (16,):
+    e0.record()
+    for _ in range(50): run()
+    e1.record(); torch.cuda.synchronize()
+    print("k_coarse_assign_exact: %.1f us per launch (B=%d, events over 50 launches)" % (e0.elapsed_time(e1) / 50 * 1e3, Bx))
+import ctypes
+try:
+    cudart = ctypes.CDLL("libcudart.so")
+except OSError:
+    cudart = None

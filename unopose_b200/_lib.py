@@ -55,6 +55,9 @@ _SIGNATURES = {
     "upk_feature_similarity_stats": [c_f, c_f, c_i, c_i, c_i, c_i, c_fl, c_f, c_sz, c_f, c_f, c_sz, c_st],
     "upk_fine_pose_stats": [c_f, c_f, c_sz, c_fl, c_f, c_i, c_f, c_i, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_fl, c_fl,
                             c_f, c_sz, c_f, c_f, c_f, c_f, c_st],
+    "upk_feature_similarity_stats_ld": [c_f, c_f, c_i, c_i, c_i, c_i, c_fl, c_f, c_sz, c_f, c_i, c_f, c_sz, c_st],
+    "upk_fine_pose_ld": [c_f, c_i, c_f, c_sz, c_fl, c_f, c_i, c_f, c_i, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_fl, c_fl,
+                         c_f, c_sz, c_f, c_f, c_f, c_f, c_st],
     "upk_weighted_procrustes": [c_f, c_f, c_f, c_i, c_i, c_fl, c_fl, c_f, c_f, c_st],
     "upk_global_lrf": [c_f, c_f, c_i, c_i, c_fl, c_f, c_f, c_st],
     "upk_geometric_embedding_supported": [c_i, c_i],

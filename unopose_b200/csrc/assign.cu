@@ -437,10 +437,12 @@ static int stats_labels_t(const float* atten, const float* score1, int ld1, cons
 
 int run_assignment_labels(const float* atten, const float* score1, int ld1, const float* score2, int ld2,
                           int b, const AssignGeom& g, const AssignWs& ws, float* w1, float* w2,
-                          cudaStream_t st, bool for_fine_solve) {
+                          cudaStream_t st, bool for_fine_solve, int atten_ld) {
+  const int ld = atten_ld > 0 ? atten_ld : g.C;
+  // large geometry, fine solve: the streaming passes of assign_fine.cu (the only ones that read a pitched atten)
+  if (g.TR != 32 && for_fine_solve) return run_fine_labels2(atten, ld, score1, ld1, score2, ld2, b, g, ws, w1, w2, st);
+  if (ld != g.C) return UPK_ERR_UNSUPPORTED;
   if (g.TR == 32) return stats_labels_t<32, 128>(atten, score1, ld1, score2, ld2, b, g, ws, w1, w2, st);
-  // large geometry, fine solve: the streaming passes of assign_fine.cu
-  if (for_fine_solve) return run_fine_labels2(atten, score1, ld1, score2, ld2, b, g, ws, w1, w2, st);
   // large geometry, coarse solve (never the case at the UNOPose shapes): the exact tile pipeline at 64 x 256
   return stats_labels_t<64, 256>(atten, score1, ld1, score2, ld2, b, g, ws, w1, w2, st);
 }
@@ -514,10 +516,13 @@ static int fine_rows_t(const float* atten, const float* score1, int ld1, const f
 
 int run_fine_rowsums(const float* atten, const float* score1, int ld1, const float* score2, int ld2, int b,
                      const AssignGeom& g, const AssignWs& ws, const float* w1, const float* w2,
-                     const float* pts2, float4* rowpart4, float* soft, float* asum, cudaStream_t st) {
-  if (g.TR == 32)
+                     const float* pts2, float4* rowpart4, float* soft, float* asum, cudaStream_t st, int atten_ld) {
+  const int ld = atten_ld > 0 ? atten_ld : g.C;
+  if (g.TR == 32) {
+    if (ld != g.C) return UPK_ERR_UNSUPPORTED;
     return fine_rows_t<32, 128>(atten, score1, ld1, score2, ld2, b, g, ws, w1, w2, pts2, rowpart4, soft, asum, st);
-  return run_fine_rows2(atten, b, g, ws, w1, w2, pts2, rowpart4, soft, asum, st);
+  }
+  return run_fine_rows2(atten, ld, b, g, ws, w1, w2, pts2, rowpart4, soft, asum, st);
 }
 
 }  // namespace upk

@@ -23,6 +23,12 @@
 // maximum and is raised (column sums rescaled) if a later partial sum exceeds 2^20.  Partial sums that
 // come out below 2^-80 or non-finite (logit range > ~50: never for cosine/temperature logits) raise a
 // per-instance flag; the merge kernel then recomputes that instance's statistics exactly (max-subtracting).
+//
+// Row pitch.  `atten` may be PITCHED (ld >= C floats per row).  compute_feature_similarity hands out a padded layout for
+// the fine shape — ld % 4 == 0 and element (i, 1) 16-byte aligned — so that the GEMM stores tiles with TMA and these
+// passes read them with 128-bit loads (VEC = true: a lane owns columns 4 lane .. 4 lane + 3 and 128 + 4 lane .. of the
+// strip); a plain contiguous tensor (pitch 2049: rows only 4-byte aligned) takes the scalar loads (VEC = false: lane
+// owns columns lane + 32 k).  Everything downstream of the loads is agnostic of which columns a lane owns.
 #include <math.h>
 
 #include "common.cuh"
@@ -71,22 +77,50 @@ __device__ __forceinline__ float reduce_pair(float a, float b, int lane, Op op) 
 struct F2Add { __device__ __forceinline__ float operator()(float a, float b) const { return a + b; } };
 struct F2Max { __device__ __forceinline__ float operator()(float a, float b) const { return fmaxf(a, b); } };
 
-// Two row segments (rows ra and ra + 8) of the strip: 16 independent coalesced loads.
+// Strip-local column of a lane's k-th value
+template <bool VEC>
+__device__ __forceinline__ int f2_lcol(int lane, int k) {
+  return VEC ? ((k >> 2) * 128 + lane * 4 + (k & 3)) : (lane + 32 * k);
+}
+
+// Two row segments (rows ra and ra + 8) of the strip: 16 values per lane, all loads independent.
 struct RowPair {
   float a[F2_CPT], b[F2_CPT];
 };
-template <bool CHECK>
-__device__ __forceinline__ void load_pair(const float* __restrict__ pa, size_t pitch8, int ncl, bool oka, bool okb,
-                                          RowPair& v) {
+// pa -> A[ra][first column of the strip]; nv = number of valid columns in the strip (C - c0)
+template <bool CHECK, bool VEC>
+__device__ __forceinline__ void load_pair(const float* __restrict__ pa, size_t pitch8, int nv, int lane, bool oka,
+                                          bool okb, RowPair& v) {
+  if (VEC) {
 #pragma unroll
-  for (int k = 0; k < F2_CPT; ++k) {
-    if (CHECK) {
-      const bool c = 32 * k < ncl;
-      v.a[k] = (oka && c) ? ld_stream_f1(pa + 32 * k) : -INFINITY;
-      v.b[k] = (okb && c) ? ld_stream_f1(pa + pitch8 + 32 * k) : -INFINITY;
-    } else {
-      v.a[k] = ld_stream_f1(pa + 32 * k);
-      v.b[k] = ld_stream_f1(pa + pitch8 + 32 * k);
+    for (int h = 0; h < 2; ++h) {
+      const int off = 128 * h + 4 * lane;
+      if (!CHECK || off + 3 < nv) {
+        float4 x = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY), y = x;
+        if (!CHECK || oka) x = ld_stream_f4(reinterpret_cast<const float4*>(pa + off));
+        if (!CHECK || okb) y = ld_stream_f4(reinterpret_cast<const float4*>(pa + pitch8 + off));
+        v.a[4 * h] = x.x; v.a[4 * h + 1] = x.y; v.a[4 * h + 2] = x.z; v.a[4 * h + 3] = x.w;
+        v.b[4 * h] = y.x; v.b[4 * h + 1] = y.y; v.b[4 * h + 2] = y.z; v.b[4 * h + 3] = y.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const bool c = off + e < nv;
+          v.a[4 * h + e] = (oka && c) ? ld_stream_f1(pa + off + e) : -INFINITY;
+          v.b[4 * h + e] = (okb && c) ? ld_stream_f1(pa + pitch8 + off + e) : -INFINITY;
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < F2_CPT; ++k) {
+      if (CHECK) {
+        const bool c = lane + 32 * k < nv;
+        v.a[k] = (oka && c) ? ld_stream_f1(pa + lane + 32 * k) : -INFINITY;
+        v.b[k] = (okb && c) ? ld_stream_f1(pa + pitch8 + lane + 32 * k) : -INFINITY;
+      } else {
+        v.a[k] = ld_stream_f1(pa + lane + 32 * k);
+        v.b[k] = ld_stream_f1(pa + pitch8 + lane + 32 * k);
+      }
     }
   }
 }
@@ -95,17 +129,20 @@ __device__ __forceinline__ void load_pair(const float* __restrict__ pa, size_t p
 struct F2Tile {
   int b, cs, rt, warp, lane;
   int i0;    // first row of this warp (rows i0 + 16 p and i0 + 16 p + 8, p < F2_PAIRS)
-  int j0;    // first column of this lane (columns j0 + 32 k)
-  int ncl;   // C - j0: column k is valid iff 32 k < ncl
+  int c0;    // first column of the strip (global index, >= 1)
+  int nv;    // C - c0: strip-local column c is valid iff c < nv
   bool full; // no row / column of the CTA's tile is out of range
 };
-__device__ __forceinline__ F2Tile f2_tile(int R, int C) {
+// flip: walk the instances in descending order (the pass then starts on the instances the previous kernel touched
+// last, which are the ones still resident in L2)
+__device__ __forceinline__ F2Tile f2_tile(int R, int C, bool flip) {
   F2Tile t;
-  t.b = blockIdx.z; t.rt = blockIdx.y; t.cs = blockIdx.x;
+  t.b = flip ? (int)(gridDim.z - 1 - blockIdx.z) : (int)blockIdx.z;
+  t.rt = blockIdx.y; t.cs = blockIdx.x;
   t.warp = threadIdx.x >> 5; t.lane = threadIdx.x & 31;
   t.i0 = 1 + t.rt * F2_RT + t.warp;
-  t.j0 = 1 + t.cs * F2_TC + t.lane;
-  t.ncl = C - t.j0;
+  t.c0 = 1 + t.cs * F2_TC;
+  t.nv = C - t.c0;
   t.full = (1 + (t.rt + 1) * F2_RT <= R) && (1 + (t.cs + 1) * F2_TC <= C);
   return t;
 }
@@ -169,11 +206,11 @@ __device__ __forceinline__ void stats_pair(const RowPair& v, float v0a, float v0
   }
 }
 
-template <bool CHECK, bool STRIP0>
-__device__ __forceinline__ void stats_body(const float* __restrict__ A, int R, int C, int nstrip, const F2Tile& t,
+template <bool CHECK, bool STRIP0, bool VEC>
+__device__ __forceinline__ void stats_body(const float* __restrict__ A, int R, int ld, int nstrip, const F2Tile& t,
                                            float2* __restrict__ rowpart, StatsState& st) {
-  const size_t pitch8 = (size_t)8 * C;
-  const float* col0 = A;  // column 0 of row i: A[i * C]
+  const size_t pitch8 = (size_t)8 * ld;
+  const float* col0 = A;  // column 0 of row i: A[i * ld]
   auto emit = [&](int ra, bool okb, const float2& oa, const float2& ob) {
     if (t.lane == 0) {
       rowpart[((size_t)t.b * R + ra) * nstrip + t.cs] = oa;
@@ -186,7 +223,7 @@ __device__ __forceinline__ void stats_body(const float* __restrict__ A, int R, i
   };
   if (t.rt == 0 && t.warp == 0) {  // the background row 0 rides with the first row tile
     RowPair v;
-    load_pair<true>(A + t.j0, pitch8, t.ncl, true, false, v);
+    load_pair<true, VEC>(A + t.c0, pitch8, t.nv, t.lane, true, false, v);
     float v0a = -INFINITY;
     if (STRIP0 && t.lane == 0) v0a = col0[0];
     float2 oa, ob;
@@ -197,15 +234,15 @@ __device__ __forceinline__ void stats_body(const float* __restrict__ A, int R, i
     }
   }
   // two row pairs in flight: the loads of pair p + 1 are issued before pair p is processed
-  auto ld = [&](RowPair& v, float& z0a, float& z0b, int p) {
+  auto fetch = [&](RowPair& v, float& z0a, float& z0b, int p) {
     const int ra = t.i0 + 16 * p;
     const bool oka = !CHECK || ra < R, okb = !CHECK || ra + 8 < R;
-    load_pair<CHECK>(A + (size_t)ra * C + t.j0, pitch8, t.ncl, oka, okb, v);
+    load_pair<CHECK, VEC>(A + (size_t)ra * ld + t.c0, pitch8, t.nv, t.lane, oka, okb, v);
     if (STRIP0) {
       z0a = z0b = -INFINITY;
       if (t.lane == 0) {
-        if (oka) z0a = col0[(size_t)ra * C];
-        if (okb) z0b = col0[(size_t)(ra + 8) * C];
+        if (oka) z0a = col0[(size_t)ra * ld];
+        if (okb) z0b = col0[(size_t)(ra + 8) * ld];
       }
     }
   };
@@ -218,38 +255,39 @@ __device__ __forceinline__ void stats_body(const float* __restrict__ A, int R, i
   };
   RowPair va, vb;
   float a0a = -INFINITY, a0b = -INFINITY, b0a = -INFINITY, b0b = -INFINITY;
-  ld(va, a0a, a0b, 0);
+  fetch(va, a0a, a0b, 0);
 #pragma unroll 1
   for (int p = 0; p < F2_PAIRS; p += 2) {
-    ld(vb, b0a, b0b, p + 1);
+    fetch(vb, b0a, b0b, p + 1);
     comp(va, a0a, a0b, p);
-    if (p + 2 < F2_PAIRS) ld(va, a0a, a0b, p + 2);
+    if (p + 2 < F2_PAIRS) fetch(va, a0a, a0b, p + 2);
     comp(vb, b0a, b0b, p + 1);
   }
 }
 
 // (80 registers: 3 CTAs / SM, 54 us vs 59 us at 2)
+template <bool VEC>
 __global__ void __launch_bounds__(F2_THREADS, 3)
-k_fine_stats(const float* __restrict__ atten, int R, int C, int nstrip, int nrt, float2* __restrict__ rowpart,
+k_fine_stats(const float* __restrict__ atten, int R, int C, int ld, int nstrip, int nrt, float2* __restrict__ rowpart,
              float2* __restrict__ colpart, int* __restrict__ flags) {
   __shared__ float s_cs[F2_WARPS][F2_TC + 1];
   __shared__ float s_g[F2_WARPS];
-  const F2Tile t = f2_tile(R, C);
-  const float* A = atten + (size_t)t.b * R * C;
+  const F2Tile t = f2_tile(R, C, false);
+  const float* A = atten + (size_t)t.b * R * ld;
   StatsState st;
   st.g = -INFINITY; st.c0 = 0.f; st.bad = false;
 #pragma unroll
   for (int k = 0; k < F2_CPT; ++k) st.cs[k] = 0.f;
   if (t.cs == 0) {
-    if (t.full) stats_body<false, true>(A, R, C, nstrip, t, rowpart, st);
-    else stats_body<true, true>(A, R, C, nstrip, t, rowpart, st);
+    if (t.full) stats_body<false, true, VEC>(A, R, ld, nstrip, t, rowpart, st);
+    else stats_body<true, true, VEC>(A, R, ld, nstrip, t, rowpart, st);
   } else {
-    if (t.full) stats_body<false, false>(A, R, C, nstrip, t, rowpart, st);
-    else stats_body<true, false>(A, R, C, nstrip, t, rowpart, st);
+    if (t.full) stats_body<false, false, VEC>(A, R, ld, nstrip, t, rowpart, st);
+    else stats_body<true, false, VEC>(A, R, ld, nstrip, t, rowpart, st);
   }
   // combine the 8 warps' column sums (each attached to its own reference)
 #pragma unroll
-  for (int k = 0; k < F2_CPT; ++k) s_cs[t.warp][t.lane + 32 * k] = st.cs[k];
+  for (int k = 0; k < F2_CPT; ++k) s_cs[t.warp][f2_lcol<VEC>(t.lane, k)] = st.cs[k];
   if (t.lane == 0) {
     s_cs[t.warp][F2_TC] = st.c0;
     s_g[t.warp] = st.g;
@@ -260,7 +298,7 @@ k_fine_stats(const float* __restrict__ atten, int R, int C, int nstrip, int nrt,
   for (int w = 0; w < F2_WARPS; ++w) G = fmaxf(G, s_g[w]);
   bool bad = st.bad;
   for (int c = threadIdx.x; c < F2_TC + (t.cs == 0 ? 1 : 0); c += F2_THREADS) {
-    const int gj = c == F2_TC ? 0 : 1 + t.cs * F2_TC + c;
+    const int gj = c == F2_TC ? 0 : t.c0 + c;
     if (gj >= C) continue;
     float s = 0.f;
 #pragma unroll
@@ -280,7 +318,7 @@ k_fine_stats(const float* __restrict__ atten, int R, int C, int nstrip, int nrt,
 // pathological logits, and it keeps the common path at one launch.
 __global__ void __launch_bounds__(256)
 k_fine_stats_merge(const float* __restrict__ atten, const float2* __restrict__ rowpart,
-                   const float2* __restrict__ colpart, int R, int C, int nstrip, int nrt,
+                   const float2* __restrict__ colpart, int R, int C, int ld, int nstrip, int nrt,
                    const float* __restrict__ score1, int ld1, const float* __restrict__ score2, int ld2,
                    const int* __restrict__ flags, float* __restrict__ rml, float* __restrict__ rmul,
                    float* __restrict__ cml, float* __restrict__ cmul) {
@@ -295,8 +333,8 @@ k_fine_stats_merge(const float* __restrict__ atten, const float2* __restrict__ r
   float* const ol = is_row ? rml + (size_t)b * R + i : cml + (size_t)b * C + c;
   float* const om = is_row ? rmul + (size_t)b * R + i : cmul + (size_t)b * C + c;
   if (flags[b]) {
-    const float* A = atten + (size_t)b * R * C + (is_row ? (size_t)i * C : (size_t)c);
-    const size_t step = is_row ? 1 : (size_t)C;
+    const float* A = atten + (size_t)b * R * ld + (is_row ? (size_t)i * ld : (size_t)c);
+    const size_t step = is_row ? 1 : (size_t)ld;
     const int len = is_row ? C : R;
     float mx = -INFINITY;
     for (int k = 0; k < len; ++k) mx = fmaxf(mx, A[k * step]);
@@ -317,51 +355,54 @@ k_fine_stats_merge(const float* __restrict__ atten, const float2* __restrict__ r
 }
 
 // ---- fused-statistics path: pass 1 came out of the similarity GEMM's epilogue (similarity_tc.cu, STATS) as
-// per-tile partial sums of 2^(v log2e - gref) over the main block; the background row / column are added here.
-__global__ void __launch_bounds__(256)
-k_fine_border_sums(const float* __restrict__ atten, int R, int C, float gref, float* __restrict__ bsum) {
-  __shared__ float s_part[2][8];
-  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const float* A = atten + (size_t)b * R * C;
-  float r0 = 0.f, c0 = 0.f;
-  for (int j = threadIdx.x; j < C; j += 256) r0 += ex2_approx(fmaf(A[j], kL2E, -gref));               // row 0
-  for (int i = threadIdx.x; i < R; i += 256) c0 += ex2_approx(fmaf(A[(size_t)i * C], kL2E, -gref));   // column 0
-  r0 = warp_sum(r0);
-  c0 = warp_sum(c0);
-  if (lane == 0) { s_part[0][warp] = r0; s_part[1][warp] = c0; }
-  __syncthreads();
-  if (threadIdx.x < 2) {
-    float t = 0.f;
-    for (int w = 0; w < 8; ++w) t += s_part[threadIdx.x][w];
-    bsum[b * 2 + threadIdx.x] = t;
-  }
-}
-
+// per-tile partial sums of 2^(v log2e - gref) over the main block.  One launch merges them (4-way unrolled partial
+// reads); the LAST CTA of every instance (blockIdx.x == nmerge) adds up the peeled background row / column itself.
 __global__ void __launch_bounds__(256)
 k_fine_stats_merge_fused(const float* __restrict__ atten, const float* __restrict__ rowpart,
-                         const float* __restrict__ colpart, int npr, int npc, float gref,
-                         const float* __restrict__ bsum, int R, int C, const float* __restrict__ score1, int ld1,
-                         const float* __restrict__ score2, int ld2, float* __restrict__ rml,
-                         float* __restrict__ rmul, float* __restrict__ cml, float* __restrict__ cmul) {
+                         const float* __restrict__ colpart, int npr, int npc, float gref, int nmerge, int R, int C,
+                         int ld, const float* __restrict__ score1, int ld1, const float* __restrict__ score2, int ld2,
+                         float* __restrict__ rml, float* __restrict__ rmul, float* __restrict__ cml,
+                         float* __restrict__ cmul) {
+  __shared__ float s_part[2][8];
   const int b = blockIdx.y;
+  const float* A = atten + (size_t)b * R * ld;
+  if ((int)blockIdx.x == nmerge) {   // background row 0 and column 0 (their own exponent sums; score 1.0)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float r0 = 0.f, c0 = 0.f;
+    for (int j = threadIdx.x; j < C; j += 256) r0 += ex2_approx(fmaf(A[j], kL2E, -gref));
+    for (int i = threadIdx.x; i < R; i += 256) c0 += ex2_approx(fmaf(A[(size_t)i * ld], kL2E, -gref));
+    r0 = warp_sum(r0);
+    c0 = warp_sum(c0);
+    if (lane == 0) { s_part[0][warp] = r0; s_part[1][warp] = c0; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      float t = 0.f;
+      for (int w = 0; w < 8; ++w) t += s_part[threadIdx.x][w];
+      if (threadIdx.x == 0) { rml[(size_t)b * R] = gref; rmul[(size_t)b * R] = 1.f / t; }
+      else { cml[(size_t)b * C] = gref; cmul[(size_t)b * C] = 1.f / t; }
+    }
+    return;
+  }
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= R + C) return;
   const bool is_row = i < R;
   const int k = is_row ? i : i - R;
-  const float* A = atten + (size_t)b * R * C;
-  float sc = 1.f, s;
-  if (is_row) { if (k > 0 && score1) sc = score1[(size_t)b * ld1 + k - 1]; }
-  else if (k > 0 && score2) sc = score2[(size_t)b * ld2 + k - 1];
-  if (k == 0) {
-    s = bsum[b * 2 + (is_row ? 0 : 1)];
-  } else {
-    // partial-major layouts: consecutive threads read consecutive words
-    const float* p = is_row ? rowpart + (size_t)b * npr * R + k : colpart + (size_t)b * npc * C + k;
-    const int n = is_row ? npr : npc;
-    const size_t step = is_row ? (size_t)R : (size_t)C;
-    s = ex2_approx(fmaf(is_row ? A[(size_t)k * C] : A[k], kL2E, -gref));   // the background column / row entry
-    for (int q = 0; q < n; ++q) s += p[q * step];
+  if (k == 0) return;
+  float sc = 1.f;
+  if (is_row) { if (score1) sc = score1[(size_t)b * ld1 + k - 1]; }
+  else if (score2) sc = score2[(size_t)b * ld2 + k - 1];
+  // partial-major layouts: consecutive threads read consecutive words
+  const float* p = is_row ? rowpart + (size_t)b * npr * R + k : colpart + (size_t)b * npc * C + k;
+  const int n = is_row ? npr : npc;
+  const size_t step = is_row ? (size_t)R : (size_t)C;
+  float s0 = ex2_approx(fmaf(is_row ? A[(size_t)k * ld] : A[k], kL2E, -gref));   // the background column / row entry
+  float s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int q = 0;
+  for (; q + 3 < n; q += 4) {
+    s0 += p[q * step]; s1 += p[(q + 1) * step]; s2 += p[(q + 2) * step]; s3 += p[(q + 3) * step];
   }
+  for (; q < n; ++q) s0 += p[q * step];
+  const float s = (s0 + s1) + (s2 + s3);
   if (is_row) { rml[(size_t)b * R + k] = gref; rmul[(size_t)b * R + k] = sc / s; }
   else { cml[(size_t)b * C + k] = gref; cmul[(size_t)b * C + k] = sc / s; }
 }
@@ -371,6 +412,7 @@ struct ColConst2 {
   unsigned long long ncml[F2_CPT / 2];  // packed -cml_j
   unsigned long long cmul[F2_CPT / 2];  // packed  s2_j / cs_j   (pass 3: times w2_j)
 };
+template <bool VEC>
 __device__ __forceinline__ void load_col_consts2(ColConst2& kc, const F2Tile& t, int C, const float* __restrict__ cml,
                                                  const float* __restrict__ cmul, const float* __restrict__ w2) {
 #pragma unroll
@@ -378,12 +420,12 @@ __device__ __forceinline__ void load_col_consts2(ColConst2& kc, const F2Tile& t,
     float l[2], m[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const int k = 2 * kk + h;
-      const bool ok = 32 * k < t.ncl;
-      const size_t o = (size_t)t.b * C + t.j0 + 32 * k;
+      const int lc = f2_lcol<VEC>(t.lane, 2 * kk + h);
+      const bool ok = lc < t.nv;
+      const size_t o = (size_t)t.b * C + t.c0 + lc;
       l[h] = ok ? -cml[o] : 0.f;
       m[h] = ok ? cmul[o] : 0.f;
-      if (w2 && ok) m[h] *= w2[(size_t)t.b * (C - 1) + t.j0 + 32 * k - 1];
+      if (w2 && ok) m[h] *= w2[(size_t)t.b * (C - 1) + t.c0 + lc - 1];
     }
     kc.ncml[kk] = pack2(l[0], l[1]);
     kc.cmul[kk] = pack2(m[0], m[1]);
@@ -404,20 +446,20 @@ __device__ __forceinline__ void row_exps(const float (&v)[F2_CPT], float nrml, c
 
 // ------------------------------------------------------------------ pass 2: background-vs-foreground tests
 //   w1[i-1] = (argmax_j S[i][:] > 0)  <=>  max_{j>=1} S[i][j] > S[i][0]   (torch.max keeps the first maximum)
-template <bool CHECK, bool STRIP0>
-__device__ __forceinline__ void labels_body(const float* __restrict__ A, int R, int C, int nstrip, const F2Tile& t,
+template <bool CHECK, bool STRIP0, bool VEC>
+__device__ __forceinline__ void labels_body(const float* __restrict__ A, int R, int ld, int nstrip, const F2Tile& t,
                                             const ColConst2& kc, float cml0, float cmul0,
                                             const float* __restrict__ rml, const float* __restrict__ rmul,
                                             float* __restrict__ rowpm, float* __restrict__ ai0,
                                             float (&cmx)[F2_CPT]) {
-  const size_t pitch8 = (size_t)8 * C;
-  auto ld = [&](RowPair& v, float& z0a, float& z0b, int p) {
+  const size_t pitch8 = (size_t)8 * ld;
+  auto fetch = [&](RowPair& v, float& z0a, float& z0b, int p) {
     const int ra = t.i0 + 16 * p;
     const bool oka = !CHECK || ra < R, okb = !CHECK || ra + 8 < R;
-    load_pair<CHECK>(A + (size_t)ra * C + t.j0, pitch8, t.ncl, oka, okb, v);
+    load_pair<CHECK, VEC>(A + (size_t)ra * ld + t.c0, pitch8, t.nv, t.lane, oka, okb, v);
     if (STRIP0 && t.lane == 0) {
-      z0a = oka ? A[(size_t)ra * C] : 0.f;
-      z0b = okb ? A[(size_t)(ra + 8) * C] : 0.f;
+      z0a = oka ? A[(size_t)ra * ld] : 0.f;
+      z0b = okb ? A[(size_t)(ra + 8) * ld] : 0.f;
     }
   };
   auto comp = [&](const RowPair& cur, float c0a, float c0b, int p) {
@@ -437,7 +479,7 @@ __device__ __forceinline__ void labels_body(const float* __restrict__ A, int R, 
       unpack2(mul2(mul2(ea[kk], MA), kc.cmul[kk]), a0, a1);
       unpack2(mul2(mul2(eb[kk], MB), kc.cmul[kk]), b0, b1);
       if (CHECK) {  // out-of-range entries must not take part in any maximum
-        const bool v0 = 32 * (2 * kk) < t.ncl, v1 = 32 * (2 * kk + 1) < t.ncl;
+        const bool v0 = f2_lcol<VEC>(t.lane, 2 * kk) < t.nv, v1 = f2_lcol<VEC>(t.lane, 2 * kk + 1) < t.nv;
         a0 = v0 ? a0 : -INFINITY; a1 = v1 ? a1 : -INFINITY;
         b0 = (v0 && okb) ? b0 : -INFINITY; b1 = (v1 && okb) ? b1 : -INFINITY;
       }
@@ -456,33 +498,34 @@ __device__ __forceinline__ void labels_body(const float* __restrict__ A, int R, 
   };
   RowPair va, vb;
   float a0a = 0.f, a0b = 0.f, b0a = 0.f, b0b = 0.f;
-  ld(va, a0a, a0b, 0);
+  fetch(va, a0a, a0b, 0);
 #pragma unroll 1
   for (int p = 0; p < F2_PAIRS; p += 2) {
-    ld(vb, b0a, b0b, p + 1);
+    fetch(vb, b0a, b0b, p + 1);
     comp(va, a0a, a0b, p);
-    if (p + 2 < F2_PAIRS) ld(va, a0a, a0b, p + 2);
+    if (p + 2 < F2_PAIRS) fetch(va, a0a, a0b, p + 2);
     comp(vb, b0a, b0b, p + 1);
   }
 }
 
 // (2 CTAs / SM with the next row pair prefetched in registers beats 3 CTAs without: 59 vs 72 us)
+template <bool VEC>
 __global__ void __launch_bounds__(F2_THREADS, 2)
-k_fine_labels(const float* __restrict__ atten, int R, int C, int nstrip, int nrt, const float* __restrict__ rml,
+k_fine_labels(const float* __restrict__ atten, int R, int C, int ld, int nstrip, int nrt, const float* __restrict__ rml,
               const float* __restrict__ rmul, const float* __restrict__ cml, const float* __restrict__ cmul,
               float* __restrict__ rowpm, float* __restrict__ colpm, float* __restrict__ ai0,
-              float* __restrict__ a0j) {
+              float* __restrict__ a0j, int flip) {
   __shared__ float s_cm[F2_WARPS][F2_TC];
-  const F2Tile t = f2_tile(R, C);
-  const float* A = atten + (size_t)t.b * R * C;
+  const F2Tile t = f2_tile(R, C, flip != 0);
+  const float* A = atten + (size_t)t.b * R * ld;
   ColConst2 kc;
-  load_col_consts2(kc, t, C, cml, cmul, nullptr);
+  load_col_consts2<VEC>(kc, t, C, cml, cmul, nullptr);
   float cmx[F2_CPT];
 #pragma unroll
   for (int k = 0; k < F2_CPT; ++k) cmx[k] = -INFINITY;
   if (t.rt == 0 && t.warp == 0) {  // S[0][j] for this strip's columns (the background row is in no maximum)
     RowPair v;
-    load_pair<true>(A + t.j0, 0, t.ncl, true, false, v);
+    load_pair<true, VEC>(A + t.c0, 0, t.nv, t.lane, true, false, v);
     const float rml0 = rml[(size_t)t.b * R], rmul0 = rmul[(size_t)t.b * R];
     unsigned long long e[F2_CPT / 2];
     row_exps(v.a, -rml0, kc, e);
@@ -491,23 +534,24 @@ k_fine_labels(const float* __restrict__ atten, int R, int C, int nstrip, int nrt
     for (int kk = 0; kk < F2_CPT / 2; ++kk) {
       float a0, a1;
       unpack2(mul2(mul2(e[kk], M0), kc.cmul[kk]), a0, a1);
-      if (32 * (2 * kk) < t.ncl) a0j[(size_t)t.b * C + t.j0 + 32 * (2 * kk)] = a0;
-      if (32 * (2 * kk + 1) < t.ncl) a0j[(size_t)t.b * C + t.j0 + 32 * (2 * kk + 1)] = a1;
+      const int l0 = f2_lcol<VEC>(t.lane, 2 * kk), l1 = f2_lcol<VEC>(t.lane, 2 * kk + 1);
+      if (l0 < t.nv) a0j[(size_t)t.b * C + t.c0 + l0] = a0;
+      if (l1 < t.nv) a0j[(size_t)t.b * C + t.c0 + l1] = a1;
     }
   }
   const float cml0 = cml[(size_t)t.b * C], cmul0 = cmul[(size_t)t.b * C];
   if (t.cs == 0) {
-    if (t.full) labels_body<false, true>(A, R, C, nstrip, t, kc, cml0, cmul0, rml, rmul, rowpm, ai0, cmx);
-    else labels_body<true, true>(A, R, C, nstrip, t, kc, cml0, cmul0, rml, rmul, rowpm, ai0, cmx);
+    if (t.full) labels_body<false, true, VEC>(A, R, ld, nstrip, t, kc, cml0, cmul0, rml, rmul, rowpm, ai0, cmx);
+    else labels_body<true, true, VEC>(A, R, ld, nstrip, t, kc, cml0, cmul0, rml, rmul, rowpm, ai0, cmx);
   } else {
-    if (t.full) labels_body<false, false>(A, R, C, nstrip, t, kc, cml0, cmul0, rml, rmul, rowpm, ai0, cmx);
-    else labels_body<true, false>(A, R, C, nstrip, t, kc, cml0, cmul0, rml, rmul, rowpm, ai0, cmx);
+    if (t.full) labels_body<false, false, VEC>(A, R, ld, nstrip, t, kc, cml0, cmul0, rml, rmul, rowpm, ai0, cmx);
+    else labels_body<true, false, VEC>(A, R, ld, nstrip, t, kc, cml0, cmul0, rml, rmul, rowpm, ai0, cmx);
   }
 #pragma unroll
-  for (int k = 0; k < F2_CPT; ++k) s_cm[t.warp][t.lane + 32 * k] = cmx[k];
+  for (int k = 0; k < F2_CPT; ++k) s_cm[t.warp][f2_lcol<VEC>(t.lane, k)] = cmx[k];
   __syncthreads();
   const int c = threadIdx.x;
-  const int gj = 1 + t.cs * F2_TC + c;
+  const int gj = t.c0 + c;
   if (gj < C) {
     float m = -INFINITY;
 #pragma unroll
@@ -518,17 +562,17 @@ k_fine_labels(const float* __restrict__ atten, int R, int C, int nstrip, int nrt
 
 // ------------------------------------------------------------------ pass 3: masked soft correspondences
 //   per row i >= 1:  rmul_i * sum_{j>=1} e_ij (cmul_j w2_j) {x_j, y_j, z_j, 1}      (model_utils.py:549-555)
-template <bool CHECK>
-__device__ __forceinline__ void rows_body(const float* __restrict__ A, int R, int C, int nstrip, const F2Tile& t,
+template <bool CHECK, bool VEC>
+__device__ __forceinline__ void rows_body(const float* __restrict__ A, int R, int ld, int nstrip, const F2Tile& t,
                                           const ColConst2& kc, const unsigned long long (&px)[F2_CPT / 2],
                                           const unsigned long long (&py)[F2_CPT / 2],
                                           const unsigned long long (&pz)[F2_CPT / 2], const float* __restrict__ rml,
                                           const float* __restrict__ rmul, float4* __restrict__ rowpart4) {
-  const size_t pitch8 = (size_t)8 * C;
+  const size_t pitch8 = (size_t)8 * ld;
   const int N1 = R - 1;
-  auto ld = [&](RowPair& v, int p) {
+  auto fetch = [&](RowPair& v, int p) {
     const int ra = t.i0 + 16 * p;
-    load_pair<CHECK>(A + (size_t)ra * C + t.j0, pitch8, t.ncl, !CHECK || ra < R, !CHECK || ra + 8 < R, v);
+    load_pair<CHECK, VEC>(A + (size_t)ra * ld + t.c0, pitch8, t.nv, t.lane, !CHECK || ra < R, !CHECK || ra + 8 < R, v);
   };
   auto comp = [&](const RowPair& cur, int p) {
     const int ra = t.i0 + 16 * p, rb = ra + 8;
@@ -584,39 +628,40 @@ __device__ __forceinline__ void rows_body(const float* __restrict__ A, int R, in
     }
   };
   RowPair va, vb;
-  ld(va, 0);
+  fetch(va, 0);
 #pragma unroll 1
   for (int p = 0; p < F2_PAIRS; p += 2) {
-    ld(vb, p + 1);
+    fetch(vb, p + 1);
     comp(va, p);
-    if (p + 2 < F2_PAIRS) ld(va, p + 2);
+    if (p + 2 < F2_PAIRS) fetch(va, p + 2);
     comp(vb, p + 1);
   }
 }
 
+template <bool VEC>
 __global__ void __launch_bounds__(F2_THREADS, 2)
-k_fine_rows(const float* __restrict__ atten, int R, int C, int nstrip, const float* __restrict__ rml,
+k_fine_rows(const float* __restrict__ atten, int R, int C, int ld, int nstrip, const float* __restrict__ rml,
             const float* __restrict__ rmul, const float* __restrict__ cml, const float* __restrict__ cmul,
             const float* __restrict__ w2, const float* __restrict__ pts2, float4* __restrict__ rowpart4) {
-  const F2Tile t = f2_tile(R, C);
-  const float* A = atten + (size_t)t.b * R * C;
+  const F2Tile t = f2_tile(R, C, false);
+  const float* A = atten + (size_t)t.b * R * ld;
   ColConst2 kc;
-  load_col_consts2(kc, t, C, cml, cmul, w2);
+  load_col_consts2<VEC>(kc, t, C, cml, cmul, w2);
   unsigned long long px[F2_CPT / 2], py[F2_CPT / 2], pz[F2_CPT / 2];
 #pragma unroll
   for (int kk = 0; kk < F2_CPT / 2; ++kk) {
     float x[2], y[2], z[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const int k = 2 * kk + h;
-      const bool ok = 32 * k < t.ncl;
-      const float* p = pts2 + ((size_t)t.b * (C - 1) + (ok ? t.j0 + 32 * k - 1 : 0)) * 3;
+      const int lc = f2_lcol<VEC>(t.lane, 2 * kk + h);
+      const bool ok = lc < t.nv;
+      const float* p = pts2 + ((size_t)t.b * (C - 1) + (ok ? t.c0 + lc - 1 : 0)) * 3;
       x[h] = p[0]; y[h] = p[1]; z[h] = p[2];
     }
     px[kk] = pack2(x[0], x[1]); py[kk] = pack2(y[0], y[1]); pz[kk] = pack2(z[0], z[1]);
   }
-  if (t.full) rows_body<false>(A, R, C, nstrip, t, kc, px, py, pz, rml, rmul, rowpart4);
-  else rows_body<true>(A, R, C, nstrip, t, kc, px, py, pz, rml, rmul, rowpart4);
+  if (t.full) rows_body<false, VEC>(A, R, ld, nstrip, t, kc, px, py, pz, rml, rmul, rowpart4);
+  else rows_body<true, VEC>(A, R, ld, nstrip, t, kc, px, py, pz, rml, rmul, rowpart4);
 }
 
 // ------------------------------------------------------------------ host side
@@ -627,44 +672,62 @@ FineGeom2 fine_geom2(int R, int C) {
   return g;
 }
 
-int run_fine_labels2(const float* atten, const float* score1, int ld1, const float* score2, int ld2, int b,
+// 128-bit loads need: pitch a multiple of 4 floats and element (i, 1) of every row 16-byte aligned
+static bool fine_vec_ok(const float* atten, int ld) {
+  return ld % 4 == 0 && ((reinterpret_cast<uintptr_t>(atten + 1)) & 15) == 0;
+}
+
+int run_fine_labels2(const float* atten, int ld, const float* score1, int ld1, const float* score2, int ld2, int b,
                      const AssignGeom& g, const AssignWs& ws, float* w1, float* w2, cudaStream_t st) {
   const FineGeom2 f = fine_geom2(g.R, g.C);
   const dim3 grid(f.nstrip, f.nrt, b);
   const dim3 mg(ceil_div(g.R + g.C, 256), b);
+  const bool vec = fine_vec_ok(atten, ld);
   UPK_CUDA_TRY(cudaMemsetAsync(ws.flags, 0, sizeof(int) * (size_t)b, st));
-  k_fine_stats<<<grid, F2_THREADS, 0, st>>>(atten, g.R, g.C, f.nstrip, f.nrt, ws.rowpart, ws.colpart, ws.flags);
-  k_fine_stats_merge<<<mg, 256, 0, st>>>(atten, ws.rowpart, ws.colpart, g.R, g.C, f.nstrip, f.nrt, score1, ld1,
+  if (vec) k_fine_stats<true><<<grid, F2_THREADS, 0, st>>>(atten, g.R, g.C, ld, f.nstrip, f.nrt, ws.rowpart, ws.colpart, ws.flags);
+  else k_fine_stats<false><<<grid, F2_THREADS, 0, st>>>(atten, g.R, g.C, ld, f.nstrip, f.nrt, ws.rowpart, ws.colpart, ws.flags);
+  k_fine_stats_merge<<<mg, 256, 0, st>>>(atten, ws.rowpart, ws.colpart, g.R, g.C, ld, f.nstrip, f.nrt, score1, ld1,
                                          score2, ld2, ws.flags, ws.rmax, ws.rsum, ws.cmax, ws.csum);
-  k_fine_labels<<<grid, F2_THREADS, 0, st>>>(atten, g.R, g.C, f.nstrip, f.nrt, ws.rmax, ws.rsum, ws.cmax, ws.csum,
-                                             ws.rowpm, ws.colpm, ws.ai0, ws.a0j);
+  if (vec) k_fine_labels<true><<<grid, F2_THREADS, 0, st>>>(atten, g.R, g.C, ld, f.nstrip, f.nrt, ws.rmax, ws.rsum, ws.cmax, ws.csum,
+                                                            ws.rowpm, ws.colpm, ws.ai0, ws.a0j, 0);
+  else k_fine_labels<false><<<grid, F2_THREADS, 0, st>>>(atten, g.R, g.C, ld, f.nstrip, f.nrt, ws.rmax, ws.rsum, ws.cmax, ws.csum,
+                                                             ws.rowpm, ws.colpm, ws.ai0, ws.a0j, 0);
   count_launch(3);
   return launch_labels_merge(ws.rowpm, ws.colpm, ws.ai0, ws.a0j, b, g.R, g.C, f.nrt, f.nstrip, w1, w2, st);
 }
 
-int run_fine_labels2_fused(const float* atten, const float* stats, float temp, const float* score1, int ld1,
+int run_fine_labels2_fused(const float* atten, int ld, const float* stats, float temp, const float* score1, int ld1,
                            const float* score2, int ld2, int b, const AssignGeom& g, const AssignWs& ws, float* w1,
                            float* w2, cudaStream_t st) {
   const FineGeom2 f = fine_geom2(g.R, g.C);
   const SimStatsGeom sg = sim_stats_geom(b, g.R, g.C);
   const float gref = sim_stats_gref(temp);
   const dim3 grid(f.nstrip, f.nrt, b);
-  const dim3 mg(ceil_div(g.R + g.C, 256), b);
-  k_fine_border_sums<<<b, 256, 0, st>>>(atten, g.R, g.C, gref, ws.bsum);
-  k_fine_stats_merge_fused<<<mg, 256, 0, st>>>(atten, stats, stats + sg.col_off_floats, sg.npr, sg.npc, gref, ws.bsum,
-                                               g.R, g.C, score1, ld1, score2, ld2, ws.rmax, ws.rsum, ws.cmax, ws.csum);
-  k_fine_labels<<<grid, F2_THREADS, 0, st>>>(atten, g.R, g.C, f.nstrip, f.nrt, ws.rmax, ws.rsum, ws.cmax, ws.csum,
-                                             ws.rowpm, ws.colpm, ws.ai0, ws.a0j);
-  count_launch(3);
+  const int nmerge = ceil_div(g.R + g.C, 256);
+  const dim3 mg(nmerge + 1, b);
+  k_fine_stats_merge_fused<<<mg, 256, 0, st>>>(atten, stats, stats + sg.col_off_floats, sg.npr, sg.npc, gref, nmerge,
+                                               g.R, g.C, ld, score1, ld1, score2, ld2, ws.rmax, ws.rsum, ws.cmax, ws.csum);
+  // the GEMM wrote the instances in ascending order: start the labels pass on the last ones (still in L2)
+  if (fine_vec_ok(atten, ld))
+    k_fine_labels<true><<<grid, F2_THREADS, 0, st>>>(atten, g.R, g.C, ld, f.nstrip, f.nrt, ws.rmax, ws.rsum, ws.cmax, ws.csum,
+                                                     ws.rowpm, ws.colpm, ws.ai0, ws.a0j, 1);
+  else
+    k_fine_labels<false><<<grid, F2_THREADS, 0, st>>>(atten, g.R, g.C, ld, f.nstrip, f.nrt, ws.rmax, ws.rsum, ws.cmax, ws.csum,
+                                                      ws.rowpm, ws.colpm, ws.ai0, ws.a0j, 1);
+  count_launch(2);
   return launch_labels_merge(ws.rowpm, ws.colpm, ws.ai0, ws.a0j, b, g.R, g.C, f.nrt, f.nstrip, w1, w2, st);
 }
 
-int run_fine_rows2(const float* atten, int b, const AssignGeom& g, const AssignWs& ws, const float* w1,
+int run_fine_rows2(const float* atten, int ld, int b, const AssignGeom& g, const AssignWs& ws, const float* w1,
                    const float* w2, const float* pts2, float4* rowpart4, float* soft, float* asum, cudaStream_t st) {
   const FineGeom2 f = fine_geom2(g.R, g.C);
   const dim3 grid(f.nstrip, f.nrt, b);
-  k_fine_rows<<<grid, F2_THREADS, 0, st>>>(atten, g.R, g.C, f.nstrip, ws.rmax, ws.rsum, ws.cmax, ws.csum, w2, pts2,
-                                           rowpart4);
+  if (fine_vec_ok(atten, ld))
+    k_fine_rows<true><<<grid, F2_THREADS, 0, st>>>(atten, g.R, g.C, ld, f.nstrip, ws.rmax, ws.rsum, ws.cmax, ws.csum, w2, pts2,
+                                                   rowpart4);
+  else
+    k_fine_rows<false><<<grid, F2_THREADS, 0, st>>>(atten, g.R, g.C, ld, f.nstrip, ws.rmax, ws.rsum, ws.cmax, ws.csum, w2, pts2,
+                                                    rowpart4);
   count_launch();
   return launch_fine_rows_merge(rowpart4, w1, b, g.R - 1, f.nstrip, soft, asum, st);
 }

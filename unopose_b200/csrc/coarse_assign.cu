@@ -42,7 +42,7 @@ namespace cg = cooperative_groups;
 namespace upk {
 
 constexpr int CA_CL = 8;          // CTAs per instance (portable cluster size)
-constexpr int CA_THREADS = 1024;
+constexpr int CA_THREADS = 512;       // 2 CTAs per SM (64 registers, < 113 KB smem): all 16 clusters of a batch resident at once
 constexpr int CA_WARPS = CA_THREADS / 32;
 constexpr int CA_RVS = 12;        // floats per block in the carry exchange (x_0, r_1 .. r_(lx+1) with lx <= 9)
 constexpr int CA_MAX_BLOCKS = 256;
@@ -87,7 +87,7 @@ __device__ __forceinline__ int ca_next_pow2(int v) {
   return p;
 }
 
-__global__ void __cluster_dims__(CA_CL, 1, 1) __launch_bounds__(CA_THREADS)
+__global__ void __cluster_dims__(CA_CL, 1, 1) __launch_bounds__(CA_THREADS, 2)
 k_coarse_assign_exact(const float* __restrict__ atten, const float* __restrict__ score1, int ld1,
                       const float* __restrict__ score2, int ld2, int R, int C, int rpc, int cpc, int lx,
                       int main_floats, float* __restrict__ w1_out, float* __restrict__ w2_out,

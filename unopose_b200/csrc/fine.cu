@@ -229,7 +229,7 @@ int upk_weighted_procrustes(const float* src, const float* ref, const float* wei
   UPK_RETURN_LAST_ERROR();
 }
 
-static int fine_pose_impl(const float* atten, const float* stats, size_t stats_bytes, float temp,
+static int fine_pose_impl(const float* atten, int atten_ld, const float* stats, size_t stats_bytes, float temp,
                           const float* score1, int score1_ld, const float* score2, int score2_ld,
                           const float* pts1, const float* pts2, const float* model_pts, int n_model, int b, int n1,
                           int n2, float dis_thres, float weight_thresh, void* workspace, size_t workspace_bytes,
@@ -246,16 +246,18 @@ static int fine_pose_impl(const float* atten, const float* stats, size_t stats_b
   carve_fine(cv, b, n1, n2, g, w);
   if (cv.bytes() > workspace_bytes) return UPK_ERR_INVALID_ARG;
   if (!model_pts) { model_pts = pts2; n_model = n2; }
+  const int ld = atten_ld > 0 ? atten_ld : n2 + 1;
+  if (ld < n2 + 1) return UPK_ERR_INVALID_ARG;
   int rc;
   if (stats) {   // pass 1 came out of the similarity GEMM's epilogue (upk_feature_similarity_stats)
     if (g.TR == 32 || stats_bytes < sim_stats_geom(b, n1 + 1, n2 + 1).total_bytes || !(temp > 0.f)) return UPK_ERR_INVALID_ARG;
-    rc = run_fine_labels2_fused(atten, stats, temp, score1, score1_ld, score2, score2_ld, b, g, w.a, w.w1, w.w2, st);
+    rc = run_fine_labels2_fused(atten, ld, stats, temp, score1, score1_ld, score2, score2_ld, b, g, w.a, w.w1, w.w2, st);
   } else {
-    rc = run_assignment_labels(atten, score1, score1_ld, score2, score2_ld, b, g, w.a, w.w1, w.w2, st, true);
+    rc = run_assignment_labels(atten, score1, score1_ld, score2, score2_ld, b, g, w.a, w.w1, w.w2, st, true, ld);
   }
   if (rc) return rc;
   if ((rc = run_fine_rowsums(atten, score1, score1_ld, score2, score2_ld, b, g, w.a, w.w1, w.w2, pts2,
-                             w.rowpart4, w.soft, w.asum, st)))
+                             w.rowpart4, w.soft, w.asum, st, ld)))
     return rc;
   k_weighted_kabsch<<<b, FK_THREADS, 0, st>>>(w.soft, pts1, w.asum, n1, weight_thresh, 1e-5f, R_out, t_out);
   UPK_CUDA_TRY(cudaMemsetAsync(w.counters, 0, sizeof(int) * 3 * (size_t)b, st));
@@ -276,7 +278,7 @@ int upk_fine_pose(const float* atten, const float* score1, int score1_ld, const 
                   const float* pts1, const float* pts2, const float* model_pts, int n_model, int b, int n1,
                   int n2, float dis_thres, float weight_thresh, void* workspace, size_t workspace_bytes,
                   float* R_out, float* t_out, float* score_out, const upk_fine_debug* dbg, upk_stream_t stream) {
-  return fine_pose_impl(atten, nullptr, 0, 0.f, score1, score1_ld, score2, score2_ld, pts1, pts2, model_pts, n_model,
+  return fine_pose_impl(atten, 0, nullptr, 0, 0.f, score1, score1_ld, score2, score2_ld, pts1, pts2, model_pts, n_model,
                         b, n1, n2, dis_thres, weight_thresh, workspace, workspace_bytes, R_out, t_out, score_out, dbg,
                         stream);
 }
@@ -288,8 +290,20 @@ int upk_fine_pose_stats(const float* atten, const float* stats, size_t stats_byt
                         float* R_out, float* t_out, float* score_out, const upk_fine_debug* dbg,
                         upk_stream_t stream) {
   if (!stats) return UPK_ERR_INVALID_ARG;
-  return fine_pose_impl(atten, stats, stats_bytes, temp, score1, score1_ld, score2, score2_ld, pts1, pts2, model_pts,
+  return fine_pose_impl(atten, 0, stats, stats_bytes, temp, score1, score1_ld, score2, score2_ld, pts1, pts2, model_pts,
                         n_model, b, n1, n2, dis_thres, weight_thresh, workspace, workspace_bytes, R_out, t_out,
+                        score_out, dbg, stream);
+}
+
+int upk_fine_pose_ld(const float* atten, int atten_ld, const float* stats, size_t stats_bytes, float temp,
+                     const float* score1, int score1_ld, const float* score2, int score2_ld,
+                     const float* pts1, const float* pts2, const float* model_pts, int n_model, int b, int n1,
+                     int n2, float dis_thres, float weight_thresh, void* workspace, size_t workspace_bytes,
+                     float* R_out, float* t_out, float* score_out, const upk_fine_debug* dbg,
+                     upk_stream_t stream) {
+  if (atten_ld < n2 + 1) return UPK_ERR_INVALID_ARG;
+  return fine_pose_impl(atten, atten_ld, stats, stats_bytes, temp, score1, score1_ld, score2, score2_ld, pts1, pts2,
+                        model_pts, n_model, b, n1, n2, dis_thres, weight_thresh, workspace, workspace_bytes, R_out, t_out,
                         score_out, dbg, stream);
 }
 

@@ -51,9 +51,11 @@ void carve_assign(Carver& cv, int b, const AssignGeom& g, AssignWs& ws);
 // for_fine_solve = false (the coarse solver): natural-log maxima / sums from the exact tile pipeline, which is what
 // run_coarse_P consumes.  for_fine_solve = true on a large geometry: the streaming passes of assign_fine.cu, which
 // leave log2-domain constants (rml, rmul, cml, cmul) in the same buffers for run_fine_rowsums.
+// atten_ld: row pitch of atten in floats (== g.C for a contiguous tensor; only the large-geometry fine passes accept
+// a pitched one, UPK_ERR_UNSUPPORTED otherwise).
 int run_assignment_labels(const float* atten, const float* score1, int ld1, const float* score2, int ld2,
                           int b, const AssignGeom& g, const AssignWs& ws, float* w1, float* w2,
-                          cudaStream_t st, bool for_fine_solve = false);
+                          cudaStream_t st, bool for_fine_solve = false, int atten_ld = 0);
 
 // coarse_assign.cu: masks + sampling CDF in one cluster kernel, bit-exact with the ATen CUDA kernels of the reference's
 // GPU path.  UPK_ERR_UNSUPPORTED for geometries it does not handle (-> the tile pipeline below).
@@ -71,7 +73,7 @@ int run_cdf(const float* pmat, const double* prow, int b, int n1, int n2, int nt
 int run_fine_rowsums(const float* atten, const float* score1, int ld1, const float* score2, int ld2, int b,
                      const AssignGeom& g, const AssignWs& ws, const float* w1, const float* w2,
                      const float* pts2, float4* rowpart4 /*[b][N1][ntc]*/, float* soft, float* asum,
-                     cudaStream_t st);
+                     cudaStream_t st, int atten_ld = 0);
 
 // Large-geometry (fine) streaming passes, assign_fine.cu.  They reuse the AssignWs buffers: rmax/rsum/cmax/csum
 // hold rml (row reference, log2 units) / rmul (score1 / row sum) / cml / cmul there.
@@ -79,9 +81,9 @@ struct FineGeom2 {
   int nstrip, nrt;  // 256-column strips / 128-row tiles of the main block (background row and column peeled off)
 };
 FineGeom2 fine_geom2(int R, int C);
-int run_fine_labels2(const float* atten, const float* score1, int ld1, const float* score2, int ld2, int b,
+int run_fine_labels2(const float* atten, int ld, const float* score1, int ld1, const float* score2, int ld2, int b,
                      const AssignGeom& g, const AssignWs& ws, float* w1, float* w2, cudaStream_t st);
-int run_fine_rows2(const float* atten, int b, const AssignGeom& g, const AssignWs& ws, const float* w1,
+int run_fine_rows2(const float* atten, int ld, int b, const AssignGeom& g, const AssignWs& ws, const float* w1,
                    const float* w2, const float* pts2, float4* rowpart4, float* soft, float* asum, cudaStream_t st);
 // helpers living in assign.cu
 int launch_labels_merge(const float* rowpm, const float* colpm, const float* ai0, const float* a0j, int b, int R,
@@ -93,9 +95,11 @@ int launch_fine_rows_merge(const float4* rowpart4, const float* w1, int b, int n
 int similarity_mode();  // 16 = 3xFP16/3xTF32 tcgen05 (default), 3 = 3xTF32, 1 = 1xTF32 tcgen05, 0 = fp32 SIMT
 bool similarity_tc_eligible(int n, int m, int c);
 size_t similarity_tc_workspace_bytes(int b, int n, int m, int c);
+// ldc: row pitch of `out` in floats (0 = contiguous, m).  With ldc % 4 == 0 and element (1, 1) 16-byte aligned the
+// CTA-pair kernel stores its tiles with TMA.
 int run_similarity_tc(const float* f1, const float* f2, int b, int n, int m, int c, float temp, int normalize,
                       int sim_type, void* workspace, size_t workspace_bytes, float* out, cudaStream_t st,
-                      float* stats_row = nullptr, float* stats_col = nullptr, float stats_gref = 0.f);
+                      float* stats_row = nullptr, float* stats_col = nullptr, float stats_gref = 0.f, int ldc = 0);
 
 // TMA descriptor of a (batch, rows, K) fp32 K-major operand, boxes of TC_BK x box_rows, SWIZZLE_64B
 // (`map` is a CUtensorMap*; UPK_ERR_UNSUPPORTED if the driver entry point is unavailable)
@@ -112,7 +116,7 @@ struct SimStatsGeom {
 };
 SimStatsGeom sim_stats_geom(int b, int n, int m);
 float sim_stats_gref(float temp);
-int run_fine_labels2_fused(const float* atten, const float* stats, float temp, const float* score1, int ld1,
+int run_fine_labels2_fused(const float* atten, int ld, const float* stats, float temp, const float* score1, int ld1,
                            const float* score2, int ld2, int b, const AssignGeom& g, const AssignWs& ws, float* w1,
                            float* w2, cudaStream_t st);
 

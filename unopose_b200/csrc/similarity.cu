@@ -178,6 +178,7 @@ int upk_feature_similarity_stats(const float* feat1, const float* feat2, int b, 
   const bool aligned16 = ((reinterpret_cast<uintptr_t>(feat1) | reinterpret_cast<uintptr_t>(feat2)) & 15) == 0;
   if (!similarity_tc_eligible(n, m, c) || (similarity_mode() != 3 && similarity_mode() != 16) || !aligned16)
     return UPK_ERR_UNSUPPORTED;
+  if (2.0f * 1.4426950408889634f / temp > 60.f) return UPK_ERR_UNSUPPORTED;   // exponent sums would underflow (see _ld)
   const SimStatsGeom sg = sim_stats_geom(b, n, m);
   if (!stats_out || stats_bytes < sg.total_bytes || !workspace ||
       workspace_bytes < similarity_tc_workspace_bytes(b, n, m, c))
@@ -186,6 +187,31 @@ int upk_feature_similarity_stats(const float* feat1, const float* feat2, int b, 
   UPK_CUDA_TRY(cudaMemsetAsync(stats_out, 0, sg.total_bytes, st));   // partials of ragged last tiles stay 0
   return run_similarity_tc(feat1, feat2, b, n, m, c, temp, /*normalize=*/1, /*cosine*/0, workspace, workspace_bytes,
                            atten_out, st, stats_out, stats_out + sg.col_off_floats, sim_stats_gref(temp));
+}
+
+int upk_feature_similarity_stats_ld(const float* feat1, const float* feat2, int b, int n, int m, int c, float temp,
+                                    void* workspace, size_t workspace_bytes, float* atten_out, int atten_ld,
+                                    float* stats_out, size_t stats_bytes, upk_stream_t stream) {
+  if (b < 0 || n <= 1 || m <= 1 || c <= 0 || !(temp > 0.f) || atten_ld < m) return UPK_ERR_INVALID_ARG;
+  if (b == 0) return UPK_OK;
+  const bool aligned16 = ((reinterpret_cast<uintptr_t>(feat1) | reinterpret_cast<uintptr_t>(feat2)) & 15) == 0;
+  if (!similarity_tc_eligible(n, m, c) || (similarity_mode() != 3 && similarity_mode() != 16) || !aligned16)
+    return UPK_ERR_UNSUPPORTED;
+  if (!atten_out || !workspace || workspace_bytes < similarity_tc_workspace_bytes(b, n, m, c)) return UPK_ERR_INVALID_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  float *srow = nullptr, *scol = nullptr;
+  if (stats_out) {
+    // one fixed reference exponent carries every exponent sum only while 2^(-2 log2e / temp) stays representable:
+    // below temp ~ 0.03 the sums flush to zero -> the caller takes the exact three-pass path
+    if (2.0f * 1.4426950408889634f / temp > 60.f) return UPK_ERR_UNSUPPORTED;
+    const SimStatsGeom sg = sim_stats_geom(b, n, m);
+    if (stats_bytes < sg.total_bytes) return UPK_ERR_INVALID_ARG;
+    UPK_CUDA_TRY(cudaMemsetAsync(stats_out, 0, sg.total_bytes, st));   // partials of ragged last tiles stay 0
+    srow = stats_out;
+    scol = stats_out + sg.col_off_floats;
+  }
+  return run_similarity_tc(feat1, feat2, b, n, m, c, temp, /*normalize=*/1, /*cosine*/0, workspace, workspace_bytes,
+                           atten_out, st, srow, scol, stats_out ? sim_stats_gref(temp) : 0.f, atten_ld);
 }
 
 }  // extern "C"

@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256)
 k_normalize_split(const float* __restrict__ x, int rows_per_batch, int c, int normalize,
                   float* __restrict__ hi, float* __restrict__ lo,
                   const float* __restrict__ other, int other_rows_per_batch, int is_a,
-                  float temp, float* __restrict__ C, int M, int N) {
+                  float temp, float* __restrict__ C, int M, int N, int ldc) {
   extern __shared__ float s_q[];   // BORDER: the normalised row 0 of the other operand (c floats)
   const int bidx = blockIdx.y;
   const int lane = threadIdx.x & 31;
@@ -159,7 +159,7 @@ k_normalize_split(const float* __restrict__ x, int rows_per_batch, int c, int no
     dot = warp_sum(dot);
     if (MODE == 1) dot = sqrtf(fmaxf(2.0f - 2.0f * dot, 0.f));
     if (lane == 0) {
-      float* o = is_a ? C + ((size_t)bidx * M + r) * N : C + (size_t)bidx * M * N + r;
+      float* o = is_a ? C + ((size_t)bidx * M + r) * ldc : C + (size_t)bidx * M * ldc + r;
       if (is_a || r > 0) *o = dot * (1.0f / temp);   // C[0][0] is written once, by the first operand's row 0
     }
   }
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 k_similarity_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                 int batch, int M, int N, int K, float temp, int off, float* __restrict__ C,
-                float* __restrict__ rowpart, float* __restrict__ colpart, float gref) {
+                float* __restrict__ rowpart, float* __restrict__ colpart, float gref, int ldc) {
   // `off` (0 or 1): the tiles cover rows/columns [off, M) x [off, N); with off = 1 the background row 0 and
   // column 0 are produced by k_normalize_split (BORDER), so the 2049 x 2049 fine shape is exactly 16 x 8 tiles
   extern __shared__ unsigned char smem_raw[];
@@ -280,7 +280,7 @@ k_similarity_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
       tc_fence_after();
       const int row0 = off + mi * TC_BM + q * 32;
       const int nrows = min(32, M - row0);
-      float* Cb = C + ((size_t)b * M + row0) * N;
+      float* Cb = C + ((size_t)b * M + row0) * ldc;
       float rsum = 0.f;   // STATS: this thread's row (row0 + lane), its 128 columns of the tile
 #pragma unroll 1
       for (int cb = half * 4; cb < half * 4 + 4; ++cb) {
@@ -309,7 +309,7 @@ k_similarity_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 #pragma unroll
             for (int rr = 0; rr < 32; ++rr) {
               const float v = src[rr * 33];
-              dst[(size_t)rr * N] = v;
+              dst[(size_t)rr * ldc] = v;
               if (STATS) {
                 float e;
                 asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(v, 1.4426950408889634f, -gref)));
@@ -319,7 +319,7 @@ k_similarity_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
           } else {
             for (int rr = 0; rr < nrows; ++rr) {
               const float v = src[rr * 33];
-              dst[(size_t)rr * N] = v;
+              dst[(size_t)rr * ldc] = v;
               if (STATS) {
                 float e;
                 asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(v, 1.4426950408889634f, -gref)));
@@ -353,22 +353,36 @@ k_similarity_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 // expect_tx for BOTH CTAs' bytes and both producers' TMA loads (.cta_group::2) complete on it; the leader's MMA
 // warp releases smem stages and publishes accumulators with multicast commits to both CTAs; both CTAs' epilogue
 // warps arrive on the leader's `tempty`.  cosine logits, 3xTF32 only.
-constexpr int TC2_STAGES = 5;                      // 32 KB per stage and CTA
 constexpr int TC2_EPI_WARPS = 8;                   // EPI/4 warps per TMEM lane quarter, 256/(EPI/4) columns each (measured: 4 -> 166 us, 8 -> 146 us, 16 -> 160 us)
 constexpr int TC2_CPW = 32 / TC2_EPI_WARPS;        // 32-column chunks per epilogue warp and tile
 constexpr int TC2_THREADS = 64 + TC2_EPI_WARPS * 32;
 constexpr uint32_t TC2_STAGE_BYTES = 4 * TC_BM * TC_BK * 4;   // A_hi, A_lo, Bhalf_hi, Bhalf_lo: 4 x 8 KB
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;     // shared::cluster address of the same offset in CTA 0 of the pair
 
+// TMAST = false: 5 operand stages of 32 KB + a padded 32x33 transpose buffer per epilogue warp (4-byte row stores).
+// TMAST = true : 4 operand stages + two 4 KB TMA-store staging boxes per epilogue warp (32 rows x 128 B, SWIZZLE_128B).
+template <bool TMAST>
 struct __align__(1024) Tc2Smem {
-  float a_hi[TC2_STAGES][TC_BM * TC_BK];
-  float a_lo[TC2_STAGES][TC_BM * TC_BK];
-  float b_hi[TC2_STAGES][TC_BM * TC_BK];   // this CTA's half (128 rows) of the 256-row B tile
-  float b_lo[TC2_STAGES][TC_BM * TC_BK];
-  float epi[TC2_EPI_WARPS][32][33];
-  unsigned long long full[TC2_STAGES], empty[TC2_STAGES], tfull[2], tempty[2];
+  static constexpr int STAGES = TMAST ? 4 : 5;
+  static constexpr int EPI_FLOATS = TMAST ? 2 * 32 * 32 : 32 * 33;
+  float a_hi[STAGES][TC_BM * TC_BK];
+  float a_lo[STAGES][TC_BM * TC_BK];
+  float b_hi[STAGES][TC_BM * TC_BK];   // this CTA's half (128 rows) of the 256-row B tile
+  float b_lo[STAGES][TC_BM * TC_BK];
+  float epi[TC2_EPI_WARPS][EPI_FLOATS];   // TMAST: 8 KB per warp, every 4 KB box 1024-byte aligned
+  unsigned long long full[STAGES], empty[STAGES], tfull[2], tempty[2];
   uint32_t tmem_base;
 };
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"((unsigned long long)map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ void tma_load_3d_2sm(const CUtensorMap* map, void* bar, void* dst, int c0, int c1, int c2) {
   asm volatile(
@@ -412,14 +426,22 @@ constexpr uint32_t kIdescF16_2sm = kIdescF16Base | ((uint32_t)(TC_BN >> 3) << 17
 
 // F16: the operands are fp16 (k_normalize_split<.., true>): a 64-byte stage row holds 32 K elements instead of 16, one
 // tcgen05.mma.kind::f16 covers K = 16; the accumulator carries the 2^24 scale of the two operands.
-template <bool STATS, bool F16 = false>
+// TMAST: the output is pitched so that element (1, 1) of every instance is 16-byte aligned and ldc % 4 == 0 (the padded
+// layout compute_feature_similarity hands out for the fine shape): an epilogue warp then writes its 32 x 32 chunk into a
+// SWIZZLE_128B staging box (8 conflict-free STS.128 per lane) and ONE elected lane issues a TMA tensor store
+// (cp.async.bulk.tensor, clipped at the ragged edges by the hardware) instead of 32 row-segment store instructions per
+// lane — the 4-byte-aligned row stores were what held the kernel below the MMA rate (profiles/r1_latency_microbench.txt).
+template <bool STATS, bool F16 = false, bool TMAST = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
 k_similarity_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                  const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-                 int batch, int M, int N, int K, float temp, int off, float* __restrict__ C,
+                 const __grid_constant__ CUtensorMap map_c,
+                 int batch, int M, int N, int K, float temp, int off, float* __restrict__ C, int ldc,
                  float* __restrict__ rowpart, float* __restrict__ colpart, float gref) {
   extern __shared__ unsigned char smem_raw[];
-  Tc2Smem& sm = *reinterpret_cast<Tc2Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  typedef Tc2Smem<TMAST> Smem;
+  constexpr int TC2_STAGES = Smem::STAGES;
+  Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint32_t rank;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
@@ -512,9 +534,10 @@ k_similarity_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     // ===== epilogue warps (both CTAs; this CTA's 128 rows of the 256-row tile) =====
     const int q = warp & 3;
     const int cq = (warp - 2) >> 2;          // column slice of the tile handled by this warp
-    float* tr = &sm.epi[warp - 2][0][0];
+    float* tr = &sm.epi[warp - 2][0];
     const float inv_temp = F16 ? 1.0f / (temp * kF16Scale * kF16Scale) : 1.0f / temp;
     int it = 0;
+    int cc = 0;   // TMAST: chunks stored so far by this warp (staging box = cc & 1)
     for (int t = cid; t < total; t += ncl, ++it) {
       const int b = t / (mt2 * nt), rem = t - b * mt2 * nt;
       const int mi2 = rem / nt, ni = rem - mi2 * nt;
@@ -525,7 +548,7 @@ k_similarity_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       tc_fence_after();
       const int row0 = off + mi * TC_BM + q * 32;
       const int nrows = min(32, M - row0);
-      float* Cb = C + ((size_t)b * M + row0) * N;
+      float* Cb = C + ((size_t)b * M + row0) * ldc;
       float rsum = 0.f;
 #pragma unroll 1
       for (int cb = cq * TC2_CPW; cb < cq * TC2_CPW + TC2_CPW; ++cb) {
@@ -533,6 +556,48 @@ k_similarity_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         if (col0 >= N) break;
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + acc * TC_BN + cb * 32 + ((uint32_t)(q * 32) << 16), r);
+        if (TMAST) {
+          float* box = tr + ((cc & 1) << 10);
+          if (lane == 0) bulk_wait_read<1>();   // the store issued from this box two chunks ago has read it
+          __syncwarp();
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            float4 v;
+            v.x = __uint_as_float(r[4 * c4]) * inv_temp;
+            v.y = __uint_as_float(r[4 * c4 + 1]) * inv_temp;
+            v.z = __uint_as_float(r[4 * c4 + 2]) * inv_temp;
+            v.w = __uint_as_float(r[4 * c4 + 3]) * inv_temp;
+            if (STATS) {
+              const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+              for (int e4 = 0; e4 < 4; ++e4) {
+                float e;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(vv[e4], 1.4426950408889634f, -gref)));
+                rsum += (col0 + 4 * c4 + e4 < N) ? e : 0.f;
+              }
+            }
+            // row `lane` of the box (128 B), 16-byte chunk c4 at position c4 ^ (row & 7): the SWIZZLE_128B pattern
+            *reinterpret_cast<float4*>(box + lane * 32 + ((c4 ^ (lane & 7)) << 2)) = v;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&map_c, box, col0 - off, row0 - off, b);
+            bulk_commit();
+          }
+          if (STATS && col0 + lane < N && nrows > 0) {
+            // column col0 + lane of the 32 rows: word (lane & 3) of chunk (lane >> 2) ^ (rr & 7) of row rr
+            float csum = 0.f;
+            for (int rr = 0; rr < nrows; ++rr) {
+              const float v = box[rr * 32 + ((((lane >> 2) ^ (rr & 7)) << 2) | (lane & 3))];
+              float e;
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(v, 1.4426950408889634f, -gref)));
+              csum += e;
+            }
+            colpart[((size_t)b * (4 * mt) + 4 * mi + q) * N + col0 + lane] = csum;
+          }
+          ++cc;
+        } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const float v = __uint_as_float(r[j]) * inv_temp;
@@ -550,7 +615,7 @@ k_similarity_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           float csum = 0.f;
           for (int rr = 0; rr < nrows; ++rr) {
             const float v = src[rr * 33];
-            dst[(size_t)rr * N] = v;
+            dst[(size_t)rr * ldc] = v;
             if (STATS) {
               float e;
               asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(v, 1.4426950408889634f, -gref)));
@@ -560,11 +625,13 @@ k_similarity_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           if (STATS) colpart[((size_t)b * (4 * mt) + 4 * mi + q) * N + col0 + lane] = csum;
         }
         __syncwarp();
+        }
       }
       if (STATS && lane < nrows) rowpart[((size_t)b * (4 * nt) + 4 * ni + cq * (16 / TC2_EPI_WARPS)) * M + row0 + lane] = rsum;
       tc_fence_before();
       if (lane == 0) mbar_arrive_leader(&sm.tempty[acc]);
     }
+    if (TMAST && lane == 0) bulk_wait_all();   // every tensor store of this warp has completed
   }
   tc_fence_before();
   __syncthreads();
@@ -620,6 +687,27 @@ static int make_map(CUtensorMap* map, const float* base, int batch, int rows, in
   return r == CUDA_SUCCESS ? UPK_OK : UPK_ERR_INVALID_ARG;
 }
 
+// fp32 output tiles for the TMA-store epilogue: the main block [1, n) x [1, m) of every instance, row pitch ldc floats,
+// boxes of 32 x 32 with SWIZZLE_128B (128-byte box rows).  `c11` = address of element (1, 1) of instance 0.
+static int make_map_out(CUtensorMap* map, float* c11, int batch, int n, int m, int ldc) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return UPK_ERR_UNSUPPORTED;
+  cuuint64_t dims[3] = {(cuuint64_t)(m - 1), (cuuint64_t)(n - 1), (cuuint64_t)batch};
+  cuuint64_t strides[2] = {(cuuint64_t)ldc * 4, (cuuint64_t)n * ldc * 4};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)c11, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? UPK_OK : UPK_ERR_INVALID_ARG;
+}
+
+static bool tma_store_ok(const float* out, int n, int m, int ldc) {
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("UPK_TC_TMA_STORE"); enabled = e ? atoi(e) : 1; }
+  return enabled && n > 1 && m > 1 && ldc % 4 == 0 && ((reinterpret_cast<uintptr_t>(out + ldc + 1)) & 15) == 0;
+}
+
 // the same encoder for the other tensor-core translation units (geoembed.cu); `map` is a CUtensorMap*
 int tc_make_map(void* map, const float* base, int batch, int rows, int K, int box_rows) {
   return make_map((CUtensorMap*)map, base, batch, rows, K, box_rows);
@@ -669,8 +757,8 @@ bool similarity_tc_eligible(int n, int m, int c) {
 // fp16 for |x| >= 16.  Returns 1 if the call is not handled here (the caller continues with the 3xTF32 path), else a
 // launch status.
 static int run_similarity_f16(const float* f1, const float* f2, int b, int n, int m, int c, float temp, int normalize,
-                              int sim_type, void* a_hi, void* a_lo, void* b_hi, void* b_lo, float* out, cudaStream_t st,
-                              float* stats_row, float* stats_col, float stats_gref) {
+                              int sim_type, void* a_hi, void* a_lo, void* b_hi, void* b_lo, float* out, int ldc,
+                              cudaStream_t st, float* stats_row, float* stats_col, float stats_gref) {
   const char* e = getenv("UPK_TC_2SM");
   if (e && atoi(e) == 0) return 1;
   if (sim_type != 0 || !normalize || n <= 1 || m <= 1 || c % (2 * TC_BK) != 0) return 1;
@@ -683,8 +771,8 @@ static int run_similarity_f16(const float* f1, const float* f2, int b, int n, in
   if (stats_row && !stats_col) return UPK_ERR_UNSUPPORTED;
   const dim3 g1((n + 8 * NS_RPW - 1) / (8 * NS_RPW), b), g2((m + 8 * NS_RPW - 1) / (8 * NS_RPW), b);
   const size_t qs = (size_t)c * sizeof(float);
-  k_normalize_split<0, true><<<g1, 256, qs, st>>>(f1, n, c, normalize, (float*)a_hi, (float*)a_lo, f2, m, 1, temp, out, n, m);
-  k_normalize_split<0, true><<<g2, 256, qs, st>>>(f2, m, c, normalize, (float*)b_hi, (float*)b_lo, f1, n, 0, temp, out, n, m);
+  k_normalize_split<0, true><<<g1, 256, qs, st>>>(f1, n, c, normalize, (float*)a_hi, (float*)a_lo, f2, m, 1, temp, out, n, m, ldc);
+  k_normalize_split<0, true><<<g2, 256, qs, st>>>(f2, m, c, normalize, (float*)b_hi, (float*)b_lo, f1, n, 0, temp, out, n, m, ldc);
   count_launch(2);
   CUtensorMap fa_hi, fa_lo, fb_hi, fb_lo;
   int rc;
@@ -693,16 +781,24 @@ static int run_similarity_f16(const float* f1, const float* f2, int b, int n, in
   if ((rc = make_map_f16(&fb_hi, b_hi, b, m, c, TC_BM))) return rc;
   if ((rc = make_map_f16(&fb_lo, b_lo, b, m, c, TC_BM))) return rc;
   const int grid2 = 2 * (tiles2 < sms / 2 ? tiles2 : sms / 2);
-  const size_t smem2 = sizeof(Tc2Smem) + 1024;
-  if (stats_row) {
-    UPK_CUDA_TRY(cudaFuncSetAttribute(k_similarity_tc2<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-    k_similarity_tc2<true, true><<<grid2, TC2_THREADS, smem2, st>>>(fa_hi, fa_lo, fb_hi, fb_lo, b, n, m, c, temp, off, out,
-                                                                  stats_row, stats_col, stats_gref);
+  CUtensorMap mc;
+  const bool tmast = tma_store_ok(out, n, m, ldc);
+  if (tmast) {
+    if ((rc = make_map_out(&mc, out + ldc + 1, b, n, m, ldc))) return rc;
   } else {
-    UPK_CUDA_TRY(cudaFuncSetAttribute(k_similarity_tc2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-    k_similarity_tc2<false, true><<<grid2, TC2_THREADS, smem2, st>>>(fa_hi, fa_lo, fb_hi, fb_lo, b, n, m, c, temp, off, out,
-                                                                   nullptr, nullptr, 0.f);
+    mc = fa_hi;   // unused by the kernel
   }
+#define UPK_LAUNCH_TC2(ST, TM)                                                                                       \
+  do {                                                                                                               \
+    auto kern = k_similarity_tc2<ST, true, TM>;                                                                      \
+    const size_t smem2 = sizeof(Tc2Smem<TM>) + 1024;                                                                 \
+    UPK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));              \
+    kern<<<grid2, TC2_THREADS, smem2, st>>>(fa_hi, fa_lo, fb_hi, fb_lo, mc, b, n, m, c, temp, off, out, ldc,         \
+                                            ST ? stats_row : nullptr, ST ? stats_col : nullptr, ST ? stats_gref : 0.f); \
+  } while (0)
+  if (stats_row) { if (tmast) UPK_LAUNCH_TC2(true, true); else UPK_LAUNCH_TC2(true, false); }
+  else { if (tmast) UPK_LAUNCH_TC2(false, true); else UPK_LAUNCH_TC2(false, false); }
+#undef UPK_LAUNCH_TC2
   count_launch();
   UPK_RETURN_LAST_ERROR();
 }
@@ -711,7 +807,9 @@ static int run_similarity_f16(const float* f1, const float* f2, int b, int n, in
 // per-tile partial sums of 2^(v log2e - stats_gref), layouts of SimStatsGeom.
 int run_similarity_tc(const float* f1, const float* f2, int b, int n, int m, int c, float temp, int normalize,
                       int sim_type, void* workspace, size_t workspace_bytes, float* out, cudaStream_t st,
-                      float* stats_row, float* stats_col, float stats_gref) {
+                      float* stats_row, float* stats_col, float stats_gref, int ldc) {
+  if (ldc <= 0) ldc = m;
+  if (ldc < m) return UPK_ERR_INVALID_ARG;
   if (workspace_bytes < similarity_tc_workspace_bytes(b, n, m, c)) return UPK_ERR_INVALID_ARG;
   char* w = (char*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
   size_t a = (((size_t)b * n * c * sizeof(float)) + 1023) & ~(size_t)1023;
@@ -721,7 +819,7 @@ int run_similarity_tc(const float* f1, const float* f2, int b, int n, int m, int
   float* b_hi = (float*)(w + 2 * a);
   float* b_lo = (float*)(w + 2 * a + bb);
   if (similarity_mode() == 16) {   // see run_similarity_f16; 1 = not applicable, fall through to 3xTF32
-    const int rc16 = run_similarity_f16(f1, f2, b, n, m, c, temp, normalize, sim_type, a_hi, a_lo, b_hi, b_lo, out, st,
+    const int rc16 = run_similarity_f16(f1, f2, b, n, m, c, temp, normalize, sim_type, a_hi, a_lo, b_hi, b_lo, out, ldc, st,
                                         stats_row, stats_col, stats_gref);
     if (rc16 != 1) return rc16;
   }
@@ -734,11 +832,11 @@ int run_similarity_tc(const float* f1, const float* f2, int b, int n, int m, int
   const dim3 g1((n + 8 * NS_RPW - 1) / (8 * NS_RPW), b), g2((m + 8 * NS_RPW - 1) / (8 * NS_RPW), b);
   const size_t qs = off ? (size_t)c * sizeof(float) : 0;
   if (sim_type == 0) {
-    k_normalize_split<0><<<g1, 256, qs, st>>>(f1, n, c, normalize, a_hi, a_lo, off ? f2 : nullptr, m, 1, temp, out, n, m);
-    k_normalize_split<0><<<g2, 256, qs, st>>>(f2, m, c, normalize, b_hi, b_lo, off ? f1 : nullptr, n, 0, temp, out, n, m);
+    k_normalize_split<0><<<g1, 256, qs, st>>>(f1, n, c, normalize, a_hi, a_lo, off ? f2 : nullptr, m, 1, temp, out, n, m, ldc);
+    k_normalize_split<0><<<g2, 256, qs, st>>>(f2, m, c, normalize, b_hi, b_lo, off ? f1 : nullptr, n, 0, temp, out, n, m, ldc);
   } else {
-    k_normalize_split<1><<<g1, 256, qs, st>>>(f1, n, c, normalize, a_hi, a_lo, off ? f2 : nullptr, m, 1, temp, out, n, m);
-    k_normalize_split<1><<<g2, 256, qs, st>>>(f2, m, c, normalize, b_hi, b_lo, off ? f1 : nullptr, n, 0, temp, out, n, m);
+    k_normalize_split<1><<<g1, 256, qs, st>>>(f1, n, c, normalize, a_hi, a_lo, off ? f2 : nullptr, m, 1, temp, out, n, m, ldc);
+    k_normalize_split<1><<<g2, 256, qs, st>>>(f2, m, c, normalize, b_hi, b_lo, off ? f1 : nullptr, n, 0, temp, out, n, m, ldc);
   }
   count_launch(2);
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
@@ -762,7 +860,7 @@ int run_similarity_tc(const float* f1, const float* f2, int b, int n, int m, int
     auto kern = k_similarity_tc<MODE, NT, ST>;                                                               \
     UPK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
     kern<<<grid, TC_THREADS, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, b, n, m, c, temp, off, out, stats_row,  \
-                                         stats_col, stats_gref);                                             \
+                                         stats_col, stats_gref, ldc);                                        \
   } while (0)
   const int tiles2 = b * ((n - off + 2 * TC_BM - 1) / (2 * TC_BM)) * ((m - off + TC_BN - 1) / TC_BN);
   if (use_2sm && sim_type == 0 && terms == 3 && tiles2 >= sms / 2) {
@@ -770,16 +868,24 @@ int run_similarity_tc(const float* f1, const float* f2, int b, int n, int m, int
     if ((rc = make_map(&mb_hi2, b_hi, b, m, c, TC_BM))) return rc;
     if ((rc = make_map(&mb_lo2, b_lo, b, m, c, TC_BM))) return rc;
     const int grid2 = 2 * (tiles2 < sms / 2 ? tiles2 : sms / 2);
-    const size_t smem2 = sizeof(Tc2Smem) + 1024;
-    if (stats_row) {
-      UPK_CUDA_TRY(cudaFuncSetAttribute(k_similarity_tc2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-      k_similarity_tc2<true><<<grid2, TC2_THREADS, smem2, st>>>(ma_hi, ma_lo, mb_hi2, mb_lo2, b, n, m, c, temp, off, out,
-                                                              stats_row, stats_col, stats_gref);
+    CUtensorMap mc;
+    const bool tmast = off == 1 && tma_store_ok(out, n, m, ldc);
+    if (tmast) {
+      if ((rc = make_map_out(&mc, out + ldc + 1, b, n, m, ldc))) return rc;
     } else {
-      UPK_CUDA_TRY(cudaFuncSetAttribute(k_similarity_tc2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-      k_similarity_tc2<false><<<grid2, TC2_THREADS, smem2, st>>>(ma_hi, ma_lo, mb_hi2, mb_lo2, b, n, m, c, temp, off, out,
-                                                               nullptr, nullptr, 0.f);
+      mc = ma_hi;   // unused by the kernel
     }
+#define UPK_LAUNCH_TC2(ST, TM)                                                                                       \
+  do {                                                                                                               \
+    auto kern = k_similarity_tc2<ST, false, TM>;                                                                     \
+    const size_t smem2 = sizeof(Tc2Smem<TM>) + 1024;                                                                 \
+    UPK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));              \
+    kern<<<grid2, TC2_THREADS, smem2, st>>>(ma_hi, ma_lo, mb_hi2, mb_lo2, mc, b, n, m, c, temp, off, out, ldc,       \
+                                            ST ? stats_row : nullptr, ST ? stats_col : nullptr, ST ? stats_gref : 0.f); \
+  } while (0)
+    if (stats_row) { if (tmast) UPK_LAUNCH_TC2(true, true); else UPK_LAUNCH_TC2(true, false); }
+    else { if (tmast) UPK_LAUNCH_TC2(false, true); else UPK_LAUNCH_TC2(false, false); }
+#undef UPK_LAUNCH_TC2
   } else if (stats_row) {   // cosine logits + fused exponent sums (3xTF32 only: the statistics need fp32-level logits)
     UPK_LAUNCH_TC(0, 3, true);
   } else if (sim_type == 0) {

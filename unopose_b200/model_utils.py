@@ -41,8 +41,36 @@ class SimilarityStats:
         self.buf, self.temp, self.shape = buf, float(temp), tuple(shape)
 
 
+LARGE_GEOMETRY = 512 * 512      # (N1+1)*(N2+1) above which the fine solver runs its streaming passes (assign_geom)
+
+
+def _padded_atten(b, n, m, device):
+    """Storage for a large-geometry `atten`: rows of `ld` floats with 3 pad floats in front, so that element (i, 1) of
+    every row is 16-byte aligned and ld % 4 == 0 — the GEMM then stores its tiles with TMA and the assignment passes
+    read them with 128-bit loads.  Returns (view (b,n,m) with strides (n*ld, ld, 1), ld); same values, shape and dtype
+    as a contiguous tensor, `.contiguous()` gives one."""
+    ld = (m + 3 + 3) // 4 * 4
+    storage = torch.empty((b, n, ld), dtype=torch.float32, device=device)
+    return storage[:, :, 3:3 + m], ld
+
+
+def _atten_pitch(atten):
+    """(tensor, row pitch in floats) the kernels can address: a pitched fp32 view of a large geometry as it is, anything
+    else as a contiguous copy."""
+    if (atten.dtype == torch.float32 and atten.dim() == 3 and atten.shape[0] > 0 and atten.stride(2) == 1
+            and atten.stride(1) >= atten.shape[2] and atten.stride(0) == atten.shape[1] * atten.stride(1)
+            and (atten.is_contiguous() or atten.shape[1] * atten.shape[2] > LARGE_GEOMETRY)):
+        return atten, atten.stride(1)
+    a = atten.float().contiguous()
+    return a, a.shape[2]
+
+
 def compute_feature_similarity(feat1, feat2, type="cosine", temp=1.0, normalize_feat=True, return_stats=False):
     """(B,N,C),(B,M,C) -> (B,N,M).  Reference: model_utils.py:260-282.
+
+    For the fine shape (N*M > 512^2, normalised cosine logits, tensor-core path) the result is a PITCHED view (row
+    pitch M+3 rounded up to a multiple of 4 floats, see _padded_atten): same shape, dtype and values as the reference's
+    tensor, not `is_contiguous()`.
 
     return_stats=True (extension): -> (atten, stats); for normalised cosine logits on the tensor-core path the
     GEMM epilogue also emits the exponent sums of the dual-softmax assignment, which
@@ -51,23 +79,32 @@ def compute_feature_similarity(feat1, feat2, type="cosine", temp=1.0, normalize_
     if type not in ("cosine", "L2"):
         raise AssertionError(type)
     _need_cuda(feat1, "compute_feature_similarity")
+    if torch.is_grad_enabled() and (feat1.requires_grad or feat2.requires_grad):
+        raise RuntimeError("compute_feature_similarity: the kernel path has no autograd edge (evaluation only); "
+                           "run under torch.no_grad() or detach the features")
     f1, f2 = _f32c(feat1), _f32c(feat2)
     b, n, c = f1.shape
     m = f2.shape[1]
     lib = L.load()
-    out = torch.empty((b, n, m), dtype=torch.float32, device=f1.device)
     nbytes = lib.upk_feature_similarity_workspace_bytes(b, n, m, c, int(bool(normalize_feat)))
     ws = _workspace(nbytes, f1.device)
-    if return_stats and type == "cosine" and normalize_feat and b > 0 and n * m > 512 * 512:
-        sbytes = lib.upk_similarity_stats_bytes(b, n, m)
-        buf = torch.empty(max(int(sbytes) // 4, 1), dtype=torch.float32, device=f1.device)
-        with torch.cuda.device(f1.device):
-            rc = lib.upk_feature_similarity_stats(L.ptr(f1), L.ptr(f2), b, n, m, c, float(temp), L.ptr(ws), ws.numel(),
-                                                  L.ptr(out), L.ptr(buf), buf.numel() * 4, L.stream_ptr(f1))
-        if rc == 0:
-            return out, SimilarityStats(buf, temp, (b, n, m))
-        if rc != -2:                       # anything but "unsupported here": a real failure
-            L.check(rc, "feature_similarity_stats")
+    if type == "cosine" and normalize_feat and b > 0 and n * m > LARGE_GEOMETRY:
+        out, ld = _padded_atten(b, n, m, f1.device)
+        buf = None
+        if return_stats:
+            sbytes = lib.upk_similarity_stats_bytes(b, n, m)
+            buf = torch.empty(max(int(sbytes) // 4, 1), dtype=torch.float32, device=f1.device)
+        for sb in ((buf, None) if buf is not None else (None,)):
+            with torch.cuda.device(f1.device):
+                rc = lib.upk_feature_similarity_stats_ld(L.ptr(f1), L.ptr(f2), b, n, m, c, float(temp), L.ptr(ws), ws.numel(),
+                                                         out.data_ptr(), ld, L.ptr(sb), sb.numel() * 4 if sb is not None else 0,
+                                                         L.stream_ptr(f1))
+            if rc == 0:
+                stats = SimilarityStats(sb, temp, (b, n, m)) if sb is not None else None
+                return (out, stats) if return_stats else out
+            if rc != -2:                       # anything but "unsupported here": a real failure
+                L.check(rc, "feature_similarity_stats_ld")
+    out = torch.empty((b, n, m), dtype=torch.float32, device=f1.device)
     with torch.cuda.device(f1.device):
         L.check(lib.upk_feature_similarity(L.ptr(f1), L.ptr(f2), b, n, m, c, float(temp), int(bool(normalize_feat)),
                                            0 if type == "cosine" else 1, L.ptr(ws), ws.numel(), L.ptr(out),
@@ -168,7 +205,8 @@ def _fine(atten, score, pts1, pts2, model_pts, dis_thres, weight_thresh, return_
     B, N1 = pts1.shape[:2]
     N2 = pts2.shape[1]
     dev = pts1.device
-    atten, pts1, pts2 = _f32c(atten), _f32c(pts1), _f32c(pts2)
+    pts1, pts2 = _f32c(pts1), _f32c(pts2)
+    atten, a_ld = _atten_pitch(atten)
     n_model = N2
     if model_pts is not None:
         model_pts = _f32c(model_pts)
@@ -198,14 +236,16 @@ def _fine(atten, score, pts1, pts2, model_pts, dis_thres, weight_thresh, return_
             L.ptr(pts1), L.ptr(pts2), L.ptr(model_pts), n_model, B, N1, N2, float(dis_thres),
             float(weight_thresh), L.ptr(ws), ws.numel(), L.ptr(R), L.ptr(t), L.ptr(sc),
             ctypes.addressof(dbg) if dbg is not None else None, L.stream_ptr(pts1))
+    if tuple(atten.shape) != (B, N1 + 1, N2 + 1):
+        raise RuntimeError("compute_fine_Rt: atten must be (B, N1 + 1, N2 + 1)")
     with torch.cuda.device(dev):
         if stats is not None:
             if stats.shape != (B, N1 + 1, N2 + 1):
                 raise RuntimeError("compute_fine_Rt: stats belong to a different atten tensor")
-            L.check(lib.upk_fine_pose_stats(L.ptr(atten), L.ptr(stats.buf), stats.buf.numel() * 4, stats.temp, *tail),
-                    "fine_pose_stats")
+            L.check(lib.upk_fine_pose_ld(atten.data_ptr(), a_ld, L.ptr(stats.buf), stats.buf.numel() * 4, stats.temp, *tail),
+                    "fine_pose_ld")
         else:
-            L.check(lib.upk_fine_pose(L.ptr(atten), *tail), "fine_pose")
+            L.check(lib.upk_fine_pose_ld(atten.data_ptr(), a_ld, None, 0, 0.0, *tail), "fine_pose_ld")
     if return_debug:
         return R, t, sc, dbg_t
     return R, t, sc

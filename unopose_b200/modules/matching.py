@@ -62,10 +62,11 @@ class CoarsePointMatchingOneRef(nn.Module):
         if self.training:
             raise NotImplementedError("training branch (losses) is out of scope; use the reference module to train")
         g1, g2, score = self.matching_features(f1, geo1, f2, geo2)
-        atten = compute_feature_similarity(g1, g2, _get(self.cfg, "sim_type"), _get(self.cfg, "temp"),
-                                           _get(self.cfg, "normalize_feat"))
-        init_R, init_t, init_score = compute_coarse_Rt_overlap(atten, score, p1, p2, None, _get(self.cfg, "nproposal1"),
-                                                               _get(self.cfg, "nproposal2"))
+        with torch.no_grad():   # the pose solve carries no gradient in the reference either (coarse module :98)
+            atten = compute_feature_similarity(g1, g2, _get(self.cfg, "sim_type"), _get(self.cfg, "temp"),
+                                               _get(self.cfg, "normalize_feat"))
+            init_R, init_t, init_score = compute_coarse_Rt_overlap(atten, score, p1, p2, None, _get(self.cfg, "nproposal1"),
+                                                                   _get(self.cfg, "nproposal2"))
         end_points["init_pose_score"] = init_score
         end_points["init_R"] = init_R
         end_points["init_t"] = init_t
@@ -165,9 +166,10 @@ class FinePointMatchingOneRef(nn.Module):
         if self.training:
             raise NotImplementedError("training branch (losses) is out of scope; use the reference module to train")
         g1, g2, score = self.matching_features(p1, f1, geo1, fps_idx1, p2, f2, geo2, fps_idx2, end_points)
-        atten, stats = compute_feature_similarity(g1, g2, _get(self.cfg, "sim_type"), _get(self.cfg, "temp"),
-                                                  _get(self.cfg, "normalize_feat"), return_stats=True)
-        pred_R, pred_t, pred_score = compute_fine_Rt_overlap(atten, score, p1, p2, None, stats=stats)
+        with torch.no_grad():   # evaluation branch: pose only
+            atten, stats = compute_feature_similarity(g1, g2, _get(self.cfg, "sim_type"), _get(self.cfg, "temp"),
+                                                      _get(self.cfg, "normalize_feat"), return_stats=True)
+            pred_R, pred_t, pred_score = compute_fine_Rt_overlap(atten, score, p1, p2, None, stats=stats)
         end_points["pred_R"] = pred_R
         end_points["pred_t"] = pred_t * (radius.reshape(-1, 1) + 1e-6)
         end_points["pred_pose_score"] = pred_score
