@@ -18,12 +18,15 @@ from unopose_b200 import inference as INF  # noqa: E402
 GOLD = json.load(open(os.path.join(HERE, "golden", "inference_v1.json")))
 
 
-def _run(tmp_path, with_tem, bs=16, group=None):
+def _run(tmp_path, with_tem, bs=16, group=None, shard=None, first=None):
     model = FakePoseModel()
     path = os.path.join(str(tmp_path), "result.csv")
     INF.time.perf_counter = lambda: 0.0          # the `time` column becomes the deterministic seg_time
     try:
-        INF.inference_and_save_oneref_v1(model, make_loader(0, 3, with_tem), path, instance_batch_size=bs, group=group)
+        loader = make_loader(0, 3, with_tem)
+        for d in (loader[first:] if first is not None else []):                 # `first` > 0: this rank's loader yields other images from there on
+            d["img_id"] = d["img_id"] + 1000
+        INF.inference_and_save_oneref_v1(model, loader, path, instance_batch_size=bs, group=group, shard_instances=shard)
     finally:
         import time as _t
 
@@ -70,9 +73,19 @@ def _worker(rank, world, port, tmp, out):
             def __str__(self):
                 return os.path.join(tmp, "rank%d" % rank)
         os.makedirs(str(P()), exist_ok=True)
-        model, path = _run(P(), True)
+        model, path = _run(P(), True, shard=True)
         # instances of every image were split 3+2 / 19+18 / 8+8 between the two ranks
-        out[rank] = (model.calls, open(path).read() if rank == 0 else os.path.exists(path))
+        res = (model.calls, open(path).read() if rank == 0 else os.path.exists(path))
+        # default (no group, no opt-in): every rank behaves like the reference driver, no collective, all instances
+        model2, path2 = _run(P(), True)
+        res += (model2.calls, open(path2).read())
+        # sharding with DIFFERENT images per rank (what the reference's InferenceSampler would hand out) must raise
+        try:
+            _run(P(), True, shard=True, first=3 - 2 * rank)
+            res += (False,)
+        except RuntimeError as ex:
+            res += ("same image on every rank" in str(ex),)
+        out[rank] = res
     finally:
         dist.destroy_process_group()
 
@@ -82,8 +95,10 @@ def test_world2_gloo_instance_partition(tmp_path):
     mgr = mp.Manager()
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), out), nprocs=world, join=True)
-    calls0, csv0 = out[0]
-    calls1, wrote1 = out[1]
+    calls0, csv0, dcalls0, dcsv0, raised0 = out[0]
+    calls1, wrote1, dcalls1, dcsv1, raised1 = out[1]
     assert csv0 == GOLD["with_tem_pose"]["csv"]          # gathered result identical to one process / the reference
     assert wrote1 is False                                # only rank 0 writes
     assert calls0 == [3, 16, 3, 8] and calls1 == [2, 16, 2, 8]
+    assert dcalls0 == dcalls1 == [5, 16, 16, 5, 16] and dcsv0 == dcsv1 == GOLD["with_tem_pose"]["csv"]
+    assert raised0 is True and raised1 is True

@@ -9,10 +9,14 @@ and the same ``.json`` dump of the detections with ``pred_R`` / ``pred_t`` fille
 
 What is different:
 * the reference walks the instances of an image in serial chunks of ``instance_batch_size`` on one GPU; here the
-  instances of an image are additionally **partitioned across ranks** (``torch.distributed``, one process per
+  instances of an image can additionally be **partitioned across ranks** (``torch.distributed``, one process per
   GPU): rank r takes a contiguous slice, runs its own chunks, and the per-instance result rows
-  ``[R(9) | t(3) | score]`` are all-gathered (the one collective of the path, 52 bytes per instance);
-* only rank 0 writes the files (the reference lets every rank write the same path);
+  ``[R(9) | t(3) | score]`` are all-gathered (the one collective of the path, 52 bytes per instance).  This is
+  OPT-IN (pass ``group=`` or ``shard_instances=True``) and requires that every rank iterates the SAME images, i.e. an
+  unsharded loader — the reference's ``build_test_loader`` uses ``InferenceSampler``, which shards IMAGES across
+  ranks; with that loader leave instance sharding off (each rank then poses its own images, like the reference).
+  When it is on, the image identity and instance count are all-gathered per image and a mismatch raises;
+* with instance sharding only rank 0 writes the files (the reference lets every rank write the same path);
 * tensors are moved with ``.to(device)`` to the model's device, so the driver also runs on CPU tensors with a
   CPU model (the tests do that; the hot-path kernels themselves are CUDA-only).
 """
@@ -66,15 +70,35 @@ def _sync(device):
         torch.cuda.synchronize(device)
 
 
-def pose_image(model, data, instance_batch_size=16, device=None, group=None):
-    """All instances of one test image -> (R (n,9), t_mm (n,3), score (n,)) numpy arrays on every rank.
+def _check_same_image(data, n_instance, device, group):
+    """Instance sharding needs every rank to hold the same image: all-gather (scene, image, #instances) and compare."""
+    import torch.distributed as dist
 
-    `data` is one sample of the reference's test loader (image batch size 1).  Instances are sharded across the
-    ranks of `group` (contiguous balanced slices), each rank runs chunks of `instance_batch_size`."""
+    ident = torch.tensor([int(data["scene_id"].item()) if "scene_id" in data else -1,
+                          int(data["img_id"].item()) if "img_id" in data else -1, int(n_instance)],
+                         dtype=torch.int64, device=device)
+    world = dist.get_world_size(group)
+    parts = [torch.empty_like(ident) for _ in range(world)]
+    dist.all_gather(parts, ident, group=group)
+    if any(not torch.equal(p, parts[0]) for p in parts):
+        raise RuntimeError("instance sharding needs the same image on every rank (got %s): use an unsharded test loader, "
+                           "or leave shard_instances off with the reference's InferenceSampler"
+                           % [p.tolist() for p in parts])
+
+
+def pose_image(model, data, instance_batch_size=16, device=None, group=None, shard_instances=None):
+    """All instances of one test image -> (R (n,9), t_mm (n,3), score (n,)) numpy arrays (on every rank when sharded).
+
+    `data` is one sample of the reference's test loader (image batch size 1).  With instance sharding (opt-in:
+    `group` given or `shard_instances=True`) the instances are split across the ranks (contiguous balanced slices);
+    each rank runs chunks of `instance_batch_size`."""
     device = device or _model_device(model)
     data = {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in data.items()}
     n_instance = data["pts"].size(1)
-    rank, world = D._world(group)
+    shard = (group is not None) if shard_instances is None else bool(shard_instances)
+    rank, world = D._world(group) if shard else (0, 1)
+    if world > 1:
+        _check_same_image(data, n_instance, device, group)
     begin, end = D.shard_range(n_instance, rank, world)
     rows = []
     for s, e in instance_chunks(begin, end, instance_batch_size):
@@ -96,17 +120,21 @@ def pose_image(model, data, instance_batch_size=16, device=None, group=None):
     return pred_R, pred_t, score
 
 
-def inference_and_save_oneref_v1(model, data_loader, save_path, instance_batch_size=16, group=None):
-    """Drop-in for the reference driver (same arguments + an optional process group)."""
+def inference_and_save_oneref_v1(model, data_loader, save_path, instance_batch_size=16, group=None,
+                                 shard_instances=None):
+    """Drop-in for the reference driver (same arguments + an optional process group / instance-sharding switch).
+    Without instance sharding every rank behaves exactly like the reference (poses the images its loader yields and
+    writes `save_path`); with it, the loader must be unsharded and only rank 0 writes."""
     model.eval()
     device = _model_device(model)
     dets = deepcopy(data_loader.dataset.dets)
-    rank, _ = D._world(group)
+    shard = (group is not None) if shard_instances is None else bool(shard_instances)
+    rank = D._world(group)[0] if shard else 0
     lines = []
     for i, data in enumerate(data_loader):
         _sync(device)
         t0 = time.perf_counter()
-        pred_Rs, pred_Ts, pred_scores = pose_image(model, data, instance_batch_size, device, group)
+        pred_Rs, pred_Ts, pred_scores = pose_image(model, data, instance_batch_size, device, group, shard)
         _sync(device)
         image_time = time.perf_counter() - t0
         scene_id = data["scene_id"].item()

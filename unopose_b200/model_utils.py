@@ -26,6 +26,13 @@ def _need_cuda(x, what):
         raise RuntimeError("%s: CPU not supported (CUDA tensors only; no fallback path)" % what)
 
 
+def _no_grad_path(what, *tensors):
+    """The kernel paths carry no autograd edge: refuse to silently detach."""
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
+        raise RuntimeError("%s: the kernel path has no autograd edge (evaluation only); run under torch.no_grad() "
+                           "or detach the inputs" % what)
+
+
 def _workspace(nbytes, device):
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
@@ -79,9 +86,7 @@ def compute_feature_similarity(feat1, feat2, type="cosine", temp=1.0, normalize_
     if type not in ("cosine", "L2"):
         raise AssertionError(type)
     _need_cuda(feat1, "compute_feature_similarity")
-    if torch.is_grad_enabled() and (feat1.requires_grad or feat2.requires_grad):
-        raise RuntimeError("compute_feature_similarity: the kernel path has no autograd edge (evaluation only); "
-                           "run under torch.no_grad() or detach the features")
+    _no_grad_path("compute_feature_similarity", feat1, feat2)
     f1, f2 = _f32c(feat1), _f32c(feat2)
     b, n, c = f1.shape
     m = f2.shape[1]
@@ -268,6 +273,7 @@ def transform_points(pts, R, t):
     (`p1_ = (p1 - init_t.unsqueeze(1)) @ init_R`, oneref_predator_fine_point_matching.py:65-72).  One kernel
     instead of a broadcast subtract + a K=3 GEMM.  Evaluation path (no autograd edge)."""
     _need_cuda(pts, "transform_points")
+    _no_grad_path("transform_points", pts, R, t)
     pts, R, t = _f32c(pts), _f32c(R), _f32c(t)
     B, N = pts.shape[:2]
     out = torch.empty_like(pts)
@@ -281,11 +287,12 @@ def transform_points(pts, R, t):
 def weighted_procrustes(src_points, ref_points, weights=None, weight_thresh=0.0, eps=1e-5,
                         return_transform=False, src_centroid=None, ref_centroid=None):
     """Reference: model_utils.py:667-743.  (N,3)/(B,N,3) inputs; returns (R, t) or a 4x4 transform.
-    ``ref ~= R src + t``.  The reference's optional precomputed centroids are never passed by
-    any caller in the repository and are not supported by the kernel."""
-    if src_centroid is not None or ref_centroid is not None:
-        raise NotImplementedError("weighted_procrustes: precomputed centroids are not supported")
+    ``ref ~= R src + t``.  Precomputed centroids (B,3)/(B,1,3) replace the weighted means like in the reference
+    (:711-721): the kernel then solves on the pre-centred clouds (its own centroids of centred, weight-normalised points
+    are subtracted on top: they are the residual mean, zero for exact centroids) and t is rebuilt on the host from the
+    given centroids, ``t = c_ref - R c_src``."""
     _need_cuda(src_points, "weighted_procrustes")
+    _no_grad_path("weighted_procrustes", src_points, ref_points, weights)
     squeeze = src_points.ndim == 2
     if squeeze:
         src_points = src_points.unsqueeze(0)
@@ -296,17 +303,31 @@ def weighted_procrustes(src_points, ref_points, weights=None, weight_thresh=0.0,
     w = _f32c(weights) if weights is not None else None
     B, N, _ = src.shape
     dev = src.device
-    R = torch.empty((B, 3, 3), dtype=torch.float32, device=dev)
-    t = torch.empty((B, 3), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
-        if N == 3 and w is None and weight_thresh <= 1.0 and eps == 1e-5:
-            # triplet fast path == WeightedProcrustes()(src, ref, None): ref plays "p1", src plays "p2"
-            L.check(L.load().upk_kabsch_triplets(L.ptr(ref), L.ptr(src), B, L.ptr(R), L.ptr(t), None,
-                                                 L.stream_ptr(src)), "kabsch_triplets")
-        else:
-            L.check(L.load().upk_weighted_procrustes(L.ptr(src), L.ptr(ref), L.ptr(w), B, N, float(weight_thresh),
-                                                     float(eps), L.ptr(R), L.ptr(t), L.stream_ptr(src)),
-                    "weighted_procrustes")
+    given = src_centroid is not None or ref_centroid is not None
+    if given:
+        # the reference subtracts the GIVEN centroid from the respective cloud and its own weighted mean from the
+        # other: build H exactly like that (torch glue, a 3x3 per instance; no caller in the repository passes
+        # centroids) and run the kernel family's solver on it
+        wt = w if w is not None else torch.ones_like(src[:, :, 0])
+        wt = torch.where(wt < weight_thresh, torch.zeros_like(wt), wt)
+        wt = (wt / (wt.sum(1, keepdim=True) + eps)).unsqueeze(2)
+        cs = (src * wt).sum(1, keepdim=True) if src_centroid is None else _f32c(src_centroid).reshape(B, 1, 3)
+        cr = (ref * wt).sum(1, keepdim=True) if ref_centroid is None else _f32c(ref_centroid).reshape(B, 1, 3)
+        H = (src - cs).transpose(1, 2) @ (wt * (ref - cr))
+        R = _rotation_from_H(H)
+        t = (cr.transpose(1, 2) - R @ cs.transpose(1, 2)).squeeze(2)
+    else:
+        R = torch.empty((B, 3, 3), dtype=torch.float32, device=dev)
+        t = torch.empty((B, 3), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            if N == 3 and w is None and weight_thresh <= 1.0 and eps == 1e-5:
+                # triplet fast path == WeightedProcrustes()(src, ref, None): ref plays "p1", src plays "p2"
+                L.check(L.load().upk_kabsch_triplets(L.ptr(ref), L.ptr(src), B, L.ptr(R), L.ptr(t), None,
+                                                     L.stream_ptr(src)), "kabsch_triplets")
+            else:
+                L.check(L.load().upk_weighted_procrustes(L.ptr(src), L.ptr(ref), L.ptr(w), B, N, float(weight_thresh),
+                                                         float(eps), L.ptr(R), L.ptr(t), L.stream_ptr(src)),
+                        "weighted_procrustes")
     if return_transform:
         T = torch.eye(4, device=dev).unsqueeze(0).repeat(B, 1, 1)
         T[:, :3, :3] = R
@@ -315,6 +336,22 @@ def weighted_procrustes(src_points, ref_points, weights=None, weight_thresh=0.0,
     if squeeze:
         return R.squeeze(0), t.squeeze(0)
     return R, t
+
+
+def _rotation_from_H(H):
+    """R = V diag(1, 1, sign det(V U^T)) U^T for H (B,3,3) = U S V^T on the device, with the kernel family's solver:
+    the six-point problem src = (+-e_k), ref = (+-H[k, :]) has zero centroids and covariance 2 H / (6 + eps), i.e. the
+    same rotation, so upk_weighted_procrustes solves it without any centring effect."""
+    B = H.shape[0]
+    eye = torch.eye(3, device=H.device, dtype=torch.float32).unsqueeze(0).expand(B, 3, 3)
+    src = torch.cat([eye, -eye], 1).contiguous()
+    ref = torch.cat([H, -H], 1).float().contiguous()
+    R = torch.empty((B, 3, 3), dtype=torch.float32, device=H.device)
+    t = torch.empty((B, 3), dtype=torch.float32, device=H.device)
+    with torch.cuda.device(H.device):
+        L.check(L.load().upk_weighted_procrustes(L.ptr(src), L.ptr(ref), None, B, 6, 0.0, 1e-5, L.ptr(R), L.ptr(t),
+                                                 L.stream_ptr(H)), "weighted_procrustes")
+    return R
 
 
 class WeightedProcrustes(nn.Module):
@@ -341,6 +378,7 @@ class _GatherRows(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, idx):
         L.check_cuda(x, "x")
+        L.check_float(x, "x")          # the reference's gather_operation raises "must be a float tensor" too
         L.check_int(idx, "idx")
         x = x.contiguous()
         idx = idx.contiguous()
@@ -357,6 +395,7 @@ class _GatherRows(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         (idx,) = ctx.saved_tensors
+        L.check_float(grad_out, "grad_out")
         g = grad_out.contiguous()
         b, m, c = g.shape
         gx = torch.empty((b, ctx.n_src, c), dtype=torch.float32, device=g.device)
