@@ -97,7 +97,9 @@ def patched(ns=None, record=None):
         setattr(mod, name, val)
 
     swap(ns.pointnet2_utils, "_ext", ext)
-    for mod in (ns.model_utils, ns.coarse_mod, ns.fine_mod, ns.transformer):
+    mods = [ns.model_utils, ns.coarse_mod, ns.fine_mod, ns.transformer]
+    mods += [m for m in (getattr(ns, "model_mod", None), getattr(ns, "featx_mod", None)) if m is not None]
+    for mod in mods:
         for name in POSE_NAMES:
             if hasattr(mod, name):
                 swap(mod, name, getattr(new_mu, name))
@@ -106,6 +108,56 @@ def patched(ns=None, record=None):
     finally:
         for mod, name, val in reversed(saved):
             setattr(mod, name, val)
+
+
+def _stub_timm():
+    """`timm` is not installed here; the reference's feature extractor subclasses
+    `timm.models.vision_transformer.VisionTransformer` (oneref_feature_extraction.py:12,25).  The stub provides that one
+    class on top of unopose_b200.model._ViT (the same token pipeline and parameter names: patch_embed, _pos_embed,
+    norm_pre, blocks, norm), so the reference's OWN `ViT.forward`, `ViT_AE`, `ViTEncoderOneRef` and `UNOPose` run
+    unmodified.  The ViT is outside the parity scope — it only has to be the same network in
+    the stock, patched and product runs."""
+    if "timm.models.vision_transformer" in sys.modules:
+        return
+    from unopose_b200.model import _ViT
+
+    class VisionTransformer(_ViT):
+        def __init__(self, patch_size=16, embed_dim=768, depth=12, num_heads=12, mlp_ratio=4, qkv_bias=True,
+                     init_values=None, reg_tokens=0, no_embed_class=False, norm_layer=None, **kw):
+            if reg_tokens and not no_embed_class:
+                raise NotImplementedError("timm stub: register tokens need no_embed_class=True")
+            if not no_embed_class:
+                raise NotImplementedError("timm stub: only the no_embed_class=True (DINOv2 reg4) layouts")
+            super().__init__(patch_size, embed_dim, depth, num_heads, reg_tokens, init_values or 1.0, 224)
+
+    timm = types.ModuleType("timm")
+    models = types.ModuleType("timm.models")
+    vt = types.ModuleType("timm.models.vision_transformer")
+    vt.VisionTransformer = VisionTransformer
+    timm.models, models.vision_transformer = models, vt
+    sys.modules.update({"timm": timm, "timm.models": models, "timm.models.vision_transformer": vt})
+
+
+def load_model():
+    """-> (namespace of load(), the reference's own `UNOPose` class, its module) with timm stubbed (see _stub_timm).
+    The model / feature-extraction modules are added to the namespace as `model_mod` / `featx_mod` and `patched()`
+    swaps the pose-function names they bound at import time, too."""
+    ns = load()
+    if getattr(ns, "model_mod", None) is None:
+        _stub_timm()
+        ns.featx_mod = importlib.import_module("core.unopose.model.oneref_feature_extraction")
+        ns.model_mod = importlib.import_module("core.unopose.model.oneref_grf_predator_pose_estimation_model")
+        assert os.path.realpath(ns.model_mod.__file__).startswith(os.path.realpath(REF_ROOT))
+    return ns, ns.model_mod.UNOPose, ns.model_mod
+
+
+def real_model_cfg(test_coarse_only=False):
+    """The `model` node of configs/main_cfg.py:119-181 (values as data), DINOv2 ViT-B/14-reg4 feature extractor."""
+    coarse, fine, geo = real_cfgs()
+    fx = Cfg(vit_type="vit_base_patch14_reg4_dinov2", up_type="linear", embed_dim=768, out_dim=256, use_pyramid_feat=True,
+             pretrained=False, vit_ckpt="")
+    return Cfg(coarse_npoint=196, fine_npoint=2048, use_ref_rad=False, test_coarse_only=test_coarse_only,
+               feature_extraction=fx, geo_embedding=geo, coarse_point_matching=coarse, fine_point_matching=fine)
 
 
 def recording_ext(ext, record):

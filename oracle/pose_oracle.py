@@ -74,17 +74,17 @@ def dual_softmax_assignment(atten, score1=None, score2=None):
 
 
 # --------------------------------------------------------------------------- a4
-def weighted_procrustes(src, ref, weights=None, weight_thresh=0.0, eps=1e-5):
-    """model_utils.py:667-743 (batched form).  src, ref (B,N,3); weights (B,N)|None.
-    Returns R (B,3,3), t (B,3) with  ref ~= R src + t."""
+def weighted_procrustes(src, ref, weights=None, weight_thresh=0.0, eps=1e-5, src_centroid=None, ref_centroid=None):
+    """model_utils.py:667-743 (batched form).  src, ref (B,N,3); weights (B,N)|None; optional precomputed centroids
+    (B,3)|(B,1,3) replace the weighted means (:710-721).  Returns R (B,3,3), t (B,3) with  ref ~= R src + t."""
     B = src.shape[0]
     if weights is None:
         weights = torch.ones_like(src[:, :, 0])
     weights = torch.where(torch.lt(weights, weight_thresh), torch.zeros_like(weights), weights)
     weights = weights / (torch.sum(weights, dim=1, keepdim=True) + eps)
     w = weights.unsqueeze(2)
-    c_src = torch.sum(src * w, dim=1, keepdim=True)
-    c_ref = torch.sum(ref * w, dim=1, keepdim=True)
+    c_src = torch.sum(src * w, dim=1, keepdim=True) if src_centroid is None else src_centroid.reshape(B, 1, 3)
+    c_ref = torch.sum(ref * w, dim=1, keepdim=True) if ref_centroid is None else ref_centroid.reshape(B, 1, 3)
     src_c = src - c_src
     ref_c = ref - c_ref
     H = src_c.permute(0, 2, 1) @ (w * ref_c)

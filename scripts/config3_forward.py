@@ -1,0 +1,125 @@
+"""BASELINE.json config 3: full UNOPose-shaped forward (ViT-B/14-reg4 stand-in + geometric point matching) on a batch of
+32 synthetic YCB-V-sized RGB-D crops, random-init (key-addressed) weights, one B200.
+
+    python scripts/config3_forward.py [B=32] [--no-reference] [--profile]
+
+Reports device time per forward (CUDA events, warm) of
+  product    unopose_b200.model.UNOPose (the kernels of this repository under the reference's module structure),
+  reference  the reference's OWN UNOPose.forward, staged unmodified under baseline/_ref with its `_ext` compiled
+             unmodified (timm's base class stubbed by the same ViT as the product's, baseline/refgpu.py),
+with TF32 off like the reference's entry point (main_unopose.py:139-141), and — with --profile — the product's top CUDA
+kernels by device time (torch profiler).  The ViT stand-in is context, not a parity component.
+"""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def timeit(fn, it, warm):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(it):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / it
+
+
+def main():
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    B = int(args[0]) if args else 32
+    with_ref = "--no-reference" not in sys.argv
+    dev = torch.device("cuda:0")
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from baseline import refgpu
+    from unopose_b200 import _lib
+    from unopose_b200.model import UNOPose
+    from unopose_b200.synthetic import forward_batch
+    from util_state import keyed_state_dict
+    from oracle import pose_oracle as PO
+
+    cfg = refgpu.real_model_cfg()
+    model = UNOPose(cfg).eval()
+    sd = keyed_state_dict(model.state_dict(), 12)
+    model.load_state_dict(sd)
+    model = model.to(dev)
+    d = forward_batch(3, B)
+    inp = {k: torch.from_numpy(v).to(dev) for k, v in d.items()}
+    feed = lambda: {k: v for k, v in inp.items() if k not in ("R", "t")}  # noqa: E731
+    res = {"config": "full forward, B=%d crops 224x224 + 2048 query / 5000 template points, ViT-B/14-reg4 stand-in, "
+                     "hidden 256, 3+3 blocks, nproposal1=6000, TF32 off" % B, "B": B,
+           "params_M": sum(v.numel() for v in sd.values()) / 1e6}
+
+    def run(m):
+        with torch.no_grad():
+            torch.manual_seed(1)
+            return m(feed())
+
+    n0 = _lib.launch_count()
+    out = run(model)
+    res["product_native_launches_per_forward"] = _lib.launch_count() - n0
+    res["product_ms"] = timeit(lambda: run(model), 5, 2)
+    res["product_instances_per_s"] = B / res["product_ms"] * 1e3
+    torch.cuda.reset_peak_memory_stats()
+    run(model)
+    res["product_peak_mem_GB"] = torch.cuda.max_memory_allocated() / 2**30
+    # stage split of the product forward
+    fx = model.feature_extraction
+    with torch.no_grad():
+        res["product_feature_extraction_ms"] = timeit(lambda: fx(feed()), 5, 2)
+        feats = fx(feed())
+    match = lambda m: m.matching_forward(*feats, feed()) if hasattr(m, "matching_forward") else None  # noqa: E731
+
+    def run_match(m):
+        with torch.no_grad():
+            torch.manual_seed(1)
+            return match(m)
+
+    res["product_matching_ms"] = timeit(lambda: run_match(model), 5, 2)
+    res["product_matching_instances_per_s"] = B / res["product_matching_ms"] * 1e3
+    gtR = inp["R"]
+    res["product_rot_err_vs_planted_deg"] = [round(float(a), 3) for a in PO.rotation_geodesic_deg(out["pred_R"], gtR)]
+    res["product_coarse_rot_err_vs_planted_deg"] = [round(float(a), 3) for a in PO.rotation_geodesic_deg(out["init_R"], gtR)]
+    res["product_pose_score"] = [round(float(a), 4) for a in out["pred_pose_score"]]
+    if "--profile" in sys.argv:
+        from torch.profiler import ProfilerActivity, profile
+
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            run_match(model)
+            torch.cuda.synchronize()
+        rows = sorted(prof.key_averages(), key=lambda e: -e.device_time_total)[:45]
+        res["product_matching_top_kernels_us"] = [[e.key[:100], round(e.device_time_total, 1), e.count] for e in rows
+                                                  if e.device_time_total > 0]
+    if with_ref and refgpu.available():
+        ns, RefUNOPose, _ = refgpu.load_model()
+        r_model = RefUNOPose(cfg).eval()
+        r_model.load_state_dict(sd)
+        r_model = r_model.to(dev)
+        ref_out = run(r_model)
+        res["reference_ms"] = timeit(lambda: run(r_model), 3, 1)
+        res["reference_instances_per_s"] = B / res["reference_ms"] * 1e3
+        torch.cuda.reset_peak_memory_stats()
+        run(r_model)
+        res["reference_peak_mem_GB"] = torch.cuda.max_memory_allocated() / 2**30
+        with torch.no_grad():
+            res["reference_feature_extraction_ms"] = timeit(lambda: r_model.feature_extraction(feed()), 3, 1)
+        res["reference_matching_ms"] = res["reference_ms"] - res["reference_feature_extraction_ms"]  # (no split entry point)
+        res["speedup_full_forward"] = res["reference_ms"] / res["product_ms"]
+        res["speedup_matching_part"] = res["reference_matching_ms"] / res["product_matching_ms"]
+        ang = PO.rotation_geodesic_deg(out["pred_R"], ref_out["pred_R"])
+        res["product_vs_reference_rot_deg"] = [float("%.2e" % a) for a in ang.tolist()]
+        res["reference_rot_err_vs_planted_deg"] = [round(float(a), 3) for a in PO.rotation_geodesic_deg(ref_out["pred_R"], gtR)]
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()

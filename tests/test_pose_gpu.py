@@ -335,6 +335,24 @@ def test_procrustes_against_reference_golden(cuda):
     assert Tm.shape == (5, 4, 4)
 
 
+def test_procrustes_precomputed_centroids_against_reference_golden(cuda):
+    """`src_centroid=` / `ref_centroid=` (reference model_utils.py:710-721), (B,3) and (B,1,3) forms, against outputs of
+    the imported reference (tests/golden/make_procrustes_centroid_golden.py) and the oracle on the device."""
+    g = np.load(os.path.join(GOLD, "pose_procrustes_centroids.npz"))
+    T = lambda k: torch.from_numpy(g[k]).to(cuda)
+    src, ref, w, cs, cr = (T(k) for k in ("src", "ref", "w", "cs", "cr"))
+    for kw, (kR, kt) in ((dict(weights=w, weight_thresh=0.2, src_centroid=cs, ref_centroid=cr.unsqueeze(1)), ("Rb", "tb")),
+                         (dict(weights=w, weight_thresh=0.2, src_centroid=cs.unsqueeze(1)), ("Rs", "ts")),
+                         (dict(ref_centroid=cr), ("Rr", "tr"))):
+        R, t = MU().weighted_procrustes(src, ref, **kw)
+        Ro, to = PO.weighted_procrustes(src, ref, **kw)
+        for Rx, tx in ((T(kR), T(kt)), (Ro, to)):
+            assert PO.rotation_geodesic_deg(R, Rx).max() <= ROT_TOL_DEG
+            assert PO.relative_translation_error(t, tx).max() <= T_TOL_REL
+    r, tt = MU().weighted_procrustes(src[0], ref[0], w[0], src_centroid=cs[:1], ref_centroid=cr[:1])
+    assert r.shape == (3, 3) and tt.shape == (3,)
+
+
 def test_sample_pts_feats_api(cuda):
     from util_clouds import batch_clouds
 

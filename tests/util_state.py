@@ -21,6 +21,8 @@ def keyed_state_dict(template, seed):
             a = 0.5 + np.abs(n)
         elif "running_mean" in k:
             a = 0.1 * n
+        elif k.endswith(".gamma"):
+            a = 1e-5 * (1.0 + 0.1 * n)             # LayerScale at its own initial value (DINOv2: init_values = 1e-5)
         elif k.endswith("bias"):
             a = 0.02 * n
         elif v.dim() <= 1 or "norm" in k.lower() or ".bn." in k:

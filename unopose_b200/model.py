@@ -1,0 +1,265 @@
+"""`UNOPose.forward` wiring around the hot path (BASELINE.json config 3: "full UNOPose-shaped forward").
+
+Reference: core/unopose/model/oneref_grf_predator_pose_estimation_model.py:12-93 (`UNOPose`), and
+core/unopose/model/oneref_feature_extraction.py:25-282 (`ViT`, `ViT_AE`, `ViTEncoderOneRef`).
+
+What is the product here and what is a stand-in:
+* `UNOPose.forward` — the same sequence as the reference (:25-76): feature extraction, global LRF of both clouds
+  (`get_batch_lrf`, one kernel), FPS + row gathers (`sample_pts_feats_wlrf`), geometric embeddings of the two sparse
+  clouds (fused kernels), the coarse module, the fine module; same attribute names (`feature_extraction`,
+  `geo_embedding`, `coarse_point_matching`, `fine_point_matching`), same `end_points` keys, same `test_coarse_only`
+  short cut.  Evaluation only (training branches raise in the matching modules).
+* `ViTEncoderOneRef` — the reference's wrapper logic (:227-282): radius normalisation by the template cloud, the
+  `dense_po`/`dense_fo` short cut for cached templates, per-pixel feature picking, template FPS via `sample_pts_feats`.
+* `ViTStandIn` — NOT a parity component (`timm` is absent; the ViT is out of scope): a plain
+  PyTorch ViT of the DINOv2 "vit_base_patch14_reg4" shape (224x224 -> 256 patches + cls + 4 register tokens = 261 tokens,
+  768-d, 12 blocks, 12 heads, LayerScale, 4-level pyramid -> Linear(3072, 16*256) -> 64x64 -> bilinear 224x224), with
+  timm's parameter names so a DINOv2 checkpoint's tensors have a place to go.  It exists so the matching path can be
+  driven, timed and memory-sized at the shapes of a full forward with random-init weights.
+"""
+from functools import partial
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import model_utils as MU
+from .modules import CoarsePointMatchingOneRef, FinePointMatchingOneRef, GeometricStructureEmbedding
+from .pointnet2.lrf import get_batch_lrf
+
+
+def _get(cfg, key, default=None):
+    if isinstance(cfg, dict):
+        return cfg.get(key, default)
+    return getattr(cfg, key, default)
+
+
+class Cfg(dict):
+    """Attribute-style dict (stands in for the reference's LazyConfig / edict nodes)."""
+    __getattr__ = dict.__getitem__
+
+    def get(self, k, d=None):  # noqa: D401
+        return dict.get(self, k, d)
+
+
+def default_config():
+    """configs/main_cfg.py:130-178 of the reference (the released model's geometry)."""
+    return Cfg(
+        coarse_npoint=196, fine_npoint=2048, use_ref_rad=False, test_coarse_only=False,
+        feature_extraction=Cfg(vit_type="vit_base_patch14_reg4_dinov2", up_type="linear", embed_dim=768, out_dim=256,
+                               use_pyramid_feat=True, pretrained=False),
+        geo_embedding=Cfg(sigma_d=0.2, sigma_a=15, angle_k=3, reduction_a="max", hidden_dim=256),
+        coarse_point_matching=Cfg(nblock=3, input_dim=256, hidden_dim=256, out_dim=256, temp=0.1, sim_type="cosine",
+                                  normalize_feat=True, nproposal1=6000, nproposal2=300),
+        fine_point_matching=Cfg(nblock=3, input_dim=256, hidden_dim=256, out_dim=256, pe_radius1=0.1, pe_radius2=0.2,
+                                focusing_factor=3, temp=0.1, sim_type="cosine", normalize_feat=True, use_lrf=True,
+                                use_xyz=True, nsample1=64, nsample2=256),
+    )
+
+
+# ------------------------------------------------------------------------------------------- ViT stand-in
+class _Attention(nn.Module):
+    def __init__(self, dim, heads):
+        super().__init__()
+        self.num_heads = heads
+        self.qkv = nn.Linear(dim, 3 * dim, bias=True)
+        self.proj = nn.Linear(dim, dim)
+
+    def forward(self, x):
+        B, N, C = x.shape
+        q, k, v = self.qkv(x).reshape(B, N, 3, self.num_heads, C // self.num_heads).permute(2, 0, 3, 1, 4)
+        x = F.scaled_dot_product_attention(q, k, v)
+        return self.proj(x.transpose(1, 2).reshape(B, N, C))
+
+
+class _LayerScale(nn.Module):
+    def __init__(self, dim, init):
+        super().__init__()
+        self.gamma = nn.Parameter(init * torch.ones(dim))
+
+    def forward(self, x):
+        return x * self.gamma
+
+
+class _Mlp(nn.Module):
+    def __init__(self, dim, hidden):
+        super().__init__()
+        self.fc1, self.fc2 = nn.Linear(dim, hidden), nn.Linear(hidden, dim)
+
+    def forward(self, x):
+        return self.fc2(F.gelu(self.fc1(x)))
+
+
+class _Block(nn.Module):
+    def __init__(self, dim, heads, init_values, norm):
+        super().__init__()
+        self.norm1, self.attn, self.ls1 = norm(dim), _Attention(dim, heads), _LayerScale(dim, init_values)
+        self.norm2, self.mlp, self.ls2 = norm(dim), _Mlp(dim, 4 * dim), _LayerScale(dim, init_values)
+
+    def forward(self, x):
+        x = x + self.ls1(self.attn(self.norm1(x)))
+        return x + self.ls2(self.mlp(self.norm2(x)))
+
+
+class _PatchEmbed(nn.Module):
+    def __init__(self, patch, dim):
+        super().__init__()
+        self.proj = nn.Conv2d(3, dim, patch, patch)
+
+    def forward(self, x):
+        return self.proj(x).flatten(2).transpose(1, 2)
+
+
+class _ViT(nn.Module):
+    """The token pipeline of timm's VisionTransformer with reg_tokens=4, no_embed_class=True, as the reference's `ViT`
+    subclass runs it (oneref_feature_extraction.py:25-46): the normed outputs of blocks d-1, d-n-1, d-2n-1, d-3n-1.
+    Attribute names (`patch_embed`, `_pos_embed`, `norm_pre`, `blocks`, `norm`) are timm's, so the reference's own
+    `ViT.forward` runs on this class too (the drop-in test stubs timm with it)."""
+
+    def __init__(self, patch=14, dim=768, depth=12, heads=12, reg_tokens=4, init_values=1e-5, img=224):
+        super().__init__()
+        norm = partial(nn.LayerNorm, eps=1e-6)
+        self.patch_embed = _PatchEmbed(patch, dim)
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, dim))
+        self.reg_token = nn.Parameter(torch.zeros(1, reg_tokens, dim)) if reg_tokens else None
+        self.pos_embed = nn.Parameter(0.02 * torch.randn(1, (img // patch) ** 2, dim))
+        self.norm_pre = nn.Identity()
+        self.blocks = nn.ModuleList([_Block(dim, heads, init_values, norm) for _ in range(depth)])
+        self.norm = norm(dim)
+        self.num_prefix_tokens = 1 + reg_tokens
+
+    def _pos_embed(self, x):
+        """no_embed_class=True: the position embedding covers the patches only; cls / register tokens are prepended."""
+        x = x + self.pos_embed
+        pre = [self.cls_token.expand(x.shape[0], -1, -1)]
+        if self.reg_token is not None:
+            pre.append(self.reg_token.expand(x.shape[0], -1, -1))
+        return torch.cat(pre + [x], 1)
+
+    def forward(self, x):
+        x = self.norm_pre(self._pos_embed(self.patch_embed(x)))
+        d = len(self.blocks)
+        n = d // 4
+        keep = (d - 1, d - n - 1, d - 2 * n - 1, d - 3 * n - 1)
+        out = []
+        for i, blk in enumerate(self.blocks):
+            x = blk(x)
+            if i in keep:
+                out.append(self.norm(x))
+        return out
+
+
+class ViTStandIn(nn.Module):
+    """`ViT_AE` (oneref_feature_extraction.py:49-224), "linear" up-scaling, with `_ViT` in place of timm."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.vit_type = _get(cfg, "vit_type", "vit_base_patch14_reg4_dinov2")
+        self.embed_dim, self.out_dim = _get(cfg, "embed_dim", 768), _get(cfg, "out_dim", 256)
+        self.use_pyramid_feat = _get(cfg, "use_pyramid_feat", True)
+        if _get(cfg, "up_type", "linear") != "linear":
+            raise NotImplementedError("ViTStandIn: only up_type='linear' (the released configuration)")
+        self.patch_size = 14 if "patch14" in self.vit_type else 16
+        self.img_size = 224
+        self.patch_num_side = self.img_size // self.patch_size
+        large, small = "large" in self.vit_type, "small" in self.vit_type
+        self.vit = _ViT(self.patch_size, self.embed_dim, 24 if large else 12, 16 if large else (6 if small else 12),
+                        4 if "reg4" in self.vit_type else 0, 1e-5, self.img_size)
+        self.output_upscaling = nn.Linear(self.embed_dim * (4 if self.use_pyramid_feat else 1), 16 * self.out_dim)
+
+    def forward(self, x):
+        B, _, H, W = x.shape
+        outs = self.vit(x)
+        cls_tokens = outs[-1][:, 0, :].contiguous()
+        outs = [o[:, self.vit.num_prefix_tokens:, :] for o in outs]
+        x = torch.cat(outs, 2) if self.use_pyramid_feat else outs[-1]
+        s = self.patch_num_side
+        x = self.output_upscaling(x).reshape(B, s, s, 4, 4, self.out_dim).permute(0, 5, 1, 3, 2, 4).reshape(B, -1, 4 * s, 4 * s)
+        return F.interpolate(x, (H, W), mode="bilinear", align_corners=False), cls_tokens
+
+
+class ViTEncoderOneRef(nn.Module):
+    """oneref_feature_extraction.py:227-282 (evaluation branches)."""
+
+    def __init__(self, cfg, npoint=None):
+        super().__init__()
+        self.npoint = npoint
+        self.rgb_net = ViTStandIn(cfg)
+
+    @staticmethod
+    def _radius(pts):
+        return torch.norm(pts - pts.mean(1, keepdim=True), dim=2).max(1)[0]
+
+    def forward(self, end_points):
+        dense_fm = self.get_img_feats(end_points["rgb"], end_points["rgb_choose"])
+        dense_pm = end_points["pts"]
+        assert end_points["rgb_choose"].size(1) == self.npoint
+        if "dense_po" in end_points and "dense_fo" in end_points:       # cached template (:239-250)
+            dense_po, dense_fo = end_points["dense_po"].clone(), end_points["dense_fo"].clone()
+            radius = self._radius(dense_po)
+            scale = radius.reshape(-1, 1, 1) + 1e-6
+            dense_pm, dense_po = dense_pm / scale, dense_po / scale
+        else:                                                           # template from the data set (:251-266)
+            tem1_pts = end_points["tem1_pts"]
+            radius = self._radius(tem1_pts)
+            scale = radius.reshape(-1, 1, 1) + 1e-6
+            dense_pm, tem1_pts = dense_pm / scale, tem1_pts / scale
+            dense_po, dense_fo = self.get_obj_feats([end_points["tem1_rgb"]], [tem1_pts], [end_points["tem1_choose"]])
+        return dense_pm, dense_fm, dense_po, dense_fo, radius
+
+    def get_img_feats(self, img, choose):
+        """`get_chosen_pixel_feats` (model_utils.py:215-227): (B,C,H,W) feature map, pixel indices (B,P) -> (B,P,C)."""
+        fmap = self.rgb_net(img)[0]
+        B, C = fmap.shape[:2]
+        return torch.gather(fmap.reshape(B, C, -1), 2, choose.unsqueeze(1).expand(-1, C, -1)).transpose(1, 2).contiguous()
+
+    def get_obj_feats(self, tem_rgb_list, tem_pts_list, tem_choose_list, npoint=None):
+        feats = [self.get_img_feats(t, c) for t, c in zip(tem_rgb_list, tem_choose_list)]
+        return MU.sample_pts_feats(torch.cat(tem_pts_list, 1), torch.cat(feats, 1), npoint or self.npoint)
+
+
+# ------------------------------------------------------------------------------------------- the model
+class UNOPose(nn.Module):
+    """oneref_grf_predator_pose_estimation_model.py:12-93, evaluation path."""
+
+    def __init__(self, cfg=None):
+        super().__init__()
+        cfg = cfg or default_config()
+        self.cfg = cfg
+        self.coarse_npoint, self.fine_npoint = _get(cfg, "coarse_npoint"), _get(cfg, "fine_npoint")
+        self.use_ref_rad = _get(cfg, "use_ref_rad", False)
+        self.test_coarse_only = _get(cfg, "test_coarse_only", False)
+        self.feature_extraction = ViTEncoderOneRef(_get(cfg, "feature_extraction"), self.fine_npoint)
+        self.geo_embedding = GeometricStructureEmbedding(_get(cfg, "geo_embedding"))
+        self.coarse_point_matching = CoarsePointMatchingOneRef(_get(cfg, "coarse_point_matching"))
+        self.fine_point_matching = FinePointMatchingOneRef(_get(cfg, "fine_point_matching"))
+
+    def get_batch_lrf(self, pts):
+        """:78-93 — centroid-anchored frame of the whole cloud; `lrf.cu::k_global_lrf` (one launch)."""
+        return get_batch_lrf(pts, use_ref_rad=self.use_ref_rad)
+
+    def forward(self, end_points):
+        dense_pm, dense_fm, dense_po, dense_fo, radius = self.feature_extraction(end_points)
+        return self.matching_forward(dense_pm, dense_fm, dense_po, dense_fo, radius, end_points)
+
+    def matching_forward(self, dense_pm, dense_fm, dense_po, dense_fo, radius, end_points):
+        """Everything after the feature extractor (:28-76): the geometric point matching on per-point features."""
+        # like the reference (:29-30) the frames are computed on the UN-normalised input clouds
+        dense_pm_lrf = self.get_batch_lrf(end_points["pts"])
+        dense_po_lrf = self.get_batch_lrf(end_points["tem1_pts"])
+        bg_point = torch.ones(dense_pm.size(0), 1, 3, dtype=torch.float32, device=dense_pm.device)
+        sparse_pm, sparse_pm_lrf, sparse_fm, fps_idx_m = MU.sample_pts_feats_wlrf(
+            dense_pm, dense_pm_lrf, dense_fm, self.coarse_npoint, return_index=True)
+        geo_embedding_m = self.geo_embedding(torch.cat([bg_point, sparse_pm_lrf], 1))
+        sparse_po, sparse_po_lrf, sparse_fo, fps_idx_o = MU.sample_pts_feats_wlrf(
+            dense_po, dense_po_lrf, dense_fo, self.coarse_npoint, return_index=True)
+        geo_embedding_o = self.geo_embedding(torch.cat([bg_point, sparse_po_lrf], 1))
+        end_points = self.coarse_point_matching(sparse_pm, sparse_fm, geo_embedding_m, sparse_po, sparse_fo,
+                                                geo_embedding_o, radius, end_points)
+        if not self.training and self.test_coarse_only:
+            end_points["pred_R"] = end_points["init_R"]
+            end_points["pred_t"] = end_points["init_t"] * (radius.reshape(-1, 1) + 1e-6)
+            end_points["pred_pose_score"] = end_points["init_pose_score"]
+            return end_points
+        return self.fine_point_matching(dense_pm, dense_fm, geo_embedding_m, fps_idx_m, dense_po, dense_fo,
+                                        geo_embedding_o, fps_idx_o, radius, end_points)

@@ -288,9 +288,9 @@ def weighted_procrustes(src_points, ref_points, weights=None, weight_thresh=0.0,
                         return_transform=False, src_centroid=None, ref_centroid=None):
     """Reference: model_utils.py:667-743.  (N,3)/(B,N,3) inputs; returns (R, t) or a 4x4 transform.
     ``ref ~= R src + t``.  Precomputed centroids (B,3)/(B,1,3) replace the weighted means like in the reference
-    (:711-721): the kernel then solves on the pre-centred clouds (its own centroids of centred, weight-normalised points
-    are subtracted on top: they are the residual mean, zero for exact centroids) and t is rebuilt on the host from the
-    given centroids, ``t = c_ref - R c_src``."""
+    (:710-721): the 3x3 covariance is then formed by torch glue exactly like the reference forms it (a given centroid is
+    subtracted from its cloud, the weighted mean from the other), the rotation comes from the kernel family's solver
+    (`_rotation_from_H`) and ``t = c_ref - R c_src`` uses the given centroids."""
     _need_cuda(src_points, "weighted_procrustes")
     _no_grad_path("weighted_procrustes", src_points, ref_points, weights)
     squeeze = src_points.ndim == 2

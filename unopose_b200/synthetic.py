@@ -70,3 +70,70 @@ def matching_batch(seed, b, n, c=256, **kw):
     rng = np.random.default_rng(seed)
     items = [matching_instance(rng, n, c, **kw) for _ in range(b)]
     return {k: np.stack([it[k] for it in items]) for k in items[0]}
+
+
+def _small_rotation(rng, max_deg):
+    ax = rng.standard_normal(3)
+    ax /= np.linalg.norm(ax)
+    ang = np.deg2rad(max_deg) * rng.uniform(-1, 1)
+    K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+    return np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * K @ K
+
+
+def forward_batch(seed, b, n_query=2048, n_template=5000, img=224, radius_m=0.08, depth_m=0.8, noise_m=0.0005,
+                  view_jitter_deg=3.0, splat=2):
+    """Inputs of a full `UNOPose.forward` (BASELINE.json config 3; keys and shapes of the reference's test loader,
+    SURVEY.md §3.1): YCB-V-sized objects (radius ~8 cm) seen at ~0.8 m, as RGB-D crops.
+
+    Geometry.  The object is a bumpy closed surface.  The template cloud `tem1_pts` (object frame, metres) holds the
+    `n_template` surface points that face the template camera; the observed cloud `pts` (camera frame, metres) is a
+    rigidly moved, noisy subset of those that also face the query camera: `pts ~= R tem1_pts[sel] + t`.  The template
+    view is within `view_jitter_deg` of the query view (UNOPose's setting: ONE reference view of the unseen object that
+    shares visible surface with the query).
+
+    Appearance.  Each point owns a pixel of its 224x224 crop (orthographic, nearest pixel, the crop spans the cloud's
+    bounding box) and is painted as a (2*splat+1)^2 footprint whose colour is a smooth function of the OBJECT-space
+    position, so the two crops show the same textured object from nearby views and corresponding points carry similar
+    image content — what a feature extractor needs to produce matchable features.
+
+    Returns numpy arrays: rgb / tem1_rgb (b,3,img,img) f32, rgb_choose (b,n_query) / tem1_choose (b,n_template) i64,
+    pts (b,n_query,3), tem1_pts (b,n_template,3), R (b,3,3), t (b,3)."""
+    rng = np.random.default_rng(seed)
+    out = {k: [] for k in ("rgb", "rgb_choose", "pts", "tem1_rgb", "tem1_choose", "tem1_pts", "R", "t")}
+    freq, phase = np.array([2.1, 2.7, 3.3]), np.array([0.3, 1.1, 2.0])
+
+    def crop(points_view, points_obj):
+        xy = points_view[:, :2]
+        lo, hi = xy.min(0), xy.max(0)
+        uv = np.clip(((xy - lo) / (hi - lo + 1e-9) * (img - 1 - 2 * splat)).round().astype(np.int64) + splat, 0, img - 1)
+        # "mean/std-normalised" RGB (zero-centred), a multi-band texture fixed to the object's surface
+        q = points_obj / radius_m
+        col = (np.sin(q * freq + phase) * np.sin(q[:, [1, 2, 0]] * (3.1 * freq) + 2 * phase)
+               + 0.5 * np.sin(q[:, [2, 0, 1]] * (5.3 * freq) + 3 * phase)).astype(np.float32)
+        image = np.zeros((img, img, 3), np.float32)
+        for dy in range(-splat, splat + 1):
+            for dx in range(-splat, splat + 1):
+                image[np.clip(uv[:, 1] + dy, 0, img - 1), np.clip(uv[:, 0] + dx, 0, img - 1)] = col
+        return uv[:, 1] * img + uv[:, 0], image.transpose(2, 0, 1).copy()
+
+    for _ in range(b):
+        R = random_rotation(rng).astype(np.float64)
+        V = _small_rotation(rng, view_jitter_deg) @ R                     # object -> template camera
+        v = rng.standard_normal((6 * n_template, 3))
+        v /= np.linalg.norm(v, axis=1, keepdims=True)
+        v = v[(v @ V.T)[:, 2] < 0.1][:n_template]                         # faces the template camera (looks down +z)
+        assert len(v) == n_template
+        rad = 0.7 + 0.15 * np.sin(3 * v[:, 0]) * np.cos(2 * v[:, 1]) + 0.1 * v[:, 2] ** 2
+        tem = v * rad[:, None]
+        tem *= radius_m / np.linalg.norm(tem - tem.mean(0), axis=1).max()
+        t = np.array([rng.normal(0, 0.05), rng.normal(0, 0.05), depth_m + rng.normal(0, 0.05)])
+        seen = np.flatnonzero((v @ R.T)[:, 2] < 0.05)                     # also faces the query camera
+        sel = rng.choice(seen, n_query, replace=len(seen) < n_query)
+        pts = tem[sel] @ R.T + t + rng.standard_normal((n_query, 3)) * noise_m
+        tem_choose, tem_rgb = crop(tem @ V.T, tem)
+        choose, rgb = crop(pts, tem[sel])
+        for k, val in (("rgb", rgb), ("rgb_choose", choose), ("pts", pts.astype(np.float32)), ("tem1_rgb", tem_rgb),
+                       ("tem1_choose", tem_choose), ("tem1_pts", tem.astype(np.float32)), ("R", R.astype(np.float32)),
+                       ("t", t.astype(np.float32))):
+            out[k].append(val)
+    return {k: np.stack(v) for k, v in out.items()}
