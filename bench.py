@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
     ap.add_argument("--mode", default="step", choices=["step", "hyp-shard"])
     ap.add_argument("--H", type=int, nargs="*", default=None, help="hyp-shard: hypotheses per instance (default sweep)")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="hyp-shard: candidate / score exchange through peer memory (fused into the kernels) or NCCL")
     ap.add_argument("--no-overlap", action="store_true", help="run the two chains of a step serially on one stream")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying CUDA graphs")
     ap.add_argument("--depth", type=int, default=2,
@@ -401,15 +403,22 @@ def run_hyp_shard(args, cfg):
     rows = []
     for H in Hs:
         u = torch.rand(B, 3 * H, generator=torch.Generator().manual_seed(H)).to(dev)
-        solver = HypothesisShardedCoarse(B, n, n, H, K, dev)
+        solver = HypothesisShardedCoarse(B, n, n, H, K, dev, exchange=args.exchange)   # auto: peer memory when mappable
+        solver_nccl = HypothesisShardedCoarse(B, n, n, H, K, dev, exchange="nccl") if solver.exchange == "p2p" else None
         single = lambda: MU._coarse(atten, T["score"], T["pts1"], T["pts2"], None, H, K, u=u)  # noqa: E731
         shard = lambda: solver.run(atten, T["score"], T["pts1"], T["pts2"], u)  # noqa: E731
+        shard_nccl = lambda: solver_nccl.run(atten, T["score"], T["pts1"], T["pts2"], u)  # noqa: E731
         R1, t1, s1 = single()
         R2, t2, s2, _ = shard()
         torch.cuda.synchronize()
         same = bool(torch.equal(R1, R2) and torch.equal(t1, t2) and torch.equal(s1, s2))
-        res = {}
-        for name, fn in (("sharded", shard), ("single_gpu", single)):
+        if solver_nccl is not None:
+            R3, t3, s3, _ = shard_nccl()
+            torch.cuda.synchronize()
+            same = same and bool(torch.equal(R1, R3) and torch.equal(t1, t3) and torch.equal(s1, s3))
+        res = {"exchange": solver.exchange}
+        variants = [("sharded", shard)] + ([("sharded_nccl", shard_nccl)] if solver_nccl is not None else []) + [("single_gpu", single)]
+        for name, fn in variants:
             graph = None
             if not args.no_graph:
                 try:                                           # NCCL collectives are graph-capturable
@@ -447,8 +456,9 @@ def run_hyp_shard(args, cfg):
         # the two collectives alone (same buffers), to name the limiter
         coll = {}
         if dist is not None:
-            for cname, fn in (("all_gather_candidates", lambda: dist.all_gather_into_tensor(solver.allc, solver.cand)),
-                              ("all_reduce_max_scores", lambda: dist.all_reduce(solver.scores, op=dist.ReduceOp.MAX))):
+            sv = solver_nccl or solver
+            for cname, fn in (("all_gather_candidates", lambda: dist.all_gather_into_tensor(sv.allc, sv.cand)),
+                              ("all_reduce_max_scores", lambda: dist.all_reduce(sv.scores, op=dist.ReduceOp.MAX))):
                 for _ in range(5):
                     fn()
                 barrier()
@@ -461,6 +471,8 @@ def run_hyp_shard(args, cfg):
                 coll[cname + "_us"] = e0.elapsed_time(e1) / 50 * 1e3
             coll["all_gather_bytes_per_rank"] = solver.cand.numel() * 4
             coll["all_reduce_bytes"] = solver.scores.numel() * 4
+            if solver.px is not None:
+                coll["peer_exchange_timed_out"] = solver.px.timed_out()
         rows.append(dict(H=H, K=K, B=B, bit_identical_to_single_gpu=same, **res, collectives=coll))
     if rank == 0:
         best = max(rows, key=lambda r: r["sharded"]["hypotheses_per_s"])
@@ -471,7 +483,8 @@ def run_hyp_shard(args, cfg):
                 "config": {"workload": "coarse solve 196x196, K=%d, hypothesis pool of one %d-instance batch split over %d rank(s); "
                                        "value = the best H of the sweep" % (K, B, world), "H_of_value": best["H"],
                            "l2": "coarse working set (0.5 MB / instance) is L2-resident by nature"},
-                "sweep": rows, "gpu_launches": int(args.steps * 10)}
+                "exchange": rows[0].get("exchange"),
+                "sweep": rows, "gpu_launches": int(args.steps * (8 if rows[0].get("exchange") == "p2p" else 10))}
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

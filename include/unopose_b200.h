@@ -231,6 +231,49 @@ int upk_pack_candidates(const float* resid, const float* Rs, const float* ts, co
 int upk_unpack_candidates(const float* gathered, int world, int my_rank, int b, int n_hyp, int n_slots, float* resid,
                           float* Rs, float* ts, upk_stream_t stream);
 
+/* Peer exchange (NVLink / NVSwitch peer memory) — the fused compute + collective form of the two exchange steps of
+ * hypothesis sharding and of the result gather of instance sharding (BASELINE.json north_star: "an NCCL
+ * gather over NVLink of per-shard best scores").  No counterpart in the reference (single process, no collective).
+ * The host maps one SYMMETRIC allocation per rank into every process (torch.distributed._symmetric_memory, CUDA VMM)
+ * and describes it with upk_peer_t; producer kernels store their results into every rank's copy and publish an epoch
+ * flag, consumer kernels wait on their local flags (csrc/peer.cuh has the protocol).  Channels are independent
+ * exchange steps; data of epoch e lives in slab (e & 1) of its channel. */
+#define UPK_MAX_PEERS 8
+#define UPK_PEER_CHANNELS 4
+typedef struct upk_peer {
+  int world, rank;
+  void* data[UPK_MAX_PEERS];                /* rank r's exchange buffer as mapped in THIS process (data[rank] = local) */
+  unsigned long long* flags[UPK_MAX_PEERS]; /* rank r's flag array [UPK_PEER_CHANNELS][UPK_MAX_PEERS], zero-initialised */
+  unsigned long long* epoch;                /* local: [UPK_PEER_CHANNELS], zero-initialised                            */
+  unsigned int* done;                       /* local: [UPK_PEER_CHANNELS] CTA-completion counters, zero-initialised     */
+  unsigned int* status;                     /* local: [1], set to 1 if a wait timed out (a peer never published)        */
+} upk_peer_t;
+
+/* upk_pack_candidates that writes this rank's candidate list into EVERY rank's gathered[world][b][n_slots][14] array
+ * (at data[r] + data_offset + slab * slab_bytes) and publishes channel `channel`. */
+int upk_pack_candidates_peer(const float* resid, const float* Rs, const float* ts, const int* top_local, int b, int n_hyp,
+                             int h_begin, int n_local, int n_slots, const upk_peer_t* peer, size_t data_offset,
+                             size_t slab_bytes, int channel, upk_stream_t stream);
+/* upk_unpack_candidates that first waits for every rank's publication on `channel`, then reads the local array. */
+int upk_unpack_candidates_peer(const upk_peer_t* peer, size_t data_offset, size_t slab_bytes, int channel, int b, int n_hyp,
+                               int n_slots, float* resid, float* Rs, float* ts, upk_stream_t stream);
+/* upk_score_hypotheses whose scores[b][n_keep] entries [k_begin,k_end) are stored into every rank's score table. */
+int upk_score_hypotheses_peer(const float* pts1, const float* model_pts, const float* w1, const float* Rs, const float* ts,
+                              const int* top, int b, int n1, int n_model, int n_hyp, int n_keep, int k_begin, int k_end,
+                              const upk_peer_t* peer, size_t data_offset, size_t slab_bytes, int channel,
+                              upk_stream_t stream);
+/* upk_select_best on the local score table after waiting for every rank's slice. */
+int upk_select_best_peer(const upk_peer_t* peer, size_t data_offset, size_t slab_bytes, int channel, const int* top,
+                         const float* Rs, const float* ts, int b, int n_hyp, int n_keep, float* R_out, float* t_out,
+                         float* score_out, int* pool_idx_out, upk_stream_t stream);
+/* Generic all-gather of `bytes` (multiple of 16) per rank: src -> every rank's data[r] + data_offset + slab * slab_bytes
+ * + rank * bytes, then publish; upk_peer_wait blocks the stream until every rank has published and (optionally) copies
+ * the gathered world * bytes out of the slab into dst (may be NULL). */
+int upk_peer_all_gather(const void* src, size_t bytes, const upk_peer_t* peer, size_t data_offset, size_t slab_bytes,
+                        int channel, upk_stream_t stream);
+int upk_peer_wait(const upk_peer_t* peer, size_t data_offset, size_t slab_bytes, int channel, void* dst, size_t bytes,
+                  upk_stream_t stream);
+
 /* ------------------------------------------------------------------------- *
  * fine pose — compute_fine_Rt[_overlap], model_utils.py:493-566
  * ------------------------------------------------------------------------- */

@@ -50,6 +50,16 @@ _SIGNATURES = {
     "upk_fill_f32": [c_f, c_sz, c_fl, c_st],
     "upk_pack_candidates": [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_f, c_st],
     "upk_unpack_candidates": [c_f, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_f, c_st],
+    # peer exchange (the upk_peer_t* is passed with ctypes.byref(peer.PeerStruct))
+    "upk_pack_candidates_peer": [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, ctypes.c_void_p, ctypes.c_size_t,
+                                 ctypes.c_size_t, c_i, c_st],
+    "upk_unpack_candidates_peer": [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, c_i, c_i, c_i, c_i, c_f, c_f, c_f, c_st],
+    "upk_score_hypotheses_peer": [c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_i, ctypes.c_void_p,
+                                  ctypes.c_size_t, ctypes.c_size_t, c_i, c_st],
+    "upk_select_best_peer": [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, c_i, c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_f,
+                             c_f, c_f, c_st],
+    "upk_peer_all_gather": [c_f, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, c_i, c_st],
+    "upk_peer_wait": [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, c_i, c_f, ctypes.c_size_t, c_st],
     "upk_fine_pose": [c_f, c_f, c_i, c_f, c_i, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_fl, c_fl,
                       c_f, c_sz, c_f, c_f, c_f, c_f, c_st],
     "upk_feature_similarity_stats": [c_f, c_f, c_i, c_i, c_i, c_i, c_fl, c_f, c_sz, c_f, c_f, c_sz, c_st],

@@ -8,6 +8,7 @@
 
 #include "common.cuh"
 #include "launch_count.h"
+#include "peer.cuh"
 #include "pose_internal.h"
 #include "solver3.cuh"
 #include "../../include/unopose_b200.h"
@@ -240,10 +241,13 @@ constexpr int SC_THREADS = 224;  // 7 warps: one query point per thread at n1 = 
 // SC_HPC kept hypotheses per CTA: the staged model and every LDS.128 of the scan serve both
 constexpr int SC_HPC = 2;
 
+// PEER: the scores go into EVERY rank's score table (peer stores) and the last CTA publishes the channel (peer.cuh)
+template <bool PEER>
 __global__ void __launch_bounds__(SC_THREADS, 4)
 k_score(const float* __restrict__ pts1, const float* __restrict__ model, const float* __restrict__ w1,
         const float* __restrict__ Rs, const float* __restrict__ ts, const int* __restrict__ top,
-        int n1, int nm, int H, int K, int k0, int k1, float* __restrict__ scores) {
+        int n1, int nm, int H, int K, int k0, int k1, float* __restrict__ scores,
+        const PeerCtx pc, size_t peer_off, size_t slab_bytes, int channel) {
   extern __shared__ __align__(16) float sm_model[];  // 4 x nm_pad (SoA x | y | z | |y|^2)
   __shared__ double s_red[2 * SC_HPC][SC_THREADS / 32];
   const int b = blockIdx.y;
@@ -298,24 +302,43 @@ k_score(const float* __restrict__ pts1, const float* __restrict__ model, const f
   if (threadIdx.x == 0) {
     double n = 0.0, da = 0.0, db = 0.0;
     for (int w = 0; w < SC_THREADS / 32; ++w) { n += s_red[0][w]; da += s_red[1][w]; db += s_red[2][w]; }
-    scores[(size_t)b * K + ka] = (float)n / ((float)da + 1e-8f);
-    if (ka + 1 < k1) scores[(size_t)b * K + ka + 1] = (float)n / ((float)db + 1e-8f);
+    const float sa = (float)n / ((float)da + 1e-8f), sb = (float)n / ((float)db + 1e-8f);
+    if (!PEER) {
+      scores[(size_t)b * K + ka] = sa;
+      if (ka + 1 < k1) scores[(size_t)b * K + ka + 1] = sb;
+    } else {
+      const size_t o = peer_off + ((pc.epoch[channel] + 1) & 1) * slab_bytes;
+      for (int r = 0; r < pc.world; ++r) {
+        float* d = reinterpret_cast<float*>(pc.data[r] + o);
+        d[(size_t)b * K + ka] = sa;
+        if (ka + 1 < k1) d[(size_t)b * K + ka + 1] = sb;
+      }
+    }
   }
+  if (PEER) peer_publish(pc, channel, pc.epoch[channel] + 1, gridDim.x * gridDim.y);
 }
 
 // arg-max over the K kept hypotheses (first maximum), gather R, t, score, pool index (:486-488)
+// PEER: `scores` is the local copy of the exchanged score table; wait until every rank has stored its slice
+template <bool PEER>
 __global__ void __launch_bounds__(256)
 k_select(const float* __restrict__ scores, const int* __restrict__ top, const float* __restrict__ Rs,
          const float* __restrict__ ts, int H, int K, float* __restrict__ R_out, float* __restrict__ t_out,
-         float* __restrict__ score_out, int* __restrict__ pool_out) {
+         float* __restrict__ score_out, int* __restrict__ pool_out,
+         const PeerCtx pc, size_t peer_off, size_t slab_bytes, int channel) {
   __shared__ float s_v[8];
   __shared__ int s_i[8];
   const int b = blockIdx.x;
+  if (PEER) {
+    const unsigned long long e = pc.epoch[channel];
+    peer_wait(pc, channel, e);
+    scores = reinterpret_cast<const float*>(pc.data[pc.rank] + peer_off + (e & 1) * slab_bytes);
+  }
   float bv = -INFINITY;
   int bi = 0x7fffffff;
   bool seen_nan = false;
   for (int k = threadIdx.x; k < K; k += 256) {
-    float v = scores[(size_t)b * K + k];
+    float v = PEER ? __ldcg(scores + (size_t)b * K + k) : scores[(size_t)b * K + k];
     if (v != v) { if (!seen_nan) { seen_nan = true; bv = v; bi = k; } continue; }
     if (!seen_nan && (v > bv || (v == bv && k < bi))) { bv = v; bi = k; }
   }
@@ -355,45 +378,73 @@ k_select(const float* __restrict__ scores, const int* __restrict__ top, const fl
 // bits), R (9), t (3)} = 14 floats.
 constexpr int CAND_F = 14;
 
+// PEER: the record goes into slot [rank] of EVERY rank's gathered[world][b][kc][14] array, then the channel is published
+template <bool PEER>
 __global__ void __launch_bounds__(128)
 k_pack_candidates(const float* __restrict__ resid, const float* __restrict__ Rs, const float* __restrict__ ts,
-                  const int* __restrict__ top_local, int h0, int H, int kl, int kc, float* __restrict__ cand) {
+                  const int* __restrict__ top_local, int h0, int H, int kl, int kc, float* __restrict__ cand,
+                  const PeerCtx pc, size_t peer_off, size_t slab_bytes, int channel) {
   const int b = blockIdx.y;
   const int j = blockIdx.x * 128 + threadIdx.x;
-  if (j >= kc) return;
-  float* o = cand + ((size_t)b * kc + j) * CAND_F;
-  if (j < kl) {
-    const int h = h0 + top_local[(size_t)b * kl + j];
-    o[0] = resid[(size_t)b * H + h];
-    o[1] = __int_as_float(h);
+  if (j < kc) {
+    float rec[CAND_F];
+    if (j < kl) {
+      const int h = h0 + top_local[(size_t)b * kl + j];
+      rec[0] = resid[(size_t)b * H + h];
+      rec[1] = __int_as_float(h);
 #pragma unroll
-    for (int i = 0; i < 9; ++i) o[2 + i] = Rs[((size_t)b * H + h) * 9 + i];
+      for (int i = 0; i < 9; ++i) rec[2 + i] = Rs[((size_t)b * H + h) * 9 + i];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) o[11 + i] = ts[((size_t)b * H + h) * 3 + i];
-  } else {
-    o[0] = INFINITY;
-    o[1] = __int_as_float(-1);
+      for (int i = 0; i < 3; ++i) rec[11 + i] = ts[((size_t)b * H + h) * 3 + i];
+    } else {
+      rec[0] = INFINITY;
+      rec[1] = __int_as_float(-1);
 #pragma unroll
-    for (int i = 2; i < CAND_F; ++i) o[i] = 0.f;
+      for (int i = 2; i < CAND_F; ++i) rec[i] = 0.f;
+    }
+    if (!PEER) {
+      float* o = cand + ((size_t)b * kc + j) * CAND_F;
+#pragma unroll
+      for (int i = 0; i < CAND_F; ++i) o[i] = rec[i];
+    } else {
+      const size_t o = peer_off + ((pc.epoch[channel] + 1) & 1) * slab_bytes +
+                       ((((size_t)pc.rank * gridDim.y + b) * kc + j) * CAND_F) * sizeof(float);
+      for (int r = 0; r < pc.world; ++r) {
+        float2* d = reinterpret_cast<float2*>(pc.data[r] + o);     // records are 56 bytes: 8-byte aligned
+#pragma unroll
+        for (int i = 0; i < CAND_F / 2; ++i) d[i] = make_float2(rec[2 * i], rec[2 * i + 1]);
+      }
+    }
   }
+  if (PEER) peer_publish(pc, channel, pc.epoch[channel] + 1, gridDim.x * gridDim.y);
 }
 
+template <bool PEER>
 __global__ void __launch_bounds__(128)
 k_unpack_candidates(const float* __restrict__ allc /* [world][b][kc][14] */, int world, int skip_rank, int nb, int H,
-                    int kc, float* __restrict__ resid, float* __restrict__ Rs, float* __restrict__ ts) {
+                    int kc, float* __restrict__ resid, float* __restrict__ Rs, float* __restrict__ ts,
+                    const PeerCtx pc, size_t peer_off, size_t slab_bytes, int channel) {
+  if (PEER) {   // the local copy of the exchanged array, once every rank has stored its list
+    const unsigned long long e = pc.epoch[channel];
+    peer_wait(pc, channel, e);
+    allc = reinterpret_cast<const float*>(pc.data[pc.rank] + peer_off + (e & 1) * slab_bytes);
+  }
   const int b = blockIdx.y;
   const int q = blockIdx.x * 128 + threadIdx.x;   // (rank, j)
   if (q >= world * kc) return;
   const int r = q / kc, j = q - r * kc;
   if (r == skip_rank) return;                     // my own slice is already in place
   const float* c = allc + (((size_t)r * nb + b) * kc + j) * CAND_F;
-  const int h = __float_as_int(c[1]);
+  float rec[CAND_F];
+#pragma unroll
+  for (int i = 0; i < CAND_F; ++i) rec[i] = PEER ? __ldcg(c + i) : c[i];
+  const int h = __float_as_int(rec[1]);
   if (h < 0 || h >= H) return;
-  resid[(size_t)b * H + h] = c[0];
+  resid[(size_t)b * H + h] = rec[0];
 #pragma unroll
-  for (int i = 0; i < 9; ++i) Rs[((size_t)b * H + h) * 9 + i] = c[2 + i];
+  for (int i = 0; i < 9; ++i) Rs[((size_t)b * H + h) * 9 + i] = rec[2 + i];
 #pragma unroll
-  for (int i = 0; i < 3; ++i) ts[((size_t)b * H + h) * 3 + i] = c[11 + i];
+  for (int i = 0; i < 3; ++i) ts[((size_t)b * H + h) * 3 + i] = rec[11 + i];
 }
 
 __global__ void __launch_bounds__(256)
@@ -425,14 +476,23 @@ static void carve_coarse(Carver& cv, int b, int n1, int n2, int H, int K, const 
 
 static int launch_score(const float* pts1, const float* model, const float* w1, const float* Rs,
                         const float* ts, const int* top, int b, int n1, int nm, int H, int K, int k0, int k1,
-                        float* scores, cudaStream_t st) {
-  if (k1 <= k0) return UPK_OK;
+                        float* scores, cudaStream_t st, const upk_peer_t* peer = nullptr, size_t peer_off = 0,
+                        size_t slab_bytes = 0, int channel = 0) {
+  if (k1 <= k0 && !peer) return UPK_OK;
   size_t smem = (size_t)((nm + 3) & ~3) * 4 * sizeof(float);
   if (smem > 200 * 1024) return UPK_ERR_UNSUPPORTED;
-  if (smem > 40 * 1024)
-    UPK_CUDA_TRY(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(ceil_div(k1 - k0, SC_HPC), b);
-  k_score<<<grid, SC_THREADS, smem, st>>>(pts1, model, w1, Rs, ts, top, n1, nm, H, K, k0, k1, scores);
+  if (peer) {
+    if (k1 <= k0) return UPK_ERR_INVALID_ARG;   // every rank must publish: the host gives each rank a non-empty slice
+    if (smem > 40 * 1024)
+      UPK_CUDA_TRY(cudaFuncSetAttribute(k_score<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_score<true><<<grid, SC_THREADS, smem, st>>>(pts1, model, w1, Rs, ts, top, n1, nm, H, K, k0, k1, nullptr,
+                                                  make_peer_ctx(peer), peer_off, slab_bytes, channel);
+  } else {
+    if (smem > 40 * 1024)
+      UPK_CUDA_TRY(cudaFuncSetAttribute(k_score<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_score<false><<<grid, SC_THREADS, smem, st>>>(pts1, model, w1, Rs, ts, top, n1, nm, H, K, k0, k1, scores, PeerCtx(), 0, 0, 0);
+  }
   count_launch();
   UPK_RETURN_LAST_ERROR();
 }
@@ -491,7 +551,8 @@ int upk_coarse_pose(const float* atten, const float* score1, int score1_ld, cons
   if ((rc = launch_score(pts1, model_pts, w.w1, w.Rs, w.ts, w.top, b, n1, n_model, n_hyp, n_keep, 0, n_keep,
                          w.scores, st)))
     return rc;
-  k_select<<<b, 256, 0, st>>>(w.scores, w.top, w.Rs, w.ts, n_hyp, n_keep, R_out, t_out, score_out, pool_idx_out);
+  k_select<false><<<b, 256, 0, st>>>(w.scores, w.top, w.Rs, w.ts, n_hyp, n_keep, R_out, t_out, score_out, pool_idx_out,
+                                     PeerCtx(), 0, 0, 0);
   count_launch();
   if (dbg) {
     // optional copies of the intermediates for stage-wise parity tests
@@ -598,8 +659,8 @@ int upk_pack_candidates(const float* resid, const float* Rs, const float* ts, co
   if (b < 0 || n_hyp <= 0 || h_begin < 0 || n_local < 0 || n_slots < n_local || n_slots <= 0) return UPK_ERR_INVALID_ARG;
   if (b == 0) return UPK_OK;
   if (!resid || !Rs || !ts || !cand_out || (n_local > 0 && !top_local)) return UPK_ERR_INVALID_ARG;
-  k_pack_candidates<<<dim3(ceil_div(n_slots, 128), b), 128, 0, (cudaStream_t)stream>>>(resid, Rs, ts, top_local, h_begin,
-                                                                                     n_hyp, n_local, n_slots, cand_out);
+  k_pack_candidates<false><<<dim3(ceil_div(n_slots, 128), b), 128, 0, (cudaStream_t)stream>>>(
+      resid, Rs, ts, top_local, h_begin, n_hyp, n_local, n_slots, cand_out, PeerCtx(), 0, 0, 0);
   count_launch();
   UPK_RETURN_LAST_ERROR();
 }
@@ -609,8 +670,8 @@ int upk_unpack_candidates(const float* gathered, int world, int my_rank, int b, 
   if (world <= 0 || b < 0 || n_hyp <= 0 || n_slots <= 0) return UPK_ERR_INVALID_ARG;
   if (b == 0) return UPK_OK;
   if (!gathered || !resid || !Rs || !ts) return UPK_ERR_INVALID_ARG;
-  k_unpack_candidates<<<dim3(ceil_div(world * n_slots, 128), b), 128, 0, (cudaStream_t)stream>>>(
-      gathered, world, my_rank, b, n_hyp, n_slots, resid, Rs, ts);
+  k_unpack_candidates<false><<<dim3(ceil_div(world * n_slots, 128), b), 128, 0, (cudaStream_t)stream>>>(
+      gathered, world, my_rank, b, n_hyp, n_slots, resid, Rs, ts, PeerCtx(), 0, 0, 0);
   count_launch();
   UPK_RETURN_LAST_ERROR();
 }
@@ -620,8 +681,56 @@ int upk_select_best(const float* scores, const int* top, const float* Rs, const 
                     upk_stream_t stream) {
   if (b < 0 || n_hyp <= 0 || n_keep <= 0) return UPK_ERR_INVALID_ARG;
   if (b == 0) return UPK_OK;
-  k_select<<<b, 256, 0, (cudaStream_t)stream>>>(scores, top, Rs, ts, n_hyp, n_keep, R_out, t_out, score_out,
-                                                pool_idx_out);
+  k_select<false><<<b, 256, 0, (cudaStream_t)stream>>>(scores, top, Rs, ts, n_hyp, n_keep, R_out, t_out, score_out,
+                                                       pool_idx_out, PeerCtx(), 0, 0, 0);
+  count_launch();
+  UPK_RETURN_LAST_ERROR();
+}
+
+// ---- peer-exchange forms (fused compute + all-gather over NVLink peer memory; csrc/peer.cuh) ----
+
+int upk_pack_candidates_peer(const float* resid, const float* Rs, const float* ts, const int* top_local, int b, int n_hyp,
+                             int h_begin, int n_local, int n_slots, const upk_peer_t* peer, size_t data_offset,
+                             size_t slab_bytes, int channel, upk_stream_t stream) {
+  if (b <= 0 || n_hyp <= 0 || h_begin < 0 || n_local < 0 || n_slots < n_local || n_slots <= 0) return UPK_ERR_INVALID_ARG;
+  if (!resid || !Rs || !ts || (n_local > 0 && !top_local) || !peer_ctx_ok(peer, channel)) return UPK_ERR_INVALID_ARG;
+  if ((data_offset | slab_bytes) & 15) return UPK_ERR_INVALID_ARG;
+  if ((size_t)peer->world * b * n_slots * CAND_F * sizeof(float) > slab_bytes) return UPK_ERR_INVALID_ARG;
+  k_pack_candidates<true><<<dim3(ceil_div(n_slots, 128), b), 128, 0, (cudaStream_t)stream>>>(
+      resid, Rs, ts, top_local, h_begin, n_hyp, n_local, n_slots, nullptr, make_peer_ctx(peer), data_offset, slab_bytes,
+      channel);
+  count_launch();
+  UPK_RETURN_LAST_ERROR();
+}
+
+int upk_unpack_candidates_peer(const upk_peer_t* peer, size_t data_offset, size_t slab_bytes, int channel, int b, int n_hyp,
+                               int n_slots, float* resid, float* Rs, float* ts, upk_stream_t stream) {
+  if (b <= 0 || n_hyp <= 0 || n_slots <= 0 || !resid || !Rs || !ts || !peer_ctx_ok(peer, channel)) return UPK_ERR_INVALID_ARG;
+  k_unpack_candidates<true><<<dim3(ceil_div(peer->world * n_slots, 128), b), 128, 0, (cudaStream_t)stream>>>(
+      nullptr, peer->world, peer->rank, b, n_hyp, n_slots, resid, Rs, ts, make_peer_ctx(peer), data_offset, slab_bytes,
+      channel);
+  count_launch();
+  UPK_RETURN_LAST_ERROR();
+}
+
+int upk_score_hypotheses_peer(const float* pts1, const float* model_pts, const float* w1, const float* Rs, const float* ts,
+                              const int* top, int b, int n1, int n_model, int n_hyp, int n_keep, int k_begin, int k_end,
+                              const upk_peer_t* peer, size_t data_offset, size_t slab_bytes, int channel,
+                              upk_stream_t stream) {
+  if (b <= 0 || n1 <= 0 || n_model <= 0 || n_hyp <= 0 || n_keep <= 0 || k_begin < 0 || k_end > n_keep ||
+      k_begin >= k_end || !peer_ctx_ok(peer, channel))
+    return UPK_ERR_INVALID_ARG;
+  if (((data_offset | slab_bytes) & 15) || (size_t)b * n_keep * sizeof(float) > slab_bytes) return UPK_ERR_INVALID_ARG;
+  return launch_score(pts1, model_pts, w1, Rs, ts, top, b, n1, n_model, n_hyp, n_keep, k_begin, k_end, nullptr,
+                      (cudaStream_t)stream, peer, data_offset, slab_bytes, channel);
+}
+
+int upk_select_best_peer(const upk_peer_t* peer, size_t data_offset, size_t slab_bytes, int channel, const int* top,
+                         const float* Rs, const float* ts, int b, int n_hyp, int n_keep, float* R_out, float* t_out,
+                         float* score_out, int* pool_idx_out, upk_stream_t stream) {
+  if (b <= 0 || n_hyp <= 0 || n_keep <= 0 || !peer_ctx_ok(peer, channel)) return UPK_ERR_INVALID_ARG;
+  k_select<true><<<b, 256, 0, (cudaStream_t)stream>>>(nullptr, top, Rs, ts, n_hyp, n_keep, R_out, t_out, score_out,
+                                                      pool_idx_out, make_peer_ctx(peer), data_offset, slab_bytes, channel);
   count_launch();
   UPK_RETURN_LAST_ERROR();
 }

@@ -17,6 +17,7 @@
 // tile apart so one group's epilogues overlap the other's MMAs.  The folded weights (84 KB, hi + lo) stay resident.
 #include <cuda.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "launch_count.h"
@@ -279,6 +280,259 @@ k_shared_mlp_max(const float* __restrict__ x, int cin, int c1, int c2, int c3, i
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Four tile slots (round 2).  With two slots the tensor pipe was 20-23 % active: a tile's chain
+//   load -> [L1] -> epilogue -> [L2] -> epilogue -> [L3] -> epilogue
+// is serial (each arrow is a commit -> mbarrier -> TMEM-load round trip) and two chains hide only half of it.  Operand
+// space, not threads, was the limit: A3 (128 x 64, hi + lo) is 64 KB per slot.  Here L3 runs in two K halves, so a slot
+// only ever holds TWO 16-wide operand chunks (32 KB): epilogue 2 writes A3 chunks 0-1, keeps the other 32 activations of
+// its row in registers, and writes chunks 2-3 into the same ring once L3a has retired.  The accumulators of a slot
+// share 128 TMEM columns (D1 [0,32), D2 [32,96), D3 [0,128) — D3 is first written after D2 has been read completely).
+// 4 slots x 32 KB + 84 KB of weights = 212 KB of shared memory, 4 x 128 = 512 TMEM columns, 18 warps; the MMA warp
+// polls the four slots' barriers and issues whatever is ready.  The max over the ball uses REDUX on the non-negative
+// bit patterns instead of a shared-memory transpose.
+constexpr int PM_SLOTS = 4;
+constexpr int PM4_THREADS = 64 + PM_SLOTS * 128;
+
+struct __align__(1024) Pm4Smem {
+  float w1_hi[PM_C1 * TC_BK], w1_lo[PM_C1 * TC_BK];
+  float w2_hi[PM_C1 / 16][PM_C2 * TC_BK], w2_lo[PM_C1 / 16][PM_C2 * TC_BK];
+  float w3_hi[PM_C2 / 16][PM_C3 * TC_BK], w3_lo[PM_C2 / 16][PM_C3 * TC_BK];
+  float a_hi[PM_SLOTS][2][PM_TILE], a_lo[PM_SLOTS][2][PM_TILE];          // per slot: a ring of two operand chunks
+  float red[PM_SLOTS][4][PM_C3];
+  float b1[PM_C1], b2[PM_C2], b3[PM_C3];
+  unsigned long long a_ready[PM_SLOTS], d_ready[PM_SLOTS];
+  uint32_t tmem_base;
+};
+static_assert(sizeof(Pm4Smem) + 1024 <= 227 * 1024, "Pm4Smem must fit the 227 KB of a CTA");
+
+__device__ __forceinline__ bool mbar_test(void* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
+template <bool CIN16>
+__global__ void __launch_bounds__(PM4_THREADS, 1)
+k_shared_mlp_max4(const float* __restrict__ x, int cin, int c1, int c2, int c3, int m, int ns, long long total_tiles,
+                  const float* __restrict__ w1, const float* __restrict__ bb1, const float* __restrict__ w2,
+                  const float* __restrict__ bb2, const float* __restrict__ w3, const float* __restrict__ bb3,
+                  float* out) {
+  extern __shared__ unsigned char smem_raw[];
+  Pm4Smem& sm = *reinterpret_cast<Pm4Smem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long rpb = (long long)m * ns;
+  const int k3 = c2 / 16;                 // A3 chunks: 2 or 4
+  const bool two_halves = k3 > 2;         // L3 in two K halves (both sides of the hand-off derive this identically)
+
+  if (threadIdx.x == 0) {
+    for (int g = 0; g < PM_SLOTS; ++g) { mbar_init(&sm.a_ready[g], 4); mbar_init(&sm.d_ready[g], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  {
+    // stage the folded weights (hi + lo, UMMA SWIZZLE_64B layout); same helper as the two-slot kernel, other stride
+    auto stage = [&](const float* w, int cout, int kin, int chunks, float* hi, float* lo, int chunk_floats) {
+      const int kpad = chunks * 16;
+      for (int i = threadIdx.x; i < cout * kpad; i += PM4_THREADS) {
+        const int row = i / kpad, k = i - row * kpad;
+        const float v = k < kin ? w[row * kin + k] : 0.f;
+        const float h = pm_tf32(v);
+        const int o = (k >> 4) * chunk_floats + pm_off(row, k & 15);
+        hi[o] = h;
+        lo[o] = v - h;
+      }
+    };
+    stage(w1, c1, cin, 1, sm.w1_hi, sm.w1_lo, PM_C1 * TC_BK);
+    stage(w2, c2, c1, c1 / 16, &sm.w2_hi[0][0], &sm.w2_lo[0][0], PM_C2 * TC_BK);
+    stage(w3, c3, c2, c2 / 16, &sm.w3_hi[0][0], &sm.w3_lo[0][0], PM_C3 * TC_BK);
+  }
+  for (int t = threadIdx.x; t < c1; t += PM4_THREADS) sm.b1[t] = bb1[t];
+  for (int t = threadIdx.x; t < c2; t += PM4_THREADS) sm.b2[t] = bb2[t];
+  for (int t = threadIdx.x; t < c3; t += PM4_THREADS) sm.b3[t] = bb3[t];
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sm.tmem_base;
+
+  if (warp == 1) {
+    // ===== MMA issuer: polls the slots, issues the next phase of whichever slot has handed its operand over =====
+    const uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BM >> 4) << 24);
+    const int nph = two_halves ? 4 : 3;
+    uint32_t par_a[PM_SLOTS];
+    int phase[PM_SLOTS];
+    long long tile[PM_SLOTS];
+    int live = 0;
+#pragma unroll
+    for (int g = 0; g < PM_SLOTS; ++g) {
+      par_a[g] = 0u;
+      phase[g] = 0;
+      tile[g] = blockIdx.x + (long long)g * gridDim.x;
+      live += tile[g] < total_tiles;
+    }
+    while (live > 0) {
+#pragma unroll
+      for (int g = 0; g < PM_SLOTS; ++g) {
+        if (tile[g] >= total_tiles) continue;
+        if (!mbar_test(&sm.a_ready[g], par_a[g])) continue;
+        par_a[g] ^= 1u;
+        tc_fence_after();
+        const int ph = phase[g];
+        if (lane == 0) {
+          const int n_out = ph == 0 ? c1 : (ph == 1 ? c2 : c3);
+          const uint32_t idesc = idesc_base | ((uint32_t)(n_out >> 3) << 17);
+          const uint32_t d_tmem = tmem_base + g * 128 + (ph == 1 ? PM_C1 : 0);
+          const int kc0 = ph == 3 ? 2 : 0;
+          const int kc1 = ph == 0 ? 1 : (ph == 1 ? c1 / 16 : (ph == 2 ? (k3 < 2 ? k3 : 2) : k3));
+          const int ksteps = ph == 0 ? (cin > 8 ? 2 : 1) : 2;
+          for (int kc = kc0; kc < kc1; ++kc) {
+            const float* bh = ph == 0 ? sm.w1_hi : (ph == 1 ? sm.w2_hi[kc] : sm.w3_hi[kc]);
+            const float* bl = ph == 0 ? sm.w1_lo : (ph == 1 ? sm.w2_lo[kc] : sm.w3_lo[kc]);
+            const uint64_t ahi = make_desc_sw128(sm.a_hi[g][kc - kc0]), alo = make_desc_sw128(sm.a_lo[g][kc - kc0]);
+            const uint64_t bhi = make_desc_sw128(bh), blo = make_desc_sw128(bl);
+            for (int kk = 0; kk < ksteps; ++kk) {
+              const uint64_t adv = (uint64_t)(kk * 8 * 4 >> 4);
+              tc_mma_tf32(d_tmem, alo + adv, bhi + adv, idesc, (ph == 3 || kc > kc0 || kk) ? 1u : 0u);
+              tc_mma_tf32(d_tmem, ahi + adv, blo + adv, idesc, 1u);
+              tc_mma_tf32(d_tmem, ahi + adv, bhi + adv, idesc, 1u);
+            }
+          }
+          tc_commit(&sm.d_ready[g]);
+        }
+        __syncwarp();
+        if (++phase[g] == nph) {
+          phase[g] = 0;
+          tile[g] += (long long)PM_SLOTS * gridDim.x;
+          live -= tile[g] >= total_tiles;
+        }
+      }
+    }
+  } else if (warp >= 2) {
+    // ===== tile-slot groups: thread = one sample (row of the tile = TMEM lane) =====
+    const int g = (warp - 2) >> 2;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int sw = (row >> 1) & 3;
+    const int gt = threadIdx.x - 64 - 128 * g;
+    const uint32_t tq = tmem_base + g * 128 + ((uint32_t)(q * 32) << 16);
+    const int cpt = ns >= 128 ? 1 : 128 / ns;
+    const int qpc = 4 / cpt;
+    uint32_t par_d = 0;
+    constexpr int NV = CIN16 ? 16 : 8;
+    float v[NV];
+    auto load_tile = [&](long long t) {
+      const long long R0 = t * 128;
+      const long long b = R0 / rpb, rib = R0 - b * rpb;
+#pragma unroll
+      for (int c = 0; c < NV; ++c) v[c] = c < cin ? __ldg(x + ((size_t)b * cin + c) * rpb + rib + row) : 0.f;
+    };
+    auto wait_d = [&]() {
+      mbar_wait(&sm.d_ready[g], par_d);
+      par_d ^= 1u;
+      tc_fence_after();
+    };
+    {
+      const long long t0 = blockIdx.x + (long long)g * gridDim.x;
+      if (t0 < total_tiles) load_tile(t0);
+    }
+    for (long long t = blockIdx.x + (long long)g * gridDim.x; t < total_tiles; t += (long long)PM_SLOTS * gridDim.x) {
+      const long long R0 = t * 128;
+      const long long b = R0 / rpb, rib = R0 - b * rpb;
+      // ---- A1 -> ring chunk 0
+      {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          float h[4], a[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            a[e] = (4 * p + e < NV) ? v[(4 * p + e) % NV] : 0.f;
+            h[e] = pm_tf32(a[e]);
+          }
+          const int o = row * 16 + ((p ^ sw) << 2);
+          *reinterpret_cast<float4*>(&sm.a_hi[g][0][o]) = make_float4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<float4*>(&sm.a_lo[g][0][o]) = make_float4(a[0] - h[0], a[1] - h[1], a[2] - h[2], a[3] - h[3]);
+        }
+        const long long tn = t + (long long)PM_SLOTS * gridDim.x;
+        if (tn < total_tiles) load_tile(tn);
+      }
+      pm_group_handoff(&sm.a_ready[g], lane);
+      // ---- epilogue 1: D1 -> A2 (ring chunks 0..c1/16-1)
+      wait_d();
+      {
+        uint32_t r[32];
+        tmem_ld_32x32(tq, r);
+#pragma unroll
+        for (int kc = 0; kc < PM_C1 / 16; ++kc)
+          if (kc * 16 < c1) pm_store16(r + 16 * kc, sm.b1 + 16 * kc, sm.a_hi[g][kc], sm.a_lo[g][kc], row, sw);
+      }
+      pm_group_handoff(&sm.a_ready[g], lane);
+      // ---- epilogue 2: D2 -> A3 chunks 0-1 now, chunks 2-3 (kept in registers) once L3a has retired
+      wait_d();
+      {
+        uint32_t r[32], r2[32];
+        tmem_ld_32x32(tq + PM_C1, r);
+        if (two_halves) tmem_ld_32x32(tq + PM_C1 + 32, r2);
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) pm_store16(r + 16 * h2, sm.b2 + 16 * h2, sm.a_hi[g][h2], sm.a_lo[g][h2], row, sw);
+        pm_group_handoff(&sm.a_ready[g], lane);
+        if (two_halves) {
+          wait_d();                                   // L3a has read ring chunks 0-1 (and may have overwritten D2)
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2)
+            pm_store16(r2 + 16 * h2, sm.b2 + 32 + 16 * h2, sm.a_hi[g][h2], sm.a_lo[g][h2], row, sw);
+          pm_group_handoff(&sm.a_ready[g], lane);
+        }
+      }
+      // ---- epilogue 3: D3 -> relu -> max over the 32 samples of this quarter (REDUX on the bit patterns) -> red[q][col]
+      wait_d();
+#pragma unroll 1
+      for (int cb = 0; cb * 32 < c3; ++cb) {
+        uint32_t r[32];
+        tmem_ld_32x32(tq + cb * 32, r);
+        unsigned mine = 0u;
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) {
+          const float a = __uint_as_float(r[jj]) + sm.b3[cb * 32 + jj];
+          const unsigned mx = __reduce_max_sync(0xffffffffu, __float_as_uint(a > 0.f ? a : 0.f));
+          if (jj == lane) mine = mx;
+        }
+        sm.red[g][q][cb * 32 + lane] = __uint_as_float(mine);
+      }
+      tc_fence_before();
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+      if (gt < c3) {
+        for (int s = 0; s < cpt; ++s) {
+          float mx = sm.red[g][s * qpc][gt];
+          for (int qq = 1; qq < qpc; ++qq) mx = fmaxf(mx, sm.red[g][s * qpc + qq][gt]);
+          const long long ball = (rib + (long long)s * (128 / cpt)) / ns;
+          float* dst = out + ((size_t)b * c3 + gt) * m + ball;
+          if (ns <= 128) *dst = mx;
+          else atomicMax(reinterpret_cast<int*>(dst), __float_as_int(mx));
+        }
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
 }  // namespace upk
 
 using namespace upk;
@@ -306,10 +560,23 @@ extern "C" int upk_shared_mlp_max(const float* x, int b, int cin, int m, int ns,
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long long tiles = (long long)b * m * ns / 128;
-  const size_t smem = sizeof(PmSmem) + 1024;
-  UPK_CUDA_TRY(cudaFuncSetAttribute(k_shared_mlp_max, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_shared_mlp_max<<<(int)(tiles < sms ? tiles : sms), PM_THREADS, smem, st>>>(x, cin, c1, c2, c3, m, ns, tiles, w1, b1,
-                                                                             w2, b2, w3, b3, out);
+  static int slots = -1;   // UPK_PE_MLP_SLOTS=2 selects the round-1 two-slot kernel (A/B measurements)
+  if (slots < 0) { const char* e = getenv("UPK_PE_MLP_SLOTS"); slots = e ? atoi(e) : PM_SLOTS; }
+  const int grid = (int)(tiles < sms ? tiles : sms);
+  if (slots == 2) {
+    const size_t smem = sizeof(PmSmem) + 1024;
+    UPK_CUDA_TRY(cudaFuncSetAttribute(k_shared_mlp_max, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_shared_mlp_max<<<grid, PM_THREADS, smem, st>>>(x, cin, c1, c2, c3, m, ns, tiles, w1, b1, w2, b2, w3, b3, out);
+  } else {
+    const size_t smem = sizeof(Pm4Smem) + 1024;
+    if (cin > 8) {
+      UPK_CUDA_TRY(cudaFuncSetAttribute(k_shared_mlp_max4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_shared_mlp_max4<true><<<grid, PM4_THREADS, smem, st>>>(x, cin, c1, c2, c3, m, ns, tiles, w1, b1, w2, b2, w3, b3, out);
+    } else {
+      UPK_CUDA_TRY(cudaFuncSetAttribute(k_shared_mlp_max4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_shared_mlp_max4<false><<<grid, PM4_THREADS, smem, st>>>(x, cin, c1, c2, c3, m, ns, tiles, w1, b1, w2, b2, w3, b3, out);
+    }
+  }
   count_launch();
   UPK_RETURN_LAST_ERROR();
 }

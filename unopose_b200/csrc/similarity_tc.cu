@@ -61,13 +61,31 @@ constexpr int NS_RPW = 4;   // rows per warp -> 32 rows per CTA
 // 3xTF32) at twice the MMA rate and half the operand bytes.
 constexpr float kF16Scale = 4096.0f;
 
+// Both operands are prepared by ONE launch (blockIdx.z selects the operand): the two preparations are independent and
+// each alone is a ~10 us launch whose tail and launch latency were serialised on the stream.
+struct NsOperand {
+  const float* x;       // (batch, rows, c)
+  int rows;
+  float* hi;
+  float* lo;
+  const float* other;   // BORDER: the other operand (its row 0 is the background token), or null
+  int other_rows;
+  int is_a;
+};
+
 template <int MODE, bool F16 = false>
 __global__ void __launch_bounds__(256)
-k_normalize_split(const float* __restrict__ x, int rows_per_batch, int c, int normalize,
-                  float* __restrict__ hi, float* __restrict__ lo,
-                  const float* __restrict__ other, int other_rows_per_batch, int is_a,
+k_normalize_split(const NsOperand opa, const NsOperand opb, int c, int normalize,
                   float temp, float* __restrict__ C, int M, int N, int ldc) {
   extern __shared__ float s_q[];   // BORDER: the normalised row 0 of the other operand (c floats)
+  const NsOperand& op = blockIdx.z ? opb : opa;
+  if ((int)blockIdx.x * 8 * NS_RPW >= op.rows) return;   // the grid covers the longer operand
+  const float* __restrict__ x = op.x;
+  const int rows_per_batch = op.rows;
+  float* __restrict__ hi = op.hi;
+  float* __restrict__ lo = op.lo;
+  const float* __restrict__ other = op.other;
+  const int other_rows_per_batch = op.other_rows, is_a = op.is_a;
   const int bidx = blockIdx.y;
   const int lane = threadIdx.x & 31;
   if (other) {
@@ -769,11 +787,11 @@ static int run_similarity_f16(const float* f1, const float* f2, int b, int n, in
   const int tiles2 = b * ((n - off + 2 * TC_BM - 1) / (2 * TC_BM)) * ((m - off + TC_BN - 1) / TC_BN);
   if (tiles2 < sms / 2) return 1;
   if (stats_row && !stats_col) return UPK_ERR_UNSUPPORTED;
-  const dim3 g1((n + 8 * NS_RPW - 1) / (8 * NS_RPW), b), g2((m + 8 * NS_RPW - 1) / (8 * NS_RPW), b);
+  const dim3 g12(((n > m ? n : m) + 8 * NS_RPW - 1) / (8 * NS_RPW), b, 2);
   const size_t qs = (size_t)c * sizeof(float);
-  k_normalize_split<0, true><<<g1, 256, qs, st>>>(f1, n, c, normalize, (float*)a_hi, (float*)a_lo, f2, m, 1, temp, out, n, m, ldc);
-  k_normalize_split<0, true><<<g2, 256, qs, st>>>(f2, m, c, normalize, (float*)b_hi, (float*)b_lo, f1, n, 0, temp, out, n, m, ldc);
-  count_launch(2);
+  const NsOperand oa{f1, n, (float*)a_hi, (float*)a_lo, f2, m, 1}, ob{f2, m, (float*)b_hi, (float*)b_lo, f1, n, 0};
+  k_normalize_split<0, true><<<g12, 256, qs, st>>>(oa, ob, c, normalize, temp, out, n, m, ldc);
+  count_launch(1);
   CUtensorMap fa_hi, fa_lo, fb_hi, fb_lo;
   int rc;
   if ((rc = make_map_f16(&fa_hi, a_hi, b, n, c, TC_BM))) return rc;
@@ -829,16 +847,12 @@ int run_similarity_tc(const float* f1, const float* f2, int b, int n, int m, int
   const int tiles1 = ((n - 1 + TC_BM - 1) / TC_BM) * ((m - 1 + TC_BN - 1) / TC_BN);
   const int off = (n > 1 && m > 1 && (tiles1 < tiles0 || stats_row)) ? 1 : 0;   // the statistics assume the peel
   if (stats_row && (!off || sim_type != 0 || !stats_col)) return UPK_ERR_UNSUPPORTED;
-  const dim3 g1((n + 8 * NS_RPW - 1) / (8 * NS_RPW), b), g2((m + 8 * NS_RPW - 1) / (8 * NS_RPW), b);
+  const dim3 g12(((n > m ? n : m) + 8 * NS_RPW - 1) / (8 * NS_RPW), b, 2);
   const size_t qs = off ? (size_t)c * sizeof(float) : 0;
-  if (sim_type == 0) {
-    k_normalize_split<0><<<g1, 256, qs, st>>>(f1, n, c, normalize, a_hi, a_lo, off ? f2 : nullptr, m, 1, temp, out, n, m, ldc);
-    k_normalize_split<0><<<g2, 256, qs, st>>>(f2, m, c, normalize, b_hi, b_lo, off ? f1 : nullptr, n, 0, temp, out, n, m, ldc);
-  } else {
-    k_normalize_split<1><<<g1, 256, qs, st>>>(f1, n, c, normalize, a_hi, a_lo, off ? f2 : nullptr, m, 1, temp, out, n, m, ldc);
-    k_normalize_split<1><<<g2, 256, qs, st>>>(f2, m, c, normalize, b_hi, b_lo, off ? f1 : nullptr, n, 0, temp, out, n, m, ldc);
-  }
-  count_launch(2);
+  const NsOperand oa{f1, n, a_hi, a_lo, off ? f2 : nullptr, m, 1}, ob{f2, m, b_hi, b_lo, off ? f1 : nullptr, n, 0};
+  if (sim_type == 0) k_normalize_split<0><<<g12, 256, qs, st>>>(oa, ob, c, normalize, temp, out, n, m, ldc);
+  else k_normalize_split<1><<<g12, 256, qs, st>>>(oa, ob, c, normalize, temp, out, n, m, ldc);
+  count_launch(1);
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int rc;
   if ((rc = make_map(&ma_hi, a_hi, b, n, c, TC_BM))) return rc;

@@ -106,9 +106,16 @@ class HypothesisShardedCoarse:
       candidates -> global top-K -> fill scores=-inf -> score my slice of the kept list -> ALL_REDUCE(MAX) #2 over the
       (B, K) score table (every entry is written by exactly one rank; MAX with -inf elsewhere moves it unchanged, no
       float is ever combined across ranks) -> arg-max + gather.
-    The result is identical on every rank and bit-identical to the single-GPU solver."""
+    The result is identical on every rank and bit-identical to the single-GPU solver.
 
-    def __init__(self, B, N1, N2, H, K, device, group=None, with_score=True):
+    exchange = "p2p": the two collectives become peer-memory exchanges fused into the kernels on either side of them
+    (csrc/peer.cuh): pack_candidates stores this rank's list into every rank's gathered array over NVLink and publishes,
+    unpack_candidates waits on its local flags; score_hypotheses stores its slice of the score table into every rank's
+    table, select_best waits.  No NCCL launch, no +-inf fills of the exchanged arrays, 8 kernel launches per solve.
+    "auto" picks p2p when the ranks can map each other's memory (peer.available) and every rank scores a non-empty
+    slice of the kept list, else NCCL; "nccl" forces the collectives (gloo on CPU tensors)."""
+
+    def __init__(self, B, N1, N2, H, K, device, group=None, with_score=True, exchange="auto"):
         from . import _lib as L
 
         self.L, self.lib = L, L.load()
@@ -132,6 +139,23 @@ class HypothesisShardedCoarse:
         self.allc = f32(self.world, B, self.kc, 14)
         self.scores = f32(B, self.K)
         self.R, self.t, self.sc, self.pool = f32(B, 3, 3), f32(B, 3), f32(B), i32(B)
+        if exchange not in ("auto", "nccl", "p2p"):
+            raise ValueError(exchange)
+        self.px = None
+        if self.world > 1 and exchange != "nccl":
+            from . import peer as P
+
+            every_rank_scores = all(score_shard_range(self.K, r, self.world)[1] > score_shard_range(self.K, r, self.world)[0]
+                                    for r in range(self.world))
+            ok = every_rank_scores and P.available(self.dev, group)
+            if exchange == "p2p" and not ok:
+                raise RuntimeError("exchange='p2p' needs peer-mappable CUDA devices under NCCL and K >= world")
+            if ok:
+                cand_bytes, score_bytes = self.allc.numel() * 4, self.scores.numel() * 4
+                self.px = P.PeerExchange(2 * (cand_bytes + 256) + 2 * (score_bytes + 256) + 1024, self.dev, group)
+                self.ch1 = self.px.reserve(cand_bytes)
+                self.ch2 = self.px.reserve(score_bytes)
+        self.exchange = "p2p" if self.px is not None else ("nccl" if self.world > 1 else "none")
 
     def run(self, atten, score, pts1, pts2, u):
         """atten (B,N1+1,N2+1), score (B,N1+N2)|None, pts (B,N,3), u (B,3H) identical on every rank (same seed).
@@ -159,12 +183,30 @@ class HypothesisShardedCoarse:
                     self.loc.copy_(self.resid[:, self.h0:self.h1])
                     L.check(lib.upk_topk_smallest(L.ptr(self.loc), B, self.h1 - self.h0, self.kl, L.ptr(self.top_l), st),
                             "topk_local")
-                L.check(lib.upk_pack_candidates(L.ptr(self.resid), L.ptr(self.Rs), L.ptr(self.ts), L.ptr(self.top_l), B, H,
-                                                self.h0, self.kl, self.kc, L.ptr(self.cand), st), "pack_candidates")
-                dist.all_gather_into_tensor(self.allc, self.cand, group=self.group)               # collective #1
-                L.check(lib.upk_unpack_candidates(L.ptr(self.allc), self.world, self.rank, B, H, self.kc, L.ptr(self.resid),
-                                                  L.ptr(self.Rs), L.ptr(self.ts), st), "unpack_candidates")
+                if self.px is not None:                                                            # exchange #1, peer memory
+                    ch, off, slab = self.ch1
+                    L.check(lib.upk_pack_candidates_peer(L.ptr(self.resid), L.ptr(self.Rs), L.ptr(self.ts), L.ptr(self.top_l),
+                                                         B, H, self.h0, self.kl, self.kc, self.px.ref, off, slab, ch, st),
+                            "pack_candidates_peer")
+                    L.check(lib.upk_unpack_candidates_peer(self.px.ref, off, slab, ch, B, H, self.kc, L.ptr(self.resid),
+                                                           L.ptr(self.Rs), L.ptr(self.ts), st), "unpack_candidates_peer")
+                else:
+                    L.check(lib.upk_pack_candidates(L.ptr(self.resid), L.ptr(self.Rs), L.ptr(self.ts), L.ptr(self.top_l), B, H,
+                                                    self.h0, self.kl, self.kc, L.ptr(self.cand), st), "pack_candidates")
+                    dist.all_gather_into_tensor(self.allc, self.cand, group=self.group)           # collective #1
+                    L.check(lib.upk_unpack_candidates(L.ptr(self.allc), self.world, self.rank, B, H, self.kc,
+                                                      L.ptr(self.resid), L.ptr(self.Rs), L.ptr(self.ts), st),
+                            "unpack_candidates")
             L.check(lib.upk_topk_smallest(L.ptr(self.resid), B, H, K, L.ptr(self.top), st), "topk_global")
+            if self.px is not None:                                                                # exchange #2, peer memory
+                ch, off, slab = self.ch2
+                L.check(lib.upk_score_hypotheses_peer(L.ptr(pts1), L.ptr(pts2), L.ptr(self.w1), L.ptr(self.Rs),
+                                                      L.ptr(self.ts), L.ptr(self.top), B, N1, N2, H, K, self.k0, self.k1,
+                                                      self.px.ref, off, slab, ch, st), "score_hypotheses_peer")
+                L.check(lib.upk_select_best_peer(self.px.ref, off, slab, ch, L.ptr(self.top), L.ptr(self.Rs), L.ptr(self.ts),
+                                                 B, H, K, L.ptr(self.R), L.ptr(self.t), L.ptr(self.sc), L.ptr(self.pool), st),
+                        "select_best_peer")
+                return self.R, self.t, self.sc, self.pool
             if self.world > 1:
                 L.check(lib.upk_fill_f32(L.ptr(self.scores), self.scores.numel(), float("-inf"), st), "fill")
             L.check(lib.upk_score_hypotheses(L.ptr(pts1), L.ptr(pts2), L.ptr(self.w1), L.ptr(self.Rs), L.ptr(self.ts),
@@ -177,7 +219,7 @@ class HypothesisShardedCoarse:
         return self.R, self.t, self.sc, self.pool
 
 
-def coarse_pose_hypothesis_sharded(atten, score, pts1, pts2, n_proposal1, n_proposal2, u, group=None):
+def coarse_pose_hypothesis_sharded(atten, score, pts1, pts2, n_proposal1, n_proposal2, u, group=None, exchange="nccl"):
     """One-shot form of HypothesisShardedCoarse (allocates its buffers per call).  `u` (B, 3*n_proposal1) must be
     identical on every rank (draw it from the same seed).  Returns (R, t, score, pool_idx), identical on every rank and
     bit-identical to the single-GPU solver."""
@@ -185,6 +227,6 @@ def coarse_pose_hypothesis_sharded(atten, score, pts1, pts2, n_proposal1, n_prop
     atten, pts1, pts2, u = (x.float().contiguous() for x in (atten, pts1, pts2, u))
     if score is not None:
         score = score.float().contiguous()
-    solver = HypothesisShardedCoarse(B, N1, pts2.shape[1], n_proposal1, n_proposal2, pts1.device, group)
+    solver = HypothesisShardedCoarse(B, N1, pts2.shape[1], n_proposal1, n_proposal2, pts1.device, group, exchange=exchange)
     R, t, sc, pool = solver.run(atten, score, pts1, pts2, u)
     return R.clone(), t.clone(), sc.clone(), pool.clone()
