@@ -231,6 +231,22 @@ int upk_pack_candidates(const float* resid, const float* Rs, const float* ts, co
 int upk_unpack_candidates(const float* gathered, int world, int my_rank, int b, int n_hyp, int n_slots, float* resid,
                           float* Rs, float* ts, upk_stream_t stream);
 
+/* Relative-position score term of the geometric self-attention (core/unopose/model/transformer.py:392-395 with the
+ * queries projected by W_p, see modules/transformer.py): out[b][h][n][m] = sum_c embed[b][n][m][c] * q2[b][n][c][h].
+ * One pass over the (B,N,M,C) embedding at HBM speed; heads == 4, c in {128, 256}; UPK_ERR_UNSUPPORTED otherwise. */
+int upk_rpe_scores(const float* embed, const float* q2, int b, int n, int m, int c, int heads, float* out,
+                   upk_stream_t stream);
+
+/* Fully-connected layer on the tensor cores at fp32-level accuracy: y[rows][out] = x[rows][in] W[out][in]^T + bias[out]
+ * (bias may be NULL), optional ReLU — torch.nn.functional.linear as the matching modules' transformer blocks call it
+ * (core/unopose/model/transformer.py:94-201,517-612: proj_q/k/v/p, linear, expand, squeeze; in_proj / out_proj of the
+ * matching modules).  The reference runs these as fp32 SIMT SGEMMs (TF32 is off, main_unopose.py:139-141); this is the
+ * 3xTF32 tcgen05 GEMM of upk_feature_similarity with a bias / ReLU epilogue.  in_features % 16 == 0, 16-byte aligned
+ * operands; UPK_ERR_UNSUPPORTED otherwise (callers then use their own GEMM). */
+size_t upk_linear_workspace_bytes(int rows, int in_features, int out_features);
+int upk_linear(const float* x, const float* weight, const float* bias, int rows, int in_features, int out_features,
+               int relu, void* workspace, size_t workspace_bytes, float* y, upk_stream_t stream);
+
 /* Peer exchange (NVLink / NVSwitch peer memory) — the fused compute + collective form of the two exchange steps of
  * hypothesis sharding and of the result gather of instance sharding (BASELINE.json north_star: "an NCCL
  * gather over NVLink of per-shard best scores").  No counterpart in the reference (single process, no collective).

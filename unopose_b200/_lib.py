@@ -58,6 +58,8 @@ _SIGNATURES = {
                                   ctypes.c_size_t, ctypes.c_size_t, c_i, c_st],
     "upk_select_best_peer": [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, c_i, c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_f,
                              c_f, c_f, c_st],
+    "upk_rpe_scores": [c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_f, c_st],
+    "upk_linear": [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_f, c_sz, c_f, c_st],
     "upk_peer_all_gather": [c_f, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, c_i, c_st],
     "upk_peer_wait": [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, c_i, c_f, ctypes.c_size_t, c_st],
     "upk_fine_pose": [c_f, c_f, c_i, c_f, c_i, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_fl, c_fl,
@@ -89,6 +91,7 @@ _SIZE_FUNCS = {
     "upk_fine_pose_workspace_bytes": [c_i, c_i, c_i],
     "upk_similarity_stats_bytes": [c_i, c_i, c_i],
     "upk_geometric_embedding_workspace_bytes": [c_i, c_i, c_i, c_i],
+    "upk_linear_workspace_bytes": [c_i, c_i, c_i],
 }
 
 

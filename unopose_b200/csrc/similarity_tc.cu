@@ -191,12 +191,15 @@ k_normalize_split(const NsOperand opa, const NsOperand opb, int c, int normalize
 // thread-local at TMEM-load time (a thread holds 32 columns of its row), column sums are thread-local at store time
 // (a lane then walks the 32 rows of its column through the transpose buffer); no shuffles, no atomics:
 //   rowpart[(b * 4 nt + 4 ni + column slice) * M + row]   colpart[(b * 4 mt + 4 mi + q) * N + col]   (partial-major: coalesced)
-template <int MODE, int NTERMS, bool STATS = false>  // MODE 0: dot/temp, 1: sqrt(clamp(2-2dot,0))/temp ; NTERMS 3 = 3xTF32, 1 = TF32
+// LIN: the same GEMM as a fully-connected layer, C = A B^T + bias (per column), optional ReLU (upk_linear): the bias
+// and the activation are applied at store time, where a lane owns one output column.
+template <int MODE, int NTERMS, bool STATS = false, bool LIN = false>  // MODE 0: dot/temp, 1: sqrt(clamp(2-2dot,0))/temp ; NTERMS 3 = 3xTF32, 1 = TF32
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_similarity_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                 int batch, int M, int N, int K, float temp, int off, float* __restrict__ C,
-                float* __restrict__ rowpart, float* __restrict__ colpart, float gref, int ldc) {
+                float* __restrict__ rowpart, float* __restrict__ colpart, float gref, int ldc,
+                const float* __restrict__ lin_bias, int lin_relu) {
   // `off` (0 or 1): the tiles cover rows/columns [off, M) x [off, N); with off = 1 the background row 0 and
   // column 0 are produced by k_normalize_split (BORDER), so the 2049 x 2049 fine shape is exactly 16 x 8 tiles
   extern __shared__ unsigned char smem_raw[];
@@ -323,7 +326,11 @@ k_similarity_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
           float* dst = Cb + col0 + lane;
           const float* src = tr + lane;
           float csum = 0.f;   // STATS: this lane's column (col0 + lane), the 32 rows of this warp
-          if (nrows == 32) {
+          if (LIN) {
+            const float bl = lin_bias ? __ldg(lin_bias + col0 + lane) : 0.f;
+            const float lo = lin_relu ? 0.f : -INFINITY;
+            for (int rr = 0; rr < nrows; ++rr) dst[(size_t)rr * ldc] = fmaxf(src[rr * 33] + bl, lo);
+          } else if (nrows == 32) {
 #pragma unroll
             for (int rr = 0; rr < 32; ++rr) {
               const float v = src[rr * 33];
@@ -874,7 +881,7 @@ int run_similarity_tc(const float* f1, const float* f2, int b, int n, int m, int
     auto kern = k_similarity_tc<MODE, NT, ST>;                                                               \
     UPK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
     kern<<<grid, TC_THREADS, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, b, n, m, c, temp, off, out, stats_row,  \
-                                         stats_col, stats_gref, ldc);                                        \
+                                         stats_col, stats_gref, ldc, nullptr, 0);                            \
   } while (0)
   const int tiles2 = b * ((n - off + 2 * TC_BM - 1) / (2 * TC_BM)) * ((m - off + TC_BN - 1) / TC_BN);
   if (use_2sm && sim_type == 0 && terms == 3 && tiles2 >= sms / 2) {
@@ -912,7 +919,60 @@ int run_similarity_tc(const float* f1, const float* f2, int b, int n, int m, int
   UPK_RETURN_LAST_ERROR();
 }
 
+// y[rows][out] = x[rows][in] W[out][in]^T + bias, optional ReLU: the single-CTA 3xTF32 kernel with batch 1, no peel,
+// temp 1, operands split (not normalised) by the same preparation launch as the similarity path.
+int run_linear_tc(const float* x, const float* w, const float* bias, int rows, int in, int out_f, int relu,
+                  void* workspace, size_t workspace_bytes, float* y, cudaStream_t st) {
+  if (workspace_bytes < similarity_tc_workspace_bytes(1, rows, out_f, in)) return UPK_ERR_INVALID_ARG;
+  char* wsp = (char*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
+  const size_t a = (((size_t)rows * in * sizeof(float)) + 1023) & ~(size_t)1023;
+  const size_t bb = (((size_t)out_f * in * sizeof(float)) + 1023) & ~(size_t)1023;
+  float* a_hi = (float*)wsp;
+  float* a_lo = (float*)(wsp + a);
+  float* b_hi = (float*)(wsp + 2 * a);
+  float* b_lo = (float*)(wsp + 2 * a + bb);
+  const dim3 g12(((rows > out_f ? rows : out_f) + 8 * NS_RPW - 1) / (8 * NS_RPW), 1, 2);
+  const NsOperand oa{x, rows, a_hi, a_lo, nullptr, out_f, 1}, ob{w, out_f, b_hi, b_lo, nullptr, rows, 0};
+  k_normalize_split<0><<<g12, 256, 0, st>>>(oa, ob, in, 0, 1.0f, y, rows, out_f, out_f);
+  count_launch(1);
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  int rc;
+  if ((rc = make_map(&ma_hi, a_hi, 1, rows, in, TC_BM))) return rc;
+  if ((rc = make_map(&ma_lo, a_lo, 1, rows, in, TC_BM))) return rc;
+  if ((rc = make_map(&mb_hi, b_hi, 1, out_f, in, TC_BN))) return rc;
+  if ((rc = make_map(&mb_lo, b_lo, 1, out_f, in, TC_BN))) return rc;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int tiles = ((rows + TC_BM - 1) / TC_BM) * ((out_f + TC_BN - 1) / TC_BN);
+  const int grid = tiles < sms ? tiles : sms;
+  const size_t smem = sizeof(TcSmem) + 1024;
+  auto kern = k_similarity_tc<0, 3, false, true>;
+  UPK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, TC_THREADS, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, 1, rows, out_f, in, 1.0f, 0, y, nullptr, nullptr, 0.f,
+                                       out_f, bias, relu);
+  count_launch();
+  UPK_RETURN_LAST_ERROR();
+}
+
 }  // namespace upk
+
+extern "C" size_t upk_linear_workspace_bytes(int rows, int in_features, int out_features) {
+  if (rows <= 0 || in_features <= 0 || out_features <= 0) return 0;
+  return upk::similarity_tc_workspace_bytes(1, rows, out_features, in_features);
+}
+
+extern "C" int upk_linear(const float* x, const float* weight, const float* bias, int rows, int in_features,
+                          int out_features, int relu, void* workspace, size_t workspace_bytes, float* y,
+                          upk_stream_t stream) {
+  if (rows < 0 || in_features <= 0 || out_features <= 0) return UPK_ERR_INVALID_ARG;
+  if (rows == 0) return UPK_OK;
+  if (!x || !weight || !y || !workspace) return UPK_ERR_INVALID_ARG;
+  if (in_features % upk::TC_BK != 0 || ((uintptr_t)x & 15) || ((uintptr_t)weight & 15) || !upk::similarity_tc_eligible(rows, out_features, in_features))
+    return UPK_ERR_UNSUPPORTED;
+  return upk::run_linear_tc(x, weight, bias, rows, in_features, out_features, relu, workspace, workspace_bytes, y,
+                            (cudaStream_t)stream);
+}
 
 extern "C" int upk_set_similarity_mode(int mode) {
   int prev = upk::similarity_mode();

@@ -12,6 +12,7 @@ from ..model_utils import (compute_coarse_Rt_overlap, compute_feature_similarity
                            transform_points)
 from ..pointnet2.pointnet2_utils import QueryAndGroup, QueryAndLRFGroup, ball_query_and_group
 from .layers import Conv1d, SharedMLP
+from .linear import linear
 from .transformer import GeometricTransformer, SparseToDenseTransformer
 
 
@@ -51,12 +52,12 @@ class CoarsePointMatchingOneRef(nn.Module):
         """The dense (cuBLAS) part: returns out_proj(f1), out_proj(f2) (B,n+1,C) and the overlap scores."""
         B, n1 = f1.size(0), f1.size(1)
         bg = self.bg_token.repeat(B, 1, 1)
-        f1 = torch.cat([bg, self.in_proj(f1)], dim=1)
-        f2 = torch.cat([bg, self.in_proj(f2)], dim=1)
+        f1 = torch.cat([bg, linear(self.in_proj, f1)], dim=1)
+        f2 = torch.cat([bg, linear(self.in_proj, f2)], dim=1)
         for i in range(self.nblock):
             f1, f2 = self.transformers[i](f1, geo1, f2, geo2)
         score = _overlap_scores(self.score_heads[self.nblock - 1](torch.cat((f1, f2), dim=1)), n1)
-        return self.out_proj(f1), self.out_proj(f2), score
+        return linear(self.out_proj, f1), linear(self.out_proj, f2), score
 
     def forward(self, p1, f1, geo1, p2, f2, geo2, radius, end_points):
         if self.training:
@@ -155,12 +156,12 @@ class FinePointMatchingOneRef(nn.Module):
         else:
             p1_ = p1
         bg = self.bg_token.repeat(B, 1, 1)
-        f1 = torch.cat([bg, self.in_proj(f1) + self.PE(p1_)], dim=1)
-        f2 = torch.cat([bg, self.in_proj(f2) + self.PE(p2)], dim=1)
+        f1 = torch.cat([bg, linear(self.in_proj, f1) + self.PE(p1_)], dim=1)
+        f2 = torch.cat([bg, linear(self.in_proj, f2) + self.PE(p2)], dim=1)
         for i in range(self.nblock):
             f1, f2 = self.transformers[i](f1, geo1, fps_idx1, f2, geo2, fps_idx2)
         score = _overlap_scores(self.score_heads[self.nblock - 1](torch.cat((f1, f2), dim=1)), n1)
-        return self.out_proj(f1), self.out_proj(f2), score
+        return linear(self.out_proj, f1), linear(self.out_proj, f2), score
 
     def forward(self, p1, f1, geo1, fps_idx1, p2, f2, geo2, fps_idx2, radius, end_points):
         if self.training:

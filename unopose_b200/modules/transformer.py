@@ -11,6 +11,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ..model_utils import _gather_rows, pairwise_distance
+from .linear import linear
 
 
 def _heads(x, h):
@@ -25,6 +26,25 @@ def _merge(x):
     return x.permute(0, 2, 1, 3).reshape(b, n, h * c)
 
 
+def _rpe_scores(embed, q2):
+    """(B,N,M,C) embedding x (B,N,C,h) projected queries -> (B,h,N,M): one pass over the embedding (`upk_rpe_scores`)
+    on CUDA without autograd, torch.matmul + permute otherwise."""
+    if embed.is_cuda and embed.dtype == torch.float32 and not (torch.is_grad_enabled() and (embed.requires_grad or q2.requires_grad)):
+        from .. import _lib as L
+
+        B, N, M, C = embed.shape
+        h = q2.shape[3]
+        e, q = embed.contiguous(), q2.contiguous().float()
+        out = torch.empty((B, h, N, M), dtype=torch.float32, device=embed.device)
+        with torch.cuda.device(embed.device):
+            rc = L.load().upk_rpe_scores(L.ptr(e), L.ptr(q), B, N, M, C, h, L.ptr(out), L.stream_ptr(e))
+        if rc == 0:
+            return out
+        if rc != -2:
+            L.check(rc, "rpe_scores")
+    return torch.matmul(embed, q2).permute(0, 3, 1, 2)
+
+
 class _FeedForward(nn.Module):
     """expand -> ReLU -> squeeze -> residual LayerNorm (transformer.py:186-201, `AttentionOutput`)."""
 
@@ -35,7 +55,7 @@ class _FeedForward(nn.Module):
         self.norm = nn.LayerNorm(d_model)
 
     def forward(self, x):
-        return self.norm(x + self.squeeze(F.relu(self.expand(x))))
+        return self.norm(x + linear(self.squeeze, linear(self.expand, x, relu=True)))
 
 
 class _DotAttention(nn.Module):
@@ -56,7 +76,7 @@ class _DotAttention(nn.Module):
 
     def forward(self, x_q, x_kv, embed_qk=None, key_masks=None):
         h = self.num_heads
-        q, k, v = _heads(self.proj_q(x_q), h), _heads(self.proj_k(x_kv), h), _heads(self.proj_v(x_kv), h)
+        q, k, v = _heads(linear(self.proj_q, x_q), h), _heads(linear(self.proj_k, x_kv), h), _heads(linear(self.proj_v, x_kv), h)
         scores = q @ k.transpose(-1, -2)
         if embed_qk is not None:
             # q.(W_p e + b_p) = (W_p^T q).e + q.b_p: the reference projects the (B,N,M,C) embedding with W_p
@@ -65,9 +85,8 @@ class _DotAttention(nn.Module):
             c = self.head_dim
             wp = self.proj_p.weight.view(h, c, -1)                                  # (h, c, C)
             q2 = torch.einsum("bhnc,hck->bnkh", q, wp)                              # (B, N, C, h)
-            sp = torch.matmul(embed_qk, q2)                                         # (B, N, M, C) @ (B, N, C, h)
             qb = torch.einsum("bhnc,hc->bhn", q, self.proj_p.bias.view(h, c))
-            scores = scores + sp.permute(0, 3, 1, 2) + qb.unsqueeze(-1)
+            scores = scores + _rpe_scores(embed_qk, q2) + qb.unsqueeze(-1)
         scores = scores / self.head_dim ** 0.5
         if key_masks is not None:
             scores = scores.masked_fill(key_masks[:, None, None, :], float("-inf"))
@@ -86,7 +105,7 @@ class _AttentionBlock(nn.Module):
 
     def forward(self, x, memory, embed=None, memory_masks=None):
         h, attn = self.attention(x, memory, embed, memory_masks)
-        return self.norm(self.linear(h) + x), attn
+        return self.norm(linear(self.linear, h) + x), attn
 
 
 class TransformerLayer(nn.Module):
@@ -161,9 +180,9 @@ class _FocusedLinearAttention(nn.Module):
     def forward(self, x_q, x_kv):
         h = self.num_heads
         scale = F.softplus(self.scale)
-        q = _heads(self._focus(self.proj_q(x_q), scale), h)   # (B,h,i,c)
-        k = _heads(self._focus(self.proj_k(x_kv), scale), h)  # (B,h,j,c)
-        v = _heads(self.proj_v(x_kv), h)                      # (B,h,j,d)
+        q = _heads(self._focus(linear(self.proj_q, x_q), scale), h)   # (B,h,i,c)
+        k = _heads(self._focus(linear(self.proj_k, x_kv), scale), h)  # (B,h,j,c)
+        v = _heads(linear(self.proj_v, x_kv), h)              # (B,h,j,d)
         z = 1.0 / (torch.einsum("bhic,bhc->bhi", q, k.sum(dim=2)) + 1e-6)
         i, j, c, d = q.shape[2], k.shape[2], k.shape[3], v.shape[3]
         if i * j * (c + d) > c * d * (i + j):
@@ -182,7 +201,7 @@ class _LinearAttentionBlock(nn.Module):
         self.norm = nn.LayerNorm(d_model)
 
     def forward(self, x, memory):
-        return self.norm(self.linear(self.attention(x, memory)) + x)
+        return self.norm(linear(self.linear, self.attention(x, memory)) + x)
 
 
 class LinearTransformerLayer(nn.Module):
