@@ -133,7 +133,9 @@ size_t upk_feature_similarity_workspace_bytes(int b, int n, int m, int c, int no
  * three-product split of fp32 operands, fp32-level accuracy either way: 3xFP16 (operands scaled by 2^12) for
  * normalised cosine logits on the CTA-pair shapes (enough 256x256 tiles to fill the GPU, c % 32 == 0), 3xTF32
  * elsewhere; 3 = 3xTF32 everywhere; 1 = single TF32 pass; 0 = fp32 SIMT everywhere.
- * Also settable with the environment variable UPK_SIMILARITY_MODE.  Returns the previous mode. */
+ * Also settable with the environment variable UPK_SIMILARITY_MODE.  Returns the previous mode.
+ * (The fused-statistics variant below has its own, larger threshold: the Python wrapper requests it above 512^2
+ * logits, where the fine solver runs its streaming passes.) */
 int upk_set_similarity_mode(int mode);
 int upk_feature_similarity(const float* feat1, const float* feat2, int b, int n, int m,
                            int c, float temp, int normalize, int sim_type,
@@ -230,6 +232,17 @@ int upk_pack_candidates(const float* resid, const float* Rs, const float* ts, co
                         int h_begin, int n_local, int n_slots, float* cand_out, upk_stream_t stream);
 int upk_unpack_candidates(const float* gathered, int world, int my_rank, int b, int n_hyp, int n_slots, float* resid,
                           float* Rs, float* ts, upk_stream_t stream);
+/* Compact merge (round 2): the gathered lists as a pool of world * n_slots candidates per instance —
+ * resid_c[b][world*n_slots] (padding records get the largest key), Rs_c [..][9], ts_c [..][3], pool_c = pool index of
+ * each entry (-1 for padding).  Compact order == pool-index order, so upk_topk_smallest / upk_score_hypotheses /
+ * upk_select_best_map on these arrays (n_hyp = world * n_slots) select exactly what the dense merge selects, without
+ * touching H-sized arrays.  upk_topk_smallest_ld is upk_topk_smallest on rows with a pitch (a slice of the pool). */
+int upk_unpack_candidates_compact(const float* gathered, int world, int b, int n_slots, float* resid_c, float* Rs_c,
+                                  float* ts_c, int* pool_c, upk_stream_t stream);
+int upk_topk_smallest_ld(const float* vals, int b, int n, int ld, int k, int* idx_out, upk_stream_t stream);
+int upk_select_best_map(const float* scores, const int* top, const float* Rs, const float* ts, const int* pool_map, int b,
+                        int n_hyp, int n_keep, float* R_out, float* t_out, float* score_out, int* pool_idx_out,
+                        upk_stream_t stream);
 
 /* Relative-position score term of the geometric self-attention (core/unopose/model/transformer.py:392-395 with the
  * queries projected by W_p, see modules/transformer.py): out[b][h][n][m] = sum_c embed[b][n][m][c] * q2[b][n][c][h].
@@ -278,10 +291,14 @@ int upk_score_hypotheses_peer(const float* pts1, const float* model_pts, const f
                               const int* top, int b, int n1, int n_model, int n_hyp, int n_keep, int k_begin, int k_end,
                               const upk_peer_t* peer, size_t data_offset, size_t slab_bytes, int channel,
                               upk_stream_t stream);
-/* upk_select_best on the local score table after waiting for every rank's slice. */
+/* upk_unpack_candidates_compact after the same wait. */
+int upk_unpack_candidates_compact_peer(const upk_peer_t* peer, size_t data_offset, size_t slab_bytes, int channel, int b,
+                                       int n_slots, float* resid_c, float* Rs_c, float* ts_c, int* pool_c,
+                                       upk_stream_t stream);
+/* upk_select_best[_map] on the local score table after waiting for every rank's slice (pool_map may be NULL). */
 int upk_select_best_peer(const upk_peer_t* peer, size_t data_offset, size_t slab_bytes, int channel, const int* top,
-                         const float* Rs, const float* ts, int b, int n_hyp, int n_keep, float* R_out, float* t_out,
-                         float* score_out, int* pool_idx_out, upk_stream_t stream);
+                         const float* Rs, const float* ts, const int* pool_map, int b, int n_hyp, int n_keep, float* R_out,
+                         float* t_out, float* score_out, int* pool_idx_out, upk_stream_t stream);
 /* Generic all-gather of `bytes` (multiple of 16) per rank: src -> every rank's data[r] + data_offset + slab * slab_bytes
  * + rank * bytes, then publish; upk_peer_wait blocks the stream until every rank has published and (optionally) copies
  * the gathered world * bytes out of the slab into dst (may be NULL). */

@@ -90,3 +90,41 @@ def test_score_and_candidate_partitions():
             assert covered == list(range(K))                       # every kept hypothesis scored by exactly one rank
             assert len({e - b for b, e in spans if e > b} | {0}) <= 3
     assert candidate_slots(5000, 300, 8) == 300 and candidate_slots(1000, 300, 8) == 125 and candidate_slots(100, 300, 1) == 100
+
+
+def _topk_smallest_lower_index_first(vals, K):
+    """The tie rule of upk_topk_smallest: the K smallest, ties at the K-th value to the lower index, ascending index."""
+    out = []
+    for row in vals:
+        order = sorted(range(len(row)), key=lambda i: (float(row[i]), i))[:K]
+        out.append(sorted(order))
+    return torch.tensor(out)
+
+
+def test_compact_merge_selects_what_the_dense_merge_selects():
+    """Hypothesis sharding, round 2: the global top-K runs on the compact pool of world*kc candidates instead of the dense
+    H-sized array.  Compact order == pool-index order (every rank's list ascending, ranks own ascending slices), so
+    the same top-K rule selects the same hypotheses in the same order — including exact ties and padded lists."""
+    from unopose_b200.dist import candidate_slots, compact_candidates
+
+    g = torch.Generator().manual_seed(5)
+    for world, H, K in ((2, 1000, 37), (3, 500, 300), (8, 2000, 300), (4, 64, 30)):
+        B = 2
+        resid = torch.rand(B, H, generator=g)
+        resid[:, 40:60] = resid[:, 3:4]                      # a block of exact ties straddling nothing in particular
+        resid[:, H // 2 - 2:H // 2 + 2] = resid[:, 3:4]      # ... and across a slice boundary (world = 2)
+        kc = candidate_slots(H, K, world)
+        cr = torch.full((world, B, kc), float("inf"))
+        ci = torch.full((world, B, kc), -1, dtype=torch.long)
+        for r in range(world):
+            h0, h1 = shard_range(H, r, world)
+            kl = min(K, h1 - h0)
+            loc = _topk_smallest_lower_index_first(resid[:, h0:h1], kl) + h0          # ascending pool index
+            cr[r, :, :kl] = torch.gather(resid, 1, loc)
+            ci[r, :, :kl] = loc
+        rc, ic = compact_candidates(cr, ci)
+        top_c = _topk_smallest_lower_index_first(rc, K)                              # indices into the compact pool
+        sel_compact = torch.gather(ic, 1, top_c)
+        sel_dense = _topk_smallest_lower_index_first(resid, K)                       # what one GPU selects
+        assert torch.equal(sel_compact, sel_dense), (world, H, K)
+        assert bool((sel_compact >= 0).all())

@@ -31,7 +31,7 @@ def T(a, dev):
 @pytest.mark.parametrize("n,m", [(1, 1), (2, 2), (3, 3), (31, 7), (196, 64), (255, 200), (256, 33), (500, 100),
                                  (777, 64), (1024, 128), (2048, 196), (2500, 300), (4096, 50), (5000, 2048),
                                  (7000, 40), (10000, 30), (14000, 20),
-                                 # long runs -> the box-pruned kernel (m >= 512, 2048 <= n <= 8192)
+                                 # long chains (m >= 512) at cloud sizes around the per-thread point-count switches
                                  (2048, 2048), (2049, 512), (3000, 600), (4096, 1000), (5120, 700), (8000, 513),
                                  (8192, 600), (8193, 600)])
 def test_fps_matches_oracle(cuda, n, m):
@@ -46,7 +46,7 @@ def test_fps_ties_match_oracle(cuda, n):
     """Quantised coordinates + duplicated points + more samples than distinct points."""
     xyz = np.round(batch_clouds(n, 2, n) * 4) / 4
     xyz[:, n // 2:] = xyz[:, : n - n // 2]
-    for m in (min(n, 400), min(n, 1500)):   # 1500 >= 512: the box-pruned kernel for n >= 2048
+    for m in (min(n, 400), min(n, 1500)):   # more samples than distinct points: every later pick is an exact tie
         got = _ext().furthest_point_sampling(T(xyz, cuda), m).cpu().numpy()
         assert np.array_equal(got, O.furthest_point_sampling(xyz, m))
     z = np.zeros((1, n, 3), np.float32)

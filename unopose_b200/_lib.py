@@ -56,8 +56,13 @@ _SIGNATURES = {
     "upk_unpack_candidates_peer": [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, c_i, c_i, c_i, c_i, c_f, c_f, c_f, c_st],
     "upk_score_hypotheses_peer": [c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_i, ctypes.c_void_p,
                                   ctypes.c_size_t, ctypes.c_size_t, c_i, c_st],
-    "upk_select_best_peer": [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, c_i, c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_f,
-                             c_f, c_f, c_st],
+    "upk_select_best_peer": [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, c_i, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_f,
+                             c_f, c_f, c_f, c_st],
+    "upk_unpack_candidates_compact_peer": [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, c_i, c_i, c_i, c_f, c_f, c_f, c_f,
+                                           c_st],
+    "upk_unpack_candidates_compact": [c_f, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_st],
+    "upk_topk_smallest_ld": [c_f, c_i, c_i, c_i, c_i, c_f, c_st],
+    "upk_select_best_map": [c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_st],
     "upk_rpe_scores": [c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_f, c_st],
     "upk_linear": [c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_f, c_sz, c_f, c_st],
     "upk_peer_all_gather": [c_f, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, c_i, c_st],

@@ -172,12 +172,12 @@ __device__ __forceinline__ unsigned block_excl_scan_u32(unsigned v, unsigned* s_
 }
 
 __global__ void __launch_bounds__(TK_THREADS)
-k_topk_smallest(const float* __restrict__ vals, int H, int K, int* __restrict__ top) {
+k_topk_smallest(const float* __restrict__ vals, int H, int K, int* __restrict__ top, int ld) {
   __shared__ unsigned hist[256];
   __shared__ unsigned s_warp[33];
   __shared__ unsigned s_prefix, s_kth_rank;
   const int b = blockIdx.x;
-  const unsigned* v = reinterpret_cast<const unsigned*>(vals) + (size_t)b * H;
+  const unsigned* v = reinterpret_cast<const unsigned*>(vals) + (size_t)b * ld;   // ld >= H: row pitch (a slice of a pool)
   top += (size_t)b * K;
   unsigned prefix = 0, mask = 0;
   unsigned want = (unsigned)K;  // rank (1-based) of the K-th smallest within the current bucket
@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(256)
 k_select(const float* __restrict__ scores, const int* __restrict__ top, const float* __restrict__ Rs,
          const float* __restrict__ ts, int H, int K, float* __restrict__ R_out, float* __restrict__ t_out,
          float* __restrict__ score_out, int* __restrict__ pool_out,
-         const PeerCtx pc, size_t peer_off, size_t slab_bytes, int channel) {
+         const PeerCtx pc, size_t peer_off, size_t slab_bytes, int channel, const int* __restrict__ pool_map = nullptr) {
   __shared__ float s_v[8];
   __shared__ int s_i[8];
   const int b = blockIdx.x;
@@ -366,7 +366,7 @@ k_select(const float* __restrict__ scores, const int* __restrict__ top, const fl
     for (int i = 0; i < 9; ++i) R_out[(size_t)b * 9 + i] = Rs[((size_t)b * H + h) * 9 + i];
     for (int i = 0; i < 3; ++i) t_out[(size_t)b * 3 + i] = ts[((size_t)b * H + h) * 3 + i];
     score_out[b] = bv;
-    if (pool_out) pool_out[b] = h;
+    if (pool_out) pool_out[b] = pool_map ? pool_map[(size_t)b * H + h] : h;   // compact candidate list -> pool index
   }
 }
 
@@ -445,6 +445,40 @@ k_unpack_candidates(const float* __restrict__ allc /* [world][b][kc][14] */, int
   for (int i = 0; i < 9; ++i) Rs[((size_t)b * H + h) * 9 + i] = rec[2 + i];
 #pragma unroll
   for (int i = 0; i < 3; ++i) ts[((size_t)b * H + h) * 3 + i] = rec[11 + i];
+}
+
+// Compact form of the merge (round 2): the gathered lists ARE the only candidates for the global top-K, so instead of
+// scattering them into the dense pool arrays (and running the top-K over H mostly-infinite entries) they are laid out
+// as a compact pool of world * kc entries per instance.  Every rank's list is ascending in pool index and the ranks
+// own ascending slices, so compact order == pool-index order and the SAME top-K kernel applies the SAME tie rule
+// (lower index first); padding records sort after everything (key 0xFFFFFFFF).
+template <bool PEER>
+__global__ void __launch_bounds__(128)
+k_unpack_candidates_compact(const float* __restrict__ allc /* [world][b][kc][14] */, int world, int nb, int kc,
+                            float* __restrict__ resid_c, float* __restrict__ Rs_c, float* __restrict__ ts_c,
+                            int* __restrict__ pool_c, const PeerCtx pc, size_t peer_off, size_t slab_bytes, int channel) {
+  if (PEER) {
+    const unsigned long long e = pc.epoch[channel];
+    peer_wait(pc, channel, e);
+    allc = reinterpret_cast<const float*>(pc.data[pc.rank] + peer_off + (e & 1) * slab_bytes);
+  }
+  const int b = blockIdx.y;
+  const int q = blockIdx.x * 128 + threadIdx.x;   // (rank, j) == compact index
+  const int n = world * kc;
+  if (q >= n) return;
+  const int r = q / kc, j = q - r * kc;
+  const float* c = allc + (((size_t)r * nb + b) * kc + j) * CAND_F;
+  float rec[CAND_F];
+#pragma unroll
+  for (int i = 0; i < CAND_F; ++i) rec[i] = PEER ? __ldcg(c + i) : c[i];
+  const int h = __float_as_int(rec[1]);
+  const size_t o = (size_t)b * n + q;
+  resid_c[o] = h < 0 ? __uint_as_float(0xFFFFFFFFu) : rec[0];
+  pool_c[o] = h;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) Rs_c[o * 9 + i] = rec[2 + i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) ts_c[o * 3 + i] = rec[11 + i];
 }
 
 __global__ void __launch_bounds__(256)
@@ -546,7 +580,7 @@ int upk_coarse_pose(const float* atten, const float* score1, int score1_ld, cons
                                               w.ts, w.resid);
     count_launch();
   }
-  k_topk_smallest<<<b, TK_THREADS, 0, st>>>(w.resid, n_hyp, n_keep, w.top);
+  k_topk_smallest<<<b, TK_THREADS, 0, st>>>(w.resid, n_hyp, n_keep, w.top, n_hyp);
   count_launch();
   if ((rc = launch_score(pts1, model_pts, w.w1, w.Rs, w.ts, w.top, b, n1, n_model, n_hyp, n_keep, 0, n_keep,
                          w.scores, st)))
@@ -629,7 +663,15 @@ int upk_kabsch_triplets(const float* p1, const float* p2, int n, float* Rs, floa
 int upk_topk_smallest(const float* vals, int b, int n, int k, int* idx_out, upk_stream_t stream) {
   if (b < 0 || n <= 0 || k <= 0 || k > n) return UPK_ERR_INVALID_ARG;
   if (b == 0) return UPK_OK;
-  k_topk_smallest<<<b, TK_THREADS, 0, (cudaStream_t)stream>>>(vals, n, k, idx_out);
+  k_topk_smallest<<<b, TK_THREADS, 0, (cudaStream_t)stream>>>(vals, n, k, idx_out, n);
+  count_launch();
+  UPK_RETURN_LAST_ERROR();
+}
+
+int upk_topk_smallest_ld(const float* vals, int b, int n, int ld, int k, int* idx_out, upk_stream_t stream) {
+  if (b < 0 || n <= 0 || k <= 0 || k > n || ld < n) return UPK_ERR_INVALID_ARG;
+  if (b == 0) return UPK_OK;
+  k_topk_smallest<<<b, TK_THREADS, 0, (cudaStream_t)stream>>>(vals, n, k, idx_out, ld);
   count_launch();
   UPK_RETURN_LAST_ERROR();
 }
@@ -687,7 +729,39 @@ int upk_select_best(const float* scores, const int* top, const float* Rs, const 
   UPK_RETURN_LAST_ERROR();
 }
 
+int upk_unpack_candidates_compact(const float* gathered, int world, int b, int n_slots, float* resid_c, float* Rs_c,
+                                  float* ts_c, int* pool_c, upk_stream_t stream) {
+  if (world <= 0 || b < 0 || n_slots <= 0) return UPK_ERR_INVALID_ARG;
+  if (b == 0) return UPK_OK;
+  if (!gathered || !resid_c || !Rs_c || !ts_c || !pool_c) return UPK_ERR_INVALID_ARG;
+  k_unpack_candidates_compact<false><<<dim3(ceil_div(world * n_slots, 128), b), 128, 0, (cudaStream_t)stream>>>(
+      gathered, world, b, n_slots, resid_c, Rs_c, ts_c, pool_c, PeerCtx(), 0, 0, 0);
+  count_launch();
+  UPK_RETURN_LAST_ERROR();
+}
+
+int upk_select_best_map(const float* scores, const int* top, const float* Rs, const float* ts, const int* pool_map, int b,
+                        int n_hyp, int n_keep, float* R_out, float* t_out, float* score_out, int* pool_idx_out,
+                        upk_stream_t stream) {
+  if (b < 0 || n_hyp <= 0 || n_keep <= 0) return UPK_ERR_INVALID_ARG;
+  if (b == 0) return UPK_OK;
+  k_select<false><<<b, 256, 0, (cudaStream_t)stream>>>(scores, top, Rs, ts, n_hyp, n_keep, R_out, t_out, score_out,
+                                                       pool_idx_out, PeerCtx(), 0, 0, 0, pool_map);
+  count_launch();
+  UPK_RETURN_LAST_ERROR();
+}
+
 // ---- peer-exchange forms (fused compute + all-gather over NVLink peer memory; csrc/peer.cuh) ----
+
+int upk_unpack_candidates_compact_peer(const upk_peer_t* peer, size_t data_offset, size_t slab_bytes, int channel, int b,
+                                       int n_slots, float* resid_c, float* Rs_c, float* ts_c, int* pool_c,
+                                       upk_stream_t stream) {
+  if (b <= 0 || n_slots <= 0 || !resid_c || !Rs_c || !ts_c || !pool_c || !peer_ctx_ok(peer, channel)) return UPK_ERR_INVALID_ARG;
+  k_unpack_candidates_compact<true><<<dim3(ceil_div(peer->world * n_slots, 128), b), 128, 0, (cudaStream_t)stream>>>(
+      nullptr, peer->world, b, n_slots, resid_c, Rs_c, ts_c, pool_c, make_peer_ctx(peer), data_offset, slab_bytes, channel);
+  count_launch();
+  UPK_RETURN_LAST_ERROR();
+}
 
 int upk_pack_candidates_peer(const float* resid, const float* Rs, const float* ts, const int* top_local, int b, int n_hyp,
                              int h_begin, int n_local, int n_slots, const upk_peer_t* peer, size_t data_offset,
@@ -726,11 +800,12 @@ int upk_score_hypotheses_peer(const float* pts1, const float* model_pts, const f
 }
 
 int upk_select_best_peer(const upk_peer_t* peer, size_t data_offset, size_t slab_bytes, int channel, const int* top,
-                         const float* Rs, const float* ts, int b, int n_hyp, int n_keep, float* R_out, float* t_out,
-                         float* score_out, int* pool_idx_out, upk_stream_t stream) {
+                         const float* Rs, const float* ts, const int* pool_map, int b, int n_hyp, int n_keep, float* R_out,
+                         float* t_out, float* score_out, int* pool_idx_out, upk_stream_t stream) {
   if (b <= 0 || n_hyp <= 0 || n_keep <= 0 || !peer_ctx_ok(peer, channel)) return UPK_ERR_INVALID_ARG;
   k_select<true><<<b, 256, 0, (cudaStream_t)stream>>>(nullptr, top, Rs, ts, n_hyp, n_keep, R_out, t_out, score_out,
-                                                      pool_idx_out, make_peer_ctx(peer), data_offset, slab_bytes, channel);
+                                                      pool_idx_out, make_peer_ctx(peer), data_offset, slab_bytes, channel,
+                                                      pool_map);
   count_launch();
   UPK_RETURN_LAST_ERROR();
 }

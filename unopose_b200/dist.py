@@ -84,6 +84,17 @@ def merge_topk_candidates(cand_resid, cand_idx, n_hyp):
     return dense
 
 
+def compact_candidates(cand_resid, cand_idx):
+    """The gathered candidate lists (world, B, kc) as the compact pool (B, world*kc) the merge selects from: residuals
+    with padding records (idx < 0) moved behind everything, and the pool index of each entry.  Torch formulation of
+    upk_unpack_candidates_compact (CPU/gloo tests of the host logic)."""
+    W, B, kc = cand_resid.shape
+    r = cand_resid.permute(1, 0, 2).reshape(B, W * kc).clone()
+    i = cand_idx.permute(1, 0, 2).reshape(B, W * kc)
+    r[i < 0] = float("inf")
+    return r, i
+
+
 def score_shard_range(K, rank, world):
     """Slice [k0, k1) of the kept list a rank scores: equal chunks of ceil(K / world), the tail ranks may be empty."""
     kmax = -(-K // world)
@@ -100,12 +111,13 @@ class HypothesisShardedCoarse:
     """compute_coarse_Rt_overlap with the hypothesis pool split across the ranks of `group` (partitioning B).
 
     All buffers are allocated once (static addresses, so a solve can be captured into a CUDA graph together with its
-    two collectives).  One solve = 10 kernel launches + 2 collectives:
-      fill resid=+inf -> assignment (replicated, bit-exact cluster kernel) -> my slice of the hypotheses -> local
-      top-K of the slice -> pack candidates -> ALL_GATHER #1 (world x B x slots x 56 B) -> unpack the other ranks'
-      candidates -> global top-K -> fill scores=-inf -> score my slice of the kept list -> ALL_REDUCE(MAX) #2 over the
-      (B, K) score table (every entry is written by exactly one rank; MAX with -inf elsewhere moves it unchanged, no
-      float is ever combined across ranks) -> arg-max + gather.
+    two collectives).  One solve = 8 kernel launches + 2 exchanges:
+      assignment (replicated, bit-exact cluster kernel) -> my slice of the hypotheses -> top-K of the slice (in place,
+      pitched) -> pack candidates -> EXCHANGE #1 (world x B x slots x 56 B) -> the gathered lists as a COMPACT pool of
+      world x slots candidates per instance (compact order == pool-index order, so the same top-K kernel applies the
+      same tie rule; no H-sized array is touched after the sampling) -> global top-K -> score my slice of the kept list
+      -> EXCHANGE #2 over the (B, K) score table (every entry is written by exactly one rank; with NCCL an
+      ALL_REDUCE(MAX) against -inf moves it unchanged, no float is ever combined across ranks) -> arg-max + gather.
     The result is identical on every rank and bit-identical to the single-GPU solver.
 
     exchange = "p2p": the two collectives become peer-memory exchanges fused into the kernels on either side of them
@@ -137,6 +149,8 @@ class HypothesisShardedCoarse:
         self.top_l, self.top = i32(B, max(self.kl, 1)), i32(B, self.K)
         self.cand = f32(B, self.kc, 14)
         self.allc = f32(self.world, B, self.kc, 14)
+        nc = self.world * self.kc                    # the compact candidate pool of the merge (world > 1)
+        self.resid_c, self.Rs_c, self.ts_c, self.pool_c = f32(B, nc), f32(B, nc, 9), f32(B, nc, 3), i32(B, nc)
         self.scores = f32(B, self.K)
         self.R, self.t, self.sc, self.pool = f32(B, 3, 3), f32(B, 3), f32(B), i32(B)
         if exchange not in ("auto", "nccl", "p2p"):
@@ -171,51 +185,61 @@ class HypothesisShardedCoarse:
             s1, s2 = score, score[:, N2:]
         st = L.stream_ptr(pts1)
         with torch.cuda.device(self.dev):
-            L.check(lib.upk_fill_f32(L.ptr(self.resid), self.resid.numel(), float("inf"), st), "fill")
+            if self.world == 1:
+                L.check(lib.upk_fill_f32(L.ptr(self.resid), self.resid.numel(), float("inf"), st), "fill")
             L.check(lib.upk_coarse_assignment(L.ptr(atten), L.ptr(s1), ld, s2.data_ptr() if s2 is not None else None, ld,
                                               B, N1, N2, L.ptr(self.ws), self.ws.numel(), L.ptr(self.w1), L.ptr(self.w2),
                                               L.ptr(self.cdf), st), "coarse_assignment")
             L.check(lib.upk_sample_hypotheses(L.ptr(self.cdf), L.ptr(u), L.ptr(pts1), L.ptr(pts2), B, N1, N2, H, self.h0,
                                               self.h1, None, None, L.ptr(self.Rs), L.ptr(self.ts), L.ptr(self.resid), st),
                     "sample_hypotheses")
-            if self.world > 1:
-                if self.kl > 0:
-                    self.loc.copy_(self.resid[:, self.h0:self.h1])
-                    L.check(lib.upk_topk_smallest(L.ptr(self.loc), B, self.h1 - self.h0, self.kl, L.ptr(self.top_l), st),
-                            "topk_local")
-                if self.px is not None:                                                            # exchange #1, peer memory
-                    ch, off, slab = self.ch1
-                    L.check(lib.upk_pack_candidates_peer(L.ptr(self.resid), L.ptr(self.Rs), L.ptr(self.ts), L.ptr(self.top_l),
-                                                         B, H, self.h0, self.kl, self.kc, self.px.ref, off, slab, ch, st),
-                            "pack_candidates_peer")
-                    L.check(lib.upk_unpack_candidates_peer(self.px.ref, off, slab, ch, B, H, self.kc, L.ptr(self.resid),
-                                                           L.ptr(self.Rs), L.ptr(self.ts), st), "unpack_candidates_peer")
-                else:
-                    L.check(lib.upk_pack_candidates(L.ptr(self.resid), L.ptr(self.Rs), L.ptr(self.ts), L.ptr(self.top_l), B, H,
-                                                    self.h0, self.kl, self.kc, L.ptr(self.cand), st), "pack_candidates")
-                    dist.all_gather_into_tensor(self.allc, self.cand, group=self.group)           # collective #1
-                    L.check(lib.upk_unpack_candidates(L.ptr(self.allc), self.world, self.rank, B, H, self.kc,
-                                                      L.ptr(self.resid), L.ptr(self.Rs), L.ptr(self.ts), st),
-                            "unpack_candidates")
-            L.check(lib.upk_topk_smallest(L.ptr(self.resid), B, H, K, L.ptr(self.top), st), "topk_global")
-            if self.px is not None:                                                                # exchange #2, peer memory
-                ch, off, slab = self.ch2
-                L.check(lib.upk_score_hypotheses_peer(L.ptr(pts1), L.ptr(pts2), L.ptr(self.w1), L.ptr(self.Rs),
-                                                      L.ptr(self.ts), L.ptr(self.top), B, N1, N2, H, K, self.k0, self.k1,
-                                                      self.px.ref, off, slab, ch, st), "score_hypotheses_peer")
-                L.check(lib.upk_select_best_peer(self.px.ref, off, slab, ch, L.ptr(self.top), L.ptr(self.Rs), L.ptr(self.ts),
-                                                 B, H, K, L.ptr(self.R), L.ptr(self.t), L.ptr(self.sc), L.ptr(self.pool), st),
-                        "select_best_peer")
+            if self.world == 1:
+                L.check(lib.upk_topk_smallest(L.ptr(self.resid), B, H, K, L.ptr(self.top), st), "topk_global")
+                L.check(lib.upk_score_hypotheses(L.ptr(pts1), L.ptr(pts2), L.ptr(self.w1), L.ptr(self.Rs), L.ptr(self.ts),
+                                                 L.ptr(self.top), B, N1, N2, H, K, 0, K, L.ptr(self.scores), st),
+                        "score_hypotheses")
+                L.check(lib.upk_select_best(L.ptr(self.scores), L.ptr(self.top), L.ptr(self.Rs), L.ptr(self.ts), B, H, K,
+                                            L.ptr(self.R), L.ptr(self.t), L.ptr(self.sc), L.ptr(self.pool), st), "select_best")
                 return self.R, self.t, self.sc, self.pool
-            if self.world > 1:
-                L.check(lib.upk_fill_f32(L.ptr(self.scores), self.scores.numel(), float("-inf"), st), "fill")
-            L.check(lib.upk_score_hypotheses(L.ptr(pts1), L.ptr(pts2), L.ptr(self.w1), L.ptr(self.Rs), L.ptr(self.ts),
-                                             L.ptr(self.top), B, N1, N2, H, K, self.k0, self.k1, L.ptr(self.scores), st),
+            # ---- my slice's K best (the top-K kernel on the slice of the pool array, row pitch H)
+            if self.kl > 0:
+                L.check(lib.upk_topk_smallest_ld(self.resid.data_ptr() + 4 * self.h0, B, self.h1 - self.h0, H, self.kl,
+                                                 L.ptr(self.top_l), st), "topk_local")
+            nc = self.world * self.kc
+            if self.px is not None:                                                            # exchange #1, peer memory
+                ch, off, slab = self.ch1
+                L.check(lib.upk_pack_candidates_peer(L.ptr(self.resid), L.ptr(self.Rs), L.ptr(self.ts), L.ptr(self.top_l),
+                                                     B, H, self.h0, self.kl, self.kc, self.px.ref, off, slab, ch, st),
+                        "pack_candidates_peer")
+                L.check(lib.upk_unpack_candidates_compact_peer(self.px.ref, off, slab, ch, B, self.kc, L.ptr(self.resid_c),
+                                                               L.ptr(self.Rs_c), L.ptr(self.ts_c), L.ptr(self.pool_c), st),
+                        "unpack_candidates_compact_peer")
+            else:
+                L.check(lib.upk_pack_candidates(L.ptr(self.resid), L.ptr(self.Rs), L.ptr(self.ts), L.ptr(self.top_l), B, H,
+                                                self.h0, self.kl, self.kc, L.ptr(self.cand), st), "pack_candidates")
+                dist.all_gather_into_tensor(self.allc, self.cand, group=self.group)           # collective #1
+                L.check(lib.upk_unpack_candidates_compact(L.ptr(self.allc), self.world, B, self.kc, L.ptr(self.resid_c),
+                                                          L.ptr(self.Rs_c), L.ptr(self.ts_c), L.ptr(self.pool_c), st),
+                        "unpack_candidates_compact")
+            # ---- global top-K over the world * kc candidates (compact order == pool-index order: same tie rule)
+            L.check(lib.upk_topk_smallest(L.ptr(self.resid_c), B, nc, K, L.ptr(self.top), st), "topk_global")
+            if self.px is not None:                                                            # exchange #2, peer memory
+                ch, off, slab = self.ch2
+                L.check(lib.upk_score_hypotheses_peer(L.ptr(pts1), L.ptr(pts2), L.ptr(self.w1), L.ptr(self.Rs_c),
+                                                      L.ptr(self.ts_c), L.ptr(self.top), B, N1, N2, nc, K, self.k0, self.k1,
+                                                      self.px.ref, off, slab, ch, st), "score_hypotheses_peer")
+                L.check(lib.upk_select_best_peer(self.px.ref, off, slab, ch, L.ptr(self.top), L.ptr(self.Rs_c),
+                                                 L.ptr(self.ts_c), L.ptr(self.pool_c), B, nc, K, L.ptr(self.R), L.ptr(self.t),
+                                                 L.ptr(self.sc), L.ptr(self.pool), st), "select_best_peer")
+                return self.R, self.t, self.sc, self.pool
+            L.check(lib.upk_fill_f32(L.ptr(self.scores), self.scores.numel(), float("-inf"), st), "fill")
+            L.check(lib.upk_score_hypotheses(L.ptr(pts1), L.ptr(pts2), L.ptr(self.w1), L.ptr(self.Rs_c), L.ptr(self.ts_c),
+                                             L.ptr(self.top), B, N1, N2, nc, K, self.k0, self.k1, L.ptr(self.scores), st),
                     "score_hypotheses")
-            if self.world > 1:
-                dist.all_reduce(self.scores, op=dist.ReduceOp.MAX, group=self.group)             # collective #2
-            L.check(lib.upk_select_best(L.ptr(self.scores), L.ptr(self.top), L.ptr(self.Rs), L.ptr(self.ts), B, H, K,
-                                        L.ptr(self.R), L.ptr(self.t), L.ptr(self.sc), L.ptr(self.pool), st), "select_best")
+            dist.all_reduce(self.scores, op=dist.ReduceOp.MAX, group=self.group)                 # collective #2
+            L.check(lib.upk_select_best_map(L.ptr(self.scores), L.ptr(self.top), L.ptr(self.Rs_c), L.ptr(self.ts_c),
+                                            L.ptr(self.pool_c), B, nc, K, L.ptr(self.R), L.ptr(self.t), L.ptr(self.sc),
+                                            L.ptr(self.pool), st), "select_best_map")
         return self.R, self.t, self.sc, self.pool
 
 
