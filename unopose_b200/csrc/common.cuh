@@ -132,7 +132,7 @@ __device__ __forceinline__ float nn_min_expansion(const float* __restrict__ mx, 
 __device__ __forceinline__ void nn_min_expansion2(const float* __restrict__ mx, const float* __restrict__ my,
                                                   const float* __restrict__ mz, const float* __restrict__ mn,
                                                   int nm_pad, const float (&xa)[4], const float (&xb)[4],
-                                                  float& best_a, float& best_b) {
+                                                  float& best_a, float& best_b, int first = 0, const int step = 4) {
   const unsigned long long A0 = pack2(xa[0], xa[0]), A1 = pack2(xa[1], xa[1]), A2 = pack2(xa[2], xa[2]);
   const unsigned long long AX = pack2(xa[3], xa[3]);
   const unsigned long long B0 = pack2(xb[0], xb[0]), B1 = pack2(xb[1], xb[1]), B2 = pack2(xb[2], xb[2]);
@@ -140,7 +140,7 @@ __device__ __forceinline__ void nn_min_expansion2(const float* __restrict__ mx, 
   const unsigned long long M2 = pack2(-2.0f, -2.0f);
   float ba = INFINITY, bb = INFINITY;
 #pragma unroll 2
-  for (int j = 0; j < nm_pad; j += 4) {
+  for (int j = first; j < nm_pad; j += step) {
     const ulonglong2 qx = *reinterpret_cast<const ulonglong2*>(mx + j);
     const ulonglong2 qy = *reinterpret_cast<const ulonglong2*>(my + j);
     const ulonglong2 qz = *reinterpret_cast<const ulonglong2*>(mz + j);

@@ -100,11 +100,14 @@ k_weighted_kabsch(const float* __restrict__ src, const float* __restrict__ ref,
 
 // Inlier score (model_utils.py:558-564): X = (pts1 - t) @ R; d_i = NN distance to the model cloud
 // (expansion form, clamp, sqrt); score = sum_fg[d<thr] / (n_fg + 1e-8) * n_fg / N1.
-// FS_PARTS threads share a query point, each scanning interleaved groups of the staged model tile (min via
+// FS_PARTS threads share a PAIR of query points (the four LDS.128 of a scan step serve both, two dependency chains
+// interleave — nn_min_expansion2, like k_score), each scanning interleaved groups of the staged model tile (min via
 // shuffles); the last CTA of an instance (ticket counter) turns the integer counts into the score.
-constexpr int FS_THREADS = 128;
-constexpr int FS_PARTS = 2;
-constexpr int FS_QPB = FS_THREADS / FS_PARTS;   // 64 query points per CTA
+// 256 threads x 2 queries / 4 parts = 128 query points per CTA (round 1: 128 threads, one query per thread, 2 parts:
+// 31 us at B = 16 with 3.5 warps per scheduler and one LDS.128 per point and query).
+constexpr int FS_THREADS = 256;
+constexpr int FS_PARTS = 4;
+constexpr int FS_QPB = 2 * FS_THREADS / FS_PARTS;   // 128 query points per CTA
 constexpr int FS_TILE = 2048;
 
 __global__ void __launch_bounds__(FS_THREADS)
@@ -116,21 +119,23 @@ k_fine_inliers(const float* __restrict__ pts1, const float* __restrict__ model,
   __shared__ int s_cnt[2];
   const int b = blockIdx.y;
   const int part = threadIdx.x & (FS_PARTS - 1);
-  const int i = blockIdx.x * FS_QPB + threadIdx.x / FS_PARTS;
+  const int ia = blockIdx.x * FS_QPB + 2 * (threadIdx.x / FS_PARTS), ib = ia + 1;   // this thread's two query points
   const float* R = Rm + (size_t)b * 9;
   const float* t = tv + (size_t)b * 3;
   if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
-  float x0 = 0.f, x1 = 0.f, x2 = 0.f, xx = 0.f;
-  const bool ok = i < n1;
-  if (ok) {
+  float xa[4] = {0.f, 0.f, 0.f, 0.f}, xb[4] = {0.f, 0.f, 0.f, 0.f};
+  const bool oka = ia < n1, okb = ib < n1;
+  auto moved = [&](int i, float (&x)[4]) {
     const float* p = pts1 + ((size_t)b * n1 + i) * 3;
-    float d0 = p[0] - t[0], d1 = p[1] - t[1], d2 = p[2] - t[2];
-    x0 = fmaf(d2, R[6], fmaf(d1, R[3], d0 * R[0]));
-    x1 = fmaf(d2, R[7], fmaf(d1, R[4], d0 * R[1]));
-    x2 = fmaf(d2, R[8], fmaf(d1, R[5], d0 * R[2]));
-    xx = sumsq3_torch(x0, x1, x2);
-  }
-  float best = INFINITY;
+    const float d0 = p[0] - t[0], d1 = p[1] - t[1], d2 = p[2] - t[2];
+    x[0] = fmaf(d2, R[6], fmaf(d1, R[3], d0 * R[0]));
+    x[1] = fmaf(d2, R[7], fmaf(d1, R[4], d0 * R[1]));
+    x[2] = fmaf(d2, R[8], fmaf(d1, R[5], d0 * R[2]));
+    x[3] = sumsq3_torch(x[0], x[1], x[2]);
+  };
+  if (oka) moved(ia, xa);
+  if (okb) moved(ib, xb);
+  float best_a = INFINITY, best_b = INFINITY;
   const float* mb = model + (size_t)b * nm * 3;
   for (int j0 = 0; j0 < nm; j0 += FS_TILE) {
     const int tn = min(FS_TILE, nm - j0);
@@ -139,17 +144,33 @@ k_fine_inliers(const float* __restrict__ pts1, const float* __restrict__ model,
     __syncthreads();
     stage_model_soa(mb + (size_t)j0 * 3, tn, tn_pad, mx, my, mz, mn);
     __syncthreads();
-    // the four threads of a query take interleaved groups of 4 points: their LDS.128 hit distinct banks
-    best = fminf(best, nn_min_expansion(mx, my, mz, mn, tn_pad, x0, x1, x2, xx, 4 * part, 4 * FS_PARTS));
+    // the four threads of a query pair take interleaved groups of 4 points: their LDS.128 hit distinct banks
+    float ba, bb;
+    nn_min_expansion2(mx, my, mz, mn, tn_pad, xa, xb, ba, bb, 4 * part, 4 * FS_PARTS);
+    best_a = fminf(best_a, ba);
+    best_b = fminf(best_b, bb);
   }
 #pragma unroll
-  for (int o = 1; o < FS_PARTS; o <<= 1) best = fminf(best, __shfl_xor_sync(kFull, best, o));
+  for (int o = 1; o < FS_PARTS; o <<= 1) {
+    best_a = fminf(best_a, __shfl_xor_sync(kFull, best_a, o));
+    best_b = fminf(best_b, __shfl_xor_sync(kFull, best_b, o));
+  }
   int inl = 0, fg = 0;
-  if (ok && part == 0) {
-    float dist = sqrtf(fmaxf(best, 0.f));
-    if (nn_out) nn_out[(size_t)b * n1 + i] = dist;
-    fg = w1[(size_t)b * n1 + i] > 0.f ? 1 : 0;
-    inl = (dist < thr && fg) ? 1 : 0;
+  if (part == 0) {
+    if (oka) {
+      const float dist = sqrtf(fmaxf(best_a, 0.f));
+      if (nn_out) nn_out[(size_t)b * n1 + ia] = dist;
+      const int f = w1[(size_t)b * n1 + ia] > 0.f ? 1 : 0;
+      fg += f;
+      inl += (dist < thr && f) ? 1 : 0;
+    }
+    if (okb) {
+      const float dist = sqrtf(fmaxf(best_b, 0.f));
+      if (nn_out) nn_out[(size_t)b * n1 + ib] = dist;
+      const int f = w1[(size_t)b * n1 + ib] > 0.f ? 1 : 0;
+      fg += f;
+      inl += (dist < thr && f) ? 1 : 0;
+    }
   }
   inl = __reduce_add_sync(kFull, inl);
   fg = __reduce_add_sync(kFull, fg);
