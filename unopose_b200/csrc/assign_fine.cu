@@ -34,6 +34,8 @@
 #include "common.cuh"
 #include "launch_count.h"
 #include "pose_internal.h"
+#include "tc_ptx.cuh"
+#include "../../include/unopose_b200.h"
 
 namespace upk {
 
@@ -664,6 +666,367 @@ k_fine_rows(const float* __restrict__ atten, int R, int C, int ld, int nstrip, c
   else rows_body<true, VEC>(A, R, ld, nstrip, t, kc, px, py, pz, rml, rmul, rowpart4);
 }
 
+// ------------------------------------------------------------------ passes 2 and 3 fed by TMA (round 2)
+// The register-streaming kernels above top out at 50-55 % of the HBM copy bandwidth: a CTA lives for one 128 x 256 tile
+// (128 KB, ~6 us), and its prologue (column constants, first row pair) and epilogue are only covered by the ONE other CTA
+// of the SM.  With the pitched layout the main block is a TMA-addressable plane, so these variants are persistent:
+// 2 CTAs per SM walk the tile list (strips fastest: the CTAs running side by side read whole rows);
+//   * a producer thread keeps a ring of 16-row x 256-column boxes (16 KB each) in flight ACROSS tile boundaries
+//     (cp.async.bulk.tensor, mbarrier complete_tx);
+//   * eight consumer warps take one row pair per stage out of shared memory (LDS.128, the lane -> column mapping of the
+//     VEC loads, so every partial is bit-identical to the kernels above) and hand the slot back as soon as the pair
+//     sits in registers;
+//   * a constants warp runs one tile ahead: it stages the tile's column / row constants in shared memory (double
+//     buffered, mbarrier hand-off) and computes the two border vectors of pass 2 (S[i][0], S[0][j]) itself, so the
+//     consumers never wait for a global load.
+// Full tiles only ((R - 1) % 128 == 0, (C - 1) % 256 == 0: the UNOPose fine shape); everything else takes the kernels above.
+constexpr int FT_ROWS = 16;                          // rows per stage: one pair per consumer warp
+constexpr int FT_STAGE_FLOATS = FT_ROWS * F2_TC;     // 16 KB
+constexpr int FT_SPT = F2_RT / FT_ROWS;              // 8 stages per tile
+constexpr int FT_THREADS = F2_THREADS + 64;          // + the producer warp + the constants warp
+static_assert(FT_ROWS == 2 * F2_WARPS, "one row pair per consumer warp and stage");
+
+// per-tile constants: NCOL column arrays of F2_TC floats, then rml | rmul of the tile's F2_RT rows
+template <int STAGES, int NCOL, bool CM>
+struct FtSmem {
+  alignas(128) float buf[STAGES][FT_STAGE_FLOATS];
+  alignas(16) float cst[2][NCOL * F2_TC + 2 * F2_RT];
+  float cm[CM ? 2 : 1][CM ? F2_WARPS : 1][CM ? F2_TC : 1];
+  unsigned long long full[STAGES], empty[STAGES], cfull[2], cempty[2];
+};
+
+struct FtTile { int b, rt, cs; };
+__device__ __forceinline__ FtTile ft_tile(int T, int nb, int nrt, int nstrip, bool flip) {
+  FtTile t;
+  const int per = nrt * nstrip;
+  const int bb = T / per, rem = T - bb * per;
+  t.b = flip ? nb - 1 - bb : bb;
+  t.rt = rem / nstrip;
+  t.cs = rem - t.rt * nstrip;
+  return t;
+}
+
+template <int STAGES, class Smem>
+__device__ __forceinline__ void ft_producer(const CUtensorMap* map, Smem& sm, int ntile, int nb, int nrt, int nstrip,
+                                            bool flip) {
+  int s = 0;
+  uint32_t ph = 0;
+  for (int T = blockIdx.x; T < ntile; T += gridDim.x) {
+    const FtTile t = ft_tile(T, nb, nrt, nstrip, flip);
+    for (int q = 0; q < FT_SPT; ++q) {
+      mbar_wait(&sm.empty[s], ph ^ 1);
+      mbar_expect_tx(&sm.full[s], FT_STAGE_FLOATS * sizeof(float));
+      tma_load_3d(map, &sm.full[s], sm.buf[s], t.cs * F2_TC, t.rt * F2_RT + q * FT_ROWS, t.b);
+      if (++s == STAGES) { s = 0; ph ^= 1; }
+    }
+  }
+}
+
+// this warp's row pair of stage `s` out of shared memory; the slot is released once every lane holds its values
+template <class Smem>
+__device__ __forceinline__ void ft_take_pair(Smem& sm, int s, uint32_t ph, int warp, int lane, RowPair& v) {
+  mbar_wait(&sm.full[s], ph);
+  const float* ra = sm.buf[s] + (2 * warp) * F2_TC + 4 * lane;
+  const float4 x0 = *reinterpret_cast<const float4*>(ra), x1 = *reinterpret_cast<const float4*>(ra + 128);
+  const float4 y0 = *reinterpret_cast<const float4*>(ra + F2_TC), y1 = *reinterpret_cast<const float4*>(ra + F2_TC + 128);
+  v.a[0] = x0.x; v.a[1] = x0.y; v.a[2] = x0.z; v.a[3] = x0.w; v.a[4] = x1.x; v.a[5] = x1.y; v.a[6] = x1.z; v.a[7] = x1.w;
+  v.b[0] = y0.x; v.b[1] = y0.y; v.b[2] = y0.z; v.b[3] = y0.w; v.b[4] = y1.x; v.b[5] = y1.y; v.b[6] = y1.z; v.b[7] = y1.w;
+  __syncwarp();
+  if (lane == 0) mbar_arrive(&sm.empty[s]);
+}
+
+template <int STAGES, class Smem>
+__device__ __forceinline__ void ft_init(Smem& sm) {
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], F2_WARPS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sm.cfull[i], 1); mbar_init(&sm.cempty[i], F2_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+}
+
+// a lane's 8 values of column array `a` (the VEC lane -> column mapping) as 4 packed pairs
+__device__ __forceinline__ void ft_col8(const float* a, int lane, unsigned long long (&o)[F2_CPT / 2]) {
+  const float4 lo = *reinterpret_cast<const float4*>(a + 4 * lane), hi = *reinterpret_cast<const float4*>(a + 128 + 4 * lane);
+  o[0] = pack2(lo.x, lo.y); o[1] = pack2(lo.z, lo.w); o[2] = pack2(hi.x, hi.y); o[3] = pack2(hi.z, hi.w);
+}
+// lane q < 16 holds the constants of the warp's q-th row of a tile (stage q >> 1, half q & 1): its tile-local row
+__device__ __forceinline__ int ft_lane_lrow(int warp, int lane) {
+  const int q = lane & 15;
+  return 2 * warp + FT_ROWS * (q >> 1) + (q & 1);
+}
+
+constexpr int FT_LABEL_STAGES = 5;
+constexpr int FT_ROWS_STAGES = 6;
+
+__global__ void __launch_bounds__(FT_THREADS, 2)
+k_fine_labels_tma(const __grid_constant__ CUtensorMap map, const float* __restrict__ atten, int nb, int R, int C, int ld,
+                  int nstrip, int nrt, const float* __restrict__ rml, const float* __restrict__ rmul,
+                  const float* __restrict__ cml, const float* __restrict__ cmul, float* __restrict__ rowpm,
+                  float* __restrict__ colpm, float* __restrict__ ai0, float* __restrict__ a0j, int flip) {
+  extern __shared__ unsigned char ft_raw[];
+  using Smem = FtSmem<FT_LABEL_STAGES, 2, true>;
+  Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(ft_raw) + 127) & ~(uintptr_t)127);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntile = nb * nrt * nstrip;
+  ft_init<FT_LABEL_STAGES>(sm);
+  if (warp == F2_WARPS) {
+    if (lane == 0) ft_producer<FT_LABEL_STAGES>(&map, sm, ntile, nb, nrt, nstrip, flip != 0);
+    return;
+  }
+  if (warp == F2_WARPS + 1) {
+    // ===== constants warp: cst = -cml[256] | cmul[256] | rml[128] | rmul[128]; border vectors straight to global
+    int it = 0;
+    for (int T = blockIdx.x; T < ntile; T += gridDim.x, ++it) {
+      const FtTile t = ft_tile(T, nb, nrt, nstrip, flip != 0);
+      const size_t oc = (size_t)t.b * C + 1 + t.cs * F2_TC, orw = (size_t)t.b * R + 1 + t.rt * F2_RT;
+      float l[F2_CPT], m[F2_CPT], rl[F2_RT / 32], rm[F2_RT / 32];
+#pragma unroll
+      for (int k = 0; k < F2_CPT; ++k) { l[k] = -cml[oc + lane + 32 * k]; m[k] = cmul[oc + lane + 32 * k]; }
+#pragma unroll
+      for (int k = 0; k < F2_RT / 32; ++k) { rl[k] = rml[orw + lane + 32 * k]; rm[k] = rmul[orw + lane + 32 * k]; }
+      mbar_wait(&sm.cempty[it & 1], ((it >> 1) & 1) ^ 1);
+      float* c = sm.cst[it & 1];
+#pragma unroll
+      for (int k = 0; k < F2_CPT; ++k) { c[lane + 32 * k] = l[k]; c[F2_TC + lane + 32 * k] = m[k]; }
+#pragma unroll
+      for (int k = 0; k < F2_RT / 32; ++k) { c[2 * F2_TC + lane + 32 * k] = rl[k]; c[2 * F2_TC + F2_RT + lane + 32 * k] = rm[k]; }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.cfull[it & 1]);
+      const float* A = atten + (size_t)t.b * R * ld;
+      if (t.cs == 0) {   // S[i][0] of the tile's rows (the background column is in no box)
+        const float cml0 = cml[(size_t)t.b * C], cmul0 = cmul[(size_t)t.b * C];
+#pragma unroll
+        for (int k = 0; k < F2_RT / 32; ++k) {
+          const float v0 = A[(size_t)(1 + t.rt * F2_RT + lane + 32 * k) * ld];
+          ai0[orw + lane + 32 * k] = (ex2_approx(fmaf(v0, 2.f * kL2E, -(rl[k] + cml0))) * rm[k]) * cmul0;
+        }
+      }
+      if (t.rt == 0) {   // S[0][j] of the strip's columns (the background row is in no maximum)
+        const float rml0 = rml[(size_t)t.b * R], rmul0 = rmul[(size_t)t.b * R];
+        const unsigned long long L2 = pack2(2.f * kL2E, 2.f * kL2E), NR = pack2(-rml0, -rml0), M0 = pack2(rmul0, rmul0);
+#pragma unroll
+        for (int k = 0; k < F2_CPT; k += 2) {
+          // the arithmetic of row_exps / labels_body on the pair (k, k + 1), whatever columns the pair holds
+          const float va = A[1 + t.cs * F2_TC + lane + 32 * k], vb = A[1 + t.cs * F2_TC + lane + 32 * (k + 1)];
+          float x0, x1, a0, a1;
+          unpack2(fma2(pack2(va, vb), L2, add2(NR, pack2(l[k], l[k + 1]))), x0, x1);
+          unpack2(mul2(mul2(pack2(ex2_approx(x0), ex2_approx(x1)), M0), pack2(m[k], m[k + 1])), a0, a1);
+          a0j[oc + lane + 32 * k] = a0;
+          a0j[oc + lane + 32 * (k + 1)] = a1;
+        }
+      }
+    }
+    return;
+  }
+  int s = 0, it = 0;
+  uint32_t ph = 0;
+  for (int T = blockIdx.x; T < ntile; T += gridDim.x, ++it) {
+    const FtTile t = ft_tile(T, nb, nrt, nstrip, flip != 0);
+    ColConst2 kc;
+    mbar_wait(&sm.cfull[it & 1], (it >> 1) & 1);
+    const float* c = sm.cst[it & 1];
+    ft_col8(c, lane, kc.ncml);
+    ft_col8(c + F2_TC, lane, kc.cmul);
+    const int lrow = ft_lane_lrow(warp, lane);
+    const float my_rml = c[2 * F2_TC + lrow], my_rmul = c[2 * F2_TC + F2_RT + lrow];
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm.cempty[it & 1]);
+    float cmx[F2_CPT];
+#pragma unroll
+    for (int k = 0; k < F2_CPT; ++k) cmx[k] = -INFINITY;
+#pragma unroll 1
+    for (int st = 0; st < FT_SPT; ++st) {
+      RowPair cur;
+      ft_take_pair(sm, s, ph, warp, lane, cur);
+      if (++s == FT_LABEL_STAGES) { s = 0; ph ^= 1; }
+      const float rmla = __shfl_sync(kFull, my_rml, 2 * st), rmula = __shfl_sync(kFull, my_rmul, 2 * st);
+      const float rmlb = __shfl_sync(kFull, my_rml, 2 * st + 1), rmulb = __shfl_sync(kFull, my_rmul, 2 * st + 1);
+      unsigned long long ea[F2_CPT / 2], eb[F2_CPT / 2];
+      row_exps(cur.a, -rmla, kc, ea);
+      row_exps(cur.b, -rmlb, kc, eb);
+      const unsigned long long MA = pack2(rmula, rmula), MB = pack2(rmulb, rmulb);
+      float ma = -INFINITY, mb = -INFINITY;
+#pragma unroll
+      for (int kk = 0; kk < F2_CPT / 2; ++kk) {
+        float a0, a1, b0, b1;
+        unpack2(mul2(mul2(ea[kk], MA), kc.cmul[kk]), a0, a1);
+        unpack2(mul2(mul2(eb[kk], MB), kc.cmul[kk]), b0, b1);
+        ma = fmaxf(ma, fmaxf(a0, a1));
+        mb = fmaxf(mb, fmaxf(b0, b1));
+        cmx[2 * kk] = fmaxf(cmx[2 * kk], fmaxf(a0, b0));
+        cmx[2 * kk + 1] = fmaxf(cmx[2 * kk + 1], fmaxf(a1, b1));
+      }
+      const float m = reduce_pair(ma, mb, lane, F2Max());
+      const size_t oa = (size_t)t.b * R + 1 + t.rt * F2_RT + 2 * warp + FT_ROWS * st;
+      if (lane == 0) rowpm[oa * nstrip + t.cs] = m;
+      if (lane == 16) rowpm[(oa + 1) * nstrip + t.cs] = m;
+    }
+    // column maxima of the tile: combine the 8 warps (double-buffered: one named barrier per tile)
+    float (*cm)[F2_TC] = sm.cm[it & 1];
+#pragma unroll
+    for (int k = 0; k < F2_CPT; ++k) cm[warp][f2_lcol<true>(lane, k)] = cmx[k];
+    asm volatile("bar.sync 1, %0;" ::"n"(F2_THREADS) : "memory");
+    {
+      const int cc = threadIdx.x;
+      float m = -INFINITY;
+#pragma unroll
+      for (int w = 0; w < F2_WARPS; ++w) m = fmaxf(m, cm[w][cc]);
+      colpm[((size_t)t.b * C + 1 + t.cs * F2_TC + cc) * nrt + t.rt] = m;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(FT_THREADS, 2)
+k_fine_rows_tma(const __grid_constant__ CUtensorMap map, int nb, int R, int C, int nstrip, int nrt,
+                const float* __restrict__ rml, const float* __restrict__ rmul, const float* __restrict__ cml,
+                const float* __restrict__ cmul, const float* __restrict__ w2, const float* __restrict__ pts2,
+                float4* __restrict__ rowpart4) {
+  extern __shared__ unsigned char ft_raw[];
+  using Smem = FtSmem<FT_ROWS_STAGES, 5, false>;
+  Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(ft_raw) + 127) & ~(uintptr_t)127);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntile = nb * nrt * nstrip;
+  const int N1 = R - 1;
+  ft_init<FT_ROWS_STAGES>(sm);
+  if (warp == F2_WARPS) {
+    if (lane == 0) ft_producer<FT_ROWS_STAGES>(&map, sm, ntile, nb, nrt, nstrip, false);
+    return;
+  }
+  if (warp == F2_WARPS + 1) {
+    // ===== constants warp: cst = -cml | cmul * w2 | x | y | z (256 each) | rml[128] | rmul[128]
+    int it = 0;
+    for (int T = blockIdx.x; T < ntile; T += gridDim.x, ++it) {
+      const FtTile t = ft_tile(T, nb, nrt, nstrip, false);
+      const size_t oc = (size_t)t.b * C + 1 + t.cs * F2_TC, orw = (size_t)t.b * R + 1 + t.rt * F2_RT;
+      const size_t ow = (size_t)t.b * (C - 1) + t.cs * F2_TC;
+      float l[F2_CPT], m[F2_CPT], rl[F2_RT / 32], rm[F2_RT / 32], xyz[3 * F2_CPT];
+#pragma unroll
+      for (int k = 0; k < F2_CPT; ++k) {
+        l[k] = -cml[oc + lane + 32 * k];
+        m[k] = cmul[oc + lane + 32 * k];
+        m[k] *= w2[ow + lane + 32 * k];
+      }
+#pragma unroll
+      for (int k = 0; k < 3 * F2_CPT; ++k) xyz[k] = pts2[ow * 3 + lane + 32 * k];   // 768 consecutive floats, AoS
+#pragma unroll
+      for (int k = 0; k < F2_RT / 32; ++k) { rl[k] = rml[orw + lane + 32 * k]; rm[k] = rmul[orw + lane + 32 * k]; }
+      mbar_wait(&sm.cempty[it & 1], ((it >> 1) & 1) ^ 1);
+      float* c = sm.cst[it & 1];
+#pragma unroll
+      for (int k = 0; k < F2_CPT; ++k) { c[lane + 32 * k] = l[k]; c[F2_TC + lane + 32 * k] = m[k]; }
+#pragma unroll
+      for (int k = 0; k < 3 * F2_CPT; ++k) {
+        const int e = lane + 32 * k, j = e / 3, a = e - 3 * j;   // AoS element e -> column j, component a
+        c[(2 + a) * F2_TC + j] = xyz[k];
+      }
+#pragma unroll
+      for (int k = 0; k < F2_RT / 32; ++k) { c[5 * F2_TC + lane + 32 * k] = rl[k]; c[5 * F2_TC + F2_RT + lane + 32 * k] = rm[k]; }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.cfull[it & 1]);
+    }
+    return;
+  }
+  int s = 0, it = 0;
+  uint32_t ph = 0;
+  for (int T = blockIdx.x; T < ntile; T += gridDim.x, ++it) {
+    const FtTile t = ft_tile(T, nb, nrt, nstrip, false);
+    ColConst2 kc;
+    unsigned long long px[F2_CPT / 2], py[F2_CPT / 2], pz[F2_CPT / 2];
+    mbar_wait(&sm.cfull[it & 1], (it >> 1) & 1);
+    const float* c = sm.cst[it & 1];
+    ft_col8(c, lane, kc.ncml);
+    ft_col8(c + F2_TC, lane, kc.cmul);
+    ft_col8(c + 2 * F2_TC, lane, px);
+    ft_col8(c + 3 * F2_TC, lane, py);
+    ft_col8(c + 4 * F2_TC, lane, pz);
+    const int lrow = ft_lane_lrow(warp, lane);
+    const float my_rml = c[5 * F2_TC + lrow], my_rmul = c[5 * F2_TC + F2_RT + lrow];
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm.cempty[it & 1]);
+#pragma unroll 1
+    for (int st = 0; st < FT_SPT; ++st) {
+      RowPair cur;
+      ft_take_pair(sm, s, ph, warp, lane, cur);
+      if (++s == FT_ROWS_STAGES) { s = 0; ph ^= 1; }
+      const float rmla = __shfl_sync(kFull, my_rml, 2 * st), rmula = __shfl_sync(kFull, my_rmul, 2 * st);
+      const float rmlb = __shfl_sync(kFull, my_rml, 2 * st + 1), rmulb = __shfl_sync(kFull, my_rmul, 2 * st + 1);
+      unsigned long long ea[F2_CPT / 2], eb[F2_CPT / 2];
+      row_exps(cur.a, -rmla, kc, ea);
+      row_exps(cur.b, -rmlb, kc, eb);
+      const unsigned long long Z = pack2(0.f, 0.f);
+      unsigned long long ax = Z, ay = Z, az = Z, aw = Z, bx = Z, by = Z, bz = Z, bw = Z;
+#pragma unroll
+      for (int kk = 0; kk < F2_CPT / 2; ++kk) {
+        const unsigned long long ta = mul2(ea[kk], kc.cmul[kk]), tb = mul2(eb[kk], kc.cmul[kk]);
+        ax = fma2(ta, px[kk], ax); ay = fma2(ta, py[kk], ay); az = fma2(ta, pz[kk], az); aw = add2(aw, ta);
+        bx = fma2(tb, px[kk], bx); by = fma2(tb, py[kk], by); bz = fma2(tb, pz[kk], bz); bw = add2(bw, tb);
+      }
+      float acc[8], u0, u1;
+      unpack2(ax, u0, u1); acc[0] = u0 + u1;
+      unpack2(ay, u0, u1); acc[1] = u0 + u1;
+      unpack2(az, u0, u1); acc[2] = u0 + u1;
+      unpack2(aw, u0, u1); acc[3] = u0 + u1;
+      unpack2(bx, u0, u1); acc[4] = u0 + u1;
+      unpack2(by, u0, u1); acc[5] = u0 + u1;
+      unpack2(bz, u0, u1); acc[6] = u0 + u1;
+      unpack2(bw, u0, u1); acc[7] = u0 + u1;
+      {   // same exchange tree as rows_body: afterwards lane group (lane >> 2) holds component (lane >> 2)
+        int off = 16;
+#pragma unroll
+        for (int n = 8; n > 1; n >>= 1, off >>= 1) {
+          const bool upper = (lane & off) != 0;
+#pragma unroll
+          for (int i = 0; i < n / 2; ++i) {
+            const float send = upper ? acc[i] : acc[i + n / 2];
+            const float keep = upper ? acc[i + n / 2] : acc[i];
+            acc[i] = keep + __shfl_xor_sync(kFull, send, off);
+          }
+        }
+        acc[0] += __shfl_xor_sync(kFull, acc[0], 2);
+        acc[0] += __shfl_xor_sync(kFull, acc[0], 1);
+      }
+      if ((lane & 3) == 0) {
+        const int cmp = lane >> 2;
+        const bool isb = cmp >= 4;
+        const int row = 1 + t.rt * F2_RT + 2 * warp + FT_ROWS * st + (isb ? 1 : 0);
+        float* dst = reinterpret_cast<float*>(rowpart4 + ((size_t)t.b * N1 + row - 1) * nstrip + t.cs) + (cmp & 3);
+        *dst = acc[0] * (isb ? rmulb : rmula);
+      }
+    }
+  }
+}
+
+// TMA-fed passes: pitched 128-bit-aligned layout, whole tiles only.  UPK_FINE_TMA=0 keeps the register-streaming kernels.
+static bool fine_tma_ok(const float* atten, int ld, int R, int C) {
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("UPK_FINE_TMA"); enabled = e ? atoi(e) : 1; }
+  return enabled && R > 1 && C > 1 && (R - 1) % F2_RT == 0 && (C - 1) % F2_TC == 0 && ld % 4 == 0 &&
+         ((reinterpret_cast<uintptr_t>(atten + ld + 1)) & 15) == 0;
+}
+
+static int fine_tma_grid(int ntile) {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return ntile < 2 * sms ? ntile : 2 * sms;
+}
+
+static int launch_fine_labels_tma(const float* atten, int ld, int b, int R, int C, const FineGeom2& f, const AssignWs& ws,
+                                  int flip, cudaStream_t st) {
+  CUtensorMap map;
+  int rc = tc_make_map_plane(&map, atten + ld + 1, b, R - 1, C - 1, ld, (size_t)R * ld, F2_TC, FT_ROWS);
+  if (rc) return rc;
+  const size_t smem = sizeof(FtSmem<FT_LABEL_STAGES, 2, true>) + 128;
+  UPK_CUDA_TRY(cudaFuncSetAttribute(k_fine_labels_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_fine_labels_tma<<<fine_tma_grid(b * f.nrt * f.nstrip), FT_THREADS, smem, st>>>(
+      map, atten, b, R, C, ld, f.nstrip, f.nrt, ws.rmax, ws.rsum, ws.cmax, ws.csum, ws.rowpm, ws.colpm, ws.ai0, ws.a0j, flip);
+  UPK_RETURN_LAST_ERROR();
+}
+
 // ------------------------------------------------------------------ host side
 FineGeom2 fine_geom2(int R, int C) {
   FineGeom2 g;
@@ -688,7 +1051,10 @@ int run_fine_labels2(const float* atten, int ld, const float* score1, int ld1, c
   else k_fine_stats<false><<<grid, F2_THREADS, 0, st>>>(atten, g.R, g.C, ld, f.nstrip, f.nrt, ws.rowpart, ws.colpart, ws.flags);
   k_fine_stats_merge<<<mg, 256, 0, st>>>(atten, ws.rowpart, ws.colpart, g.R, g.C, ld, f.nstrip, f.nrt, score1, ld1,
                                          score2, ld2, ws.flags, ws.rmax, ws.rsum, ws.cmax, ws.csum);
-  if (vec) k_fine_labels<true><<<grid, F2_THREADS, 0, st>>>(atten, g.R, g.C, ld, f.nstrip, f.nrt, ws.rmax, ws.rsum, ws.cmax, ws.csum,
+  if (fine_tma_ok(atten, ld, g.R, g.C)) {
+    int rc = launch_fine_labels_tma(atten, ld, b, g.R, g.C, f, ws, 0, st);
+    if (rc) return rc;
+  } else if (vec) k_fine_labels<true><<<grid, F2_THREADS, 0, st>>>(atten, g.R, g.C, ld, f.nstrip, f.nrt, ws.rmax, ws.rsum, ws.cmax, ws.csum,
                                                             ws.rowpm, ws.colpm, ws.ai0, ws.a0j, 0);
   else k_fine_labels<false><<<grid, F2_THREADS, 0, st>>>(atten, g.R, g.C, ld, f.nstrip, f.nrt, ws.rmax, ws.rsum, ws.cmax, ws.csum,
                                                              ws.rowpm, ws.colpm, ws.ai0, ws.a0j, 0);
@@ -708,7 +1074,10 @@ int run_fine_labels2_fused(const float* atten, int ld, const float* stats, float
   k_fine_stats_merge_fused<<<mg, 256, 0, st>>>(atten, stats, stats + sg.col_off_floats, sg.npr, sg.npc, gref, nmerge,
                                                g.R, g.C, ld, score1, ld1, score2, ld2, ws.rmax, ws.rsum, ws.cmax, ws.csum);
   // the GEMM wrote the instances in ascending order: start the labels pass on the last ones (still in L2)
-  if (fine_vec_ok(atten, ld))
+  if (fine_tma_ok(atten, ld, g.R, g.C)) {
+    int rc = launch_fine_labels_tma(atten, ld, b, g.R, g.C, f, ws, 1, st);
+    if (rc) return rc;
+  } else if (fine_vec_ok(atten, ld))
     k_fine_labels<true><<<grid, F2_THREADS, 0, st>>>(atten, g.R, g.C, ld, f.nstrip, f.nrt, ws.rmax, ws.rsum, ws.cmax, ws.csum,
                                                      ws.rowpm, ws.colpm, ws.ai0, ws.a0j, 1);
   else
@@ -722,7 +1091,15 @@ int run_fine_rows2(const float* atten, int ld, int b, const AssignGeom& g, const
                    const float* w2, const float* pts2, float4* rowpart4, float* soft, float* asum, cudaStream_t st) {
   const FineGeom2 f = fine_geom2(g.R, g.C);
   const dim3 grid(f.nstrip, f.nrt, b);
-  if (fine_vec_ok(atten, ld))
+  if (fine_tma_ok(atten, ld, g.R, g.C)) {
+    CUtensorMap map;
+    int rc = tc_make_map_plane(&map, atten + ld + 1, b, g.R - 1, g.C - 1, ld, (size_t)g.R * ld, F2_TC, FT_ROWS);
+    if (rc) return rc;
+    const size_t smem = sizeof(FtSmem<FT_ROWS_STAGES, 5, false>) + 128;
+    UPK_CUDA_TRY(cudaFuncSetAttribute(k_fine_rows_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_fine_rows_tma<<<fine_tma_grid(b * f.nrt * f.nstrip), FT_THREADS, smem, st>>>(
+        map, b, g.R, g.C, f.nstrip, f.nrt, ws.rmax, ws.rsum, ws.cmax, ws.csum, w2, pts2, rowpart4);
+  } else if (fine_vec_ok(atten, ld))
     k_fine_rows<true><<<grid, F2_THREADS, 0, st>>>(atten, g.R, g.C, ld, f.nstrip, ws.rmax, ws.rsum, ws.cmax, ws.csum, w2, pts2,
                                                    rowpart4);
   else

@@ -742,6 +742,22 @@ int tc_make_map_f16(void* map, const void* base, int batch, int rows, int K, int
   return make_map_f16((CUtensorMap*)map, base, batch, rows, K, box_rows);
 }
 
+// Plain (unswizzled) fp32 boxes of box_cols x box_rows out of a pitched (batch, rows, cols) matrix: the streaming
+// passes of assign_fine.cu read `atten` through it.  `base` = element (0, 0) of the block the boxes tile, 16-byte aligned.
+int tc_make_map_plane(void* map, const float* base, int batch, int rows, int cols, int ld, size_t batch_stride,
+                      int box_cols, int box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return UPK_ERR_UNSUPPORTED;
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)batch_stride * 4};
+  cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc((CUtensorMap*)map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? UPK_OK : UPK_ERR_INVALID_ARG;
+}
+
 static int g_sim_mode = -1;  // 16 = 3xFP16 on the CTA-pair shapes with normalised operands, 3xTF32 elsewhere (default); 3 = 3xTF32; 1 = 1xTF32; 0 = fp32 SIMT
 
 int similarity_mode() {
