@@ -171,63 +171,174 @@ __device__ __forceinline__ unsigned block_excl_scan_u32(unsigned v, unsigned* s_
   return res;
 }
 
+// CACHED (H <= 8 * TK_THREADS: every pool size of the reference): a thread keeps its contiguous chunk of the row in
+// registers for all four passes and the compaction (one read of the row instead of six).  Histogram updates are
+// warp-aggregated (__match_any_sync): the first pass sees two or three distinct exponent bytes, which serialised
+// thousands of same-address shared atomics; the digit search is a warp scan over 8 bins per lane instead of one thread
+// walking 256 bins (round 1: 17 us per launch, most of it in those two places).
+constexpr int TK_PER = 8;
+
+template <bool CACHED>
 __global__ void __launch_bounds__(TK_THREADS)
-k_topk_smallest(const float* __restrict__ vals, int H, int K, int* __restrict__ top, int ld) {
+k_topk_smallest(const float* __restrict__ vals, int H, int K, int* __restrict__ top, int ld, int* __restrict__ zero_me) {
   __shared__ unsigned hist[256];
   __shared__ unsigned s_warp[33];
   __shared__ unsigned s_prefix, s_kth_rank;
   const int b = blockIdx.x;
+  const int lane = threadIdx.x & 31;
   const unsigned* v = reinterpret_cast<const unsigned*>(vals) + (size_t)b * ld;   // ld >= H: row pitch (a slice of a pool)
   top += (size_t)b * K;
+  if (zero_me && threadIdx.x == 0) zero_me[b] = 0;   // the ticket counter of the scoring launch that follows
+  // each thread owns a contiguous chunk (the compaction below emits in ascending pool index)
+  const int per = (H + TK_THREADS - 1) / TK_THREADS;
+  const int beg = min(H, (int)threadIdx.x * per), end = min(H, beg + per);
+  unsigned x[TK_PER];
+  if (CACHED) {
+#pragma unroll
+    for (int k = 0; k < TK_PER; ++k) x[k] = beg + k < end ? v[beg + k] : 0u;
+  }
   unsigned prefix = 0, mask = 0;
   unsigned want = (unsigned)K;  // rank (1-based) of the K-th smallest within the current bucket
   for (int shift = 24; shift >= 0; shift -= 8) {
-    for (int i = threadIdx.x; i < 256; i += TK_THREADS) hist[i] = 0;
+    if (threadIdx.x < 256) hist[threadIdx.x] = 0;
     __syncthreads();
-    for (int i = threadIdx.x; i < H; i += TK_THREADS) {
-      unsigned x = v[i];
-      if ((x & mask) == prefix) atomicAdd(&hist[(x >> shift) & 255u], 1u);
+    auto vote = [&](bool in, unsigned xv) {
+      const unsigned act = __ballot_sync(kFull, in);
+      if (in) {
+        const unsigned d = (xv >> shift) & 255u;
+        const unsigned peers = __match_any_sync(act, d);
+        if (lane == __ffs(peers) - 1) atomicAdd(&hist[d], (unsigned)__popc(peers));
+      }
+    };
+    if (CACHED) {
+#pragma unroll
+      for (int k = 0; k < TK_PER; ++k) vote(beg + k < end && (x[k] & mask) == prefix, x[k]);
+    } else {
+      for (int i0 = 0; i0 < H; i0 += TK_THREADS) {   // warp-uniform trip count
+        const int i = i0 + threadIdx.x;
+        const unsigned xv = i < H ? v[i] : 0u;
+        vote(i < H && (xv & mask) == prefix, xv);
+      }
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      unsigned acc = 0;
-      int d = 0;
-      for (; d < 256; ++d) {
-        if (acc + hist[d] >= want) break;
-        acc += hist[d];
+    if (threadIdx.x < 32) {   // digit of the K-th smallest: first bin whose inclusive count reaches `want`
+      unsigned c[8], sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { c[j] = hist[8 * lane + j]; sum += c[j]; }
+      unsigned inc = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(kFull, inc, o);
+        if (lane >= o) inc += t;
       }
-      s_prefix = prefix | ((unsigned)d << shift);
-      s_kth_rank = want - acc;
+      const unsigned reach = __ballot_sync(kFull, inc >= want);   // never empty: the bucket holds >= want elements
+      if (lane == __ffs(reach) - 1) {
+        unsigned acc = inc - sum;
+        int j = 0;
+#pragma unroll
+        for (; j < 7; ++j) {
+          if (acc + c[j] >= want) break;
+          acc += c[j];
+        }
+        s_prefix = prefix | ((unsigned)(8 * lane + j) << shift);
+        s_kth_rank = want - acc;
+      }
     }
     __syncthreads();
     prefix = s_prefix;
     want = s_kth_rank;
     mask |= 255u << shift;
-    __syncthreads();
   }
   const unsigned kth = prefix;    // bit pattern of the K-th smallest value
   const unsigned n_equal = want;  // how many elements == kth belong to the selection
-  // ordered compaction: each thread owns a contiguous chunk
-  const int per = (H + TK_THREADS - 1) / TK_THREADS;
-  const int beg = min(H, (int)threadIdx.x * per), end = min(H, beg + per);
+  // ordered compaction: counts of (< kth, == kth) packed in one word (H < 2^16 when CACHED), one block scan
   unsigned nl = 0, ne = 0;
-  for (int i = beg; i < end; ++i) {
-    unsigned x = v[i];
-    nl += x < kth;
-    ne += x == kth;
+  if (CACHED) {
+#pragma unroll
+    for (int k = 0; k < TK_PER; ++k)
+      if (beg + k < end) { nl += x[k] < kth; ne += x[k] == kth; }
+  } else {
+    for (int i = beg; i < end; ++i) {
+      const unsigned xv = v[i];
+      nl += xv < kth;
+      ne += xv == kth;
+    }
   }
-  unsigned tot;
-  unsigned l0 = block_excl_scan_u32(nl, s_warp, tot);
-  unsigned e0 = block_excl_scan_u32(ne, s_warp, tot);
-  for (int i = beg; i < end; ++i) {
-    unsigned x = v[i];
-    if (x < kth) {
+  unsigned tot, l0, e0;
+  if (CACHED) {
+    const unsigned both = block_excl_scan_u32(nl | (ne << 16), s_warp, tot);
+    l0 = both & 0xffffu; e0 = both >> 16;
+  } else {
+    l0 = block_excl_scan_u32(nl, s_warp, tot);
+    e0 = block_excl_scan_u32(ne, s_warp, tot);
+  }
+  auto emit = [&](int i, unsigned xv) {
+    if (xv < kth) {
       top[l0 + min(e0, n_equal)] = i;
       ++l0;
-    } else if (x == kth) {
+    } else if (xv == kth) {
       if (e0 < n_equal) top[l0 + e0] = i;
       ++e0;
     }
+  };
+  if (CACHED) {
+#pragma unroll
+    for (int k = 0; k < TK_PER; ++k)
+      if (beg + k < end) emit(beg + k, x[k]);
+  } else {
+    for (int i = beg; i < end; ++i) emit(i, v[i]);
+  }
+}
+
+static void launch_topk(const float* vals, int b, int n, int ld, int k, int* idx_out, cudaStream_t st,
+                        int* zero_me = nullptr) {
+  if (n <= TK_PER * TK_THREADS) k_topk_smallest<true><<<b, TK_THREADS, 0, st>>>(vals, n, k, idx_out, ld, zero_me);
+  else k_topk_smallest<false><<<b, TK_THREADS, 0, st>>>(vals, n, k, idx_out, ld, zero_me);
+  count_launch();
+}
+
+// arg-max over the K kept hypotheses (first maximum), gather R, t, score, pool index (:486-488); called by every
+// thread of a CTA of at most 8 warps.  VOLATILE_SCORES: the scores were written by other CTAs of the same launch or by
+// peers (read past L1).
+template <bool VOLATILE_SCORES>
+__device__ __forceinline__ void select_best(const float* __restrict__ scores, const int* __restrict__ top,
+                                            const float* __restrict__ Rs, const float* __restrict__ ts, int H, int K, int b,
+                                            float* __restrict__ R_out, float* __restrict__ t_out,
+                                            float* __restrict__ score_out, int* __restrict__ pool_out,
+                                            const int* __restrict__ pool_map, float* s_v, int* s_i) {
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  bool seen_nan = false;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    float v = VOLATILE_SCORES ? __ldcg(scores + (size_t)b * K + k) : scores[(size_t)b * K + k];
+    if (v != v) { if (!seen_nan) { seen_nan = true; bv = v; bi = k; } continue; }
+    if (!seen_nan && (v > bv || (v == bv && k < bi))) { bv = v; bi = k; }
+  }
+  // warp reduce (NaN wins, then larger value, then smaller index) — torch.max propagates NaN
+  for (int o = 16; o > 0; o >>= 1) {
+    float ov = __shfl_xor_sync(kFull, bv, o);
+    int oi = __shfl_xor_sync(kFull, bi, o);
+    bool a_nan = bv != bv, b_nan = ov != ov;
+    bool take = b_nan ? (!a_nan || oi < bi) : (!a_nan && (ov > bv || (ov == bv && oi < bi)));
+    if (take) { bv = ov; bi = oi; }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (lane == 0) { s_v[warp] = bv; s_i[warp] = bi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < nw; ++w) {
+      float ov = s_v[w];
+      int oi = s_i[w];
+      bool a_nan = bv != bv, b_nan = ov != ov;
+      bool take = b_nan ? (!a_nan || oi < bi) : (!a_nan && (ov > bv || (ov == bv && oi < bi)));
+      if (take) { bv = ov; bi = oi; }
+    }
+    if (bi == 0x7fffffff) bi = 0;
+    int h = top ? top[(size_t)b * K + bi] : bi;
+    for (int i = 0; i < 9; ++i) R_out[(size_t)b * 9 + i] = Rs[((size_t)b * H + h) * 9 + i];
+    for (int i = 0; i < 3; ++i) t_out[(size_t)b * 3 + i] = ts[((size_t)b * H + h) * 3 + i];
+    score_out[b] = bv;
+    if (pool_out) pool_out[b] = pool_map ? pool_map[(size_t)b * H + h] : h;   // compact candidate list -> pool index
   }
 }
 
@@ -247,7 +358,9 @@ __global__ void __launch_bounds__(SC_THREADS, 4)
 k_score(const float* __restrict__ pts1, const float* __restrict__ model, const float* __restrict__ w1,
         const float* __restrict__ Rs, const float* __restrict__ ts, const int* __restrict__ top,
         int n1, int nm, int H, int K, int k0, int k1, float* __restrict__ scores,
-        const PeerCtx pc, size_t peer_off, size_t slab_bytes, int channel) {
+        const PeerCtx pc, size_t peer_off, size_t slab_bytes, int channel,
+        int* __restrict__ tickets = nullptr, float* __restrict__ R_out = nullptr, float* __restrict__ t_out = nullptr,
+        float* __restrict__ score_out = nullptr, int* __restrict__ pool_out = nullptr) {
   extern __shared__ __align__(16) float sm_model[];  // 4 x nm_pad (SoA x | y | z | |y|^2)
   __shared__ double s_red[2 * SC_HPC][SC_THREADS / 32];
   const int b = blockIdx.y;
@@ -316,9 +429,24 @@ k_score(const float* __restrict__ pts1, const float* __restrict__ model, const f
     }
   }
   if (PEER) peer_publish(pc, channel, pc.epoch[channel] + 1, gridDim.x * gridDim.y);
+  if (!PEER && tickets) {
+    // the last CTA of an instance (ticket counter, zeroed by the top-K launch) selects the best hypothesis: the
+    // separate k_select launch (5 us incl. its boundary) is gone
+    __shared__ int s_last;
+    __shared__ float s_v[8];
+    __shared__ int s_i[8];
+    if (threadIdx.x == 0) {
+      __threadfence();
+      s_last = atomicAdd(tickets + b, 1) == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      select_best<true>(scores, top, Rs, ts, H, K, b, R_out, t_out, score_out, pool_out, nullptr, s_v, s_i);
+    }
+  }
 }
 
-// arg-max over the K kept hypotheses (first maximum), gather R, t, score, pool index (:486-488)
 // PEER: `scores` is the local copy of the exchanged score table; wait until every rank has stored its slice
 template <bool PEER>
 __global__ void __launch_bounds__(256)
@@ -334,40 +462,7 @@ k_select(const float* __restrict__ scores, const int* __restrict__ top, const fl
     peer_wait(pc, channel, e);
     scores = reinterpret_cast<const float*>(pc.data[pc.rank] + peer_off + (e & 1) * slab_bytes);
   }
-  float bv = -INFINITY;
-  int bi = 0x7fffffff;
-  bool seen_nan = false;
-  for (int k = threadIdx.x; k < K; k += 256) {
-    float v = PEER ? __ldcg(scores + (size_t)b * K + k) : scores[(size_t)b * K + k];
-    if (v != v) { if (!seen_nan) { seen_nan = true; bv = v; bi = k; } continue; }
-    if (!seen_nan && (v > bv || (v == bv && k < bi))) { bv = v; bi = k; }
-  }
-  // warp reduce (NaN wins, then larger value, then smaller index) — torch.max propagates NaN
-  for (int o = 16; o > 0; o >>= 1) {
-    float ov = __shfl_xor_sync(kFull, bv, o);
-    int oi = __shfl_xor_sync(kFull, bi, o);
-    bool a_nan = bv != bv, b_nan = ov != ov;
-    bool take = b_nan ? (!a_nan || oi < bi) : (!a_nan && (ov > bv || (ov == bv && oi < bi)));
-    if (take) { bv = ov; bi = oi; }
-  }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) { s_v[warp] = bv; s_i[warp] = bi; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < 8; ++w) {
-      float ov = s_v[w];
-      int oi = s_i[w];
-      bool a_nan = bv != bv, b_nan = ov != ov;
-      bool take = b_nan ? (!a_nan || oi < bi) : (!a_nan && (ov > bv || (ov == bv && oi < bi)));
-      if (take) { bv = ov; bi = oi; }
-    }
-    if (bi == 0x7fffffff) bi = 0;
-    int h = top ? top[(size_t)b * K + bi] : bi;
-    for (int i = 0; i < 9; ++i) R_out[(size_t)b * 9 + i] = Rs[((size_t)b * H + h) * 9 + i];
-    for (int i = 0; i < 3; ++i) t_out[(size_t)b * 3 + i] = ts[((size_t)b * H + h) * 3 + i];
-    score_out[b] = bv;
-    if (pool_out) pool_out[b] = pool_map ? pool_map[(size_t)b * H + h] : h;   // compact candidate list -> pool index
-  }
+  select_best<PEER>(scores, top, Rs, ts, H, K, b, R_out, t_out, score_out, pool_out, pool_map, s_v, s_i);
 }
 
 // ---------------------------------------------------------------- hypothesis sharding
@@ -492,6 +587,7 @@ struct CoarseWs {
   float* pmat; double* prow; float* cdf;
   float* Rs; float* ts; float* resid;
   int* top; float* scores;
+  int* tickets;
 };
 
 static void carve_coarse(Carver& cv, int b, int n1, int n2, int H, int K, const AssignGeom& g, CoarseWs& w) {
@@ -506,12 +602,14 @@ static void carve_coarse(Carver& cv, int b, int n1, int n2, int H, int K, const 
   w.resid = cv.take<float>((size_t)b * H);
   w.top = cv.take<int>((size_t)b * K);
   w.scores = cv.take<float>((size_t)b * K);
+  w.tickets = cv.take<int>((size_t)b);
 }
 
 static int launch_score(const float* pts1, const float* model, const float* w1, const float* Rs,
                         const float* ts, const int* top, int b, int n1, int nm, int H, int K, int k0, int k1,
                         float* scores, cudaStream_t st, const upk_peer_t* peer = nullptr, size_t peer_off = 0,
-                        size_t slab_bytes = 0, int channel = 0) {
+                        size_t slab_bytes = 0, int channel = 0, int* tickets = nullptr, float* R_out = nullptr,
+                        float* t_out = nullptr, float* score_out = nullptr, int* pool_out = nullptr) {
   if (k1 <= k0 && !peer) return UPK_OK;
   size_t smem = (size_t)((nm + 3) & ~3) * 4 * sizeof(float);
   if (smem > 200 * 1024) return UPK_ERR_UNSUPPORTED;
@@ -525,7 +623,8 @@ static int launch_score(const float* pts1, const float* model, const float* w1, 
   } else {
     if (smem > 40 * 1024)
       UPK_CUDA_TRY(cudaFuncSetAttribute(k_score<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_score<false><<<grid, SC_THREADS, smem, st>>>(pts1, model, w1, Rs, ts, top, n1, nm, H, K, k0, k1, scores, PeerCtx(), 0, 0, 0);
+    k_score<false><<<grid, SC_THREADS, smem, st>>>(pts1, model, w1, Rs, ts, top, n1, nm, H, K, k0, k1, scores, PeerCtx(), 0, 0, 0,
+                                                   tickets, R_out, t_out, score_out, pool_out);
   }
   count_launch();
   UPK_RETURN_LAST_ERROR();
@@ -580,14 +679,11 @@ int upk_coarse_pose(const float* atten, const float* score1, int score1_ld, cons
                                               w.ts, w.resid);
     count_launch();
   }
-  k_topk_smallest<<<b, TK_THREADS, 0, st>>>(w.resid, n_hyp, n_keep, w.top, n_hyp);
-  count_launch();
+  // the top-K launch zeroes the per-instance tickets; the LAST scoring CTA of an instance selects the best hypothesis
+  launch_topk(w.resid, b, n_hyp, n_hyp, n_keep, w.top, st, w.tickets);
   if ((rc = launch_score(pts1, model_pts, w.w1, w.Rs, w.ts, w.top, b, n1, n_model, n_hyp, n_keep, 0, n_keep,
-                         w.scores, st)))
+                         w.scores, st, nullptr, 0, 0, 0, w.tickets, R_out, t_out, score_out, pool_idx_out)))
     return rc;
-  k_select<false><<<b, 256, 0, st>>>(w.scores, w.top, w.Rs, w.ts, n_hyp, n_keep, R_out, t_out, score_out, pool_idx_out,
-                                     PeerCtx(), 0, 0, 0);
-  count_launch();
   if (dbg) {
     // optional copies of the intermediates for stage-wise parity tests
     if (dbg->w1) UPK_CUDA_TRY(cudaMemcpyAsync(dbg->w1, w.w1, sizeof(float) * (size_t)b * n1, cudaMemcpyDeviceToDevice, st));
@@ -663,16 +759,14 @@ int upk_kabsch_triplets(const float* p1, const float* p2, int n, float* Rs, floa
 int upk_topk_smallest(const float* vals, int b, int n, int k, int* idx_out, upk_stream_t stream) {
   if (b < 0 || n <= 0 || k <= 0 || k > n) return UPK_ERR_INVALID_ARG;
   if (b == 0) return UPK_OK;
-  k_topk_smallest<<<b, TK_THREADS, 0, (cudaStream_t)stream>>>(vals, n, k, idx_out, n);
-  count_launch();
+  launch_topk(vals, b, n, n, k, idx_out, (cudaStream_t)stream);
   UPK_RETURN_LAST_ERROR();
 }
 
 int upk_topk_smallest_ld(const float* vals, int b, int n, int ld, int k, int* idx_out, upk_stream_t stream) {
   if (b < 0 || n <= 0 || k <= 0 || k > n || ld < n) return UPK_ERR_INVALID_ARG;
   if (b == 0) return UPK_OK;
-  k_topk_smallest<<<b, TK_THREADS, 0, (cudaStream_t)stream>>>(vals, n, k, idx_out, ld);
-  count_launch();
+  launch_topk(vals, b, n, ld, k, idx_out, (cudaStream_t)stream);
   UPK_RETURN_LAST_ERROR();
 }
 

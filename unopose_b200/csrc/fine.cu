@@ -38,9 +38,10 @@ __device__ __forceinline__ void block_sum(double (&v)[N], double* s_buf /* N * 3
 __global__ void __launch_bounds__(FK_THREADS)
 k_weighted_kabsch(const float* __restrict__ src, const float* __restrict__ ref,
                   const float* __restrict__ weights, int n, float thresh, float eps,
-                  float* __restrict__ R_out, float* __restrict__ t_out) {
+                  float* __restrict__ R_out, float* __restrict__ t_out, int* __restrict__ zero3 = nullptr) {
   __shared__ double s_buf[9 * 32];
   const int b = blockIdx.x;
+  if (zero3 && threadIdx.x < 3) zero3[b * 3 + threadIdx.x] = 0;   // counters of the inlier launch that follows
   src += (size_t)b * n * 3;
   ref += (size_t)b * n * 3;
   const float* wt = weights ? weights + (size_t)b * n : nullptr;
@@ -103,11 +104,11 @@ k_weighted_kabsch(const float* __restrict__ src, const float* __restrict__ ref,
 // FS_PARTS threads share a PAIR of query points (the four LDS.128 of a scan step serve both, two dependency chains
 // interleave — nn_min_expansion2, like k_score), each scanning interleaved groups of the staged model tile (min via
 // shuffles); the last CTA of an instance (ticket counter) turns the integer counts into the score.
-// 256 threads x 2 queries / 4 parts = 128 query points per CTA (round 1: 128 threads, one query per thread, 2 parts:
-// 31 us at B = 16 with 3.5 warps per scheduler and one LDS.128 per point and query).
+// 256 threads x 2 queries / 8 parts = 64 query points per CTA: 512 CTAs at B = 16, 3.5 per SM (4 parts: 256 CTAs, 1.7 per
+// SM, 8-16 warps per SM and a 2:1 imbalance between the SMs; round 1: 128 threads, one query per thread, 2 parts).
 constexpr int FS_THREADS = 256;
-constexpr int FS_PARTS = 4;
-constexpr int FS_QPB = 2 * FS_THREADS / FS_PARTS;   // 128 query points per CTA
+constexpr int FS_PARTS = 8;
+constexpr int FS_QPB = 2 * FS_THREADS / FS_PARTS;   // 64 query points per CTA
 constexpr int FS_TILE = 2048;
 
 __global__ void __launch_bounds__(FS_THREADS)
@@ -280,8 +281,7 @@ static int fine_pose_impl(const float* atten, int atten_ld, const float* stats, 
   if ((rc = run_fine_rowsums(atten, score1, score1_ld, score2, score2_ld, b, g, w.a, w.w1, w.w2, pts2,
                              w.rowpart4, w.soft, w.asum, st, ld)))
     return rc;
-  k_weighted_kabsch<<<b, FK_THREADS, 0, st>>>(w.soft, pts1, w.asum, n1, weight_thresh, 1e-5f, R_out, t_out);
-  UPK_CUDA_TRY(cudaMemsetAsync(w.counters, 0, sizeof(int) * 3 * (size_t)b, st));
+  k_weighted_kabsch<<<b, FK_THREADS, 0, st>>>(w.soft, pts1, w.asum, n1, weight_thresh, 1e-5f, R_out, t_out, w.counters);
   dim3 grid(ceil_div(n1, FS_QPB), b);
   k_fine_inliers<<<grid, FS_THREADS, 0, st>>>(pts1, model_pts, w.w1, R_out, t_out, n1, n_model, dis_thres,
                                               w.counters, dbg ? dbg->nn : nullptr, score_out);

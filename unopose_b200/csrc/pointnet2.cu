@@ -41,7 +41,7 @@ __device__ __forceinline__ unsigned bitrev_n(unsigned v, int nbits) {
   return nbits == 0 ? 0u : (__brev(v) >> (32 - nbits));
 }
 
-template <int THREADS, int PPT, bool X2 = false>
+template <int THREADS, int PPT, bool X2 = false, bool GENKEY = false>
 __global__ void __launch_bounds__(THREADS, 1)
 fps_kernel(const float* __restrict__ xyz, int n, int m, int bs_log2,
            int* __restrict__ idx_out) {
@@ -123,7 +123,10 @@ fps_kernel(const float* __restrict__ xyz, int n, int m, int bs_log2,
     // d2 >= 0 for real points, so signed-int order of the bit patterns == float order and the
     // sentinel -1.0f (negative as int) loses against everything
     const int hi = __float_as_int(best);
-    const unsigned lo = my_rev | ((unsigned)(tid + bestp * THREADS) >> bs_log2);
+    // tie key of point k: (bitrev(k mod BS), k div BS).  With THREADS a multiple of BS, k mod BS == tid mod BS for all of
+    // a thread's points; the configurations with fewer warps than BS / 32 (GENKEY) evaluate it for the winning point
+    const unsigned kb = (unsigned)(tid + bestp * THREADS);
+    const unsigned lo = (GENKEY ? bitrev_n(kb & bs_mask, bs_log2) << 20 : my_rev) | (kb >> bs_log2);
     const int whi = __reduce_max_sync(kFull, hi);
     const unsigned wlo = __reduce_min_sync(kFull, hi == whi ? lo : 0xffffffffu);
     if (lane == 0) sred[buf][warp] = make_int2(whi, (int)wlo);
@@ -209,7 +212,7 @@ static int fps_exclusive() {
   return v;
 }
 
-template <int THREADS, int PPT, bool X2 = false>
+template <int THREADS, int PPT, bool X2 = false, bool GENKEY = false>
 static int launch_fps(const float* xyz, int b, int n, int m, int bs_log2, int* out,
                       cudaStream_t st) {
   size_t smem = (size_t)n * 3 * sizeof(float);
@@ -217,7 +220,7 @@ static int launch_fps(const float* xyz, int b, int n, int m, int bs_log2, int* o
   // co-reside on its SM steal issue slots and stretch every one of its m-1 iterations.  Claiming most of
   // the SM's shared memory keeps the SM exclusive (opt-in: UPK_FPS_EXCLUSIVE=1).
   if (fps_exclusive() && (long long)n * m >= 4096LL * 1024LL && smem < 200 * 1024) smem = 200 * 1024;
-  auto kern = fps_kernel<THREADS, PPT, X2>;
+  auto kern = fps_kernel<THREADS, PPT, X2, GENKEY>;
   if (smem > 40 * 1024) {  // dynamic + the 512 B of static smem must stay within the default 48 KB
     UPK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
@@ -572,6 +575,8 @@ int upk_furthest_point_sampling(const float* xyz, int b, int n, int m, int* idx_
     if (cfg == 1) return launch_fps<1024, 2>(xyz, b, n, m, bs_log2, idx_out, st);
     if (cfg == 2) return launch_fps<512, 4>(xyz, b, n, m, bs_log2, idx_out, st);
     if (cfg == 4) return launch_fps<512, 4, true>(xyz, b, n, m, bs_log2, idx_out, st);
+    if (cfg == 5) return launch_fps<256, 8, true, true>(xyz, b, n, m, bs_log2, idx_out, st);
+    if (cfg == 6) return launch_fps<128, 16, true, true>(xyz, b, n, m, bs_log2, idx_out, st);
     return launch_fps<512, 4, true>(xyz, b, n, m, bs_log2, idx_out, st);
   }
   if (n <= 3072) return launch_fps<1024, 3>(xyz, b, n, m, bs_log2, idx_out, st);
@@ -580,6 +585,8 @@ int upk_furthest_point_sampling(const float* xyz, int b, int n, int m, int* idx_
     if (cfg == 1) return launch_fps<1024, 5>(xyz, b, n, m, bs_log2, idx_out, st);
     if (cfg == 2) return launch_fps<512, 10>(xyz, b, n, m, bs_log2, idx_out, st);
     if (cfg == 4) return launch_fps<512, 10, true>(xyz, b, n, m, bs_log2, idx_out, st);
+    if (cfg == 5) return launch_fps<256, 20, true, true>(xyz, b, n, m, bs_log2, idx_out, st);
+    if (cfg == 6) return launch_fps<128, 40, true, true>(xyz, b, n, m, bs_log2, idx_out, st);
     return launch_fps<512, 10, true>(xyz, b, n, m, bs_log2, idx_out, st);
   }
   if (n <= 8192) return launch_fps<512, 16>(xyz, b, n, m, bs_log2, idx_out, st);

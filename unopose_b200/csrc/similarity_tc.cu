@@ -27,6 +27,10 @@
 #include "tc_ptx.cuh"
 #include "../../include/unopose_b200.h"
 
+#ifndef UPK_EPI_XCHG
+#define UPK_EPI_XCHG 0   // see the epilogue of k_similarity_tc2
+#endif
+
 namespace upk {
 
 constexpr int TC_STAGES = 3;  // 48 KB / stage
@@ -73,7 +77,7 @@ struct NsOperand {
   int is_a;
 };
 
-template <int MODE, bool F16 = false>
+template <int MODE, bool F16 = false, int RIF = 4>   // RIF: rows in flight per warp (4 for c <= 256, else 2)
 __global__ void __launch_bounds__(256)
 k_normalize_split(const NsOperand opa, const NsOperand opb, int c, int normalize,
                   float temp, float* __restrict__ C, int M, int N, int ldc) {
@@ -101,87 +105,100 @@ k_normalize_split(const NsOperand opa, const NsOperand opb, int c, int normalize
       qn = fmaxf(sqrtf(s), 1e-12f);
     }
     const float qinv = 1.0f / qn;
-    for (int k = threadIdx.x; k < c; k += 256) s_q[k] = q[k] * qinv;
+    // F16: the row values below carry the 2^12 scale, so the staged row carries 2^-12 (exact: the products are the same)
+    for (int k = threadIdx.x; k < c; k += 256) s_q[k] = F16 ? (q[k] * qinv) * (1.0f / kF16Scale) : q[k] * qinv;
     __syncthreads();
   }
-  // NS_RPW rows per warp: the border prologue above (norm + staging of the other operand's row 0) is per CTA
-#pragma unroll 1
-  for (int rw = 0; rw < NS_RPW; ++rw) {
-  const int r = (blockIdx.x * 8 + (threadIdx.x >> 5)) * NS_RPW + rw;
-  if (r >= rows_per_batch) return;
-  const size_t row = (size_t)bidx * rows_per_batch + r;
-  const float* p = x + row * c;
-  // 128-bit accesses (c % 4 == 0 is guaranteed by the tensor-core path, rows are 16-byte aligned with the
-  // workspace); the row stays in registers between the norm and the split for c <= 512
-  const int nv = c >> 2;
-  const float4* p4 = reinterpret_cast<const float4*>(p);
-  float4 keep[4];
-  float s = 0.f;
-#pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const int k = lane + 32 * u;
-    if (k < nv) {
-      keep[u] = __ldg(p4 + k);
-      s = fmaf(keep[u].x, keep[u].x, fmaf(keep[u].y, keep[u].y, fmaf(keep[u].z, keep[u].z, fmaf(keep[u].w, keep[u].w, s))));
-    }
-  }
-  for (int k = lane + 128; k < nv; k += 32) {
-    const float4 v = __ldg(p4 + k);
-    s = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, s))));
-  }
-  float inv = 1.f;
-  if (normalize) {
-    s = warp_sum(s);
-    inv = 1.0f / fmaxf(sqrtf(s), 1e-12f);   // x * (1 / ||x||): within 1 ulp of F.normalize's division
-  }
-  float dot = 0.f;
-  float4* hi4 = reinterpret_cast<float4*>(hi + row * c);
-  float4* lo4 = reinterpret_cast<float4*>(lo + row * c);
+  // NS_RPW rows per warp: the border prologue above (norm + staging of the other operand's row 0) is per CTA.
+  // All of a warp's rows are requested before the first one is reduced (c <= 256: 8 independent 128-bit loads per
+  // lane in flight instead of 2 - the kernel was latency-bound at 2.9 TB/s); wider rows go two at a time.
+  const int nv = c >> 2;   // 128-bit accesses (c % 4 == 0 is guaranteed by the tensor-core path, rows are 16-byte aligned)
+  constexpr int rif = RIF;                        // rows in flight
+  constexpr int kv = 8 / rif;                     // float4 kept per lane and row (covers c <= 256 / c <= 512)
+  static_assert(NS_RPW % RIF == 0 && (RIF == 2 || RIF == 4), "");
   const float4* q4 = reinterpret_cast<const float4*>(s_q);
-  auto split = [&](float4 v, int k) {
-    v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
-    float4 h;
-    uint32_t t;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.x)); h.x = __uint_as_float(t);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.y)); h.y = __uint_as_float(t);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.z)); h.z = __uint_as_float(t);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.w)); h.w = __uint_as_float(t);
-    if (F16) {
-      const float sx = v.x * kF16Scale, sy = v.y * kF16Scale, sz = v.z * kF16Scale, sw = v.w * kF16Scale;
-      const __half hx = __float2half_rn(sx), hy = __float2half_rn(sy), hz = __float2half_rn(sz), hw = __float2half_rn(sw);
-      const __half lx = __float2half_rn(sx - __half2float(hx)), ly = __float2half_rn(sy - __half2float(hy));
-      const __half lz = __float2half_rn(sz - __half2float(hz)), lw = __float2half_rn(sw - __half2float(hw));
-      uint2 ph, pl;
-      ph.x = (uint32_t)__half_as_ushort(hx) | ((uint32_t)__half_as_ushort(hy) << 16);
-      ph.y = (uint32_t)__half_as_ushort(hz) | ((uint32_t)__half_as_ushort(hw) << 16);
-      pl.x = (uint32_t)__half_as_ushort(lx) | ((uint32_t)__half_as_ushort(ly) << 16);
-      pl.y = (uint32_t)__half_as_ushort(lz) | ((uint32_t)__half_as_ushort(lw) << 16);
-      reinterpret_cast<uint2*>(reinterpret_cast<__half*>(hi) + row * c)[k] = ph;
-      reinterpret_cast<uint2*>(reinterpret_cast<__half*>(lo) + row * c)[k] = pl;
-    } else {
-    hi4[k] = h;
-    lo4[k] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
-    }
-    if (other) {
-      const float4 q = q4[k];
-      dot = fmaf(v.x, q.x, fmaf(v.y, q.y, fmaf(v.z, q.z, fmaf(v.w, q.w, dot))));
-    }
-  };
+  const int r_first = (blockIdx.x * 8 + (threadIdx.x >> 5)) * NS_RPW;
+#pragma unroll 1
+  for (int rw0 = 0; rw0 < NS_RPW; rw0 += rif) {
+    float4 keep[8];
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const int k = lane + 32 * u;
-    if (k < nv) split(keep[u], k);
-  }
-  for (int k = lane + 128; k < nv; k += 32) split(__ldg(p4 + k), k);
-  if (other) {
-    dot = warp_sum(dot);
-    if (MODE == 1) dot = sqrtf(fmaxf(2.0f - 2.0f * dot, 0.f));
-    if (lane == 0) {
-      float* o = is_a ? C + ((size_t)bidx * M + r) * ldc : C + (size_t)bidx * M * ldc + r;
-      if (is_a || r > 0) *o = dot * (1.0f / temp);   // C[0][0] is written once, by the first operand's row 0
+    for (int j = 0; j < rif; ++j) {
+      const int r = r_first + rw0 + j;
+      const float4* p4 = reinterpret_cast<const float4*>(x + ((size_t)bidx * rows_per_batch + r) * c);
+#pragma unroll
+      for (int u = 0; u < kv; ++u) {
+        const int k = lane + 32 * u;
+        keep[j * kv + u] = (r < rows_per_batch && k < nv) ? __ldg(p4 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < rif; ++j) {
+      const int r = r_first + rw0 + j;
+      if (r >= rows_per_batch) break;
+      const size_t row = (size_t)bidx * rows_per_batch + r;
+      const float4* p4 = reinterpret_cast<const float4*>(x + row * c);
+      float s = 0.f;
+#pragma unroll
+      for (int u = 0; u < kv; ++u) {
+        const float4 v = keep[j * kv + u];   // zero beyond the row: adds nothing
+        s = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, s))));
+      }
+      for (int k = lane + 32 * kv; k < nv; k += 32) {
+        const float4 v = __ldg(p4 + k);
+        s = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, s))));
+      }
+      float inv = 1.f;
+      if (normalize) {
+        s = warp_sum(s);
+        inv = 1.0f / fmaxf(sqrtf(s), 1e-12f);   // x * (1 / ||x||): within 1 ulp of F.normalize's division
+      }
+      float dot = 0.f;
+      float4* hi4 = reinterpret_cast<float4*>(hi + row * c);
+      float4* lo4 = reinterpret_cast<float4*>(lo + row * c);
+      auto split = [&](float4 v, int k) {
+        v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+        if (F16) {
+          // packed conversions (F2FP / HADD2.F32 on the FMA pipes; the scalar F2F.F16.F32 runs at 16 lanes per clock)
+          v.x *= kF16Scale; v.y *= kF16Scale; v.z *= kF16Scale; v.w *= kF16Scale;
+          const __half2 hxy = __floats2half2_rn(v.x, v.y), hzw = __floats2half2_rn(v.z, v.w);
+          const float2 fxy = __half22float2(hxy), fzw = __half22float2(hzw);
+          const __half2 lxy = __floats2half2_rn(v.x - fxy.x, v.y - fxy.y), lzw = __floats2half2_rn(v.z - fzw.x, v.w - fzw.y);
+          uint2 ph, pl;
+          ph.x = *reinterpret_cast<const uint32_t*>(&hxy); ph.y = *reinterpret_cast<const uint32_t*>(&hzw);
+          pl.x = *reinterpret_cast<const uint32_t*>(&lxy); pl.y = *reinterpret_cast<const uint32_t*>(&lzw);
+          reinterpret_cast<uint2*>(reinterpret_cast<__half*>(hi) + row * c)[k] = ph;
+          reinterpret_cast<uint2*>(reinterpret_cast<__half*>(lo) + row * c)[k] = pl;
+        } else {
+          float4 h;
+          uint32_t t;
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.x)); h.x = __uint_as_float(t);
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.y)); h.y = __uint_as_float(t);
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.z)); h.z = __uint_as_float(t);
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.w)); h.w = __uint_as_float(t);
+          hi4[k] = h;
+          lo4[k] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+        }
+        if (other) {
+          const float4 q = q4[k];
+          dot = fmaf(v.x, q.x, fmaf(v.y, q.y, fmaf(v.z, q.z, fmaf(v.w, q.w, dot))));
+        }
+      };
+#pragma unroll
+      for (int u = 0; u < kv; ++u) {
+        const int k = lane + 32 * u;
+        if (k < nv) split(keep[j * kv + u], k);
+      }
+      for (int k = lane + 32 * kv; k < nv; k += 32) split(__ldg(p4 + k), k);
+      if (other) {
+        dot = warp_sum(dot);
+        if (MODE == 1) dot = sqrtf(fmaxf(2.0f - 2.0f * dot, 0.f));
+        if (lane == 0) {
+          float* o = is_a ? C + ((size_t)bidx * M + r) * ldc : C + (size_t)bidx * M * ldc + r;
+          if (is_a || r > 0) *o = dot * (1.0f / temp);   // C[0][0] is written once, by the first operand's row 0
+        }
+      }
     }
   }
-  }   // rows of this warp
 }
 
 // ---------------------------------------------------------------- the GEMM
@@ -585,6 +602,7 @@ k_similarity_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           float* box = tr + ((cc & 1) << 10);
           if (lane == 0) bulk_wait_read<1>();   // the store issued from this box two chunks ago has read it
           __syncwarp();
+          float ex[(STATS && UPK_EPI_XCHG) ? 32 : 1];   // XCHG: this row's exponentials of the chunk
 #pragma unroll
           for (int c4 = 0; c4 < 8; ++c4) {
             float4 v;
@@ -598,7 +616,8 @@ k_similarity_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
               for (int e4 = 0; e4 < 4; ++e4) {
                 float e;
                 asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(vv[e4], 1.4426950408889634f, -gref)));
-                rsum += (col0 + 4 * c4 + e4 < N) ? e : 0.f;
+                if (UPK_EPI_XCHG) ex[4 * c4 + e4] = e;
+                else rsum += (col0 + 4 * c4 + e4 < N) ? e : 0.f;
               }
             }
             // row `lane` of the box (128 B), 16-byte chunk c4 at position c4 ^ (row & 7): the SWIZZLE_128B pattern
@@ -610,7 +629,30 @@ k_similarity_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             tma_store_3d(&map_c, box, col0 - off, row0 - off, b);
             bulk_commit();
           }
-          if (STATS && col0 + lane < N && nrows > 0) {
+          if (STATS && UPK_EPI_XCHG) {
+            // Experiment (compile with -DUPK_EPI_XCHG=1): column sums by halving exchanges between the lanes instead of
+            // a second pass over the staging box.  Fewer issue slots and half the MUFU work, but measured SLOWER
+            // (fine similarity 136 -> 145 us): the epilogue is bound by the length of its dependent chain with two
+            // warps per scheduler, not by its instruction count, and five shuffle rounds lengthen that chain.
+            if (col0 + 32 > N || nrows < 32) {   // ragged chunk (warp-uniform; never for the 2048 x 2048 main block)
+#pragma unroll
+              for (int j = 0; j < 32; ++j) ex[j] = (col0 + j < N && lane < nrows) ? ex[j] : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) rsum += ex[j];
+            int o = 16;
+#pragma unroll
+            for (int n = 32; n > 1; n >>= 1, o >>= 1) {
+              const bool upper = (lane & o) != 0;
+#pragma unroll
+              for (int i = 0; i < n / 2; ++i) {
+                const float send = upper ? ex[i] : ex[i + n / 2];
+                const float keep = upper ? ex[i + n / 2] : ex[i];
+                ex[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+              }
+            }
+            if (col0 + lane < N && nrows > 0) colpart[((size_t)b * (4 * mt) + 4 * mi + q) * N + col0 + lane] = ex[0];
+          } else if (STATS && col0 + lane < N && nrows > 0) {
             // column col0 + lane of the 32 rows: word (lane & 3) of chunk (lane >> 2) ^ (rr & 7) of row rr
             float csum = 0.f;
             for (int rr = 0; rr < nrows; ++rr) {
@@ -813,7 +855,8 @@ static int run_similarity_f16(const float* f1, const float* f2, int b, int n, in
   const dim3 g12(((n > m ? n : m) + 8 * NS_RPW - 1) / (8 * NS_RPW), b, 2);
   const size_t qs = (size_t)c * sizeof(float);
   const NsOperand oa{f1, n, (float*)a_hi, (float*)a_lo, f2, m, 1}, ob{f2, m, (float*)b_hi, (float*)b_lo, f1, n, 0};
-  k_normalize_split<0, true><<<g12, 256, qs, st>>>(oa, ob, c, normalize, temp, out, n, m, ldc);
+  if (c <= 256) k_normalize_split<0, true, 4><<<g12, 256, qs, st>>>(oa, ob, c, normalize, temp, out, n, m, ldc);
+  else k_normalize_split<0, true, 2><<<g12, 256, qs, st>>>(oa, ob, c, normalize, temp, out, n, m, ldc);
   count_launch(1);
   CUtensorMap fa_hi, fa_lo, fb_hi, fb_lo;
   int rc;
@@ -873,8 +916,12 @@ int run_similarity_tc(const float* f1, const float* f2, int b, int n, int m, int
   const dim3 g12(((n > m ? n : m) + 8 * NS_RPW - 1) / (8 * NS_RPW), b, 2);
   const size_t qs = off ? (size_t)c * sizeof(float) : 0;
   const NsOperand oa{f1, n, a_hi, a_lo, off ? f2 : nullptr, m, 1}, ob{f2, m, b_hi, b_lo, off ? f1 : nullptr, n, 0};
-  if (sim_type == 0) k_normalize_split<0><<<g12, 256, qs, st>>>(oa, ob, c, normalize, temp, out, n, m, ldc);
-  else k_normalize_split<1><<<g12, 256, qs, st>>>(oa, ob, c, normalize, temp, out, n, m, ldc);
+  if (sim_type == 0) {
+    if (c <= 256) k_normalize_split<0, false, 4><<<g12, 256, qs, st>>>(oa, ob, c, normalize, temp, out, n, m, ldc);
+    else k_normalize_split<0, false, 2><<<g12, 256, qs, st>>>(oa, ob, c, normalize, temp, out, n, m, ldc);
+  } else {
+    k_normalize_split<1, false, 2><<<g12, 256, qs, st>>>(oa, ob, c, normalize, temp, out, n, m, ldc);
+  }
   count_launch(1);
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int rc;
@@ -949,7 +996,8 @@ int run_linear_tc(const float* x, const float* w, const float* bias, int rows, i
   float* b_lo = (float*)(wsp + 2 * a + bb);
   const dim3 g12(((rows > out_f ? rows : out_f) + 8 * NS_RPW - 1) / (8 * NS_RPW), 1, 2);
   const NsOperand oa{x, rows, a_hi, a_lo, nullptr, out_f, 1}, ob{w, out_f, b_hi, b_lo, nullptr, rows, 0};
-  k_normalize_split<0><<<g12, 256, 0, st>>>(oa, ob, in, 0, 1.0f, y, rows, out_f, out_f);
+  if (in <= 256) k_normalize_split<0, false, 4><<<g12, 256, 0, st>>>(oa, ob, in, 0, 1.0f, y, rows, out_f, out_f);
+  else k_normalize_split<0, false, 2><<<g12, 256, 0, st>>>(oa, ob, in, 0, 1.0f, y, rows, out_f, out_f);
   count_launch(1);
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int rc;
