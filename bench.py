@@ -39,7 +39,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=None, help="instances per GPU per step (default 16 = the reference's "
                                                             "instance_batch_size; 8 in --mode hyp-shard)")
-    ap.add_argument("--sets", type=int, default=4, help="resident input sets to rotate over (defeats L2 reuse)")
+    ap.add_argument("--sets", type=int, default=None,
+                    help="resident input sets to rotate over (defeats L2 reuse; default 2 x --depth)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
     ap.add_argument("--mode", default="step", choices=["step", "hyp-shard"])
     ap.add_argument("--H", type=int, nargs="*", default=None, help="hyp-shard: hypotheses per instance (default sweep)")
@@ -47,7 +48,7 @@ def parse():
                     help="hyp-shard: candidate / score exchange through peer memory (fused into the kernels) or NCCL")
     ap.add_argument("--no-overlap", action="store_true", help="run the two chains of a step serially on one stream")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying CUDA graphs")
-    ap.add_argument("--depth", type=int, default=2,
+    ap.add_argument("--depth", type=int, default=3,
                     help="steps in flight: consecutive steps (different resident sets) replay on alternating "
                          "streams, so one step's serial FPS chain (16 SMs) overlaps the next step's full-GPU kernels")
     ap.add_argument("--no-zero-copy", action="store_true",
@@ -59,7 +60,10 @@ def parse():
     ap.add_argument("--no-widened", action="store_true", help="skip the informational timings of the f1/f2 kernels")
     ap.add_argument("--no-peaks", action="store_true", help="skip the live TF32 dense-peak measurement")
     ap.add_argument("--no-numa", action="store_true", help="do not pin the process to the GPU's NUMA node")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.sets is None:
+        args.sets = 2 * max(1, args.depth)
+    return args
 
 
 def peaks():

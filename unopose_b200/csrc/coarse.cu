@@ -172,10 +172,8 @@ __device__ __forceinline__ unsigned block_excl_scan_u32(unsigned v, unsigned* s_
 }
 
 // CACHED (H <= 8 * TK_THREADS: every pool size of the reference): a thread keeps its contiguous chunk of the row in
-// registers for all four passes and the compaction (one read of the row instead of six).  Histogram updates are
-// warp-aggregated (__match_any_sync): the first pass sees two or three distinct exponent bytes, which serialised
-// thousands of same-address shared atomics; the digit search is a warp scan over 8 bins per lane instead of one thread
-// walking 256 bins (round 1: 17 us per launch, most of it in those two places).
+// registers for all four passes and the compaction (one read of the row instead of six); the digit search is a warp
+// scan over 8 bins per lane instead of one thread walking 256 bins (round 1: 17 us per launch, now 10).
 constexpr int TK_PER = 8;
 
 template <bool CACHED>
@@ -202,22 +200,16 @@ k_topk_smallest(const float* __restrict__ vals, int H, int K, int* __restrict__ 
   for (int shift = 24; shift >= 0; shift -= 8) {
     if (threadIdx.x < 256) hist[threadIdx.x] = 0;
     __syncthreads();
-    auto vote = [&](bool in, unsigned xv) {
-      const unsigned act = __ballot_sync(kFull, in);
-      if (in) {
-        const unsigned d = (xv >> shift) & 255u;
-        const unsigned peers = __match_any_sync(act, d);
-        if (lane == __ffs(peers) - 1) atomicAdd(&hist[d], (unsigned)__popc(peers));
-      }
-    };
+    // plain shared atomics: aggregating per warp with __match_any_sync was measured slower at every pool size (the first
+    // pass sees few distinct exponent bytes, but same-address shared atomics of a warp are combined by the hardware)
     if (CACHED) {
 #pragma unroll
-      for (int k = 0; k < TK_PER; ++k) vote(beg + k < end && (x[k] & mask) == prefix, x[k]);
+      for (int k = 0; k < TK_PER; ++k)
+        if (beg + k < end && (x[k] & mask) == prefix) atomicAdd(&hist[(x[k] >> shift) & 255u], 1u);
     } else {
-      for (int i0 = 0; i0 < H; i0 += TK_THREADS) {   // warp-uniform trip count
-        const int i = i0 + threadIdx.x;
-        const unsigned xv = i < H ? v[i] : 0u;
-        vote(i < H && (xv & mask) == prefix, xv);
+      for (int i = threadIdx.x; i < H; i += TK_THREADS) {
+        const unsigned xv = v[i];
+        if ((xv & mask) == prefix) atomicAdd(&hist[(xv >> shift) & 255u], 1u);
       }
     }
     __syncthreads();

@@ -632,8 +632,10 @@ k_similarity_tc2(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           if (STATS && UPK_EPI_XCHG) {
             // Experiment (compile with -DUPK_EPI_XCHG=1): column sums by halving exchanges between the lanes instead of
             // a second pass over the staging box.  Fewer issue slots and half the MUFU work, but measured SLOWER
-            // (fine similarity 136 -> 145 us): the epilogue is bound by the length of its dependent chain with two
-            // warps per scheduler, not by its instruction count, and five shuffle rounds lengthen that chain.
+            // (fine similarity 136 -> 145 us).  So was a variant of the column pass below with shared-window LDS / STS
+            // (the compiler emits generic LD.E / ST.E.128 for the staging box) and no bound checks on whole chunks:
+            // 25 % fewer issue slots, 136 -> 140 us.  The epilogue's instruction count is not what bounds the kernel;
+            // ncu: SM -> L2 request port busy 64 % of the cycles, 302 MB of TMA stores + 4.9 TB/s of operand reads.
             if (col0 + 32 > N || nrows < 32) {   // ragged chunk (warp-uniform; never for the 2048 x 2048 main block)
 #pragma unroll
               for (int j = 0; j < 32; ++j) ex[j] = (col0 + j < N && lane < nrows) ? ex[j] : 0.f;
