@@ -23,11 +23,10 @@ namespace upk {
 
 constexpr int BG_THREADS = 256;
 constexpr int BG_WARPS = BG_THREADS / 32;
-constexpr int BG_QPB = 64;                 // queries per CTA (two warps of queries)
-constexpr int BG_PARTS = BG_WARPS / 2;     // the tile's points are split over 4 warp pairs
+constexpr int BG_QPB = 64;                 // queries per CTA (every scan thread takes queries lane and 32 + lane)
 constexpr int BG_TILE = 2048;              // points per smem tile
 constexpr int BG_WORDS = BG_TILE / 32;     // 64 mask words per query per tile
-constexpr int BG_WPP = BG_WORDS / BG_PARTS;  // 16 words per thread per tile
+constexpr int BG_WPP2 = BG_WORDS / BG_WARPS;  // 8 words per thread per tile, two queries per thread
 constexpr int BG_MPITCH = BG_WORDS + 2;    // even (64-bit reads of word pairs), 2-way conflicts on the 16 stores only
 constexpr int BG_ROWCAP = 512;             // staged path: nsample0 + nsample1 <= 512 ints per warp
 
@@ -42,28 +41,39 @@ __device__ __forceinline__ float bg_d2(float px, float py, float pz, float nqx, 
   return sqdist_ref(px + nqx, py + nqy, pz + nqz);
 }
 
-// 32 points -> hit mask against r2.  d2 < r2  <=>  sign(d2 - r2) for every finite or infinite d2 (round to
-// nearest never turns a non-zero difference into zero, x - x = +0, NaN results are the canonical positive NaN).
-__device__ __forceinline__ unsigned bg_scan_word(const float* __restrict__ sx, const float* __restrict__ sy,
-                                                 const float* __restrict__ sz, int k0, unsigned long long nqx,
-                                                 unsigned long long nqy, unsigned long long nqz,
-                                                 unsigned long long nr2) {
-  unsigned mask = 0u;
+// 32 points -> hit masks against r2 for TWO queries: the three LDS.128 of a step serve both.  (A uniform-address LDS.128
+// costs two shared-memory wavefronts; with one query per thread the scan asked for 24 wavefront cycles per 21 issue
+// cycles of the SM.)  d2 < r2  <=>  sign(d2 - r2) for every finite or infinite d2 (round to nearest never turns a
+// non-zero difference into zero, x - x = +0, NaN results are the canonical positive NaN).
+__device__ __forceinline__ void bg_scan_word2(const float* __restrict__ sx, const float* __restrict__ sy,
+                                              const float* __restrict__ sz, int k0, const unsigned long long (&nqa)[3],
+                                              const unsigned long long (&nqb)[3], unsigned long long nr2,
+                                              unsigned& mask_a, unsigned& mask_b) {
+  unsigned ma = 0u, mb = 0u;
 #pragma unroll
   for (int g = 0; g < 8; ++g) {
     const ulonglong2 X = *reinterpret_cast<const ulonglong2*>(sx + k0 + 4 * g);
     const ulonglong2 Y = *reinterpret_cast<const ulonglong2*>(sy + k0 + 4 * g);
     const ulonglong2 Z = *reinterpret_cast<const ulonglong2*>(sz + k0 + 4 * g);
-    unsigned long long dx = add2(X.x, nqx), dy = add2(Y.x, nqy), dz = add2(Z.x, nqz);
+    unsigned long long dx = add2(X.x, nqa[0]), dy = add2(Y.x, nqa[1]), dz = add2(Z.x, nqa[2]);
     const unsigned long long sa = add2(fma2(dz, dz, fma2(dx, dx, mul2(dy, dy))), nr2);
-    dx = add2(X.y, nqx); dy = add2(Y.y, nqy); dz = add2(Z.y, nqz);
+    dx = add2(X.y, nqa[0]); dy = add2(Y.y, nqa[1]); dz = add2(Z.y, nqa[2]);
     const unsigned long long sb = add2(fma2(dz, dz, fma2(dx, dx, mul2(dy, dy))), nr2);
-    mask = __funnelshift_l((unsigned)sa, mask, 1);
-    mask = __funnelshift_l((unsigned)(sa >> 32), mask, 1);
-    mask = __funnelshift_l((unsigned)sb, mask, 1);
-    mask = __funnelshift_l((unsigned)(sb >> 32), mask, 1);
+    dx = add2(X.x, nqb[0]); dy = add2(Y.x, nqb[1]); dz = add2(Z.x, nqb[2]);
+    const unsigned long long ta = add2(fma2(dz, dz, fma2(dx, dx, mul2(dy, dy))), nr2);
+    dx = add2(X.y, nqb[0]); dy = add2(Y.y, nqb[1]); dz = add2(Z.y, nqb[2]);
+    const unsigned long long tb = add2(fma2(dz, dz, fma2(dx, dx, mul2(dy, dy))), nr2);
+    ma = __funnelshift_l((unsigned)sa, ma, 1);
+    ma = __funnelshift_l((unsigned)(sa >> 32), ma, 1);
+    ma = __funnelshift_l((unsigned)sb, ma, 1);
+    ma = __funnelshift_l((unsigned)(sb >> 32), ma, 1);
+    mb = __funnelshift_l((unsigned)ta, mb, 1);
+    mb = __funnelshift_l((unsigned)(ta >> 32), mb, 1);
+    mb = __funnelshift_l((unsigned)tb, mb, 1);
+    mb = __funnelshift_l((unsigned)(tb >> 32), mb, 1);
   }
-  return __brev(mask);  // point k0 + i -> bit i
+  mask_a = __brev(ma);
+  mask_b = __brev(mb);
 }
 
 // inclusive warp scan of a packed pair of 16-bit counters
@@ -130,12 +140,16 @@ ball_group_kernel(const float* __restrict__ new_xyz, const float* __restrict__ x
     s_cnt[0][tid] = s_cnt[1][tid] = 0;
     s_first[0][tid] = s_first[1][tid] = 0;
   }
-  // scan role: query (warp & 1) * 32 + lane, point part warp >> 1
-  const int sq = (warp & 1) * 32 + lane, part = warp >> 1;
-  const int sj = min(q0 + sq, m - 1);
-  const unsigned long long nqx = pack2(-new_xyz[sj * 3 + 0], -new_xyz[sj * 3 + 0]);
-  const unsigned long long nqy = pack2(-new_xyz[sj * 3 + 1], -new_xyz[sj * 3 + 1]);
-  const unsigned long long nqz = pack2(-new_xyz[sj * 3 + 2], -new_xyz[sj * 3 + 2]);
+  // scan role: queries lane and 32 + lane of the CTA, words [warp * BG_WPP2, (warp + 1) * BG_WPP2) of the tile
+  unsigned long long nqa[3], nqb[3];
+  {
+    const int ja = min(q0 + lane, m - 1), jb = min(q0 + 32 + lane, m - 1);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      nqa[a] = pack2(-new_xyz[ja * 3 + a], -new_xyz[ja * 3 + a]);
+      nqb[a] = pack2(-new_xyz[jb * 3 + a], -new_xyz[jb * 3 + a]);
+    }
+  }
   const unsigned long long nr2 = pack2(-out.r2, -out.r2);
 
   for (int t0 = 0; t0 < n; t0 += BG_TILE) {
@@ -143,14 +157,15 @@ ball_group_kernel(const float* __restrict__ new_xyz, const float* __restrict__ x
     __syncthreads();  // previous tile fully consumed (and the counters initialised)
     bg_load_tile(xyz, t0, tn, sx, sy, sz);
     __syncthreads();
-    // ---- scan: 16 words of 32 points per thread
+    // ---- scan: 8 words of 32 points for two queries per thread
     const int nwords = (tn + 31) >> 5;
 #pragma unroll 1
-    for (int w = 0; w < BG_WPP; ++w) {
-      const int word = part * BG_WPP + w;
-      unsigned mask = 0u;
-      if (word < nwords) mask = bg_scan_word(sx, sy, sz, word * 32, nqx, nqy, nqz, nr2);
-      s_mask[sq * BG_MPITCH + word] = mask;
+    for (int w = 0; w < BG_WPP2; ++w) {
+      const int word = warp * BG_WPP2 + w;
+      unsigned mask_a = 0u, mask_b = 0u;
+      if (word < nwords) bg_scan_word2(sx, sy, sz, word * 32, nqa, nqb, nr2, mask_a, mask_b);
+      s_mask[lane * BG_MPITCH + word] = mask_a;
+      s_mask[(32 + lane) * BG_MPITCH + word] = mask_b;
     }
     __syncthreads();
     // ---- emission: warp per query; lane l owns points [64 l, 64 l + 64) of the tile

@@ -101,14 +101,16 @@ k_weighted_kabsch(const float* __restrict__ src, const float* __restrict__ ref,
 
 // Inlier score (model_utils.py:558-564): X = (pts1 - t) @ R; d_i = NN distance to the model cloud
 // (expansion form, clamp, sqrt); score = sum_fg[d<thr] / (n_fg + 1e-8) * n_fg / N1.
-// FS_PARTS threads share a PAIR of query points (the four LDS.128 of a scan step serve both, two dependency chains
-// interleave — nn_min_expansion2, like k_score), each scanning interleaved groups of the staged model tile (min via
-// shuffles); the last CTA of an instance (ticket counter) turns the integer counts into the score.
-// 256 threads x 2 queries / 8 parts = 64 query points per CTA: 512 CTAs at B = 16, 3.5 per SM (4 parts: 256 CTAs, 1.7 per
-// SM, 8-16 warps per SM and a 2:1 imbalance between the SMs; round 1: 128 threads, one query per thread, 2 parts).
+// A thread scans for a PAIR of query points (the four LDS.128 of a scan step serve both, two dependency chains
+// interleave — nn_min_expansion2, like k_score).  The staged model tile is cut into FS_PARTS interleaved slices, ONE PER
+// WARP: every lane of a warp then reads the same shared-memory address.  (Slices across the lanes of a warp — 8 distinct
+// addresses per quarter warp — cost 4.0 shared-memory wavefronts per LDS.128 in ncu, against 1.85 for a uniform address;
+// the kernel sat at 53 % of the shared-memory pipe with short-scoreboard stalls on 58 % of its samples.)  The minima of
+// the slices meet in shared memory; the last CTA of an instance (ticket counter) turns the integer counts into the score.
+// 8 warps x 32 pairs = 64 query points per CTA: 512 CTAs at B = 16.
 constexpr int FS_THREADS = 256;
-constexpr int FS_PARTS = 8;
-constexpr int FS_QPB = 2 * FS_THREADS / FS_PARTS;   // 64 query points per CTA
+constexpr int FS_PARTS = FS_THREADS / 32;           // one model slice per warp
+constexpr int FS_QPB = 64;                          // query points per CTA (32 pairs)
 constexpr int FS_TILE = 2048;
 
 __global__ void __launch_bounds__(FS_THREADS)
@@ -117,10 +119,11 @@ k_fine_inliers(const float* __restrict__ pts1, const float* __restrict__ model,
                int n1, int nm, float thr, int* __restrict__ counters /* [b][3]: inliers, fg, ticket */,
                float* __restrict__ nn_out, float* __restrict__ score) {
   __shared__ __align__(16) float sm_model[4 * FS_TILE];
+  __shared__ float s_best[FS_PARTS][FS_QPB];
   __shared__ int s_cnt[2];
   const int b = blockIdx.y;
-  const int part = threadIdx.x & (FS_PARTS - 1);
-  const int ia = blockIdx.x * FS_QPB + 2 * (threadIdx.x / FS_PARTS), ib = ia + 1;   // this thread's two query points
+  const int part = threadIdx.x >> 5, pair = threadIdx.x & 31;
+  const int ia = blockIdx.x * FS_QPB + 2 * pair, ib = ia + 1;   // this thread's two query points
   const float* R = Rm + (size_t)b * 9;
   const float* t = tv + (size_t)b * 3;
   if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
@@ -140,44 +143,37 @@ k_fine_inliers(const float* __restrict__ pts1, const float* __restrict__ model,
   const float* mb = model + (size_t)b * nm * 3;
   for (int j0 = 0; j0 < nm; j0 += FS_TILE) {
     const int tn = min(FS_TILE, nm - j0);
-    const int tn_pad = (tn + 4 * FS_PARTS - 1) & ~(4 * FS_PARTS - 1);   // every part scans a multiple of 4 points
+    const int tn_pad = (tn + 4 * FS_PARTS - 1) & ~(4 * FS_PARTS - 1);   // every slice scans a multiple of 4 points
     float* mx = sm_model; float* my = mx + FS_TILE; float* mz = my + FS_TILE; float* mn = mz + FS_TILE;
     __syncthreads();
     stage_model_soa(mb + (size_t)j0 * 3, tn, tn_pad, mx, my, mz, mn);
     __syncthreads();
-    // the four threads of a query pair take interleaved groups of 4 points: their LDS.128 hit distinct banks
     float ba, bb;
     nn_min_expansion2(mx, my, mz, mn, tn_pad, xa, xb, ba, bb, 4 * part, 4 * FS_PARTS);
     best_a = fminf(best_a, ba);
     best_b = fminf(best_b, bb);
   }
+  s_best[part][2 * pair] = best_a;
+  s_best[part][2 * pair + 1] = best_b;
+  __syncthreads();
+  if (threadIdx.x < FS_QPB) {   // warps 0 and 1: one query point per thread
+    const int i = blockIdx.x * FS_QPB + threadIdx.x;
+    float best = s_best[0][threadIdx.x];
 #pragma unroll
-  for (int o = 1; o < FS_PARTS; o <<= 1) {
-    best_a = fminf(best_a, __shfl_xor_sync(kFull, best_a, o));
-    best_b = fminf(best_b, __shfl_xor_sync(kFull, best_b, o));
-  }
-  int inl = 0, fg = 0;
-  if (part == 0) {
-    if (oka) {
-      const float dist = sqrtf(fmaxf(best_a, 0.f));
-      if (nn_out) nn_out[(size_t)b * n1 + ia] = dist;
-      const int f = w1[(size_t)b * n1 + ia] > 0.f ? 1 : 0;
-      fg += f;
-      inl += (dist < thr && f) ? 1 : 0;
+    for (int p = 1; p < FS_PARTS; ++p) best = fminf(best, s_best[p][threadIdx.x]);
+    int inl = 0, fg = 0;
+    if (i < n1) {
+      const float dist = sqrtf(fmaxf(best, 0.f));
+      if (nn_out) nn_out[(size_t)b * n1 + i] = dist;
+      fg = w1[(size_t)b * n1 + i] > 0.f ? 1 : 0;
+      inl = (dist < thr && fg) ? 1 : 0;
     }
-    if (okb) {
-      const float dist = sqrtf(fmaxf(best_b, 0.f));
-      if (nn_out) nn_out[(size_t)b * n1 + ib] = dist;
-      const int f = w1[(size_t)b * n1 + ib] > 0.f ? 1 : 0;
-      fg += f;
-      inl += (dist < thr && f) ? 1 : 0;
+    inl = __reduce_add_sync(kFull, inl);
+    fg = __reduce_add_sync(kFull, fg);
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(&s_cnt[0], inl);
+      atomicAdd(&s_cnt[1], fg);
     }
-  }
-  inl = __reduce_add_sync(kFull, inl);
-  fg = __reduce_add_sync(kFull, fg);
-  if ((threadIdx.x & 31) == 0) {
-    atomicAdd(&s_cnt[0], inl);
-    atomicAdd(&s_cnt[1], fg);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
