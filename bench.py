@@ -787,8 +787,9 @@ def main():
         "fine_similarity": ("k_similarity_tc2<stats, fp16> (tcgen05.mma.cta_group::2 kind::f16, 3xFP16 split, CTA pairs on "
                             "256x256 tiles, background row/column peeled, exponent sums of the assignment in the epilogue) "
                             "+ k_normalize_split x2", "tensor-f16", 2.0 * n1 * n1 * cfg.feat_dim * B),
-        "fine_pose": ("k_fine_labels + k_fine_rows (2 reads of the 2049^2 fp32 logits; pass 1 = exponent sums, fused "
-                      "into the similarity GEMM's epilogue) + Kabsch + inliers", "hbm", 2.0 * n1 * n1 * 4 * B),
+        "fine_pose": ("k_fine_labels_tma + k_fine_rows_tma (2 reads of the 2049^2 fp32 logits through a TMA box ring; "
+                      "pass 1 = exponent sums, fused into the similarity GEMM's epilogue) + merges + Kabsch + inliers",
+                      "hbm", 2.0 * n1 * n1 * 4 * B),
         "fps_template+gather": ("fps_kernel<512,10> (5000->2048; serial chain, one SM per instance)", "fp32",
                                 fps_ops(cfg.n_template, cfg.n_fine)),
         "fps_sparse_ref+gather": ("fps_kernel<512,4> (2048->196)", "fp32", fps_ops(cfg.n_fine, cfg.n_coarse)),
