@@ -244,3 +244,24 @@ def test_ball_query_group_randomised_shapes(cuda):
             exp = O.ball_query(q, xyz, r, ns)
             assert np.array_equal(idx.cpu().numpy(), exp), (case, n, m, r, ns)
             assert np.array_equal(g.cpu().numpy(), O.group_points(xyz_cf, exp)), (case, n, m, r, ns)
+
+
+@pytest.mark.gpu
+def test_fps_thread_configurations_bit_identical(tmp_path):
+    """UPK_FPS_CFG=5 / 6 run the FPS on 8 / 4 warps per instance with the general tie key (bit reversal of k mod BS
+    evaluated for the winning point instead of per thread): the indices must equal the default configuration's bit for
+    bit, including on quantised clouds with many exact distance ties (sampling_gpu.cu:64-70 tournament order)."""
+    import subprocess
+    import sys as _sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    child = os.path.join(root, "scripts", "dev", "fps_cfg_sweep.py")
+    outs = {}
+    for cfg in ("0", "5", "6"):
+        p = str(tmp_path / ("fps_%s.pt" % cfg))
+        r = subprocess.run([_sys.executable, child, "--child", p], env=dict(os.environ, UPK_FPS_CFG=cfg),
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-3000:]
+        outs[cfg] = torch.load(p)
+    for cfg in ("5", "6"):
+        for k, v in outs["0"].items():
+            assert torch.equal(v, outs[cfg][k]), (cfg, k)

@@ -550,3 +550,32 @@ def test_coarse_cdf_bit_exact_vs_torch(cuda, B, n, c):
         nbits = int((m["cdf"].view(torch.int32) != o["cdf"].view(torch.int32)).sum())
         assert nbits == 0, (nbits, float((m["cdf"] - o["cdf"]).abs().max()))
         assert torch.equal(m["idx1"].reshape(B, -1).long(), o["idx1"]) and torch.equal(m["idx2"].reshape(B, -1).long(), o["idx2"])
+
+
+@pytest.mark.gpu
+def test_fine_tma_passes_bit_identical_to_streaming(tmp_path):
+    """The TMA-fed persistent passes (k_fine_labels_tma / k_fine_rows_tma, default for the padded layout on whole
+    128 x 256 tiles) against the register-streaming kernels they replace (UPK_FINE_TMA=0): every intermediate of the
+    fine solve (masks, soft correspondences, row sums, NN distances) and R / t / score must be bit-identical, with the
+    GEMM's fused exponent sums and without, on the fine shape and on other whole-tile shapes; a ragged shape takes the
+    streaming kernels in both modes (sanity: still identical).  Reference: compute_fine_Rt_overlap, model_utils.py:526-566."""
+    import subprocess
+    import sys as _sys
+    child = os.path.join(os.path.dirname(os.path.abspath(__file__)), "fine_tma_child.py")
+    spec = "2,2048,2048;3,1024,768;2,640,1024;2,1000,900"
+    outs = {}
+    for mode in ("0", "1"):
+        p = str(tmp_path / ("fine_%s.pt" % mode))
+        r = subprocess.run([_sys.executable, child, p, spec], env=dict(os.environ, UPK_FINE_TMA=mode),
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-3000:]
+        outs[mode] = torch.load(p)
+    assert outs["0"].keys() == outs["1"].keys() and len(outs["0"]) > 40
+    for item in spec.split(";"):
+        assert int(outs["1"]["%s/pitched" % item]) == 1      # the padded layout the TMA passes need
+    for k in outs["0"]:
+        assert torch.equal(outs["0"][k], outs["1"][k]), k
+    # the solve did something: on the planted matches the foreground masks are neither empty nor full
+    w1 = outs["1"]["2,2048,2048/fused/w1"]
+    assert 0.02 < float(w1.mean()) < 0.98, float(w1.mean())
+    assert bool(torch.isfinite(outs["1"]["2,2048,2048/fused/R"]).all())

@@ -41,11 +41,28 @@ __device__ __forceinline__ unsigned bitrev_n(unsigned v, int nbits) {
   return nbits == 0 ? 0u : (__brev(v) >> (32 - nbits));
 }
 
+// Offset of a thread's p-th point from its thread index.  Default: k = tid + p * THREADS; with THREADS a multiple of the
+// reference block size BS every point of a thread has the same k mod BS, so ascending p is ascending tie key and the
+// strict ">" of the scan keeps the reference's winner among equal distances.  GENKEY (THREADS = BS / S, BS = 512): a thread
+// owns S residues r_s = tid + s * THREADS; the key orders them by bitrev(r_s), i.e. by the bit-reversed s, so the points
+// are laid out residue by residue in THAT order (J = PPT / S blocks each) and ascending p is again ascending key.
+template <int THREADS, int PPT, bool GENKEY>
+__host__ __device__ constexpr int fps_koff(int p) {
+  if (!GENKEY) return p * THREADS;
+  constexpr int S = GENKEY ? 512 / THREADS : 1, J = PPT / S;
+  const int si = p / J, j = p % J;
+  int s = 0;
+  for (int bit = 1, rb = S >> 1; bit < S; bit <<= 1, rb >>= 1)
+    if (si & bit) s |= rb;
+  return s * THREADS + j * 512;
+}
+
 template <int THREADS, int PPT, bool X2 = false, bool GENKEY = false>
 __global__ void __launch_bounds__(THREADS, 1)
 fps_kernel(const float* __restrict__ xyz, int n, int m, int bs_log2,
            int* __restrict__ idx_out) {
   static_assert(!X2 || PPT % 2 == 0, "packed variant needs an even number of points per thread");
+  static_assert(!GENKEY || (512 % THREADS == 0 && PPT % (512 / THREADS) == 0), "GENKEY: BS = 512 split over S residues per thread");
   extern __shared__ float smem_f[];
   float* sx = smem_f;
   float* sy = sx + n;
@@ -71,7 +88,7 @@ fps_kernel(const float* __restrict__ xyz, int n, int m, int bs_log2,
   float px[PPT], py[PPT], pz[PPT], td[PPT];
 #pragma unroll
   for (int p = 0; p < PPT; ++p) {
-    int k = tid + p * THREADS;
+    int k = tid + fps_koff<THREADS, PPT, GENKEY>(p);
     bool ok = k < n;
     px[p] = ok ? sx[k] : 0.f;
     py[p] = ok ? sy[k] : 0.f;
@@ -103,10 +120,10 @@ fps_kernel(const float* __restrict__ xyz, int n, int m, int bs_log2,
         td[p] = d2a;
         td[p + 1] = d2b;
         bool ga = d2a > best;
-        bestp = ga ? p : bestp;
+        bestp = ga ? fps_koff<THREADS, PPT, GENKEY>(p) : bestp;
         best = ga ? d2a : best;
         bool gb = d2b > best;
-        bestp = gb ? p + 1 : bestp;
+        bestp = gb ? fps_koff<THREADS, PPT, GENKEY>(p + 1) : bestp;
         best = gb ? d2b : best;
       }
     } else {
@@ -116,7 +133,7 @@ fps_kernel(const float* __restrict__ xyz, int n, int m, int bs_log2,
         float d2 = fminf(d, td[p]);
         td[p] = d2;
         bool g = d2 > best;
-        bestp = g ? p : bestp;
+        bestp = g ? fps_koff<THREADS, PPT, GENKEY>(p) : bestp;
         best = g ? d2 : best;
       }
     }
@@ -125,7 +142,7 @@ fps_kernel(const float* __restrict__ xyz, int n, int m, int bs_log2,
     const int hi = __float_as_int(best);
     // tie key of point k: (bitrev(k mod BS), k div BS).  With THREADS a multiple of BS, k mod BS == tid mod BS for all of
     // a thread's points; the configurations with fewer warps than BS / 32 (GENKEY) evaluate it for the winning point
-    const unsigned kb = (unsigned)(tid + bestp * THREADS);
+    const unsigned kb = (unsigned)(tid + bestp);   // bestp = offset of the thread's winning point (fps_koff)
     const unsigned lo = (GENKEY ? bitrev_n(kb & bs_mask, bs_log2) << 20 : my_rev) | (kb >> bs_log2);
     const int whi = __reduce_max_sync(kFull, hi);
     const unsigned wlo = __reduce_min_sync(kFull, hi == whi ? lo : 0xffffffffu);
