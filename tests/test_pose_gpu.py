@@ -579,3 +579,72 @@ def test_fine_tma_passes_bit_identical_to_streaming(tmp_path):
     w1 = outs["1"]["2,2048,2048/fused/w1"]
     assert 0.02 < float(w1.mean()) < 0.98, float(w1.mean())
     assert bool(torch.isfinite(outs["1"]["2,2048,2048/fused/R"]).all())
+
+
+def _topk_reference(vals, K):
+    """upk_topk_smallest's contract: the K smallest by float bit pattern (values >= 0; NaN and the 0xFFFFFFFF padding key
+    sort last), ties at the K-th value to the lower index, result in ascending index (torch.topk(largest=False), :476,
+    leaves the tie order open)."""
+    keys = vals.view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    n = vals.shape[1]
+    order = torch.argsort(keys * n + torch.arange(n, device=vals.device), dim=1)[:, :K]
+    return torch.sort(order, dim=1)[0].to(torch.int32)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("H,K", [(37, 1), (37, 37), (1000, 300), (5000, 300), (8192, 300), (8193, 300), (20000, 7),
+                                 (100000, 300)])
+def test_topk_smallest_abi_ties_and_specials(cuda, H, K):
+    """Both code paths of k_topk_smallest (row kept in registers up to 8192 values, streamed above) on tie-heavy rows:
+    quantised residuals with many duplicates at the K-th value, exact zeros, +inf, NaN and the all-ones padding key."""
+    import ctypes
+    from unopose_b200 import _lib as L
+    lib = L.load()
+    g = torch.Generator(device="cpu").manual_seed(H * 31 + K)
+    B = 3
+    v = torch.rand(B, H, generator=g)
+    v[0] = (v[0] * 8).floor() / 8                      # 8 distinct values: the K-th value is shared by hundreds of entries
+    v[1, ::7] = 0.0
+    v[1, 3::11] = float("inf")
+    if H > 20:
+        v[2, 5] = float("nan")
+        v[2, 9:13] = torch.tensor([-1], dtype=torch.int32).view(torch.float32)   # 0xFFFFFFFF padding key
+    v = v.to(cuda)
+    top = torch.empty((B, K), dtype=torch.int32, device=cuda)
+    L.check(lib.upk_topk_smallest(L.ptr(v), B, H, K, L.ptr(top), L.stream_ptr(v)), "topk")
+    torch.cuda.synchronize()
+    assert torch.equal(top, _topk_reference(v, K))
+    # pitched form: a slice of a wider pool
+    if H >= 1000:
+        h0, hs = 128, H - 300
+        ks = min(K, hs)
+        top2 = torch.empty((B, ks), dtype=torch.int32, device=cuda)
+        L.check(lib.upk_topk_smallest_ld(v.data_ptr() + 4 * h0, B, hs, H, ks, L.ptr(top2), L.stream_ptr(v)), "topk_ld")
+        torch.cuda.synchronize()
+        assert torch.equal(top2, _topk_reference(v[:, h0:h0 + hs].contiguous(), ks))
+
+
+@pytest.mark.gpu
+def test_fused_selection_equals_separate_select(cuda):
+    """upk_coarse_pose lets the LAST scoring CTA of an instance run the arg-max (ticket counter zeroed by the top-K
+    launch); the stage-wise entry points (upk_score_hypotheses + upk_select_best) are the separate form: same R, t, score
+    and pool index, also when called repeatedly on the same workspace."""
+    from unopose_b200 import _lib as L
+    from unopose_b200 import model_utils as MU
+    lib = L.load()
+    B, n, H, K = 5, 196, 3000, 301      # odd K: the last scoring CTA of an instance holds one hypothesis
+    d = {k: torch.from_numpy(v).to(cuda) for k, v in matching_batch(11, B, n, 64).items() if k in ("pts1", "pts2", "f1", "f2", "score")}
+    atten = PO.feature_similarity(d["f1"], d["f2"], "cosine", 0.1, True)
+    u = torch.rand(B, 3 * H, device=cuda)
+    for _ in range(3):
+        R, t, s, m = MU._coarse(atten, d["score"], d["pts1"], d["pts2"], None, H, K, u=u, return_debug=True)
+        scores = torch.empty((B, K), device=cuda)
+        L.check(lib.upk_score_hypotheses(L.ptr(d["pts1"]), L.ptr(d["pts2"]), L.ptr(m["w1"]), L.ptr(m["Rs"]), L.ptr(m["ts"]),
+                                         L.ptr(m["top"]), B, n, n, H, K, 0, K, L.ptr(scores), L.stream_ptr(u)), "score")
+        R2 = torch.empty((B, 3, 3), device=cuda); t2 = torch.empty((B, 3), device=cuda)
+        s2 = torch.empty((B,), device=cuda); pool2 = torch.empty((B,), dtype=torch.int32, device=cuda)
+        L.check(lib.upk_select_best(L.ptr(scores), L.ptr(m["top"]), L.ptr(m["Rs"]), L.ptr(m["ts"]), B, H, K, L.ptr(R2),
+                                    L.ptr(t2), L.ptr(s2), L.ptr(pool2), L.stream_ptr(u)), "select")
+        torch.cuda.synchronize()
+        assert torch.equal(scores, m["scores"])
+        assert torch.equal(R, R2) and torch.equal(t, t2) and torch.equal(s, s2) and torch.equal(m["pool"].to(torch.int32), pool2)
