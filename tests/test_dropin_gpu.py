@@ -311,3 +311,38 @@ def test_full_forward_reference_stock_vs_patched_vs_product(cuda, ref):
         assert int(same_coarse.sum()) * 2 > B, same_coarse.tolist()
         assert ang[same_coarse].max() <= ROT_TOL_DEG and terr[same_coarse].max() <= T_TOL_REL
         assert ds[same_coarse].max() <= 2.5 / 2048
+
+
+def test_graphed_matching_forward_equals_eager(cuda):
+    """`unopose_b200.model.GraphedMatching`: `UNOPose.matching_forward` (oneref_grf_predator_pose_estimation_model.py:28-76)
+    captured into one CUDA graph replays to the same end_points as the eager call under the same generator seed — the
+    coarse stage is a real arg-max over 6000 hypotheses, so the `torch.rand` draw inside the graph must be the eager one."""
+    from baseline import refgpu
+    from unopose_b200.model import GraphedMatching, UNOPose
+    from util_state import keyed_state_dict
+
+    B = 3
+    cfg = refgpu.real_model_cfg()
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        model = UNOPose(cfg).eval()
+        model.load_state_dict(keyed_state_dict(model.state_dict(), 12))
+        model = model.to(cuda)
+        inp = {k: v for k, v in _forward_inputs(cuda, B, 78).items() if k not in ("R", "t")}
+        with torch.no_grad():
+            feats = model.feature_extraction(dict(inp))
+            torch.manual_seed(9)
+            eager = model.matching_forward(*feats, dict(inp))
+            eager = {k: eager[k].clone() for k in ("init_R", "init_t", "init_pose_score", "pred_R", "pred_t", "pred_pose_score")}
+        gm = GraphedMatching(model, feats, dict(inp))
+        for _ in range(2):      # replays are repeatable
+            torch.manual_seed(9)
+            out = gm.replay()
+            torch.cuda.synchronize()
+            for k, v in eager.items():
+                assert torch.equal(out[k], v), k
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    eye = torch.eye(3, device=cuda)
+    assert min(float((eager["init_R"][b] - eye).abs().max()) for b in range(B)) > 1e-3
