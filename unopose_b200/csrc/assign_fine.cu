@@ -1001,7 +1001,7 @@ k_fine_rows_tma(const __grid_constant__ CUtensorMap map, int nb, int R, int C, i
 static bool fine_tma_ok(const float* atten, int ld, int R, int C) {
   static int enabled = -1;
   if (enabled < 0) { const char* e = getenv("UPK_FINE_TMA"); enabled = e ? atoi(e) : 1; }
-  return enabled && R > 1 && C > 1 && (R - 1) % F2_RT == 0 && (C - 1) % F2_TC == 0 && ld % 4 == 0 &&
+  return enabled && tc_tma_available() && R > 1 && C > 1 && (R - 1) % F2_RT == 0 && (C - 1) % F2_TC == 0 && ld % 4 == 0 &&
          ((reinterpret_cast<uintptr_t>(atten + ld + 1)) & 15) == 0;
 }
 

@@ -786,6 +786,9 @@ int tc_make_map_f16(void* map, const void* base, int batch, int rows, int K, int
   return make_map_f16((CUtensorMap*)map, base, batch, rows, K, box_rows);
 }
 
+// whether the driver hands out cuTensorMapEncodeTiled (callers keep their non-TMA kernels otherwise)
+bool tc_tma_available() { return get_encode() != nullptr; }
+
 // Plain (unswizzled) fp32 boxes of box_cols x box_rows out of a pitched (batch, rows, cols) matrix: the streaming
 // passes of assign_fine.cu read `atten` through it.  `base` = element (0, 0) of the block the boxes tile, 16-byte aligned.
 int tc_make_map_plane(void* map, const float* base, int batch, int rows, int cols, int ld, size_t batch_stride,
