@@ -81,3 +81,25 @@ def test_rpe_scores_kernel(cuda, fp32_matmul, B, N, C):
     e_ours, e_torch = float((got.double() - ref64).abs().max()), float((ref32.double() - ref64).abs().max())
     print("rpe scores: max err ours %.2e, torch fp32 %.2e" % (e_ours, e_torch))
     assert got.shape == (B, 4, N, N) and e_ours <= 2 * e_torch + 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows", [6304, 65536])
+def test_linear_multi_bit_identical_to_single_layers(cuda, rows):
+    """`linear_multi` (q / k / v projections of an attention block as ONE operand split + ONE GEMM over the
+    concatenated weights, transformer.py:116-118 / :371-373) returns exactly what `linear(layer, x)` returns per layer;
+    the cached concatenation follows in-place parameter updates."""
+    import torch.nn as nn
+    from unopose_b200.modules.linear import linear, linear_multi
+    torch.manual_seed(3)
+    layers = [nn.Linear(256, 256).to(cuda) for _ in range(3)]
+    x = torch.randn(rows // 197 if rows == 6304 else 32, 197 if rows == 6304 else 2048, 256, device=cuda)
+    with torch.no_grad():
+        for n in (3, 2):
+            outs = linear_multi(layers[:n], x)
+            for l, o in zip(layers[:n], outs):
+                assert o.shape == x.shape[:-1] + (256,)
+                assert torch.equal(o, linear(l, x))
+        layers[1].weight.mul_(0.5)                       # bumps the version counter: the cache must be rebuilt
+        outs = linear_multi(layers, x)
+        assert torch.equal(outs[1], linear(layers[1], x)) and torch.equal(outs[2], linear(layers[2], x))

@@ -11,7 +11,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ..model_utils import _gather_rows, pairwise_distance
-from .linear import linear
+from .linear import linear, linear_multi
 
 
 def _heads(x, h):
@@ -76,7 +76,12 @@ class _DotAttention(nn.Module):
 
     def forward(self, x_q, x_kv, embed_qk=None, key_masks=None):
         h = self.num_heads
-        q, k, v = _heads(linear(self.proj_q, x_q), h), _heads(linear(self.proj_k, x_kv), h), _heads(linear(self.proj_v, x_kv), h)
+        if x_q is x_kv:     # self-attention: one operand split and one GEMM for the three projections
+            q, k, v = linear_multi((self.proj_q, self.proj_k, self.proj_v), x_q)
+        else:
+            q = linear(self.proj_q, x_q)
+            k, v = linear_multi((self.proj_k, self.proj_v), x_kv)
+        q, k, v = _heads(q, h), _heads(k, h), _heads(v, h)
         scores = q @ k.transpose(-1, -2)
         if embed_qk is not None:
             # q.(W_p e + b_p) = (W_p^T q).e + q.b_p: the reference projects the (B,N,M,C) embedding with W_p
@@ -180,9 +185,10 @@ class _FocusedLinearAttention(nn.Module):
     def forward(self, x_q, x_kv):
         h = self.num_heads
         scale = F.softplus(self.scale)
+        kp, vp = linear_multi((self.proj_k, self.proj_v), x_kv)
         q = _heads(self._focus(linear(self.proj_q, x_q), scale), h)   # (B,h,i,c)
-        k = _heads(self._focus(linear(self.proj_k, x_kv), scale), h)  # (B,h,j,c)
-        v = _heads(linear(self.proj_v, x_kv), h)              # (B,h,j,d)
+        k = _heads(self._focus(kp, scale), h)                         # (B,h,j,c)
+        v = _heads(vp, h)                                             # (B,h,j,d)
         z = 1.0 / (torch.einsum("bhic,bhc->bhi", q, k.sum(dim=2)) + 1e-6)
         i, j, c, d = q.shape[2], k.shape[2], k.shape[3], v.shape[3]
         if i * j * (c + d) > c * d * (i + j):
