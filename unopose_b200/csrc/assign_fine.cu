@@ -706,17 +706,24 @@ __device__ __forceinline__ FtTile ft_tile(int T, int nb, int nrt, int nstrip, bo
   return t;
 }
 
+// keep_lo: instances b < keep_lo are what the NEXT pass reads first (it walks the instances upwards): their lines get
+// evict_last, everything else evict_first (read once by this kernel).  keep_lo < 0: no hints.
 template <int STAGES, class Smem>
 __device__ __forceinline__ void ft_producer(const CUtensorMap* map, Smem& sm, int ntile, int nb, int nrt, int nstrip,
-                                            bool flip) {
+                                            bool flip, int keep_lo) {
   int s = 0;
   uint32_t ph = 0;
+  const uint64_t pol_last = l2_policy_evict_last(), pol_first = l2_policy_evict_first();
   for (int T = blockIdx.x; T < ntile; T += gridDim.x) {
     const FtTile t = ft_tile(T, nb, nrt, nstrip, flip);
     for (int q = 0; q < FT_SPT; ++q) {
       mbar_wait(&sm.empty[s], ph ^ 1);
       mbar_expect_tx(&sm.full[s], FT_STAGE_FLOATS * sizeof(float));
-      tma_load_3d(map, &sm.full[s], sm.buf[s], t.cs * F2_TC, t.rt * F2_RT + q * FT_ROWS, t.b);
+      if (keep_lo >= 0)
+        tma_load_3d_hint(map, &sm.full[s], sm.buf[s], t.cs * F2_TC, t.rt * F2_RT + q * FT_ROWS, t.b,
+                         t.b < keep_lo ? pol_last : pol_first);
+      else
+        tma_load_3d(map, &sm.full[s], sm.buf[s], t.cs * F2_TC, t.rt * F2_RT + q * FT_ROWS, t.b);
       if (++s == STAGES) { s = 0; ph ^= 1; }
     }
   }
@@ -763,7 +770,7 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
 k_fine_labels_tma(const __grid_constant__ CUtensorMap map, const float* __restrict__ atten, int nb, int R, int C, int ld,
                   int nstrip, int nrt, const float* __restrict__ rml, const float* __restrict__ rmul,
                   const float* __restrict__ cml, const float* __restrict__ cmul, float* __restrict__ rowpm,
-                  float* __restrict__ colpm, float* __restrict__ ai0, float* __restrict__ a0j, int flip) {
+                  float* __restrict__ colpm, float* __restrict__ ai0, float* __restrict__ a0j, int flip, int l2_keep) {
   extern __shared__ unsigned char ft_raw[];
   using Smem = FtSmem<FT_LABEL_STAGES, 2, true>;
   Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(ft_raw) + 127) & ~(uintptr_t)127);
@@ -771,7 +778,7 @@ k_fine_labels_tma(const __grid_constant__ CUtensorMap map, const float* __restri
   const int ntile = nb * nrt * nstrip;
   ft_init<FT_LABEL_STAGES>(sm);
   if (warp == F2_WARPS) {
-    if (lane == 0) ft_producer<FT_LABEL_STAGES>(&map, sm, ntile, nb, nrt, nstrip, flip != 0);
+    if (lane == 0) ft_producer<FT_LABEL_STAGES>(&map, sm, ntile, nb, nrt, nstrip, flip != 0, l2_keep > 0 ? l2_keep : -1);
     return;
   }
   if (warp == F2_WARPS + 1) {
@@ -881,7 +888,7 @@ __global__ void __launch_bounds__(FT_THREADS, 2)
 k_fine_rows_tma(const __grid_constant__ CUtensorMap map, int nb, int R, int C, int nstrip, int nrt,
                 const float* __restrict__ rml, const float* __restrict__ rmul, const float* __restrict__ cml,
                 const float* __restrict__ cmul, const float* __restrict__ w2, const float* __restrict__ pts2,
-                float4* __restrict__ rowpart4) {
+                float4* __restrict__ rowpart4, int l2_keep) {
   extern __shared__ unsigned char ft_raw[];
   using Smem = FtSmem<FT_ROWS_STAGES, 5, false>;
   Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(ft_raw) + 127) & ~(uintptr_t)127);
@@ -890,7 +897,7 @@ k_fine_rows_tma(const __grid_constant__ CUtensorMap map, int nb, int R, int C, i
   const int N1 = R - 1;
   ft_init<FT_ROWS_STAGES>(sm);
   if (warp == F2_WARPS) {
-    if (lane == 0) ft_producer<FT_ROWS_STAGES>(&map, sm, ntile, nb, nrt, nstrip, false);
+    if (lane == 0) ft_producer<FT_ROWS_STAGES>(&map, sm, ntile, nb, nrt, nstrip, false, l2_keep > 0 ? 0 : -1);   // read once
     return;
   }
   if (warp == F2_WARPS + 1) {
@@ -1023,7 +1030,8 @@ static int launch_fine_labels_tma(const float* atten, int ld, int b, int R, int 
   const size_t smem = sizeof(FtSmem<FT_LABEL_STAGES, 2, true>) + 128;
   UPK_CUDA_TRY(cudaFuncSetAttribute(k_fine_labels_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_fine_labels_tma<<<fine_tma_grid(b * f.nrt * f.nstrip), FT_THREADS, smem, st>>>(
-      map, atten, b, R, C, ld, f.nstrip, f.nrt, ws.rmax, ws.rsum, ws.cmax, ws.csum, ws.rowpm, ws.colpm, ws.ai0, ws.a0j, flip);
+      map, atten, b, R, C, ld, f.nstrip, f.nrt, ws.rmax, ws.rsum, ws.cmax, ws.csum, ws.rowpm, ws.colpm, ws.ai0, ws.a0j, flip,
+      flip ? fine_l2_keep(b, R, C) : 0);   // only behind the statistics-fused GEMM (descending walk)
   UPK_RETURN_LAST_ERROR();
 }
 
@@ -1098,7 +1106,7 @@ int run_fine_rows2(const float* atten, int ld, int b, const AssignGeom& g, const
     const size_t smem = sizeof(FtSmem<FT_ROWS_STAGES, 5, false>) + 128;
     UPK_CUDA_TRY(cudaFuncSetAttribute(k_fine_rows_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_fine_rows_tma<<<fine_tma_grid(b * f.nrt * f.nstrip), FT_THREADS, smem, st>>>(
-        map, b, g.R, g.C, f.nstrip, f.nrt, ws.rmax, ws.rsum, ws.cmax, ws.csum, w2, pts2, rowpart4);
+        map, b, g.R, g.C, f.nstrip, f.nrt, ws.rmax, ws.rsum, ws.cmax, ws.csum, w2, pts2, rowpart4, fine_l2_keep(b, g.R, g.C));
   } else if (fine_vec_ok(atten, ld))
     k_fine_rows<true><<<grid, F2_THREADS, 0, st>>>(atten, g.R, g.C, ld, f.nstrip, ws.rmax, ws.rsum, ws.cmax, ws.csum, w2, pts2,
                                                    rowpart4);

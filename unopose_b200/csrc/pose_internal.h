@@ -106,6 +106,7 @@ int run_similarity_tc(const float* f1, const float* f2, int b, int n, int m, int
 int tc_make_map(void* map, const float* base, int batch, int rows, int K, int box_rows);
 // same for fp16 operands (32 halves per 64-byte box row); experimental 3xFP16 paths
 int tc_make_map_f16(void* map, const void* base, int batch, int rows, int K, int box_rows);
+int fine_l2_keep(int b, int n, int m);   // instances of a fine-shape atten kept in L2 between the fine-stage kernels (0 = no hints)
 bool tc_tma_available();   // the driver entry point for tensor-map encoding exists
 // unswizzled fp32 boxes (box_cols x box_rows) of a pitched (batch, rows, cols) matrix; `base` 16-byte aligned, `ld` and
 // `batch_stride` in floats (ld % 4 == 0)
