@@ -342,7 +342,9 @@ __device__ __forceinline__ void select_best(const float* __restrict__ scores, co
 constexpr int SC_THREADS = 224;  // 7 warps: one query point per thread at n1 = 196
 
 // SC_HPC kept hypotheses per CTA: the staged model and every LDS.128 of the scan serve both (four per CTA, measured in
-// round 2 with a generic Q-query scan: 80 registers with spills at 3 CTAs / SM, coarse solve 134 -> 138 us)
+// round 2 with a generic Q-query scan: 80 registers with spills at 3 CTAs / SM, coarse solve 134 -> 138 us; a persistent
+// grid pulling (instance, pair) items from a device-side queue instead of 4.05 waves of CTAs: 132 -> 143 us — the
+// per-item barriers and the lost overlap of one CTA's prologue with its neighbours' scans cost more than the fifth wave)
 constexpr int SC_HPC = 2;
 
 // PEER: the scores go into EVERY rank's score table (peer stores) and the last CTA publishes the channel (peer.cuh)
