@@ -179,3 +179,28 @@ def test_real_config_modules_match_reference_features():
     assert abs(float(geo1.mean()) - float(g["geo1_mean"])) < 1e-6
     assert torch.allclose(g1, torch.from_numpy(g["coarse_g1"]), atol=2e-5, rtol=1e-4)
     assert torch.allclose(g2, torch.from_numpy(g["coarse_g2"]), atol=2e-5, rtol=1e-4)
+
+
+def test_linear_multi_cpu_fallback_and_weight_cache():
+    """`linear_multi` (q / k / v projections as one GEMM on CUDA) falls back to one `F.linear` per layer on CPU, and its
+    cached weight concatenation follows in-place parameter updates and reloaded state dicts."""
+    import torch.nn as nn
+    from unopose_b200.modules.linear import _cat_params, linear_multi
+
+    torch.manual_seed(0)
+    layers = [nn.Linear(32, 16), nn.Linear(32, 16), nn.Linear(32, 48)]
+    x = torch.randn(2, 5, 32)
+    with torch.no_grad():
+        outs = linear_multi(layers, x)
+        for l, o in zip(layers, outs):
+            assert torch.equal(o, l(x))
+        w, b = _cat_params(layers)
+        assert w.shape == (80, 32) and torch.equal(w[16:32], layers[1].weight) and torch.equal(b[32:], layers[2].bias)
+        w_again, _ = _cat_params(layers)
+        assert w_again is w                                      # cached
+        layers[1].weight.mul_(2.0)                               # in-place update: version counter moves
+        w2, _ = _cat_params(layers)
+        assert w2 is not w and torch.equal(w2[16:32], layers[1].weight)
+        layers[2].load_state_dict({"weight": torch.ones(48, 32), "bias": torch.zeros(48)})
+        w3, b3 = _cat_params(layers)
+        assert torch.equal(w3[32:], torch.ones(48, 32)) and torch.equal(b3[32:], torch.zeros(48))
