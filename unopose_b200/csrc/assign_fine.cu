@@ -682,7 +682,7 @@ k_fine_rows(const float* __restrict__ atten, int R, int C, int ld, int nstrip, c
 //     VEC loads, so every partial is bit-identical to the kernels above) and hand the slot back as soon as the pair
 //     sits in registers;
 //   * a constants warp runs one tile ahead: it stages the tile's column / row constants in shared memory (double
-//     buffered, mbarrier hand-off) and computes the two border vectors of pass 2 (S[i][0], S[0][j]) itself, so the
+//     buffered, named-barrier hand-off) and computes the two border vectors of pass 2 (S[i][0], S[0][j]) itself, so the
 //     consumers never wait for a global load.
 // Full tiles only ((R - 1) % 128 == 0, (C - 1) % 256 == 0: the UNOPose fine shape); everything else takes the kernels above.
 constexpr int FT_ROWS = 16;                          // rows per stage: one pair per consumer warp
@@ -697,7 +697,7 @@ struct FtSmem {
   alignas(128) float buf[STAGES][FT_STAGE_FLOATS];
   alignas(16) float cst[2][NCOL * F2_TC + 2 * F2_RT];
   float cm[CM ? 2 : 1][CM ? F2_WARPS : 1][CM ? F2_TC : 1];
-  unsigned long long full[STAGES], empty[STAGES], cfull[2], cempty[2];
+  unsigned long long full[STAGES], empty[STAGES];
 };
 
 struct FtTile { int b, rt, cs; };
@@ -751,10 +751,27 @@ template <int STAGES, class Smem>
 __device__ __forceinline__ void ft_init(Smem& sm) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], F2_WARPS); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&sm.cfull[i], 1); mbar_init(&sm.cempty[i], F2_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+}
+
+// Hand-off of the per-tile constants buffers between the constants warp and the eight consumer warps: named barriers
+// (bar.arrive / bar.sync over the 288 participating threads), ids FT_BAR_FULL + buffer and FT_BAR_EMPTY + buffer.  The
+// constants warp arrives on `full` after its stores and syncs on `empty` before it reuses a buffer (from the third tile
+// on); the consumers sync on `full`, read, and arrive on `empty`.  (An mbarrier pair did the same job; named barriers are
+// what compute-sanitizer's racecheck models for thread-issued shared-memory accesses.)
+constexpr int FT_BAR_CM = 1, FT_BAR_FULL = 2, FT_BAR_EMPTY = 4;
+constexpr int FT_CST_THREADS = F2_THREADS + 32;
+template <int BASE>   // immediate barrier ids (a register id makes ptxas reserve all 16 barriers)
+__device__ __forceinline__ void ft_bar_sync(int buf) {
+  if (buf) asm volatile("bar.sync %0, %1;" ::"n"(BASE + 1), "n"(FT_CST_THREADS) : "memory");
+  else asm volatile("bar.sync %0, %1;" ::"n"(BASE), "n"(FT_CST_THREADS) : "memory");
+}
+template <int BASE>
+__device__ __forceinline__ void ft_bar_arrive(int buf) {
+  if (buf) asm volatile("bar.arrive %0, %1;" ::"n"(BASE + 1), "n"(FT_CST_THREADS) : "memory");
+  else asm volatile("bar.arrive %0, %1;" ::"n"(BASE), "n"(FT_CST_THREADS) : "memory");
 }
 
 // a lane's 8 values of column array `a` (the VEC lane -> column mapping) as 4 packed pairs
@@ -797,14 +814,13 @@ k_fine_labels_tma(const __grid_constant__ CUtensorMap map, const float* __restri
       for (int k = 0; k < F2_CPT; ++k) { l[k] = -cml[oc + lane + 32 * k]; m[k] = cmul[oc + lane + 32 * k]; }
 #pragma unroll
       for (int k = 0; k < F2_RT / 32; ++k) { rl[k] = rml[orw + lane + 32 * k]; rm[k] = rmul[orw + lane + 32 * k]; }
-      mbar_wait(&sm.cempty[it & 1], ((it >> 1) & 1) ^ 1);
+      if (it >= 2) ft_bar_sync<FT_BAR_EMPTY>(it & 1);   // the consumers are done with this buffer's previous tile
       float* c = sm.cst[it & 1];
 #pragma unroll
       for (int k = 0; k < F2_CPT; ++k) { c[lane + 32 * k] = l[k]; c[F2_TC + lane + 32 * k] = m[k]; }
 #pragma unroll
       for (int k = 0; k < F2_RT / 32; ++k) { c[2 * F2_TC + lane + 32 * k] = rl[k]; c[2 * F2_TC + F2_RT + lane + 32 * k] = rm[k]; }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.cfull[it & 1]);
+      ft_bar_arrive<FT_BAR_FULL>(it & 1);
       const float* A = atten + (size_t)t.b * R * ld;
       if (t.cs == 0) {   // S[i][0] of the tile's rows (the background column is in no box)
         const float cml0 = cml[(size_t)t.b * C], cmul0 = cmul[(size_t)t.b * C];
@@ -836,14 +852,13 @@ k_fine_labels_tma(const __grid_constant__ CUtensorMap map, const float* __restri
   for (int T = blockIdx.x; T < ntile; T += gridDim.x, ++it) {
     const FtTile t = ft_tile(T, nb, nrt, nstrip, flip != 0);
     ColConst2 kc;
-    mbar_wait(&sm.cfull[it & 1], (it >> 1) & 1);
+    ft_bar_sync<FT_BAR_FULL>(it & 1);
     const float* c = sm.cst[it & 1];
     ft_col8(c, lane, kc.ncml);
     ft_col8(c + F2_TC, lane, kc.cmul);
     const int lrow = ft_lane_lrow(warp, lane);
     const float my_rml = c[2 * F2_TC + lrow], my_rmul = c[2 * F2_TC + F2_RT + lrow];
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&sm.cempty[it & 1]);
+    ft_bar_arrive<FT_BAR_EMPTY>(it & 1);
     float cmx[F2_CPT];
 #pragma unroll
     for (int k = 0; k < F2_CPT; ++k) cmx[k] = -INFINITY;
@@ -878,7 +893,7 @@ k_fine_labels_tma(const __grid_constant__ CUtensorMap map, const float* __restri
     float (*cm)[F2_TC] = sm.cm[it & 1];
 #pragma unroll
     for (int k = 0; k < F2_CPT; ++k) cm[warp][f2_lcol<true>(lane, k)] = cmx[k];
-    asm volatile("bar.sync 1, %0;" ::"n"(F2_THREADS) : "memory");
+    asm volatile("bar.sync %0, %1;" ::"n"(FT_BAR_CM), "n"(F2_THREADS) : "memory");
     {
       const int cc = threadIdx.x;
       float m = -INFINITY;
@@ -923,7 +938,7 @@ k_fine_rows_tma(const __grid_constant__ CUtensorMap map, int nb, int R, int C, i
       for (int k = 0; k < 3 * F2_CPT; ++k) xyz[k] = pts2[ow * 3 + lane + 32 * k];   // 768 consecutive floats, AoS
 #pragma unroll
       for (int k = 0; k < F2_RT / 32; ++k) { rl[k] = rml[orw + lane + 32 * k]; rm[k] = rmul[orw + lane + 32 * k]; }
-      mbar_wait(&sm.cempty[it & 1], ((it >> 1) & 1) ^ 1);
+      if (it >= 2) ft_bar_sync<FT_BAR_EMPTY>(it & 1);   // the consumers are done with this buffer's previous tile
       float* c = sm.cst[it & 1];
 #pragma unroll
       for (int k = 0; k < F2_CPT; ++k) { c[lane + 32 * k] = l[k]; c[F2_TC + lane + 32 * k] = m[k]; }
@@ -934,8 +949,7 @@ k_fine_rows_tma(const __grid_constant__ CUtensorMap map, int nb, int R, int C, i
       }
 #pragma unroll
       for (int k = 0; k < F2_RT / 32; ++k) { c[5 * F2_TC + lane + 32 * k] = rl[k]; c[5 * F2_TC + F2_RT + lane + 32 * k] = rm[k]; }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.cfull[it & 1]);
+      ft_bar_arrive<FT_BAR_FULL>(it & 1);
     }
     return;
   }
@@ -945,7 +959,7 @@ k_fine_rows_tma(const __grid_constant__ CUtensorMap map, int nb, int R, int C, i
     const FtTile t = ft_tile(T, nb, nrt, nstrip, false);
     ColConst2 kc;
     unsigned long long px[F2_CPT / 2], py[F2_CPT / 2], pz[F2_CPT / 2];
-    mbar_wait(&sm.cfull[it & 1], (it >> 1) & 1);
+    ft_bar_sync<FT_BAR_FULL>(it & 1);
     const float* c = sm.cst[it & 1];
     ft_col8(c, lane, kc.ncml);
     ft_col8(c + F2_TC, lane, kc.cmul);
@@ -954,8 +968,7 @@ k_fine_rows_tma(const __grid_constant__ CUtensorMap map, int nb, int R, int C, i
     ft_col8(c + 4 * F2_TC, lane, pz);
     const int lrow = ft_lane_lrow(warp, lane);
     const float my_rml = c[5 * F2_TC + lrow], my_rmul = c[5 * F2_TC + F2_RT + lrow];
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&sm.cempty[it & 1]);
+    ft_bar_arrive<FT_BAR_EMPTY>(it & 1);
 #pragma unroll 1
     for (int st = 0; st < FT_SPT; ++st) {
       RowPair cur;
